@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""Benchmark of the particle-filter hot path (BASELINE.json metric).
+
+A "step" is one whole filter evaluation -- what ``particle_filter$run(pars)`` does on
+the compiled-compare path (R/particle_filter_state.R:138-162): reset the particles to
+the model's initial state, then 100 data intervals of 4 model steps each with compare,
+log-mean-exp, systematic resampling and state gather -- on the SIR model at
+2^20 particles (config C2).  At N > 1 GPUs every rank runs its own filter (independent
+chains, the pmcmc_parallel layout: R/pmcmc_parallel.R:8-20), so scaling is weak and the
+path has no collective; ranks only meet at the timing barrier.
+
+  python bench.py --gpus N --steps K --warmup W          (this engine)
+  python bench.py --impl reference ...                   (CPU arm: the oracle port on
+                                                          all host cores; dust/R absent)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_PARTICLES = 1 << 20
+RATE = 4
+METRIC = "SIR particle-steps/sec (particle_filter$run, 2^20 particles per GPU)"
+UNIT = "particle-steps/s"
+# algorithmic bytes per particle per data interval
+BYTES_K1, BYTES_K2, BYTES_K2B, BYTES_K34 = 152, 16, 0, 84 + 8
+BYTES_INTERVAL = 264
+
+
+def load_data():
+    d = np.loadtxt(os.path.join(ROOT, "tests", "golden", "sir_incidence.csv"), delimiter=",",
+                   skiprows=1)
+    return d[:, 1].astype(np.uint64) * RATE, d[:, 0]
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names)
+                   if any(r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]),
+                "reasons": reasons, "samples": len(self.rows),
+                "power_w_max": max(float(r[2]) for r in self.rows)}
+
+
+def cpu_baseline(n_particles, n_threads, reps=1):
+    """The oracle port (OpenMP over particles, serial scan) on the host cores."""
+    from oracle import oracle as O
+
+    t, x = load_data()
+    m = O.OracleModel(n_particles=n_particles, seed=1, n_threads=n_threads)
+    m.set_data(t, x)
+    best = None
+    ll = None
+    for _ in range(reps + 1):  # first is warm-up
+        m.update_state(pars=O.default_pars(), time=0)
+        t0 = time.perf_counter()
+        ll = m.filter()["log_likelihood"][0]
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return n_particles * int(t[-1]) / best, best, ll
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_sample = 1 << 17
+    t, _ = load_data()
+    from oracle import oracle as O
+
+    O.build()
+    times = []
+    m = O.OracleModel(n_particles=n_sample, seed=1, n_threads=cores)
+    tt, x = load_data()
+    m.set_data(tt, x)
+    for i in range(args.warmup + args.steps):
+        m.update_state(pars=O.default_pars(), time=0)
+        t0 = time.perf_counter()
+        m.filter()
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    value = n_sample * int(t[-1]) * len(times) / total
+    sample = "filter at %d particles (1/%d of the workload's 2^20), all 100 intervals" % (
+        n_sample, N_PARTICLES // n_sample)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic (reference's inst/sir_incidence.csv, 100 days, rate 4)",
+        "config": config_dict(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "mcstate is pure R and its native dependency dust is absent from the image, so "
+                "the reference arm is the C/OpenMP oracle port of dust's filter loop",
+    }
+    print(json.dumps(line))
+
+
+def config_dict(n_gpus):
+    return {"workload": "SIR particle_filter$run, 2^20 particles x 100 data intervals x 4 steps "
+                        "(BASELINE config C2), one independent filter per GPU",
+            "n_particles_per_gpu": N_PARTICLES, "n_intervals": 100, "rate": RATE,
+            "parallelism": "chains x%d" % n_gpus,
+            "l2": "live set 138 MB per GPU exceeds the 126 MB L2; a 256 MB buffer is also "
+                  "written between steps"}
+
+
+def run_engine(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: mcstate_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from mcstate_b200 import dust
+
+    t, x = load_data()
+    n_steps_model = int(t[-1])
+    gen = dust.dust_example("sir")
+    # chain k on rank k: seeds by long jump so placement does not matter (R/pmcmc_parallel.R:133)
+    seed = dust.dust_rng_distributed_state(1, 1, world)[rank]
+    model = gen.new({}, 0, N_PARTICLES, seed=seed, gpu_config=local)
+    model.set_data(dust.dust_data({"time_end": t, "incidence": x}), False)
+    stream = torch.cuda.current_stream()
+    model.set_stream(stream.cuda_stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    pars = {"beta": 0.2, "gamma": 0.1}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        flush.zero_()
+        model.update_state(pars=pars, time=0)
+        model.filter_enqueue()
+        return model.filter_collect()
+
+    def step_e2e():
+        flush.zero_()
+        model.update_state(pars=pars, time=0)
+        return model.filter()["log_likelihood"]
+
+    for _ in range(args.warmup):
+        step_resident()
+    # ---- kernel-resident timing --------------------------------------------------
+    model.set_kernel_timing(True)
+    step_resident()  # builds the timed graph outside the timed region
+    model.kernel_timing()
+    launches0 = model.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with ClockSampler(local) as clocks:
+        ev0.record(stream)
+        for _ in range(args.steps):
+            ll = step_resident()
+        ev1.record(stream)
+        barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = model.launch_count() - launches0
+    k_ms, k_n = model.kernel_timing()
+    model.set_kernel_timing(False)
+
+    # ---- end to end through the host API (host pars in, host log-likelihood out) ---
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    tmax = torch.tensor([ms_total, e2e_s * 1e3], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(tmax[0]), float(tmax[1])
+    work = world * N_PARTICLES * n_steps_model * args.steps
+    value = work / (ms_total * 1e-3)
+    e2e_value = work / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peak, peak_kind = measured_peak_gbs()
+        names = ["k_run_compare", "k_tile_weights", "k_finalize_row", "k_resample_gather"]
+        per_launch_bytes = [BYTES_K1 * N_PARTICLES, BYTES_K2 * N_PARTICLES, 0,
+                            BYTES_K34 * N_PARTICLES]
+        kernels = {}
+        for k, name in enumerate(names):
+            if k_n[k]:
+                avg_ms = k_ms[k] / float(k_n[k])
+                kernels[name] = {"avg_us": 1e3 * avg_ms, "launches": int(k_n[k]),
+                                 "share_of_step": k_ms[k] / ms_total,
+                                 "achieved_gbs": per_launch_bytes[k] / (avg_ms * 1e-3) / 1e9}
+        dom = max(kernels, key=lambda n: kernels[n]["share_of_step"]) if kernels else None
+        roofline = None
+        if dom:
+            a = kernels[dom]["achieved_gbs"]
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s",
+                        "frac": a / peak, "traffic": None, "peak_source": peak_kind,
+                        "algorithmic_bytes_per_launch": per_launch_bytes[names.index(dom)],
+                        "whole_interval_frac": (BYTES_INTERVAL * N_PARTICLES * 100 * args.steps /
+                                                (ms_total * 1e-3) / 1e9) / peak,
+                        "kernels": kernels}
+        cores = os.cpu_count() or 1
+        cpu = None
+        if world == 1 or True:
+            n_cpu = 1 << 16
+            v, secs, _ = cpu_baseline(n_cpu, cores, reps=2)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "oracle filter at %d particles x 100 intervals (1/16 of one GPU's "
+                             "work), best of 2 after warm-up, %.2f s" % (n_cpu, secs)}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic (reference's inst/sir_incidence.csv, 100 days, rate 4)",
+            "config": config_dict(world),
+            "filter_evals_per_s": world * args.steps / (ms_total * 1e-3),
+            "log_likelihood": float(ll[0]),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * 8,
+                    "d2h_bytes_per_step": 8 + 8,
+                    "api": "dust_model.update_state(pars, time) + dust_model.filter()"},
+            "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks.summary(),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,173 @@
+/*
+ * mcstate_b200.h -- C ABI of the B200-native particle-filter engine.
+ *
+ * This is the drop-in boundary of SURVEY.md section 8(b): the native layer
+ * underneath the `dust_generator` model object that mcstate drives.  Every
+ * entry point replaces one method mcstate calls on that object; the call
+ * sites are cited as reference file:line (paths relative to the mcstate
+ * tree).  The R binding a maintainer would add (`.Call` shims + an R6
+ * generator) is in INTEGRATION.md.
+ *
+ * Conventions (mirroring dust's cpp11 entry points):
+ *   - every function returns MCB_OK (0) or a negative error code and never
+ *     aborts; mcb_last_error() gives the message (thread-local);
+ *   - a handle is created by mcb_alloc, owned by the caller, freed by
+ *     mcb_free; calls on one handle are synchronous and single-threaded,
+ *     different handles are independent (SMC^2 holds up to 1024 of them,
+ *     R/smc2.R:72-78);
+ *   - arrays are HOST pointers borrowed for the call, in R's column-major
+ *     layout: a state matrix [n_state, n_particles(, n_pars)] has n_state
+ *     fastest; nothing here is a torch type;
+ *   - all compute happens on the GPU: there is no CPU fallback, and
+ *     mcb_alloc fails with MCB_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef MCSTATE_B200_H
+#define MCSTATE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCB_OK 0
+#define MCB_ERR_ARG (-1)    /* bad argument (R: stop() with a message)          */
+#define MCB_ERR_CUDA (-2)   /* CUDA runtime failure, or no usable device         */
+#define MCB_ERR_STATE (-3)  /* call not valid in the handle's current state      */
+
+#define MCB_SCRAMBLER_PLUS 0      /* xoshiro256+  (dust's generator for double;  */
+                                  /* tests/testthat/test-pmcmc-parallel.R:41)    */
+#define MCB_SCRAMBLER_STARSTAR 1  /* xoshiro256** (BASELINE.json north_star)     */
+
+typedef struct mcb_model mcb_model;
+
+/* ---- library ---------------------------------------------------------- */
+int mcb_version(void);
+const char *mcb_last_error(void);
+/* replaces model$public_methods$has_gpu_support / gpu_info (R/particle_filter.R:212,241) */
+int mcb_device_count(int *n_devices);
+int mcb_device_info(int device_id, char *name, size_t name_len, int *cc_major,
+                    int *cc_minor, int *n_sm, size_t *mem_bytes);
+
+/* ---- model registry (dust::dust_example; tests/testthat/helper-mcstate.R:3) */
+/* names: "sir", "sirs".  Parameter vectors are positional; names/defaults via the
+ * two accessors so a host binding can map an R list and ignore extra keys
+ * (R/particle_filter.R:283-284). */
+int mcb_model_lookup(const char *name, int *model_id, size_t *n_state, size_t *n_par,
+                     size_t *n_data_fields);
+const char *mcb_model_par_name(int model_id, size_t i);
+double mcb_model_par_default(int model_id, size_t i);
+const char *mcb_model_state_name(int model_id, size_t i);
+
+/* ---- RNG state arithmetic on the host (pure seeding plumbing) ----------- */
+/* dust::dust_rng$new(seed): integer seed -> first stream */
+int mcb_rng_seed(uint64_t seed, uint64_t state[4]);
+/* $jump() / $long_jump()  (R/pmcmc_parallel.R:147) */
+int mcb_rng_jump(uint64_t state[4]);
+int mcb_rng_long_jump(uint64_t state[4]);
+/* $random_real(n) on one stream (R/pmcmc_parallel.R:148) */
+int mcb_rng_random_real(uint64_t state[4], int scrambler, size_t n, double *out);
+/* dust::dust_rng_distributed_state (R/pmcmc_parallel.R:133, R/smc2.R:68):
+ * out[n_nodes][n_streams][4]; node k = seed long-jumped k times */
+int mcb_rng_distributed_state(const uint64_t seed_state[4], size_t n_streams,
+                              size_t n_nodes, uint64_t *out);
+
+/* ---- the model object --------------------------------------------------- */
+/*
+ * generator$new(pars, time, n_particles, n_threads, seed, gpu_config, pars_multi)
+ *   R/particle_filter_state.R:237-241
+ * pars: [max(1,n_pars)][n_par]; n_pars == 0 <=> pars_multi = FALSE.
+ * seed_state: 4*n_seed_streams words (an integer seed is expanded by the host
+ * binding with mcb_rng_seed); the model owns n_particles*max(1,n_pars)+1
+ * streams, the last one is the filter's resampling stream.
+ */
+int mcb_alloc(int model_id, const double *pars, size_t n_particles, size_t n_pars,
+              uint64_t time, const uint64_t *seed_state, size_t n_seed_streams,
+              int scrambler, int deterministic, int device_id, mcb_model **out);
+int mcb_free(mcb_model *m);
+/* launch everything on this cudaStream_t (default: a stream owned by the handle) */
+int mcb_set_stream(mcb_model *m, void *cuda_stream);
+int mcb_synchronize(mcb_model *m);
+
+/* $n_state() $n_particles() $n_pars() $time()  (R/particle_filter_state.R:268,288,373) */
+int mcb_shape(const mcb_model *m, size_t *n_state, size_t *n_particles, size_t *n_pars,
+              size_t *n_index);
+int mcb_time(const mcb_model *m, uint64_t *time);
+/* $pars(): the parameter vectors currently on the device */
+int mcb_pars(const mcb_model *m, double *out);
+
+/* $set_index(idx): 0-based row indices here (R/particle_filter_state.R:261,263) */
+int mcb_set_index(mcb_model *m, const size_t *index, size_t n_index);
+/* $run(time_end) -> [n_index, n_total]; out may be NULL (R/particle_filter_state.R:65) */
+int mcb_run(mcb_model *m, uint64_t time_end, double *out);
+/* $simulate(times) -> [n_index, n_total, n_times] (R/predict.R:79) */
+int mcb_simulate(mcb_model *m, const uint64_t *times, size_t n_times, double *out);
+/* $state(index) (R/particle_filter_state.R:79,81,114,272); index NULL = all rows */
+int mcb_state(mcb_model *m, const size_t *index, size_t n_index, double *out);
+/*
+ * $update_state(pars=, state=, time=, set_initial_state=)
+ *   R/particle_filter_state.R:248,253,512; R/smc2.R:141
+ * pars NULL = keep; state NULL = keep; state_len is n_state (recycled over
+ * particles) or n_state*n_total.  Never touches the RNG.
+ */
+int mcb_update_state(mcb_model *m, const double *pars, const double *state,
+                     size_t state_len, int has_time, uint64_t time,
+                     int set_initial_state);
+/* $reorder(kappa): 1-based, within-block for [N,P] input (R/particle_filter_state.R:100) */
+int mcb_reorder(mcb_model *m, const int *kappa);
+/* $rng_state(first_only) / $set_rng_state(raw): 4 words (32 bytes) per stream
+ * (R/particle_filter.R:813,877; R/particle_filter_state.R:363,369,406,420) */
+int mcb_rng_state(mcb_model *m, int first_only, uint64_t *out);
+int mcb_set_rng_state(mcb_model *m, const uint64_t *state, size_t n_words);
+/*
+ * $set_data(dust_data(...), shared)  (R/particle_filter_state.R:243-246)
+ * values: [n_data][shared ? 1 : max(1,n_pars)][n_data_fields]; NaN = NA.
+ */
+int mcb_set_data(mcb_model *m, size_t n_data, const uint64_t *time_end,
+                 const double *values, int shared);
+/* $compare_data(): log-weights [n_total] for the datum at the current time;
+ * *has_data = 0 (and out untouched) when there is none */
+int mcb_compare_data(mcb_model *m, double *logw, int *has_data);
+/* $resample(weights) -> kappa (1-based, within-block); draws from the filter stream */
+int mcb_resample(mcb_model *m, const double *weights, int *kappa);
+
+/*
+ * $filter(time_end, save_trajectories, time_snapshot)   <- THE HOT PATH
+ *   R/particle_filter_state.R:151 (step_compiled)
+ * Runs every not-yet-consumed data row with time_end <= `time_end`; one CUDA
+ * graph launch, no host synchronisation between intervals.
+ *   log_likelihood [max(1,n_pars)]
+ *   trajectories   [n_index, n_total, n_rows+1] ancestor-traced, or NULL
+ *   snapshots      [n_state, n_total, n_snapshots] (state after resampling), or NULL
+ *   min_log_likelihood: n_min = 0 (reference behaviour: never forwarded,
+ *     R/particle_filter_state.R:151), 1 or max(1,n_pars) (rule of
+ *     R/particle_filter_state.R:463-474)
+ * mcb_filter_rows tells the caller how many rows a call would consume (to size
+ * `trajectories`).
+ */
+int mcb_filter_rows(const mcb_model *m, uint64_t time_end, size_t *n_rows);
+int mcb_filter(mcb_model *m, uint64_t time_end, int save_trajectories,
+               const uint64_t *snapshot_times, size_t n_snapshots,
+               const double *min_log_likelihood, size_t n_min,
+               double *log_likelihood, double *trajectories, double *snapshots);
+/* the same, split so many handles / GPUs can be in flight at once: enqueue
+ * returns as soon as the work is queued, collect waits and copies out */
+int mcb_filter_enqueue(mcb_model *m, uint64_t time_end);
+int mcb_filter_collect(mcb_model *m, double *log_likelihood);
+/* number of kernels launched by this handle so far (bench.py: gpu_launches) */
+int mcb_launch_count(const mcb_model *m, uint64_t *n);
+/*
+ * Per-kernel device timing for the roofline report.  When enabled, the filter's
+ * CUDA graph carries event records around the four per-interval kernels
+ * (0: run+compare, 1: tile weights, 2: finalize, 3: resample+gather);
+ * mcb_kernel_timing returns the accumulated milliseconds and launch counts
+ * since the last reset and clears them.
+ */
+int mcb_set_kernel_timing(mcb_model *m, int enable);
+int mcb_kernel_timing(mcb_model *m, double ms[4], uint64_t launches[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

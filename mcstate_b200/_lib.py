@@ -1,0 +1,117 @@
+"""ctypes binding of include/mcstate_b200.h (libmcstate_b200.so).
+
+The shared library holds every kernel and the whole engine; Python only
+marshals host arrays across the C ABI.  There is deliberately no fallback: if
+the library is missing, or no CUDA device is usable, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmcstate_b200.so")
+
+OK, ERR_ARG, ERR_CUDA, ERR_STATE = 0, -1, -2, -3
+SCRAMBLER_PLUS, SCRAMBLER_STARSTAR = 0, 1
+
+u64p = C.POINTER(C.c_uint64)
+f64p = C.POINTER(C.c_double)
+i32p = C.POINTER(C.c_int)
+szp = C.POINTER(C.c_size_t)
+handle_p = C.c_void_p
+
+
+class McbError(RuntimeError):
+    """An error reported by the native engine (R: a stop() from the model object)."""
+
+    def __init__(self, code, message):
+        super().__init__(message)
+        self.code = code
+
+
+# name -> (restype, argtypes); every symbol declared in include/mcstate_b200.h
+SIGNATURES = {
+    "mcb_version": (C.c_int, []),
+    "mcb_last_error": (C.c_char_p, []),
+    "mcb_device_count": (C.c_int, [i32p]),
+    "mcb_device_info": (C.c_int, [C.c_int, C.c_char_p, C.c_size_t, i32p, i32p, i32p, szp]),
+    "mcb_model_lookup": (C.c_int, [C.c_char_p, i32p, szp, szp, szp]),
+    "mcb_model_par_name": (C.c_char_p, [C.c_int, C.c_size_t]),
+    "mcb_model_par_default": (C.c_double, [C.c_int, C.c_size_t]),
+    "mcb_model_state_name": (C.c_char_p, [C.c_int, C.c_size_t]),
+    "mcb_rng_seed": (C.c_int, [C.c_uint64, u64p]),
+    "mcb_rng_jump": (C.c_int, [u64p]),
+    "mcb_rng_long_jump": (C.c_int, [u64p]),
+    "mcb_rng_random_real": (C.c_int, [u64p, C.c_int, C.c_size_t, f64p]),
+    "mcb_rng_distributed_state": (C.c_int, [u64p, C.c_size_t, C.c_size_t, u64p]),
+    "mcb_alloc": (C.c_int, [C.c_int, f64p, C.c_size_t, C.c_size_t, C.c_uint64, u64p, C.c_size_t,
+                            C.c_int, C.c_int, C.c_int, C.POINTER(handle_p)]),
+    "mcb_free": (C.c_int, [handle_p]),
+    "mcb_set_stream": (C.c_int, [handle_p, C.c_void_p]),
+    "mcb_synchronize": (C.c_int, [handle_p]),
+    "mcb_shape": (C.c_int, [handle_p, szp, szp, szp, szp]),
+    "mcb_time": (C.c_int, [handle_p, u64p]),
+    "mcb_pars": (C.c_int, [handle_p, f64p]),
+    "mcb_set_index": (C.c_int, [handle_p, szp, C.c_size_t]),
+    "mcb_run": (C.c_int, [handle_p, C.c_uint64, f64p]),
+    "mcb_simulate": (C.c_int, [handle_p, u64p, C.c_size_t, f64p]),
+    "mcb_state": (C.c_int, [handle_p, szp, C.c_size_t, f64p]),
+    "mcb_update_state": (C.c_int, [handle_p, f64p, f64p, C.c_size_t, C.c_int, C.c_uint64, C.c_int]),
+    "mcb_reorder": (C.c_int, [handle_p, i32p]),
+    "mcb_rng_state": (C.c_int, [handle_p, C.c_int, u64p]),
+    "mcb_set_rng_state": (C.c_int, [handle_p, u64p, C.c_size_t]),
+    "mcb_set_data": (C.c_int, [handle_p, C.c_size_t, u64p, f64p, C.c_int]),
+    "mcb_compare_data": (C.c_int, [handle_p, f64p, i32p]),
+    "mcb_resample": (C.c_int, [handle_p, f64p, i32p]),
+    "mcb_filter_rows": (C.c_int, [handle_p, C.c_uint64, szp]),
+    "mcb_filter": (C.c_int, [handle_p, C.c_uint64, C.c_int, u64p, C.c_size_t, f64p, C.c_size_t,
+                             f64p, f64p, f64p]),
+    "mcb_filter_enqueue": (C.c_int, [handle_p, C.c_uint64]),
+    "mcb_filter_collect": (C.c_int, [handle_p, f64p]),
+    "mcb_launch_count": (C.c_int, [handle_p, u64p]),
+    "mcb_set_kernel_timing": (C.c_int, [handle_p, C.c_int]),
+    "mcb_kernel_timing": (C.c_int, [handle_p, f64p, u64p]),
+}
+
+
+def build(force: bool = False) -> str:
+    """Compile libmcstate_b200.so in-tree with nvcc for sm_100a (no GPU needed)."""
+    src = os.path.join(_HERE, "csrc")
+    newest = max(os.path.getmtime(os.path.join(src, f)) for f in os.listdir(src))
+    hdr = os.path.join(os.path.dirname(_HERE), "include", "mcstate_b200.h")
+    newest = max(newest, os.path.getmtime(hdr))
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < newest:
+        subprocess.run(["make", "-C", src, "-s"] + (["-B"] if force else []), check=True)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Load the engine; raises if the shared library has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libmcstate_b200.so is missing: run `python -c 'import __graft_entry__ as g; "
+                "g.build()'` (mcstate_b200 has no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != OK:
+        msg = lib().mcb_last_error()
+        raise McbError(rc, msg.decode() if msg else "mcstate_b200 error %d" % rc)
+
+
+def ptr(a, typ):
+    return None if a is None else a.ctypes.data_as(typ)

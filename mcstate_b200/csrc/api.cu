@@ -1,0 +1,1046 @@
+// C ABI of the B200 particle-filter engine (include/mcstate_b200.h).
+//
+// One mcb_model = one dust model object: particle state, one
+// RNG stream per particle (+ the filter stream), parameters, observations and
+// the scratch the filter needs, all resident in HBM for the life of the
+// handle.  model$filter() is recorded once per (row range, options) as a CUDA
+// graph and replayed: ~4 kernels per data interval, no host round trip until
+// the log-likelihood is read.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/mcstate_b200.h"
+#include "kernels.cuh"
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string &msg) {
+  g_error = msg;
+  return code;
+}
+
+#define MCB_CUDA(expr)                                                             \
+  do {                                                                             \
+    cudaError_t err__ = (expr);                                                    \
+    if (err__ != cudaSuccess) {                                                    \
+      return fail(MCB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(err__)); \
+    }                                                                              \
+  } while (0)
+
+#define MCB_TRY(expr)              \
+  do {                             \
+    int rc__ = (expr);             \
+    if (rc__ != MCB_OK) return rc__; \
+  } while (0)
+
+struct ModelDesc {
+  const char *name;
+  int n_state, n_par, n_data;
+  const char *par_names[mcb::kMaxPar];
+  double par_defaults[mcb::kMaxPar];
+  const char *state_names[mcb::kMaxState];
+};
+
+// defaults: scripts/generate_vignette_data.R:11-12, tests/testthat/helper-mcstate.R:11-15
+const ModelDesc kModels[] = {
+    {"sir", 5, 7, 1,
+     {"beta", "gamma", "I0", "exp_noise", "S0", "R0", "freq"},
+     {0.2, 0.1, 10.0, 1e6, 1000.0, 0.0, 4.0},
+     {"S", "I", "R", "cases_cumul", "cases_inc"}},
+    {"sirs", 4, 8, 1,
+     {"alpha", "beta", "gamma", "I0", "exp_noise", "S0", "R0", "freq"},
+     {0.1, 0.2, 0.1, 10.0, 1e6, 1000.0, 0.0, 4.0},
+     {"S", "I", "R", "cases_inc"}},
+};
+constexpr int kNumModels = sizeof(kModels) / sizeof(kModels[0]);
+
+size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
+
+int ceil_log2(size_t n) {
+  int k = 0;
+  while (((size_t)1 << k) < n) ++k;
+  return k;
+}
+
+// fractional bits of a fixed-point weight: n of them must sum below 2^63
+int weight_shift(size_t n) {
+  int k = 62 - ceil_log2(n);
+  return k > 52 ? 52 : k;
+}
+
+// per-device table of jump-matrix powers, built once
+struct JumpCache {
+  std::mutex mu;
+  std::map<int, uint64_t *> dev;
+  mcb::JumpTable *host = nullptr;
+};
+JumpCache g_jump;
+
+int jump_table_device(int device, uint64_t **out) {
+  std::lock_guard<std::mutex> lock(g_jump.mu);
+  auto it = g_jump.dev.find(device);
+  if (it != g_jump.dev.end()) { *out = it->second; return MCB_OK; }
+  if (!g_jump.host) {
+    g_jump.host = new mcb::JumpTable;
+    mcb::jump_table_build(*g_jump.host);
+  }
+  uint64_t *d = nullptr;
+  MCB_CUDA(cudaMalloc(&d, sizeof(mcb::JumpTable)));
+  MCB_CUDA(cudaMemcpy(d, g_jump.host, sizeof(mcb::JumpTable), cudaMemcpyHostToDevice));
+  g_jump.dev[device] = d;
+  *out = d;
+  return MCB_OK;
+}
+
+struct GraphKey {
+  int row_first, row_last, hist, n_snap, n_min;
+  uint64_t snap_hash;
+  bool operator<(const GraphKey &o) const {
+    return std::tie(row_first, row_last, hist, n_snap, n_min, snap_hash) <
+           std::tie(o.row_first, o.row_last, o.hist, o.n_snap, o.n_min, o.snap_hash);
+  }
+};
+
+struct GraphEntry {
+  cudaGraphExec_t exec = nullptr;
+  uint64_t n_kernels = 0;
+};
+
+}  // namespace
+
+struct mcb_model {
+  int model_id = 0, scrambler = 0, device = 0;
+  const ModelDesc *desc = nullptr;
+  mcb::View v{};
+  uint64_t time = 0;
+  std::vector<double> pars_host;
+
+  // observations
+  size_t n_data = 0, data_cursor = 0;
+  std::vector<uint64_t> data_time;
+  std::vector<char> row_all_na;  // per row: every set NA
+  double *d_data = nullptr;
+  double *d_u = nullptr;
+  uint64_t *d_fs_after = nullptr;
+  unsigned long long *d_wmax = nullptr;
+
+  // state
+  double *d_pars = nullptr;
+  int *d_index = nullptr;
+  int *d_flags = nullptr;
+  double *d_min_ll = nullptr;
+  double *d_ll = nullptr;
+  int *d_kappa = nullptr;      // scratch for reorder/resample
+  double *d_stage = nullptr;   // staging for packed state in/out
+  size_t stage_bytes = 0;
+  std::vector<int> index_host;
+
+  // history / snapshots of the last filter call
+  double *d_hist_value = nullptr;
+  int *d_hist_order = nullptr;
+  double *d_traj = nullptr;
+  double *d_snap = nullptr;
+  size_t hist_rows_cap = 0, hist_index_cap = 0, snap_cap = 0;
+
+  // pinned result block: ll[n_sets], flags[2]
+  double *h_ll = nullptr;
+  int *h_flags = nullptr;
+
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  std::map<GraphKey, GraphEntry> graphs;
+  uint64_t launches = 0;
+
+  // optional per-kernel timing (bench.py roofline): 5 events per data row
+  bool timing = false;
+  std::vector<cudaEvent_t> events;
+  double kernel_ms[4] = {0, 0, 0, 0};
+  uint64_t kernel_n[4] = {0, 0, 0, 0};
+
+  // pending enqueue
+  bool pending = false;
+  int pend_first = 0, pend_last = 0;
+};
+
+namespace {
+
+using mcb::View;
+
+void clear_graphs(mcb_model *m) {
+  for (auto &g : m->graphs)
+    if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+  m->graphs.clear();
+}
+
+int ensure_stage(mcb_model *m, size_t bytes) {
+  if (bytes <= m->stage_bytes) return MCB_OK;
+  if (m->d_stage) cudaFree(m->d_stage);
+  m->d_stage = nullptr;
+  m->stage_bytes = 0;
+  MCB_CUDA(cudaMalloc(&m->d_stage, bytes));
+  m->stage_bytes = bytes;
+  return MCB_OK;
+}
+
+unsigned blocks_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+template <class M, int SCR>
+void launch_run_compare(mcb_model *m, const double *y_in, double *y_out, uint64_t t0,
+                        uint32_t n_steps, int row, double *hist) {
+  const unsigned grid = blocks_for(m->v.n_total, mcb::kRunThreads);
+  if (hist)
+    mcb::k_run_compare<M, SCR, true><<<grid, mcb::kRunThreads, 0, m->stream>>>(
+        m->v, y_in, y_out, t0, n_steps, row, hist);
+  else
+    mcb::k_run_compare<M, SCR, false><<<grid, mcb::kRunThreads, 0, m->stream>>>(
+        m->v, y_in, y_out, t0, n_steps, row, nullptr);
+  ++m->launches;
+}
+
+void run_compare(mcb_model *m, const double *y_in, double *y_out, uint64_t t0,
+                 uint32_t n_steps, int row, double *hist) {
+  const int key = m->model_id * 2 + m->scrambler;
+  switch (key) {
+    case 0: launch_run_compare<mcb::SirModel, 0>(m, y_in, y_out, t0, n_steps, row, hist); break;
+    case 1: launch_run_compare<mcb::SirModel, 1>(m, y_in, y_out, t0, n_steps, row, hist); break;
+    case 2: launch_run_compare<mcb::SirsModel, 0>(m, y_in, y_out, t0, n_steps, row, hist); break;
+    default: launch_run_compare<mcb::SirsModel, 1>(m, y_in, y_out, t0, n_steps, row, hist); break;
+  }
+}
+
+void resample_gather(mcb_model *m, int row, int *kappa_out) {
+  const unsigned grid = blocks_for(m->v.n_total, mcb::kGatherThreads);
+  if (m->v.n_state == 5)
+    mcb::k_resample_gather<5><<<grid, mcb::kGatherThreads, 0, m->stream>>>(m->v, row, kappa_out);
+  else
+    mcb::k_resample_gather<4><<<grid, mcb::kGatherThreads, 0, m->stream>>>(m->v, row, kappa_out);
+  ++m->launches;
+}
+
+void set_initial(mcb_model *m) {
+  const unsigned grid = blocks_for(m->v.n_total, 256);
+  if (m->model_id == 0) mcb::k_set_initial<mcb::SirModel><<<grid, 256, 0, m->stream>>>(m->v);
+  else mcb::k_set_initial<mcb::SirsModel><<<grid, 256, 0, m->stream>>>(m->v);
+  ++m->launches;
+}
+
+void draw_uniforms(mcb_model *m, int row_first, int row_last) {
+  if (m->scrambler == 0)
+    mcb::k_draw_uniforms<0><<<1, 32, 0, m->stream>>>(m->v, row_first, row_last, m->d_u, m->d_fs_after);
+  else
+    mcb::k_draw_uniforms<1><<<1, 32, 0, m->stream>>>(m->v, row_first, row_last, m->d_u, m->d_fs_after);
+  ++m->launches;
+}
+
+// boundary k (0..4) of a data row: before K1, after K1, K2, K2b, K3
+void mark(mcb_model *m, int row, int k) {
+  if (!m->timing) return;
+  const size_t need = (size_t)(row + 1) * 5;
+  while (m->events.size() < need) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    m->events.push_back(e);
+  }
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(m->stream, &st);
+  cudaEventRecordWithFlags(m->events[(size_t)row * 5 + k], m->stream,
+                           st == cudaStreamCaptureStatusActive ? cudaEventRecordExternal
+                                                               : cudaEventRecordDefault);
+}
+
+void reset_cursor(mcb_model *m) {
+  m->data_cursor = 0;
+  while (m->data_cursor < m->n_data && m->data_time[m->data_cursor] <= m->time) ++m->data_cursor;
+}
+
+int pack_to_host(mcb_model *m, const double *y, const int *d_index, int n_rows, double *out) {
+  const size_t bytes = m->v.n_total * (size_t)n_rows * sizeof(double);
+  MCB_TRY(ensure_stage(m, bytes));
+  mcb::k_pack_rows<<<blocks_for(m->v.n_total, 256), 256, 0, m->stream>>>(
+      y, m->v.ld, m->v.n_total, d_index, n_rows, m->d_stage);
+  ++m->launches;
+  MCB_CUDA(cudaMemcpyAsync(out, m->d_stage, bytes, cudaMemcpyDeviceToHost, m->stream));
+  MCB_CUDA(cudaStreamSynchronize(m->stream));
+  return MCB_OK;
+}
+
+// Enqueue rows [first, last) of the filter on m->stream (also used under capture).
+// Returns the number of kernels enqueued.
+uint64_t enqueue_filter_rows(mcb_model *m, int first, int last, bool hist,
+                             const std::vector<int> &snap_rows) {
+  const uint64_t before = m->launches;
+  View &v = m->v;
+  const size_t n_sets = v.n_sets;
+  cudaMemsetAsync(m->d_flags, 0, 2 * sizeof(int), m->stream);
+  cudaMemsetAsync(m->d_ll, 0, n_sets * sizeof(double), m->stream);
+  cudaMemsetAsync(m->d_wmax + (size_t)first * n_sets, 0,
+                  (size_t)(last - first) * n_sets * sizeof(unsigned long long), m->stream);
+  draw_uniforms(m, first, last);
+  if (hist) {
+    // slice 0: the state before the first interval, identity order
+    const size_t slice = (size_t)v.n_index * v.ld;
+    run_compare(m, v.y, v.y, 0, 0, -1, m->d_hist_value);
+    (void)slice;
+    mcb::k_iota<<<blocks_for(v.n_total, 256), 256, 0, m->stream>>>(m->d_hist_order, v.n_total);
+    ++m->launches;
+  }
+  uint64_t t = m->time;
+  size_t snap_i = 0;
+  for (int row = first; row < last; ++row) {
+    const uint64_t t_end = m->data_time[row];
+    const uint32_t n_steps = (uint32_t)(t_end - t);
+    const int rel = row - first;
+    double *hist_slice = hist ? m->d_hist_value + (size_t)(rel + 1) * v.n_index * v.ld : nullptr;
+    int *order_slice = hist ? m->d_hist_order + (size_t)(rel + 1) * v.n_total : nullptr;
+    if (m->row_all_na[row]) {
+      // no observation anywhere: run in place, nothing to weigh or resample
+      run_compare(m, v.y, v.y, t, n_steps, -1, hist_slice);
+      if (hist) {
+        mcb::k_iota<<<blocks_for(v.n_total, 256), 256, 0, m->stream>>>(order_slice, v.n_total);
+        ++m->launches;
+      }
+    } else {
+      mark(m, row, 0);
+      run_compare(m, v.y, v.y_tmp, t, n_steps, row, hist_slice);
+      mark(m, row, 1);
+      mcb::k_tile_weights<false><<<(unsigned)(n_sets * v.tiles_per_set), mcb::kTileThreads, 0,
+                                   m->stream>>>(v, row);
+      mark(m, row, 2);
+      mcb::k_finalize_row<<<1, 1024, 0, m->stream>>>(v, row);
+      mark(m, row, 3);
+      m->launches += 2;
+      resample_gather(m, row, order_slice);
+      mark(m, row, 4);
+    }
+    while (snap_i < snap_rows.size() && snap_rows[snap_i] < row) ++snap_i;
+    if (snap_i < snap_rows.size() && snap_rows[snap_i] == row) {
+      mcb::k_copy_state_if_running<<<blocks_for(v.n_total, 256), 256, 0, m->stream>>>(
+          v, m->d_snap + snap_i * (size_t)v.n_state * v.ld);
+      ++m->launches;
+      ++snap_i;
+    }
+    t = t_end;
+  }
+  mcb::k_filter_finish<<<1, 32, 0, m->stream>>>(v, first, last, m->d_fs_after);
+  mcb::k_adopt_tmp_if_stopped<<<blocks_for(v.n_total, 256), 256, 0, m->stream>>>(v);
+  m->launches += 2;
+  return m->launches - before;
+}
+
+int filter_rows_range(const mcb_model *m, uint64_t time_end, int *first, int *last) {
+  size_t a = m->data_cursor, b = a;
+  while (b < m->n_data && m->data_time[b] <= time_end) ++b;
+  *first = (int)a;
+  *last = (int)b;
+  return MCB_OK;
+}
+
+int prepare_history(mcb_model *m, int rows) {
+  View &v = m->v;
+  if ((size_t)rows + 1 > m->hist_rows_cap || (size_t)v.n_index > m->hist_index_cap) {
+    if (m->d_hist_value) cudaFree(m->d_hist_value);
+    if (m->d_hist_order) cudaFree(m->d_hist_order);
+    if (m->d_traj) cudaFree(m->d_traj);
+    m->d_hist_value = nullptr; m->d_hist_order = nullptr; m->d_traj = nullptr;
+    m->hist_rows_cap = 0;
+    clear_graphs(m);  // baked pointers are stale
+    const size_t T1 = (size_t)rows + 1;
+    MCB_CUDA(cudaMalloc(&m->d_hist_value, T1 * v.n_index * v.ld * sizeof(double)));
+    MCB_CUDA(cudaMalloc(&m->d_hist_order, T1 * v.n_total * sizeof(int)));
+    MCB_CUDA(cudaMalloc(&m->d_traj, T1 * v.n_total * v.n_index * sizeof(double)));
+    m->hist_rows_cap = T1;
+    m->hist_index_cap = v.n_index;
+  }
+  return MCB_OK;
+}
+
+int run_filter(mcb_model *m, uint64_t time_end, bool hist, const uint64_t *snapshot_times,
+               size_t n_snap, const double *min_ll, size_t n_min, bool wait,
+               double *ll_out, double *traj_out, double *snap_out) {
+  if (m->pending) return fail(MCB_ERR_STATE, "a filter is already enqueued; collect it first");
+  if (m->n_data == 0) return fail(MCB_ERR_STATE, "filter: no data set (call set_data first)");
+  View &v = m->v;
+  if (n_min != 0 && n_min != 1 && n_min != v.n_sets)
+    return fail(MCB_ERR_ARG, "min_log_likelihood must have length 0, 1 or n_pars");
+  int first, last;
+  filter_rows_range(m, time_end, &first, &last);
+  const int rows = last - first;
+
+  std::vector<int> snap_rows;
+  uint64_t snap_hash = 1469598103934665603ULL;
+  for (size_t k = 0; k < n_snap; ++k) {
+    int found = -1;
+    for (int r = first; r < last; ++r)
+      if (m->data_time[r] == snapshot_times[k]) found = r;
+    if (found < 0) return fail(MCB_ERR_ARG, "snapshot time is not a data time of this call");
+    if (!snap_rows.empty() && found <= snap_rows.back())
+      return fail(MCB_ERR_ARG, "snapshot times must be strictly increasing");
+    snap_rows.push_back(found);
+    snap_hash = (snap_hash ^ (uint64_t)found) * 1099511628211ULL;
+  }
+  if (n_snap > m->snap_cap) {
+    if (m->d_snap) cudaFree(m->d_snap);
+    m->d_snap = nullptr;
+    clear_graphs(m);
+    MCB_CUDA(cudaMalloc(&m->d_snap, n_snap * (size_t)v.n_state * v.ld * sizeof(double)));
+    m->snap_cap = n_snap;
+  }
+  if (hist) MCB_TRY(prepare_history(m, rows));
+  if (n_snap)
+    MCB_CUDA(cudaMemsetAsync(m->d_snap, 0xff, n_snap * (size_t)v.n_state * v.ld * sizeof(double),
+                             m->stream));
+  v.n_min = (int)n_min;
+  if (n_min)
+    MCB_CUDA(cudaMemcpyAsync(m->d_min_ll, min_ll, n_min * sizeof(double), cudaMemcpyHostToDevice,
+                             m->stream));
+
+  if (rows > 0) {
+    const GraphKey key{first, last, (hist ? 1 : 0) | (m->timing ? 2 : 0), (int)n_snap, (int)n_min,
+                       snap_hash};
+    auto it = m->graphs.find(key);
+    if (it == m->graphs.end()) {
+      cudaGraph_t graph = nullptr;
+      MCB_CUDA(cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal));
+      const uint64_t n_k = enqueue_filter_rows(m, first, last, hist, snap_rows);
+      m->launches -= n_k;  // counted per replay below
+      cudaError_t err = cudaStreamEndCapture(m->stream, &graph);
+      if (err != cudaSuccess)
+        return fail(MCB_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(err));
+      GraphEntry e;
+      err = cudaGraphInstantiate(&e.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (err != cudaSuccess)
+        return fail(MCB_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(err));
+      e.n_kernels = n_k;
+      it = m->graphs.emplace(key, e).first;
+    }
+    MCB_CUDA(cudaGraphLaunch(it->second.exec, m->stream));
+    m->launches += it->second.n_kernels;
+  } else {
+    MCB_CUDA(cudaMemsetAsync(m->d_flags, 0, 2 * sizeof(int), m->stream));
+    MCB_CUDA(cudaMemsetAsync(m->d_ll, 0, v.n_sets * sizeof(double), m->stream));
+  }
+  MCB_CUDA(cudaMemcpyAsync(m->h_ll, m->d_ll, v.n_sets * sizeof(double), cudaMemcpyDeviceToHost,
+                           m->stream));
+  MCB_CUDA(cudaMemcpyAsync(m->h_flags, m->d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost,
+                           m->stream));
+  m->pending = true;
+  m->pend_first = first;
+  m->pend_last = last;
+  if (!wait) return MCB_OK;
+
+  if (hist && traj_out) {
+    mcb::k_trace_history<<<blocks_for(v.n_total, 128), 128, 0, m->stream>>>(
+        v, m->d_hist_value, m->d_hist_order, rows, first, m->d_traj);
+    ++m->launches;
+    MCB_CUDA(cudaMemcpyAsync(traj_out, m->d_traj,
+                             (size_t)(rows + 1) * v.n_total * v.n_index * sizeof(double),
+                             cudaMemcpyDeviceToHost, m->stream));
+  }
+  if (n_snap && snap_out) {
+    for (size_t k = 0; k < n_snap; ++k) {
+      MCB_TRY(pack_to_host(m, m->d_snap + k * (size_t)v.n_state * v.ld, nullptr, v.n_state,
+                           snap_out + k * v.n_total * (size_t)v.n_state));
+    }
+  }
+  return mcb_filter_collect(m, ll_out);
+}
+
+}  // namespace
+
+// ===========================================================================
+extern "C" {
+
+int mcb_version(void) { return 100; }
+const char *mcb_last_error(void) { return g_error.c_str(); }
+
+int mcb_device_count(int *n_devices) {
+  if (!n_devices) return fail(MCB_ERR_ARG, "n_devices is NULL");
+  int n = 0;
+  cudaError_t err = cudaGetDeviceCount(&n);
+  if (err != cudaSuccess) {
+    *n_devices = 0;
+    return fail(MCB_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(err));
+  }
+  *n_devices = n;
+  return MCB_OK;
+}
+
+int mcb_device_info(int device_id, char *name, size_t name_len, int *cc_major, int *cc_minor,
+                    int *n_sm, size_t *mem_bytes) {
+  cudaDeviceProp p;
+  MCB_CUDA(cudaGetDeviceProperties(&p, device_id));
+  if (name && name_len) { std::strncpy(name, p.name, name_len - 1); name[name_len - 1] = 0; }
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  if (n_sm) *n_sm = p.multiProcessorCount;
+  if (mem_bytes) *mem_bytes = p.totalGlobalMem;
+  return MCB_OK;
+}
+
+int mcb_model_lookup(const char *name, int *model_id, size_t *n_state, size_t *n_par,
+                     size_t *n_data_fields) {
+  if (!name) return fail(MCB_ERR_ARG, "model name is NULL");
+  for (int i = 0; i < kNumModels; ++i)
+    if (std::strcmp(name, kModels[i].name) == 0) {
+      if (model_id) *model_id = i;
+      if (n_state) *n_state = kModels[i].n_state;
+      if (n_par) *n_par = kModels[i].n_par;
+      if (n_data_fields) *n_data_fields = kModels[i].n_data;
+      return MCB_OK;
+    }
+  return fail(MCB_ERR_ARG, std::string("unknown model '") + name + "'");
+}
+
+const char *mcb_model_par_name(int model_id, size_t i) {
+  if (model_id < 0 || model_id >= kNumModels || i >= (size_t)kModels[model_id].n_par) return nullptr;
+  return kModels[model_id].par_names[i];
+}
+double mcb_model_par_default(int model_id, size_t i) {
+  if (model_id < 0 || model_id >= kNumModels || i >= (size_t)kModels[model_id].n_par) return NAN;
+  return kModels[model_id].par_defaults[i];
+}
+const char *mcb_model_state_name(int model_id, size_t i) {
+  if (model_id < 0 || model_id >= kNumModels || i >= (size_t)kModels[model_id].n_state) return nullptr;
+  return kModels[model_id].state_names[i];
+}
+
+// ---- RNG plumbing on the host ---------------------------------------------
+int mcb_rng_seed(uint64_t seed, uint64_t state[4]) {
+  if (!state) return fail(MCB_ERR_ARG, "state is NULL");
+  mcb::xo_seed(seed, state);
+  return MCB_OK;
+}
+int mcb_rng_jump(uint64_t state[4]) {
+  if (!state) return fail(MCB_ERR_ARG, "state is NULL");
+  mcb::xo_jump(state);
+  return MCB_OK;
+}
+int mcb_rng_long_jump(uint64_t state[4]) {
+  if (!state) return fail(MCB_ERR_ARG, "state is NULL");
+  mcb::xo_long_jump(state);
+  return MCB_OK;
+}
+int mcb_rng_random_real(uint64_t state[4], int scrambler, size_t n, double *out) {
+  if (!state || !out) return fail(MCB_ERR_ARG, "NULL argument");
+  mcb::Xoshiro r{state[0], state[1], state[2], state[3]};
+  for (size_t i = 0; i < n; ++i)
+    out[i] = scrambler == MCB_SCRAMBLER_PLUS ? mcb::xo_real<0>(r) : mcb::xo_real<1>(r);
+  state[0] = r.s0; state[1] = r.s1; state[2] = r.s2; state[3] = r.s3;
+  return MCB_OK;
+}
+int mcb_rng_distributed_state(const uint64_t seed_state[4], size_t n_streams, size_t n_nodes,
+                              uint64_t *out) {
+  if (!seed_state || !out) return fail(MCB_ERR_ARG, "NULL argument");
+  uint64_t base[4] = {seed_state[0], seed_state[1], seed_state[2], seed_state[3]};
+  for (size_t k = 0; k < n_nodes; ++k) {
+    uint64_t cur[4] = {base[0], base[1], base[2], base[3]};
+    for (size_t s = 0; s < n_streams; ++s) {
+      std::memcpy(out + (k * n_streams + s) * 4, cur, sizeof cur);
+      mcb::xo_jump(cur);
+    }
+    mcb::xo_long_jump(base);
+  }
+  return MCB_OK;
+}
+
+// ---- model object ------------------------------------------------------------
+int mcb_alloc(int model_id, const double *pars, size_t n_particles, size_t n_pars, uint64_t time,
+              const uint64_t *seed_state, size_t n_seed_streams, int scrambler,
+              int deterministic, int device_id, mcb_model **out) {
+  if (!out) return fail(MCB_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (model_id < 0 || model_id >= kNumModels) return fail(MCB_ERR_ARG, "unknown model id");
+  if (n_particles == 0) return fail(MCB_ERR_ARG, "'n_particles' must be at least 1");
+  if (!pars) return fail(MCB_ERR_ARG, "pars is NULL");
+  if (!seed_state || n_seed_streams == 0) return fail(MCB_ERR_ARG, "seed state is empty");
+  if (scrambler != MCB_SCRAMBLER_PLUS && scrambler != MCB_SCRAMBLER_STARSTAR)
+    return fail(MCB_ERR_ARG, "unknown scrambler");
+  const size_t n_sets = n_pars == 0 ? 1 : n_pars;
+  const size_t n_total = n_particles * n_sets;
+  if (n_total >= ((size_t)1 << 31)) return fail(MCB_ERR_ARG, "too many particles (int32 kappa)");
+  int n_dev = 0;
+  MCB_TRY(mcb_device_count(&n_dev));
+  if (n_dev == 0) return fail(MCB_ERR_CUDA, "no CUDA device: this engine has no CPU fallback");
+  if (device_id < 0 || device_id >= n_dev) return fail(MCB_ERR_ARG, "device_id out of range");
+  MCB_CUDA(cudaSetDevice(device_id));
+
+  mcb_model *m = new mcb_model;
+  m->model_id = model_id;
+  m->desc = &kModels[model_id];
+  m->scrambler = scrambler;
+  m->device = device_id;
+  m->time = time;
+  View &v = m->v;
+  v.n_particles = n_particles;
+  v.n_sets = n_sets;
+  v.n_total = n_total;
+  v.ld = round_up(n_total, 32);
+  v.ld_rng = round_up(n_total + 1, 32);
+  v.n_state = m->desc->n_state;
+  v.n_index = v.n_state;
+  v.n_min = 0;
+  v.data_sets = 1;
+  v.tiles_per_set = (int)((n_particles + mcb::kTile - 1) / mcb::kTile);
+  v.shift = weight_shift(n_particles);
+  v.deterministic = deterministic;
+
+  auto cleanup = [&](int rc) { mcb_free(m); return rc; };
+#define ALLOC(ptr, bytes)                                                         \
+  do {                                                                            \
+    cudaError_t e__ = cudaMalloc(&(ptr), (bytes));                                \
+    if (e__ != cudaSuccess)                                                       \
+      return cleanup(fail(MCB_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e__))); \
+  } while (0)
+  ALLOC(v.y, (size_t)v.n_state * v.ld * sizeof(double));
+  ALLOC(v.y_tmp, (size_t)v.n_state * v.ld * sizeof(double));
+  ALLOC(v.rng, 4 * v.ld_rng * sizeof(uint64_t));
+  ALLOC(m->d_pars, n_sets * mcb::kMaxPar * sizeof(double));
+  ALLOC(v.logw, v.ld * sizeof(double));
+  ALLOC(v.cw, v.ld * sizeof(unsigned long long));
+  ALLOC(v.tile_incl, n_sets * v.tiles_per_set * sizeof(unsigned long long));
+  ALLOC(v.setinfo, n_sets * sizeof(mcb::SetInfo));
+  ALLOC(m->d_ll, n_sets * sizeof(double));
+  ALLOC(m->d_min_ll, n_sets * sizeof(double));
+  ALLOC(m->d_flags, 2 * sizeof(int));
+  ALLOC(m->d_index, mcb::kMaxState * sizeof(int));
+  ALLOC(m->d_kappa, v.ld * sizeof(int));
+  ALLOC(m->d_u, n_sets * sizeof(double));
+  ALLOC(m->d_wmax, n_sets * sizeof(unsigned long long));
+  ALLOC(m->d_fs_after, 4 * sizeof(uint64_t));
+#undef ALLOC
+  v.pars = m->d_pars;
+  v.ll = m->d_ll;
+  v.min_ll = m->d_min_ll;
+  v.flags = m->d_flags;
+  v.index = m->d_index;
+  v.u_draws = m->d_u;
+  v.wmax = m->d_wmax;
+  if (cudaMallocHost(&m->h_ll, n_sets * sizeof(double)) != cudaSuccess ||
+      cudaMallocHost(&m->h_flags, 2 * sizeof(int)) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking) != cudaSuccess)
+    return cleanup(fail(MCB_ERR_CUDA, "pinned memory / stream creation failed"));
+  m->stream = m->own_stream;
+  cudaMemsetAsync(m->d_flags, 0, 2 * sizeof(int), m->stream);
+  cudaMemsetAsync(v.y, 0, (size_t)v.n_state * v.ld * sizeof(double), m->stream);
+  cudaMemsetAsync(v.y_tmp, 0, (size_t)v.n_state * v.ld * sizeof(double), m->stream);
+  m->index_host.resize(v.n_state);
+  for (int s = 0; s < v.n_state; ++s) m->index_host[s] = s;
+  cudaMemcpyAsync(m->d_index, m->index_host.data(), v.n_state * sizeof(int),
+                  cudaMemcpyHostToDevice, m->stream);
+
+  // RNG streams: supplied ones verbatim, the rest by parallel jump-ahead
+  {
+    const size_t n_streams = n_total + 1;
+    const size_t have = n_seed_streams < n_streams ? n_seed_streams : n_streams;
+    std::vector<uint64_t> soa(4 * have);
+    for (size_t i = 0; i < have; ++i)
+      for (int w = 0; w < 4; ++w) soa[w * have + i] = seed_state[4 * i + w];
+    for (int w = 0; w < 4; ++w)
+      cudaMemcpyAsync(v.rng + w * v.ld_rng, soa.data() + w * have, have * sizeof(uint64_t),
+                      cudaMemcpyHostToDevice, m->stream);
+    cudaStreamSynchronize(m->stream);
+    if (have < n_streams) {
+      uint64_t *d_jump = nullptr;
+      int rc = jump_table_device(device_id, &d_jump);
+      if (rc != MCB_OK) return cleanup(rc);
+      mcb::k_derive_streams<<<blocks_for(n_streams - have, 128), 128, 0, m->stream>>>(
+          v.rng, v.ld_rng, have, n_streams, d_jump);
+      ++m->launches;
+    }
+  }
+  int rc = mcb_update_state(m, pars, nullptr, 0, 1, time, 1);
+  if (rc != MCB_OK) return cleanup(rc);
+  cudaError_t err = cudaStreamSynchronize(m->stream);
+  if (err != cudaSuccess)
+    return cleanup(fail(MCB_ERR_CUDA, std::string("alloc: ") + cudaGetErrorString(err)));
+  *out = m;
+  return MCB_OK;
+}
+
+int mcb_free(mcb_model *m) {
+  if (!m) return MCB_OK;
+  cudaSetDevice(m->device);
+  if (m->stream) cudaStreamSynchronize(m->stream);
+  clear_graphs(m);
+  void *ptrs[] = {m->v.y, m->v.y_tmp, m->v.rng, m->d_pars, m->v.logw, m->v.cw, m->v.tile_incl,
+                  m->v.setinfo, m->d_ll, m->d_min_ll, m->d_flags, m->d_index, m->d_kappa, m->d_u,
+                  m->d_wmax, m->d_fs_after, m->d_data, m->d_stage, m->d_hist_value,
+                  m->d_hist_order, m->d_traj, m->d_snap};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  for (cudaEvent_t e : m->events) cudaEventDestroy(e);
+  if (m->h_ll) cudaFreeHost(m->h_ll);
+  if (m->h_flags) cudaFreeHost(m->h_flags);
+  if (m->own_stream) cudaStreamDestroy(m->own_stream);
+  delete m;
+  return MCB_OK;
+}
+
+int mcb_set_stream(mcb_model *m, void *cuda_stream) {
+  if (!m) return fail(MCB_ERR_ARG, "model is NULL");
+  cudaSetDevice(m->device);
+  cudaStreamSynchronize(m->stream);
+  m->stream = cuda_stream ? (cudaStream_t)cuda_stream : m->own_stream;
+  return MCB_OK;
+}
+
+int mcb_synchronize(mcb_model *m) {
+  if (!m) return fail(MCB_ERR_ARG, "model is NULL");
+  MCB_CUDA(cudaSetDevice(m->device));
+  MCB_CUDA(cudaStreamSynchronize(m->stream));
+  return MCB_OK;
+}
+
+int mcb_shape(const mcb_model *m, size_t *n_state, size_t *n_particles, size_t *n_pars,
+              size_t *n_index) {
+  if (!m) return fail(MCB_ERR_ARG, "model is NULL");
+  if (n_state) *n_state = m->v.n_state;
+  if (n_particles) *n_particles = m->v.n_particles;
+  if (n_pars) *n_pars = m->v.n_sets;
+  if (n_index) *n_index = m->v.n_index;
+  return MCB_OK;
+}
+
+int mcb_time(const mcb_model *m, uint64_t *time) {
+  if (!m || !time) return fail(MCB_ERR_ARG, "NULL argument");
+  *time = m->time;
+  return MCB_OK;
+}
+
+int mcb_pars(const mcb_model *m, double *out) {
+  if (!m || !out) return fail(MCB_ERR_ARG, "NULL argument");
+  for (size_t p = 0; p < m->v.n_sets; ++p)
+    std::memcpy(out + p * m->desc->n_par, m->pars_host.data() + p * mcb::kMaxPar,
+                m->desc->n_par * sizeof(double));
+  return MCB_OK;
+}
+
+int mcb_set_index(mcb_model *m, const size_t *index, size_t n_index) {
+  if (!m) return fail(MCB_ERR_ARG, "model is NULL");
+  MCB_CUDA(cudaSetDevice(m->device));
+  if (!index) {
+    n_index = m->v.n_state;
+    m->index_host.resize(n_index);
+    for (size_t s = 0; s < n_index; ++s) m->index_host[s] = (int)s;
+  } else {
+    if (n_index == 0 || n_index > (size_t)mcb::kMaxState)
+      return fail(MCB_ERR_ARG, "index length must be between 1 and 8");
+    for (size_t k = 0; k < n_index; ++k)
+      if (index[k] >= (size_t)m->v.n_state) return fail(MCB_ERR_ARG, "index out of range");
+    m->index_host.assign(n_index, 0);
+    for (size_t k = 0; k < n_index; ++k) m->index_host[k] = (int)index[k];
+  }
+  MCB_CUDA(cudaStreamSynchronize(m->stream));
+  MCB_CUDA(cudaMemcpy(m->d_index, m->index_host.data(), n_index * sizeof(int),
+                      cudaMemcpyHostToDevice));
+  if ((int)n_index != m->v.n_index) {
+    m->v.n_index = (int)n_index;
+    clear_graphs(m);
+  }
+  return MCB_OK;
+}
+
+int mcb_run(mcb_model *m, uint64_t time_end, double *out) {
+  if (!m) return fail(MCB_ERR_ARG, "model is NULL");
+  MCB_CUDA(cudaSetDevice(m->device));
+  if (time_end < m->time) return fail(MCB_ERR_ARG, "'time_end' must be at least the current time");
+  if (time_end > m->time) {
+    run_compare(m, m->v.y, m->v.y, m->time, (uint32_t)(time_end - m->time), -1, nullptr);
+    m->time = time_end;
+    reset_cursor(m);
+  }
+  if (out) return pack_to_host(m, m->v.y, m->d_index, m->v.n_index, out);
+  MCB_CUDA(cudaGetLastError());
+  return MCB_OK;
+}
+
+int mcb_simulate(mcb_model *m, const uint64_t *times, size_t n_times, double *out) {
+  if (!m || !times || !out) return fail(MCB_ERR_ARG, "NULL argument");
+  for (size_t k = 0; k < n_times; ++k) {
+    if (k > 0 && times[k] <= times[k - 1]) return fail(MCB_ERR_ARG, "'times' must be increasing");
+    MCB_TRY(mcb_run(m, times[k], out + k * m->v.n_total * (size_t)m->v.n_index));
+  }
+  return MCB_OK;
+}
+
+int mcb_state(mcb_model *m, const size_t *index, size_t n_index, double *out) {
+  if (!m || !out) return fail(MCB_ERR_ARG, "NULL argument");
+  MCB_CUDA(cudaSetDevice(m->device));
+  if (!index) return pack_to_host(m, m->v.y, nullptr, m->v.n_state, out);
+  if (n_index == 0) return MCB_OK;
+  std::vector<int> idx(n_index);
+  for (size_t k = 0; k < n_index; ++k) {
+    if (index[k] >= (size_t)m->v.n_state) return fail(MCB_ERR_ARG, "index out of range");
+    idx[k] = (int)index[k];
+  }
+  int *d_idx = nullptr;
+  MCB_CUDA(cudaMalloc(&d_idx, n_index * sizeof(int)));
+  cudaMemcpy(d_idx, idx.data(), n_index * sizeof(int), cudaMemcpyHostToDevice);
+  int rc = pack_to_host(m, m->v.y, d_idx, (int)n_index, out);
+  cudaFree(d_idx);
+  return rc;
+}
+
+int mcb_update_state(mcb_model *m, const double *pars, const double *state, size_t state_len,
+                     int has_time, uint64_t time, int set_initial_state) {
+  if (!m) return fail(MCB_ERR_ARG, "model is NULL");
+  MCB_CUDA(cudaSetDevice(m->device));
+  View &v = m->v;
+  if (state && state_len != (size_t)v.n_state && state_len != (size_t)v.n_state * v.n_total)
+    return fail(MCB_ERR_ARG, "'state' must have length n_state or n_state * n_particles");
+  if (has_time) {
+    m->time = time;
+    reset_cursor(m);
+  }
+  if (pars) {
+    const int np = m->desc->n_par;
+    m->pars_host.assign(v.n_sets * mcb::kMaxPar, 0.0);
+    for (size_t p = 0; p < v.n_sets; ++p)
+      for (int k = 0; k < np; ++k) m->pars_host[p * mcb::kMaxPar + k] = pars[p * np + k];
+    // pageable source: the runtime stages it before returning, so pars_host may change
+    MCB_CUDA(cudaMemcpyAsync(m->d_pars, m->pars_host.data(),
+                             m->pars_host.size() * sizeof(double), cudaMemcpyHostToDevice,
+                             m->stream));
+    if (set_initial_state && !state) set_initial(m);
+  }
+  if (state) {
+    MCB_TRY(ensure_stage(m, state_len * sizeof(double)));
+    MCB_CUDA(cudaMemcpyAsync(m->d_stage, state, state_len * sizeof(double),
+                             cudaMemcpyHostToDevice, m->stream));
+    mcb::k_unpack_state<<<blocks_for(v.n_total, 256), 256, 0, m->stream>>>(
+        m->d_stage, state_len == (size_t)v.n_state, v.n_state, v.ld, v.n_total, v.y);
+    ++m->launches;
+    MCB_CUDA(cudaStreamSynchronize(m->stream));
+  }
+  MCB_CUDA(cudaGetLastError());
+  return MCB_OK;
+}
+
+int mcb_reorder(mcb_model *m, const int *kappa) {
+  if (!m || !kappa) return fail(MCB_ERR_ARG, "NULL argument");
+  MCB_CUDA(cudaSetDevice(m->device));
+  View &v = m->v;
+  for (size_t i = 0; i < v.n_total; ++i)
+    if (kappa[i] < 1 || (size_t)kappa[i] > v.n_particles)
+      return fail(MCB_ERR_ARG, "'index' must be in [1, n_particles]");
+  MCB_CUDA(cudaMemcpyAsync(m->d_kappa, kappa, v.n_total * sizeof(int), cudaMemcpyHostToDevice,
+                           m->stream));
+  mcb::k_gather_by_kappa<<<blocks_for(v.n_total, 256), 256, 0, m->stream>>>(v, m->d_kappa);
+  ++m->launches;
+  MCB_CUDA(cudaMemcpyAsync(v.y, v.y_tmp, (size_t)v.n_state * v.ld * sizeof(double),
+                           cudaMemcpyDeviceToDevice, m->stream));
+  MCB_CUDA(cudaStreamSynchronize(m->stream));
+  return MCB_OK;
+}
+
+int mcb_rng_state(mcb_model *m, int first_only, uint64_t *out) {
+  if (!m || !out) return fail(MCB_ERR_ARG, "NULL argument");
+  MCB_CUDA(cudaSetDevice(m->device));
+  const View &v = m->v;
+  const size_t n = first_only ? 1 : v.n_total + 1;
+  std::vector<uint64_t> soa(4 * n);
+  MCB_CUDA(cudaStreamSynchronize(m->stream));
+  for (int w = 0; w < 4; ++w)
+    MCB_CUDA(cudaMemcpy(soa.data() + w * n, v.rng + w * v.ld_rng, n * sizeof(uint64_t),
+                        cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < n; ++i)
+    for (int w = 0; w < 4; ++w) out[4 * i + w] = soa[w * n + i];
+  return MCB_OK;
+}
+
+int mcb_set_rng_state(mcb_model *m, const uint64_t *state, size_t n_words) {
+  if (!m || !state) return fail(MCB_ERR_ARG, "NULL argument");
+  MCB_CUDA(cudaSetDevice(m->device));
+  const View &v = m->v;
+  const size_t n = v.n_total + 1;
+  if (n_words != 4 * n)
+    return fail(MCB_ERR_ARG, "'rng_state' must hold 32 bytes for each of n_particles + 1 streams");
+  std::vector<uint64_t> soa(4 * n);
+  for (size_t i = 0; i < n; ++i)
+    for (int w = 0; w < 4; ++w) soa[w * n + i] = state[4 * i + w];
+  MCB_CUDA(cudaStreamSynchronize(m->stream));
+  for (int w = 0; w < 4; ++w)
+    MCB_CUDA(cudaMemcpy(v.rng + w * v.ld_rng, soa.data() + w * n, n * sizeof(uint64_t),
+                        cudaMemcpyHostToDevice));
+  return MCB_OK;
+}
+
+int mcb_set_data(mcb_model *m, size_t n_data, const uint64_t *time_end, const double *values,
+                 int shared) {
+  if (!m || !time_end || !values) return fail(MCB_ERR_ARG, "NULL argument");
+  if (n_data == 0) return fail(MCB_ERR_ARG, "data must have at least one row");
+  MCB_CUDA(cudaSetDevice(m->device));
+  View &v = m->v;
+  for (size_t i = 1; i < n_data; ++i)
+    if (time_end[i] <= time_end[i - 1]) return fail(MCB_ERR_ARG, "data times must be increasing");
+  MCB_CUDA(cudaStreamSynchronize(m->stream));
+  clear_graphs(m);
+  const size_t sets = shared ? 1 : v.n_sets;
+  std::vector<double> packed(n_data * sets * 2);
+  m->row_all_na.assign(n_data, 1);
+  for (size_t r = 0; r < n_data; ++r)
+    for (size_t s = 0; s < sets; ++s) {
+      const double x = values[r * sets + s];
+      packed[(r * sets + s) * 2] = x;
+      // lgamma(x + 1) depends on the datum only: once here, never per particle
+      packed[(r * sets + s) * 2 + 1] = std::isnan(x) ? NAN : std::lgamma(x + 1.0);
+      if (!std::isnan(x)) m->row_all_na[r] = 0;
+    }
+  void *old[] = {m->d_data, m->d_u, m->d_fs_after, m->d_wmax};
+  for (void *p : old)
+    if (p) cudaFree(p);
+  m->d_data = nullptr; m->d_u = nullptr; m->d_fs_after = nullptr; m->d_wmax = nullptr;
+  MCB_CUDA(cudaMalloc(&m->d_data, packed.size() * sizeof(double)));
+  MCB_CUDA(cudaMalloc(&m->d_u, n_data * v.n_sets * sizeof(double)));
+  MCB_CUDA(cudaMalloc(&m->d_fs_after, n_data * 4 * sizeof(uint64_t)));
+  MCB_CUDA(cudaMalloc(&m->d_wmax, n_data * v.n_sets * sizeof(unsigned long long)));
+  MCB_CUDA(cudaMemcpy(m->d_data, packed.data(), packed.size() * sizeof(double),
+                      cudaMemcpyHostToDevice));
+  v.data = m->d_data;
+  v.data_sets = (int)sets;
+  v.u_draws = m->d_u;
+  v.wmax = m->d_wmax;
+  m->n_data = n_data;
+  m->data_time.assign(time_end, time_end + n_data);
+  reset_cursor(m);
+  return MCB_OK;
+}
+
+int mcb_compare_data(mcb_model *m, double *logw, int *has_data) {
+  if (!m || !logw || !has_data) return fail(MCB_ERR_ARG, "NULL argument");
+  MCB_CUDA(cudaSetDevice(m->device));
+  View &v = m->v;
+  *has_data = 0;
+  int row = -1;
+  for (size_t r = 0; r < m->n_data; ++r)
+    if (m->data_time[r] == m->time) row = (int)r;
+  if (row < 0 || m->row_all_na[row]) return MCB_OK;
+  MCB_CUDA(cudaMemsetAsync(v.logw, 0, v.n_total * sizeof(double), m->stream));
+  MCB_CUDA(cudaMemsetAsync(m->d_flags, 0, 2 * sizeof(int), m->stream));
+  run_compare(m, v.y, v.y, m->time, 0, row, nullptr);
+  MCB_CUDA(cudaMemcpyAsync(logw, v.logw, v.n_total * sizeof(double), cudaMemcpyDeviceToHost,
+                           m->stream));
+  MCB_CUDA(cudaStreamSynchronize(m->stream));
+  *has_data = 1;
+  return MCB_OK;
+}
+
+int mcb_resample(mcb_model *m, const double *weights, int *kappa) {
+  if (!m || !weights || !kappa) return fail(MCB_ERR_ARG, "NULL argument");
+  MCB_CUDA(cudaSetDevice(m->device));
+  View &v = m->v;
+  for (size_t i = 0; i < v.n_total; ++i)
+    if (!(weights[i] >= 0.0 && weights[i] <= 1.0))
+      return fail(MCB_ERR_ARG, "'weights' must lie in [0, 1] (exp(log_weight - max))");
+  MCB_CUDA(cudaMemsetAsync(m->d_flags, 0, 2 * sizeof(int), m->stream));
+  MCB_CUDA(cudaMemcpyAsync(v.logw, weights, v.n_total * sizeof(double), cudaMemcpyHostToDevice,
+                           m->stream));
+  draw_uniforms(m, -1, 0);
+  mcb::k_tile_weights<true><<<(unsigned)(v.n_sets * v.tiles_per_set), mcb::kTileThreads, 0,
+                              m->stream>>>(v, -1);
+  mcb::k_finalize_row<<<1, 1024, 0, m->stream>>>(v, -1);
+  m->launches += 2;
+  MCB_CUDA(cudaMemcpyAsync(v.y_tmp, v.y, (size_t)v.n_state * v.ld * sizeof(double),
+                           cudaMemcpyDeviceToDevice, m->stream));
+  resample_gather(m, -1, m->d_kappa);
+  std::vector<int> k0(v.n_total);
+  MCB_CUDA(cudaMemcpyAsync(k0.data(), m->d_kappa, v.n_total * sizeof(int), cudaMemcpyDeviceToHost,
+                           m->stream));
+  MCB_CUDA(cudaStreamSynchronize(m->stream));
+  for (size_t i = 0; i < v.n_total; ++i)
+    kappa[i] = k0[i] - (int)((i / v.n_particles) * v.n_particles) + 1;
+  return MCB_OK;
+}
+
+int mcb_filter_rows(const mcb_model *m, uint64_t time_end, size_t *n_rows) {
+  if (!m || !n_rows) return fail(MCB_ERR_ARG, "NULL argument");
+  int first, last;
+  filter_rows_range(m, time_end, &first, &last);
+  *n_rows = (size_t)(last - first);
+  return MCB_OK;
+}
+
+int mcb_filter(mcb_model *m, uint64_t time_end, int save_trajectories,
+               const uint64_t *snapshot_times, size_t n_snapshots,
+               const double *min_log_likelihood, size_t n_min, double *log_likelihood,
+               double *trajectories, double *snapshots) {
+  if (!m || !log_likelihood) return fail(MCB_ERR_ARG, "NULL argument");
+  if (save_trajectories && !trajectories) return fail(MCB_ERR_ARG, "trajectories is NULL");
+  if (n_snapshots && (!snapshot_times || !snapshots)) return fail(MCB_ERR_ARG, "snapshots is NULL");
+  MCB_CUDA(cudaSetDevice(m->device));
+  return run_filter(m, time_end, save_trajectories != 0, snapshot_times, n_snapshots,
+                    min_log_likelihood, n_min, true, log_likelihood, trajectories, snapshots);
+}
+
+int mcb_filter_enqueue(mcb_model *m, uint64_t time_end) {
+  if (!m) return fail(MCB_ERR_ARG, "model is NULL");
+  MCB_CUDA(cudaSetDevice(m->device));
+  return run_filter(m, time_end, false, nullptr, 0, nullptr, 0, false, nullptr, nullptr, nullptr);
+}
+
+int mcb_filter_collect(mcb_model *m, double *log_likelihood) {
+  if (!m) return fail(MCB_ERR_ARG, "model is NULL");
+  if (!m->pending) return fail(MCB_ERR_STATE, "no filter enqueued");
+  MCB_CUDA(cudaSetDevice(m->device));
+  m->pending = false;
+  MCB_CUDA(cudaStreamSynchronize(m->stream));
+  MCB_CUDA(cudaGetLastError());
+  const bool stopped = m->h_flags[0] != 0;
+  const int last_row = stopped ? m->h_flags[1] : m->pend_last - 1;
+  if (m->timing && !stopped) {
+    for (int row = m->pend_first; row < m->pend_last; ++row) {
+      if (m->row_all_na[row] || m->events.size() < (size_t)(row + 1) * 5) continue;
+      for (int k = 0; k < 4; ++k) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, m->events[(size_t)row * 5 + k],
+                                 m->events[(size_t)row * 5 + k + 1]) == cudaSuccess) {
+          m->kernel_ms[k] += ms;
+          ++m->kernel_n[k];
+        }
+      }
+    }
+  }
+  if (last_row >= m->pend_first) {
+    m->time = m->data_time[last_row];
+    m->data_cursor = (size_t)last_row + 1;
+  }
+  if (log_likelihood)
+    std::memcpy(log_likelihood, m->h_ll, m->v.n_sets * sizeof(double));
+  return MCB_OK;
+}
+
+int mcb_set_kernel_timing(mcb_model *m, int enable) {
+  if (!m) return fail(MCB_ERR_ARG, "model is NULL");
+  m->timing = enable != 0;
+  for (int k = 0; k < 4; ++k) { m->kernel_ms[k] = 0; m->kernel_n[k] = 0; }
+  return MCB_OK;
+}
+
+int mcb_kernel_timing(mcb_model *m, double ms[4], uint64_t launches[4]) {
+  if (!m || !ms || !launches) return fail(MCB_ERR_ARG, "NULL argument");
+  for (int k = 0; k < 4; ++k) {
+    ms[k] = m->kernel_ms[k];
+    launches[k] = m->kernel_n[k];
+    m->kernel_ms[k] = 0;
+    m->kernel_n[k] = 0;
+  }
+  return MCB_OK;
+}
+
+int mcb_launch_count(const mcb_model *m, uint64_t *n) {
+  if (!m || !n) return fail(MCB_ERR_ARG, "NULL argument");
+  *n = m->launches;
+  return MCB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,92 @@
+// Reproducible fp64 exp / log for the model and weight kernels.
+//
+// The reference asserts that its CPU and GPU back ends return bit-identical
+// log-likelihoods (tests/testthat/test-particle-filter.R:1480-1504).  CUDA's
+// exp()/log() and a host libm differ in the last place now and then, so these
+// two functions use nothing but IEEE add/mul/div, explicit fma and integer
+// ops: any IEEE machine computing the same sequence gets the same bits.  The
+// file is compiled with -fmad=false, so a fused multiply-add happens only
+// where fma() is written.  Both are within 1 ulp of the correctly rounded
+// result.
+#pragma once
+#include <cstdint>
+
+namespace mcb {
+
+__device__ __forceinline__ double bits_to_double(uint64_t u) { return __longlong_as_double((long long)u); }
+__device__ __forceinline__ uint64_t double_to_bits(double x) { return (uint64_t)__double_as_longlong(x); }
+
+// exp(x): k = rint(x / ln 2); Cody-Waite reduction r = x - k ln2 with ln2 split
+// in two doubles (the fma keeps k*ln2_hi exact); degree-13 Taylor polynomial on
+// |r| <= ln2/2 (truncation < 5e-18); scaling by 2^k in two steps so a
+// subnormal result is rounded once.
+__device__ __forceinline__ double det_exp(double x) {
+  if (x != x) return x;
+  if (x > 709.782712893384) return __longlong_as_double(0x7ff0000000000000LL);
+  if (x < -745.1332191019412) return 0.0;
+  const double kd = rint(x * 1.4426950408889634074);
+  double r = fma(-kd, 6.93147180559945286e-01, x);
+  r = fma(-kd, 2.31904681384629956e-17, r);
+  double p = 1.6059043836821613e-10;
+  p = fma(p, r, 2.08767569878681e-09);
+  p = fma(p, r, 2.505210838544172e-08);
+  p = fma(p, r, 2.755731922398589e-07);
+  p = fma(p, r, 2.7557319223985893e-06);
+  p = fma(p, r, 2.48015873015873e-05);
+  p = fma(p, r, 1.984126984126984e-04);
+  p = fma(p, r, 1.388888888888889e-03);
+  p = fma(p, r, 8.333333333333333e-03);
+  p = fma(p, r, 4.1666666666666664e-02);
+  p = fma(p, r, 1.6666666666666666e-01);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const int k = (int)kd;
+  const int k1 = k >> 1, k2 = k - k1;
+  const double s1 = bits_to_double((uint64_t)(1023 + k1) << 52);
+  const double s2 = bits_to_double((uint64_t)(1023 + k2) << 52);
+  return (p * s1) * s2;
+}
+
+// log(x): x = 2^k m with m in [sqrt(1/2), sqrt(2)); f = m - 1, s = f/(2+f);
+// log(1+f) = f - f^2/2 + s (f^2/2 + R(s^2)) with the classic 7-term minimax R;
+// ln2 is split so k*ln2_hi is exact.
+__device__ __forceinline__ double det_log(double x) {
+  uint64_t ix = double_to_bits(x);
+  uint32_t hx = (uint32_t)(ix >> 32);
+  int k = 0;
+  if (hx < 0x00100000u || (hx >> 31)) {
+    if ((ix << 1) == 0) return __longlong_as_double(0xfff0000000000000LL);
+    if (hx >> 31) return __longlong_as_double(0x7ff8000000000000LL);
+    k -= 54;
+    x *= 0x1p54;
+    ix = double_to_bits(x);
+    hx = (uint32_t)(ix >> 32);
+  } else if (hx >= 0x7ff00000u) {
+    return x;
+  } else if (hx == 0x3ff00000u && (ix << 32) == 0) {
+    return 0.0;
+  }
+  hx += 0x3ff00000u - 0x3fe6a09eu;
+  k += (int)(hx >> 20) - 0x3ff;
+  hx = (hx & 0x000fffffu) + 0x3fe6a09eu;
+  x = bits_to_double(((uint64_t)hx << 32) | (ix & 0xffffffffULL));
+
+  const double f = x - 1.0;
+  const double hfsq = 0.5 * f * f;
+  const double s = f / (2.0 + f);
+  const double z = s * s;
+  const double w = z * z;
+  const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01),
+                            3.999999999940941908e-01);
+  const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01,
+                                          1.818357216161805012e-01),
+                                   2.857142874366239149e-01),
+                            6.666666666666735130e-01);
+  const double R = t2 + t1;
+  const double dk = (double)k;
+  return s * (hfsq + R) + dk * 1.90821492927058770002e-10 - hfsq + f +
+         dk * 6.93147180369123816490e-01;
+}
+
+}  // namespace mcb

@@ -1,0 +1,495 @@
+// The per-interval kernels of the compiled particle filter
+// (model$filter, R/particle_filter_state.R:151; per-interval order as
+// R/particle_filter_state.R:63-117).
+//
+//   K1  k_run_compare      run `rate` model steps + compare  -> state', rng', logw, max
+//   K2  k_tile_weights     w = exp(logw - max) as fixed point; per-tile inclusive scan
+//   K2b k_finalize_row     tile prefix, log-mean-exp -> ll, resampling thresholds, early exit
+//   K3+K4 k_resample_gather  systematic-resampling index by binary search + state gather
+//
+// Data layout (HBM): state is SoA [n_state][ld] fp64, RNG is SoA [4][ld_rng]
+// u64, both with ld a multiple of 32 so every row starts 256-byte aligned and a
+// warp's access to one row is one contiguous 256-byte segment.
+// The post-update state is written to a second buffer (`y_tmp`) and the gather
+// brings it back into `y`, so the live state is always in `y` and the launch
+// sequence has no pointer flip -- it replays unchanged as a CUDA graph.
+//
+// Weights are summed as fixed-point integers (scale_log_weights:
+// R/particle_filter.R:570-587; resample_weight: SURVEY.md R2b).  Integer
+// addition is associative, so the tiled parallel scan gives the same
+// cumulative sums as a serial loop and the chosen ancestors do not depend on
+// tile size, SM count or scheduling.
+#pragma once
+#include <cstdint>
+
+#include "models.cuh"
+
+namespace mcb {
+
+constexpr int kRunThreads = 128;
+constexpr int kTile = 1024;         // particles per weight tile
+constexpr int kTileThreads = 256;   // 4 consecutive particles per thread
+constexpr int kGatherThreads = 256;
+
+struct SetInfo {   // per parameter set, rewritten every interval by K2b
+  double uu0, du;  // threshold_i = uu0 + i * du   (fixed-point units)
+};
+
+struct View {
+  double *y;          // [n_state][ld]   live state
+  double *y_tmp;      // [n_state][ld]   post-update, pre-resample
+  uint64_t *rng;      // [4][ld_rng]     stream n_total is the filter's
+  const double *pars; // [n_sets][kMaxPar]
+  const double *data; // [n_data][data_sets][2] = {value, lgamma(value+1)}
+  double *logw;       // [n_total]
+  unsigned long long *cw;        // [n_total] inclusive fixed-point cumsum inside a tile
+  unsigned long long *tile_incl; // [n_sets][tiles_per_set] tile sums, then inclusive prefix
+  unsigned long long *wmax;      // [n_data][n_sets] order-preserving key of max logw
+  const double *u_draws;         // [n_data][n_sets] resampling uniforms (filter stream)
+  SetInfo *setinfo;   // [n_sets]
+  double *ll;         // [n_sets] accumulated log-likelihood of this filter call
+  const double *min_ll; // [n_min]
+  int *flags;         // [0] stopped, [1] stop row
+  const int *index;   // [n_index] rows returned by run()/saved in trajectories
+  size_t n_particles, n_sets, n_total, ld, ld_rng;
+  int n_state, n_index, n_min, data_sets, tiles_per_set, shift, deterministic;
+};
+
+// ---- order-preserving map double -> u64 so max is one integer atomic --------
+__device__ __forceinline__ unsigned long long key_of(double x) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+}
+__device__ __forceinline__ double key_to_double(unsigned long long k) {
+  // key 0 (never written) decodes as -inf: a set nobody weighted is dead
+  if (k == 0) return __longlong_as_double(0xfff0000000000000LL);
+  const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffULL) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
+__device__ __forceinline__ bool datum_is_na(const View &v, int row, size_t set) {
+  const size_t ds = v.data_sets == 1 ? 0 : set;
+  const double x = __ldg(v.data + ((size_t)row * v.data_sets + ds) * 2);
+  return x != x;
+}
+
+__device__ __forceinline__ unsigned long long shfl_u64(unsigned long long x, int src) {
+  return __shfl_sync(0xffffffffu, x, src);
+}
+__device__ __forceinline__ unsigned long long shfl_up_u64(unsigned long long x, int d) {
+  return __shfl_up_sync(0xffffffffu, x, d);
+}
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long x, int m) {
+  return __shfl_xor_sync(0xffffffffu, x, m);
+}
+
+// ---------------------------------------------------------------------------
+// K1: one thread per particle.  State (kState doubles) and the generator
+// (4 words) stay in registers for all n_steps updates and the compare; every
+// global access is a coalesced row access.  row < 0: no compare (model$run).
+// ---------------------------------------------------------------------------
+template <class M, int SCR, bool HIST>
+__global__ void __launch_bounds__(kRunThreads)
+k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_out,
+              uint64_t t0, uint32_t n_steps, int row, double *__restrict__ hist) {
+  __shared__ unsigned long long s_key[kRunThreads / 32];
+  if (v.flags[0]) return;
+  const size_t i = (size_t)blockIdx.x * kRunThreads + threadIdx.x;
+  const bool live = i < v.n_total;
+  const size_t ii = live ? i : v.n_total - 1;
+  const size_t set = v.n_sets == 1 ? 0 : ii / v.n_particles;
+  const double *pars = v.pars + set * kMaxPar;
+  const typename M::Ctx ctx = M::context(pars);
+  const bool det = v.deterministic != 0;
+
+  double y[M::kState];
+  Xoshiro rng;
+  unsigned long long key = 0;
+  bool weighted = false;
+  if (live) {
+#pragma unroll
+    for (int s = 0; s < M::kState; ++s) y[s] = y_in[(size_t)s * v.ld + i];
+    rng.s0 = v.rng[0 * v.ld_rng + i];
+    rng.s1 = v.rng[1 * v.ld_rng + i];
+    rng.s2 = v.rng[2 * v.ld_rng + i];
+    rng.s3 = v.rng[3 * v.ld_rng + i];
+
+    for (uint32_t k = 0; k < n_steps; ++k) M::template update<SCR>(t0 + k, y, rng, ctx, det);
+
+    if (n_steps > 0 || y_in != y_out) {
+#pragma unroll
+      for (int s = 0; s < M::kState; ++s) y_out[(size_t)s * v.ld + i] = y[s];
+    }
+    if (HIST) {
+      for (int k = 0; k < v.n_index; ++k) {
+        const int s = v.index[k];
+        double val = y[0];
+#pragma unroll
+        for (int q = 1; q < M::kState; ++q) val = (s == q) ? y[q] : val;
+        hist[(size_t)k * v.ld + i] = val;
+      }
+    }
+    if (row >= 0 && !datum_is_na(v, row, set)) {
+      const size_t ds = v.data_sets == 1 ? 0 : set;
+      const double *d = v.data + ((size_t)row * v.data_sets + ds) * 2;
+      double lw = M::template compare<SCR>(y, __ldg(d), __ldg(d + 1), rng, ctx, det);
+      if (lw != lw) lw = __longlong_as_double(0xfff0000000000000LL);  // NaN -> -Inf
+      v.logw[i] = lw;
+      key = key_of(lw);
+      weighted = true;
+    }
+    if (n_steps > 0 || weighted) {
+      v.rng[0 * v.ld_rng + i] = rng.s0;
+      v.rng[1 * v.ld_rng + i] = rng.s1;
+      v.rng[2 * v.ld_rng + i] = rng.s2;
+      v.rng[3 * v.ld_rng + i] = rng.s3;
+    }
+  }
+  if (row < 0) return;
+
+  // max of logw per parameter set: block reduce when the block sits inside
+  // one set (the common case), else one atomic per weighted thread
+  const size_t first = (size_t)blockIdx.x * kRunThreads;
+  size_t last = first + kRunThreads - 1;
+  if (last >= v.n_total) last = v.n_total - 1;
+  const bool one_set = v.n_sets == 1 || (first / v.n_particles == last / v.n_particles);
+  unsigned long long *slot = v.wmax + (size_t)row * v.n_sets;
+  if (one_set) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+      const unsigned long long o = shfl_xor_u64(key, m);
+      key = o > key ? o : key;
+    }
+    if ((threadIdx.x & 31) == 0) s_key[threadIdx.x >> 5] = key;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int w = 1; w < kRunThreads / 32; ++w) key = s_key[w] > key ? s_key[w] : key;
+      if (key) atomicMax(slot + first / v.n_particles, key);
+    }
+  } else if (weighted) {
+    atomicMax(slot + set, key);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K2: per tile of kTile particles (tiles never straddle a parameter set):
+// w = exp(logw - max) -> fixed point, inclusive scan inside the tile.
+// GIVEN = true: `logw` already holds weights in [0,1] (model$resample(weights)).
+// ---------------------------------------------------------------------------
+template <bool GIVEN>
+__global__ void __launch_bounds__(kTileThreads) k_tile_weights(View v, int row) {
+  __shared__ unsigned long long s_warp[kTileThreads / 32];
+  if (v.flags[0]) return;
+  const size_t set = blockIdx.x / v.tiles_per_set;
+  const int tile = blockIdx.x % v.tiles_per_set;
+  if (!GIVEN && datum_is_na(v, row, set)) return;
+  double mx = 0.0;
+  if (!GIVEN) mx = key_to_double(v.wmax[(size_t)row * v.n_sets + set]);
+  const bool dead = !GIVEN && !(mx > __longlong_as_double(0xfff0000000000000LL));
+  const double scale = bits_to_double((uint64_t)(1023 + v.shift) << 52);
+
+  const size_t in_set = (size_t)tile * kTile + (size_t)threadIdx.x * 4;
+  const size_t base = set * v.n_particles + in_set;
+  unsigned long long q[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    q[j] = 0;
+    if (in_set + j < v.n_particles && !dead) {
+      const double lw = v.logw[base + j];
+      const double w = GIVEN ? lw : det_exp(lw - mx);
+      q[j] = (unsigned long long)__double2ll_rn(w * scale);
+    }
+  }
+  q[1] += q[0]; q[2] += q[1]; q[3] += q[2];
+  unsigned long long incl = q[3];
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long o = shfl_up_u64(incl, d);
+    if ((threadIdx.x & 31) >= d) incl += o;
+  }
+  if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  unsigned long long offset = incl - q[3];
+  unsigned long long total = 0;
+#pragma unroll
+  for (int w = 0; w < kTileThreads / 32; ++w) {
+    if (w < (int)(threadIdx.x >> 5)) offset += s_warp[w];
+    total += s_warp[w];
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (in_set + j < v.n_particles) v.cw[base + j] = q[j] + offset;
+  if (threadIdx.x == 0) v.tile_incl[blockIdx.x] = total;
+}
+
+// ---------------------------------------------------------------------------
+// K2b: one block.  Warp w owns sets w, w+32, ...: inclusive prefix over the
+// set's tile sums, log-mean-exp into ll, thresholds for K3.  Then thread 0
+// applies the early-exit rule of R/particle_filter_state.R:463-474.
+// row < 0: model$resample(weights) -- thresholds only, u taken from u_draws[0..].
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_finalize_row(View v, int row) {
+  __shared__ int s_dead;
+  if (v.flags[0]) return;
+  if (threadIdx.x == 0) s_dead = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int T = v.tiles_per_set;
+  const int chunk = (T + 31) / 32;
+  for (size_t set = warp; set < v.n_sets; set += 32) {
+    if (row >= 0 && datum_is_na(v, row, set)) continue;
+    unsigned long long *ts = v.tile_incl + set * T;
+    const int lo = lane * chunk, hi = min(T, lo + chunk);
+    unsigned long long local = 0;
+    for (int t = lo; t < hi; ++t) local += ts[t];
+    unsigned long long incl = local;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long o = shfl_up_u64(incl, d);
+      if (lane >= d) incl += o;
+    }
+    unsigned long long run = incl - local;
+    for (int t = lo; t < hi; ++t) { run += ts[t]; ts[t] = run; }
+    const unsigned long long tot = shfl_u64(incl, 31);
+    if (lane == 0) {
+      const double n = (double)v.n_particles;
+      const double tot_d = (double)tot;
+      const double u = v.u_draws[(size_t)(row < 0 ? 0 : row) * v.n_sets + set];
+      SetInfo si;
+      si.uu0 = tot_d * u / n;
+      si.du = tot_d / n;
+      v.setinfo[set] = si;
+      if (row >= 0) {
+        const double mx = key_to_double(v.wmax[(size_t)row * v.n_sets + set]);
+        if (!(mx > __longlong_as_double(0xfff0000000000000LL)) || tot == 0) {
+          v.ll[set] = __longlong_as_double(0xfff0000000000000LL);
+          atomicExch(&s_dead, 1);
+        } else {
+          const double mean = (tot_d * bits_to_double((uint64_t)(1023 - v.shift) << 52)) / n;
+          v.ll[set] += det_log(mean) + mx;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && row >= 0) {
+    bool stop = s_dead != 0;
+    if (!stop && v.n_min > 0) {
+      if (v.n_sets == 1) {
+        stop = v.ll[0] < v.min_ll[0];
+      } else if (v.n_min == 1) {
+        double tot = 0.0;
+        for (size_t p = 0; p < v.n_sets; ++p) tot += v.ll[p];
+        stop = tot < v.min_ll[0];
+      } else {
+        stop = true;
+        for (size_t p = 0; p < v.n_sets; ++p) stop = stop && (v.ll[p] < v.min_ll[p]);
+      }
+    }
+    if (stop) {
+      for (size_t p = 0; p < v.n_sets; ++p) v.ll[p] = __longlong_as_double(0xfff0000000000000LL);
+      v.flags[1] = row;
+      __threadfence();
+      v.flags[0] = 1;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K3+K4: thread i owns output slot i.  Its threshold ceil(uu0 + i du) is
+// compared exactly (integers) with the cumulative weights: binary search over
+// the set's tile prefix, then inside the tile.  Thresholds increase with i, so
+// neighbouring threads search neighbouring addresses and the gather reads are
+// near-coalesced (kappa is monotone).  kappa is written only when trajectories
+// are being saved.
+// ---------------------------------------------------------------------------
+template <int NS>
+__global__ void __launch_bounds__(kGatherThreads)
+k_resample_gather(View v, int row, int *__restrict__ kappa_out) {
+  if (v.flags[0]) return;
+  const size_t i = (size_t)blockIdx.x * kGatherThreads + threadIdx.x;
+  if (i >= v.n_total) return;
+  const size_t set = v.n_sets == 1 ? 0 : i / v.n_particles;
+  const size_t il = i - set * v.n_particles;
+  size_t src = i;
+  if (row < 0 || !datum_is_na(v, row, set)) {
+    const SetInfo si = v.setinfo[set];
+    const unsigned long long thr =
+        (unsigned long long)__double2ll_ru(si.uu0 + (double)il * si.du);
+    const unsigned long long *ts = v.tile_incl + set * v.tiles_per_set;
+    int lo = 0, hi = v.tiles_per_set - 1;  // first tile whose inclusive prefix reaches thr
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(ts + mid) >= thr) hi = mid; else lo = mid + 1;
+    }
+    const unsigned long long before = lo ? __ldg(ts + lo - 1) : 0ULL;
+    const unsigned long long rem = thr > before ? thr - before : 0ULL;
+    const size_t tile_base = (size_t)lo * kTile;
+    const size_t in_tile = min((size_t)kTile, v.n_particles - tile_base);
+    const unsigned long long *cw = v.cw + set * v.n_particles + tile_base;
+    int a = 0, b = (int)in_tile - 1;
+    while (a < b) {
+      const int mid = (a + b) >> 1;
+      if (__ldg(cw + mid) >= rem) b = mid; else a = mid + 1;
+    }
+    src = set * v.n_particles + tile_base + a;
+  }
+#pragma unroll
+  for (int s = 0; s < NS; ++s) v.y[(size_t)s * v.ld + i] = v.y_tmp[(size_t)s * v.ld + src];
+  if (kappa_out) kappa_out[i] = (int)src;
+}
+
+// ---- small kernels off the hot path ---------------------------------------
+
+// resampling uniforms for every pending (row, set) pair, drawn in order from
+// the filter stream (the last stream); the state after each row is kept so an
+// early stop can rewind to the draws that were really made.
+template <int SCR>
+__global__ void k_draw_uniforms(View v, int row_first, int row_last, double *u_draws,
+                                uint64_t *fs_after) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  Xoshiro r;
+  const size_t f = v.n_total;
+  r.s0 = v.rng[0 * v.ld_rng + f]; r.s1 = v.rng[1 * v.ld_rng + f];
+  r.s2 = v.rng[2 * v.ld_rng + f]; r.s3 = v.rng[3 * v.ld_rng + f];
+  for (int row = row_first; row < row_last; ++row) {
+    for (size_t p = 0; p < v.n_sets; ++p)
+      if (row_first < 0 || !datum_is_na(v, row, p))
+        u_draws[(size_t)(row < 0 ? 0 : row) * v.n_sets + p] = xo_real<SCR>(r);
+    if (row >= 0) {
+      fs_after[4 * row + 0] = r.s0; fs_after[4 * row + 1] = r.s1;
+      fs_after[4 * row + 2] = r.s2; fs_after[4 * row + 3] = r.s3;
+    }
+  }
+  if (row_first < 0) {  // model$resample(): consume the draws immediately
+    v.rng[0 * v.ld_rng + f] = r.s0; v.rng[1 * v.ld_rng + f] = r.s1;
+    v.rng[2 * v.ld_rng + f] = r.s2; v.rng[3 * v.ld_rng + f] = r.s3;
+  }
+}
+
+// end of a filter call: the filter stream advances past the draws of the rows
+// that were resampled (a stopped row was not: R breaks before particle_resample)
+__global__ void k_filter_finish(View v, int row_first, int row_last, const uint64_t *fs_after) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int done_last = v.flags[0] ? v.flags[1] - 1 : row_last - 1;
+  if (done_last < row_first) return;
+  const size_t f = v.n_total;
+  v.rng[0 * v.ld_rng + f] = fs_after[4 * done_last + 0];
+  v.rng[1 * v.ld_rng + f] = fs_after[4 * done_last + 1];
+  v.rng[2 * v.ld_rng + f] = fs_after[4 * done_last + 2];
+  v.rng[3 * v.ld_rng + f] = fs_after[4 * done_last + 3];
+}
+
+template <class M>
+__global__ void k_set_initial(View v) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= v.n_total) return;
+  const size_t set = v.n_sets == 1 ? 0 : i / v.n_particles;
+  double y[M::kState];
+  M::initial(v.pars + set * kMaxPar, y);
+#pragma unroll
+  for (int s = 0; s < M::kState; ++s) v.y[(size_t)s * v.ld + i] = y[s];
+}
+
+// SoA rows -> R layout [n_rows fastest][particle]; index == nullptr: all rows
+__global__ void k_pack_rows(const double *__restrict__ y, size_t ld, size_t n_total,
+                            const int *__restrict__ index, int n_rows, double *__restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_total) return;
+  for (int k = 0; k < n_rows; ++k) {
+    const int s = index ? index[k] : k;
+    out[i * n_rows + k] = y[(size_t)s * ld + i];
+  }
+}
+
+// R layout (n_state fastest) -> SoA; recycle = 1: one state vector for everyone
+__global__ void k_unpack_state(const double *__restrict__ in, int recycle, int n_state,
+                               size_t ld, size_t n_total, double *__restrict__ y) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_total) return;
+  for (int s = 0; s < n_state; ++s)
+    y[(size_t)s * ld + i] = in[(recycle ? 0 : i * n_state) + s];
+}
+
+// model$reorder(kappa): kappa 1-based within the set (as R passes it)
+__global__ void k_gather_by_kappa(View v, const int *__restrict__ kappa) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= v.n_total) return;
+  const size_t set = v.n_sets == 1 ? 0 : i / v.n_particles;
+  const size_t src = set * v.n_particles + (size_t)(kappa[i] - 1);
+  for (int s = 0; s < v.n_state; ++s) v.y_tmp[(size_t)s * v.ld + i] = v.y[(size_t)s * v.ld + src];
+}
+
+__global__ void k_copy_state_if_running(View v, double *__restrict__ dst) {
+  if (v.flags[0]) return;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= v.n_total) return;
+  for (int s = 0; s < v.n_state; ++s) dst[(size_t)s * v.ld + i] = v.y[(size_t)s * v.ld + i];
+}
+
+// a stopped filter leaves the post-run state of the stop row as the live state
+__global__ void k_adopt_tmp_if_stopped(View v) {
+  if (!v.flags[0]) return;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= v.n_total) return;
+  for (int s = 0; s < v.n_state; ++s) v.y[(size_t)s * v.ld + i] = v.y_tmp[(size_t)s * v.ld + i];
+}
+
+__global__ void k_iota(int *out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (int)i;
+}
+
+// ancestor tracing of the saved history, as history_single
+// (R/particle_filter.R:635-642): walk the order arrays back from the final
+// particles.  value [T1][n_index][ld], order [T1][n_total] (global, 0-based),
+// out in R layout [n_index fastest][particle][time].
+__global__ void k_trace_history(View v, const double *__restrict__ value,
+                                const int *__restrict__ order, int rows, int row_first,
+                                double *__restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= v.n_total) return;
+  const int T1 = rows + 1;
+  const bool stopped = v.flags[0] != 0;
+  const int filled = stopped ? (v.flags[1] - row_first) + 2 : T1;
+  const double na = __longlong_as_double(0x7ff8000000000000LL);
+  size_t cur = i;
+  for (int t = T1 - 1; t >= 0; --t) {
+    double *o = out + ((size_t)t * v.n_total + i) * v.n_index;
+    if (t >= filled) {
+      for (int k = 0; k < v.n_index; ++k) o[k] = na;
+      continue;
+    }
+    if (!(stopped && t == filled - 1)) cur = (size_t)order[(size_t)t * v.n_total + cur];
+    for (int k = 0; k < v.n_index; ++k)
+      o[k] = value[((size_t)t * v.n_index + k) * v.ld + cur];
+  }
+}
+
+// stream i (i >= have) = J^(i - have + 1) applied to stream have-1, by the
+// precomputed powers J^(2^l) (rng.cuh).  The column loads are warp-uniform.
+__global__ void k_derive_streams(uint64_t *rng, size_t ld_rng, size_t have, size_t n_streams,
+                                 const uint64_t *__restrict__ jump_cols) {
+  const size_t i = have + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_streams) return;
+  uint64_t s[4];
+  for (int w = 0; w < 4; ++w) s[w] = rng[w * ld_rng + (have - 1)];
+  const uint64_t e = (uint64_t)(i - have + 1);
+  for (int l = 0; l < kJumpLevels; ++l) {
+    if (!((e >> l) & 1ULL)) continue;
+    const uint64_t *cols = jump_cols + (size_t)l * 256 * 4;
+    uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (int b = 0; b < 256; ++b) {
+      const uint64_t m = 0ULL - ((s[b >> 6] >> (b & 63)) & 1ULL);
+      a0 ^= m & __ldg(cols + b * 4 + 0);
+      a1 ^= m & __ldg(cols + b * 4 + 1);
+      a2 ^= m & __ldg(cols + b * 4 + 2);
+      a3 ^= m & __ldg(cols + b * 4 + 3);
+    }
+    s[0] = a0; s[1] = a1; s[2] = a2; s[3] = a3;
+  }
+  for (int w = 0; w < 4; ++w) rng[w * ld_rng + i] = s[w];
+}
+
+}  // namespace mcb

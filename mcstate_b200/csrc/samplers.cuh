@@ -1,0 +1,124 @@
+// Per-particle samplers and densities for the compartmental models.
+//
+// Algorithms are those of the reference's native dependency dust [SURVEY.md
+// A.2]: binomial by CDF inversion (n q < 10) or Hoermann's BTRS transformed
+// rejection, Poisson by Knuth's product (lambda < 10) or PTRS.  The number of
+// uniforms a draw consumes is data dependent, which is why every particle owns
+// a stream; the order of draws and of floating-point operations is part of the
+// contract (bit-exact against the oracle).
+#pragma once
+#include "detmath.cuh"
+#include "rng.cuh"
+
+namespace mcb {
+
+template <int SCR>
+__device__ __forceinline__ double draw_exponential(Xoshiro &r, double rate) {
+  return -det_log(xo_real<SCR>(r)) / rate;
+}
+
+// x^n by squaring, multiplying in the low bits first (not pow())
+__device__ __forceinline__ double pow_int(double x, int n) {
+  double acc = 1.0;
+  while (n != 0) {
+    if (n & 1) acc *= x;
+    n >>= 1;
+    if (n != 0) x *= x;
+  }
+  return acc;
+}
+
+template <int SCR>
+__device__ __forceinline__ double binomial_inversion(Xoshiro &rng, int n, double q) {
+  const double qq = 1.0 - q;
+  const double r = q / qq;
+  const double g = r * (double)(n + 1);
+  const double f0 = pow_int(qq, n);
+  for (;;) {
+    double u = xo_real<SCR>(rng);
+    double f = f0, f_prev = f0;
+    int k = 0;
+    bool ok = true;
+    while (u >= f) {
+      u -= f;
+      ++k;
+      f *= (g / (double)k - r);
+      if (f == f_prev || k > n) { ok = false; break; }
+      f_prev = f;
+    }
+    if (ok) return (double)k;
+  }
+}
+
+__device__ __forceinline__ double stirling_tail(double k) {
+  // table for k <= 9 held as immediates (no local-memory array)
+  if (k <= 9.0) {
+    const int i = (int)k;
+    double t = 0.0810614667953272;
+    t = i == 1 ? 0.0413406959554092 : t;
+    t = i == 2 ? 0.0276779256849983 : t;
+    t = i == 3 ? 0.02079067210376509 : t;
+    t = i == 4 ? 0.0166446911898211 : t;
+    t = i == 5 ? 0.0138761288230707 : t;
+    t = i == 6 ? 0.0118967099458917 : t;
+    t = i == 7 ? 0.0104112652619720 : t;
+    t = i == 8 ? 0.00925546218271273 : t;
+    t = i == 9 ? 0.00833056343336287 : t;
+    return t;
+  }
+  const double kp1sq = (k + 1.0) * (k + 1.0);
+  return (1.0 / 12.0 - (1.0 / 360.0 - 1.0 / 1260.0 / kp1sq) / kp1sq) / (k + 1.0);
+}
+
+template <int SCR>
+__device__ __forceinline__ double binomial_btrs(Xoshiro &rng, double n, double q) {
+  const double sd = sqrt(n * q * (1.0 - q));
+  const double b = 1.15 + 2.53 * sd;
+  const double a = -0.0873 + 0.0248 * b + 0.01 * q;
+  const double c = n * q + 0.5;
+  const double v_r = 0.92 - 4.2 / b;
+  const double r = q / (1.0 - q);
+  const double alpha = (2.83 + 5.1 / b) * sd;
+  const double m = floor((n + 1.0) * q);
+  for (;;) {
+    double u = xo_real<SCR>(rng);
+    double v = xo_real<SCR>(rng);
+    u -= 0.5;
+    const double us = 0.5 - fabs(u);
+    const double k = floor((2.0 * a / us + b) * u + c);
+    if (us >= 0.07 && v <= v_r) return k;
+    if (k < 0.0 || k > n) continue;
+    v = det_log(v * alpha / (a / (us * us) + b));
+    const double bound =
+        (m + 0.5) * det_log((m + 1.0) / (r * (n - m + 1.0))) +
+        (n + 1.0) * det_log((n - m + 1.0) / (n - k + 1.0)) +
+        (k + 0.5) * det_log(r * (n - k + 1.0) / (k + 1.0)) +
+        stirling_tail(m) + stirling_tail(n - m) - stirling_tail(k) -
+        stirling_tail(n - k);
+    if (v <= bound) return k;
+  }
+}
+
+// deterministic = true replaces the draw by its mean (dust deterministic mode,
+// R/deterministic_state.R:190-203)
+template <int SCR>
+__device__ __forceinline__ double draw_binomial(Xoshiro &rng, bool deterministic, double n,
+                                                double p) {
+  if (deterministic) return n * p;
+  if (n == 0.0 || p == 0.0) return 0.0;
+  if (p == 1.0) return n;
+  const double q = p > 0.5 ? 1.0 - p : p;
+  const double draw = (n * q >= 10.0) ? binomial_btrs<SCR>(rng, n, q)
+                                      : binomial_inversion<SCR>(rng, (int)n, q);
+  return p > 0.5 ? n - draw : draw;
+}
+
+// x log(lambda) - lambda - lgamma(x + 1); lgamma(x + 1) depends on the datum
+// only and is computed once per datum on the host (mcb_set_data).
+__device__ __forceinline__ double density_poisson_log(double x, double lgamma_x1,
+                                                      double lambda) {
+  if (x == 0.0 && lambda == 0.0) return 0.0;
+  return x * det_log(lambda) - lambda - lgamma_x1;
+}
+
+}  // namespace mcb

@@ -1,0 +1,518 @@
+"""The `dust_generator` model-object protocol on the B200 engine.
+
+mcstate talks to its native engine only through this object:
+``generator$new(...)`` then ``$run / $filter / $state / $reorder /
+$update_state / $set_index / $set_data / $rng_state / ...``.  This module is the
+Python twin of that R6 object: every method forwards to one C-ABI entry point
+of ``libmcstate_b200.so`` (include/mcstate_b200.h), which runs CUDA kernels.
+R is not available in the build image, so the host side is Python; the
+equivalent R6/.Call binding is in INTEGRATION.md.
+
+Arrays use R's dimension order: a state matrix is ``(n_state, n_particles)``
+or ``(n_state, n_particles, n_pars)``; indices passed to ``set_index`` /
+``state`` / ``reorder`` are 1-based, as R passes them.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, f64p, i32p, ptr, szp, u64p
+
+_ALGORITHMS = {"xoshiro256plus": _lib.SCRAMBLER_PLUS, "xoshiro256starstar": _lib.SCRAMBLER_STARSTAR}
+
+
+# --------------------------------------------------------------------------
+# dust::dust_rng and friends (host-side RNG-state arithmetic)
+# --------------------------------------------------------------------------
+def _seed_words(seed) -> np.ndarray:
+    """NULL / positive integer / raw vector of 32k bytes -> uint64 words
+    (R/particle_filter.R:199-204)."""
+    if seed is None:
+        seed = int(np.random.randint(1, 2 ** 31 - 1))
+    if isinstance(seed, (int, np.integer)):
+        if seed < 0:
+            raise ValueError("'seed' must be a positive integer")
+        s = np.zeros(4, dtype=np.uint64)
+        check(_lib.lib().mcb_rng_seed(C.c_uint64(int(seed)), ptr(s, u64p)))
+        return s
+    if isinstance(seed, (bytes, bytearray)):
+        raw = np.frombuffer(bytes(seed), dtype=np.uint8)
+    else:
+        raw = np.asarray(seed)
+        if raw.dtype == np.uint64:
+            raw = np.ascontiguousarray(raw).view(np.uint8)
+        raw = raw.astype(np.uint8, copy=False)
+    if raw.size == 0 or raw.size % 32 != 0:
+        raise ValueError("'seed' as a raw vector must have a length that is a multiple of 32")
+    return np.frombuffer(raw.tobytes(), dtype=np.uint64).copy()
+
+
+class dust_rng:
+    """``dust::dust_rng$new(seed)``: one host-side stream
+    (R/pmcmc_parallel.R:147-148 uses ``$long_jump()$random_real(1)``)."""
+
+    def __init__(self, seed=None, algorithm="xoshiro256plus"):
+        self._s = _seed_words(seed)[:4].copy()
+        self._alg = _ALGORITHMS[algorithm]
+
+    def jump(self):
+        check(_lib.lib().mcb_rng_jump(ptr(self._s, u64p)))
+        return self
+
+    def long_jump(self):
+        check(_lib.lib().mcb_rng_long_jump(ptr(self._s, u64p)))
+        return self
+
+    def random_real(self, n):
+        out = np.zeros(n)
+        check(_lib.lib().mcb_rng_random_real(ptr(self._s, u64p), self._alg, n, ptr(out, f64p)))
+        return out
+
+    def state(self) -> bytes:
+        return self._s.tobytes()
+
+
+def dust_rng_distributed_state(seed=None, n_streams=1, n_nodes=1, algorithm="xoshiro256plus"):
+    """``dust::dust_rng_distributed_state`` (R/pmcmc_parallel.R:133, R/smc2.R:68):
+    a list of raw states, node k long-jumped k times from the seed."""
+    base = _seed_words(seed)[:4].copy()
+    out = np.zeros((n_nodes, n_streams, 4), dtype=np.uint64)
+    check(_lib.lib().mcb_rng_distributed_state(ptr(base, u64p), n_streams, n_nodes, ptr(out, u64p)))
+    return [out[k].tobytes() for k in range(n_nodes)]
+
+
+def dust_data(data, name_time="time_end", multi=None):
+    """``dust::dust_data`` (R/particle_filter_data.R:197-198): one entry per time,
+    ``(time_end, [row, ...])`` with one row (a dict) per population."""
+    cols = {k: np.asarray(v) for k, v in data.items()}
+    n = len(cols[name_time])
+    rows = [{k: (v[i].item() if hasattr(v[i], "item") else v[i]) for k, v in cols.items()}
+            for i in range(n)]
+    if multi is None:
+        return [(int(r[name_time]), [r]) for r in rows]
+    levels = sorted(set(cols[multi].tolist()))
+    groups = [[r for r in rows if r[multi] == lv] for lv in levels]
+    if len({len(g) for g in groups}) != 1:
+        raise ValueError("All groups must have the same number of rows")
+    out = []
+    for i in range(len(groups[0])):
+        t = {int(g[i][name_time]) for g in groups}
+        if len(t) != 1:
+            raise ValueError("All groups must have the same time")
+        out.append((t.pop(), [g[i] for g in groups]))
+    return out
+
+
+# --------------------------------------------------------------------------
+# the model object
+# --------------------------------------------------------------------------
+class dust_model:
+    """One instantiated model: particle state, RNG streams and data in HBM."""
+
+    def __init__(self, generator, pars, time, n_particles, n_threads=1, seed=None,
+                 pars_multi=False, deterministic=False, gpu_config=None):
+        L = _lib.lib()
+        self._gen = generator
+        self._n_threads = int(n_threads)
+        self._pars_multi = bool(pars_multi)
+        if pars_multi:
+            if isinstance(pars, dict) or pars is None:
+                raise ValueError("Expected an unnamed list of parameters for 'pars'")
+            self._pars = [dict(p) for p in pars]
+            n_pars = len(self._pars)
+            if n_particles is None:  # R/if2.R:122: one particle per parameter set
+                n_particles = 1
+        else:
+            self._pars = dict(pars or {})
+            n_pars = 0
+        if n_particles is None or int(n_particles) < 1:
+            raise ValueError("'n_particles' must be at least 1")
+        device_id = 0
+        if gpu_config is not None:
+            device_id = int(gpu_config["device_id"]) if isinstance(gpu_config, dict) else int(gpu_config)
+        words = _seed_words(seed)
+        vec = generator._pars_vector(self._pars, pars_multi)
+        h = C.c_void_p()
+        check(L.mcb_alloc(generator.model_id, ptr(vec, f64p), int(n_particles), n_pars, int(time),
+                          ptr(words, u64p), words.size // 4, generator.scrambler,
+                          int(deterministic), device_id, C.byref(h)))
+        self._h = h
+        self._n_state = generator.n_state
+        self._n_particles = int(n_particles)
+        self._n_pars = n_pars
+        self._n_sets = max(1, n_pars)
+        self._n_total = self._n_particles * self._n_sets
+        self._n_index = self._n_state
+        self._index_names = None
+        self._data_times = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.lib().mcb_free(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # ---- shape helpers
+    def _shape_out(self, buf, n_rows):
+        """C buffer (n_total, n_rows) -> (n_rows, n_particles[, n_pars])."""
+        if self._pars_multi:
+            return buf.reshape(self._n_sets, self._n_particles, n_rows).transpose(2, 1, 0)
+        return buf.reshape(self._n_particles, n_rows).T
+
+    def _name_rows(self, arr):
+        return arr
+
+    # ---- protocol (each method cites its call site in mcstate)
+    def n_state(self):
+        return self._n_state
+
+    def n_particles(self):
+        return self._n_particles
+
+    def n_particles_each(self):
+        return self._n_particles
+
+    def n_pars(self):
+        """R/particle_filter_state.R:497: 0 unless pars_multi."""
+        return self._n_pars
+
+    def shape(self):
+        """R/particle_filter_state.R:268: N or c(N, P)."""
+        return (self._n_particles, self._n_pars) if self._pars_multi else (self._n_particles,)
+
+    def time(self):
+        t = C.c_uint64()
+        check(_lib.lib().mcb_time(self._h, C.byref(t)))
+        return int(t.value)
+
+    def pars(self):
+        return self._pars
+
+    def info(self):
+        """R/particle_filter_state.R:288: model-defined list (list of lists if multi)."""
+        return [self._gen._info(p) for p in self._pars] if self._pars_multi else self._gen._info(self._pars)
+
+    def n_threads(self):
+        return self._n_threads
+
+    def set_n_threads(self, n_threads):
+        """Accepted for protocol compatibility; parallelism is the GPU's."""
+        prev, self._n_threads = self._n_threads, int(n_threads)
+        return prev
+
+    def has_openmp(self):
+        return False
+
+    def uses_gpu(self, fake_gpu=False):
+        """tests/testthat/test-particle-filter.R:1215."""
+        return True
+
+    def set_index(self, index):
+        """R/particle_filter_state.R:261,263 (1-based; dict keeps row names)."""
+        if index is None:
+            check(_lib.lib().mcb_set_index(self._h, None, 0))
+            self._n_index, self._index_names = self._n_state, None
+            return
+        if isinstance(index, dict):
+            self._index_names = list(index.keys())
+            index = list(index.values())
+        else:
+            self._index_names = None
+        idx = np.ascontiguousarray(np.atleast_1d(index), dtype=np.int64) - 1
+        if np.any(idx < 0) or np.any(idx >= self._n_state):
+            raise ValueError("All elements of 'index' must lie in [1, %d]" % self._n_state)
+        idx = idx.astype(np.uintp)
+        check(_lib.lib().mcb_set_index(self._h, ptr(idx, szp), idx.size))
+        self._n_index = int(idx.size)
+
+    def run(self, time_end):
+        """R/particle_filter_state.R:65."""
+        out = np.zeros((self._n_total, self._n_index))
+        check(_lib.lib().mcb_run(self._h, int(time_end), ptr(out, f64p)))
+        return self._shape_out(out, self._n_index)
+
+    def simulate(self, time_end):
+        """R/predict.R:79: (n_index, n_particles[, n_pars], n_times)."""
+        t = np.ascontiguousarray(np.atleast_1d(time_end), dtype=np.uint64)
+        out = np.zeros((t.size, self._n_total, self._n_index))
+        check(_lib.lib().mcb_simulate(self._h, ptr(t, u64p), t.size, ptr(out, f64p)))
+        if self._pars_multi:
+            return out.reshape(t.size, self._n_sets, self._n_particles, self._n_index).transpose(3, 2, 1, 0)
+        return out.transpose(2, 1, 0)
+
+    def state(self, index=None):
+        """R/particle_filter_state.R:79,81,114,272."""
+        if index is None:
+            out = np.zeros((self._n_total, self._n_state))
+            check(_lib.lib().mcb_state(self._h, None, 0, ptr(out, f64p)))
+            return self._shape_out(out, self._n_state)
+        if isinstance(index, dict):
+            index = list(index.values())
+        idx = np.ascontiguousarray(np.atleast_1d(index), dtype=np.int64) - 1
+        if np.any(idx < 0) or np.any(idx >= self._n_state):
+            raise ValueError("All elements of 'index' must lie in [1, %d]" % self._n_state)
+        idx = idx.astype(np.uintp)
+        out = np.zeros((self._n_total, idx.size))
+        check(_lib.lib().mcb_state(self._h, ptr(idx, szp), idx.size, ptr(out, f64p)))
+        return self._shape_out(out, idx.size)
+
+    def update_state(self, pars=None, state=None, time=None, set_initial_state=None):
+        """R/particle_filter_state.R:248,253,512; R/smc2.R:141; R/if2.R:160-161."""
+        vec = None
+        if pars is not None:
+            if self._pars_multi:
+                if isinstance(pars, dict) or len(pars) != self._n_sets:
+                    raise ValueError("'pars' must be an unnamed list of length %d" % self._n_sets)
+                self._pars = [dict(p) for p in pars]
+            else:
+                self._pars = dict(pars)
+            vec = self._gen._pars_vector(self._pars, self._pars_multi)
+        st, st_len = None, 0
+        if state is not None:
+            s = np.asarray(state, dtype=np.float64)
+            if s.ndim == 1:
+                if s.size != self._n_state:
+                    raise ValueError("Expected a vector of length %d for 'state'" % self._n_state)
+                st = np.ascontiguousarray(s)
+            else:
+                want = (self._n_state, self._n_particles) + ((self._n_sets,) if self._pars_multi else ())
+                if s.shape != want:
+                    raise ValueError("Expected 'state' with dimensions %s" % (want,))
+                st = np.ascontiguousarray(np.transpose(s)).ravel()  # (pars,) particle, state
+            st_len = st.size
+        if set_initial_state is None:
+            set_initial_state = state is None
+        check(_lib.lib().mcb_update_state(self._h, ptr(vec, f64p), ptr(st, f64p), st_len,
+                                          int(time is not None), 0 if time is None else int(time),
+                                          int(bool(set_initial_state))))
+
+    def reorder(self, index):
+        """R/particle_filter_state.R:100: 1-based, [N] or [N, P] within-block."""
+        k = np.asarray(index)
+        if self._pars_multi:
+            if k.shape != (self._n_particles, self._n_sets):
+                raise ValueError("Expected a matrix with %d rows and %d columns for 'index'"
+                                 % (self._n_particles, self._n_sets))
+            k = k.T
+        elif k.size != self._n_particles:
+            raise ValueError("Expected a vector of length %d for 'index'" % self._n_particles)
+        k = np.ascontiguousarray(k, dtype=np.int32).ravel()
+        check(_lib.lib().mcb_reorder(self._h, ptr(k, i32p)))
+
+    def rng_state(self, first_only=False, last_only=False):
+        """R/particle_filter.R:813; R/particle_filter_state.R:363,406,420: raw bytes."""
+        out = np.zeros((self._n_total + 1) * 4, dtype=np.uint64)
+        check(_lib.lib().mcb_rng_state(self._h, 0, ptr(out, u64p)))
+        if first_only:
+            return out[:4].tobytes()
+        if last_only:
+            return out[-4:].tobytes()
+        return out.tobytes()
+
+    def set_rng_state(self, rng_state):
+        """R/particle_filter_state.R:369,420; R/particle_filter.R:877."""
+        raw = np.frombuffer(bytes(rng_state), dtype=np.uint64).copy()
+        if raw.size != (self._n_total + 1) * 4:
+            raise ValueError("'rng_state' must be a raw vector of length %d (but was %d)"
+                             % ((self._n_total + 1) * 32, raw.size * 8))
+        check(_lib.lib().mcb_set_rng_state(self._h, ptr(raw, u64p), raw.size))
+
+    def set_data(self, data, shared=False):
+        """R/particle_filter_state.R:243-246: ``data`` = dust_data(...)."""
+        n_sets_data = 1 if shared or not self._pars_multi else self._n_sets
+        fields = self._gen.data_fields
+        times = np.zeros(len(data), dtype=np.uint64)
+        vals = np.full((len(data), n_sets_data, len(fields)), np.nan)
+        for i, (t, rows) in enumerate(data):
+            times[i] = t
+            if len(rows) != n_sets_data:
+                raise ValueError("Expected each element of data to have %d rows" % n_sets_data)
+            for j, row in enumerate(rows):
+                for f, name in enumerate(fields):
+                    if name not in row:
+                        raise KeyError("data is missing the field '%s'" % name)
+                    x = row[name]
+                    vals[i, j, f] = np.nan if x is None else float(x)
+        check(_lib.lib().mcb_set_data(self._h, times.size, ptr(times, u64p), ptr(vals, f64p),
+                                      int(bool(shared))))
+        self._data_times = times
+
+    def compare_data(self):
+        """``$compare_data()``: log-weights for the datum at the current time, or None."""
+        w = np.zeros(self._n_total)
+        has = C.c_int(0)
+        check(_lib.lib().mcb_compare_data(self._h, ptr(w, f64p), C.byref(has)))
+        if not has.value:
+            return None
+        return w.reshape(self._n_sets, self._n_particles).T if self._pars_multi else w
+
+    def resample(self, weights):
+        """``$resample(weights)`` -> kappa (1-based, within block); reorders the state."""
+        w = np.asarray(weights, dtype=np.float64)
+        w = np.ascontiguousarray(w.T if w.ndim == 2 else w).ravel()
+        k = np.zeros(self._n_total, dtype=np.int32)
+        check(_lib.lib().mcb_resample(self._h, ptr(w, f64p), ptr(k, i32p)))
+        return k.reshape(self._n_sets, self._n_particles).T if self._pars_multi else k
+
+    def filter(self, time_end=None, save_trajectories=False, time_snapshot=None,
+               min_log_likelihood=None):
+        """R/particle_filter_state.R:151 -- the hot path, one native call.
+
+        Returns ``dict(log_likelihood, trajectories, snapshots)``.
+        """
+        if self._data_times is None:
+            raise _lib.McbError(_lib.ERR_STATE, "Data has not been set for this object")
+        if time_end is None:
+            time_end = int(self._data_times[-1])
+        L = _lib.lib()
+        n_rows = C.c_size_t()
+        check(L.mcb_filter_rows(self._h, int(time_end), C.byref(n_rows)))
+        ll = np.zeros(self._n_sets)
+        traj = None
+        if save_trajectories:
+            traj = np.zeros((n_rows.value + 1, self._n_total, self._n_index))
+        snap_t, snaps = None, None
+        if time_snapshot is not None and len(time_snapshot) > 0:
+            snap_t = np.ascontiguousarray(time_snapshot, dtype=np.uint64)
+            snaps = np.zeros((snap_t.size, self._n_total, self._n_state))
+        mll = None
+        if min_log_likelihood is not None:
+            mll = np.ascontiguousarray(np.atleast_1d(min_log_likelihood), dtype=np.float64)
+        check(L.mcb_filter(self._h, int(time_end), int(bool(save_trajectories)),
+                           ptr(snap_t, u64p), 0 if snap_t is None else snap_t.size,
+                           ptr(mll, f64p), 0 if mll is None else mll.size,
+                           ptr(ll, f64p), ptr(traj, f64p), ptr(snaps, f64p)))
+        if traj is not None:
+            if self._pars_multi:
+                traj = traj.reshape(-1, self._n_sets, self._n_particles, self._n_index).transpose(3, 2, 1, 0)
+            else:
+                traj = traj.transpose(2, 1, 0)
+        if snaps is not None:
+            if self._pars_multi:
+                snaps = snaps.reshape(-1, self._n_sets, self._n_particles, self._n_state).transpose(3, 2, 1, 0)
+            else:
+                snaps = snaps.transpose(2, 1, 0)
+        return {"log_likelihood": ll, "trajectories": traj, "snapshots": snaps}
+
+    # ---- asynchronous variant used to keep several GPUs / handles busy
+    def filter_enqueue(self, time_end=None):
+        if time_end is None:
+            time_end = int(self._data_times[-1])
+        check(_lib.lib().mcb_filter_enqueue(self._h, int(time_end)))
+
+    def filter_collect(self):
+        ll = np.zeros(self._n_sets)
+        check(_lib.lib().mcb_filter_collect(self._h, ptr(ll, f64p)))
+        return ll
+
+    def set_stream(self, cuda_stream):
+        check(_lib.lib().mcb_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        check(_lib.lib().mcb_synchronize(self._h))
+
+    def set_kernel_timing(self, enable=True):
+        check(_lib.lib().mcb_set_kernel_timing(self._h, int(bool(enable))))
+
+    def kernel_timing(self):
+        """(ms[4], launches[4]) for run+compare, tile weights, finalize, resample+gather."""
+        ms = np.zeros(4)
+        n = np.zeros(4, dtype=np.uint64)
+        check(_lib.lib().mcb_kernel_timing(self._h, ptr(ms, f64p), ptr(n, u64p)))
+        return ms, n
+
+    def launch_count(self):
+        n = C.c_uint64()
+        check(_lib.lib().mcb_launch_count(self._h, C.byref(n)))
+        return int(n.value)
+
+
+class dust_generator:
+    """What ``dust::dust_example(name)`` returns: the generator with its static
+    capability queries (R/particle_filter.R:590-593, 991, 241, 1029, 212)."""
+
+    name = "dust_generator"
+
+    def __init__(self, model_name, algorithm="xoshiro256plus"):
+        L = _lib.lib()
+        mid, ns, npar, nd = C.c_int(), C.c_size_t(), C.c_size_t(), C.c_size_t()
+        check(L.mcb_model_lookup(model_name.encode(), C.byref(mid), C.byref(ns), C.byref(npar),
+                                 C.byref(nd)))
+        if algorithm not in _ALGORITHMS:
+            raise ValueError("Unknown algorithm '%s'" % algorithm)
+        self.model_name = model_name
+        self.model_id = mid.value
+        self.n_state = ns.value
+        self.n_par = npar.value
+        self.algorithm = algorithm
+        self.scrambler = _ALGORITHMS[algorithm]
+        self.par_names = [L.mcb_model_par_name(mid.value, i).decode() for i in range(npar.value)]
+        self.par_defaults = [L.mcb_model_par_default(mid.value, i) for i in range(npar.value)]
+        self.state_names = [L.mcb_model_state_name(mid.value, i).decode() for i in range(ns.value)]
+        self.data_fields = ["incidence"]
+        self.public_methods = self  # R: model$public_methods$has_compare()
+
+    # -- static capability queries
+    def has_compare(self):
+        return True
+
+    def has_gpu_support(self, fake_gpu=False):
+        return True
+
+    def has_openmp(self):
+        return False
+
+    def time_type(self):
+        return "discrete"
+
+    def rng_algorithm(self):
+        return self.algorithm
+
+    def gpu_info(self):
+        L = _lib.lib()
+        n = C.c_int(0)
+        rc = L.mcb_device_count(C.byref(n))
+        devices = []
+        if rc == _lib.OK:
+            for d in range(n.value):
+                name = C.create_string_buffer(256)
+                major, minor, sm, mem = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
+                check(L.mcb_device_info(d, name, 256, C.byref(major), C.byref(minor), C.byref(sm),
+                                        C.byref(mem)))
+                devices.append({"id": d, "name": name.value.decode(), "memory": mem.value,
+                                "version": major.value * 10 + minor.value, "n_sm": sm.value})
+        return {"has_cuda": n.value > 0, "devices": devices}
+
+    # -- instantiate
+    def new(self, pars, time, n_particles, n_threads=1, seed=None, pars_multi=False,
+            deterministic=False, gpu_config=None, **ignored):
+        """R/particle_filter_state.R:237-241."""
+        return dust_model(self, pars, time, n_particles, n_threads=n_threads, seed=seed,
+                          pars_multi=pars_multi, deterministic=deterministic,
+                          gpu_config=gpu_config)
+
+    # -- helpers
+    def _pars_vector(self, pars, multi):
+        sets = pars if multi else [pars]
+        vec = np.zeros((len(sets), self.n_par))
+        for j, p in enumerate(sets):
+            for i, name in enumerate(self.par_names):
+                x = p.get(name, self.par_defaults[i])  # extra keys ignored (R/particle_filter.R:283-284)
+                vec[j, i] = float(x)
+        return np.ascontiguousarray(vec)
+
+    def _info(self, pars):
+        vals = {n: float(pars.get(n, d)) for n, d in zip(self.par_names, self.par_defaults)}
+        return {"vars": list(self.state_names), "pars": vals,
+                "index": {n: i + 1 for i, n in enumerate(self.state_names)}}
+
+
+def dust_example(name, algorithm="xoshiro256plus"):
+    """``dust::dust_example("sir")`` (tests/testthat/helper-mcstate.R:3)."""
+    return dust_generator(name, algorithm)

@@ -1,0 +1,402 @@
+"""GPU parity: the CUDA engine, called through the C ABI (via mcstate_b200.dust),
+against the CPU oracle on identical seeds and inputs.  Everything is compared
+bit for bit: states, RNG words, log-weights, ancestor indices, log-likelihoods
+(the reference's own CPU == GPU test demands identical results,
+tests/testthat/test-particle-filter.R:1480-1504).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dust():
+    from mcstate_b200 import dust as d
+
+    n = d.dust_example("sir").gpu_info()
+    if not n["has_cuda"]:
+        pytest.fail("no CUDA device visible: the engine has no CPU fallback")
+    return d
+
+
+def _data(sir_data, n=None, rate=4):
+    day = sir_data["day"][:n]
+    inc = sir_data["incidence"][:n]
+    return day * rate, inc
+
+
+def _set_data(model, t, x):
+    from mcstate_b200 import dust as d
+
+    model.set_data(d.dust_data({"time_end": t, "incidence": x}), False)
+
+
+def _rng_words(model):
+    return np.frombuffer(model.rng_state(), dtype=np.uint64).reshape(-1, 4)
+
+
+@pytest.mark.parametrize("n", [1, 31, 1000, (1 << 16) + 3])
+def test_stream_derivation_matches_serial_jumps(dust, orc, n):
+    m = dust.dust_example("sir").new({}, 0, n, seed=1)
+    assert np.array_equal(_rng_words(m), orc.rng_streams(1, n + 1))
+    # raw seed with several streams: verbatim, remainder jumped from the last one
+    raw = orc.rng_streams(42, 3)
+    m = dust.dust_example("sir").new({}, 0, 50, seed=raw.tobytes())
+    assert np.array_equal(_rng_words(m), orc.rng_streams(raw.ravel(), 51))
+
+
+@pytest.mark.parametrize("model,mid", [("sir", 0), ("sirs", 1)])
+@pytest.mark.parametrize("alg,scr", [("xoshiro256plus", 0), ("xoshiro256starstar", 1)])
+def test_run_state_and_rng_bit_exact(dust, orc, model, mid, alg, scr):
+    n = 5000
+    pars = {"beta": 0.3, "gamma": 0.12, "I0": 25}
+    g = dust.dust_example(model, alg)
+    m = g.new(pars, 0, n, seed=7)
+    vec = g._pars_vector(pars, False)
+    o = orc.OracleModel(pars=vec, n_particles=n, seed=7, model=mid, scrambler=scr, n_threads=8)
+    assert np.array_equal(m.state(), o.state())
+    for t_end in (1, 4, 5, 400):
+        got = m.run(t_end)
+        want = o.run(t_end)
+        assert np.array_equal(got, want), t_end
+        assert np.array_equal(_rng_words(m), o.rng_state()), t_end
+        assert m.time() == t_end
+
+
+def test_run_covers_both_binomial_algorithms(dust, orc):
+    # large populations push n*q above 10 (BTRS); tiny ones stay on inversion
+    n = 4096
+    for pars in ({"S0": 1e6, "I0": 5000.0, "beta": 0.5}, {"S0": 50.0, "I0": 2.0}):
+        g = dust.dust_example("sir")
+        m = g.new(pars, 0, n, seed=3)
+        o = orc.OracleModel(pars=g._pars_vector(pars, False), n_particles=n, seed=3, n_threads=8)
+        assert np.array_equal(m.run(80), o.run(80))
+        assert np.array_equal(_rng_words(m), o.rng_state())
+
+
+def test_deterministic_mode(dust, orc):
+    g = dust.dust_example("sir")
+    m = g.new({}, 0, 3, seed=1, deterministic=True)
+    o = orc.OracleModel(n_particles=3, seed=1, deterministic=True)
+    assert np.array_equal(m.run(100), o.run(100))
+    assert np.array_equal(_rng_words(m), orc.rng_streams(1, 4))  # no draws consumed
+
+
+def test_index_update_state_reorder_simulate(dust, orc):
+    n = 300
+    g = dust.dust_example("sir")
+    m = g.new({}, 0, n, seed=2)
+    o = orc.OracleModel(n_particles=n, seed=2)
+    m.set_index([5, 1])
+    got = m.run(8)
+    want = o.run(8)
+    assert got.shape == (2, n) and np.array_equal(got, want[[4, 0]])
+    assert np.array_equal(m.state([2, 3]), want[[1, 2]])
+    m.set_index(None)
+    # reorder: 1-based indices
+    kappa = np.random.default_rng(0).integers(1, n + 1, n)
+    m.reorder(kappa)
+    o.reorder(kappa - 1)
+    assert np.array_equal(m.state(), o.state())
+    with pytest.raises(Exception, match="index"):
+        m.reorder(np.zeros(n, dtype=int))
+    # update_state: vector recycled, matrix, pars + time reset; RNG untouched
+    before = _rng_words(m).copy()
+    m.update_state(state=[10, 20, 30, 40, 50])
+    assert np.array_equal(m.state(), np.tile(np.array([[10, 20, 30, 40, 50.0]]).T, (1, n)))
+    mat = np.arange(5 * n, dtype=float).reshape(5, n)
+    m.update_state(state=mat)
+    assert np.array_equal(m.state(), mat)
+    m.update_state(pars={"I0": 33}, time=0)
+    assert m.time() == 0
+    assert np.array_equal(m.state()[:, 0], [1000, 33, 0, 0, 0])
+    assert np.array_equal(_rng_words(m), before)
+    # simulate
+    o.update_state(pars=g._pars_vector({"I0": 33}, False), time=0)
+    sim = m.simulate([4, 8, 20])
+    assert sim.shape == (5, n, 3)
+    for k, t in enumerate((4, 8, 20)):
+        assert np.array_equal(sim[:, :, k], o.run(t))
+
+
+def test_rng_state_roundtrip(dust, orc):
+    g = dust.dust_example("sir")
+    m = g.new({}, 0, 10, seed=1)
+    s = m.rng_state()
+    assert len(s) == 11 * 32 and m.rng_state(first_only=True) == s[:32]
+    m.run(12)
+    m2 = g.new({}, 0, 10, seed=99)
+    m2.set_rng_state(s)
+    assert np.array_equal(m2.run(12), m.state())
+    with pytest.raises(Exception, match="rng_state"):
+        m2.set_rng_state(s[:64])
+
+
+def test_compare_data_bit_exact(dust, orc, sir_data):
+    n = 2000
+    t, x = _data(sir_data, 10)
+    g = dust.dust_example("sir")
+    m = g.new({}, 0, n, seed=5)
+    o = orc.OracleModel(n_particles=n, seed=5)
+    _set_data(m, t, x)
+    o.set_data(t, x)
+    assert m.compare_data() is None  # no datum at time 0
+    m.run(4); o.run(4)
+    got, want = m.compare_data(), o.compare_data()
+    assert np.array_equal(got, want)
+    assert np.array_equal(_rng_words(m), o.rng_state())  # one exponential draw each
+
+
+WEIGHT_KINDS = ["uniform", "onehot", "sparse", "heavy", "tiny", "real"]
+
+
+@pytest.mark.parametrize("kind", WEIGHT_KINDS)
+@pytest.mark.parametrize("n", [1, 7, 1024, 1025, 5000, (1 << 17) + 11])
+def test_resample_indices_bit_exact(dust, orc, kind, n):
+    rng = np.random.default_rng(n)
+    if kind == "uniform":
+        w = np.ones(n)
+    elif kind == "onehot":
+        w = np.zeros(n); w[(2 * n) // 3] = 1.0
+    elif kind == "sparse":
+        w = rng.uniform(size=n); w[rng.uniform(size=n) < 0.9] = 0.0; w[n - 1] = 1.0
+    elif kind == "heavy":
+        w = np.exp(rng.normal(0, 10, n)); w /= w.max()
+    elif kind == "tiny":
+        w = np.full(n, 1e-300); w[0] = 1.0
+    else:
+        lw = -0.5 * rng.normal(0, 3, n) ** 2
+        w = np.exp(lw - lw.max())
+    g = dust.dust_example("sir")
+    m = g.new({}, 0, n, seed=11)
+    o = orc.OracleModel(n_particles=n, seed=11)
+    m.run(4); o.run(4)
+    for _ in range(2):  # consecutive draws from the filter stream
+        got = m.resample(w)
+        want = o.resample(w) + 1
+        assert np.array_equal(got, want)
+        assert np.array_equal(m.state(), o.state())
+    assert np.array_equal(_rng_words(m)[-1], o.rng_state()[-1])
+
+
+def _filter_pair(dust, orc, n, sir_data, n_rows=None, pars=None, seed=1, n_pars=0, **kw):
+    t, x = _data(sir_data, n_rows)
+    g = dust.dust_example("sir")
+    if n_pars:
+        plist = pars or [{"beta": 0.2 + 0.02 * p} for p in range(n_pars)]
+        m = g.new(plist, 0, n, seed=seed, pars_multi=True)
+        o = orc.OracleModel(pars=g._pars_vector(plist, True), n_particles=n, n_pars=n_pars,
+                            seed=seed, n_threads=8)
+    else:
+        m = g.new(pars or {}, 0, n, seed=seed)
+        o = orc.OracleModel(pars=g._pars_vector(pars or {}, False), n_particles=n, seed=seed,
+                            n_threads=8)
+    return m, o, t, x
+
+
+@pytest.mark.parametrize("n", [1, 100, 1000, 4097, 1 << 16])
+def test_filter_log_likelihood_state_rng_bit_exact(dust, orc, sir_data, n):
+    m, o, t, x = _filter_pair(dust, orc, n, sir_data)
+    _set_data(m, t, x)
+    o.set_data(t, x)
+    got = m.filter()
+    want = o.filter()
+    assert np.array_equal(got["log_likelihood"], want["log_likelihood"])
+    assert np.isfinite(got["log_likelihood"]).all()
+    assert np.array_equal(m.state(), o.state())
+    assert np.array_equal(_rng_words(m), o.rng_state())
+    assert m.time() == 400
+    # the model object (and its RNG) persists: a second evaluation continues the streams
+    m.update_state(pars={}, time=0)
+    o.update_state(pars=o_default(orc), time=0)
+    got2, want2 = m.filter(), o.filter()
+    assert np.array_equal(got2["log_likelihood"], want2["log_likelihood"])
+    assert got2["log_likelihood"][0] != got["log_likelihood"][0]
+
+
+def o_default(orc):
+    return orc.default_pars(orc.SIR)
+
+
+def test_filter_trajectories_and_snapshots(dust, orc, sir_data):
+    n = 333
+    m, o, t, x = _filter_pair(dust, orc, n, sir_data, n_rows=30, seed=4)
+    _set_data(m, t, x)
+    o.set_data(t, x)
+    m.set_index([1, 2, 3])
+    snaps = [t[4], t[17], t[29]]
+    got = m.filter(save_trajectories=True, time_snapshot=snaps)
+    want = o.filter(save_trajectories=True, index=[0, 1, 2], snapshot_times=snaps)
+    assert got["trajectories"].shape == (3, n, 31)
+    assert np.array_equal(got["trajectories"], want["trajectories"])
+    assert np.array_equal(got["snapshots"], want["snapshots"])
+    assert np.array_equal(got["log_likelihood"], want["log_likelihood"])
+    tr = got["trajectories"]
+    assert np.all(np.diff(tr[0], axis=1) <= 0) and np.all(np.diff(tr[2], axis=1) >= 0)
+    assert np.array_equal(got["snapshots"][:, :, 2], m.state())
+
+
+def test_filter_incremental_equals_one_shot(dust, orc, sir_data):
+    # tests/testthat/test-particle-filter.R:604-658
+    n = 500
+    t, x = _data(sir_data, 40)
+    g = dust.dust_example("sir")
+    a = g.new({}, 0, n, seed=9)
+    b = g.new({}, 0, n, seed=9)
+    _set_data(a, t, x); _set_data(b, t, x)
+    one = a.filter()["log_likelihood"]
+    parts = b.filter(t[9])["log_likelihood"] + b.filter(t[10])["log_likelihood"] + \
+        b.filter(t[39])["log_likelihood"]
+    o = orc.OracleModel(n_particles=n, seed=9)
+    o.set_data(t, x)
+    p1 = o.filter(t[9])["log_likelihood"]; p2 = o.filter(t[10])["log_likelihood"]
+    p3 = o.filter(t[39])["log_likelihood"]
+    assert np.array_equal(parts, p1 + p2 + p3)
+    assert abs(one[0] - parts[0]) < 1e-9 * abs(one[0])
+    assert np.array_equal(a.state(), b.state())
+
+
+def test_filter_missing_data_rows_equal_dropped_rows(dust, orc, sir_data):
+    # tests/testthat/test-particle-filter.R:1698-1776
+    n = 400
+    t, x = _data(sir_data, 50)
+    x_na = x.copy()
+    x_na[::2] = np.nan
+    keep = ~np.isnan(x_na)
+    g = dust.dust_example("sir")
+    a = g.new({}, 0, n, seed=3)
+    b = g.new({}, 0, n, seed=3)
+    _set_data(a, t, x_na)
+    _set_data(b, t[keep], x_na[keep])
+    la, lb = a.filter()["log_likelihood"], b.filter()["log_likelihood"]
+    assert np.array_equal(la, lb)
+    assert np.array_equal(a.state(), b.state())
+    o = orc.OracleModel(n_particles=n, seed=3)
+    o.set_data(t, x_na)
+    assert np.array_equal(la, o.filter()["log_likelihood"])
+    # trailing / leading NA rows
+    x2 = x.copy(); x2[:3] = np.nan; x2[-2:] = np.nan
+    c = g.new({}, 0, n, seed=3)
+    _set_data(c, t, x2)
+    o = orc.OracleModel(n_particles=n, seed=3)
+    o.set_data(t, x2)
+    assert np.array_equal(c.filter(save_trajectories=True)["trajectories"],
+                          o.filter(save_trajectories=True)["trajectories"])
+    assert np.array_equal(c.state(), o.state()) and c.time() == o.time()
+
+
+def test_filter_impossible_data_stops(dust, orc, sir_data):
+    # tests/testthat/test-particle-filter.R:71-93: -Inf, later history NA.
+    # No infections and no noise => modelled incidence is exactly 0: a zero
+    # observation has log density 0, a positive one -Inf for every particle.
+    n = 64
+    t, x = _data(sir_data, 20)
+    x = x.copy()
+    x[:6] = 0.0
+    pars = {"exp_noise": float("inf"), "I0": 0}
+    g = dust.dust_example("sir")
+    m = g.new(pars, 0, n, seed=1)
+    o = orc.OracleModel(pars=g._pars_vector(pars, False), n_particles=n, seed=1)
+    _set_data(m, t, x); o.set_data(t, x)
+    got = m.filter(save_trajectories=True)
+    want = o.filter(save_trajectories=True)
+    assert got["log_likelihood"][0] == -np.inf and want["log_likelihood"][0] == -np.inf
+    stop = want["n_intervals"]
+    assert stop == 7
+    assert np.array_equal(np.isnan(got["trajectories"]), np.isnan(want["trajectories"]))
+    assert np.array_equal(np.nan_to_num(got["trajectories"]), np.nan_to_num(want["trajectories"]))
+    assert np.isnan(got["trajectories"][:, :, stop + 1:]).all()
+    assert not np.isnan(got["trajectories"][:, :, :stop + 1]).any()
+    assert m.time() == o.time() == t[6]
+    assert np.array_equal(m.state(), o.state())
+    assert np.array_equal(_rng_words(m), o.rng_state())
+
+
+def test_filter_min_log_likelihood_early_exit(dust, orc, sir_data):
+    # R/particle_filter_state.R:463-474
+    n = 256
+    m, o, t, x = _filter_pair(dust, orc, n, sir_data, seed=2)
+    _set_data(m, t, x); o.set_data(t, x)
+    got = m.filter(min_log_likelihood=-100.0)
+    want = o.filter(min_log_likelihood=-100.0)
+    assert got["log_likelihood"][0] == -np.inf == want["log_likelihood"][0]
+    assert m.time() == o.time() and m.time() < 400
+    assert np.array_equal(m.state(), o.state())
+    assert np.array_equal(_rng_words(m), o.rng_state())
+    # a bound that never binds changes nothing
+    m2, o2, _, _ = _filter_pair(dust, orc, n, sir_data, seed=2)
+    _set_data(m2, t, x); o2.set_data(t, x)
+    assert np.array_equal(m2.filter(min_log_likelihood=-1e9)["log_likelihood"],
+                          o2.filter()["log_likelihood"])
+
+
+@pytest.mark.parametrize("n,n_pars", [(100, 2), (1500, 3), (37, 8)])
+def test_multi_parameter_filter(dust, orc, sir_data, n, n_pars):
+    m, o, t, x = _filter_pair(dust, orc, n, sir_data, n_rows=40, n_pars=n_pars, seed=6)
+    from mcstate_b200 import dust as d
+    # shared data: one stream of observations for every parameter set
+    m.set_data(d.dust_data({"time_end": t, "incidence": x}), True)
+    o.set_data(t, x, shared=True)
+    got = m.filter(save_trajectories=True)
+    want = o.filter(save_trajectories=True)
+    assert got["log_likelihood"].shape == (n_pars,)
+    assert np.array_equal(got["log_likelihood"], want["log_likelihood"])
+    tr = want["trajectories"].reshape(5, n_pars, n, -1).transpose(0, 2, 1, 3)
+    assert got["trajectories"].shape == (5, n, n_pars, 41)
+    assert np.array_equal(got["trajectories"], tr)
+    assert np.array_equal(_rng_words(m), o.rng_state())
+    st = o.state().reshape(5, n_pars, n).transpose(0, 2, 1)
+    assert np.array_equal(m.state(), st)
+
+
+def test_nested_equals_independent_filters_on_split_streams(dust, orc, sir_data):
+    # tests/testthat/test-particle-filter.R:1285-1353: streams 1..n -> population 1,
+    # n+1..2n -> population 2; the filter stream is shared and drawn in set order
+    n = 200
+    t, x = _data(sir_data, 30)
+    x2 = np.roll(x, 3)
+    from mcstate_b200 import dust as d
+    g = d.dust_example("sir")
+    plist = [{"beta": 0.2}, {"beta": 0.25}]
+    m = g.new(plist, 0, n, seed=1, pars_multi=True)
+    rows = [(int(t[i]), [{"incidence": x[i]}, {"incidence": x2[i]}]) for i in range(len(t))]
+    m.set_data(rows, False)
+    ll = m.filter()["log_likelihood"]
+    o = orc.OracleModel(pars=g._pars_vector(plist, True), n_particles=n, n_pars=2, seed=1)
+    o.set_data(t, np.stack([x, x2], axis=1))
+    assert np.array_equal(ll, o.filter()["log_likelihood"])
+    # each population alone, seeded with its slice of the streams
+    streams = orc.rng_streams(1, 2 * n + 1)
+    for p, (pars, xs) in enumerate(zip(plist, (x, x2))):
+        s = np.concatenate([streams[p * n:(p + 1) * n], streams[-1:]])
+        single = g.new(pars, 0, n, seed=s.tobytes())
+        single.set_data(d.dust_data({"time_end": t, "incidence": xs}), False)
+        # the first interval's likelihood depends on the particle streams only (the
+        # shared filter stream is first used after it), so it must agree exactly
+        l1 = single.filter(t[0])["log_likelihood"][0]
+        m1 = g.new(plist, 0, n, seed=1, pars_multi=True)
+        m1.set_data(rows, False)
+        assert l1 == m1.filter(t[0])["log_likelihood"][p]
+
+
+def test_full_size_filter_2_20(dust, orc, sir_data):
+    """BASELINE config C2: 2^20 particles, bit-exact against the oracle, plus
+    size-independent properties."""
+    n = 1 << 20
+    m, o, t, x = _filter_pair(dust, orc, n, sir_data, seed=1)
+    _set_data(m, t, x); o.set_data(t, x)
+    got = m.filter()["log_likelihood"]
+    want = o.filter()["log_likelihood"]
+    assert np.array_equal(got, want)
+    st = m.state()
+    assert np.array_equal(st, o.state())
+    assert np.array_equal(st[0] + st[1] + st[2], np.full(n, 1010.0))  # population conserved
+    assert np.all(st >= 0)
+    # identical seeds => identical results; continuing the object continues the RNG
+    m2 = dust.dust_example("sir").new({}, 0, n, seed=1)
+    _set_data(m2, t, x)
+    assert np.array_equal(m2.filter()["log_likelihood"], got)
+    m2.update_state(pars={}, time=0)
+    again = m2.filter()["log_likelihood"]
+    assert again[0] != got[0] and abs(again[0] - got[0]) < 0.5
