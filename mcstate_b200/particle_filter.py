@@ -1,0 +1,561 @@
+"""``particle_filter`` / ``particle_filter_state``: the filter facade mcstate users call.
+
+Python twin of R/particle_filter.R and R/particle_filter_state.R for the hot path:
+``particle_filter(data, model, n_particles, compare).run(pars)``.  With
+``compare = None`` the whole time series is handed to the model object in one call
+(``step_compiled``, R/particle_filter_state.R:138-162) -- on the B200 engine that is
+one CUDA-graph launch.  With a host ``compare`` callable the per-interval loop of
+``step_r`` (R/particle_filter_state.R:35-136) runs here, crossing to the device twice
+per interval exactly as the reference crosses into dust; it works against the same
+model object but is never the fast path.
+
+Any object following the dust generator protocol can be the ``model`` (the boundary
+is the protocol).  Error messages are the reference's.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .particle_filter_data import particle_filter_data, particle_filter_data_split
+
+
+# ------------------------------------------------------------------ helpers
+def scale_log_weights(log_weights):
+    """R/particle_filter.R:570-587."""
+    lw = np.array(log_weights, dtype=np.float64)
+    lw[np.isnan(lw)] = -np.inf
+    m = lw.max()
+    if not np.isfinite(m):
+        return {"weights": np.full(lw.shape, np.nan), "average": -np.inf}
+    w = np.exp(lw - m)
+    return {"weights": w, "average": float(np.log(np.mean(w)) + m)}
+
+
+def particle_resample(weights, rng=None):
+    """R/particle_filter.R:515-523: systematic resampling with the HOST generator
+    (R's runif; here numpy's), 1-based indices; a matrix is resampled column-wise."""
+    w = np.asarray(weights, dtype=np.float64)
+    if w.ndim == 2:
+        return np.stack([particle_resample(w[:, j], rng) for j in range(w.shape[1])], axis=1)
+    n = w.size
+    draw = (rng.uniform if rng is not None else np.random.uniform)(0.0, 1.0 / n)
+    u = draw + np.arange(n) * (1.0 / n)
+    cw = np.cumsum(w / w.sum())
+    return (np.searchsorted(cw, u, side="right") + 1).astype(np.int64)
+
+
+def is_dust_generator(x):
+    """R/particle_filter.R:590-593."""
+    return getattr(x, "name", None) == "dust_generator" and hasattr(x, "new")
+
+
+def particle_filter_early_exit(log_likelihood, min_log_likelihood):
+    """R/particle_filter_state.R:463-474."""
+    ll = np.atleast_1d(np.asarray(log_likelihood, dtype=np.float64))
+    mn = np.atleast_1d(np.asarray(min_log_likelihood, dtype=np.float64))
+    if np.any(ll == -np.inf):
+        return True
+    if ll.size == 1:
+        return bool(ll[0] < mn[0])
+    if mn.size == 1:
+        return bool(ll.sum() < mn[0])
+    return bool(np.all(ll < mn))
+
+
+def check_n_parameters(n_parameters, data):
+    """R/particle_filter.R:1000-1024."""
+    has_multiple_data = data.is_nested
+    n_data = len(data.populations) if has_multiple_data else 1
+    if n_parameters is None:
+        has_multiple_parameters = has_multiple_data
+        n_parameters = n_data
+    else:
+        if int(n_parameters) != n_parameters or n_parameters < 1:
+            raise ValueError("'n_parameters' must be at least 1")
+        if has_multiple_data and n_parameters != n_data:
+            raise ValueError("To match the number of populations in your data, "
+                             "n_parameters must be %d (if not NULL)" % n_data)
+        has_multiple_parameters = True
+        n_parameters = int(n_parameters)
+    return {"has_multiple_parameters": has_multiple_parameters,
+            "has_multiple_data": has_multiple_data, "n_parameters": n_parameters,
+            "n_data": n_data}
+
+
+def check_save_restart(save_restart, data):
+    """R/particle_filter.R:596-613: model times -> step times."""
+    if save_restart is None:
+        return np.zeros(0, dtype=np.int64)
+    sr = np.atleast_1d(np.asarray(save_restart))
+    if np.any(np.diff(sr) <= 0):
+        raise ValueError("'save_restart' must be strictly increasing")
+    time_end = data.model_times[:, 1]
+    idx = [int(np.where(time_end == s)[0][0]) if np.any(time_end == s) else -1 for s in sr]
+    bad = [str(s) for s, i in zip(sr.tolist(), idx) if i < 0]
+    if bad:
+        raise ValueError("'save_restart' contains times not in '%s': %s" % (data.time, ", ".join(bad)))
+    return data.times[idx, 1].astype(np.int64)
+
+
+def check_time_step(curr, time_index, times, name):
+    """R/particle_filter_state.R:428-444."""
+    n_times = times.shape[0]
+    if curr >= n_times:
+        raise ValueError("%s has reached the end of the data" % name)
+    if time_index > n_times:
+        raise ValueError("time_index %d is beyond the length of the data (max %d)"
+                         % (time_index, n_times))
+    if time_index <= curr:
+        raise ValueError("%s has already run step index %d (to model step %d)"
+                         % (name, time_index, times[time_index - 1, 1]))
+
+
+def history_single(history_value, history_order, index_particle=None):
+    """R/particle_filter.R:616-646 (1-based indices)."""
+    hv = np.asarray(history_value)
+    if history_order is None:
+        return hv if index_particle is None else hv[:, np.atleast_1d(index_particle) - 1, :]
+    ip = (np.arange(1, hv.shape[1] + 1) if index_particle is None
+          else np.atleast_1d(index_particle))
+    nt = history_order.shape[1]
+    out = np.empty((hv.shape[0], ip.size, nt))
+    for t in range(nt - 1, -1, -1):
+        ip = history_order[ip - 1, t]
+        out[:, :, t] = hv[:, ip - 1, t]
+    return out
+
+
+def history_multiple(history_value, history_order, index_particle=None):
+    """R/particle_filter.R:653-714."""
+    hv = np.asarray(history_value)
+    ny, npart, npop, nt = hv.shape
+    if history_order is None:
+        if index_particle is None:
+            return hv
+        ip = np.asarray(index_particle)
+        if ip.ndim < 2:
+            return hv[:, np.atleast_1d(ip) - 1, :, :]
+        if ip.shape[1] != npop:
+            raise ValueError("'index_particle' should have %d columns" % npop)
+        out = np.empty((ny, ip.shape[0], npop, nt))
+        for i in range(npop):
+            out[:, :, i, :] = hv[:, ip[:, i] - 1, i, :]
+        return out
+    if index_particle is None:
+        ip = np.tile(np.arange(1, npart + 1)[:, None], (1, npop))
+    else:
+        ip = np.asarray(index_particle)
+        if ip.ndim == 2:
+            if ip.shape[1] != npop:
+                raise ValueError("'index_particle' should have %d columns" % npop)
+        else:
+            ip = np.tile(np.atleast_1d(ip)[:, None], (1, npop))
+    out = np.empty((ny, ip.shape[0], npop, nt))
+    for t in range(nt - 1, -1, -1):
+        nxt = np.empty_like(ip)
+        for j in range(npop):
+            nxt[:, j] = history_order[ip[:, j] - 1, j, t]
+            out[:, :, j, t] = hv[:, nxt[:, j] - 1, j, t]
+        ip = nxt
+    return out
+
+
+def _restart_subset(restart_state, index_particle):
+    rs = np.asarray(restart_state)
+    if index_particle is None:
+        return rs
+    ip = np.asarray(index_particle)
+    if rs.ndim == 3:
+        return rs[:, np.atleast_1d(ip) - 1, :]
+    if ip.ndim < 2:
+        return rs[:, np.atleast_1d(ip) - 1, :, :]
+    if ip.shape[1] != rs.shape[2]:
+        raise ValueError("'index_particle' should have %d columns" % rs.shape[2])
+    out = np.empty((rs.shape[0], ip.shape[0], rs.shape[2], rs.shape[3]))
+    for i in range(rs.shape[2]):
+        out[:, :, i, :] = rs[:, ip[:, i] - 1, i, :]
+    return out
+
+
+# ------------------------------------------- single / multiple parameter adapters
+def _pfs_compare_single(state, compare, data, pars):
+    """R/particle_filter_state.R:566-572."""
+    lw = compare(state, data, pars)
+    return None if lw is None else scale_log_weights(lw)
+
+
+def _pfs_compare_multiple(has_multiple_data, state, compare, data, pars):
+    """R/particle_filter_state.R:577-593."""
+    n_layer = state.shape[2]
+    lws = [compare(state[:, :, i], data[i] if has_multiple_data else data, pars[i])
+           for i in range(n_layer)]
+    if all(lw is None or len(lw) == 0 for lw in lws):
+        return None
+    ws = [scale_log_weights(lw) for lw in lws]
+    return {"average": np.array([w["average"] for w in ws]),
+            "weights": np.stack([w["weights"] for w in ws], axis=1)}
+
+
+class particle_filter_state:
+    """R/particle_filter_state.R: one run of the filter, steppable."""
+
+    def __init__(self, pars, generator, model, data, data_split, times, n_particles,
+                 has_multiple_parameters, n_threads, initial, index, compare,
+                 constant_log_likelihood, gpu_config, seed, min_log_likelihood,
+                 save_history, save_restart):
+        has_multiple_data = data.is_nested
+        if model is None:
+            # first run: create the model object and upload the observations ONCE
+            # (R/particle_filter_state.R:237-246)
+            model = generator.new(pars=pars, time=int(times[0, 0]), n_particles=n_particles,
+                                  n_threads=n_threads, seed=seed, gpu_config=gpu_config,
+                                  pars_multi=has_multiple_parameters)
+            if compare is None:
+                data_is_shared = has_multiple_parameters and not has_multiple_data
+                model.set_data(data_split, data_is_shared)
+        else:
+            # later runs reuse it: new parameters, initial state, RNG continues (:248)
+            model.update_state(pars=pars, time=int(times[0, 0]))
+
+        if initial is not None:
+            if has_multiple_parameters:
+                infos = model.info()
+                states = [initial(infos[i], n_particles, pars[i]) for i in range(len(pars))]
+                if not all(s is None for s in states):
+                    lens = {np.asarray(s).shape for s in states}
+                    if len(lens) != 1:
+                        raise ValueError("initial() produced unequal state lengths")
+                    st = np.stack([np.asarray(s, dtype=float) for s in states], axis=-1)
+                    if st.ndim == 2:  # vectors: recycle over particles
+                        st = np.repeat(st[:, None, :], n_particles, axis=1)
+                    model.update_state(state=st)
+            else:
+                st = initial(model.info(), n_particles, pars)
+                if isinstance(st, dict):
+                    raise ValueError("Setting 'time' from initial no longer supported")
+                model.update_state(state=st)
+
+        if index is None:
+            index_data = None
+        else:
+            if has_multiple_parameters:
+                all_idx = [index(i) for i in model.info()]
+                if any(_idx_key(a) != _idx_key(all_idx[0]) for a in all_idx[1:]):
+                    raise ValueError("index must be identical across populations")
+                index_data = all_idx[0]
+            else:
+                index_data = index(model.info())
+            model.set_index(index_data["run"] if compare is not None else index_data["state"])
+
+        shape = model.shape()
+        self.history = None
+        if save_history:
+            length = times.shape[0] + 1
+            state = model.state(None if index_data is None else index_data["state"])
+            value = np.full(state.shape + (length,), np.nan)
+            value[..., 0] = state
+            order = np.empty(tuple(shape) + (length,), dtype=np.int64)
+            order[...] = np.arange(1, n_particles + 1).reshape((n_particles,) + (1,) * len(shape))
+            self.history = {"value": value, "order": order,
+                            "index": None if index_data is None else index_data["state"]}
+
+        self._save_restart_time = check_save_restart(save_restart, data)
+        self.restart_state = None
+        if self._save_restart_time.size > 0:
+            self.restart_state = np.full((model.n_state(),) + tuple(shape) +
+                                         (self._save_restart_time.size,), np.nan)
+
+        self._generator = generator
+        self._pars = pars
+        self._data = data
+        self._data_split = data_split
+        self._times = times
+        self._n_particles = n_particles
+        self._n_threads = n_threads
+        self._has_multiple_parameters = has_multiple_parameters
+        self._has_multiple_data = has_multiple_data
+        self._initial = initial
+        self._index = index
+        self._compare = compare
+        self._constant_log_likelihood = constant_log_likelihood
+        self._gpu = gpu_config is not None
+        self._min_log_likelihood = min_log_likelihood
+        self._save_restart = save_restart
+
+        self.model = model
+        self.current_time_index = 0
+        self.log_likelihood_step = None
+        # R/particle_filter_state.R:313-314, 477-493
+        if constant_log_likelihood is None:
+            self.log_likelihood = np.zeros(len(pars)) if has_multiple_parameters else 0.0
+        elif has_multiple_parameters:
+            self.log_likelihood = np.array([constant_log_likelihood(p) for p in pars], dtype=float)
+        else:
+            self.log_likelihood = float(constant_log_likelihood(pars))
+
+    # ---- public
+    def run(self):
+        return self.step(self._times.shape[0])
+
+    def step(self, time_index, partial=False):
+        if self._compare is None:
+            return self._step_compiled(time_index, partial)
+        return self._step_r(time_index, partial)
+
+    # ---- R/particle_filter_state.R:138-162
+    def _step_compiled(self, time_index, partial=False):
+        if partial:
+            raise ValueError("'partial' not supported with compiled compare")
+        check_time_step(self.current_time_index, time_index, self._times, "Particle filter")
+        time = int(self._times[time_index - 1, 1])
+        save_history = self.history is not None
+        snap = self._save_restart_time if self._save_restart_time.size else None
+        # the one native call for all the intervals; min_log_likelihood is NOT forwarded,
+        # as in the reference (:151)
+        res = self.model.filter(time, save_history, snap)
+        self.log_likelihood_step = np.nan
+        ll = res["log_likelihood"]
+        self.log_likelihood = self.log_likelihood + (ll if self._has_multiple_parameters else float(ll[0]))
+        self.current_time_index = time_index
+        if save_history:
+            self.history = {"value": res["trajectories"], "order": None,
+                            "index": self.history["index"]}
+        self.restart_state = res["snapshots"]
+        return self.log_likelihood
+
+    # ---- R/particle_filter_state.R:35-136
+    def _step_r(self, time_index, partial=False):
+        curr = self.current_time_index
+        check_time_step(curr, time_index, self._times, "Particle filter")
+        model = self.model
+        multi = self._has_multiple_parameters
+        save_history = self.history is not None
+        save_restart = self.restart_state is not None
+        log_likelihood = self.log_likelihood
+        log_likelihood_step = None
+        n_particles = self._n_particles
+        for t in range(curr + 1, time_index + 1):
+            time_end = int(self._times[t - 1, 1])
+            state = model.run(time_end)
+            if save_history:
+                self.history["value"][..., t] = model.state(self.history["index"])
+            if multi:
+                weights = _pfs_compare_multiple(self._has_multiple_data, state, self._compare,
+                                                self._data_split[t - 1], self._pars)
+            else:
+                weights = _pfs_compare_single(state, self._compare, self._data_split[t - 1],
+                                              self._pars)
+            if weights is None:
+                log_likelihood_step = np.nan
+                kappa = np.arange(1, n_particles + 1)
+                if multi:
+                    kappa = np.tile(kappa[:, None], (1, len(self._pars)))
+            else:
+                log_likelihood_step = weights["average"]
+                log_likelihood = log_likelihood + log_likelihood_step
+                if particle_filter_early_exit(log_likelihood, self._min_log_likelihood):
+                    log_likelihood = (np.full_like(np.asarray(log_likelihood, dtype=float), -np.inf)
+                                      if multi else -np.inf)
+                    break
+                kappa = particle_resample(weights["weights"])
+                model.reorder(kappa)
+            if save_history:
+                self.history["order"][..., t] = kappa
+            if save_restart:
+                hit = np.where(self._save_restart_time == time_end)[0]
+                if hit.size:
+                    self.restart_state[..., hit[0]] = model.state()
+        self.log_likelihood_step = log_likelihood_step
+        self.log_likelihood = log_likelihood
+        self.current_time_index = time_index
+        return log_likelihood_step if partial else log_likelihood
+
+    def fork_smc2(self, pars):
+        """R/particle_filter_state.R:402-424: re-run from the start with new parameters
+        on the parent's RNG state, then hand the advanced RNG back to the parent.  The
+        reference forbids this on its GPU back end (:403); RNG state get/set is cheap
+        here, so it is allowed."""
+        seed = self.model.rng_state()
+        ret = particle_filter_state(
+            pars, self._generator, None, self._data, self._data_split, self._times,
+            self._n_particles, self._has_multiple_parameters, self._n_threads, self._initial,
+            self._index, self._compare, self._constant_log_likelihood, None, seed,
+            self._min_log_likelihood, self.history is not None, self._save_restart)
+        ret.step(self.current_time_index)
+        self.model.set_rng_state(ret.model.rng_state())
+        return ret
+
+
+def _idx_key(d):
+    return {k: (list(v.items()) if isinstance(v, dict) else list(np.atleast_1d(v)))
+            for k, v in d.items()}
+
+
+class particle_filter:
+    """R/particle_filter.R: ``particle_filter$new(data, model, n_particles, compare, ...)``."""
+
+    def __init__(self, data, model, n_particles, compare, index=None, initial=None,
+                 constant_log_likelihood=None, n_threads=1, seed=None, n_parameters=None,
+                 gpu_config=None, stochastic_schedule=None, ode_control=None):
+        if not is_dust_generator(model):
+            raise TypeError("'model' must be a dust_generator")
+        for name, fn in (("index", index), ("initial", initial),
+                         ("constant_log_likelihood", constant_log_likelihood)):
+            if fn is not None and not callable(fn):
+                raise TypeError("'%s' must be function if not NULL" % name)
+        if not isinstance(data, particle_filter_data):
+            raise TypeError("'data' must be a particle_filter_data")
+        if compare is None:
+            if not model.public_methods.has_compare():
+                raise ValueError("Your model does not have a built-in 'compare' function")
+        elif not callable(compare):
+            raise TypeError("'compare' must be a function")
+        if gpu_config is not None and not model.public_methods.has_gpu_support(True):
+            raise ValueError("'gpu_config' provided, but 'model' does not have GPU support")
+        if model.public_methods.time_type() != "discrete":
+            raise ValueError("'model' is continuous but 'data' is of type "
+                             "'particle_filter_data_discrete'")
+        if stochastic_schedule is not None:
+            raise ValueError("'stochastic_schedule' provided but 'model' does not support this")
+        if ode_control is not None:
+            raise ValueError("'ode_control' provided but 'model' does not support this")
+        self.model = model
+        self._data = data
+        info = check_n_parameters(n_parameters, data)
+        self.has_multiple_parameters = info["has_multiple_parameters"]
+        self.has_multiple_data = info["has_multiple_data"]
+        self.n_parameters = info["n_parameters"]
+        self.n_data = info["n_data"]
+        self._times = data.times
+        self._data_split = particle_filter_data_split(data, compare is None)
+        self._compare = compare
+        self._gpu_config = gpu_config
+        self._index = index
+        self._initial = initial
+        self._constant_log_likelihood = constant_log_likelihood
+        if int(n_particles) != n_particles or n_particles < 1:
+            raise ValueError("'n_particles' must be at least 1")
+        self.n_particles = int(n_particles)
+        if int(n_threads) != n_threads or n_threads < 1:
+            raise ValueError("'n_threads' must be at least 1")
+        self._n_threads = int(n_threads)
+        self._seed = seed
+        self._last_model = None
+        self._last_history = None
+        self._last_state = None
+        self._last_restart_state = None
+
+    def run(self, pars=None, save_history=False, save_restart=None, min_log_likelihood=None):
+        """R/particle_filter.R:313-317 -> filter_run -> filter_run_simple (:819-849)."""
+        pars = {} if pars is None else pars
+        if not isinstance(save_history, (bool, np.bool_)):
+            raise TypeError("'save_history' must be a logical")
+        if self.has_multiple_parameters:
+            if isinstance(pars, dict):
+                raise ValueError("Expected an unnamed list of parameters for 'pars'")
+            if len(pars) != self.n_parameters:
+                raise ValueError("'pars' must have length %d" % self.n_parameters)
+        obj = self.run_begin(pars, save_history, save_restart, min_log_likelihood)
+        obj.run()
+        self._last_history = obj.history
+        self._last_model = [obj.model]
+        self._last_state = obj.model.state
+        self._last_restart_state = obj.restart_state
+        return obj.log_likelihood
+
+    def run_begin(self, pars=None, save_history=False, save_restart=None,
+                  min_log_likelihood=None):
+        """R/particle_filter.R:338-351."""
+        pars = {} if pars is None else pars
+        if min_log_likelihood is None:
+            min_log_likelihood = -np.inf
+        last = None if self._last_model is None else self._last_model[0]
+        return particle_filter_state(
+            pars, self.model, last, self._data, self._data_split, self._times,
+            self.n_particles, self.has_multiple_parameters, self._n_threads, self._initial,
+            self._index, self._compare, self._constant_log_likelihood, self._gpu_config,
+            self._seed, min_log_likelihood, bool(save_history), save_restart)
+
+    def state(self, index_state=None):
+        """R/particle_filter.R:360-366."""
+        if self._last_state is None:
+            raise RuntimeError("Model has not yet been run")
+        return self._last_state(index_state)
+
+    def history(self, index_particle=None):
+        """R/particle_filter.R:377-397."""
+        if self._last_model is None:
+            raise RuntimeError("Model has not yet been run")
+        if self._last_history is None:
+            raise RuntimeError("Can't get history as model was run with save_history = FALSE")
+        value, order = self._last_history["value"], self._last_history["order"]
+        if value.ndim == 4:
+            return history_multiple(value, order, index_particle)
+        return history_single(value, order, index_particle)
+
+    def restart_state(self, index_particle=None, save_restart=None, restart_match=False):
+        """R/particle_filter.R:444-468 (the compiled path has no order array, so
+        ``restart_match`` falls back to plain subsetting exactly as there, :718)."""
+        if self._last_model is None:
+            raise RuntimeError("Model has not yet been run")
+        if self._last_restart_state is None:
+            raise RuntimeError("Can't get history as model was run with save_restart = NULL")
+        order = None if self._last_history is None else self._last_history["order"]
+        rs = self._last_restart_state
+        if index_particle is None or order is None or not restart_match:
+            return _restart_subset(rs, index_particle)
+        times_restart = check_save_restart(save_restart, self._data)
+        idx_save = [int(np.where(self._times[:, 0] == s)[0][0]) + 1 for s in times_restart]
+        ip = np.atleast_1d(index_particle)
+        if rs.ndim == 3:
+            nt = order.shape[1]
+            idx = np.empty((ip.size, nt), dtype=np.int64)
+            for t in range(nt - 1, -1, -1):
+                ip = idx[:, t] = order[ip - 1, t]
+            out = np.empty((rs.shape[0], idx.shape[0], len(idx_save)))
+            for i, s in enumerate(idx_save):
+                out[:, :, i] = rs[:, idx[:, s] - 1, i]
+            return out
+        npop, nt = rs.shape[2], order.shape[2]
+        ipm = ip if ip.ndim == 2 else np.tile(ip[:, None], (1, npop))
+        idx = np.empty((ipm.shape[0], npop, nt), dtype=np.int64)
+        for t in range(nt - 1, -1, -1):
+            for j in range(npop):
+                idx[:, j, t] = order[ipm[:, j] - 1, j, t]
+            ipm = idx[:, :, t]
+        out = np.empty((rs.shape[0], idx.shape[0], npop, len(idx_save)))
+        for i in range(npop):
+            for j, s in enumerate(idx_save):
+                out[:, :, i, j] = rs[:, idx[:, i, s] - 1, i, j]
+        return out
+
+    def inputs(self):
+        """R/particle_filter.R:479-496: everything needed to rebuild the filter; the
+        seed is the live first-stream RNG state (:811-816)."""
+        seed = self._seed
+        if self._last_model is not None and hasattr(self._last_model[-1], "rng_state"):
+            seed = self._last_model[-1].rng_state(first_only=True)
+        return {"data": self._data, "model": self.model, "n_particles": self.n_particles,
+                "index": self._index, "initial": self._initial, "compare": self._compare,
+                "constant_log_likelihood": self._constant_log_likelihood,
+                "gpu_config": self._gpu_config, "n_threads": self._n_threads,
+                "n_parameters": self.n_parameters if self.has_multiple_parameters else None,
+                "stochastic_schedule": None, "ode_control": None, "seed": seed}
+
+    def set_n_threads(self, n_threads):
+        """R/particle_filter.R:508-510."""
+        prev, self._n_threads = self._n_threads, n_threads
+        for m in self._last_model or []:
+            if m is not None:
+                m.set_n_threads(n_threads)
+        return prev
+
+
+def particle_filter_from_inputs(inputs, seed=None):
+    """R/particle_filter.R:528-567."""
+    return particle_filter(
+        inputs["data"], inputs["model"], inputs["n_particles"], inputs["compare"],
+        index=inputs["index"], initial=inputs["initial"],
+        constant_log_likelihood=inputs["constant_log_likelihood"],
+        n_threads=inputs["n_threads"], seed=inputs["seed"] if seed is None else seed,
+        n_parameters=inputs["n_parameters"], gpu_config=inputs["gpu_config"])

@@ -1,0 +1,164 @@
+"""A dust-protocol generator backed by the CPU oracle -- a TEST DOUBLE.
+
+Lets the host-side logic of mcstate_b200.particle_filter run in the CPU-only test
+suite (the reference tests its MCMC machinery the same way, with fake filters:
+tests/testthat/helper-mcstate.R:222-386), and gives the GPU tests a second
+implementation of the whole protocol to compare against.  Never imported by the
+product.
+"""
+import numpy as np
+
+from oracle import oracle as O
+
+PAR_NAMES = {O.SIR: ["beta", "gamma", "I0", "exp_noise", "S0", "R0", "freq"],
+             O.SIRS: ["alpha", "beta", "gamma", "I0", "exp_noise", "S0", "R0", "freq"]}
+STATE_NAMES = {O.SIR: ["S", "I", "R", "cases_cumul", "cases_inc"],
+               O.SIRS: ["S", "I", "R", "cases_inc"]}
+
+
+def _seed_words(seed):
+    if seed is None:
+        seed = int(np.random.randint(1, 2 ** 31 - 1))
+    if isinstance(seed, (int, np.integer)):
+        return O.seed_state(int(seed))
+    return np.frombuffer(bytes(seed), dtype=np.uint64).copy()
+
+
+class OracleDustModel:
+    def __init__(self, gen, pars, time, n_particles, n_threads, seed, pars_multi, deterministic):
+        self._gen = gen
+        self._multi = bool(pars_multi)
+        self._pars = [dict(p) for p in pars] if pars_multi else dict(pars or {})
+        self._np = int(n_particles)
+        self._n_pars = len(pars) if pars_multi else 0
+        self._n_sets = max(1, self._n_pars)
+        self._n_state = len(STATE_NAMES[gen.model_id])
+        self._index = None
+        self._o = O.OracleModel(pars=gen._pars_vector(self._pars, self._multi), time=int(time),
+                                n_particles=self._np, n_pars=self._n_pars,
+                                seed=_seed_words(seed), model=gen.model_id,
+                                scrambler=gen.scrambler, deterministic=deterministic,
+                                n_threads=max(1, int(n_threads)))
+
+    def _shape_out(self, a):  # (rows, n_total) -> (rows, N[, P])
+        if self._multi:
+            return a.reshape(a.shape[0], self._n_sets, self._np).transpose(0, 2, 1)
+        return a
+
+    def n_state(self): return self._n_state
+    def n_particles(self): return self._np
+    def n_pars(self): return self._n_pars
+    def shape(self): return (self._np, self._n_pars) if self._multi else (self._np,)
+    def time(self): return int(self._o.time())
+    def pars(self): return self._pars
+    def n_threads(self): return 1
+    def set_n_threads(self, n): self._o.set_n_threads(int(n)); return 1
+    def uses_gpu(self, fake_gpu=False): return False
+
+    def info(self):
+        return [self._gen._info(p) for p in self._pars] if self._multi else self._gen._info(self._pars)
+
+    def set_index(self, index):
+        if index is None:
+            self._index = None
+            return
+        if isinstance(index, dict):
+            index = list(index.values())
+        self._index = np.atleast_1d(index).astype(np.int64) - 1
+
+    def run(self, time_end):
+        self._o.run(int(time_end))
+        return self._shape_out(self._o.state(self._index))
+
+    def state(self, index=None):
+        if index is None:
+            return self._shape_out(self._o.state())
+        if isinstance(index, dict):
+            index = list(index.values())
+        return self._shape_out(self._o.state(np.atleast_1d(index).astype(np.int64) - 1))
+
+    def update_state(self, pars=None, state=None, time=None, set_initial_state=None):
+        vec = None
+        if pars is not None:
+            self._pars = [dict(p) for p in pars] if self._multi else dict(pars)
+            vec = self._gen._pars_vector(self._pars, self._multi)
+        st = None
+        if state is not None:
+            s = np.asarray(state, dtype=np.float64)
+            st = s if s.ndim == 1 else np.ascontiguousarray(np.transpose(s)).reshape(-1, self._n_state).T
+        if set_initial_state is None:
+            set_initial_state = state is None
+        self._o.update_state(pars=vec, state=st, time=time, set_initial_state=set_initial_state)
+
+    def reorder(self, index):
+        k = np.asarray(index)
+        if self._multi:
+            k = (k.T - 1) + (np.arange(self._n_sets) * self._np)[:, None]
+        else:
+            k = k - 1
+        self._o.reorder(np.ascontiguousarray(k).ravel())
+
+    def rng_state(self, first_only=False, last_only=False):
+        s = self._o.rng_state()
+        if first_only:
+            return s[0].tobytes()
+        if last_only:
+            return s[-1].tobytes()
+        return s.tobytes()
+
+    def set_rng_state(self, raw):
+        self._o.set_rng_state(np.frombuffer(bytes(raw), dtype=np.uint64).copy())
+
+    def set_data(self, data, shared=False):
+        n_sets = 1 if shared or not self._multi else self._n_sets
+        t = np.array([d[0] for d in data], dtype=np.uint64)
+        v = np.array([[np.nan if r["incidence"] is None else float(r["incidence"]) for r in d[1]]
+                      for d in data])
+        assert v.shape == (len(data), n_sets)
+        self._o.set_data(t, v, shared=bool(shared))
+        self._times = t
+
+    def filter(self, time_end=None, save_trajectories=False, time_snapshot=None,
+               min_log_likelihood=None):
+        if time_end is None:
+            time_end = int(self._times[-1])
+        snap = None if time_snapshot is None or len(time_snapshot) == 0 else time_snapshot
+        r = self._o.filter(int(time_end), save_trajectories, self._index, snap, min_log_likelihood)
+        traj, snaps = r["trajectories"], r["snapshots"]
+        if self._multi:
+            if traj is not None:
+                traj = traj.reshape(traj.shape[0], self._n_sets, self._np, -1).transpose(0, 2, 1, 3)
+            if snaps is not None:
+                snaps = snaps.reshape(snaps.shape[0], self._n_sets, self._np, -1).transpose(0, 2, 1, 3)
+        return {"log_likelihood": r["log_likelihood"], "trajectories": traj, "snapshots": snaps}
+
+
+class OracleGenerator:
+    name = "dust_generator"
+
+    def __init__(self, model_name="sir", algorithm="xoshiro256plus"):
+        self.model_id = {"sir": O.SIR, "sirs": O.SIRS}[model_name]
+        self.scrambler = {"xoshiro256plus": O.PLUS, "xoshiro256starstar": O.STARSTAR}[algorithm]
+        self.par_names = PAR_NAMES[self.model_id]
+        self.par_defaults = list(O.default_pars(self.model_id))
+        self.state_names = STATE_NAMES[self.model_id]
+        self.public_methods = self
+
+    def has_compare(self): return True
+    def has_gpu_support(self, fake_gpu=False): return False
+    def time_type(self): return "discrete"
+
+    def new(self, pars, time, n_particles, n_threads=1, seed=None, pars_multi=False,
+            deterministic=False, gpu_config=None, **kw):
+        return OracleDustModel(self, pars, time, n_particles, n_threads, seed, pars_multi,
+                               deterministic)
+
+    def _pars_vector(self, pars, multi):
+        sets = pars if multi else [pars]
+        return np.array([[float(p.get(n, d)) for n, d in zip(self.par_names, self.par_defaults)]
+                         for p in sets])
+
+    def _info(self, pars):
+        vals = {n: float(pars.get(n, d)) for n, d in zip(self.par_names, self.par_defaults)}
+        return {"vars": list(self.state_names), "pars": vals,
+                "index": {n: i + 1 for i, n in enumerate(self.state_names)}}
