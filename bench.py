@@ -33,8 +33,15 @@ N_PARTICLES = 1 << 20
 RATE = 4
 METRIC = "SIR particle-steps/sec (particle_filter$run, 2^20 particles per GPU)"
 UNIT = "particle-steps/s"
-# algorithmic bytes per particle per data interval
-BYTES_K1, BYTES_K2, BYTES_K2B, BYTES_K34 = 152, 16, 0, 84 + 8
+# Algorithmic bytes per particle per data interval.  SURVEY.md 8(d) counts 264 B for the
+# unfused pipeline (K1 152 + K2 8 + K3 20 + K4 84).  The engine fuses K3+K4 into K1's load,
+# so the bytes its kernels must move are fewer; the per-kernel roofline uses THESE (the
+# conservative figure), the whole-interval fraction uses the survey's 264 B.
+#   k_run_compare : state in 40 (gathered) + rng in 32 + cumulative-weight probe 8
+#                   + state out 40 + rng out 32 + logw out 8                      = 160
+#   k_weights_scan: logw in 8 + cumulative weight out 8                           = 16
+#   k_finish_state: (once per filter call) probe 8 + state in 40 + state out 40   = 88
+BYTES_K1, BYTES_K2, BYTES_FINISH = 160, 16, 88
 BYTES_INTERVAL = 264
 
 
@@ -244,9 +251,9 @@ def run_engine(args):
 
     if rank == 0:
         peak, peak_kind = measured_peak_gbs()
-        names = ["k_run_compare", "k_tile_weights", "k_finalize_row", "k_resample_gather"]
+        names = ["k_run_compare", "k_weights_scan", "unused", "k_finish_state"]
         per_launch_bytes = [BYTES_K1 * N_PARTICLES, BYTES_K2 * N_PARTICLES, 0,
-                            BYTES_K34 * N_PARTICLES]
+                            BYTES_FINISH * N_PARTICLES]
         kernels = {}
         for k, name in enumerate(names):
             if k_n[k]:

@@ -11,7 +11,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmcstate_b200.so")
+# MCSTATE_B200_LIB: load another build of the same engine (kernel tuning experiments)
+LIB_PATH = os.environ.get("MCSTATE_B200_LIB") or os.path.join(_HERE, "libmcstate_b200.so")
 
 OK, ERR_ARG, ERR_CUDA, ERR_STATE = 0, -1, -2, -3
 SCRAMBLER_PLUS, SCRAMBLER_STARSTAR = 0, 1

@@ -86,6 +86,20 @@ struct JumpCache {
 };
 JumpCache g_jump;
 
+// per-device constants (reciprocals of small integers for the inversion sampler)
+int device_constants(int device) {
+  static std::mutex mu;
+  static std::map<int, bool> done;
+  std::lock_guard<std::mutex> lock(mu);
+  if (done[device]) return MCB_OK;
+  double inv[mcb::kInvSmall];
+  inv[0] = 0.0;
+  for (int k = 1; k < mcb::kInvSmall; ++k) inv[k] = 1.0 / (double)k;
+  MCB_CUDA(cudaMemcpyToSymbol(mcb::c_inv_small, inv, sizeof inv));
+  done[device] = true;
+  return MCB_OK;
+}
+
 int jump_table_device(int device, uint64_t **out) {
   std::lock_guard<std::mutex> lock(g_jump.mu);
   auto it = g_jump.dev.find(device);
@@ -138,6 +152,7 @@ struct mcb_model {
   double *d_pars = nullptr;
   int *d_index = nullptr;
   int *d_flags = nullptr;
+  unsigned int *d_ticket = nullptr;
   double *d_min_ll = nullptr;
   double *d_ll = nullptr;
   int *d_kappa = nullptr;      // scratch for reorder/resample
@@ -195,34 +210,52 @@ unsigned blocks_for(size_t n, int threads) { return (unsigned)((n + threads - 1)
 
 template <class M, int SCR>
 void launch_run_compare(mcb_model *m, const double *y_in, double *y_out, uint64_t t0,
-                        uint32_t n_steps, int row, double *hist) {
+                        uint32_t n_steps, int prev_row, int row, double *hist, int *kappa_out) {
   const unsigned grid = blocks_for(m->v.n_total, mcb::kRunThreads);
   if (hist)
     mcb::k_run_compare<M, SCR, true><<<grid, mcb::kRunThreads, 0, m->stream>>>(
-        m->v, y_in, y_out, t0, n_steps, row, hist);
+        m->v, y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out);
   else
     mcb::k_run_compare<M, SCR, false><<<grid, mcb::kRunThreads, 0, m->stream>>>(
-        m->v, y_in, y_out, t0, n_steps, row, nullptr);
+        m->v, y_in, y_out, t0, n_steps, prev_row, row, nullptr, nullptr);
   ++m->launches;
 }
 
-void run_compare(mcb_model *m, const double *y_in, double *y_out, uint64_t t0,
-                 uint32_t n_steps, int row, double *hist) {
+// K1: [resample prev_row on load] -> n_steps updates -> compare against `row`
+void run_compare(mcb_model *m, const double *y_in, double *y_out, uint64_t t0, uint32_t n_steps,
+                 int prev_row, int row, double *hist, int *kappa_out) {
   const int key = m->model_id * 2 + m->scrambler;
   switch (key) {
-    case 0: launch_run_compare<mcb::SirModel, 0>(m, y_in, y_out, t0, n_steps, row, hist); break;
-    case 1: launch_run_compare<mcb::SirModel, 1>(m, y_in, y_out, t0, n_steps, row, hist); break;
-    case 2: launch_run_compare<mcb::SirsModel, 0>(m, y_in, y_out, t0, n_steps, row, hist); break;
-    default: launch_run_compare<mcb::SirsModel, 1>(m, y_in, y_out, t0, n_steps, row, hist); break;
+    case 0: launch_run_compare<mcb::SirModel, 0>(m, y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out); break;
+    case 1: launch_run_compare<mcb::SirModel, 1>(m, y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out); break;
+    case 2: launch_run_compare<mcb::SirsModel, 0>(m, y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out); break;
+    default: launch_run_compare<mcb::SirsModel, 1>(m, y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out); break;
   }
 }
 
-void resample_gather(mcb_model *m, int row, int *kappa_out) {
+// K2: weights -> fixed point -> tile scan; the last block finalizes the interval
+void weights_scan(mcb_model *m, int row) {
+  const unsigned grid = (unsigned)(m->v.n_sets * m->v.tiles_per_set);
+  if (row < 0) mcb::k_weights_scan<true><<<grid, mcb::kTileThreads, 0, m->stream>>>(m->v, row);
+  else mcb::k_weights_scan<false><<<grid, mcb::kTileThreads, 0, m->stream>>>(m->v, row);
+  ++m->launches;
+}
+
+void resample_gather(mcb_model *m, int row, const double *src, double *dst, int *kappa_out) {
   const unsigned grid = blocks_for(m->v.n_total, mcb::kGatherThreads);
   if (m->v.n_state == 5)
-    mcb::k_resample_gather<5><<<grid, mcb::kGatherThreads, 0, m->stream>>>(m->v, row, kappa_out);
+    mcb::k_resample_gather<5><<<grid, mcb::kGatherThreads, 0, m->stream>>>(m->v, row, src, dst, kappa_out);
   else
-    mcb::k_resample_gather<4><<<grid, mcb::kGatherThreads, 0, m->stream>>>(m->v, row, kappa_out);
+    mcb::k_resample_gather<4><<<grid, mcb::kGatherThreads, 0, m->stream>>>(m->v, row, src, dst, kappa_out);
+  ++m->launches;
+}
+
+void finish_state(mcb_model *m, int last, int last_weighted, int *kappa_out) {
+  const unsigned grid = blocks_for(m->v.n_total, mcb::kGatherThreads);
+  if (m->v.n_state == 5)
+    mcb::k_finish_state<5><<<grid, mcb::kGatherThreads, 0, m->stream>>>(m->v, last, last_weighted, kappa_out);
+  else
+    mcb::k_finish_state<4><<<grid, mcb::kGatherThreads, 0, m->stream>>>(m->v, last, last_weighted, kappa_out);
   ++m->launches;
 }
 
@@ -241,10 +274,11 @@ void draw_uniforms(mcb_model *m, int row_first, int row_last) {
   ++m->launches;
 }
 
-// boundary k (0..4) of a data row: before K1, after K1, K2, K2b, K3
+// boundary k of a data row: 0 before K1, 1 after K1, 2 after K2; row n_data holds the
+// two boundaries around k_finish_state
 void mark(mcb_model *m, int row, int k) {
   if (!m->timing) return;
-  const size_t need = (size_t)(row + 1) * 5;
+  const size_t need = (size_t)(row + 1) * 3;
   while (m->events.size() < need) {
     cudaEvent_t e;
     cudaEventCreate(&e);
@@ -252,7 +286,7 @@ void mark(mcb_model *m, int row, int k) {
   }
   cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(m->stream, &st);
-  cudaEventRecordWithFlags(m->events[(size_t)row * 5 + k], m->stream,
+  cudaEventRecordWithFlags(m->events[(size_t)row * 3 + k], m->stream,
                            st == cudaStreamCaptureStatusActive ? cudaEventRecordExternal
                                                                : cudaEventRecordDefault);
 }
@@ -285,54 +319,57 @@ uint64_t enqueue_filter_rows(mcb_model *m, int first, int last, bool hist,
   cudaMemsetAsync(m->d_wmax + (size_t)first * n_sets, 0,
                   (size_t)(last - first) * n_sets * sizeof(unsigned long long), m->stream);
   draw_uniforms(m, first, last);
+  auto iota = [&](int *dst) {
+    mcb::k_iota<<<blocks_for(v.n_total, 256), 256, 0, m->stream>>>(dst, v.n_total);
+    ++m->launches;
+  };
   if (hist) {
     // slice 0: the state before the first interval, identity order
-    const size_t slice = (size_t)v.n_index * v.ld;
-    run_compare(m, v.y, v.y, 0, 0, -1, m->d_hist_value);
-    (void)slice;
-    mcb::k_iota<<<blocks_for(v.n_total, 256), 256, 0, m->stream>>>(m->d_hist_order, v.n_total);
-    ++m->launches;
+    run_compare(m, v.y, v.y, 0, 0, -1, -1, m->d_hist_value, nullptr);
+    iota(m->d_hist_order);
   }
   uint64_t t = m->time;
   size_t snap_i = 0;
+  int prev_weighted = -1;          // row whose resampling is still owed, or -1
+  const double *in = v.y;
   for (int row = first; row < last; ++row) {
     const uint64_t t_end = m->data_time[row];
     const uint32_t n_steps = (uint32_t)(t_end - t);
     const int rel = row - first;
+    // buffers alternate so that the last row always writes y_tmp
+    double *out = ((last - 1 - row) & 1) == 0 ? v.y_tmp : v.y;
     double *hist_slice = hist ? m->d_hist_value + (size_t)(rel + 1) * v.n_index * v.ld : nullptr;
-    int *order_slice = hist ? m->d_hist_order + (size_t)(rel + 1) * v.n_total : nullptr;
-    if (m->row_all_na[row]) {
-      // no observation anywhere: run in place, nothing to weigh or resample
-      run_compare(m, v.y, v.y, t, n_steps, -1, hist_slice);
-      if (hist) {
-        mcb::k_iota<<<blocks_for(v.n_total, 256), 256, 0, m->stream>>>(order_slice, v.n_total);
-        ++m->launches;
-      }
-    } else {
-      mark(m, row, 0);
-      run_compare(m, v.y, v.y_tmp, t, n_steps, row, hist_slice);
-      mark(m, row, 1);
-      mcb::k_tile_weights<false><<<(unsigned)(n_sets * v.tiles_per_set), mcb::kTileThreads, 0,
-                                   m->stream>>>(v, row);
-      mark(m, row, 2);
-      mcb::k_finalize_row<<<1, 1024, 0, m->stream>>>(v, row);
-      mark(m, row, 3);
-      m->launches += 2;
-      resample_gather(m, row, order_slice);
-      mark(m, row, 4);
-    }
+    int *order_prev = hist ? m->d_hist_order + (size_t)rel * v.n_total : nullptr;
+    const int weigh = m->row_all_na[row] ? -1 : row;
+    mark(m, row, 0);
+    run_compare(m, in, out, t, n_steps, prev_weighted, weigh, hist_slice,
+                prev_weighted >= 0 ? order_prev : nullptr);
+    if (hist && rel > 0 && prev_weighted < 0) iota(order_prev);
+    mark(m, row, 1);
+    if (weigh >= 0) weights_scan(m, row);
+    mark(m, row, 2);
+    prev_weighted = weigh;
     while (snap_i < snap_rows.size() && snap_rows[snap_i] < row) ++snap_i;
     if (snap_i < snap_rows.size() && snap_rows[snap_i] == row) {
-      mcb::k_copy_state_if_running<<<blocks_for(v.n_total, 256), 256, 0, m->stream>>>(
-          v, m->d_snap + snap_i * (size_t)v.n_state * v.ld);
-      ++m->launches;
+      double *dst = m->d_snap + snap_i * (size_t)v.n_state * v.ld;
+      if (weigh >= 0) {
+        resample_gather(m, row, out, dst, nullptr);
+      } else {
+        mcb::k_copy_state_if_running<<<blocks_for(v.n_total, 256), 256, 0, m->stream>>>(v, out, dst);
+        ++m->launches;
+      }
       ++snap_i;
     }
+    in = out;
     t = t_end;
   }
+  mark(m, (int)m->n_data, 0);
+  int *order_last = hist ? m->d_hist_order + (size_t)(last - first) * v.n_total : nullptr;
+  finish_state(m, last, prev_weighted >= 0 ? 1 : 0, prev_weighted >= 0 ? order_last : nullptr);
+  if (hist && prev_weighted < 0) iota(order_last);
+  mark(m, (int)m->n_data, 1);
   mcb::k_filter_finish<<<1, 32, 0, m->stream>>>(v, first, last, m->d_fs_after);
-  mcb::k_adopt_tmp_if_stopped<<<blocks_for(v.n_total, 256), 256, 0, m->stream>>>(v);
-  m->launches += 2;
+  ++m->launches;
   return m->launches - before;
 }
 
@@ -573,6 +610,7 @@ int mcb_alloc(int model_id, const double *pars, size_t n_particles, size_t n_par
   if (n_dev == 0) return fail(MCB_ERR_CUDA, "no CUDA device: this engine has no CPU fallback");
   if (device_id < 0 || device_id >= n_dev) return fail(MCB_ERR_ARG, "device_id out of range");
   MCB_CUDA(cudaSetDevice(device_id));
+  MCB_TRY(device_constants(device_id));
 
   mcb_model *m = new mcb_model;
   m->model_id = model_id;
@@ -612,6 +650,7 @@ int mcb_alloc(int model_id, const double *pars, size_t n_particles, size_t n_par
   ALLOC(m->d_ll, n_sets * sizeof(double));
   ALLOC(m->d_min_ll, n_sets * sizeof(double));
   ALLOC(m->d_flags, 2 * sizeof(int));
+  ALLOC(m->d_ticket, sizeof(unsigned int));
   ALLOC(m->d_index, mcb::kMaxState * sizeof(int));
   ALLOC(m->d_kappa, v.ld * sizeof(int));
   ALLOC(m->d_u, n_sets * sizeof(double));
@@ -622,6 +661,7 @@ int mcb_alloc(int model_id, const double *pars, size_t n_particles, size_t n_par
   v.ll = m->d_ll;
   v.min_ll = m->d_min_ll;
   v.flags = m->d_flags;
+  v.ticket = m->d_ticket;
   v.index = m->d_index;
   v.u_draws = m->d_u;
   v.wmax = m->d_wmax;
@@ -631,6 +671,7 @@ int mcb_alloc(int model_id, const double *pars, size_t n_particles, size_t n_par
     return cleanup(fail(MCB_ERR_CUDA, "pinned memory / stream creation failed"));
   m->stream = m->own_stream;
   cudaMemsetAsync(m->d_flags, 0, 2 * sizeof(int), m->stream);
+  cudaMemsetAsync(m->d_ticket, 0, sizeof(unsigned int), m->stream);
   cudaMemsetAsync(v.y, 0, (size_t)v.n_state * v.ld * sizeof(double), m->stream);
   cudaMemsetAsync(v.y_tmp, 0, (size_t)v.n_state * v.ld * sizeof(double), m->stream);
   m->index_host.resize(v.n_state);
@@ -673,7 +714,7 @@ int mcb_free(mcb_model *m) {
   if (m->stream) cudaStreamSynchronize(m->stream);
   clear_graphs(m);
   void *ptrs[] = {m->v.y, m->v.y_tmp, m->v.rng, m->d_pars, m->v.logw, m->v.cw, m->v.tile_incl,
-                  m->v.setinfo, m->d_ll, m->d_min_ll, m->d_flags, m->d_index, m->d_kappa, m->d_u,
+                  m->v.setinfo, m->d_ll, m->d_min_ll, m->d_flags, m->d_ticket, m->d_index, m->d_kappa, m->d_u,
                   m->d_wmax, m->d_fs_after, m->d_data, m->d_stage, m->d_hist_value,
                   m->d_hist_order, m->d_traj, m->d_snap};
   for (void *p : ptrs)
@@ -755,7 +796,7 @@ int mcb_run(mcb_model *m, uint64_t time_end, double *out) {
   MCB_CUDA(cudaSetDevice(m->device));
   if (time_end < m->time) return fail(MCB_ERR_ARG, "'time_end' must be at least the current time");
   if (time_end > m->time) {
-    run_compare(m, m->v.y, m->v.y, m->time, (uint32_t)(time_end - m->time), -1, nullptr);
+    run_compare(m, m->v.y, m->v.y, m->time, (uint32_t)(time_end - m->time), -1, -1, nullptr, nullptr);
     m->time = time_end;
     reset_cursor(m);
   }
@@ -927,7 +968,7 @@ int mcb_compare_data(mcb_model *m, double *logw, int *has_data) {
   if (row < 0 || m->row_all_na[row]) return MCB_OK;
   MCB_CUDA(cudaMemsetAsync(v.logw, 0, v.n_total * sizeof(double), m->stream));
   MCB_CUDA(cudaMemsetAsync(m->d_flags, 0, 2 * sizeof(int), m->stream));
-  run_compare(m, v.y, v.y, m->time, 0, row, nullptr);
+  run_compare(m, v.y, v.y, m->time, 0, -1, row, nullptr, nullptr);
   MCB_CUDA(cudaMemcpyAsync(logw, v.logw, v.n_total * sizeof(double), cudaMemcpyDeviceToHost,
                            m->stream));
   MCB_CUDA(cudaStreamSynchronize(m->stream));
@@ -946,13 +987,10 @@ int mcb_resample(mcb_model *m, const double *weights, int *kappa) {
   MCB_CUDA(cudaMemcpyAsync(v.logw, weights, v.n_total * sizeof(double), cudaMemcpyHostToDevice,
                            m->stream));
   draw_uniforms(m, -1, 0);
-  mcb::k_tile_weights<true><<<(unsigned)(v.n_sets * v.tiles_per_set), mcb::kTileThreads, 0,
-                              m->stream>>>(v, -1);
-  mcb::k_finalize_row<<<1, 1024, 0, m->stream>>>(v, -1);
-  m->launches += 2;
+  weights_scan(m, -1);
   MCB_CUDA(cudaMemcpyAsync(v.y_tmp, v.y, (size_t)v.n_state * v.ld * sizeof(double),
                            cudaMemcpyDeviceToDevice, m->stream));
-  resample_gather(m, -1, m->d_kappa);
+  resample_gather(m, -1, v.y_tmp, v.y, m->d_kappa);
   std::vector<int> k0(v.n_total);
   MCB_CUDA(cudaMemcpyAsync(k0.data(), m->d_kappa, v.n_total * sizeof(int), cudaMemcpyDeviceToHost,
                            m->stream));
@@ -998,17 +1036,19 @@ int mcb_filter_collect(mcb_model *m, double *log_likelihood) {
   const bool stopped = m->h_flags[0] != 0;
   const int last_row = stopped ? m->h_flags[1] : m->pend_last - 1;
   if (m->timing && !stopped) {
-    for (int row = m->pend_first; row < m->pend_last; ++row) {
-      if (m->row_all_na[row] || m->events.size() < (size_t)(row + 1) * 5) continue;
-      for (int k = 0; k < 4; ++k) {
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, m->events[(size_t)row * 5 + k],
-                                 m->events[(size_t)row * 5 + k + 1]) == cudaSuccess) {
-          m->kernel_ms[k] += ms;
-          ++m->kernel_n[k];
-        }
+    auto add = [&](int slot, size_t e0, size_t e1) {
+      float ms = 0.f;
+      if (e1 < m->events.size() &&
+          cudaEventElapsedTime(&ms, m->events[e0], m->events[e1]) == cudaSuccess) {
+        m->kernel_ms[slot] += ms;
+        ++m->kernel_n[slot];
       }
+    };
+    for (int row = m->pend_first; row < m->pend_last; ++row) {
+      add(0, (size_t)row * 3, (size_t)row * 3 + 1);
+      if (!m->row_all_na[row]) add(1, (size_t)row * 3 + 1, (size_t)row * 3 + 2);
     }
+    if (m->pend_last > m->pend_first) add(3, m->n_data * 3, m->n_data * 3 + 1);
   }
   if (last_row >= m->pend_first) {
     m->time = m->data_time[last_row];

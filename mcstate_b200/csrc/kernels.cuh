@@ -2,17 +2,20 @@
 // (model$filter, R/particle_filter_state.R:151; per-interval order as
 // R/particle_filter_state.R:63-117).
 //
-//   K1  k_run_compare      run `rate` model steps + compare  -> state', rng', logw, max
-//   K2  k_tile_weights     w = exp(logw - max) as fixed point; per-tile inclusive scan
-//   K2b k_finalize_row     tile prefix, log-mean-exp -> ll, resampling thresholds, early exit
-//   K3+K4 k_resample_gather  systematic-resampling index by binary search + state gather
+// Two launches per data interval:
+//   K1 k_run_compare   [resample + gather of the previous interval, fused into the
+//                      load] -> `rate` model steps -> compare -> state', rng', logw, max
+//   K2 k_weights_scan  w = exp(logw - max) as fixed point, per-tile inclusive scan;
+//                      the last block adds the tile prefix, log-mean-exp -> ll,
+//                      resampling thresholds and the early-exit rule
+// plus k_finish_state once per filter call (the last interval's resample).
 //
 // Data layout (HBM): state is SoA [n_state][ld] fp64, RNG is SoA [4][ld_rng]
 // u64, both with ld a multiple of 32 so every row starts 256-byte aligned and a
 // warp's access to one row is one contiguous 256-byte segment.
-// The post-update state is written to a second buffer (`y_tmp`) and the gather
-// brings it back into `y`, so the live state is always in `y` and the launch
-// sequence has no pointer flip -- it replays unchanged as a CUDA graph.
+// The state ping-pongs between `y` and `y_tmp`, arranged so the last interval
+// always writes `y_tmp` and k_finish_state lands the live state in `y`: the
+// launch sequence is fixed per row range and replays as a CUDA graph.
 //
 // Weights are summed as fixed-point integers (scale_log_weights:
 // R/particle_filter.R:570-587; resample_weight: SURVEY.md R2b).  Integer
@@ -50,6 +53,7 @@ struct View {
   double *ll;         // [n_sets] accumulated log-likelihood of this filter call
   const double *min_ll; // [n_min]
   int *flags;         // [0] stopped, [1] stop row
+  unsigned int *ticket; // K2 block counter (the last block finalizes)
   const int *index;   // [n_index] rows returned by run()/saved in trajectories
   size_t n_particles, n_sets, n_total, ld, ld_rng;
   int n_state, n_index, n_min, data_sets, tiles_per_set, shift, deterministic;
@@ -84,14 +88,56 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long x,
 }
 
 // ---------------------------------------------------------------------------
-// K1: one thread per particle.  State (kState doubles) and the generator
-// (4 words) stay in registers for all n_steps updates and the compare; every
-// global access is a coalesced row access.  row < 0: no compare (model$run).
+// Systematic resampling (dust resample_weight; the R twin is
+// particle_resample, R/particle_filter.R:515-523): output slot `il` of `set`
+// takes the first particle whose inclusive cumulative weight reaches
+// ceil(uu0 + il du).  Compared exactly, as integers: binary search over the
+// set's tile prefix (8 KB, L1 resident), then inside the tile.  Thresholds grow
+// with il, so neighbouring threads probe neighbouring addresses and the
+// chosen sources are monotone (near-coalesced gather).
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ size_t resample_source(const View &v, size_t set, size_t il) {
+  const SetInfo si = v.setinfo[set];
+  const unsigned long long thr =
+      (unsigned long long)__double2ll_ru(si.uu0 + (double)il * si.du);
+  const unsigned long long *ts = v.tile_incl + set * v.tiles_per_set;
+  int lo = 0, hi = v.tiles_per_set - 1;  // first tile whose inclusive prefix reaches thr
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(ts + mid) >= thr) hi = mid; else lo = mid + 1;
+  }
+  const unsigned long long before = lo ? __ldg(ts + lo - 1) : 0ULL;
+  const unsigned long long rem = thr > before ? thr - before : 0ULL;
+  const size_t tile_base = (size_t)lo * kTile;
+  const size_t in_tile = min((size_t)kTile, v.n_particles - tile_base);
+  const unsigned long long *cw = v.cw + set * v.n_particles + tile_base;
+  int a = 0, b = (int)in_tile - 1;
+  while (a < b) {
+    const int mid = (a + b) >> 1;
+    if (__ldg(cw + mid) >= rem) b = mid; else a = mid + 1;
+  }
+  return set * v.n_particles + tile_base + a;
+}
+
+// ---------------------------------------------------------------------------
+// K1: one thread per particle: [resample of the previous interval, fused into
+// the load] -> `n_steps` model updates -> compare.  State (kState doubles) and
+// the generator (4 words) stay in registers throughout.
+//   prev_row >= 0: slot i starts from the particle systematic resampling picks
+//                  for it (reads y_in[src]; y_in != y_out), so the resampled
+//                  state is never written to HBM and read back;
+//   prev_row <  0: slot i continues its own particle (y_in may equal y_out);
+//   row >= 0: weigh against data row `row`; row < 0: no compare (model$run).
+// kappa_out (trajectories only) records src, the order slice of prev_row.
+// ---------------------------------------------------------------------------
+#ifndef MCB_K1_MINBLOCKS
+#define MCB_K1_MINBLOCKS 8
+#endif
 template <class M, int SCR, bool HIST>
-__global__ void __launch_bounds__(kRunThreads)
+__global__ void __launch_bounds__(kRunThreads, MCB_K1_MINBLOCKS)
 k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_out,
-              uint64_t t0, uint32_t n_steps, int row, double *__restrict__ hist) {
+              uint64_t t0, uint32_t n_steps, int prev_row, int row,
+              double *__restrict__ hist, int *__restrict__ kappa_out) {
   __shared__ unsigned long long s_key[kRunThreads / 32];
   if (v.flags[0]) return;
   const size_t i = (size_t)blockIdx.x * kRunThreads + threadIdx.x;
@@ -107,8 +153,12 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
   unsigned long long key = 0;
   bool weighted = false;
   if (live) {
+    size_t src = i;
+    if (prev_row >= 0 && !datum_is_na(v, prev_row, set))
+      src = resample_source(v, set, i - set * v.n_particles);
+    if (HIST && kappa_out) kappa_out[i] = (int)src;
 #pragma unroll
-    for (int s = 0; s < M::kState; ++s) y[s] = y_in[(size_t)s * v.ld + i];
+    for (int s = 0; s < M::kState; ++s) y[s] = y_in[(size_t)s * v.ld + src];
     rng.s0 = v.rng[0 * v.ld_rng + i];
     rng.s1 = v.rng[1 * v.ld_rng + i];
     rng.s2 = v.rng[2 * v.ld_rng + i];
@@ -173,107 +223,87 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
 }
 
 // ---------------------------------------------------------------------------
-// K2: per tile of kTile particles (tiles never straddle a parameter set):
-// w = exp(logw - max) -> fixed point, inclusive scan inside the tile.
-// GIVEN = true: `logw` already holds weights in [0,1] (model$resample(weights)).
+// Per parameter set, once its total weight is known: log-mean-exp into ll
+// (scale_log_weights, R/particle_filter.R:570-587) and the resampling
+// thresholds.  One thread.  Returns true if the set is dead (all -Inf).
 // ---------------------------------------------------------------------------
-template <bool GIVEN>
-__global__ void __launch_bounds__(kTileThreads) k_tile_weights(View v, int row) {
-  __shared__ unsigned long long s_warp[kTileThreads / 32];
-  if (v.flags[0]) return;
-  const size_t set = blockIdx.x / v.tiles_per_set;
-  const int tile = blockIdx.x % v.tiles_per_set;
-  if (!GIVEN && datum_is_na(v, row, set)) return;
-  double mx = 0.0;
-  if (!GIVEN) mx = key_to_double(v.wmax[(size_t)row * v.n_sets + set]);
-  const bool dead = !GIVEN && !(mx > __longlong_as_double(0xfff0000000000000LL));
-  const double scale = bits_to_double((uint64_t)(1023 + v.shift) << 52);
-
-  const size_t in_set = (size_t)tile * kTile + (size_t)threadIdx.x * 4;
-  const size_t base = set * v.n_particles + in_set;
-  unsigned long long q[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    q[j] = 0;
-    if (in_set + j < v.n_particles && !dead) {
-      const double lw = v.logw[base + j];
-      const double w = GIVEN ? lw : det_exp(lw - mx);
-      q[j] = (unsigned long long)__double2ll_rn(w * scale);
-    }
+__device__ __forceinline__ bool finish_set(const View &v, int row, size_t set,
+                                           unsigned long long tot) {
+  const double n = (double)v.n_particles;
+  const double tot_d = (double)tot;
+  const double u = v.u_draws[(size_t)(row < 0 ? 0 : row) * v.n_sets + set];
+  SetInfo si;
+  si.uu0 = tot_d * u / n;
+  si.du = tot_d / n;
+  v.setinfo[set] = si;
+  if (row < 0) return false;
+  const double mx = key_to_double(v.wmax[(size_t)row * v.n_sets + set]);
+  if (!(mx > __longlong_as_double(0xfff0000000000000LL)) || tot == 0) {
+    v.ll[set] = __longlong_as_double(0xfff0000000000000LL);
+    return true;
   }
-  q[1] += q[0]; q[2] += q[1]; q[3] += q[2];
-  unsigned long long incl = q[3];
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const unsigned long long o = shfl_up_u64(incl, d);
-    if ((threadIdx.x & 31) >= d) incl += o;
-  }
-  if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
-  __syncthreads();
-  unsigned long long offset = incl - q[3];
-  unsigned long long total = 0;
-#pragma unroll
-  for (int w = 0; w < kTileThreads / 32; ++w) {
-    if (w < (int)(threadIdx.x >> 5)) offset += s_warp[w];
-    total += s_warp[w];
-  }
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-    if (in_set + j < v.n_particles) v.cw[base + j] = q[j] + offset;
-  if (threadIdx.x == 0) v.tile_incl[blockIdx.x] = total;
+  const double mean = (tot_d * bits_to_double((uint64_t)(1023 - v.shift) << 52)) / n;
+  v.ll[set] += det_log(mean) + mx;
+  return false;
 }
 
-// ---------------------------------------------------------------------------
-// K2b: one block.  Warp w owns sets w, w+32, ...: inclusive prefix over the
-// set's tile sums, log-mean-exp into ll, thresholds for K3.  Then thread 0
-// applies the early-exit rule of R/particle_filter_state.R:463-474.
-// row < 0: model$resample(weights) -- thresholds only, u taken from u_draws[0..].
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_finalize_row(View v, int row) {
+// Run by the LAST block of K2 to finish: inclusive prefix over every set's tile
+// sums, finish_set, then the early-exit rule of R/particle_filter_state.R:463-474.
+__device__ __forceinline__ void finalize_sets(const View &v, int row) {
+  __shared__ unsigned long long s_tot[kTileThreads / 32];
+  __shared__ unsigned long long s_carry;
   __shared__ int s_dead;
-  if (v.flags[0]) return;
-  if (threadIdx.x == 0) s_dead = 0;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = v.tiles_per_set;
-  const int chunk = (T + 31) / 32;
-  for (size_t set = warp; set < v.n_sets; set += 32) {
-    if (row >= 0 && datum_is_na(v, row, set)) continue;
-    unsigned long long *ts = v.tile_incl + set * T;
-    const int lo = lane * chunk, hi = min(T, lo + chunk);
-    unsigned long long local = 0;
-    for (int t = lo; t < hi; ++t) local += ts[t];
-    unsigned long long incl = local;
+  if (tid == 0) s_dead = 0;
+  __syncthreads();
+  if (T <= 32) {
+    // many small sets (nested populations, SMC^2): one warp per set
+    for (size_t set = warp; set < v.n_sets; set += kTileThreads / 32) {
+      if (row >= 0 && datum_is_na(v, row, set)) continue;
+      unsigned long long *ts = v.tile_incl + set * T;
+      unsigned long long incl = lane < T ? __ldcg(ts + lane) : 0ULL;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const unsigned long long o = shfl_up_u64(incl, d);
-      if (lane >= d) incl += o;
-    }
-    unsigned long long run = incl - local;
-    for (int t = lo; t < hi; ++t) { run += ts[t]; ts[t] = run; }
-    const unsigned long long tot = shfl_u64(incl, 31);
-    if (lane == 0) {
-      const double n = (double)v.n_particles;
-      const double tot_d = (double)tot;
-      const double u = v.u_draws[(size_t)(row < 0 ? 0 : row) * v.n_sets + set];
-      SetInfo si;
-      si.uu0 = tot_d * u / n;
-      si.du = tot_d / n;
-      v.setinfo[set] = si;
-      if (row >= 0) {
-        const double mx = key_to_double(v.wmax[(size_t)row * v.n_sets + set]);
-        if (!(mx > __longlong_as_double(0xfff0000000000000LL)) || tot == 0) {
-          v.ll[set] = __longlong_as_double(0xfff0000000000000LL);
-          atomicExch(&s_dead, 1);
-        } else {
-          const double mean = (tot_d * bits_to_double((uint64_t)(1023 - v.shift) << 52)) / n;
-          v.ll[set] += det_log(mean) + mx;
-        }
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long o = shfl_up_u64(incl, d);
+        if (lane >= d) incl += o;
       }
+      if (lane < T) ts[lane] = incl;
+      const unsigned long long tot = shfl_u64(incl, 31);
+      if (lane == 0 && finish_set(v, row, set, tot)) atomicExch(&s_dead, 1);
+    }
+  } else {
+    // few big sets: the whole block scans one set's tiles, 256 at a time
+    for (size_t set = 0; set < v.n_sets; ++set) {
+      if (row >= 0 && datum_is_na(v, row, set)) continue;
+      unsigned long long *ts = v.tile_incl + set * T;
+      if (tid == 0) s_carry = 0;
+      __syncthreads();
+      for (int base = 0; base < T; base += kTileThreads) {
+        const int t = base + tid;
+        unsigned long long incl = t < T ? __ldcg(ts + t) : 0ULL;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const unsigned long long o = shfl_up_u64(incl, d);
+          if (lane >= d) incl += o;
+        }
+        if (lane == 31) s_tot[warp] = incl;
+        __syncthreads();
+        unsigned long long offset = s_carry;
+#pragma unroll
+        for (int w = 0; w < kTileThreads / 32; ++w)
+          if (w < warp) offset += s_tot[w];
+        if (t < T) ts[t] = incl + offset;
+        __syncthreads();
+        if (tid == kTileThreads - 1) s_carry = incl + offset;
+        __syncthreads();
+      }
+      if (tid == 0 && finish_set(v, row, set, s_carry)) s_dead = 1;
+      __syncthreads();
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0 && row >= 0) {
+  if (tid == 0 && row >= 0) {
     bool stop = s_dead != 0;
     if (!stop && v.n_min > 0) {
       if (v.n_sets == 1) {
@@ -297,44 +327,109 @@ __global__ void __launch_bounds__(1024) k_finalize_row(View v, int row) {
 }
 
 // ---------------------------------------------------------------------------
-// K3+K4: thread i owns output slot i.  Its threshold ceil(uu0 + i du) is
-// compared exactly (integers) with the cumulative weights: binary search over
-// the set's tile prefix, then inside the tile.  Thresholds increase with i, so
-// neighbouring threads search neighbouring addresses and the gather reads are
-// near-coalesced (kappa is monotone).  kappa is written only when trajectories
-// are being saved.
+// K2: one block per tile of kTile particles (tiles never straddle a set):
+// w = exp(logw - max) -> fixed point, inclusive scan inside the tile, tile sum.
+// The last block to finish (ticket counter) then runs finalize_sets, so the
+// whole weights stage is one launch.
+// GIVEN = true: `logw` already holds weights in [0,1] (model$resample(weights)).
+// ---------------------------------------------------------------------------
+template <bool GIVEN>
+__global__ void __launch_bounds__(kTileThreads) k_weights_scan(View v, int row) {
+  __shared__ unsigned long long s_warp[kTileThreads / 32];
+  __shared__ bool s_last;
+  if (v.flags[0]) return;
+  const size_t set = blockIdx.x / v.tiles_per_set;
+  const int tile = blockIdx.x % v.tiles_per_set;
+  if (GIVEN || !datum_is_na(v, row, set)) {
+    double mx = 0.0;
+    if (!GIVEN) mx = key_to_double(v.wmax[(size_t)row * v.n_sets + set]);
+    const bool dead = !GIVEN && !(mx > __longlong_as_double(0xfff0000000000000LL));
+    const double scale = bits_to_double((uint64_t)(1023 + v.shift) << 52);
+    const size_t in_set = (size_t)tile * kTile + (size_t)threadIdx.x * 4;
+    const size_t base = set * v.n_particles + in_set;
+    unsigned long long q[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      q[j] = 0;
+      if (in_set + j < v.n_particles && !dead) {
+        const double lw = v.logw[base + j];
+        const double w = GIVEN ? lw : det_exp(lw - mx);
+        q[j] = (unsigned long long)__double2ll_rn(w * scale);
+      }
+    }
+    q[1] += q[0]; q[2] += q[1]; q[3] += q[2];
+    unsigned long long incl = q[3];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long o = shfl_up_u64(incl, d);
+      if ((threadIdx.x & 31) >= d) incl += o;
+    }
+    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    unsigned long long offset = incl - q[3];
+    unsigned long long total = 0;
+#pragma unroll
+    for (int w = 0; w < kTileThreads / 32; ++w) {
+      if (w < (int)(threadIdx.x >> 5)) offset += s_warp[w];
+      total += s_warp[w];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (in_set + j < v.n_particles) v.cw[base + j] = q[j] + offset;
+    if (threadIdx.x == 0) v.tile_incl[blockIdx.x] = total;
+  }
+  // ---- the last block to get here finishes the stage
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(v.ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  if (threadIdx.x == 0) *v.ticket = 0;
+  __threadfence();
+  finalize_sets(v, row);
+}
+
+// ---------------------------------------------------------------------------
+// Stand-alone resample + gather (src -> dst), used where the resampled state
+// must exist in memory: snapshots and model$resample.
+// row < 0: every set is resampled; else sets whose datum is NA copy through.
 // ---------------------------------------------------------------------------
 template <int NS>
 __global__ void __launch_bounds__(kGatherThreads)
-k_resample_gather(View v, int row, int *__restrict__ kappa_out) {
+k_resample_gather(View v, int row, const double *__restrict__ src_buf,
+                  double *__restrict__ dst_buf, int *__restrict__ kappa_out) {
   if (v.flags[0]) return;
   const size_t i = (size_t)blockIdx.x * kGatherThreads + threadIdx.x;
   if (i >= v.n_total) return;
   const size_t set = v.n_sets == 1 ? 0 : i / v.n_particles;
-  const size_t il = i - set * v.n_particles;
   size_t src = i;
-  if (row < 0 || !datum_is_na(v, row, set)) {
-    const SetInfo si = v.setinfo[set];
-    const unsigned long long thr =
-        (unsigned long long)__double2ll_ru(si.uu0 + (double)il * si.du);
-    const unsigned long long *ts = v.tile_incl + set * v.tiles_per_set;
-    int lo = 0, hi = v.tiles_per_set - 1;  // first tile whose inclusive prefix reaches thr
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (__ldg(ts + mid) >= thr) hi = mid; else lo = mid + 1;
+  if (row < 0 || !datum_is_na(v, row, set)) src = resample_source(v, set, i - set * v.n_particles);
+#pragma unroll
+  for (int s = 0; s < NS; ++s) dst_buf[(size_t)s * v.ld + i] = src_buf[(size_t)s * v.ld + src];
+  if (kappa_out) kappa_out[i] = (int)src;
+}
+
+// End of a filter call over rows [first, last): bring the live state back into
+// v.y.  The last row always wrote v.y_tmp.  Running: resample row last-1 (if it
+// was weighed) on the way.  Stopped at row rs: the post-update state of rs, as
+// it is (R breaks before resampling), from whichever buffer rs wrote.
+template <int NS>
+__global__ void __launch_bounds__(kGatherThreads)
+k_finish_state(View v, int last, int last_weighted, int *__restrict__ kappa_out) {
+  const size_t i = (size_t)blockIdx.x * kGatherThreads + threadIdx.x;
+  if (i >= v.n_total) return;
+  if (v.flags[0]) {
+    const int rs = v.flags[1];
+    if (((last - 1 - rs) & 1) == 0) {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) v.y[(size_t)s * v.ld + i] = v.y_tmp[(size_t)s * v.ld + i];
     }
-    const unsigned long long before = lo ? __ldg(ts + lo - 1) : 0ULL;
-    const unsigned long long rem = thr > before ? thr - before : 0ULL;
-    const size_t tile_base = (size_t)lo * kTile;
-    const size_t in_tile = min((size_t)kTile, v.n_particles - tile_base);
-    const unsigned long long *cw = v.cw + set * v.n_particles + tile_base;
-    int a = 0, b = (int)in_tile - 1;
-    while (a < b) {
-      const int mid = (a + b) >> 1;
-      if (__ldg(cw + mid) >= rem) b = mid; else a = mid + 1;
-    }
-    src = set * v.n_particles + tile_base + a;
+    return;
   }
+  const size_t set = v.n_sets == 1 ? 0 : i / v.n_particles;
+  size_t src = i;
+  if (last_weighted && !datum_is_na(v, last - 1, set))
+    src = resample_source(v, set, i - set * v.n_particles);
 #pragma unroll
   for (int s = 0; s < NS; ++s) v.y[(size_t)s * v.ld + i] = v.y_tmp[(size_t)s * v.ld + src];
   if (kappa_out) kappa_out[i] = (int)src;
@@ -421,19 +516,12 @@ __global__ void k_gather_by_kappa(View v, const int *__restrict__ kappa) {
   for (int s = 0; s < v.n_state; ++s) v.y_tmp[(size_t)s * v.ld + i] = v.y[(size_t)s * v.ld + src];
 }
 
-__global__ void k_copy_state_if_running(View v, double *__restrict__ dst) {
+__global__ void k_copy_state_if_running(View v, const double *__restrict__ src,
+                                        double *__restrict__ dst) {
   if (v.flags[0]) return;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= v.n_total) return;
-  for (int s = 0; s < v.n_state; ++s) dst[(size_t)s * v.ld + i] = v.y[(size_t)s * v.ld + i];
-}
-
-// a stopped filter leaves the post-run state of the stop row as the live state
-__global__ void k_adopt_tmp_if_stopped(View v) {
-  if (!v.flags[0]) return;
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= v.n_total) return;
-  for (int s = 0; s < v.n_state; ++s) v.y[(size_t)s * v.ld + i] = v.y_tmp[(size_t)s * v.ld + i];
+  for (int s = 0; s < v.n_state; ++s) dst[(size_t)s * v.ld + i] = src[(size_t)s * v.ld + i];
 }
 
 __global__ void k_iota(int *out, size_t n) {

@@ -28,12 +28,37 @@ __device__ __forceinline__ double pow_int(double x, int n) {
   return acc;
 }
 
+// RN(1/k) for k = 1..kInvSmall-1 (entry 0 unused), filled by the host with IEEE division
+constexpr int kInvSmall = 64;
+__constant__ double c_inv_small[kInvSmall];
+__constant__ double c_stirling_tail[10] = {
+    0.0810614667953272,  0.0413406959554092,  0.0276779256849983, 0.02079067210376509,
+    0.0166446911898211,  0.0138761288230707,  0.0118967099458917, 0.0104112652619720,
+    0.00925546218271273, 0.00833056343336287};
+
+// a / k for a small integer k, correctly rounded WITHOUT the generic division
+// sequence: y = RN(1/k) from the table, q0 = RN(a y), then two residual
+// corrections q <- RN(q + RN(a - k q) y).  The residuals are exact (fma), the
+// first correction makes q faithful, and Markstein's theorem then gives
+// RN(a/k) from the second -- so the bits equal those of `a / k`.  Needs a away
+// from overflow/underflow; the caller checks that once per draw.
+__device__ __forceinline__ double div_small_int(double a, double kd, double y) {
+  double q = a * y;
+  double r = fma(-q, kd, a);
+  q = fma(r, y, q);
+  r = fma(-q, kd, a);
+  return fma(r, y, q);
+}
+
+// CDF walk from k = 0.  Every lane of a warp is at the same k in the same
+// iteration, so 1/k is a uniform constant-bank load.
 template <int SCR>
 __device__ __forceinline__ double binomial_inversion(Xoshiro &rng, int n, double q) {
   const double qq = 1.0 - q;
   const double r = q / qq;
   const double g = r * (double)(n + 1);
   const double f0 = pow_int(qq, n);
+  const bool safe = g > 1e-280 && g < 1e280;
   for (;;) {
     double u = xo_real<SCR>(rng);
     double f = f0, f_prev = f0;
@@ -42,7 +67,9 @@ __device__ __forceinline__ double binomial_inversion(Xoshiro &rng, int n, double
     while (u >= f) {
       u -= f;
       ++k;
-      f *= (g / (double)k - r);
+      const double kd = (double)k;
+      const double gk = (safe && k < kInvSmall) ? div_small_int(g, kd, c_inv_small[k]) : g / kd;
+      f *= (gk - r);
       if (f == f_prev || k > n) { ok = false; break; }
       f_prev = f;
     }
@@ -51,21 +78,7 @@ __device__ __forceinline__ double binomial_inversion(Xoshiro &rng, int n, double
 }
 
 __device__ __forceinline__ double stirling_tail(double k) {
-  // table for k <= 9 held as immediates (no local-memory array)
-  if (k <= 9.0) {
-    const int i = (int)k;
-    double t = 0.0810614667953272;
-    t = i == 1 ? 0.0413406959554092 : t;
-    t = i == 2 ? 0.0276779256849983 : t;
-    t = i == 3 ? 0.02079067210376509 : t;
-    t = i == 4 ? 0.0166446911898211 : t;
-    t = i == 5 ? 0.0138761288230707 : t;
-    t = i == 6 ? 0.0118967099458917 : t;
-    t = i == 7 ? 0.0104112652619720 : t;
-    t = i == 8 ? 0.00925546218271273 : t;
-    t = i == 9 ? 0.00833056343336287 : t;
-    return t;
-  }
+  if (k <= 9.0) return c_stirling_tail[(int)k];
   const double kp1sq = (k + 1.0) * (k + 1.0);
   return (1.0 / 12.0 - (1.0 / 360.0 - 1.0 / 1260.0 / kp1sq) / kp1sq) / (k + 1.0);
 }
