@@ -92,9 +92,9 @@ int device_constants(int device) {
   static std::map<int, bool> done;
   std::lock_guard<std::mutex> lock(mu);
   if (done[device]) return MCB_OK;
-  double inv[mcb::kInvSmall];
-  inv[0] = 0.0;
-  for (int k = 1; k < mcb::kInvSmall; ++k) inv[k] = 1.0 / (double)k;
+  double2 inv[mcb::kInvSmall];
+  inv[0] = make_double2(0.0, 0.0);
+  for (int k = 1; k < mcb::kInvSmall; ++k) inv[k] = make_double2((double)k, 1.0 / (double)k);
   MCB_CUDA(cudaMemcpyToSymbol(mcb::c_inv_small, inv, sizeof inv));
   done[device] = true;
   return MCB_OK;
@@ -256,6 +256,14 @@ void finish_state(mcb_model *m, int last, int last_weighted, int *kappa_out) {
     mcb::k_finish_state<5><<<grid, mcb::kGatherThreads, 0, m->stream>>>(m->v, last, last_weighted, kappa_out);
   else
     mcb::k_finish_state<4><<<grid, mcb::kGatherThreads, 0, m->stream>>>(m->v, last, last_weighted, kappa_out);
+  ++m->launches;
+}
+
+void prepare_sets(mcb_model *m) {
+  const int tables = m->model_id == 0 ? mcb::SirModel::kTables : mcb::SirsModel::kTables;
+  const dim3 grid(blocks_for((size_t)tables * m->v.n_tab, 256), (unsigned)m->v.n_sets);
+  if (m->model_id == 0) mcb::k_prepare_sets<mcb::SirModel><<<grid, 256, 0, m->stream>>>(m->v);
+  else mcb::k_prepare_sets<mcb::SirsModel><<<grid, 256, 0, m->stream>>>(m->v);
   ++m->launches;
 }
 
@@ -643,6 +651,25 @@ int mcb_alloc(int model_id, const double *pars, size_t n_particles, size_t n_par
   ALLOC(v.y_tmp, (size_t)v.n_state * v.ld * sizeof(double));
   ALLOC(v.rng, 4 * v.ld_rng * sizeof(uint64_t));
   ALLOC(m->d_pars, n_sets * mcb::kMaxPar * sizeof(double));
+  {
+    // memo tables cover compartment counts up to the largest initial population,
+    // within 64 Ki entries and 256 MB in total; larger counts take the direct path
+    double max_pop = 0.0;
+    const int np = m->desc->n_par;
+    for (size_t p = 0; p < n_sets; ++p) {
+      const double *pp = pars + p * np;
+      const double pop = model_id == 0 ? pp[4] + pp[2] + pp[5] : pp[5] + pp[3] + pp[6];
+      if (pop > max_pop) max_pop = pop;
+    }
+    size_t n_tab = max_pop < 65535.0 ? (size_t)max_pop + 1 : 65536;
+    n_tab = round_up(n_tab < 256 ? 256 : n_tab, 256);
+    const size_t budget = ((size_t)256 << 20) / (n_sets * mcb::kMaxTables * sizeof(double));
+    if (n_tab > budget) n_tab = budget / 256 * 256;
+    if (n_tab < 256) n_tab = 256;
+    v.n_tab = (int)n_tab;
+  }
+  ALLOC(v.derived, n_sets * mcb::kMaxDerived * sizeof(double));
+  ALLOC(v.tables, n_sets * mcb::kMaxTables * (size_t)v.n_tab * sizeof(double));
   ALLOC(v.logw, v.ld * sizeof(double));
   ALLOC(v.cw, v.ld * sizeof(unsigned long long));
   ALLOC(v.tile_incl, n_sets * v.tiles_per_set * sizeof(unsigned long long));
@@ -713,7 +740,7 @@ int mcb_free(mcb_model *m) {
   cudaSetDevice(m->device);
   if (m->stream) cudaStreamSynchronize(m->stream);
   clear_graphs(m);
-  void *ptrs[] = {m->v.y, m->v.y_tmp, m->v.rng, m->d_pars, m->v.logw, m->v.cw, m->v.tile_incl,
+  void *ptrs[] = {m->v.y, m->v.y_tmp, m->v.rng, m->v.derived, m->v.tables, m->d_pars, m->v.logw, m->v.cw, m->v.tile_incl,
                   m->v.setinfo, m->d_ll, m->d_min_ll, m->d_flags, m->d_ticket, m->d_index, m->d_kappa, m->d_u,
                   m->d_wmax, m->d_fs_after, m->d_data, m->d_stage, m->d_hist_value,
                   m->d_hist_order, m->d_traj, m->d_snap};
@@ -852,6 +879,7 @@ int mcb_update_state(mcb_model *m, const double *pars, const double *state, size
     MCB_CUDA(cudaMemcpyAsync(m->d_pars, m->pars_host.data(),
                              m->pars_host.size() * sizeof(double), cudaMemcpyHostToDevice,
                              m->stream));
+    prepare_sets(m);
     if (set_initial_state && !state) set_initial(m);
   }
   if (state) {

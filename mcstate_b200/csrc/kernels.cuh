@@ -30,8 +30,9 @@
 namespace mcb {
 
 constexpr int kRunThreads = 128;
-constexpr int kTile = 1024;         // particles per weight tile
-constexpr int kTileThreads = 256;   // 4 consecutive particles per thread
+constexpr int kTileThreads = 256;
+constexpr int kTileItems = 8;       // consecutive particles per thread in K2
+constexpr int kTile = kTileThreads * kTileItems;  // particles per weight tile
 constexpr int kGatherThreads = 256;
 
 struct SetInfo {   // per parameter set, rewritten every interval by K2b
@@ -43,6 +44,8 @@ struct View {
   double *y_tmp;      // [n_state][ld]   post-update, pre-resample
   uint64_t *rng;      // [4][ld_rng]     stream n_total is the filter's
   const double *pars; // [n_sets][kMaxPar]
+  double *derived;    // [n_sets][kMaxDerived]  parameter-only constants (Model::derive)
+  double *tables;     // [n_sets][kMaxTables][n_tab] memo tables (Model::table)
   const double *data; // [n_data][data_sets][2] = {value, lgamma(value+1)}
   double *logw;       // [n_total]
   unsigned long long *cw;        // [n_total] inclusive fixed-point cumsum inside a tile
@@ -56,7 +59,7 @@ struct View {
   unsigned int *ticket; // K2 block counter (the last block finalizes)
   const int *index;   // [n_index] rows returned by run()/saved in trajectories
   size_t n_particles, n_sets, n_total, ld, ld_rng;
-  int n_state, n_index, n_min, data_sets, tiles_per_set, shift, deterministic;
+  int n_state, n_index, n_min, data_sets, tiles_per_set, shift, deterministic, n_tab;
 };
 
 // ---- order-preserving map double -> u64 so max is one integer atomic --------
@@ -131,7 +134,7 @@ __device__ __forceinline__ size_t resample_source(const View &v, size_t set, siz
 // kappa_out (trajectories only) records src, the order slice of prev_row.
 // ---------------------------------------------------------------------------
 #ifndef MCB_K1_MINBLOCKS
-#define MCB_K1_MINBLOCKS 8
+#define MCB_K1_MINBLOCKS 12
 #endif
 template <class M, int SCR, bool HIST>
 __global__ void __launch_bounds__(kRunThreads, MCB_K1_MINBLOCKS)
@@ -144,8 +147,9 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
   const bool live = i < v.n_total;
   const size_t ii = live ? i : v.n_total - 1;
   const size_t set = v.n_sets == 1 ? 0 : ii / v.n_particles;
-  const double *pars = v.pars + set * kMaxPar;
-  const typename M::Ctx ctx = M::context(pars);
+  const SetData sd{v.derived + set * kMaxDerived,
+                   v.tables + set * (size_t)kMaxTables * v.n_tab, v.n_tab};
+  const typename M::Ctx ctx = M::context(sd);
   const bool det = v.deterministic != 0;
 
   double y[M::kState];
@@ -273,15 +277,27 @@ __device__ __forceinline__ void finalize_sets(const View &v, int row) {
       if (lane == 0 && finish_set(v, row, set, tot)) atomicExch(&s_dead, 1);
     }
   } else {
-    // few big sets: the whole block scans one set's tiles, 256 at a time
+    // few big sets: the whole block scans one set's tiles; each thread owns
+    // `per` consecutive tiles so a set of up to 256 * 8 tiles is one pass
+    constexpr int kPer = 8;
     for (size_t set = 0; set < v.n_sets; ++set) {
       if (row >= 0 && datum_is_na(v, row, set)) continue;
       unsigned long long *ts = v.tile_incl + set * T;
       if (tid == 0) s_carry = 0;
       __syncthreads();
-      for (int base = 0; base < T; base += kTileThreads) {
-        const int t = base + tid;
-        unsigned long long incl = t < T ? __ldcg(ts + t) : 0ULL;
+      for (int base = 0; base < T; base += kTileThreads * kPer) {
+        const int span = min(T - base, kTileThreads * kPer);
+        const int per = (span + kTileThreads - 1) / kTileThreads;
+        const int lo = base + tid * per, hi = min(base + span, lo + per);
+        unsigned long long x[kPer];
+        unsigned long long local = 0;
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+          x[j] = (j < per && lo + j < hi) ? __ldcg(ts + lo + j) : 0ULL;
+          local += x[j];
+          x[j] = local;
+        }
+        unsigned long long incl = local;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
           const unsigned long long o = shfl_up_u64(incl, d);
@@ -289,13 +305,15 @@ __device__ __forceinline__ void finalize_sets(const View &v, int row) {
         }
         if (lane == 31) s_tot[warp] = incl;
         __syncthreads();
-        unsigned long long offset = s_carry;
+        unsigned long long offset = s_carry + incl - local;
 #pragma unroll
         for (int w = 0; w < kTileThreads / 32; ++w)
           if (w < warp) offset += s_tot[w];
-        if (t < T) ts[t] = incl + offset;
+#pragma unroll
+        for (int j = 0; j < kPer; ++j)
+          if (j < per && lo + j < hi) ts[lo + j] = x[j] + offset;
         __syncthreads();
-        if (tid == kTileThreads - 1) s_carry = incl + offset;
+        if (tid == kTileThreads - 1) s_carry = offset + local;
         __syncthreads();
       }
       if (tid == 0 && finish_set(v, row, set, s_carry)) s_dead = 1;
@@ -334,7 +352,7 @@ __device__ __forceinline__ void finalize_sets(const View &v, int row) {
 // GIVEN = true: `logw` already holds weights in [0,1] (model$resample(weights)).
 // ---------------------------------------------------------------------------
 template <bool GIVEN>
-__global__ void __launch_bounds__(kTileThreads) k_weights_scan(View v, int row) {
+__global__ void __launch_bounds__(kTileThreads, 4) k_weights_scan(View v, int row) {
   __shared__ unsigned long long s_warp[kTileThreads / 32];
   __shared__ bool s_last;
   if (v.flags[0]) return;
@@ -345,20 +363,36 @@ __global__ void __launch_bounds__(kTileThreads) k_weights_scan(View v, int row) 
     if (!GIVEN) mx = key_to_double(v.wmax[(size_t)row * v.n_sets + set]);
     const bool dead = !GIVEN && !(mx > __longlong_as_double(0xfff0000000000000LL));
     const double scale = bits_to_double((uint64_t)(1023 + v.shift) << 52);
-    const size_t in_set = (size_t)tile * kTile + (size_t)threadIdx.x * 4;
+    const size_t in_set = (size_t)tile * kTile + (size_t)threadIdx.x * kTileItems;
     const size_t base = set * v.n_particles + in_set;
-    unsigned long long q[4];
+    const bool full = in_set + kTileItems <= v.n_particles && (base & 1) == 0;
+    double lw[kTileItems];
+    if (full) {  // 16-byte vector loads: the 8 values of a thread are contiguous
+      const double2 *src = reinterpret_cast<const double2 *>(v.logw + base);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      q[j] = 0;
-      if (in_set + j < v.n_particles && !dead) {
-        const double lw = v.logw[base + j];
-        const double w = GIVEN ? lw : det_exp(lw - mx);
-        q[j] = (unsigned long long)__double2ll_rn(w * scale);
+      for (int j = 0; j < kTileItems / 2; ++j) {
+        const double2 t = src[j];
+        lw[2 * j] = t.x;
+        lw[2 * j + 1] = t.y;
       }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kTileItems; ++j)
+        lw[j] = in_set + j < v.n_particles ? v.logw[base + j] : __longlong_as_double(0xfff0000000000000LL);
     }
-    q[1] += q[0]; q[2] += q[1]; q[3] += q[2];
-    unsigned long long incl = q[3];
+    unsigned long long q[kTileItems];
+    unsigned long long run = 0;
+#pragma unroll
+    for (int j = 0; j < kTileItems; ++j) {
+      unsigned long long x = 0;
+      if (in_set + j < v.n_particles && !dead) {
+        const double w = GIVEN ? lw[j] : det_exp(lw[j] - mx);
+        x = (unsigned long long)__double2ll_rn(w * scale);
+      }
+      run += x;
+      q[j] = run;
+    }
+    unsigned long long incl = run;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const unsigned long long o = shfl_up_u64(incl, d);
@@ -366,22 +400,31 @@ __global__ void __launch_bounds__(kTileThreads) k_weights_scan(View v, int row) 
     }
     if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
     __syncthreads();
-    unsigned long long offset = incl - q[3];
+    unsigned long long offset = incl - run;
     unsigned long long total = 0;
 #pragma unroll
     for (int w = 0; w < kTileThreads / 32; ++w) {
       if (w < (int)(threadIdx.x >> 5)) offset += s_warp[w];
       total += s_warp[w];
     }
+    if (full) {
+      ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(v.cw + base);
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (in_set + j < v.n_particles) v.cw[base + j] = q[j] + offset;
+      for (int j = 0; j < kTileItems / 2; ++j)
+        dst[j] = make_ulonglong2(q[2 * j] + offset, q[2 * j + 1] + offset);
+    } else {
+#pragma unroll
+      for (int j = 0; j < kTileItems; ++j)
+        if (in_set + j < v.n_particles) v.cw[base + j] = q[j] + offset;
+    }
     if (threadIdx.x == 0) v.tile_incl[blockIdx.x] = total;
   }
-  // ---- the last block to get here finishes the stage
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(v.ticket, 1u) == gridDim.x - 1;
+  // ---- the last block to get here finishes the stage.  Only the tile sum
+  // (written by thread 0) is read by that block; cw is for the next launch.
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(v.ticket, 1u) == gridDim.x - 1;
+  }
   __syncthreads();
   if (!s_last) return;
   if (threadIdx.x == 0) *v.ticket = 0;
@@ -474,6 +517,26 @@ __global__ void k_filter_finish(View v, int row_first, int row_last, const uint6
   v.rng[1 * v.ld_rng + f] = fs_after[4 * done_last + 1];
   v.rng[2 * v.ld_rng + f] = fs_after[4 * done_last + 2];
   v.rng[3 * v.ld_rng + f] = fs_after[4 * done_last + 3];
+}
+
+// Once per update_state(pars): the parameter-only constants and memo tables of
+// every set (blockIdx.y = set).
+template <class M>
+__global__ void k_prepare_sets(View v) {
+  const size_t set = blockIdx.y;
+  double d[kMaxDerived];
+#pragma unroll
+  for (int k = 0; k < kMaxDerived; ++k) d[k] = 0.0;
+  M::derive(v.pars + set * kMaxPar, d);
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e == 0) {
+#pragma unroll
+    for (int k = 0; k < kMaxDerived; ++k) v.derived[set * kMaxDerived + k] = d[k];
+  }
+  if (e < M::kTables * v.n_tab) {
+    const int t = e / v.n_tab, n = e - t * v.n_tab;
+    v.tables[(set * kMaxTables + t) * (size_t)v.n_tab + n] = M::table(t, n, d);
+  }
 }
 
 template <class M>

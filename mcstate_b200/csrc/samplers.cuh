@@ -28,9 +28,10 @@ __device__ __forceinline__ double pow_int(double x, int n) {
   return acc;
 }
 
-// RN(1/k) for k = 1..kInvSmall-1 (entry 0 unused), filled by the host with IEEE division
+// {(double)k, RN(1/k)} for k = 0..kInvSmall-1 (entry 0 unused), filled by the host
+// with IEEE division: the walk reads its divisor and reciprocal with one uniform load
 constexpr int kInvSmall = 64;
-__constant__ double c_inv_small[kInvSmall];
+__constant__ double2 c_inv_small[kInvSmall];
 __constant__ double c_stirling_tail[10] = {
     0.0810614667953272,  0.0413406959554092,  0.0276779256849983, 0.02079067210376509,
     0.0166446911898211,  0.0138761288230707,  0.0118967099458917, 0.0104112652619720,
@@ -50,31 +51,48 @@ __device__ __forceinline__ double div_small_int(double a, double kd, double y) {
   return fma(r, y, q);
 }
 
-// CDF walk from k = 0.  Every lane of a warp is at the same k in the same
-// iteration, so 1/k is a uniform constant-bank load.
+// CDF walk from k = 0 given r = q/(1-q) and f0 = (1-q)^n: stop at the first k
+// with u < f_k, where f_k = f_{k-1} (g/k - r).  An attempt is abandoned (fresh
+// uniform) when f stops changing or k runs past n.
+// Every lane of a warp is at the same k in the same iteration, so the table
+// entry is a uniform constant-bank load.  The first loop covers k up to
+// min(n, kInvSmall - 1) with the table division and no inner branch (k <= n
+// holds by construction there); the second is the general form.
 template <int SCR>
-__device__ __forceinline__ double binomial_inversion(Xoshiro &rng, int n, double q) {
-  const double qq = 1.0 - q;
-  const double r = q / qq;
+__device__ __forceinline__ double inversion_walk(Xoshiro &rng, int n, double r, double f0) {
   const double g = r * (double)(n + 1);
-  const double f0 = pow_int(qq, n);
   const bool safe = g > 1e-280 && g < 1e280;
+  const int k_fast = safe ? min(n, kInvSmall - 1) : 0;
   for (;;) {
     double u = xo_real<SCR>(rng);
-    double f = f0, f_prev = f0;
+    double f = f0;
     int k = 0;
     bool ok = true;
-    while (u >= f) {
+    while (u >= f && k < k_fast) {
       u -= f;
       ++k;
-      const double kd = (double)k;
-      const double gk = (safe && k < kInvSmall) ? div_small_int(g, kd, c_inv_small[k]) : g / kd;
-      f *= (gk - r);
-      if (f == f_prev || k > n) { ok = false; break; }
-      f_prev = f;
+      const double2 e = c_inv_small[k];
+      const double fn = f * (div_small_int(g, e.x, e.y) - r);
+      if (fn == f) { ok = false; break; }
+      f = fn;
+    }
+    if (ok) {
+      while (u >= f) {
+        u -= f;
+        ++k;
+        const double fn = f * (g / (double)k - r);
+        if (fn == f || k > n) { ok = false; break; }
+        f = fn;
+      }
     }
     if (ok) return (double)k;
   }
+}
+
+template <int SCR>
+__device__ __forceinline__ double binomial_inversion(Xoshiro &rng, int n, double q) {
+  const double qq = 1.0 - q;
+  return inversion_walk<SCR>(rng, n, q / qq, pow_int(qq, n));
 }
 
 __device__ __forceinline__ double stirling_tail(double k) {
@@ -83,8 +101,11 @@ __device__ __forceinline__ double stirling_tail(double k) {
   return (1.0 / 12.0 - (1.0 / 360.0 - 1.0 / 1260.0 / kp1sq) / kp1sq) / (k + 1.0);
 }
 
+#ifndef MCB_BTRS_INLINE
+#define MCB_BTRS_INLINE __forceinline__
+#endif
 template <int SCR>
-__device__ __forceinline__ double binomial_btrs(Xoshiro &rng, double n, double q) {
+__device__ MCB_BTRS_INLINE double binomial_btrs(Xoshiro &rng, double n, double q) {
   const double sd = sqrt(n * q * (1.0 - q));
   const double b = 1.15 + 2.53 * sd;
   const double a = -0.0873 + 0.0248 * b + 0.01 * q;
@@ -124,6 +145,34 @@ __device__ __forceinline__ double draw_binomial(Xoshiro &rng, bool deterministic
   const double draw = (n * q >= 10.0) ? binomial_btrs<SCR>(rng, n, q)
                                       : binomial_inversion<SCR>(rng, (int)n, q);
   return p > 0.5 ? n - draw : draw;
+}
+
+// A binomial whose probability is fixed by the parameter set (recovery, waning):
+// q, 1-q, q/(1-q) and the table n -> (1-q)^n are prepared once per parameter
+// set (k_prepare_sets), so the per-draw setup -- a division and the integer
+// power -- becomes one cached load.  Same operations, same bits.
+struct BinomialConst {
+  double p, q, qq, r;   // q = min(p, 1-p), qq = 1-q, r = q/qq
+  bool flip;            // p > 0.5
+  const double *f0;     // f0[n] = pow_int(qq, n), n < n_tab
+  int n_tab;
+};
+
+template <int SCR>
+__device__ __forceinline__ double draw_binomial_const(Xoshiro &rng, bool deterministic, double n,
+                                                      const BinomialConst &c) {
+  if (deterministic) return n * c.p;
+  if (n == 0.0 || c.p == 0.0) return 0.0;
+  if (c.p == 1.0) return n;
+  double draw;
+  if (n * c.q >= 10.0) {
+    draw = binomial_btrs<SCR>(rng, n, c.q);
+  } else {
+    const int ni = (int)n;
+    const double f0 = ni < c.n_tab ? __ldg(c.f0 + ni) : pow_int(c.qq, ni);
+    draw = inversion_walk<SCR>(rng, ni, c.r, f0);
+  }
+  return c.flip ? n - draw : draw;
 }
 
 // x log(lambda) - lambda - lgamma(x + 1); lgamma(x + 1) depends on the datum
