@@ -182,18 +182,24 @@ def run_engine(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from mcstate_b200 import dust
+    from mcstate_b200.particle_filter import particle_filter
+    from mcstate_b200.particle_filter_data import particle_filter_data
 
     t, x = load_data()
     n_steps_model = int(t[-1])
     gen = dust.dust_example("sir")
     # chain k on rank k: seeds by long jump so placement does not matter (R/pmcmc_parallel.R:133)
     seed = dust.dust_rng_distributed_state(1, 1, world)[rank]
-    model = gen.new({}, 0, N_PARTICLES, seed=seed, gpu_config=local)
-    model.set_data(dust.dust_data({"time_end": t, "incidence": x}), False)
+    data = particle_filter_data({"day": (t // RATE).astype(np.int64), "incidence": x}, "day",
+                                RATE, 0)
+    # the user-facing object: particle_filter$new(data, model, n_particles, compare = NULL)
+    pf = particle_filter(data, gen, N_PARTICLES, None, seed=seed, gpu_config=local)
+    pars = {"beta": 0.2, "gamma": 0.1}
+    pf.run(pars)                       # creates the model object and uploads the data once
+    model = pf._last_model[0]
     stream = torch.cuda.current_stream()
     model.set_stream(stream.cuda_stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    pars = {"beta": 0.2, "gamma": 0.1}
 
     def barrier():
         if world > 1:
@@ -207,9 +213,9 @@ def run_engine(args):
         return model.filter_collect()
 
     def step_e2e():
+        # particle_filter$run(pars): host parameters in, host log-likelihood out
         flush.zero_()
-        model.update_state(pars=pars, time=0)
-        return model.filter()["log_likelihood"]
+        return np.atleast_1d(pf.run(pars))
 
     for _ in range(args.warmup):
         step_resident()
@@ -289,7 +295,7 @@ def run_engine(args):
             "log_likelihood": float(ll[0]),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * 8,
                     "d2h_bytes_per_step": 8 + 8,
-                    "api": "dust_model.update_state(pars, time) + dust_model.filter()"},
+                    "api": "particle_filter(data, model, 2^20, compare=None).run(pars)"},
             "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks.summary(),
         }
