@@ -663,13 +663,13 @@ int mcb_alloc(int model_id, const double *pars, size_t n_particles, size_t n_par
     }
     size_t n_tab = max_pop < 65535.0 ? (size_t)max_pop + 1 : 65536;
     n_tab = round_up(n_tab < 256 ? 256 : n_tab, 256);
-    const size_t budget = ((size_t)256 << 20) / (n_sets * mcb::kMaxTables * sizeof(double));
+    const size_t budget = ((size_t)256 << 20) / (n_sets * mcb::kMaxTables * sizeof(double2));
     if (n_tab > budget) n_tab = budget / 256 * 256;
     if (n_tab < 256) n_tab = 256;
     v.n_tab = (int)n_tab;
   }
   ALLOC(v.derived, n_sets * mcb::kMaxDerived * sizeof(double));
-  ALLOC(v.tables, n_sets * mcb::kMaxTables * (size_t)v.n_tab * sizeof(double));
+  ALLOC(v.tables, n_sets * mcb::kMaxTables * (size_t)v.n_tab * sizeof(double2));
   ALLOC(v.logw, v.ld * sizeof(double));
   ALLOC(v.cw, v.ld * sizeof(unsigned long long));
   ALLOC(v.tile_incl, n_sets * v.tiles_per_set * sizeof(unsigned long long));

@@ -45,7 +45,7 @@ struct View {
   uint64_t *rng;      // [4][ld_rng]     stream n_total is the filter's
   const double *pars; // [n_sets][kMaxPar]
   double *derived;    // [n_sets][kMaxDerived]  parameter-only constants (Model::derive)
-  double *tables;     // [n_sets][kMaxTables][n_tab] memo tables (Model::table)
+  double2 *tables;    // [n_sets][kMaxTables][n_tab] memo tables (Model::table)
   const double *data; // [n_data][data_sets][2] = {value, lgamma(value+1)}
   double *logw;       // [n_total]
   unsigned long long *cw;        // [n_total] inclusive fixed-point cumsum inside a tile
@@ -133,6 +133,25 @@ __device__ __forceinline__ size_t resample_source(const View &v, size_t set, siz
 //   row >= 0: weigh against data row `row`; row < 0: no compare (model$run).
 // kappa_out (trajectories only) records src, the order slice of prev_row.
 // ---------------------------------------------------------------------------
+// The general form of the model steps (state as doubles, every special case of
+// the draws), out of line so the run kernel's registers are sized for the lean
+// path: deterministic mode, non-integer or out-of-table states.
+template <class M, int SCR>
+__device__ __noinline__ void run_general(double *y, uint64_t *rs, uint64_t t0, uint32_t n_steps,
+                                         const double *derived, const double2 *tables, int n_tab,
+                                         bool det) {
+  const SetData sd{derived, tables, n_tab};
+  const typename M::Ctx ctx = M::context(sd);
+  Xoshiro rng{rs[0], rs[1], rs[2], rs[3]};
+  double z[M::kState];
+#pragma unroll
+  for (int s = 0; s < M::kState; ++s) z[s] = y[s];
+  for (uint32_t k = 0; k < n_steps; ++k) M::template update<SCR>(t0 + k, z, rng, ctx, det);
+#pragma unroll
+  for (int s = 0; s < M::kState; ++s) y[s] = z[s];
+  rs[0] = rng.s0; rs[1] = rng.s1; rs[2] = rng.s2; rs[3] = rng.s3;
+}
+
 #ifndef MCB_K1_MINBLOCKS
 #define MCB_K1_MINBLOCKS 12
 #endif
@@ -142,7 +161,10 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
               uint64_t t0, uint32_t n_steps, int prev_row, int row,
               double *__restrict__ hist, int *__restrict__ kappa_out) {
   __shared__ unsigned long long s_key[kRunThreads / 32];
+  __shared__ double2 s_inv[kInvSmall];
   if (v.flags[0]) return;
+  if (threadIdx.x < kInvSmall) s_inv[threadIdx.x] = c_inv_small[threadIdx.x];
+  __syncthreads();
   const size_t i = (size_t)blockIdx.x * kRunThreads + threadIdx.x;
   const bool live = i < v.n_total;
   const size_t ii = live ? i : v.n_total - 1;
@@ -168,7 +190,24 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
     rng.s2 = v.rng[2 * v.ld_rng + i];
     rng.s3 = v.rng[3 * v.ld_rng + i];
 
-    for (uint32_t k = 0; k < n_steps; ++k) M::template update<SCR>(t0 + k, y, rng, ctx, det);
+    if (n_steps > 0) {
+      int yi[M::kState];
+      typename M::Lean lc;
+      if (!det && M::lean_load(sd, y, yi, lc)) {
+        // the usual case: integer compartments, setup from the memo tables
+        uint32_t phase = (uint32_t)(t0 % lc.freq);
+        for (uint32_t k = 0; k < n_steps; ++k) {
+          M::template lean_update<SCR>(phase == 0, yi, rng, lc, s_inv);
+          phase = phase + 1 == lc.freq ? 0 : phase + 1;
+        }
+#pragma unroll
+        for (int s = 0; s < M::kState; ++s) y[s] = (double)yi[s];
+      } else {
+        uint64_t rs[4] = {rng.s0, rng.s1, rng.s2, rng.s3};
+        run_general<M, SCR>(y, rs, t0, n_steps, sd.derived, sd.tables, sd.n_tab, det);
+        rng.s0 = rs[0]; rng.s1 = rs[1]; rng.s2 = rs[2]; rng.s3 = rs[3];
+      }
+    }
 
     if (n_steps > 0 || y_in != y_out) {
 #pragma unroll

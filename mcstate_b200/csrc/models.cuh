@@ -12,10 +12,14 @@
 //   table()    per parameter set: memo tables indexed by a compartment count
 //              (pure functions of a small integer and the parameters);
 //   context()  per thread, per launch: pointers to the above;
-//   initial(), update(), compare().
+//   initial(), update(), compare()  the general form, state as doubles;
+//   lean_load(), lean_update(), lean_store()  the same arithmetic for the usual
+//              case -- every compartment a non-negative integer, the closed
+//              population equal to the one the tables were built for -- with the
+//              state held as int32 and the per-draw setup read from the tables.
 // State lives in registers for all `rate` steps of an interval.  A memo table is
-// only consulted where its value is bit-identical to evaluating the expression
-// (the guards are in update()); counts beyond the table take the direct path.
+// only consulted where its value is bit-identical to evaluating the expression;
+// anything else takes the general path.
 #pragma once
 #include "samplers.cuh"
 
@@ -25,13 +29,66 @@ constexpr int kMaxState = 8;
 constexpr int kMaxPar = 8;
 constexpr int kMaxDerived = 16;
 constexpr int kMaxTables = 3;
+constexpr double kLeanMax = 1073741824.0;  // 2^30: counts the int32 path accepts
 
 // where a thread finds its parameter set's prepared data
 struct SetData {
-  const double *derived;  // [kMaxDerived]
-  const double *tables;   // [kMaxTables][n_tab]
+  const double *derived;   // [kMaxDerived]
+  const double2 *tables;   // [kMaxTables][n_tab]
   int n_tab;
 };
+
+// ---- memo-table entries ----------------------------------------------------
+// A draw with a probability fixed by the parameter set (recovery, waning):
+// entry n = {(1-q)^n, r (n+1)}, or {-1, .} when count n is not a plain
+// inversion draw with this probability.
+__device__ __forceinline__ double2 const_binomial_entry(double p, double q, double qq, double r,
+                                                        int n) {
+  const double g = r * (double)(n + 1);
+  const bool plain = p > 0.0 && p <= 0.5 && !((double)n * q >= 10.0) && g > 1e-280 && g < 1e280;
+  return make_double2(plain ? pow_int(qq, n) : -1.0, g);
+}
+// Infection: entry I = {q, q/(1-q)} with q = p_SI(I) dt, {0, 0} when the
+// probability is zero (no draw), {-1, .} when it is not in (0, 1/2] or r is
+// near the ends of the exponent range.
+__device__ __forceinline__ double2 infection_entry(double beta, double n_tot, double dt, int I) {
+  const double p = (1.0 - det_exp(-beta * (double)I / n_tot)) * dt;
+  if (p == 0.0) return make_double2(0.0, 0.0);
+  const double r = p / (1.0 - p);
+  const bool plain = p > 0.0 && p <= 0.5 && r > 1e-270 && r < 1e270;
+  return make_double2(plain ? p : -1.0, r);
+}
+
+// y (doubles) -> int32 compartments; false unless every value is an integer in [0, 2^30)
+template <int N>
+__device__ __forceinline__ bool to_counts(const double *y, int *yi) {
+  bool ok = true;
+#pragma unroll
+  for (int s = 0; s < N; ++s) {
+    ok = ok && y[s] >= 0.0 && y[s] < kLeanMax;
+    yi[s] = (int)y[s];
+    ok = ok && (double)yi[s] == y[s];
+  }
+  return ok;
+}
+
+// Binomial(S, q) for a state-dependent probability taken from an infection table.
+// derived[0] = beta, [1] = dt, [4] = n_tot in both models (for the rare general draw).
+template <int SCR>
+__device__ __forceinline__ int draw_infection_lean(Xoshiro &rng, int S, int I, double2 e,
+                                                   const double *__restrict__ derived,
+                                                   const double2 *__restrict__ s_inv) {
+  if (S == 0 || e.x == 0.0) return 0;
+  const double Sd1 = (double)(S + 1);
+  const double Sd = Sd1 - 1.0;
+  if (e.x < 0.0) {  // probability outside (0, 1/2]: the general draw
+    const double p = (1.0 - det_exp(-__ldg(derived + 0) * (double)I / __ldg(derived + 4))) *
+                     __ldg(derived + 1);
+    return draw_binomial_cold<SCR>(rng, Sd, p);
+  }
+  if (Sd * e.x >= 10.0) return draw_binomial_cold<SCR>(rng, Sd, e.x);
+  return walk_lean<SCR>(rng, S, e.y, pow_int_lean(1.0 - e.x, S), e.y * Sd1, s_inv);
+}
 
 struct SirModel {
   static constexpr int kState = 5;
@@ -39,7 +96,7 @@ struct SirModel {
   static constexpr int kData = 1; // incidence
   static constexpr int kTables = 2;
   enum { D_BETA, D_DT, D_EXP_NOISE, D_FREQ, D_NTOT, D_P_IR, D_Q_IR, D_QQ_IR, D_R_IR, D_FLIP_IR };
-  enum { T_F0_IR, T_PSI_DT };
+  enum { T_IR, T_SI };
 
   __device__ __forceinline__ static void derive(const double *__restrict__ p, double *d) {
     const double dt = 1.0 / p[6];
@@ -58,16 +115,16 @@ struct SirModel {
     d[D_FLIP_IR] = p_ir > 0.5 ? 1.0 : 0.0;
   }
   // entry n of table t
-  __device__ __forceinline__ static double table(int t, int n, const double *d) {
-    if (t == T_F0_IR) return pow_int(d[D_QQ_IR], n);
-    return (1.0 - det_exp(-d[D_BETA] * (double)n / d[D_NTOT])) * d[D_DT];
+  __device__ __forceinline__ static double2 table(int t, int n, const double *d) {
+    if (t == T_IR) return const_binomial_entry(d[D_P_IR], d[D_Q_IR], d[D_QQ_IR], d[D_R_IR], n);
+    return infection_entry(d[D_BETA], d[D_NTOT], d[D_DT], n);
   }
 
   struct Ctx {
     const double *derived;
     BinomialConst ir;
     double beta, dt, n_tot;
-    const double *psi_dt;
+    const double2 *tab_ir, *tab_si;
     int n_tab;
     uint32_t freq;
   };
@@ -85,9 +142,9 @@ struct SirModel {
     c.ir.qq = __ldg(d + D_QQ_IR);
     c.ir.r = __ldg(d + D_R_IR);
     c.ir.flip = __ldg(d + D_FLIP_IR) != 0.0;
-    c.ir.f0 = sd.tables + (size_t)T_F0_IR * sd.n_tab;
     c.ir.n_tab = sd.n_tab;
-    c.psi_dt = sd.tables + (size_t)T_PSI_DT * sd.n_tab;
+    c.tab_ir = sd.tables + (size_t)T_IR * sd.n_tab;
+    c.tab_si = sd.tables + (size_t)T_SI * sd.n_tab;
     return c;
   }
   __device__ __forceinline__ static void initial(const double *__restrict__ p, double *y) {
@@ -98,15 +155,7 @@ struct SirModel {
                                                 const Ctx &c, bool det) {
     const double S = y[0], I = y[1], R = y[2];
     const double N = S + I + R;
-    // p_SI dt = (1 - exp(-beta I / N)) dt: from the memo table when I is an
-    // in-range integer and N is the population the table was built for
-    double p_SI_dt;
-    const int Ii = (int)I;
-    if (N == c.n_tot && Ii >= 0 && Ii < c.n_tab && (double)Ii == I) {
-      p_SI_dt = __ldg(c.psi_dt + Ii);
-    } else {
-      p_SI_dt = (1.0 - det_exp(-c.beta * I / N)) * c.dt;
-    }
+    const double p_SI_dt = (1.0 - det_exp(-c.beta * I / N)) * c.dt;
     const double n_IR = draw_binomial_const<SCR>(rng, det, I, c.ir);
     const double n_SI = draw_binomial<SCR>(rng, det, S, p_SI_dt);
     y[0] = S - n_SI;
@@ -123,6 +172,45 @@ struct SirModel {
     const double noise = det ? 1.0 / rate : draw_exponential<SCR>(rng, rate);
     return density_poisson_log(observed, lgamma_obs1, y[4] + noise);
   }
+
+  // ---- the lean path ------------------------------------------------------
+  // only what the hot loop needs stays in registers; the cold calls fetch their
+  // parameters from `derived` when they happen
+  struct Lean {
+    const double *derived;
+    const double2 *tab;   // [kTables][n_tab]
+    double r_ir;
+    int n_tab;
+    uint32_t freq;
+  };
+  __device__ __forceinline__ static bool lean_load(const SetData &sd, const double *y, int *yi,
+                                                   Lean &c) {
+    c.derived = sd.derived;
+    c.tab = sd.tables;
+    c.n_tab = sd.n_tab;
+    c.r_ir = __ldg(sd.derived + D_R_IR);
+    c.freq = (uint32_t)__ldg(sd.derived + D_FREQ);
+    if (!to_counts<kState>(y, yi)) return false;
+    // the infection table is built for N = n_tot and covers I < n_tab
+    const double n_tot = __ldg(sd.derived + D_NTOT);
+    return y[0] + y[1] + y[2] == n_tot && n_tot < (double)sd.n_tab;
+  }
+  // `reset`: this step starts a new incidence interval (time % freq == 0)
+  template <int SCR>
+  __device__ __forceinline__ static void lean_update(bool reset, int *y, Xoshiro &rng,
+                                                     const Lean &c,
+                                                     const double2 *__restrict__ s_inv) {
+    const int S = y[0], I = y[1];
+    const double2 e_si = __ldg(c.tab + (size_t)T_SI * c.n_tab + I);  // I <= N < n_tab
+    const int n_IR = draw_binomial_const_lean<SCR>(rng, I, c.r_ir, c.tab + (size_t)T_IR * c.n_tab,
+                                                   c.n_tab, c.derived + D_P_IR, s_inv);
+    const int n_SI = draw_infection_lean<SCR>(rng, S, I, e_si, c.derived, s_inv);
+    y[0] = S - n_SI;
+    y[1] = I + n_SI - n_IR;
+    y[2] = y[2] + n_IR;
+    y[3] = y[3] + n_SI;
+    y[4] = reset ? n_SI : y[4] + n_SI;
+  }
 };
 
 struct SirsModel {
@@ -132,7 +220,7 @@ struct SirsModel {
   static constexpr int kTables = 3;
   enum { D_BETA, D_DT, D_EXP_NOISE, D_FREQ, D_NTOT, D_P_IR, D_Q_IR, D_QQ_IR, D_R_IR, D_FLIP_IR,
          D_P_RS, D_Q_RS, D_QQ_RS, D_R_RS, D_FLIP_RS };
-  enum { T_F0_IR, T_PSI_DT, T_F0_RS };
+  enum { T_IR, T_SI, T_RS };
 
   __device__ __forceinline__ static void derive(const double *__restrict__ p, double *d) {
     const double dt = 1.0 / p[7];
@@ -150,17 +238,17 @@ struct SirsModel {
     d[D_P_RS] = p_rs; d[D_Q_RS] = q2; d[D_QQ_RS] = 1.0 - q2; d[D_R_RS] = q2 / (1.0 - q2);
     d[D_FLIP_RS] = p_rs > 0.5 ? 1.0 : 0.0;
   }
-  __device__ __forceinline__ static double table(int t, int n, const double *d) {
-    if (t == T_F0_IR) return pow_int(d[D_QQ_IR], n);
-    if (t == T_F0_RS) return pow_int(d[D_QQ_RS], n);
-    return (1.0 - det_exp(-d[D_BETA] * (double)n / d[D_NTOT])) * d[D_DT];
+  __device__ __forceinline__ static double2 table(int t, int n, const double *d) {
+    if (t == T_IR) return const_binomial_entry(d[D_P_IR], d[D_Q_IR], d[D_QQ_IR], d[D_R_IR], n);
+    if (t == T_RS) return const_binomial_entry(d[D_P_RS], d[D_Q_RS], d[D_QQ_RS], d[D_R_RS], n);
+    return infection_entry(d[D_BETA], d[D_NTOT], d[D_DT], n);
   }
 
   struct Ctx {
     const double *derived;
     BinomialConst ir, rs;
     double beta, dt, n_tot;
-    const double *psi_dt;
+    const double2 *tab_ir, *tab_si, *tab_rs;
     int n_tab;
     uint32_t freq;
   };
@@ -175,11 +263,13 @@ struct SirsModel {
     c.freq = (uint32_t)__ldg(d + D_FREQ);
     c.ir.p = __ldg(d + D_P_IR); c.ir.q = __ldg(d + D_Q_IR); c.ir.qq = __ldg(d + D_QQ_IR);
     c.ir.r = __ldg(d + D_R_IR); c.ir.flip = __ldg(d + D_FLIP_IR) != 0.0;
-    c.ir.f0 = sd.tables + (size_t)T_F0_IR * sd.n_tab; c.ir.n_tab = sd.n_tab;
+    c.ir.n_tab = sd.n_tab;
     c.rs.p = __ldg(d + D_P_RS); c.rs.q = __ldg(d + D_Q_RS); c.rs.qq = __ldg(d + D_QQ_RS);
     c.rs.r = __ldg(d + D_R_RS); c.rs.flip = __ldg(d + D_FLIP_RS) != 0.0;
-    c.rs.f0 = sd.tables + (size_t)T_F0_RS * sd.n_tab; c.rs.n_tab = sd.n_tab;
-    c.psi_dt = sd.tables + (size_t)T_PSI_DT * sd.n_tab;
+    c.rs.n_tab = sd.n_tab;
+    c.tab_ir = sd.tables + (size_t)T_IR * sd.n_tab;
+    c.tab_si = sd.tables + (size_t)T_SI * sd.n_tab;
+    c.tab_rs = sd.tables + (size_t)T_RS * sd.n_tab;
     return c;
   }
   __device__ __forceinline__ static void initial(const double *__restrict__ p, double *y) {
@@ -190,13 +280,7 @@ struct SirsModel {
                                                 const Ctx &c, bool det) {
     const double S = y[0], I = y[1], R = y[2];
     const double N = S + I + R;
-    double p_SI_dt;
-    const int Ii = (int)I;
-    if (N == c.n_tot && Ii >= 0 && Ii < c.n_tab && (double)Ii == I) {
-      p_SI_dt = __ldg(c.psi_dt + Ii);
-    } else {
-      p_SI_dt = (1.0 - det_exp(-c.beta * I / N)) * c.dt;
-    }
+    const double p_SI_dt = (1.0 - det_exp(-c.beta * I / N)) * c.dt;
     const double n_SI = draw_binomial<SCR>(rng, det, S, p_SI_dt);
     const double n_IR = draw_binomial_const<SCR>(rng, det, I, c.ir);
     const double n_RS = draw_binomial_const<SCR>(rng, det, R, c.rs);
@@ -212,6 +296,42 @@ struct SirsModel {
     const double rate = __ldg(c.derived + D_EXP_NOISE);
     const double noise = det ? 1.0 / rate : draw_exponential<SCR>(rng, rate);
     return density_poisson_log(observed, lgamma_obs1, y[3] + noise);
+  }
+
+  struct Lean {
+    const double *derived;
+    const double2 *tab;
+    double r_ir, r_rs;
+    int n_tab;
+    uint32_t freq;
+  };
+  __device__ __forceinline__ static bool lean_load(const SetData &sd, const double *y, int *yi,
+                                                   Lean &c) {
+    c.derived = sd.derived;
+    c.tab = sd.tables;
+    c.n_tab = sd.n_tab;
+    c.r_ir = __ldg(sd.derived + D_R_IR);
+    c.r_rs = __ldg(sd.derived + D_R_RS);
+    c.freq = (uint32_t)__ldg(sd.derived + D_FREQ);
+    if (!to_counts<kState>(y, yi)) return false;
+    const double n_tot = __ldg(sd.derived + D_NTOT);
+    return y[0] + y[1] + y[2] == n_tot && n_tot < (double)sd.n_tab;
+  }
+  template <int SCR>
+  __device__ __forceinline__ static void lean_update(bool reset, int *y, Xoshiro &rng,
+                                                     const Lean &c,
+                                                     const double2 *__restrict__ s_inv) {
+    const int S = y[0], I = y[1], R = y[2];
+    const double2 e_si = __ldg(c.tab + (size_t)T_SI * c.n_tab + I);
+    const int n_SI = draw_infection_lean<SCR>(rng, S, I, e_si, c.derived, s_inv);
+    const int n_IR = draw_binomial_const_lean<SCR>(rng, I, c.r_ir, c.tab + (size_t)T_IR * c.n_tab,
+                                                   c.n_tab, c.derived + D_P_IR, s_inv);
+    const int n_RS = draw_binomial_const_lean<SCR>(rng, R, c.r_rs, c.tab + (size_t)T_RS * c.n_tab,
+                                                   c.n_tab, c.derived + D_P_RS, s_inv);
+    y[0] = S - n_SI + n_RS;
+    y[1] = I + n_SI - n_IR;
+    y[2] = R + n_IR - n_RS;
+    y[3] = reset ? n_SI : y[3] + n_SI;
   }
 };
 

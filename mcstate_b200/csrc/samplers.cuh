@@ -95,6 +95,83 @@ __device__ __forceinline__ double binomial_inversion(Xoshiro &rng, int n, double
   return inversion_walk<SCR>(rng, n, q / qq, pow_int(qq, n));
 }
 
+// ---------------------------------------------------------------------------
+// Lean twins used by the integer-state path of the run kernel (models.cuh).
+// Same operations in the same order as the functions above -- same bits -- with
+// the bookkeeping stripped: comparisons of non-negative doubles are done on
+// their bit patterns (integer pipe instead of the half-rate fp64 pipe), the
+// {k, 1/k} table is read from shared memory with one 16-byte load, and every
+// rare event (walk past the table, stalled f, k > n) leaves to a cold function.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ long long as_ll(double x) { return __double_as_longlong(x); }
+
+// pow_int with the first multiplication peeled (1.0 * x == x) and the squaring
+// moved to the top of the loop: the same products in the same order
+__device__ __forceinline__ double pow_int_lean(double x, int n) {
+  double acc = (n & 1) ? x : 1.0;
+  n >>= 1;
+  while (n != 0) {
+    x *= x;
+    if (n & 1) acc *= x;
+    n >>= 1;
+    if (n == 0) break;
+    x *= x;
+    if (n & 1) acc *= x;
+    n >>= 1;
+  }
+  return acc;
+}
+
+// continuation of a walk that left the fast loop: `stalled` = f stopped changing
+// (the attempt is abandoned), else k reached the end of the reciprocal table with
+// u >= f still (continue with the true division).  Cold.
+template <int SCR>
+__device__ __noinline__ double walk_cold(uint64_t *rs, int n, double r, double f0, double g,
+                                         double u, double f, int k, int stalled) {
+  Xoshiro rng{rs[0], rs[1], rs[2], rs[3]};
+  double out = -1.0;
+  if (!stalled) {
+    bool ok = true;
+    while (u >= f) {
+      u -= f;
+      ++k;
+      const double fn = f * (g / (double)k - r);
+      if (fn == f || k > n) { ok = false; break; }
+      f = fn;
+    }
+    if (ok) out = (double)k;
+  }
+  if (out < 0.0) out = inversion_walk<SCR>(rng, n, r, f0);
+  rs[0] = rng.s0; rs[1] = rng.s1; rs[2] = rng.s2; rs[3] = rng.s3;
+  return out;
+}
+
+// s_inv: the {k, RN(1/k)} table in shared memory; g = r (n + 1) must be away from
+// overflow/underflow (the caller's table entry guarantees it)
+template <int SCR>
+__device__ __forceinline__ int walk_lean(Xoshiro &rng, int n, double r, double f0, double g,
+                                         const double2 *__restrict__ s_inv) {
+  const int k_fast = min(n, kInvSmall - 1);
+  double u = xo_real<SCR>(rng);
+  double f = f0;
+  int k = 0;
+  int stalled = 0;
+  while (as_ll(u) >= as_ll(f)) {
+    if (k >= k_fast) { stalled = -1; break; }
+    u -= f;
+    ++k;
+    const double2 e = s_inv[k];
+    const double fn = f * (div_small_int(g, e.x, e.y) - r);
+    if (as_ll(fn) == as_ll(f)) { stalled = 1; break; }
+    f = fn;
+  }
+  if (stalled == 0) return k;
+  uint64_t rs[4] = {rng.s0, rng.s1, rng.s2, rng.s3};
+  const double out = walk_cold<SCR>(rs, n, r, f0, g, u, f, k, stalled > 0);
+  rng.s0 = rs[0]; rng.s1 = rs[1]; rng.s2 = rs[2]; rng.s3 = rs[3];
+  return (int)out;
+}
+
 __device__ __forceinline__ double stirling_tail(double k) {
   if (k <= 9.0) return c_stirling_tail[(int)k];
   const double kp1sq = (k + 1.0) * (k + 1.0);
@@ -154,8 +231,7 @@ __device__ __forceinline__ double draw_binomial(Xoshiro &rng, bool deterministic
 struct BinomialConst {
   double p, q, qq, r;   // q = min(p, 1-p), qq = 1-q, r = q/qq
   bool flip;            // p > 0.5
-  const double *f0;     // f0[n] = pow_int(qq, n), n < n_tab
-  int n_tab;
+  int n_tab;            // entries in the set's memo table (the lean path)
 };
 
 template <int SCR>
@@ -169,10 +245,43 @@ __device__ __forceinline__ double draw_binomial_const(Xoshiro &rng, bool determi
     draw = binomial_btrs<SCR>(rng, n, c.q);
   } else {
     const int ni = (int)n;
-    const double f0 = ni < c.n_tab ? __ldg(c.f0 + ni) : pow_int(c.qq, ni);
-    draw = inversion_walk<SCR>(rng, ni, c.r, f0);
+    draw = inversion_walk<SCR>(rng, ni, c.r, pow_int(c.qq, ni));
   }
   return c.flip ? n - draw : draw;
+}
+
+// the general draws, out of line: what the lean path calls for anything unusual
+// (probability 0, 1 or above one half, a count beyond the memo table, ...)
+template <int SCR>
+__device__ __noinline__ double draw_binomial_call(uint64_t *rs, double n, double p) {
+  Xoshiro rng{rs[0], rs[1], rs[2], rs[3]};
+  const double k = draw_binomial<SCR>(rng, false, n, p);
+  rs[0] = rng.s0; rs[1] = rng.s1; rs[2] = rng.s2; rs[3] = rng.s3;
+  return k;
+}
+template <int SCR>
+__device__ __forceinline__ int draw_binomial_cold(Xoshiro &rng, double n, double p) {
+  uint64_t rs[4] = {rng.s0, rng.s1, rng.s2, rng.s3};
+  const double k = draw_binomial_call<SCR>(rs, n, p);
+  rng.s0 = rs[0]; rng.s1 = rs[1]; rng.s2 = rs[2]; rng.s3 = rs[3];
+  return (int)k;
+}
+
+// Lean draw of Binomial(n, p) for a probability fixed by the parameter set.
+// tab[n] = {f0, g}: f0 = (1-q)^n, g = r (n + 1), or f0 < 0 when this n is not a
+// plain inversion draw (n q >= 10 -> BTRS; p outside (0, 1/2]; g near the ends of
+// the exponent range).  *p_ptr is read only on the cold branch.
+template <int SCR>
+__device__ __forceinline__ int draw_binomial_const_lean(Xoshiro &rng, int n, double r,
+                                                        const double2 *__restrict__ tab, int n_tab,
+                                                        const double *__restrict__ p_ptr,
+                                                        const double2 *__restrict__ s_inv) {
+  if (n == 0) return 0;
+  if (n < n_tab) {
+    const double2 e = __ldg(tab + n);
+    if (e.x >= 0.0) return walk_lean<SCR>(rng, n, r, e.x, e.y, s_inv);
+  }
+  return draw_binomial_cold<SCR>(rng, (double)n, __ldg(p_ptr));
 }
 
 // x log(lambda) - lambda - lgamma(x + 1); lgamma(x + 1) depends on the datum
