@@ -72,22 +72,29 @@ __device__ __forceinline__ bool to_counts(const double *y, int *yi) {
   return ok;
 }
 
-// Binomial(S, q) for a state-dependent probability taken from an infection table.
-// derived[0] = beta, [1] = dt, [4] = n_tot in both models (for the rare general draw).
-template <int SCR>
-__device__ __forceinline__ int draw_infection_lean(Xoshiro &rng, int S, int I, double2 e,
-                                                   const double *__restrict__ derived,
-                                                   const double2 *__restrict__ s_inv) {
-  if (S == 0 || e.x == 0.0) return 0;
+// Binomial(S, q) for a state-dependent probability taken from infection table
+// `table` of the set (entry I).  derived[0] = beta, [1] = dt, [4] = n_tot in both
+// models (for the rare general draw).
+template <int SCR, class Tabs>
+__device__ __forceinline__ int draw_infection_lean(Xoshiro &rng, int S, int I, const Tabs &t,
+                                                   int table, uint32_t s_inv) {
+  if (S == 0) return 0;
+  const double2 e = __ldg(t.table(table) + I);
+  if (e.x == 0.0) return 0;
   const double Sd1 = (double)(S + 1);
   const double Sd = Sd1 - 1.0;
   if (e.x < 0.0) {  // probability outside (0, 1/2]: the general draw
+    const double *derived = t.derived();
     const double p = (1.0 - det_exp(-__ldg(derived + 0) * (double)I / __ldg(derived + 4))) *
                      __ldg(derived + 1);
     return draw_binomial_cold<SCR>(rng, Sd, p);
   }
-  if (Sd * e.x >= 10.0) return draw_binomial_cold<SCR>(rng, Sd, e.x);
-  return walk_lean<SCR>(rng, S, e.y, pow_int_lean(1.0 - e.x, S), e.y * Sd1, s_inv);
+  if (!(Sd * e.x >= 10.0)) {
+    const int k = walk_lean<SCR>(rng, S, e.y, pow_int_lean(1.0 - e.x, S), e.y * Sd1, s_inv);
+    if (k >= 0) return k;
+    xo_rewind(rng);
+  }
+  return draw_binomial_cold<SCR>(rng, Sd, __ldg(t.table(table) + I).x);
 }
 
 struct SirModel {
@@ -174,42 +181,44 @@ struct SirModel {
   }
 
   // ---- the lean path ------------------------------------------------------
-  // only what the hot loop needs stays in registers; the cold calls fetch their
-  // parameters from `derived` when they happen
+  // Register diet: only r = q/(1-q) of the recovery draw stays live across the
+  // walks; table and parameter addresses are re-derived from (set, kernel
+  // arguments) where they are used, R is implied by the closed population, and
+  // the cold calls fetch their parameters when they happen.
   struct Lean {
-    const double *derived;
-    const double2 *tab;   // [kTables][n_tab]
     double r_ir;
-    int n_tab;
-    uint32_t freq;
   };
+  static constexpr int kLeanState = 4;  // S, I, cumulative, interval incidence (R = N - S - I)
   __device__ __forceinline__ static bool lean_load(const SetData &sd, const double *y, int *yi,
                                                    Lean &c) {
-    c.derived = sd.derived;
-    c.tab = sd.tables;
-    c.n_tab = sd.n_tab;
     c.r_ir = __ldg(sd.derived + D_R_IR);
-    c.freq = (uint32_t)__ldg(sd.derived + D_FREQ);
-    if (!to_counts<kState>(y, yi)) return false;
+    int all[kState];
+    if (!to_counts<kState>(y, all)) return false;
+    yi[0] = all[0]; yi[1] = all[1]; yi[2] = all[3]; yi[3] = all[4];
     // the infection table is built for N = n_tot and covers I < n_tab
     const double n_tot = __ldg(sd.derived + D_NTOT);
     return y[0] + y[1] + y[2] == n_tot && n_tot < (double)sd.n_tab;
   }
+  __device__ __forceinline__ static void lean_store(const SetData &sd, const int *yi, double *y) {
+    const double n_tot = __ldg(sd.derived + D_NTOT);
+    y[0] = (double)yi[0];
+    y[1] = (double)yi[1];
+    y[2] = n_tot - (double)(yi[0] + yi[1]);   // exact: integers below 2^31
+    y[3] = (double)yi[2];
+    y[4] = (double)yi[3];
+  }
   // `reset`: this step starts a new incidence interval (time % freq == 0)
-  template <int SCR>
+  template <int SCR, class Tabs>
   __device__ __forceinline__ static void lean_update(bool reset, int *y, Xoshiro &rng,
-                                                     const Lean &c,
-                                                     const double2 *__restrict__ s_inv) {
+                                                     const Lean &c, const Tabs &t,
+                                                     uint32_t s_inv) {
     const int S = y[0], I = y[1];
-    const double2 e_si = __ldg(c.tab + (size_t)T_SI * c.n_tab + I);  // I <= N < n_tab
-    const int n_IR = draw_binomial_const_lean<SCR>(rng, I, c.r_ir, c.tab + (size_t)T_IR * c.n_tab,
-                                                   c.n_tab, c.derived + D_P_IR, s_inv);
-    const int n_SI = draw_infection_lean<SCR>(rng, S, I, e_si, c.derived, s_inv);
+    const int n_IR = draw_binomial_const_lean<SCR>(rng, I, c.r_ir, t, T_IR, D_P_IR, s_inv);
+    const int n_SI = draw_infection_lean<SCR>(rng, S, I, t, T_SI, s_inv);  // I <= N < n_tab
     y[0] = S - n_SI;
     y[1] = I + n_SI - n_IR;
-    y[2] = y[2] + n_IR;
-    y[3] = y[3] + n_SI;
-    y[4] = reset ? n_SI : y[4] + n_SI;
+    y[2] = y[2] + n_SI;
+    y[3] = reset ? n_SI : y[3] + n_SI;
   }
 };
 
@@ -299,35 +308,29 @@ struct SirsModel {
   }
 
   struct Lean {
-    const double *derived;
-    const double2 *tab;
     double r_ir, r_rs;
-    int n_tab;
-    uint32_t freq;
   };
+  static constexpr int kLeanState = 4;
   __device__ __forceinline__ static bool lean_load(const SetData &sd, const double *y, int *yi,
                                                    Lean &c) {
-    c.derived = sd.derived;
-    c.tab = sd.tables;
-    c.n_tab = sd.n_tab;
     c.r_ir = __ldg(sd.derived + D_R_IR);
     c.r_rs = __ldg(sd.derived + D_R_RS);
-    c.freq = (uint32_t)__ldg(sd.derived + D_FREQ);
     if (!to_counts<kState>(y, yi)) return false;
     const double n_tot = __ldg(sd.derived + D_NTOT);
     return y[0] + y[1] + y[2] == n_tot && n_tot < (double)sd.n_tab;
   }
-  template <int SCR>
+  __device__ __forceinline__ static void lean_store(const SetData &, const int *yi, double *y) {
+#pragma unroll
+    for (int s = 0; s < kState; ++s) y[s] = (double)yi[s];
+  }
+  template <int SCR, class Tabs>
   __device__ __forceinline__ static void lean_update(bool reset, int *y, Xoshiro &rng,
-                                                     const Lean &c,
-                                                     const double2 *__restrict__ s_inv) {
+                                                     const Lean &c, const Tabs &t,
+                                                     uint32_t s_inv) {
     const int S = y[0], I = y[1], R = y[2];
-    const double2 e_si = __ldg(c.tab + (size_t)T_SI * c.n_tab + I);
-    const int n_SI = draw_infection_lean<SCR>(rng, S, I, e_si, c.derived, s_inv);
-    const int n_IR = draw_binomial_const_lean<SCR>(rng, I, c.r_ir, c.tab + (size_t)T_IR * c.n_tab,
-                                                   c.n_tab, c.derived + D_P_IR, s_inv);
-    const int n_RS = draw_binomial_const_lean<SCR>(rng, R, c.r_rs, c.tab + (size_t)T_RS * c.n_tab,
-                                                   c.n_tab, c.derived + D_P_RS, s_inv);
+    const int n_SI = draw_infection_lean<SCR>(rng, S, I, t, T_SI, s_inv);
+    const int n_IR = draw_binomial_const_lean<SCR>(rng, I, c.r_ir, t, T_IR, D_P_IR, s_inv);
+    const int n_RS = draw_binomial_const_lean<SCR>(rng, R, c.r_rs, t, T_RS, D_P_RS, s_inv);
     y[0] = S - n_SI + n_RS;
     y[1] = I + n_SI - n_IR;
     y[2] = R + n_IR - n_RS;

@@ -122,54 +122,58 @@ __device__ __forceinline__ double pow_int_lean(double x, int n) {
   return acc;
 }
 
-// continuation of a walk that left the fast loop: `stalled` = f stopped changing
-// (the attempt is abandoned), else k reached the end of the reciprocal table with
-// u >= f still (continue with the true division).  Cold.
-template <int SCR>
-__device__ __noinline__ double walk_cold(uint64_t *rs, int n, double r, double f0, double g,
-                                         double u, double f, int k, int stalled) {
-  Xoshiro rng{rs[0], rs[1], rs[2], rs[3]};
-  double out = -1.0;
-  if (!stalled) {
-    bool ok = true;
-    while (u >= f) {
-      u -= f;
-      ++k;
-      const double fn = f * (g / (double)k - r);
-      if (fn == f || k > n) { ok = false; break; }
-      f = fn;
-    }
-    if (ok) out = (double)k;
-  }
-  if (out < 0.0) out = inversion_walk<SCR>(rng, n, r, f0);
-  rs[0] = rng.s0; rs[1] = rng.s1; rs[2] = rng.s2; rs[3] = rng.s3;
-  return out;
+// One step back of the xoshiro256 state walk (the map is linear and invertible):
+// s1 = A ^ (s1 << 17) with A = s1' ^ s2' unrolls to four shifted terms.
+__device__ __forceinline__ void xo_rewind(Xoshiro &r) {
+  const uint64_t s3m = (r.s3 >> 45) | (r.s3 << 19);   // rotr 45
+  const uint64_t a = r.s1 ^ r.s2;
+  const uint64_t s1 = a ^ (a << 17) ^ (a << 34) ^ (a << 51);
+  const uint64_t s0 = r.s0 ^ s3m;
+  const uint64_t s2m = r.s2 ^ (s1 << 17);
+  r.s0 = s0;
+  r.s1 = s1;
+  r.s2 = s2m ^ s0;
+  r.s3 = s3m ^ s1;
 }
 
+// The CDF walk for the lean path.  Returns k >= 0, or -1 when anything unusual
+// happened (the walk ran past min(n, table), or f stopped changing): the caller
+// then rewinds the generator by the one uniform drawn here and repeats the draw
+// with the general code, which handles those cases by the book.
 // s_inv: the {k, RN(1/k)} table in shared memory; g = r (n + 1) must be away from
-// overflow/underflow (the caller's table entry guarantees it)
+// overflow/underflow (the caller's table entry guarantees it).
+// The loop is unrolled by two so f and its successor swap roles without moves.
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
+  double2 e;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(e.x), "=d"(e.y) : "r"(addr));
+  return e;
+}
+
+// s_inv_addr: shared-window address of the {k, RN(1/k)} table
 template <int SCR>
 __device__ __forceinline__ int walk_lean(Xoshiro &rng, int n, double r, double f0, double g,
-                                         const double2 *__restrict__ s_inv) {
-  const int k_fast = min(n, kInvSmall - 1);
+                                         uint32_t s_inv_addr) {
+  uint32_t a = s_inv_addr;
+  const uint32_t a_end = s_inv_addr + 16u * (uint32_t)min(n, kInvSmall - 1);
   double u = xo_real<SCR>(rng);
   double f = f0;
-  int k = 0;
-  int stalled = 0;
-  while (as_ll(u) >= as_ll(f)) {
-    if (k >= k_fast) { stalled = -1; break; }
+  for (;;) {
+    if (!(u >= f)) break;
+    if (a >= a_end) return -1;
     u -= f;
-    ++k;
-    const double2 e = s_inv[k];
+    a += 16;
+    const double2 e = lds_f64x2(a);
     const double fn = f * (div_small_int(g, e.x, e.y) - r);
-    if (as_ll(fn) == as_ll(f)) { stalled = 1; break; }
-    f = fn;
+    if (fn == f) return -1;
+    if (!(u >= fn)) break;
+    if (a >= a_end) return -1;
+    u -= fn;
+    a += 16;
+    const double2 e2 = lds_f64x2(a);
+    f = fn * (div_small_int(g, e2.x, e2.y) - r);
+    if (f == fn) return -1;
   }
-  if (stalled == 0) return k;
-  uint64_t rs[4] = {rng.s0, rng.s1, rng.s2, rng.s3};
-  const double out = walk_cold<SCR>(rs, n, r, f0, g, u, f, k, stalled > 0);
-  rng.s0 = rs[0]; rng.s1 = rs[1]; rng.s2 = rs[2]; rng.s3 = rs[3];
-  return (int)out;
+  return (int)((a - s_inv_addr) >> 4);
 }
 
 __device__ __forceinline__ double stirling_tail(double k) {
@@ -268,20 +272,24 @@ __device__ __forceinline__ int draw_binomial_cold(Xoshiro &rng, double n, double
 }
 
 // Lean draw of Binomial(n, p) for a probability fixed by the parameter set.
-// tab[n] = {f0, g}: f0 = (1-q)^n, g = r (n + 1), or f0 < 0 when this n is not a
-// plain inversion draw (n q >= 10 -> BTRS; p outside (0, 1/2]; g near the ends of
-// the exponent range).  *p_ptr is read only on the cold branch.
-template <int SCR>
+// Entry n of the set's table `table` is {f0, g}: f0 = (1-q)^n, g = r (n + 1), or
+// f0 < 0 when this n is not a plain inversion draw (n q >= 10 -> BTRS; p outside
+// (0, 1/2]; g near the ends of the exponent range).  `t` re-derives addresses from
+// the kernel arguments; derived[d_p] (the probability) is read only when cold.
+template <int SCR, class Tabs>
 __device__ __forceinline__ int draw_binomial_const_lean(Xoshiro &rng, int n, double r,
-                                                        const double2 *__restrict__ tab, int n_tab,
-                                                        const double *__restrict__ p_ptr,
-                                                        const double2 *__restrict__ s_inv) {
+                                                        const Tabs &t, int table, int d_p,
+                                                        uint32_t s_inv) {
   if (n == 0) return 0;
-  if (n < n_tab) {
-    const double2 e = __ldg(tab + n);
-    if (e.x >= 0.0) return walk_lean<SCR>(rng, n, r, e.x, e.y, s_inv);
+  if (n < t.n_tab()) {
+    const double2 e = __ldg(t.table(table) + n);
+    if (e.x >= 0.0) {
+      const int k = walk_lean<SCR>(rng, n, r, e.x, e.y, s_inv);
+      if (k >= 0) return k;
+      xo_rewind(rng);
+    }
   }
-  return draw_binomial_cold<SCR>(rng, (double)n, __ldg(p_ptr));
+  return draw_binomial_cold<SCR>(rng, (double)n, __ldg(t.derived() + d_p));
 }
 
 // x log(lambda) - lambda - lgamma(x + 1); lgamma(x + 1) depends on the datum
