@@ -133,20 +133,6 @@ __device__ __forceinline__ size_t resample_source(const View &v, size_t set, siz
 //   row >= 0: weigh against data row `row`; row < 0: no compare (model$run).
 // kappa_out (trajectories only) records src, the order slice of prev_row.
 // ---------------------------------------------------------------------------
-// How the lean path finds its set's tables: nothing but the set index is kept
-// in a register; addresses come from the kernel arguments (constant bank).
-struct LeanTabs {
-  const View &v;
-  uint32_t set;
-  __device__ __forceinline__ int n_tab() const { return v.n_tab; }
-  __device__ __forceinline__ const double2 *table(int t) const {
-    return v.tables + ((size_t)set * kMaxTables + t) * (size_t)v.n_tab;
-  }
-  __device__ __forceinline__ const double *derived() const {
-    return v.derived + (size_t)set * kMaxDerived;
-  }
-};
-
 // The general form of the model steps (state as doubles, every special case of
 // the draws), out of line so the run kernel's registers are sized for the lean
 // path: deterministic mode, non-integer or out-of-table states.
@@ -207,29 +193,35 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
     if (n_steps > 0) {
       int yi[M::kLeanState];
       typename M::Lean lc;
+      uint32_t done = 0;
+      lc.off = (uint32_t)set * (uint32_t)(kMaxTables * v.n_tab);
       if (!det && M::lean_load(sd, y, yi, lc)) {
-        // the usual case: integer compartments, setup from the memo tables
+        // the usual case: integer compartments, setup from the memo tables, no calls
         const uint32_t s_inv_addr = (uint32_t)__cvta_generic_to_shared(s_inv);
-        const LeanTabs tabs{v, (uint32_t)set};
         const uint32_t freq = (uint32_t)__ldg(sd.derived + M::D_FREQ);
         uint32_t phase = (uint32_t)(t0 % freq);
-        for (uint32_t k0 = 0; k0 < n_steps; k0 += 32) {
-          // bit k: step k0 + k starts a new incidence interval
-          const uint32_t nk = min(n_steps - k0, 32u);
+        bool ok = true;
+        while (ok && done < n_steps) {
+          // bit k: step done + k starts a new incidence interval
+          const uint32_t nk = min(n_steps - done, 32u);
           uint32_t resets = 0;
           for (uint32_t k = 0; k < nk; ++k) {
             resets |= (phase == 0 ? 1u : 0u) << k;
             phase = phase + 1 == freq ? 0 : phase + 1;
           }
           for (uint32_t k = 0; k < nk; ++k) {
-            M::template lean_update<SCR>((resets & 1u) != 0, yi, rng, lc, tabs, s_inv_addr);
+            ok = M::template lean_update<SCR>((resets & 1u) != 0, yi, rng, lc, v.tables,
+                                              (uint32_t)v.n_tab, s_inv_addr);
+            if (!ok) break;
             resets >>= 1;
+            ++done;
           }
         }
         M::lean_store(sd, yi, y);
-      } else {
+      }
+      if (done < n_steps) {  // whatever the lean path did not take
         uint64_t rs[4] = {rng.s0, rng.s1, rng.s2, rng.s3};
-        run_general<M, SCR>(y, rs, t0, n_steps, sd.derived, sd.tables, sd.n_tab, det);
+        run_general<M, SCR>(y, rs, t0 + done, n_steps - done, sd.derived, sd.tables, sd.n_tab, det);
         rng.s0 = rs[0]; rng.s1 = rs[1]; rng.s2 = rs[2]; rng.s3 = rs[3];
       }
     }

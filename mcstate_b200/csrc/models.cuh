@@ -72,29 +72,19 @@ __device__ __forceinline__ bool to_counts(const double *y, int *yi) {
   return ok;
 }
 
-// Binomial(S, q) for a state-dependent probability taken from infection table
-// `table` of the set (entry I).  derived[0] = beta, [1] = dt, [4] = n_tot in both
-// models (for the rare general draw).
-template <int SCR, class Tabs>
-__device__ __forceinline__ int draw_infection_lean(Xoshiro &rng, int S, int I, const Tabs &t,
-                                                   int table, uint32_t s_inv) {
-  if (S == 0) return 0;
-  const double2 e = __ldg(t.table(table) + I);
-  if (e.x == 0.0) return 0;
+// Binomial(S, q) for a state-dependent probability: e = entry I of the set's
+// infection table.  Returns the draw, or -1 (generator untouched) when the
+// general code must take over: probability outside (0, 1/2], S q >= 10 (BTRS), or
+// a walk that met one of its rare exits.
+template <int SCR>
+__device__ __forceinline__ int draw_infection_lean(Xoshiro &rng, int S, double2 e,
+                                                   uint32_t s_inv) {
+  if (S == 0 || e.x == 0.0) return 0;
   const double Sd1 = (double)(S + 1);
-  const double Sd = Sd1 - 1.0;
-  if (e.x < 0.0) {  // probability outside (0, 1/2]: the general draw
-    const double *derived = t.derived();
-    const double p = (1.0 - det_exp(-__ldg(derived + 0) * (double)I / __ldg(derived + 4))) *
-                     __ldg(derived + 1);
-    return draw_binomial_cold<SCR>(rng, Sd, p);
-  }
-  if (!(Sd * e.x >= 10.0)) {
-    const int k = walk_lean<SCR>(rng, S, e.y, pow_int_lean(1.0 - e.x, S), e.y * Sd1, s_inv);
-    if (k >= 0) return k;
-    xo_rewind(rng);
-  }
-  return draw_binomial_cold<SCR>(rng, Sd, __ldg(t.table(table) + I).x);
+  if (e.x < 0.0 || (Sd1 - 1.0) * e.x >= 10.0) return -1;
+  const int k = walk_lean<SCR>(rng, S, e.y, pow_int_lean(1.0 - e.x, S), e.y * Sd1, s_inv);
+  if (k < 0) xo_rewind(rng);
+  return k;
 }
 
 struct SirModel {
@@ -181,21 +171,22 @@ struct SirModel {
   }
 
   // ---- the lean path ------------------------------------------------------
-  // Register diet: only r = q/(1-q) of the recovery draw stays live across the
-  // walks; table and parameter addresses are re-derived from (set, kernel
-  // arguments) where they are used, R is implied by the closed population, and
-  // the cold calls fetch their parameters when they happen.
+  // Register diet: the hot loop keeps r = q/(1-q) of the recovery draw, one
+  // pointer to the set's tables and four counts (R is implied by the closed
+  // population); it makes no calls.  A step that meets anything unusual is
+  // abandoned with state and generator as they were at its start.
   struct Lean {
     double r_ir;
+    uint32_t off;  // entry offset of the set's tables: set * kMaxTables * n_tab
   };
-  static constexpr int kLeanState = 4;  // S, I, cumulative, interval incidence (R = N - S - I)
+  static constexpr int kLeanState = 4;  // S, I, cumulative, interval incidence
   __device__ __forceinline__ static bool lean_load(const SetData &sd, const double *y, int *yi,
                                                    Lean &c) {
     c.r_ir = __ldg(sd.derived + D_R_IR);
     int all[kState];
     if (!to_counts<kState>(y, all)) return false;
     yi[0] = all[0]; yi[1] = all[1]; yi[2] = all[3]; yi[3] = all[4];
-    // the infection table is built for N = n_tot and covers I < n_tab
+    // the tables are built for N = n_tot and cover counts < n_tab
     const double n_tot = __ldg(sd.derived + D_NTOT);
     return y[0] + y[1] + y[2] == n_tot && n_tot < (double)sd.n_tab;
   }
@@ -207,18 +198,28 @@ struct SirModel {
     y[3] = (double)yi[2];
     y[4] = (double)yi[3];
   }
-  // `reset`: this step starts a new incidence interval (time % freq == 0)
-  template <int SCR, class Tabs>
-  __device__ __forceinline__ static void lean_update(bool reset, int *y, Xoshiro &rng,
-                                                     const Lean &c, const Tabs &t,
-                                                     uint32_t s_inv) {
+  // One model step; `reset`: it starts a new incidence interval (time % freq == 0).
+  // false: nothing changed, the general code must run this step.
+  template <int SCR>
+  __device__ __forceinline__ static bool lean_update(bool reset, int *y, Xoshiro &rng,
+                                                     const Lean &c, const double2 *__restrict__ tables,
+                                                     uint32_t n_tab, uint32_t s_inv) {
     const int S = y[0], I = y[1];
-    const int n_IR = draw_binomial_const_lean<SCR>(rng, I, c.r_ir, t, T_IR, D_P_IR, s_inv);
-    const int n_SI = draw_infection_lean<SCR>(rng, S, I, t, T_SI, s_inv);  // I <= N < n_tab
+    int n_IR = 0;
+    if (I != 0) {
+      n_IR = draw_binomial_const_lean<SCR>(rng, I, c.r_ir, __ldg(tables + (c.off + T_IR * n_tab + (uint32_t)I)), s_inv);
+      if (n_IR < 0) return false;
+    }
+    const int n_SI = draw_infection_lean<SCR>(rng, S, __ldg(tables + (c.off + T_SI * n_tab + (uint32_t)I)), s_inv);
+    if (n_SI < 0) {
+      if (I != 0) xo_rewind(rng);  // the recovery draw's uniform
+      return false;
+    }
     y[0] = S - n_SI;
     y[1] = I + n_SI - n_IR;
     y[2] = y[2] + n_SI;
     y[3] = reset ? n_SI : y[3] + n_SI;
+    return true;
   }
 };
 
@@ -309,6 +310,7 @@ struct SirsModel {
 
   struct Lean {
     double r_ir, r_rs;
+    uint32_t off;
   };
   static constexpr int kLeanState = 4;
   __device__ __forceinline__ static bool lean_load(const SetData &sd, const double *y, int *yi,
@@ -323,18 +325,37 @@ struct SirsModel {
 #pragma unroll
     for (int s = 0; s < kState; ++s) y[s] = (double)yi[s];
   }
-  template <int SCR, class Tabs>
-  __device__ __forceinline__ static void lean_update(bool reset, int *y, Xoshiro &rng,
-                                                     const Lean &c, const Tabs &t,
-                                                     uint32_t s_inv) {
+  template <int SCR>
+  __device__ __forceinline__ static bool lean_update(bool reset, int *y, Xoshiro &rng,
+                                                     const Lean &c, const double2 *__restrict__ tables,
+                                                     uint32_t n_tab, uint32_t s_inv) {
     const int S = y[0], I = y[1], R = y[2];
-    const int n_SI = draw_infection_lean<SCR>(rng, S, I, t, T_SI, s_inv);
-    const int n_IR = draw_binomial_const_lean<SCR>(rng, I, c.r_ir, t, T_IR, D_P_IR, s_inv);
-    const int n_RS = draw_binomial_const_lean<SCR>(rng, R, c.r_rs, t, T_RS, D_P_RS, s_inv);
+    const int n_SI = draw_infection_lean<SCR>(rng, S, __ldg(tables + (c.off + T_SI * n_tab + (uint32_t)I)), s_inv);
+    if (n_SI < 0) return false;
+    // did the infection draw take a uniform?  (it returns 0 without one for S = 0 or p = 0)
+    const bool si_drew = S != 0 && I != 0 && __ldg(tables + (c.off + T_SI * n_tab + (uint32_t)I)).x != 0.0;
+    int n_IR = 0;
+    if (I != 0) {
+      n_IR = draw_binomial_const_lean<SCR>(rng, I, c.r_ir, __ldg(tables + (c.off + T_IR * n_tab + (uint32_t)I)), s_inv);
+      if (n_IR < 0) {
+        if (si_drew) xo_rewind(rng);
+        return false;
+      }
+    }
+    int n_RS = 0;
+    if (R != 0) {
+      n_RS = draw_binomial_const_lean<SCR>(rng, R, c.r_rs, __ldg(tables + (c.off + T_RS * n_tab + (uint32_t)R)), s_inv);
+      if (n_RS < 0) {
+        if (I != 0) xo_rewind(rng);
+        if (si_drew) xo_rewind(rng);
+        return false;
+      }
+    }
     y[0] = S - n_SI + n_RS;
     y[1] = I + n_SI - n_IR;
     y[2] = R + n_IR - n_RS;
     y[3] = reset ? n_SI : y[3] + n_SI;
+    return true;
   }
 };
 

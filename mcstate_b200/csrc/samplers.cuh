@@ -254,42 +254,19 @@ __device__ __forceinline__ double draw_binomial_const(Xoshiro &rng, bool determi
   return c.flip ? n - draw : draw;
 }
 
-// the general draws, out of line: what the lean path calls for anything unusual
-// (probability 0, 1 or above one half, a count beyond the memo table, ...)
-template <int SCR>
-__device__ __noinline__ double draw_binomial_call(uint64_t *rs, double n, double p) {
-  Xoshiro rng{rs[0], rs[1], rs[2], rs[3]};
-  const double k = draw_binomial<SCR>(rng, false, n, p);
-  rs[0] = rng.s0; rs[1] = rng.s1; rs[2] = rng.s2; rs[3] = rng.s3;
-  return k;
-}
-template <int SCR>
-__device__ __forceinline__ int draw_binomial_cold(Xoshiro &rng, double n, double p) {
-  uint64_t rs[4] = {rng.s0, rng.s1, rng.s2, rng.s3};
-  const double k = draw_binomial_call<SCR>(rs, n, p);
-  rng.s0 = rs[0]; rng.s1 = rs[1]; rng.s2 = rs[2]; rng.s3 = rs[3];
-  return (int)k;
-}
-
 // Lean draw of Binomial(n, p) for a probability fixed by the parameter set.
-// Entry n of the set's table `table` is {f0, g}: f0 = (1-q)^n, g = r (n + 1), or
+// e = entry n of the set's table: {f0, g} with f0 = (1-q)^n, g = r (n + 1), or
 // f0 < 0 when this n is not a plain inversion draw (n q >= 10 -> BTRS; p outside
-// (0, 1/2]; g near the ends of the exponent range).  `t` re-derives addresses from
-// the kernel arguments; derived[d_p] (the probability) is read only when cold.
-template <int SCR, class Tabs>
-__device__ __forceinline__ int draw_binomial_const_lean(Xoshiro &rng, int n, double r,
-                                                        const Tabs &t, int table, int d_p,
+// (0, 1/2]; g near the ends of the exponent range).  Returns the draw, or -1 with
+// the generator exactly as it was on entry: the caller then hands the rest of the
+// interval to the general code.
+template <int SCR>
+__device__ __forceinline__ int draw_binomial_const_lean(Xoshiro &rng, int n, double r, double2 e,
                                                         uint32_t s_inv) {
-  if (n == 0) return 0;
-  if (n < t.n_tab()) {
-    const double2 e = __ldg(t.table(table) + n);
-    if (e.x >= 0.0) {
-      const int k = walk_lean<SCR>(rng, n, r, e.x, e.y, s_inv);
-      if (k >= 0) return k;
-      xo_rewind(rng);
-    }
-  }
-  return draw_binomial_cold<SCR>(rng, (double)n, __ldg(t.derived() + d_p));
+  if (e.x < 0.0) return -1;
+  const int k = walk_lean<SCR>(rng, n, r, e.x, e.y, s_inv);
+  if (k < 0) xo_rewind(rng);
+  return k;
 }
 
 // x log(lambda) - lambda - lgamma(x + 1); lgamma(x + 1) depends on the datum
