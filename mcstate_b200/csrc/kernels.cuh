@@ -29,7 +29,10 @@
 
 namespace mcb {
 
-constexpr int kRunThreads = 128;
+#ifndef MCB_RUN_THREADS
+#define MCB_RUN_THREADS 128
+#endif
+constexpr int kRunThreads = MCB_RUN_THREADS;
 constexpr int kTileThreads = 256;
 constexpr int kTileItems = 8;       // consecutive particles per thread in K2
 constexpr int kTile = kTileThreads * kTileItems;  // particles per weight tile
@@ -161,9 +164,9 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
               uint64_t t0, uint32_t n_steps, int prev_row, int row,
               double *__restrict__ hist, int *__restrict__ kappa_out) {
   __shared__ unsigned long long s_key[kRunThreads / 32];
-  __shared__ double2 s_inv[kInvSmall];
+  __shared__ double2 s_inv[kInvSmall + 1];  // one spare entry (walk_lean looks two ahead)
   if (v.flags[0]) return;
-  if (threadIdx.x < kInvSmall) s_inv[threadIdx.x] = c_inv_small[threadIdx.x];
+  if (threadIdx.x <= kInvSmall) s_inv[threadIdx.x] = c_inv_small[min((int)threadIdx.x, kInvSmall - 1)];
   __syncthreads();
   const size_t i = (size_t)blockIdx.x * kRunThreads + threadIdx.x;
   const bool live = i < v.n_total;
@@ -199,7 +202,7 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
         // the usual case: integer compartments, setup from the memo tables, no calls
         const uint32_t s_inv_addr = (uint32_t)__cvta_generic_to_shared(s_inv);
         const uint32_t freq = (uint32_t)__ldg(sd.derived + M::D_FREQ);
-        uint32_t phase = (uint32_t)(t0 % freq);
+        uint32_t phase = t0 <= 0xffffffffULL ? (uint32_t)t0 % freq : (uint32_t)(t0 % freq);
         bool ok = true;
         while (ok && done < n_steps) {
           // bit k: step done + k starts a new incidence interval
@@ -265,11 +268,12 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
   const bool one_set = v.n_sets == 1 || (first / v.n_particles == last / v.n_particles);
   unsigned long long *slot = v.wmax + (size_t)row * v.n_sets;
   if (one_set) {
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) {
-      const unsigned long long o = shfl_xor_u64(key, m);
-      key = o > key ? o : key;
-    }
+    // warp max of a 64-bit key with two 32-bit REDUX: high words, then the low
+    // words of the lanes that hold the maximal high word
+    const unsigned hi = (unsigned)(key >> 32);
+    const unsigned m_hi = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned m_lo = __reduce_max_sync(0xffffffffu, hi == m_hi ? (unsigned)key : 0u);
+    key = ((unsigned long long)m_hi << 32) | m_lo;
     if ((threadIdx.x & 31) == 0) s_key[threadIdx.x >> 5] = key;
     __syncthreads();
     if (threadIdx.x == 0) {

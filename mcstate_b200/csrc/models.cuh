@@ -29,7 +29,6 @@ constexpr int kMaxState = 8;
 constexpr int kMaxPar = 8;
 constexpr int kMaxDerived = 16;
 constexpr int kMaxTables = 3;
-constexpr double kLeanMax = 1073741824.0;  // 2^30: counts the int32 path accepts
 
 // where a thread finds its parameter set's prepared data
 struct SetData {
@@ -59,15 +58,17 @@ __device__ __forceinline__ double2 infection_entry(double beta, double n_tot, do
   return make_double2(plain ? p : -1.0, r);
 }
 
-// y (doubles) -> int32 compartments; false unless every value is an integer in [0, 2^30)
+// y (doubles) -> int32 compartments; false unless every value is an integer in
+// [0, 2^30) with a clear sign bit (-0.0 stays on the general path: its sign
+// would be lost)
 template <int N>
 __device__ __forceinline__ bool to_counts(const double *y, int *yi) {
   bool ok = true;
 #pragma unroll
   for (int s = 0; s < N; ++s) {
-    ok = ok && y[s] >= 0.0 && y[s] < kLeanMax;
-    yi[s] = (int)y[s];
-    ok = ok && (double)yi[s] == y[s];
+    const unsigned u = __double2uint_rz(y[s]);
+    ok = ok & (__double2hiint(y[s]) >= 0) & ((double)u == y[s]) & (u < (1u << 30));
+    yi[s] = (int)u;
   }
   return ok;
 }

@@ -106,18 +106,22 @@ __device__ __forceinline__ double binomial_inversion(Xoshiro &rng, int n, double
 __device__ __forceinline__ long long as_ll(double x) { return __double_as_longlong(x); }
 
 // pow_int with the first multiplication peeled (1.0 * x == x) and the squaring
-// moved to the top of the loop: the same products in the same order
+// moved to the top of the loop: the same products in the same order.  The
+// conditional product is one predicated DMUL.
+__device__ __forceinline__ void mul_if(double &acc, double x, int bit) {
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p mul.rn.f64 %0, %0, %1;\n\t}"
+      : "+d"(acc) : "d"(x), "r"(bit));
+}
 __device__ __forceinline__ double pow_int_lean(double x, int n) {
   double acc = (n & 1) ? x : 1.0;
   n >>= 1;
   while (n != 0) {
     x *= x;
-    if (n & 1) acc *= x;
-    n >>= 1;
-    if (n == 0) break;
+    mul_if(acc, x, n & 1);
+    if ((n >> 1) == 0) break;
     x *= x;
-    if (n & 1) acc *= x;
-    n >>= 1;
+    mul_if(acc, x, n & 2);
+    n >>= 2;
   }
   return acc;
 }
@@ -145,11 +149,15 @@ __device__ __forceinline__ void xo_rewind(Xoshiro &r) {
 // The loop is unrolled by two so f and its successor swap roles without moves.
 __device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
   double2 e;
-  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(e.x), "=d"(e.y) : "r"(addr));
+  asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(e.x), "=d"(e.y) : "r"(addr));
   return e;
 }
 
-// s_inv_addr: shared-window address of the {k, RN(1/k)} table
+// s_inv_addr: shared-window address of the {k, RN(1/k)} table.
+// One predicate drives the loop: keep walking while u >= f, f changed, and the
+// table has another entry; the two rare reasons are told apart after the loop
+// (the order of the reference's tests is kept: a stalled f abandons the attempt
+// whatever u is).
 template <int SCR>
 __device__ __forceinline__ int walk_lean(Xoshiro &rng, int n, double r, double f0, double g,
                                          uint32_t s_inv_addr) {
@@ -157,23 +165,35 @@ __device__ __forceinline__ int walk_lean(Xoshiro &rng, int n, double r, double f
   const uint32_t a_end = s_inv_addr + 16u * (uint32_t)min(n, kInvSmall - 1);
   double u = xo_real<SCR>(rng);
   double f = f0;
+  if (!(u >= f)) return 0;   // n >= 1: the table has an entry to move to
+  bool bad;
   for (;;) {
-    if (!(u >= f)) break;
-    if (a >= a_end) return -1;
+    // The factors c_k = g/k - r do not depend on f or u: the next two are computed
+    // side by side (two independent dependency chains), then applied in order.
+    // The second may go unused; the table has one spare entry for its load.
+    const double2 e1 = lds_f64x2(a + 16);
+    const double2 e2 = lds_f64x2(a + 32);
+    double q1 = g * e1.y, q2 = g * e2.y;
+    double r1 = fma(-q1, e1.x, g), r2 = fma(-q2, e2.x, g);
+    q1 = fma(r1, e1.y, q1); q2 = fma(r2, e2.y, q2);
+    r1 = fma(-q1, e1.x, g); r2 = fma(-q2, e2.x, g);
+    const double c1 = fma(r1, e1.y, q1) - r, c2 = fma(r2, e2.y, q2) - r;
     u -= f;
-    a += 16;
-    const double2 e = lds_f64x2(a);
-    const double fn = f * (div_small_int(g, e.x, e.y) - r);
-    if (fn == f) return -1;
-    if (!(u >= fn)) break;
-    if (a >= a_end) return -1;
-    u -= fn;
-    a += 16;
-    const double2 e2 = lds_f64x2(a);
-    f = fn * (div_small_int(g, e2.x, e2.y) - r);
-    if (f == fn) return -1;
+    const double f1 = f * c1;
+    if (!((u >= f1) & (f1 != f) & (a + 16 < a_end))) {
+      bad = (f1 == f) | (u >= f1);  // stalled, or out of table with u >= f still
+      a += 16;
+      break;
+    }
+    u -= f1;
+    a += 32;
+    f = f1 * c2;
+    if (!((u >= f) & (f != f1) & (a < a_end))) {
+      bad = (f == f1) | (u >= f);
+      break;
+    }
   }
-  return (int)((a - s_inv_addr) >> 4);
+  return bad ? -1 : (int)((a - s_inv_addr) >> 4);
 }
 
 __device__ __forceinline__ double stirling_tail(double k) {
