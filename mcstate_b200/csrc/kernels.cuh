@@ -34,7 +34,10 @@ namespace mcb {
 #endif
 constexpr int kRunThreads = MCB_RUN_THREADS;
 constexpr int kTileThreads = 256;
-constexpr int kTileItems = 8;       // consecutive particles per thread in K2
+#ifndef MCB_TILE_ITEMS
+#define MCB_TILE_ITEMS 8
+#endif
+constexpr int kTileItems = MCB_TILE_ITEMS;  // consecutive particles per thread in K2
 constexpr int kTile = kTileThreads * kTileItems;  // particles per weight tile
 constexpr int kGatherThreads = 256;
 
@@ -126,6 +129,74 @@ __device__ __forceinline__ size_t resample_source(const View &v, size_t set, siz
 }
 
 // ---------------------------------------------------------------------------
+// The same search done by a whole warp for 32 consecutive output slots of one
+// set (the usual case in K1).  Thresholds grow with the slot, so the warp first
+// finds lane 0's position with 32-way probes (2 rounds over the tile prefix, 3
+// inside a 2048-particle tile, every probe round one coalesced or strided load
+// instead of a chain of 20 dependent ones), then each lane finishes inside a
+// 64-entry window staged in shared memory.  Lanes whose threshold lies beyond
+// the window, and warps whose slots span two tiles, fall back to the per-thread
+// search: the result is identical by construction.
+// ---------------------------------------------------------------------------
+// first index in [0, n) with arr[idx] >= key, else n - 1; uniform across the warp
+__device__ __forceinline__ int warp_lower_bound(const unsigned long long *__restrict__ arr, int n,
+                                                unsigned long long key, int lane) {
+  int lo = 0, cnt = n;
+  while (cnt > 1) {
+    const int step = (cnt + 31) >> 5;
+    const int last = lo + cnt - 1;
+    const int idx = min(lo + (lane + 1) * step - 1, last);
+    const unsigned b = __ballot_sync(0xffffffffu, __ldg(arr + idx) >= key);
+    if (b == 0) return last;
+    const int j = __ffs(b) - 1;
+    lo += j * step;
+    cnt = min(lo + step - 1, last) - lo + 1;
+  }
+  return lo;
+}
+
+constexpr int kWindow = 64;
+__device__ __forceinline__ size_t resample_source_warp(const View &v, size_t set, size_t il,
+                                                       unsigned long long *s_win, int lane) {
+  const SetInfo si = v.setinfo[set];
+  const unsigned long long thr =
+      (unsigned long long)__double2ll_ru(si.uu0 + (double)il * si.du);
+  const unsigned long long thr0 = shfl_u64(thr, 0), thr31 = shfl_u64(thr, 31);
+  const unsigned long long *ts = v.tile_incl + set * v.tiles_per_set;
+  const int T = v.tiles_per_set;
+  const int t0 = warp_lower_bound(ts, T, thr0, lane);
+  if (t0 < T - 1 && thr31 > __ldg(ts + t0)) return resample_source(v, set, il);  // two tiles
+  const unsigned long long before = t0 ? __ldg(ts + t0 - 1) : 0ULL;
+  const unsigned long long rem = thr > before ? thr - before : 0ULL;
+  const size_t tile_base = (size_t)t0 * kTile;
+  const int in_tile = (int)min((size_t)kTile, v.n_particles - tile_base);
+  const unsigned long long *cw = v.cw + set * v.n_particles + tile_base;
+  const int a0 = warp_lower_bound(cw, in_tile, shfl_u64(rem, 0), lane);
+  // window cw[a0 .. a0 + 63] (clamped to the tile) -> shared memory
+  s_win[lane] = __ldg(cw + min(a0 + lane, in_tile - 1));
+  s_win[lane + 32] = __ldg(cw + min(a0 + 32 + lane, in_tile - 1));
+  __syncwarp();
+  int lo = 0, hi = kWindow - 1;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const int mid = (lo + hi) >> 1;
+    if (s_win[mid] >= rem) hi = mid; else lo = mid + 1;
+  }
+  int a = min(a0 + lo, in_tile - 1);
+  if (lo == kWindow - 1 && s_win[kWindow - 1] < rem && a0 + kWindow < in_tile) {
+    // beyond the window: the plain search over what is left of the tile
+    int x = a0 + kWindow, y = in_tile - 1;
+    while (x < y) {
+      const int mid = (x + y) >> 1;
+      if (__ldg(cw + mid) >= rem) y = mid; else x = mid + 1;
+    }
+    a = x;
+  }
+  __syncwarp();
+  return set * v.n_particles + tile_base + a;
+}
+
+// ---------------------------------------------------------------------------
 // K1: one thread per particle: [resample of the previous interval, fused into
 // the load] -> `n_steps` model updates -> compare.  State (kState doubles) and
 // the generator (4 words) stay in registers throughout.
@@ -164,6 +235,7 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
               uint64_t t0, uint32_t n_steps, int prev_row, int row,
               double *__restrict__ hist, int *__restrict__ kappa_out) {
   __shared__ unsigned long long s_key[kRunThreads / 32];
+  __shared__ unsigned long long s_win[kRunThreads / 32][kWindow];
   __shared__ double2 s_inv[kInvSmall + 1];  // one spare entry (walk_lean looks two ahead)
   if (v.flags[0]) return;
   if (threadIdx.x <= kInvSmall) s_inv[threadIdx.x] = c_inv_small[min((int)threadIdx.x, kInvSmall - 1)];
@@ -181,10 +253,19 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
   Xoshiro rng;
   unsigned long long key = 0;
   bool weighted = false;
-  if (live) {
-    size_t src = i;
-    if (prev_row >= 0 && !datum_is_na(v, prev_row, set))
+  // which particle this slot continues: systematic resampling of prev_row
+  size_t src = i;
+  {
+    const bool want = live && prev_row >= 0 && !datum_is_na(v, prev_row, set);
+    const int lane = threadIdx.x & 31;
+    const unsigned set0 = __shfl_sync(0xffffffffu, (unsigned)set, 0);  // every lane takes part
+    const bool together = want && set0 == (unsigned)set;
+    if (__all_sync(0xffffffffu, together))
+      src = resample_source_warp(v, set, i - set * v.n_particles, s_win[threadIdx.x >> 5], lane);
+    else if (want)
       src = resample_source(v, set, i - set * v.n_particles);
+  }
+  if (live) {
     if (HIST && kappa_out) kappa_out[i] = (int)src;
 #pragma unroll
     for (int s = 0; s < M::kState; ++s) y[s] = y_in[(size_t)s * v.ld + src];
