@@ -268,11 +268,13 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
   if (live) {
     if (HIST && kappa_out) kappa_out[i] = (int)src;
 #pragma unroll
-    for (int s = 0; s < M::kState; ++s) y[s] = y_in[(size_t)s * v.ld + src];
-    rng.s0 = v.rng[0 * v.ld_rng + i];
-    rng.s1 = v.rng[1 * v.ld_rng + i];
-    rng.s2 = v.rng[2 * v.ld_rng + i];
-    rng.s3 = v.rng[3 * v.ld_rng + i];
+    // state and generator stream through once per launch: keep them out of L1's
+    // way (evict-first), the memo tables and the search arrays live there
+    for (int s = 0; s < M::kState; ++s) y[s] = __ldcs(y_in + (size_t)s * v.ld + src);
+    rng.s0 = __ldcs(v.rng + 0 * v.ld_rng + i);
+    rng.s1 = __ldcs(v.rng + 1 * v.ld_rng + i);
+    rng.s2 = __ldcs(v.rng + 2 * v.ld_rng + i);
+    rng.s3 = __ldcs(v.rng + 3 * v.ld_rng + i);
 
     if (n_steps > 0) {
       int yi[M::kLeanState];
@@ -312,7 +314,7 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
 
     if (n_steps > 0 || y_in != y_out) {
 #pragma unroll
-      for (int s = 0; s < M::kState; ++s) y_out[(size_t)s * v.ld + i] = y[s];
+      for (int s = 0; s < M::kState; ++s) __stcs(y_out + (size_t)s * v.ld + i, y[s]);
     }
     if (HIST) {
       for (int k = 0; k < v.n_index; ++k) {
@@ -333,10 +335,10 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
       weighted = true;
     }
     if (n_steps > 0 || weighted) {
-      v.rng[0 * v.ld_rng + i] = rng.s0;
-      v.rng[1 * v.ld_rng + i] = rng.s1;
-      v.rng[2 * v.ld_rng + i] = rng.s2;
-      v.rng[3 * v.ld_rng + i] = rng.s3;
+      __stcs(v.rng + 0 * v.ld_rng + i, rng.s0);
+      __stcs(v.rng + 1 * v.ld_rng + i, rng.s1);
+      __stcs(v.rng + 2 * v.ld_rng + i, rng.s2);
+      __stcs(v.rng + 3 * v.ld_rng + i, rng.s3);
     }
   }
   if (row < 0) return;
