@@ -1,0 +1,381 @@
+"""pMCMC driving the B200 filter: the caller side of the hot path.
+
+The reference's ``pmcmc()`` is host logic around ``filter$run(pars)``
+(R/pmcmc_state.R:101-106): propose -> prior -> uniform -> filter -> accept
+(:108-138).  This module restates that control flow so the B200 filter can be
+driven exactly as mcstate drives its own (BASELINE config C3), and adds the
+B200 analogue of ``pmcmc_parallel`` (R/pmcmc_parallel.R:8-20): chains are
+sharded one per GPU / rank with ``torch.distributed``, seeded by long jumps so a
+result does not depend on where a chain ran (R/pmcmc_parallel.R:125-151), and
+the per-chain samples are gathered at the end (``pmcmc_combine``,
+R/pmcmc_tools.R:104-156).  There is no data-path collective: a chain's filter
+never leaves its GPU.
+
+Only what the path needs is here: simple (non-nested) parameters with a
+multivariate-normal proposal and reflecting bounds.  Nested parameter
+containers, adaptive proposals and the result-thinning helpers are out of scope
+(SURVEY.md section 2, rows 9, 10, 13).  R's global RNG (``runif``, ``rnorm``,
+``sample.int``) becomes a ``numpy.random.Generator`` seeded where the reference
+calls ``set.seed`` (R/pmcmc.R:75-81).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from .dust import dust_rng, dust_rng_distributed_state
+from .particle_filter import particle_filter_from_inputs
+
+
+# ---------------------------------------------------------------------------
+# parameters (R/pmcmc_parameters.R)
+# ---------------------------------------------------------------------------
+class pmcmc_parameter:
+    """``pmcmc_parameter(name, initial, min, max, discrete, integer, prior)``."""
+
+    def __init__(self, name, initial, min=-math.inf, max=math.inf, discrete=False,
+                 integer=False, prior=None):
+        if not (min <= initial <= max):
+            raise ValueError("'initial' must be within [min, max] for '%s'" % name)
+        self.name, self.initial, self.min, self.max = name, float(initial), float(min), float(max)
+        self.integer = bool(discrete or integer)
+        self.prior = prior if prior is not None else (lambda p: 0.0)
+        if not math.isfinite(self.prior(self.initial)):
+            raise ValueError("Prior for '%s' is not finite at its initial value" % name)
+
+
+def reflect_proposal(x, x_min, x_max):
+    """R/pmcmc_parameters.R:382-404: reflect a proposal at its bounds."""
+    x = np.array(x, dtype=float)
+    x_min, x_max = np.asarray(x_min, dtype=float), np.asarray(x_max, dtype=float)
+    out = x < x_min
+    out |= x > x_max
+    if out.any():
+        fmin, fmax = np.isfinite(x_min), np.isfinite(x_max)
+        both, lo, hi = out & fmin & fmax, out & fmin & ~fmax, out & ~fmin & fmax
+        xr = x_max[both] - x_min[both]
+        x[both] = np.abs(np.mod(x[both] + xr - x_min[both], 2 * xr) - xr) + x_min[both]
+        x[lo] = 2 * x_min[lo] - x[lo]
+        x[hi] = 2 * x_max[hi] - x[hi]
+    return x
+
+
+def rmvnorm_generator(vcv):
+    """R/utils.R:37-75: draws from N(mean, scale * vcv) by eigendecomposition, skipping
+    parameters whose row of ``vcv`` is all zero."""
+    vcv = np.asarray(vcv, dtype=float)
+    if vcv.ndim != 2 or vcv.shape[0] != vcv.shape[1] or not np.allclose(vcv, vcv.T, atol=1.5e-8):
+        raise ValueError("vcv must be symmetric")
+    include = ~np.all(vcv == 0, axis=1)
+    sub = vcv[np.ix_(include, include)]
+    values, vectors = np.linalg.eigh(sub) if sub.size else (np.zeros(0), np.zeros((0, 0)))
+    if values.size and not np.all(values >= -math.sqrt(np.finfo(float).eps) * abs(values[-1])):
+        raise ValueError("vcv must be positive definite")
+    res = (vectors * np.sqrt(np.maximum(values, 0))) @ vectors.T
+
+    def draw(mean, rng, scale=1.0):
+        x = np.zeros(include.size)
+        x[include] = rng.standard_normal(res.shape[0]) @ (res * math.sqrt(scale))
+        return np.asarray(mean, dtype=float) + x
+
+    return draw
+
+
+class pmcmc_parameters:
+    """``pmcmc_parameters$new(parameters, proposal, transform)`` (R/pmcmc_parameters.R)."""
+
+    def __init__(self, parameters, proposal, transform=None):
+        if len(parameters) == 0:
+            raise ValueError("At least one parameter is required")
+        self._p = list(parameters)
+        names = [p.name for p in self._p]
+        if len(set(names)) != len(names):
+            raise ValueError("Duplicate parameter names")
+        proposal = np.asarray(proposal, dtype=float)
+        if proposal.shape != (len(names), len(names)):
+            raise ValueError("Expected a square proposal matrix with %d rows" % len(names))
+        self._names = names
+        self._proposal = rmvnorm_generator(proposal)
+        self._min = np.array([p.min for p in self._p])
+        self._max = np.array([p.max for p in self._p])
+        self._integer = np.array([p.integer for p in self._p])
+        self._transform = transform if transform is not None else (lambda d: d)
+
+    def names(self):
+        return list(self._names)
+
+    def initial(self):
+        return np.array([p.initial for p in self._p])
+
+    def prior(self, theta):
+        return float(sum(p.prior(t) for p, t in zip(self._p, theta)))
+
+    def propose(self, theta, rng, scale=1.0):
+        theta = self._proposal(theta, rng, scale)
+        theta[self._integer] = np.round(theta[self._integer])
+        return reflect_proposal(theta, self._min, self._max)
+
+    def model(self, theta):
+        """theta -> what the filter's ``run`` takes (a dict of named values, transformed)."""
+        return self._transform(dict(zip(self._names, (float(t) for t in theta))))
+
+
+# ---------------------------------------------------------------------------
+# control (R/pmcmc_control.R:187-290, the fields this path reads)
+# ---------------------------------------------------------------------------
+class pmcmc_control:
+    def __init__(self, n_steps, n_chains=1, n_burnin=0, n_steps_retain=None, save_state=True,
+                 save_restart=None, save_trajectories=False, rerun_every=math.inf,
+                 rerun_random=False, filter_early_exit=False, use_parallel_seed=False,
+                 n_workers=1, progress=False):
+        if n_steps < 1 or n_chains < 1 or n_workers < 1:
+            raise ValueError("'n_steps', 'n_chains' and 'n_workers' must be at least 1")
+        if n_workers > n_chains:
+            raise ValueError("'n_chains' must be at least 'n_workers'")
+        if n_burnin >= n_steps:
+            raise ValueError("'n_burnin' cannot be greater than or equal to 'n_steps'")
+        self.n_steps, self.n_chains, self.n_burnin = int(n_steps), int(n_chains), int(n_burnin)
+        n_retain = self.n_steps - self.n_burnin
+        if n_steps_retain is None:
+            n_steps_retain = n_retain
+        if n_steps_retain > n_retain:
+            raise ValueError("'n_steps_retain' is too large, max possible is %d" % n_retain)
+        self.n_steps_retain = int(n_steps_retain)
+        self.n_steps_every = n_retain // self.n_steps_retain
+        # keep the last n_steps_retain * n_steps_every steps (R/pmcmc_control.R:292-311)
+        self.n_burnin = self.n_steps - self.n_steps_retain * self.n_steps_every
+        self.save_state, self.save_trajectories = bool(save_state), bool(save_trajectories)
+        self.save_restart = save_restart
+        self.rerun_every, self.rerun_random = rerun_every, bool(rerun_random)
+        self.filter_early_exit = bool(filter_early_exit)
+        # more than one worker always uses the parallel seeds (R/pmcmc_control.R:260-262)
+        self.use_parallel_seed = bool(use_parallel_seed) or n_workers > 1
+        self.n_workers, self.progress = int(n_workers), bool(progress)
+
+
+# ---------------------------------------------------------------------------
+# seeds (R/pmcmc_parallel.R:125-151)
+# ---------------------------------------------------------------------------
+def make_seeds(n, seed, algorithm="xoshiro256plus"):
+    """One ``dict(dust=<raw 32 k bytes>, r=<int>)`` per chain.  Chain k's filter streams
+    are the base state long-jumped k times (chain 1 = the input, prefix-stable in ``n``:
+    tests/testthat/test-pmcmc-parallel.R:40-60); the host-RNG seeds are
+    ``ceiling(random_real * 2^24)`` from one more long-jumped copy."""
+    n_streams = len(bytes(seed)) // 32 if isinstance(seed, (bytes, bytearray)) else 1
+    seed_dust = dust_rng_distributed_state(seed, n_streams, n, algorithm)
+    rng = dust_rng(seed_dust[0], algorithm).long_jump()
+    seed_r = np.ceil(np.asarray(rng.random_real(n)) * 2 ** 24).astype(np.int64)
+    return [{"dust": seed_dust[i], "r": int(seed_r[i])} for i in range(n)]
+
+
+# ---------------------------------------------------------------------------
+# one chain (R/pmcmc_state.R)
+# ---------------------------------------------------------------------------
+def _make_rerun(every, random, rng):
+    if not math.isfinite(every):
+        return lambda i: False
+    if random:
+        return lambda i: rng.random() < 1.0 / every
+    return lambda i: i % every == 0
+
+
+class pmcmc_state:
+    """R/pmcmc_state.R: the Metropolis-Hastings state machine of one chain."""
+
+    def __init__(self, pars, initial, filter, control, rng):
+        if getattr(filter, "has_multiple_parameters", False):
+            raise ValueError("nested filters need pmcmc_parameters_nested (out of scope here)")
+        self._filter, self._pars, self._control, self._rng = filter, pars, control, rng
+        self.n_filter_runs = 0
+        self._curr_pars = np.array(initial, dtype=float)
+        self._curr_lprior = pars.prior(self._curr_pars)
+        self._curr_llik = self._run_filter(self._curr_pars)
+        self._curr_lpost = self._curr_lprior + self._curr_llik
+        self._curr_state = self._curr_traj = self._curr_restart = None
+        self._update_particle_history()
+        self._h_pars, self._h_prob = [], []
+        self._h_state, self._h_traj, self._h_restart = [], [], []
+
+    def _run_filter(self, theta, min_log_likelihood=-math.inf):
+        # R/pmcmc_state.R:101-106 -- the hot path, once per step
+        self.n_filter_runs += 1
+        c = self._control
+        return float(self._filter.run(self._pars.model(theta), c.save_trajectories,
+                                      c.save_restart, min_log_likelihood))
+
+    def _update_particle_history(self):
+        # R/pmcmc_state.R:32-51: ONE particle's lineage leaves the device
+        c = self._control
+        i = int(self._rng.integers(1, self._filter.n_particles + 1))
+        if c.save_trajectories:
+            self._curr_traj = np.asarray(self._filter.history(i))[:, 0]
+        if c.save_state:
+            self._curr_state = np.asarray(self._filter.state())[:, i - 1]
+        if c.save_restart is not None and len(c.save_restart) > 0:
+            self._curr_restart = np.asarray(self._filter.restart_state(i, c.save_restart))[:, 0]
+
+    def _min_log_likelihood(self, prop_lprior, u):
+        # u < exp(prop_llik + prop_lprior - curr_lpost)   (R/pmcmc_state.R:85-99)
+        if not self._control.filter_early_exit:
+            return -math.inf
+        return self._curr_lpost - prop_lprior + math.log(u)
+
+    def _update_simple(self):
+        # R/pmcmc_state.R:108-138
+        prop_pars = self._pars.propose(self._curr_pars, self._rng)
+        prop_lprior = self._pars.prior(prop_pars)
+        u = self._rng.random()
+        prop_llik = self._run_filter(prop_pars, self._min_log_likelihood(prop_lprior, u))
+        prop_lpost = prop_lprior + prop_llik
+        d = prop_lpost - self._curr_lpost
+        accept_prob = 1.0 if d >= 0 else (math.exp(d) if d == d else 0.0)
+        if u < accept_prob:
+            self._curr_pars, self._curr_lprior = prop_pars, prop_lprior
+            self._curr_llik, self._curr_lpost = prop_llik, prop_lpost
+            self._update_particle_history()
+
+    def _record(self, i):
+        # R/pmcmc_state.R:53-84
+        c = self._control
+        self._h_pars.append(self._curr_pars.copy())
+        self._h_prob.append((self._curr_lprior, self._curr_llik, self._curr_lpost))
+        j = i - c.n_burnin - 1
+        if j >= 0 and j % c.n_steps_every == 0:
+            if c.save_trajectories:
+                self._h_traj.append(self._curr_traj)
+            if c.save_state:
+                self._h_state.append(self._curr_state)
+            if self._curr_restart is not None:
+                self._h_restart.append(self._curr_restart)
+
+    def run(self):
+        # R/pmcmc_state.R:284-308
+        c = self._control
+        rerun = _make_rerun(c.rerun_every, c.rerun_random, self._rng)
+        for i in range(1, c.n_steps + 1):
+            if rerun(i):
+                self._curr_llik = self._run_filter(self._curr_pars)
+                self._curr_lpost = self._curr_lprior + self._curr_llik
+                self._update_particle_history()
+            self._update_simple()
+            self._record(i)
+
+    def finish(self):
+        # R/pmcmc_state.R:310-428: keep every n_steps_every-th step after the burn-in
+        c = self._control
+        keep = [i for i in range(c.n_steps) if i - c.n_burnin >= 0
+                and (i - c.n_burnin) % c.n_steps_every == 0]
+        out = {
+            "pars": np.array(self._h_pars)[keep],
+            "probabilities": np.array(self._h_prob)[keep],
+            "pars_names": self._pars.names(),
+            "iteration": np.array(keep) + 1,
+            "chain": None,
+            "state": np.stack(self._h_state, axis=1) if self._h_state else None,
+            "trajectories": np.stack(self._h_traj, axis=1) if self._h_traj else None,
+            "restart": np.stack(self._h_restart, axis=1) if self._h_restart else None,
+            "n_filter_runs": self.n_filter_runs,
+        }
+        return out
+
+
+def pmcmc_run_chain(pars, initial, filter, control, rng):
+    """R/pmcmc.R:93-102."""
+    obj = pmcmc_state(pars, initial, filter, control, rng)
+    obj.run()
+    return obj.finish()
+
+
+def pmcmc_combine(samples):
+    """R/pmcmc_tools.R:104-156: stack chains, remembering which sample came from which."""
+    out = {"pars_names": samples[0]["pars_names"]}
+    for key in ("pars", "probabilities", "iteration"):
+        out[key] = np.concatenate([s[key] for s in samples], axis=0)
+    out["chain"] = np.concatenate([np.full(s["pars"].shape[0], k + 1)
+                                   for k, s in enumerate(samples)])
+    for key in ("state", "trajectories", "restart"):
+        parts = [s[key] for s in samples]
+        out[key] = None if any(p is None for p in parts) else np.concatenate(parts, axis=1)
+    out["n_filter_runs"] = int(sum(s["n_filter_runs"] for s in samples))
+    return out
+
+
+def _check_initial(initial, pars, n_chains):
+    # R/pmcmc.R: pmcmc_check_initial -- a vector is recycled over chains
+    if initial is None:
+        initial = pars.initial()
+    initial = np.asarray(initial, dtype=float)
+    if initial.ndim == 1:
+        initial = np.tile(initial[None, :], (n_chains, 1))
+    if initial.shape != (n_chains, len(pars.names())):
+        raise ValueError("Expected 'initial' to have %d columns and %d rows"
+                         % (len(pars.names()), n_chains))
+    for row in initial:
+        if not math.isfinite(pars.prior(row)):
+            raise ValueError("Starting point does not have finite prior probability")
+    return initial
+
+
+def _run_one(k, pars, initial, filter, control, seeds, device):
+    """Chain k (0-based) on ``device``: a fresh filter on the chain's own streams and a
+    host RNG seeded as ``set.seed(seed$r)`` (R/pmcmc.R:75-81, R/pmcmc_chains.R:71-97)."""
+    if seeds is None:
+        return pmcmc_run_chain(pars, initial[k], filter, control, np.random.default_rng())
+    inputs = dict(filter.inputs())
+    if device is not None and inputs.get("gpu_config") is not None:
+        inputs["gpu_config"] = device
+    f = particle_filter_from_inputs(inputs, seeds[k]["dust"])
+    return pmcmc_run_chain(pars, initial[k], f, control, np.random.default_rng(seeds[k]["r"]))
+
+
+def pmcmc(pars, filter, initial=None, control=None):
+    """``pmcmc(pars, filter, initial, control)`` (R/pmcmc.R:47-58).
+
+    ``control.n_workers == 1``: chains run one after another on this process's device
+    (``pmcmc_multiple_series``, R/pmcmc.R:61-90).  ``n_workers > 1``: the chains are
+    sharded over the ranks of the initialised ``torch.distributed`` group, rank r taking
+    chains r, r + world, ... on its own GPU (``pmcmc_sharded``)."""
+    if control is None:
+        raise TypeError("'control' must be a pmcmc_control")
+    if control.n_workers > 1:
+        return pmcmc_sharded(pars, filter, initial, control)
+    initial = _check_initial(initial, pars, control.n_chains)
+    seeds = None
+    if control.use_parallel_seed:
+        seeds = make_seeds(control.n_chains, filter.inputs()["seed"],
+                           getattr(filter.model, "algorithm", "xoshiro256plus"))
+    samples = [_run_one(k, pars, initial, filter, control, seeds, None)
+               for k in range(control.n_chains)]
+    return samples[0] if control.n_chains == 1 else pmcmc_combine(samples)
+
+
+def chain_owner(chain, world):
+    """Which rank runs chain ``chain`` (0-based): round robin, like the reference hands
+    the next chain to the next free worker (R/pmcmc_parallel.R:71-102)."""
+    return chain % world
+
+
+def pmcmc_sharded(pars, filter, initial=None, control=None, group=None, device=None):
+    """The B200 ``pmcmc_parallel``: one chain per GPU at a time, no collective while the
+    chains run, one gather of the per-chain samples at the end.  Every rank returns the
+    combined result, identical to the serial run with ``use_parallel_seed``
+    (tests/testthat/test-pmcmc-parallel.R:3-25)."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("pmcmc with n_workers > 1 needs an initialised torch.distributed "
+                           "process group (one rank per GPU)")
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    initial = _check_initial(initial, pars, control.n_chains)
+    seeds = make_seeds(control.n_chains, filter.inputs()["seed"],
+                       getattr(filter.model, "algorithm", "xoshiro256plus"))
+    mine = {k: _run_one(k, pars, initial, filter, control, seeds, device)
+            for k in range(control.n_chains) if chain_owner(k, world) == rank}
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine, group=group)
+    merged = {}
+    for part in gathered:
+        merged.update(part)
+    samples = [merged[k] for k in range(control.n_chains)]
+    return samples[0] if control.n_chains == 1 else pmcmc_combine(samples)

@@ -1,0 +1,225 @@
+"""pMCMC driving the filter (mcstate_b200.pmcmc) against the relations the reference
+asserts for pmcmc / pmcmc_parallel (file:line per test).
+
+CPU runs use the oracle-backed generator (a test double, as the reference's own MCMC
+tests use fake filters: tests/testthat/helper-mcstate.R:222-386); `-m gpu` runs the
+same on the B200 engine.  The sharded path is covered with world_size-2 gloo processes.
+"""
+import math
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+from mcstate_b200.particle_filter import particle_filter
+from mcstate_b200.particle_filter_data import particle_filter_data
+from mcstate_b200.pmcmc import (chain_owner, make_seeds, pmcmc, pmcmc_control, pmcmc_parameter,
+                                pmcmc_parameters, reflect_proposal, rmvnorm_generator)
+from oracle_generator import OracleGenerator
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BACKENDS = [pytest.param("oracle", id="oracle"),
+            pytest.param("gpu", id="b200", marks=pytest.mark.gpu)]
+
+
+def _generator(kind):
+    if kind == "oracle":
+        return OracleGenerator("sir")
+    from mcstate_b200 import dust
+
+    g = dust.dust_example("sir")
+    if not g.gpu_info()["has_cuda"]:
+        pytest.fail("no CUDA device visible: the engine has no CPU fallback")
+    return g
+
+
+def example_pars():
+    """tests/testthat/helper-mcstate.R:44-52."""
+    kernel = [[0.00057, 0.00034], [0.00034, 0.00026]]
+    flat = lambda p: math.log(1e-10)  # noqa: E731
+    return pmcmc_parameters([pmcmc_parameter("beta", 0.2, min=0, max=1, prior=flat),
+                             pmcmc_parameter("gamma", 0.1, min=0, max=1, prior=flat)], kernel)
+
+
+def example_filter(kind, sir_data, n_particles=64, seed=1):
+    data = particle_filter_data({"day": sir_data["day"], "incidence": sir_data["incidence"]},
+                                "day", 4, 0)
+    index = lambda info: {"run": [5], "state": [1, 2, 3]}  # noqa: E731
+    gpu = 0 if kind == "gpu" else None
+    return particle_filter(data, _generator(kind), n_particles, None, index=index, seed=seed,
+                           gpu_config=gpu)
+
+
+# ---------------------------------------------------------------- pure host pieces
+def test_reflect_proposal_known_answers():
+    """tests/testthat/test-pmcmc.R:40-75."""
+    inf = math.inf
+    assert list(reflect_proposal([0.4, 1.2, 2.6], [0] * 3, [inf] * 3)) == [0.4, 1.2, 2.6]
+    assert np.allclose(reflect_proposal([-0.4, 1.2, 2.6], [0] * 3, [inf] * 3), [0.4, 1.2, 2.6])
+    assert np.allclose(reflect_proposal([0.4, 1.4, 2.6], [-inf] * 3, [1] * 3), [0.4, 0.6, -0.6])
+    x = np.array([0.5, 1.25, 2.5, -0.25, -1.75])
+    assert np.allclose(reflect_proposal(x, [0] * 5, [1] * 5), [0.5, 0.75, 0.5, 0.25, 0.25])
+
+
+def test_rmvnorm_generator_moments_and_zero_rows():
+    vcv = np.array([[4.0, 1.0, 0.0], [1.0, 2.0, 0.0], [0.0, 0.0, 0.0]])
+    draw = rmvnorm_generator(vcv)
+    rng = np.random.default_rng(1)
+    x = np.array([draw([1.0, 2.0, 3.0], rng) for _ in range(20000)])
+    assert np.all(x[:, 2] == 3.0)  # the all-zero row never moves (R/utils.R:49-53)
+    assert np.allclose(x.mean(axis=0), [1, 2, 3], atol=0.05)
+    assert np.allclose(np.cov(x[:, :2].T), vcv[:2, :2], atol=0.1)
+    with pytest.raises(ValueError, match="symmetric"):
+        rmvnorm_generator([[1.0, 0.5], [0.0, 1.0]])
+
+
+def test_control_validation_and_retention():
+    c = pmcmc_control(100, n_burnin=10, n_steps_retain=30)
+    assert (c.n_steps_every, c.n_burnin) == (3, 10)
+    with pytest.raises(ValueError):
+        pmcmc_control(10, n_chains=1, n_workers=2)
+    with pytest.raises(ValueError):
+        pmcmc_control(10, n_burnin=10)
+    assert pmcmc_control(10, n_chains=2, n_workers=2).use_parallel_seed
+
+
+def test_make_seeds_deterministic_prefix_stable():
+    """tests/testthat/test-pmcmc-parallel.R:40-60."""
+    s2, s5 = make_seeds(2, 1), make_seeds(5, 1)
+    assert all(len(s["dust"]) == 32 for s in s5)
+    assert [s["dust"] for s in s5[:2]] == [s["dust"] for s in s2]  # prefix stable
+    assert [s["r"] for s in s5[:2]] == [s["r"] for s in s2]
+    from mcstate_b200.dust import dust_rng
+
+    assert s5[0]["dust"] == dust_rng(1).state()  # chain 1 runs on the input seed
+    assert s5[1]["dust"] == dust_rng(1).long_jump().state()
+    assert all(1 <= s["r"] <= 2 ** 24 for s in s5)
+    raw = make_seeds(3, s5[1]["dust"] + s5[2]["dust"])  # a raw 64-byte seed: two streams
+    assert all(len(s["dust"]) == 64 for s in raw)
+    assert [chain_owner(k, 2) for k in range(5)] == [0, 1, 0, 1, 0]
+
+
+# ---------------------------------------------------------------- chains on a filter
+@pytest.mark.parametrize("kind", BACKENDS)
+def test_pmcmc_runs_and_is_reproducible(kind, sir_data):
+    """tests/testthat/test-pmcmc.R:80-108: shapes, and same seeds => same chain."""
+    control = pmcmc_control(30, n_chains=1, save_state=True, save_trajectories=True,
+                            use_parallel_seed=True)
+    a = pmcmc(example_pars(), example_filter(kind, sir_data), control=control)
+    b = pmcmc(example_pars(), example_filter(kind, sir_data), control=control)
+    assert a["pars"].shape == (30, 2) and a["probabilities"].shape == (30, 3)
+    assert a["state"].shape == (5, 30)
+    assert a["trajectories"].shape == (3, 30, 101)
+    assert np.array_equal(a["pars"], b["pars"])
+    assert np.array_equal(a["probabilities"], b["probabilities"])
+    assert np.array_equal(a["trajectories"], b["trajectories"])
+    assert np.allclose(a["probabilities"][:, 0] + a["probabilities"][:, 1],
+                       a["probabilities"][:, 2])
+    assert a["n_filter_runs"] == 31  # one at initialisation, one per step
+    # lineages: S never rises, R never falls (tests/testthat/test-particle-filter.R:270-293)
+    assert np.all(np.diff(a["trajectories"][0], axis=1) <= 0)
+    assert np.all(np.diff(a["trajectories"][2], axis=1) >= 0)
+
+
+@pytest.mark.parametrize("kind", BACKENDS)
+def test_chain_independent_of_what_is_saved(kind, sir_data):
+    """tests/testthat/test-pmcmc.R:110-128: saving state/trajectories changes nothing.
+    (The particle index is drawn from the host RNG either way.)"""
+    pars = example_pars()
+    c1 = pmcmc_control(20, save_state=False, save_trajectories=False, use_parallel_seed=True)
+    c2 = pmcmc_control(20, save_state=True, save_trajectories=True, use_parallel_seed=True)
+    a = pmcmc(pars, example_filter(kind, sir_data), control=c1)
+    b = pmcmc(pars, example_filter(kind, sir_data), control=c2)
+    assert a["state"] is None and a["trajectories"] is None
+    assert np.array_equal(a["pars"], b["pars"])
+    assert np.array_equal(a["probabilities"], b["probabilities"])
+
+
+@pytest.mark.parametrize("kind", BACKENDS)
+def test_early_exit_does_not_change_the_chain(kind, sir_data):
+    """filter_early_exit only skips work for proposals that would be rejected anyway
+    (R/pmcmc_state.R:85-99); on the compiled path the reference never forwards the
+    bound (R/particle_filter_state.R:151), so the chain is identical."""
+    pars = example_pars()
+    a = pmcmc(pars, example_filter(kind, sir_data),
+              control=pmcmc_control(20, use_parallel_seed=True))
+    b = pmcmc(pars, example_filter(kind, sir_data),
+              control=pmcmc_control(20, use_parallel_seed=True, filter_early_exit=True))
+    assert np.array_equal(a["pars"], b["pars"])
+
+
+@pytest.mark.parametrize("kind", BACKENDS)
+def test_multiple_chains_and_rerun(kind, sir_data):
+    control = pmcmc_control(12, n_chains=3, use_parallel_seed=True, rerun_every=4)
+    res = pmcmc(example_pars(), example_filter(kind, sir_data), control=control)
+    assert res["pars"].shape == (36, 2)
+    assert list(np.unique(res["chain"])) == [1, 2, 3]
+    assert res["n_filter_runs"] == 3 * (1 + 12 + 3)  # + a rerun at steps 4, 8, 12
+    assert not np.array_equal(res["pars"][:12], res["pars"][12:24])  # chains differ
+    # chain 1 of a 3-chain run == the single-chain run (same seeds: prefix stability)
+    one = pmcmc(example_pars(), example_filter(kind, sir_data),
+                control=pmcmc_control(12, n_chains=1, use_parallel_seed=True, rerun_every=4))
+    assert np.array_equal(one["pars"], res["pars"][:12])
+
+
+def test_posterior_moves_towards_the_data(sir_data):
+    """A sanity check of the sampler itself: starting from poor parameters the chain
+    climbs (tests/testthat/test-pmcmc.R uses the same style of check on its fixtures)."""
+    f = example_filter("oracle", sir_data, n_particles=128)
+    res = pmcmc(example_pars(), f, initial=[0.35, 0.25],
+                control=pmcmc_control(150, use_parallel_seed=True))
+    assert res["probabilities"][-30:, 1].mean() > res["probabilities"][0, 1] + 5
+
+
+# ---------------------------------------------------------------- sharded == serial
+_WORKER = textwrap.dedent("""
+    import os, sys, pickle
+    import numpy as np
+    import torch.distributed as dist
+    sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+    from test_pmcmc import example_filter, example_pars
+    from mcstate_b200.pmcmc import pmcmc, pmcmc_control
+    kind, n_chains = sys.argv[1], int(sys.argv[2])
+    dist.init_process_group({backend!r})
+    rank, world = dist.get_rank(), dist.get_world_size()
+    d = np.loadtxt(os.path.join({root!r}, "tests", "golden", "sir_incidence.csv"), delimiter=",",
+                   skiprows=1)
+    sir = {{"day": d[:, 1].astype(int), "incidence": d[:, 0]}}
+    control = pmcmc_control(10, n_chains=n_chains, n_workers=world, save_trajectories=True)
+    res = pmcmc(example_pars(), example_filter(kind, sir), control=control)
+    if rank == 0:
+        with open(sys.argv[3], "wb") as fh:
+            pickle.dump(res, fh)
+    dist.barrier()
+    dist.destroy_process_group()
+""")
+
+
+def _run_sharded(tmp_path, kind, n_chains, world, backend):
+    import pickle
+
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT, backend=backend))
+    out = tmp_path / "res.pkl"
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+           "--nproc-per-node=%d" % world, "--master-addr", "127.0.0.1", "--master-port",
+           str(29500 + os.getpid() % 2000), str(script), kind, str(n_chains), str(out)]
+    p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-3000:]
+    with open(out, "rb") as fh:
+        return pickle.load(fh)
+
+
+def test_sharded_chains_equal_serial_gloo(tmp_path, sir_data):
+    """tests/testthat/test-pmcmc-parallel.R:3-25: results do not depend on the number of
+    workers.  Two gloo ranks, three chains (rank 0 runs chains 1 and 3)."""
+    serial = pmcmc(example_pars(), example_filter("oracle", sir_data),
+                   control=pmcmc_control(10, n_chains=3, use_parallel_seed=True,
+                                         save_trajectories=True))
+    sharded = _run_sharded(tmp_path, "oracle", 3, 2, "gloo")
+    for key in ("pars", "probabilities", "chain", "iteration", "state", "trajectories"):
+        assert np.array_equal(serial[key], sharded[key]), key
