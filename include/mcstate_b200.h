@@ -68,6 +68,9 @@ int mcb_rng_jump(uint64_t state[4]);
 int mcb_rng_long_jump(uint64_t state[4]);
 /* $random_real(n) on one stream (R/pmcmc_parallel.R:148) */
 int mcb_rng_random_real(uint64_t state[4], int scrambler, size_t n, double *out);
+/* n jumps at once (stream i of a seed = the seed jumped i times): how a shard finds
+ * the first stream of its block of a larger model without walking there */
+int mcb_rng_jump_n(uint64_t state[4], uint64_t n);
 /* dust::dust_rng_distributed_state (R/pmcmc_parallel.R:133, R/smc2.R:68):
  * out[n_nodes][n_streams][4]; node k = seed long-jumped k times */
 int mcb_rng_distributed_state(const uint64_t seed_state[4], size_t n_streams,
@@ -85,6 +88,20 @@ int mcb_rng_distributed_state(const uint64_t seed_state[4], size_t n_streams,
 int mcb_alloc(int model_id, const double *pars, size_t n_particles, size_t n_pars,
               uint64_t time, const uint64_t *seed_state, size_t n_seed_streams,
               int scrambler, int deterministic, int device_id, mcb_model **out);
+/*
+ * The same with the seeding made explicit.  MCB_SEED_SHARED is mcb_alloc (the dust
+ * pars_multi layout: n_total particle streams and ONE filter stream shared by all
+ * sets).  MCB_SEED_PER_SET takes one seed stream per parameter set and gives set p the
+ * streams a separate model object seeded with it would hold (n_particles particle
+ * streams and its own filter stream): independent filters batched in one handle, the
+ * layout smc2 uses for its parameter particles (R/smc2.R:68-78).
+ */
+#define MCB_SEED_SHARED 0
+#define MCB_SEED_PER_SET 1
+int mcb_alloc_ex(int model_id, const double *pars, size_t n_particles, size_t n_pars,
+                 uint64_t time, const uint64_t *seed_state, size_t n_seed_streams,
+                 int seed_mode, int scrambler, int deterministic, int device_id,
+                 mcb_model **out);
 int mcb_free(mcb_model *m);
 /* launch everything on this cudaStream_t (default: a stream owned by the handle) */
 int mcb_set_stream(mcb_model *m, void *cuda_stream);
@@ -126,6 +143,27 @@ int mcb_set_rng_state(mcb_model *m, const uint64_t *state, size_t n_words);
  */
 int mcb_set_data(mcb_model *m, size_t n_data, const uint64_t *time_end,
                  const double *values, int shared);
+/*
+ * Sharding one multi-parameter model over several handles / GPUs (nested populations,
+ * SURVEY.md 8e): the model's single filter stream draws one uniform per set per data
+ * row, in set order.  A handle that holds sets [set_offset, set_offset + n_pars) of
+ * n_sets_global replays the whole order on its own copy of the stream and keeps only
+ * its own draws, so every shard's stream advances exactly as the unsharded model's
+ * would.  na_global [n_data][n_sets_global] (1 = that set's datum is NA, no draw) is
+ * needed because a shard does not hold the other sets' data.  Call after mcb_set_data;
+ * mcb_set_filter_stream installs the shared stream (stream n_total_global of the seed).
+ */
+int mcb_set_filter_stream(mcb_model *m, const uint64_t state[4]);
+int mcb_set_stream_sharing(mcb_model *m, size_t n_sets_global, size_t set_offset,
+                           const unsigned char *na_global);
+/*
+ * smc2 replenishment on the device (R/smc2.R:174-189, `filter[accept] <- proposed$filter
+ * [accept]`; R/particle_filter_state.R:420, the parent's RNG takes the child's): for every
+ * parameter set p with take[p] != 0 copy the particle state and/or the RNG streams of
+ * `src` into `dst` (same shape, same device).  RNG copies need MCB_SEED_PER_SET.
+ */
+int mcb_copy_sets(mcb_model *dst, mcb_model *src, const unsigned char *take, int copy_state,
+                  int copy_rng);
 /* $compare_data(): log-weights [n_total] for the datum at the current time;
  * *has_data = 0 (and out untouched) when there is none */
 int mcb_compare_data(mcb_model *m, double *logw, int *has_data);

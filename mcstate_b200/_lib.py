@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("MCSTATE_B200_LIB") or os.path.join(_HERE, "libmcstate
 
 OK, ERR_ARG, ERR_CUDA, ERR_STATE = 0, -1, -2, -3
 SCRAMBLER_PLUS, SCRAMBLER_STARSTAR = 0, 1
+SEED_SHARED, SEED_PER_SET = 0, 1
 
 u64p = C.POINTER(C.c_uint64)
 f64p = C.POINTER(C.c_double)
@@ -46,9 +47,12 @@ SIGNATURES = {
     "mcb_rng_jump": (C.c_int, [u64p]),
     "mcb_rng_long_jump": (C.c_int, [u64p]),
     "mcb_rng_random_real": (C.c_int, [u64p, C.c_int, C.c_size_t, f64p]),
+    "mcb_rng_jump_n": (C.c_int, [u64p, C.c_uint64]),
     "mcb_rng_distributed_state": (C.c_int, [u64p, C.c_size_t, C.c_size_t, u64p]),
     "mcb_alloc": (C.c_int, [C.c_int, f64p, C.c_size_t, C.c_size_t, C.c_uint64, u64p, C.c_size_t,
                             C.c_int, C.c_int, C.c_int, C.POINTER(handle_p)]),
+    "mcb_alloc_ex": (C.c_int, [C.c_int, f64p, C.c_size_t, C.c_size_t, C.c_uint64, u64p, C.c_size_t,
+                               C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(handle_p)]),
     "mcb_free": (C.c_int, [handle_p]),
     "mcb_set_stream": (C.c_int, [handle_p, C.c_void_p]),
     "mcb_synchronize": (C.c_int, [handle_p]),
@@ -64,6 +68,9 @@ SIGNATURES = {
     "mcb_rng_state": (C.c_int, [handle_p, C.c_int, u64p]),
     "mcb_set_rng_state": (C.c_int, [handle_p, u64p, C.c_size_t]),
     "mcb_set_data": (C.c_int, [handle_p, C.c_size_t, u64p, f64p, C.c_int]),
+    "mcb_set_filter_stream": (C.c_int, [handle_p, u64p]),
+    "mcb_set_stream_sharing": (C.c_int, [handle_p, C.c_size_t, C.c_size_t, C.c_char_p]),
+    "mcb_copy_sets": (C.c_int, [handle_p, handle_p, C.c_char_p, C.c_int, C.c_int]),
     "mcb_compare_data": (C.c_int, [handle_p, f64p, i32p]),
     "mcb_resample": (C.c_int, [handle_p, f64p, i32p]),
     "mcb_filter_rows": (C.c_int, [handle_p, C.c_uint64, szp]),

@@ -147,6 +147,7 @@ struct mcb_model {
   double *d_u = nullptr;
   uint64_t *d_fs_after = nullptr;
   unsigned long long *d_wmax = nullptr;
+  unsigned char *d_na_global = nullptr;
 
   // state
   double *d_pars = nullptr;
@@ -275,10 +276,11 @@ void set_initial(mcb_model *m) {
 }
 
 void draw_uniforms(mcb_model *m, int row_first, int row_last) {
+  const unsigned grid = blocks_for((size_t)m->v.n_fs, 128);
   if (m->scrambler == 0)
-    mcb::k_draw_uniforms<0><<<1, 32, 0, m->stream>>>(m->v, row_first, row_last, m->d_u, m->d_fs_after);
+    mcb::k_draw_uniforms<0><<<grid, 128, 0, m->stream>>>(m->v, row_first, row_last, m->d_u, m->d_fs_after);
   else
-    mcb::k_draw_uniforms<1><<<1, 32, 0, m->stream>>>(m->v, row_first, row_last, m->d_u, m->d_fs_after);
+    mcb::k_draw_uniforms<1><<<grid, 128, 0, m->stream>>>(m->v, row_first, row_last, m->d_u, m->d_fs_after);
   ++m->launches;
 }
 
@@ -376,7 +378,8 @@ uint64_t enqueue_filter_rows(mcb_model *m, int first, int last, bool hist,
   finish_state(m, last, prev_weighted >= 0 ? 1 : 0, prev_weighted >= 0 ? order_last : nullptr);
   if (hist && prev_weighted < 0) iota(order_last);
   mark(m, (int)m->n_data, 1);
-  mcb::k_filter_finish<<<1, 32, 0, m->stream>>>(v, first, last, m->d_fs_after);
+  mcb::k_filter_finish<<<blocks_for((size_t)v.n_fs, 128), 128, 0, m->stream>>>(v, first, last,
+                                                                                m->d_fs_after);
   ++m->launches;
   return m->launches - before;
 }
@@ -602,6 +605,13 @@ int mcb_rng_distributed_state(const uint64_t seed_state[4], size_t n_streams, si
 int mcb_alloc(int model_id, const double *pars, size_t n_particles, size_t n_pars, uint64_t time,
               const uint64_t *seed_state, size_t n_seed_streams, int scrambler,
               int deterministic, int device_id, mcb_model **out) {
+  return mcb_alloc_ex(model_id, pars, n_particles, n_pars, time, seed_state, n_seed_streams,
+                      MCB_SEED_SHARED, scrambler, deterministic, device_id, out);
+}
+
+int mcb_alloc_ex(int model_id, const double *pars, size_t n_particles, size_t n_pars,
+                 uint64_t time, const uint64_t *seed_state, size_t n_seed_streams, int seed_mode,
+                 int scrambler, int deterministic, int device_id, mcb_model **out) {
   if (!out) return fail(MCB_ERR_ARG, "out is NULL");
   *out = nullptr;
   if (model_id < 0 || model_id >= kNumModels) return fail(MCB_ERR_ARG, "unknown model id");
@@ -610,6 +620,10 @@ int mcb_alloc(int model_id, const double *pars, size_t n_particles, size_t n_par
   if (!seed_state || n_seed_streams == 0) return fail(MCB_ERR_ARG, "seed state is empty");
   if (scrambler != MCB_SCRAMBLER_PLUS && scrambler != MCB_SCRAMBLER_STARSTAR)
     return fail(MCB_ERR_ARG, "unknown scrambler");
+  if (seed_mode != MCB_SEED_SHARED && seed_mode != MCB_SEED_PER_SET)
+    return fail(MCB_ERR_ARG, "unknown seed mode");
+  if (seed_mode == MCB_SEED_PER_SET && n_seed_streams != (n_pars == 0 ? 1 : n_pars))
+    return fail(MCB_ERR_ARG, "per-set seeding needs exactly one seed stream per parameter set");
   const size_t n_sets = n_pars == 0 ? 1 : n_pars;
   const size_t n_total = n_particles * n_sets;
   if (n_total >= ((size_t)1 << 31)) return fail(MCB_ERR_ARG, "too many particles (int32 kappa)");
@@ -631,7 +645,11 @@ int mcb_alloc(int model_id, const double *pars, size_t n_particles, size_t n_par
   v.n_sets = n_sets;
   v.n_total = n_total;
   v.ld = round_up(n_total, 32);
-  v.ld_rng = round_up(n_total + 1, 32);
+  v.n_fs = seed_mode == MCB_SEED_PER_SET ? (int)n_sets : 1;
+  v.n_sets_global = (int)n_sets;
+  v.set_offset = 0;
+  v.na_global = nullptr;
+  v.ld_rng = round_up(n_total + v.n_fs, 32);
   v.n_state = m->desc->n_state;
   v.n_index = v.n_state;
   v.n_min = 0;
@@ -682,7 +700,7 @@ int mcb_alloc(int model_id, const double *pars, size_t n_particles, size_t n_par
   ALLOC(m->d_kappa, v.ld * sizeof(int));
   ALLOC(m->d_u, n_sets * sizeof(double));
   ALLOC(m->d_wmax, n_sets * sizeof(unsigned long long));
-  ALLOC(m->d_fs_after, 4 * sizeof(uint64_t));
+  ALLOC(m->d_fs_after, 4 * (size_t)v.n_fs * sizeof(uint64_t));
 #undef ALLOC
   v.pars = m->d_pars;
   v.ll = m->d_ll;
@@ -707,7 +725,21 @@ int mcb_alloc(int model_id, const double *pars, size_t n_particles, size_t n_par
                   cudaMemcpyHostToDevice, m->stream);
 
   // RNG streams: supplied ones verbatim, the rest by parallel jump-ahead
-  {
+  if (seed_mode == MCB_SEED_PER_SET) {
+    uint64_t *d_bases = nullptr, *d_jump = nullptr;
+    int rc = jump_table_device(device_id, &d_jump);
+    if (rc != MCB_OK) return cleanup(rc);
+    if (cudaMalloc(&d_bases, n_sets * 4 * sizeof(uint64_t)) != cudaSuccess)
+      return cleanup(fail(MCB_ERR_CUDA, "cudaMalloc: seed bases"));
+    cudaMemcpyAsync(d_bases, seed_state, n_sets * 4 * sizeof(uint64_t), cudaMemcpyHostToDevice,
+                    m->stream);
+    mcb::k_derive_streams_per_set<<<blocks_for((n_particles + 1) * n_sets, 128), 128, 0,
+                                    m->stream>>>(v.rng, v.ld_rng, d_bases, n_particles, n_sets,
+                                                 d_jump);
+    ++m->launches;
+    cudaStreamSynchronize(m->stream);
+    cudaFree(d_bases);
+  } else {
     const size_t n_streams = n_total + 1;
     const size_t have = n_seed_streams < n_streams ? n_seed_streams : n_streams;
     std::vector<uint64_t> soa(4 * have);
@@ -742,7 +774,7 @@ int mcb_free(mcb_model *m) {
   clear_graphs(m);
   void *ptrs[] = {m->v.y, m->v.y_tmp, m->v.rng, m->v.derived, m->v.tables, m->d_pars, m->v.logw, m->v.cw, m->v.tile_incl,
                   m->v.setinfo, m->d_ll, m->d_min_ll, m->d_flags, m->d_ticket, m->d_index, m->d_kappa, m->d_u,
-                  m->d_wmax, m->d_fs_after, m->d_data, m->d_stage, m->d_hist_value,
+                  m->d_wmax, m->d_fs_after, m->d_na_global, m->d_data, m->d_stage, m->d_hist_value,
                   m->d_hist_order, m->d_traj, m->d_snap};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -916,7 +948,7 @@ int mcb_rng_state(mcb_model *m, int first_only, uint64_t *out) {
   if (!m || !out) return fail(MCB_ERR_ARG, "NULL argument");
   MCB_CUDA(cudaSetDevice(m->device));
   const View &v = m->v;
-  const size_t n = first_only ? 1 : v.n_total + 1;
+  const size_t n = first_only ? 1 : v.n_total + (size_t)v.n_fs;
   std::vector<uint64_t> soa(4 * n);
   MCB_CUDA(cudaStreamSynchronize(m->stream));
   for (int w = 0; w < 4; ++w)
@@ -931,9 +963,9 @@ int mcb_set_rng_state(mcb_model *m, const uint64_t *state, size_t n_words) {
   if (!m || !state) return fail(MCB_ERR_ARG, "NULL argument");
   MCB_CUDA(cudaSetDevice(m->device));
   const View &v = m->v;
-  const size_t n = v.n_total + 1;
+  const size_t n = v.n_total + (size_t)v.n_fs;
   if (n_words != 4 * n)
-    return fail(MCB_ERR_ARG, "'rng_state' must hold 32 bytes for each of n_particles + 1 streams");
+    return fail(MCB_ERR_ARG, "'rng_state' must hold 32 bytes for each particle and filter stream");
   std::vector<uint64_t> soa(4 * n);
   for (size_t i = 0; i < n; ++i)
     for (int w = 0; w < 4; ++w) soa[w * n + i] = state[4 * i + w];
@@ -941,6 +973,84 @@ int mcb_set_rng_state(mcb_model *m, const uint64_t *state, size_t n_words) {
   for (int w = 0; w < 4; ++w)
     MCB_CUDA(cudaMemcpy(v.rng + w * v.ld_rng, soa.data() + w * n, n * sizeof(uint64_t),
                         cudaMemcpyHostToDevice));
+  return MCB_OK;
+}
+
+int mcb_copy_sets(mcb_model *dst, mcb_model *src, const unsigned char *take, int copy_state,
+                  int copy_rng) {
+  if (!dst || !src || !take) return fail(MCB_ERR_ARG, "NULL argument");
+  const View &a = dst->v, &b = src->v;
+  if (a.n_particles != b.n_particles || a.n_sets != b.n_sets || a.n_state != b.n_state ||
+      a.n_fs != b.n_fs || dst->device != src->device)
+    return fail(MCB_ERR_ARG, "copy_sets needs two handles of the same shape on one device");
+  if (copy_rng && a.n_fs == 1 && a.n_sets > 1)
+    return fail(MCB_ERR_STATE, "per-set RNG copies need per-set filter streams");
+  MCB_CUDA(cudaSetDevice(dst->device));
+  MCB_CUDA(cudaStreamSynchronize(src->stream));
+  unsigned char *d_take = nullptr;
+  MCB_CUDA(cudaMalloc(&d_take, a.n_sets));
+  cudaMemcpyAsync(d_take, take, a.n_sets, cudaMemcpyHostToDevice, dst->stream);
+  mcb::k_copy_sets<<<blocks_for(a.n_total, 256), 256, 0, dst->stream>>>(a, b, d_take, copy_state,
+                                                                        copy_rng);
+  ++dst->launches;
+  cudaError_t err = cudaStreamSynchronize(dst->stream);
+  cudaFree(d_take);
+  if (err != cudaSuccess) return fail(MCB_ERR_CUDA, std::string("copy_sets: ") + cudaGetErrorString(err));
+  return MCB_OK;
+}
+
+int mcb_rng_jump_n(uint64_t state[4], uint64_t n) {
+  if (!state) return fail(MCB_ERR_ARG, "state is NULL");
+  if (n >> mcb::kJumpLevels) return fail(MCB_ERR_ARG, "jump count too large");
+  {
+    std::lock_guard<std::mutex> lock(g_jump.mu);
+    if (!g_jump.host) {
+      g_jump.host = new mcb::JumpTable;
+      mcb::jump_table_build(*g_jump.host);
+    }
+  }
+  for (int l = 0; l < mcb::kJumpLevels; ++l) {
+    if (!((n >> l) & 1ULL)) continue;
+    uint64_t acc[4] = {0, 0, 0, 0};
+    for (int b = 0; b < 256; ++b)
+      if ((state[b >> 6] >> (b & 63)) & 1ULL)
+        for (int w = 0; w < 4; ++w) acc[w] ^= g_jump.host->col[l][b][w];
+    for (int w = 0; w < 4; ++w) state[w] = acc[w];
+  }
+  return MCB_OK;
+}
+
+int mcb_set_filter_stream(mcb_model *m, const uint64_t state[4]) {
+  if (!m || !state) return fail(MCB_ERR_ARG, "NULL argument");
+  if (m->v.n_fs != 1) return fail(MCB_ERR_STATE, "the model has one filter stream per set");
+  MCB_CUDA(cudaSetDevice(m->device));
+  MCB_CUDA(cudaStreamSynchronize(m->stream));
+  for (int w = 0; w < 4; ++w)
+    MCB_CUDA(cudaMemcpy(m->v.rng + w * m->v.ld_rng + m->v.n_total, state + w, sizeof(uint64_t),
+                        cudaMemcpyHostToDevice));
+  return MCB_OK;
+}
+
+int mcb_set_stream_sharing(mcb_model *m, size_t n_sets_global, size_t set_offset,
+                           const unsigned char *na_global) {
+  if (!m) return fail(MCB_ERR_ARG, "model is NULL");
+  View &v = m->v;
+  if (v.n_fs != 1) return fail(MCB_ERR_STATE, "the model has one filter stream per set");
+  if (m->n_data == 0) return fail(MCB_ERR_STATE, "set the data before the stream sharing");
+  if (set_offset + v.n_sets > n_sets_global)
+    return fail(MCB_ERR_ARG, "this handle's sets do not fit in the global set range");
+  if (!na_global) return fail(MCB_ERR_ARG, "na_global is NULL");
+  MCB_CUDA(cudaSetDevice(m->device));
+  MCB_CUDA(cudaStreamSynchronize(m->stream));
+  clear_graphs(m);
+  if (m->d_na_global) cudaFree(m->d_na_global);
+  m->d_na_global = nullptr;
+  MCB_CUDA(cudaMalloc(&m->d_na_global, m->n_data * n_sets_global));
+  MCB_CUDA(cudaMemcpy(m->d_na_global, na_global, m->n_data * n_sets_global,
+                      cudaMemcpyHostToDevice));
+  v.na_global = m->d_na_global;
+  v.n_sets_global = (int)n_sets_global;
+  v.set_offset = (int)set_offset;
   return MCB_OK;
 }
 
@@ -971,10 +1081,15 @@ int mcb_set_data(mcb_model *m, size_t n_data, const uint64_t *time_end, const do
   m->d_data = nullptr; m->d_u = nullptr; m->d_fs_after = nullptr; m->d_wmax = nullptr;
   MCB_CUDA(cudaMalloc(&m->d_data, packed.size() * sizeof(double)));
   MCB_CUDA(cudaMalloc(&m->d_u, n_data * v.n_sets * sizeof(double)));
-  MCB_CUDA(cudaMalloc(&m->d_fs_after, n_data * 4 * sizeof(uint64_t)));
+  MCB_CUDA(cudaMalloc(&m->d_fs_after, n_data * (size_t)v.n_fs * 4 * sizeof(uint64_t)));
   MCB_CUDA(cudaMalloc(&m->d_wmax, n_data * v.n_sets * sizeof(unsigned long long)));
   MCB_CUDA(cudaMemcpy(m->d_data, packed.data(), packed.size() * sizeof(double),
                       cudaMemcpyHostToDevice));
+  if (m->d_na_global) cudaFree(m->d_na_global);
+  m->d_na_global = nullptr;
+  v.na_global = nullptr;   // a new series: mcb_set_stream_sharing must be called again
+  v.n_sets_global = (int)v.n_sets;
+  v.set_offset = 0;
   v.data = m->d_data;
   v.data_sets = (int)sets;
   v.u_draws = m->d_u;

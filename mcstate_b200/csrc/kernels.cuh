@@ -66,6 +66,14 @@ struct View {
   const int *index;   // [n_index] rows returned by run()/saved in trajectories
   size_t n_particles, n_sets, n_total, ld, ld_rng;
   int n_state, n_index, n_min, data_sets, tiles_per_set, shift, deterministic, n_tab;
+  // filter streams (resampling uniforms).  n_fs == 1: one stream shared by every set
+  // (the dust pars_multi layout), drawn in set order; when the sets of one model are
+  // sharded over several handles, each handle replays the whole order
+  // (n_sets_global draws per row, its own sets at [set_offset, set_offset + n_sets))
+  // so the shared stream advances identically everywhere.  n_fs == n_sets: one stream
+  // per set (independent filters batched in one handle).  Streams n_total .. n_total+n_fs-1.
+  int n_fs, n_sets_global, set_offset;
+  const unsigned char *na_global;  // [n_data][n_sets_global] datum is NA, or nullptr
 };
 
 // ---- order-preserving map double -> u64 so max is one integer atomic --------
@@ -623,43 +631,58 @@ k_finish_state(View v, int last, int last_weighted, int *__restrict__ kappa_out)
 
 // ---- small kernels off the hot path ---------------------------------------
 
-// resampling uniforms for every pending (row, set) pair, drawn in order from
-// the filter stream (the last stream); the state after each row is kept so an
-// early stop can rewind to the draws that were really made.
+// resampling uniforms for every pending (row, set) pair, drawn in order from the
+// filter stream(s); the state after each row is kept so an early stop can rewind to
+// the draws that were really made.  Shared stream: one thread walks rows x global
+// sets.  Per-set streams: one thread per set.
 template <int SCR>
 __global__ void k_draw_uniforms(View v, int row_first, int row_last, double *u_draws,
                                 uint64_t *fs_after) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const size_t f = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= (size_t)v.n_fs) return;
   Xoshiro r;
-  const size_t f = v.n_total;
-  r.s0 = v.rng[0 * v.ld_rng + f]; r.s1 = v.rng[1 * v.ld_rng + f];
-  r.s2 = v.rng[2 * v.ld_rng + f]; r.s3 = v.rng[3 * v.ld_rng + f];
+  const size_t st = v.n_total + f;
+  r.s0 = v.rng[0 * v.ld_rng + st]; r.s1 = v.rng[1 * v.ld_rng + st];
+  r.s2 = v.rng[2 * v.ld_rng + st]; r.s3 = v.rng[3 * v.ld_rng + st];
+  const bool per_set = v.n_fs > 1;
+  const int n_glob = per_set ? 1 : v.n_sets_global;
   for (int row = row_first; row < row_last; ++row) {
-    for (size_t p = 0; p < v.n_sets; ++p)
-      if (row_first < 0 || !datum_is_na(v, row, p))
-        u_draws[(size_t)(row < 0 ? 0 : row) * v.n_sets + p] = xo_real<SCR>(r);
+    const size_t slot = (size_t)(row < 0 ? 0 : row) * v.n_sets;
+    for (int pg = 0; pg < n_glob; ++pg) {
+      const int p = per_set ? (int)f : pg - v.set_offset;   // local set index
+      const bool mine = p >= 0 && p < (int)v.n_sets;
+      bool na = false;
+      if (row_first >= 0)
+        na = (!per_set && v.na_global) ? v.na_global[(size_t)row * n_glob + pg] != 0
+                                       : (mine && datum_is_na(v, row, (size_t)p));
+      if (na) continue;
+      const double u = xo_real<SCR>(r);
+      if (mine) u_draws[slot + p] = u;
+    }
     if (row >= 0) {
-      fs_after[4 * row + 0] = r.s0; fs_after[4 * row + 1] = r.s1;
-      fs_after[4 * row + 2] = r.s2; fs_after[4 * row + 3] = r.s3;
+      uint64_t *o = fs_after + ((size_t)row * v.n_fs + f) * 4;
+      o[0] = r.s0; o[1] = r.s1; o[2] = r.s2; o[3] = r.s3;
     }
   }
   if (row_first < 0) {  // model$resample(): consume the draws immediately
-    v.rng[0 * v.ld_rng + f] = r.s0; v.rng[1 * v.ld_rng + f] = r.s1;
-    v.rng[2 * v.ld_rng + f] = r.s2; v.rng[3 * v.ld_rng + f] = r.s3;
+    v.rng[0 * v.ld_rng + st] = r.s0; v.rng[1 * v.ld_rng + st] = r.s1;
+    v.rng[2 * v.ld_rng + st] = r.s2; v.rng[3 * v.ld_rng + st] = r.s3;
   }
 }
 
-// end of a filter call: the filter stream advances past the draws of the rows
+// end of a filter call: the filter streams advance past the draws of the rows
 // that were resampled (a stopped row was not: R breaks before particle_resample)
 __global__ void k_filter_finish(View v, int row_first, int row_last, const uint64_t *fs_after) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const size_t f = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= (size_t)v.n_fs) return;
   const int done_last = v.flags[0] ? v.flags[1] - 1 : row_last - 1;
   if (done_last < row_first) return;
-  const size_t f = v.n_total;
-  v.rng[0 * v.ld_rng + f] = fs_after[4 * done_last + 0];
-  v.rng[1 * v.ld_rng + f] = fs_after[4 * done_last + 1];
-  v.rng[2 * v.ld_rng + f] = fs_after[4 * done_last + 2];
-  v.rng[3 * v.ld_rng + f] = fs_after[4 * done_last + 3];
+  const size_t st = v.n_total + f;
+  const uint64_t *o = fs_after + ((size_t)done_last * v.n_fs + f) * 4;
+  v.rng[0 * v.ld_rng + st] = o[0];
+  v.rng[1 * v.ld_rng + st] = o[1];
+  v.rng[2 * v.ld_rng + st] = o[2];
+  v.rng[3 * v.ld_rng + st] = o[3];
 }
 
 // Once per update_state(pars): the parameter-only constants and memo tables of
@@ -784,6 +807,56 @@ __global__ void k_derive_streams(uint64_t *rng, size_t ld_rng, size_t have, size
     s[0] = a0; s[1] = a1; s[2] = a2; s[3] = a3;
   }
   for (int w = 0; w < 4; ++w) rng[w * ld_rng + i] = s[w];
+}
+
+// smc2 replenishment (R/smc2.R:174-189: filter[accept] <- proposed$filter[accept]): take
+// the particle state and/or the RNG streams of the flagged sets from another handle of
+// the same shape.
+__global__ void k_copy_sets(View dst, View src, const unsigned char *__restrict__ take,
+                            int copy_state, int copy_rng) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < dst.n_total) {
+    const size_t set = i / dst.n_particles;
+    if (take[set]) {
+      if (copy_state)
+        for (int s = 0; s < dst.n_state; ++s) dst.y[(size_t)s * dst.ld + i] = src.y[(size_t)s * src.ld + i];
+      if (copy_rng)
+        for (int w = 0; w < 4; ++w) dst.rng[w * dst.ld_rng + i] = src.rng[w * src.ld_rng + i];
+    }
+  }
+  if (copy_rng && dst.n_fs > 1 && i < (size_t)dst.n_fs && take[i]) {  // the set's filter stream
+    for (int w = 0; w < 4; ++w)
+      dst.rng[w * dst.ld_rng + dst.n_total + i] = src.rng[w * src.ld_rng + src.n_total + i];
+  }
+}
+
+// Per-set seeding (independent filters batched in one handle): set p's particle
+// streams are J^j base_p, j < n_particles, and its filter stream J^n_particles base_p
+// -- what n_sets separate model objects seeded with base_p would hold.
+__global__ void k_derive_streams_per_set(uint64_t *rng, size_t ld_rng,
+                                         const uint64_t *__restrict__ bases, size_t n_particles,
+                                         size_t n_sets, const uint64_t *__restrict__ jump_cols) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t per = n_particles + 1;
+  if (t >= per * n_sets) return;
+  const size_t p = t / per, j = t - p * per;
+  uint64_t s[4];
+  for (int w = 0; w < 4; ++w) s[w] = bases[4 * p + w];
+  for (int l = 0; l < kJumpLevels; ++l) {
+    if (!((j >> l) & 1ULL)) continue;
+    const uint64_t *cols = jump_cols + (size_t)l * 256 * 4;
+    uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (int b = 0; b < 256; ++b) {
+      const uint64_t m = 0ULL - ((s[b >> 6] >> (b & 63)) & 1ULL);
+      a0 ^= m & __ldg(cols + b * 4 + 0);
+      a1 ^= m & __ldg(cols + b * 4 + 1);
+      a2 ^= m & __ldg(cols + b * 4 + 2);
+      a3 ^= m & __ldg(cols + b * 4 + 3);
+    }
+    s[0] = a0; s[1] = a1; s[2] = a2; s[3] = a3;
+  }
+  const size_t dst = j < n_particles ? p * n_particles + j : n_particles * n_sets + p;
+  for (int w = 0; w < 4; ++w) rng[w * ld_rng + dst] = s[w];
 }
 
 }  // namespace mcb

@@ -58,8 +58,12 @@ class dust_rng:
         self._s = _seed_words(seed)[:4].copy()
         self._alg = _ALGORITHMS[algorithm]
 
-    def jump(self):
-        check(_lib.lib().mcb_rng_jump(ptr(self._s, u64p)))
+    def jump(self, n=1):
+        """``$jump()``; ``n`` jumps at once lands on stream n of this seed."""
+        if n == 1:
+            check(_lib.lib().mcb_rng_jump(ptr(self._s, u64p)))
+        else:
+            check(_lib.lib().mcb_rng_jump_n(ptr(self._s, u64p), int(n)))
         return self
 
     def long_jump(self):
@@ -113,7 +117,7 @@ class dust_model:
     """One instantiated model: particle state, RNG streams and data in HBM."""
 
     def __init__(self, generator, pars, time, n_particles, n_threads=1, seed=None,
-                 pars_multi=False, deterministic=False, gpu_config=None):
+                 pars_multi=False, deterministic=False, gpu_config=None, seed_per_set=False):
         L = _lib.lib()
         self._gen = generator
         self._n_threads = int(n_threads)
@@ -136,9 +140,13 @@ class dust_model:
         words = _seed_words(seed)
         vec = generator._pars_vector(self._pars, pars_multi)
         h = C.c_void_p()
-        check(L.mcb_alloc(generator.model_id, ptr(vec, f64p), int(n_particles), n_pars, int(time),
-                          ptr(words, u64p), words.size // 4, generator.scrambler,
-                          int(deterministic), device_id, C.byref(h)))
+        # seed_per_set: one 32-byte seed per parameter set; each set then owns the streams a
+        # separate model object seeded with it would (independent filters in one handle)
+        self._n_fs = max(1, n_pars) if seed_per_set else 1
+        check(L.mcb_alloc_ex(generator.model_id, ptr(vec, f64p), int(n_particles), n_pars,
+                             int(time), ptr(words, u64p), words.size // 4,
+                             _lib.SEED_PER_SET if seed_per_set else _lib.SEED_SHARED,
+                             generator.scrambler, int(deterministic), device_id, C.byref(h)))
         self._h = h
         self._n_state = generator.n_state
         self._n_particles = int(n_particles)
@@ -307,20 +315,20 @@ class dust_model:
 
     def rng_state(self, first_only=False, last_only=False):
         """R/particle_filter.R:813; R/particle_filter_state.R:363,406,420: raw bytes."""
-        out = np.zeros((self._n_total + 1) * 4, dtype=np.uint64)
+        out = np.zeros((self._n_total + self._n_fs) * 4, dtype=np.uint64)
         check(_lib.lib().mcb_rng_state(self._h, 0, ptr(out, u64p)))
         if first_only:
             return out[:4].tobytes()
-        if last_only:
-            return out[-4:].tobytes()
+        if last_only:  # the filter stream(s)
+            return out[-4 * self._n_fs:].tobytes()
         return out.tobytes()
 
     def set_rng_state(self, rng_state):
         """R/particle_filter_state.R:369,420; R/particle_filter.R:877."""
         raw = np.frombuffer(bytes(rng_state), dtype=np.uint64).copy()
-        if raw.size != (self._n_total + 1) * 4:
+        if raw.size != (self._n_total + self._n_fs) * 4:
             raise ValueError("'rng_state' must be a raw vector of length %d (but was %d)"
-                             % ((self._n_total + 1) * 32, raw.size * 8))
+                             % ((self._n_total + self._n_fs) * 32, raw.size * 8))
         check(_lib.lib().mcb_set_rng_state(self._h, ptr(raw, u64p), raw.size))
 
     def set_data(self, data, shared=False):
@@ -342,6 +350,31 @@ class dust_model:
         check(_lib.lib().mcb_set_data(self._h, times.size, ptr(times, u64p), ptr(vals, f64p),
                                       int(bool(shared))))
         self._data_times = times
+
+    # ---- sharding one multi-parameter model over several handles (include/mcstate_b200.h)
+    def set_filter_stream(self, raw):
+        """Install the (shared) filter stream: 32 raw bytes."""
+        w = np.frombuffer(bytes(raw), dtype=np.uint64).copy()
+        if w.size != 4:
+            raise ValueError("the filter stream is 32 bytes")
+        check(_lib.lib().mcb_set_filter_stream(self._h, ptr(w, u64p)))
+
+    def set_stream_sharing(self, n_sets_global, set_offset, na_global):
+        """This handle holds sets [set_offset, set_offset + n_pars) of ``n_sets_global``;
+        ``na_global`` [n_data, n_sets_global] marks the data rows that are NA."""
+        na = np.ascontiguousarray(na_global, dtype=np.uint8)
+        if na.shape != (len(self._data_times), int(n_sets_global)):
+            raise ValueError("'na_global' must be [n_data, n_sets_global]")
+        check(_lib.lib().mcb_set_stream_sharing(self._h, int(n_sets_global), int(set_offset),
+                                                na.tobytes()))
+
+    def copy_sets_from(self, other, take, state=True, rng=True):
+        """Take the particle state and/or RNG streams of the flagged parameter sets from
+        ``other`` (same shape; smc2 replenishment, R/smc2.R:174-189)."""
+        t = np.ascontiguousarray(take, dtype=np.uint8)
+        if t.size != self._n_sets:
+            raise ValueError("'take' must have one flag per parameter set")
+        check(_lib.lib().mcb_copy_sets(self._h, other._h, t.tobytes(), int(state), int(rng)))
 
     def compare_data(self):
         """``$compare_data()``: log-weights for the datum at the current time, or None."""
@@ -491,11 +524,11 @@ class dust_generator:
 
     # -- instantiate
     def new(self, pars, time, n_particles, n_threads=1, seed=None, pars_multi=False,
-            deterministic=False, gpu_config=None, **ignored):
+            deterministic=False, gpu_config=None, seed_per_set=False, **ignored):
         """R/particle_filter_state.R:237-241."""
         return dust_model(self, pars, time, n_particles, n_threads=n_threads, seed=seed,
                           pars_multi=pars_multi, deterministic=deterministic,
-                          gpu_config=gpu_config)
+                          gpu_config=gpu_config, seed_per_set=seed_per_set)
 
     # -- helpers
     def _pars_vector(self, pars, multi):

@@ -121,6 +121,22 @@ class particle_filter_data:
         return new
 
 
+def subset_populations(data, populations):
+    """The nested data restricted to some of its populations (all time rows kept): what a
+    shard of a multi-population filter holds."""
+    if not data.is_nested:
+        raise ValueError("'data' is not nested")
+    populations = list(populations)
+    if any(p not in data.populations for p in populations):
+        raise ValueError("unknown population")
+    keep = np.isin(np.asarray(data.columns[data.population]), populations)
+    new = object.__new__(particle_filter_data)
+    new.__dict__.update(data.__dict__)
+    new.columns = {k: v[keep] for k, v in data.columns.items()}
+    new.populations = [p for p in data.populations if p in populations]
+    return new
+
+
 def _as_columns(data):
     if hasattr(data, "to_dict") and hasattr(data, "columns"):  # pandas.DataFrame
         return {c: np.asarray(data[c]) for c in data.columns}

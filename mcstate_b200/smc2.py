@@ -1,0 +1,290 @@
+"""SMC^2 driving the B200 filter (BASELINE config C5).
+
+The reference's ``smc2()`` keeps one ``particle_filter_state`` per parameter particle
+and advances them one data row at a time (R/smc2.R:58-114), re-running whole filters
+from t = 0 when it replenishes (``fork_smc2``, R/particle_filter_state.R:402-424).  It
+forbids all of that on its GPU back end (:403).  Here the parameter particles of a rank
+are ONE batched model handle -- ``pars_multi`` with per-set seeds, i.e. exactly the
+streams the reference's separate model objects would hold (R/smc2.R:68-71) -- so every
+data row is one incremental ``model$filter(time_end)`` call over all of them, and a
+replenishment is one more batched filter run plus a device-side per-set copy
+(``mcb_copy_sets``).
+
+Sharding (one rank per GPU): parameter particles [lo, hi) live on rank r; the per-row
+log-likelihoods are all-gathered (8 bytes x n_parameter_sets) and every rank then makes
+the same host-side decisions from the same host RNG.  The reference's resampling step
+permutes parameters and probabilities but NOT the filters (SURVEY.md Q1,
+R/smc2.R:120-149), so no particle state ever moves between GPUs; that quirk and the
+one of passing log-weights to ``particle_resample`` (:122) are reproduced as they are.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from .dust import dust_rng_distributed_state
+from .particle_filter import particle_resample, scale_log_weights
+from .particle_filter_data import particle_filter_data_split
+from .pmcmc import reflect_proposal, rmvnorm_generator
+from .sharding import block_range
+
+
+class smc2_parameter:
+    """``smc2_parameter(name, sample, prior, min, max, discrete, integer)``
+    (R/smc2_parameters.R): ``sample(n, rng)`` draws n values, ``prior(x)`` is the log density."""
+
+    def __init__(self, name, sample, prior, min=-math.inf, max=math.inf, discrete=False,
+                 integer=False):
+        self.name, self.sample, self.prior = name, sample, prior
+        self.min, self.max = float(min), float(max)
+        self.integer = bool(discrete or integer)
+
+
+class smc2_parameters:
+    """``smc2_parameters$new(parameters, transform)`` (R/smc2_parameters.R)."""
+
+    def __init__(self, parameters, transform=None):
+        if len(parameters) == 0:
+            raise ValueError("At least one parameter is required")
+        self._p = list(parameters)
+        self._names = [p.name for p in self._p]
+        self._min = np.array([p.min for p in self._p])
+        self._max = np.array([p.max for p in self._p])
+        self._integer = np.array([p.integer for p in self._p])
+        self._transform = transform if transform is not None else (lambda d: d)
+
+    def names(self):
+        return list(self._names)
+
+    def sample(self, n, rng):
+        return np.stack([np.asarray(p.sample(n, rng), dtype=float) for p in self._p], axis=1)
+
+    def prior(self, theta):
+        theta = np.atleast_2d(theta)
+        return np.array([sum(p.prior(x) for p, x in zip(self._p, row)) for row in theta])
+
+    def propose(self, theta, vcv, rng):
+        # R/smc2_parameters.R: one multivariate-normal step per row, reflected at the bounds
+        draw = rmvnorm_generator(vcv)
+        out = np.stack([draw(row, rng) for row in theta])
+        out[:, self._integer] = np.round(out[:, self._integer])
+        return np.stack([reflect_proposal(row, self._min, self._max) for row in out])
+
+    def model(self, theta):
+        return [self._transform(dict(zip(self._names, (float(x) for x in row))))
+                for row in np.atleast_2d(theta)]
+
+
+class smc2_control:
+    """R/smc2_control.R:30-40."""
+
+    def __init__(self, n_parameter_sets, degeneracy_threshold=0.5, covariance_scaling=0.5,
+                 progress=False, save_trajectories=False, seed=1):
+        if n_parameter_sets < 2:
+            raise ValueError("'n_parameter_sets' must be at least 2")
+        if save_trajectories:
+            raise ValueError("save_trajectories is not supported by the batched smc2 engine")
+        self.n_parameter_sets = int(n_parameter_sets)
+        self.degeneracy_threshold = float(degeneracy_threshold)
+        self.covariance_scaling = float(covariance_scaling)
+        self.progress = bool(progress)
+        self.seed = seed  # host RNG (R: the session's RNG state)
+
+
+def cov_wt(x, w):
+    """``stats::cov.wt(x, wt = w)$cov`` (R/smc2.R:116-118): weights normalised to sum 1,
+    unbiased correction 1 / (1 - sum w^2)."""
+    w = np.asarray(w, dtype=float)
+    w = w / w.sum()
+    xc = x - (w[:, None] * x).sum(axis=0)
+    return (xc * w[:, None]).T @ xc / (1.0 - np.sum(w ** 2))
+
+
+class smc2_engine:
+    """R/smc2.R:38-220 on batched, optionally sharded, filters."""
+
+    def __init__(self, pars, filter, control, group=None):
+        inputs = filter.inputs()
+        if inputs["compare"] is not None:
+            raise ValueError("the batched smc2 engine needs the compiled compare (compare = NULL)")
+        if filter.has_multiple_parameters:
+            raise ValueError("smc2 takes a single-parameter filter")
+        self._pars, self._control = pars, control
+        self._rng = np.random.default_rng(control.seed)
+        self._group = group
+        self.rank, self.world = 0, 1
+        self._dist = None
+        try:
+            import torch.distributed as dist
+
+            if dist.is_available() and dist.is_initialized():
+                self._dist = dist
+                self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        except ImportError:
+            pass
+        n = control.n_parameter_sets
+        self._lo, self._hi = block_range(n, self.rank, self.world)
+        self._counts = [hi - lo for lo, hi in (block_range(n, r, self.world)
+                                               for r in range(self.world))]
+        if min(self._counts) < 1:
+            raise ValueError("more ranks than parameter sets")
+
+        # R/smc2.R:63-66: sample, prior; every rank draws the same values
+        theta = pars.sample(n, self._rng)
+        self.pars = theta
+        self.log_prior = pars.prior(theta)
+        self.log_likelihood = np.zeros(n)
+        self.log_posterior = self.log_prior + self.log_likelihood
+        self.log_weights = np.zeros(n)
+        self.weights = np.ones(n)
+
+        # R/smc2.R:68-78: filter i runs on node i of the distributed seed
+        algorithm = getattr(inputs["model"], "algorithm", "xoshiro256plus")
+        seeds = dust_rng_distributed_state(inputs["seed"], 1, n, algorithm)
+        self._seed_local = b"".join(seeds[self._lo:self._hi])
+        self._inputs = inputs
+        self._data = inputs["data"]
+        self._times = self._data.times
+        self._data_split = particle_filter_data_split(self._data, True)
+        self.n_particles = inputs["n_particles"]
+        self.n_steps = self._times.shape[0]
+        # the parameters each local filter really runs with: resample() permutes self.pars
+        # but not the filters (Q1), so the two drift apart until a proposal is accepted
+        self._model_theta = theta[self._lo:self._hi].copy()
+        self._model = self._new_model(pars.model(self._model_theta))
+        self._filter_facade = filter
+
+        self.step_current = 0
+        self.acceptance_rate = np.full(self.n_steps, np.nan)
+        self.ess = np.full(self.n_steps, np.nan)
+        self.n_filter_rows = 0  # model rows x parameter sets run on this rank
+
+    # ---- model handles ------------------------------------------------------------
+    def _new_model(self, pars_model, rng_state=None):
+        i = self._inputs
+        m = i["model"].new(pars=pars_model, time=int(self._times[0, 0]),
+                           n_particles=self.n_particles, n_threads=i["n_threads"],
+                           seed=self._seed_local, gpu_config=i["gpu_config"], pars_multi=True,
+                           seed_per_set=True)
+        m.set_data(self._data_split, True)  # one data stream shared by every parameter set
+        if i["initial"] is not None:
+            raise ValueError("'initial' is not supported by the batched smc2 engine")
+        if rng_state is not None:
+            m.set_rng_state(rng_state)
+        return m
+
+    def _gather(self, local):
+        if self._dist is None or self.world == 1:
+            return np.asarray(local, dtype=float)
+        from .sharding import gather_log_likelihood
+
+        device = None
+        if self._dist.get_backend(self._group) == "nccl":
+            import torch
+
+            device = torch.device("cuda", torch.cuda.current_device())
+        return gather_log_likelihood(local, self._counts, self._group, device)
+
+    # ---- R/smc2.R:89-108 ------------------------------------------------------------
+    def step(self):
+        t = self.step_current + 1
+        time_end = int(self._times[t - 1, 1])
+        step_ll = self._gather(self._model.filter(time_end)["log_likelihood"])
+        self.n_filter_rows += self._hi - self._lo
+        self.log_likelihood = self.log_likelihood + step_ll
+        self.log_posterior = self.log_posterior + step_ll
+        self.log_weights = self.log_weights + step_ll
+        self.weights = scale_log_weights(self.log_weights)["weights"]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            ess = self.weights.sum() ** 2 / np.sum(self.weights ** 2)
+        self.step_current = t
+        self.ess[t - 1] = ess
+        if ess < self._control.degeneracy_threshold * self._control.n_parameter_sets:
+            kernel = cov_wt(self.pars, self.weights) * self._control.covariance_scaling
+            self.resample()
+            self.update(self.propose(kernel))
+
+    def run(self):
+        for _ in range(self.step_current, self.n_steps):
+            self.step()
+
+    # ---- R/smc2.R:120-149 (Q1: log-weights in, filters stay where they are) -----------
+    def resample(self):
+        kappa = particle_resample(self.log_weights, self._rng) - 1
+        self.pars = self.pars[kappa]
+        self.log_prior = self.log_prior[kappa]
+        self.log_likelihood = self.log_likelihood[kappa]
+        self.log_posterior = self.log_posterior[kappa]
+        self.log_weights = self.log_weights[kappa]
+
+    # ---- R/smc2.R:151-172 + fork_smc2 ---------------------------------------------------
+    def propose(self, kernel):
+        pars = self._pars.propose(self.pars, kernel, self._rng)
+        log_prior = self._pars.prior(pars)
+        finite = np.isfinite(log_prior)
+        lo, hi = self._lo, self._hi
+        # sets with an impossible proposal are not forked (:164-169); the batched child
+        # still needs valid parameters in those slots, so they keep the current ones
+        run_pars = np.where(finite[lo:hi, None], pars[lo:hi], self._model_theta)
+        child = self._new_model(self._pars.model(run_pars), self._model.rng_state())
+        time_end = int(self._times[self.step_current - 1, 1])
+        ll_child = child.filter(time_end)["log_likelihood"]
+        self.n_filter_rows += (hi - lo) * self.step_current
+        # the parent's generator takes the child's, for the sets that were forked (:420)
+        self._model.copy_sets_from(child, finite[lo:hi], state=False, rng=True)
+        ll = self._gather(np.where(finite[lo:hi], ll_child, -np.inf))
+        return {"pars": pars, "log_prior": log_prior, "log_likelihood": ll,
+                "log_posterior": log_prior + ll, "model": child, "finite": finite}
+
+    # ---- R/smc2.R:174-189 -----------------------------------------------------------
+    def update(self, proposed):
+        with np.errstate(over="ignore", invalid="ignore"):
+            pr = np.exp(proposed["log_posterior"] - self.log_posterior)
+        accept = self._rng.random(pr.size) < pr
+        if accept.any():
+            self.pars[accept] = proposed["pars"][accept]
+            self.log_prior[accept] = proposed["log_prior"][accept]
+            self.log_likelihood[accept] = proposed["log_likelihood"][accept]
+            self.log_posterior[accept] = proposed["log_posterior"][accept]
+            lo, hi = self._lo, self._hi
+            take = accept[lo:hi]
+            if take.any():
+                # filter[accept] <- proposed$filter[accept]: parameters and particle state
+                self._model_theta[take] = proposed["pars"][lo:hi][take]
+                self._model.update_state(pars=self._pars.model(self._model_theta),
+                                         set_initial_state=False)
+                self._model.copy_sets_from(proposed["model"], take, state=True, rng=False)
+            self.log_weights[:] = 0.0
+        self.acceptance_rate[self.step_current - 1] = accept.mean()
+
+    # ---- R/smc2.R:191-220 -----------------------------------------------------------
+    def results(self):
+        weight = scale_log_weights(self.log_posterior)["weights"]
+        acc = self.acceptance_rate
+        effort = sum(1 if np.isnan(a) else i + 2 for i, a in enumerate(acc)) / self.n_steps \
+            * self.pars.shape[0]
+        return {
+            "pars": self.pars.copy(), "pars_names": self._pars.names(),
+            "probabilities": np.stack([self.log_prior, self.log_likelihood, self.log_posterior,
+                                       weight / weight.sum()], axis=1),
+            "statistics": {"ess": self.ess.copy(), "acceptance_rate": acc.copy(),
+                           "n_particles": self.n_particles,
+                           "n_parameter_sets": self.pars.shape[0], "n_steps": self.n_steps,
+                           "effort": effort},
+        }
+
+
+def smc2(pars, filter, control, group=None):
+    """``smc2(pars, filter, control)`` (R/smc2.R:29-36)."""
+    obj = smc2_engine(pars, filter, control, group)
+    obj.run()
+    return obj.results()
+
+
+def smc2_predict(result, n=None, rng=None):
+    """``predict.smc2_result`` (R/smc2.R:236-240)."""
+    rng = np.random.default_rng() if rng is None else rng
+    w = result["probabilities"][:, 3]
+    i = rng.choice(w.size, size=w.size if n is None else n, replace=True, p=w)
+    return result["pars"][i]

@@ -567,6 +567,11 @@ struct orc_model {
   uint64_t *data_time;
   double *data;         /* [n_data][n_data_sets][2] = {value, lgamma(value+1)} */
   int data_shared;
+  /* one multi-parameter model sharded over several handles: this one holds sets
+   * [set_offset, set_offset + n_sets) of n_sets_global and replays the whole draw order
+   * of the shared filter stream (include/mcstate_b200.h: mcb_set_stream_sharing) */
+  size_t n_sets_global, set_offset;
+  unsigned char *na_global; /* [n_data][n_sets_global] or NULL */
 };
 
 orc_model *orc_alloc(int model, const double *pars, size_t n_particles, size_t n_pars,
@@ -584,6 +589,9 @@ orc_model *orc_alloc(int model, const double *pars, size_t n_particles, size_t n
   m->n_pars = n_pars;
   m->n_sets = n_pars == 0 ? 1 : n_pars;
   m->n_total = n_particles * m->n_sets;
+  m->n_sets_global = m->n_sets;
+  m->set_offset = 0;
+  m->na_global = NULL;
   m->time = time;
   m->y = (double *)malloc(m->n_total * m->n_state * sizeof(double));
   m->y_next = (double *)malloc(m->n_total * m->n_state * sizeof(double));
@@ -597,7 +605,7 @@ orc_model *orc_alloc(int model, const double *pars, size_t n_particles, size_t n
 void orc_free(orc_model *m) {
   if (!m) return;
   free(m->y); free(m->y_next); free(m->rng); free(m->pars);
-  free(m->data_time); free(m->data);
+  free(m->data_time); free(m->data); free(m->na_global);
   free(m);
 }
 
@@ -682,7 +690,7 @@ void orc_set_rng_state(orc_model *m, const uint64_t *in) {
 
 void orc_set_data(orc_model *m, size_t n_data, const uint64_t *time_end,
                   const double *values, int shared) {
-  free(m->data_time); free(m->data);
+  free(m->data_time); free(m->data); free(m->na_global);
   const size_t sets = shared ? 1 : m->n_sets;
   m->n_data = n_data;
   m->data_shared = shared;
@@ -722,11 +730,26 @@ int orc_compare_data(orc_model *m, double *logw) {
   return 0;
 }
 
+void orc_set_filter_stream(orc_model *m, const uint64_t state[4]) {
+  memcpy(m->rng + 4 * m->n_total, state, 4 * sizeof(uint64_t));
+}
+
+void orc_set_stream_sharing(orc_model *m, size_t n_sets_global, size_t set_offset,
+                            const unsigned char *na_global) {
+  free(m->na_global);
+  m->na_global = (unsigned char *)malloc(m->n_data * n_sets_global);
+  memcpy(m->na_global, na_global, m->n_data * n_sets_global);
+  m->n_sets_global = n_sets_global;
+  m->set_offset = set_offset;
+}
+
 /* one uniform per parameter set, in set order, from the LAST stream (A.4 step 6) */
 void orc_resample(orc_model *m, const double *weights, int *kappa) {
   uint64_t *fs = m->rng + 4 * m->n_total;
-  for (size_t p = 0; p < m->n_sets; ++p) {
+  for (size_t pg = 0; pg < m->n_sets_global; ++pg) {
     const double u = orc_random_real(fs, m->scrambler);
+    if (pg < m->set_offset || pg >= m->set_offset + m->n_sets) continue;
+    const size_t p = pg - m->set_offset;
     int *kp = kappa + p * m->n_particles;
     orc_resample_weight(weights + p * m->n_particles, m->n_particles, u,
                         m->resample_mode, kp);
@@ -795,13 +818,19 @@ size_t orc_filter(orc_model *m, uint64_t time_end, double *log_likelihood,
     }
     /* resample set by set; a set whose datum is NA keeps its particles */
     uint64_t *fs = m->rng + 4 * nt;
-    for (size_t p = 0; p < m->n_sets; ++p) {
-      int *kp = kappa + p * np;
-      if (isnan(datum_for(m, row, p)[0])) {
-        for (size_t i = 0; i < np; ++i) kp[i] = (int)(p * np + i);
+    for (size_t pg = 0; pg < m->n_sets_global; ++pg) {
+      const int mine = pg >= m->set_offset && pg < m->set_offset + m->n_sets;
+      const size_t p = pg - m->set_offset;
+      const int na = m->na_global ? m->na_global[row * m->n_sets_global + pg]
+                                  : (mine && isnan(datum_for(m, row, p)[0]));
+      if (na) {
+        if (mine)
+          for (size_t i = 0; i < np; ++i) kappa[p * np + i] = (int)(p * np + i);
         continue;
       }
       const double u = orc_random_real(fs, m->scrambler);
+      if (!mine) continue;
+      int *kp = kappa + p * np;
       orc_resample_weight(w + p * np, np, u, m->resample_mode, kp);
       for (size_t i = 0; i < np; ++i) kp[i] += (int)(p * np);
     }

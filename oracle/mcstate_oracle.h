@@ -110,6 +110,10 @@ void orc_set_data(orc_model *m, size_t n_data, const uint64_t *time_end,
 /* log weights of the datum whose time_end == current time; returns 0 if none */
 int orc_compare_data(orc_model *m, double *logw);
 /* weights in (length n_total), kappa out (0-based global); consumes the filter stream */
+/* sharding twins of mcb_set_filter_stream / mcb_set_stream_sharing */
+void orc_set_filter_stream(orc_model *m, const uint64_t state[4]);
+void orc_set_stream_sharing(orc_model *m, size_t n_sets_global, size_t set_offset,
+                            const unsigned char *na_global);
 void orc_resample(orc_model *m, const double *weights, int *kappa);
 /*
  * The compiled filter (A.4).  trajectories: [T+1][n_total][n_index] or NULL,

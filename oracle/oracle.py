@@ -57,8 +57,7 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_LIB_PATH):
-        build()
+    build()  # no-op unless the C source is newer than the library
     if not _cpu_has_fma():
         raise RuntimeError("oracle is built with -mfma but this CPU lacks FMA")
     L = C.CDLL(_LIB_PATH)
@@ -103,6 +102,8 @@ def lib():
         "orc_set_data": (None, [C.c_void_p, C.c_size_t, _u64p, _f64p, C.c_int]),
         "orc_compare_data": (C.c_int, [C.c_void_p, _f64p]),
         "orc_resample": (None, [C.c_void_p, _f64p, _i32p]),
+        "orc_set_filter_stream": (None, [C.c_void_p, _u64p]),
+        "orc_set_stream_sharing": (None, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_char_p]),
         "orc_filter": (C.c_size_t, [C.c_void_p, C.c_uint64, _f64p, _szp, C.c_size_t, _f64p,
                                     _u64p, C.c_size_t, _f64p, _f64p, C.c_size_t]),
         "orc_model_update": (None, [C.c_int, C.c_uint64, _f64p, _u64p, C.c_int, C.c_int, _f64p,
@@ -262,6 +263,14 @@ class OracleModel:
         lib().orc_set_data(self._h, t.size, _p(t, _u64p), _p(v, _f64p), int(shared))
         self._n_data = t.size
         self._data_time = t.copy()
+
+    def set_filter_stream(self, state):
+        s = np.ascontiguousarray(state, dtype=np.uint64)
+        lib().orc_set_filter_stream(self._h, _p(s, _u64p))
+
+    def set_stream_sharing(self, n_sets_global, set_offset, na_global):
+        na = np.ascontiguousarray(na_global, dtype=np.uint8)
+        lib().orc_set_stream_sharing(self._h, int(n_sets_global), int(set_offset), na.tobytes())
 
     def compare_data(self):
         w = np.zeros(self.n_total)

@@ -109,6 +109,12 @@ class OracleDustModel:
     def set_rng_state(self, raw):
         self._o.set_rng_state(np.frombuffer(bytes(raw), dtype=np.uint64).copy())
 
+    def set_filter_stream(self, raw):
+        self._o.set_filter_stream(np.frombuffer(bytes(raw), dtype=np.uint64).copy())
+
+    def set_stream_sharing(self, n_sets_global, set_offset, na_global):
+        self._o.set_stream_sharing(n_sets_global, set_offset, na_global)
+
     def set_data(self, data, shared=False):
         n_sets = 1 if shared or not self._multi else self._n_sets
         t = np.array([d[0] for d in data], dtype=np.uint64)
@@ -133,6 +139,64 @@ class OracleDustModel:
         return {"log_likelihood": r["log_likelihood"], "trajectories": traj, "snapshots": snaps}
 
 
+class OraclePerSetModel:
+    """``pars_multi`` with per-set seeds (MCB_SEED_PER_SET) = independent filters: here,
+    literally one single-set oracle model per parameter set.  Covers what smc2 uses."""
+
+    def __init__(self, gen, pars, time, n_particles, n_threads, seed, deterministic):
+        raw = bytes(seed)
+        assert len(raw) == 32 * len(pars)
+        self._gen, self._np, self._n_sets = gen, int(n_particles), len(pars)
+        self._m = [OracleDustModel(gen, p, time, n_particles, n_threads, raw[32 * k:32 * k + 32],
+                                   False, deterministic) for k, p in enumerate(pars)]
+
+    def n_particles(self): return self._np
+    def n_pars(self): return self._n_sets
+    def shape(self): return (self._np, self._n_sets)
+    def time(self): return self._m[0].time()
+
+    def set_data(self, data, shared=False):
+        assert shared
+        for m in self._m:
+            m.set_data(data, False)
+
+    def filter(self, time_end=None, **kw):
+        return {"log_likelihood": np.array([m.filter(time_end)["log_likelihood"][0]
+                                            for m in self._m]),
+                "trajectories": None, "snapshots": None}
+
+    def state(self, index=None):
+        return np.stack([m.state(index) for m in self._m], axis=-1)
+
+    def update_state(self, pars=None, state=None, time=None, set_initial_state=None):
+        assert state is None
+        for k, m in enumerate(self._m):
+            m.update_state(pars=None if pars is None else pars[k], time=time,
+                           set_initial_state=set_initial_state)
+
+    def rng_state(self, first_only=False, last_only=False):
+        # the engine's order: every particle stream, then the filter streams
+        parts = [np.frombuffer(m.rng_state(), dtype=np.uint64).reshape(-1, 4) for m in self._m]
+        out = np.concatenate([p[:-1] for p in parts] + [p[-1:] for p in parts])
+        return out.tobytes()
+
+    def set_rng_state(self, raw):
+        a = np.frombuffer(bytes(raw), dtype=np.uint64).reshape(-1, 4)
+        nt = self._np * self._n_sets
+        for k, m in enumerate(self._m):
+            m.set_rng_state(np.concatenate([a[k * self._np:(k + 1) * self._np],
+                                            a[nt + k:nt + k + 1]]).tobytes())
+
+    def copy_sets_from(self, other, take, state=True, rng=True):
+        for k, t in enumerate(take):
+            if not t:
+                continue
+            if state:
+                self._m[k].update_state(state=other._m[k].state(), set_initial_state=False)
+            if rng:
+                self._m[k].set_rng_state(other._m[k].rng_state())
+
+
 class OracleGenerator:
     name = "dust_generator"
 
@@ -149,7 +213,10 @@ class OracleGenerator:
     def time_type(self): return "discrete"
 
     def new(self, pars, time, n_particles, n_threads=1, seed=None, pars_multi=False,
-            deterministic=False, gpu_config=None, **kw):
+            deterministic=False, gpu_config=None, seed_per_set=False, **kw):
+        if seed_per_set:
+            assert pars_multi
+            return OraclePerSetModel(self, pars, time, n_particles, n_threads, seed, deterministic)
         return OracleDustModel(self, pars, time, n_particles, n_threads, seed, pars_multi,
                                deterministic)
 
