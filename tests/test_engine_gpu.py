@@ -400,3 +400,61 @@ def test_full_size_filter_2_20(dust, orc, sir_data):
     m2.update_state(pars={}, time=0)
     again = m2.filter()["log_likelihood"]
     assert again[0] != got[0] and abs(again[0] - got[0]) < 0.5
+
+
+# ---- the lean (integer-state, table-driven) path of K1 against the general one -------------
+# Every case is bit-exact against the oracle, which only knows the general algorithm.
+@pytest.mark.parametrize("pars,label", [
+    ({"S0": 1e6, "I0": 5000.0, "beta": 0.5}, "population beyond the memo tables"),
+    ({"S0": 70000.0, "I0": 30.0}, "n_tot just above 65536 entries"),
+    ({"beta": 1.5, "gamma": 0.4}, "S q >= 10 mid-interval: lean steps then BTRS"),
+    ({"beta": 0.0}, "probability exactly zero: no draw, no uniform"),
+    ({"gamma": 0.0}, "recovery probability zero"),
+    ({"freq": 1.0, "gamma": 0.6931471805599453}, "p_IR = 1/2: r = 1, stalled walks"),
+    ({"freq": 1.0, "gamma": 50.0, "beta": 30.0}, "probabilities above one half (flipped)"),
+    ({"freq": 3.0}, "freq 3: incidence resets off the data grid"),
+    ({"S0": 3.0, "I0": 1.0}, "tiny population"),
+    ({"S0": 0.0, "I0": 40.0}, "no susceptibles"),
+])
+def test_lean_path_special_cases(dust, orc, pars, label):
+    n = 3000
+    g = dust.dust_example("sir")
+    m = g.new(pars, 0, n, seed=9)
+    o = orc.OracleModel(pars=g._pars_vector(pars, False), n_particles=n, seed=9, n_threads=8)
+    for t_end in (3, 4, 50, 51, 130):   # 46 and 79 steps in one launch: beyond one 32-bit mask
+        assert np.array_equal(m.run(t_end), o.run(t_end)), (label, t_end)
+        assert np.array_equal(_rng_words(m), o.rng_state()), (label, t_end)
+
+
+def test_lean_path_leaves_non_integer_states_to_the_general_code(dust, orc):
+    n = 500
+    g = dust.dust_example("sir")
+    m = g.new({}, 0, n, seed=4)
+    o = orc.OracleModel(n_particles=n, seed=4, n_threads=4)
+    st = np.tile(np.array([[999.5, 10.0, 0.5, 0.0, 0.0]]).T, (1, n))
+    st[:, ::3] = np.array([[1000.0, 10.0, 0.0, 0.0, 0.0]]).T     # a third stays integral
+    st[:, 1::7] = np.array([[900.0, 10.0, 0.0, 0.0, 0.0]]).T     # N differs from the tables'
+    st[0, 5] = -0.0                                              # the sign of a zero survives
+    m.update_state(state=st)
+    o.update_state(state=st, set_initial_state=False)
+    for t_end in (1, 8, 60):
+        assert np.array_equal(m.run(t_end), o.run(t_end))
+        assert np.array_equal(_rng_words(m), o.rng_state())
+    assert np.array_equal(np.signbit(m.state()), np.signbit(o.state()))
+
+
+@pytest.mark.parametrize("alg,scr", [("xoshiro256plus", 0), ("xoshiro256starstar", 1)])
+def test_sirs_filter_bit_exact(dust, orc, sir_data, alg, scr):
+    """The second model family (three draws per step, waning immunity) through the filter."""
+    n = 2048
+    t, x = _data(sir_data, 60)
+    pars = {"alpha": 0.05, "beta": 0.3, "gamma": 0.1, "I0": 15}
+    g = dust.dust_example("sirs", alg)
+    m = g.new(pars, 0, n, seed=21)
+    _set_data(m, t, x)
+    o = orc.OracleModel(pars=g._pars_vector(pars, False), n_particles=n, seed=21, model=1,
+                        scrambler=scr, n_threads=8)
+    o.set_data(t, x)
+    assert np.array_equal(m.filter()["log_likelihood"], o.filter()["log_likelihood"])
+    assert np.array_equal(m.state(), o.state())
+    assert np.array_equal(_rng_words(m), o.rng_state())
