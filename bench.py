@@ -51,6 +51,27 @@ def load_data():
     return d[:, 1].astype(np.uint64) * RATE, d[:, 0]
 
 
+def ncu_traffic_bytes(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the
+    committed summary of the last `ncu --set full` capture (profiles/); None if absent."""
+    import csv
+    import glob
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_full_summary_r*.csv")))
+    if not files:
+        return None, None
+    try:
+        rows = list(csv.reader(open(files[-1])))
+        hdr, units = rows[0], rows[1]
+        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        scale = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}
+        vals = [float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
+                for r in rows[2:] if kernel in r[0]]
+        return (sum(vals) / len(vals) if vals else None), os.path.basename(files[-1])
+    except Exception:
+        return None, None
+
+
 def measured_peak_gbs():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -283,8 +304,10 @@ def run_engine(args):
         roofline = None
         if dom:
             a = kernels[dom]["achieved_gbs"]
+            traffic, traffic_src = ncu_traffic_bytes(dom)
             roofline = {"kernel": dom, "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s",
-                        "frac": a / peak, "traffic": None, "peak_source": peak_kind,
+                        "frac": a / peak, "traffic": traffic, "traffic_source": traffic_src,
+                        "peak_source": peak_kind,
                         "algorithmic_bytes_per_launch": per_launch_bytes[names.index(dom)],
                         "whole_interval_frac": (BYTES_INTERVAL * N_PARTICLES * 100 * args.steps /
                                                 (ms_total * 1e-3) / 1e9) / peak,
