@@ -44,11 +44,18 @@ def example_pars():
                              pmcmc_parameter("gamma", 0.1, min=0, max=1, prior=flat)], kernel)
 
 
+def _device():
+    """The GPU this process should use: its local rank under torchrun, else 0."""
+    import torch
+
+    return int(os.environ.get("LOCAL_RANK", "0")) % max(1, torch.cuda.device_count())
+
+
 def example_filter(kind, sir_data, n_particles=64, seed=1):
     data = particle_filter_data({"day": sir_data["day"], "incidence": sir_data["incidence"]},
                                 "day", 4, 0)
     index = lambda info: {"run": [5], "state": [1, 2, 3]}  # noqa: E731
-    gpu = 0 if kind == "gpu" else None
+    gpu = _device() if kind == "gpu" else None
     return particle_filter(data, _generator(kind), n_particles, None, index=index, seed=seed,
                            gpu_config=gpu)
 
@@ -183,7 +190,11 @@ _WORKER = textwrap.dedent("""
     from test_pmcmc import example_filter, example_pars
     from mcstate_b200.pmcmc import pmcmc, pmcmc_control
     kind, n_chains = sys.argv[1], int(sys.argv[2])
-    dist.init_process_group({backend!r})
+    backend = os.environ.get("MCB_TEST_BACKEND", {backend!r}) if kind == "gpu" else {backend!r}
+    if backend == "nccl":
+        import torch
+        torch.cuda.set_device(int(os.environ["LOCAL_RANK"]) % torch.cuda.device_count())
+    dist.init_process_group(backend)
     rank, world = dist.get_rank(), dist.get_world_size()
     d = np.loadtxt(os.path.join({root!r}, "tests", "golden", "sir_incidence.csv"), delimiter=",",
                    skiprows=1)
@@ -221,5 +232,17 @@ def test_sharded_chains_equal_serial_gloo(tmp_path, sir_data):
                    control=pmcmc_control(10, n_chains=3, use_parallel_seed=True,
                                          save_trajectories=True))
     sharded = _run_sharded(tmp_path, "oracle", 3, 2, "gloo")
+    for key in ("pars", "probabilities", "chain", "iteration", "state", "trajectories"):
+        assert np.array_equal(serial[key], sharded[key]), key
+
+
+@pytest.mark.gpu
+def test_sharded_chains_equal_serial_b200(tmp_path, sir_data):
+    """The same on the B200 engine: two ranks, one chain at a time per GPU (both on device 0
+    when the box has one GPU; MCB_TEST_BACKEND=nccl uses one GPU per rank and NCCL)."""
+    serial = pmcmc(example_pars(), example_filter("gpu", sir_data),
+                   control=pmcmc_control(10, n_chains=3, use_parallel_seed=True,
+                                         save_trajectories=True))
+    sharded = _run_sharded(tmp_path, "gpu", 3, 2, "gloo")
     for key in ("pars", "probabilities", "chain", "iteration", "state", "trajectories"):
         assert np.array_equal(serial[key], sharded[key]), key

@@ -69,9 +69,15 @@ _WORKER = textwrap.dedent("""
     from test_sharding import nested_data, pars_for, make_generator
     from mcstate_b200.sharding import nested_filter_sharded
     kind, n_pop, n_particles = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
-    dist.init_process_group("gloo")
+    backend = os.environ.get("MCB_TEST_BACKEND", "gloo") if kind == "gpu" else "gloo"
+    dev = None
+    if kind == "gpu":
+        import torch
+        dev = int(os.environ["LOCAL_RANK"]) % torch.cuda.device_count()
+        torch.cuda.set_device(dev)
+    dist.init_process_group(backend)
     f = nested_filter_sharded(nested_data(n_pop), make_generator(kind), n_particles, seed=7,
-                              gpu_config=0 if kind == "gpu" else None)
+                              gpu_config=dev)
     p = pars_for(n_pop)
     out = [f.run(p), f.run(p), f.run(list(reversed(p)))]
     if dist.get_rank() == 0:

@@ -38,12 +38,18 @@ def load_sir():
     return {"day": d[:, 1].astype(int), "incidence": d[:, 0]}
 
 
+def _device():
+    import torch
+
+    return int(os.environ.get("LOCAL_RANK", "0")) % max(1, torch.cuda.device_count())
+
+
 def example(kind, n_particles=42, n_days=None):
     sir = load_sir()
     data = particle_filter_data({"day": sir["day"][:n_days], "incidence": sir["incidence"][:n_days]},
                                 "day", 4, 0)
     f = particle_filter(data, make_generator(kind), n_particles, None, seed=1,
-                        gpu_config=0 if kind == "gpu" else None)
+                        gpu_config=_device() if kind == "gpu" else None)
     unif = lambda n, rng: rng.uniform(0, 1, n)  # noqa: E731
     dunif = lambda x: 0.0 if 0 <= x <= 1 else -math.inf  # noqa: E731
     p = smc2_parameters([smc2_parameter("beta", unif, dunif, min=0, max=1),
@@ -138,7 +144,11 @@ _WORKER = textwrap.dedent("""
     from test_smc2 import example
     from mcstate_b200.smc2 import smc2, smc2_control
     kind = sys.argv[1]
-    dist.init_process_group("gloo")
+    backend = os.environ.get("MCB_TEST_BACKEND", "gloo") if kind == "gpu" else "gloo"
+    if backend == "nccl":
+        import torch
+        torch.cuda.set_device(int(os.environ["LOCAL_RANK"]) % torch.cuda.device_count())
+    dist.init_process_group(backend)
     f, p = example(kind, n_days=30)
     res = smc2(p, f, smc2_control(7, seed=5))
     if dist.get_rank() == 0:
