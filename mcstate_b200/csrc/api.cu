@@ -63,6 +63,7 @@ const ModelDesc kModels[] = {
      {"S", "I", "R", "cases_inc"}},
 };
 constexpr int kNumModels = sizeof(kModels) / sizeof(kModels[0]);
+constexpr size_t kMaxWalkRows = 2048;  // counts covered by a walk table (samplers.cuh)
 
 size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
 
@@ -133,7 +134,7 @@ struct GraphEntry {
 }  // namespace
 
 struct mcb_model {
-  int model_id = 0, scrambler = 0, device = 0;
+  int model_id = 0, scrambler = 0, device = 0, n_const = 0;
   const ModelDesc *desc = nullptr;
   mcb::View v{};
   uint64_t time = 0;
@@ -261,10 +262,11 @@ void finish_state(mcb_model *m, int last, int last_weighted, int *kappa_out) {
 }
 
 void prepare_sets(mcb_model *m) {
-  const int tables = m->model_id == 0 ? mcb::SirModel::kTables : mcb::SirsModel::kTables;
-  const dim3 grid(blocks_for((size_t)tables * m->v.n_tab, 256), (unsigned)m->v.n_sets);
-  if (m->model_id == 0) mcb::k_prepare_sets<mcb::SirModel><<<grid, 256, 0, m->stream>>>(m->v);
-  else mcb::k_prepare_sets<mcb::SirsModel><<<grid, 256, 0, m->stream>>>(m->v);
+  const int n_const = m->model_id == 0 ? mcb::SirModel::kConst : mcb::SirsModel::kConst;
+  const dim3 grid(blocks_for((size_t)m->v.n_tab + (size_t)n_const * m->v.n_wrows, 128),
+                  (unsigned)m->v.n_sets);
+  if (m->model_id == 0) mcb::k_prepare_sets<mcb::SirModel><<<grid, 128, 0, m->stream>>>(m->v);
+  else mcb::k_prepare_sets<mcb::SirsModel><<<grid, 128, 0, m->stream>>>(m->v);
   ++m->launches;
 }
 
@@ -671,7 +673,8 @@ int mcb_alloc_ex(int model_id, const double *pars, size_t n_particles, size_t n_
   ALLOC(m->d_pars, n_sets * mcb::kMaxPar * sizeof(double));
   {
     // memo tables cover compartment counts up to the largest initial population,
-    // within 64 Ki entries and 256 MB in total; larger counts take the direct path
+    // within 64 Ki rows and 1 GB in total; larger counts take the direct path.  The
+    // walk tables stop at kMaxWalkRows counts (beyond: the direct path).
     double max_pop = 0.0;
     const int np = m->desc->n_par;
     for (size_t p = 0; p < n_sets; ++p) {
@@ -681,13 +684,18 @@ int mcb_alloc_ex(int model_id, const double *pars, size_t n_particles, size_t n_
     }
     size_t n_tab = max_pop < 65535.0 ? (size_t)max_pop + 1 : 65536;
     n_tab = round_up(n_tab < 256 ? 256 : n_tab, 256);
-    const size_t budget = ((size_t)256 << 20) / (n_sets * mcb::kMaxTables * sizeof(double2));
+    const size_t n_const = model_id == 0 ? mcb::SirModel::kConst : mcb::SirsModel::kConst;
+    const size_t row_bytes = (2 + n_const * mcb::kWalkK) * sizeof(double);
+    const size_t budget = ((size_t)1 << 30) / (n_sets * row_bytes);
     if (n_tab > budget) n_tab = budget / 256 * 256;
     if (n_tab < 256) n_tab = 256;
     v.n_tab = (int)n_tab;
+    v.n_wrows = (int)(n_tab < kMaxWalkRows ? n_tab : kMaxWalkRows);
+    m->n_const = (int)n_const;
   }
   ALLOC(v.derived, n_sets * mcb::kMaxDerived * sizeof(double));
-  ALLOC(v.tables, n_sets * mcb::kMaxTables * (size_t)v.n_tab * sizeof(double2));
+  ALLOC(v.tab_inf, n_sets * (size_t)v.n_tab * sizeof(double2));
+  ALLOC(v.tab_walk, n_sets * (size_t)m->n_const * v.n_wrows * mcb::kWalkK * sizeof(double));
   ALLOC(v.logw, v.ld * sizeof(double));
   ALLOC(v.cw, v.ld * sizeof(unsigned long long));
   ALLOC(v.tile_incl, n_sets * v.tiles_per_set * sizeof(unsigned long long));
@@ -772,7 +780,7 @@ int mcb_free(mcb_model *m) {
   cudaSetDevice(m->device);
   if (m->stream) cudaStreamSynchronize(m->stream);
   clear_graphs(m);
-  void *ptrs[] = {m->v.y, m->v.y_tmp, m->v.rng, m->v.derived, m->v.tables, m->d_pars, m->v.logw, m->v.cw, m->v.tile_incl,
+  void *ptrs[] = {m->v.y, m->v.y_tmp, m->v.rng, m->v.derived, m->v.tab_inf, m->v.tab_walk, m->d_pars, m->v.logw, m->v.cw, m->v.tile_incl,
                   m->v.setinfo, m->d_ll, m->d_min_ll, m->d_flags, m->d_ticket, m->d_index, m->d_kappa, m->d_u,
                   m->d_wmax, m->d_fs_after, m->d_na_global, m->d_data, m->d_stage, m->d_hist_value,
                   m->d_hist_order, m->d_traj, m->d_snap};

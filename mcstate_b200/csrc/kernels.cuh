@@ -51,7 +51,8 @@ struct View {
   uint64_t *rng;      // [4][ld_rng]     stream n_total is the filter's
   const double *pars; // [n_sets][kMaxPar]
   double *derived;    // [n_sets][kMaxDerived]  parameter-only constants (Model::derive)
-  double2 *tables;    // [n_sets][kMaxTables][n_tab] memo tables (Model::table)
+  double2 *tab_inf;   // [n_sets][n_tab]                     infection entries (Model::inf_entry)
+  double *tab_walk;   // [n_sets][n_const][n_wrows][kWalkK]  walk tables (Model::walk_row)
   const double *data; // [n_data][data_sets][2] = {value, lgamma(value+1)}
   double *logw;       // [n_total]
   unsigned long long *cw;        // [n_total] inclusive fixed-point cumsum inside a tile
@@ -65,7 +66,7 @@ struct View {
   unsigned int *ticket; // K2 block counter (the last block finalizes)
   const int *index;   // [n_index] rows returned by run()/saved in trajectories
   size_t n_particles, n_sets, n_total, ld, ld_rng;
-  int n_state, n_index, n_min, data_sets, tiles_per_set, shift, deterministic, n_tab;
+  int n_state, n_index, n_min, data_sets, tiles_per_set, shift, deterministic, n_tab, n_wrows;
   // filter streams (resampling uniforms).  n_fs == 1: one stream shared by every set
   // (the dust pars_multi layout), drawn in set order; when the sets of one model are
   // sharded over several handles, each handle replays the whole order
@@ -220,9 +221,8 @@ __device__ __forceinline__ size_t resample_source_warp(const View &v, size_t set
 // path: deterministic mode, non-integer or out-of-table states.
 template <class M, int SCR>
 __device__ __noinline__ void run_general(double *y, uint64_t *rs, uint64_t t0, uint32_t n_steps,
-                                         const double *derived, const double2 *tables, int n_tab,
-                                         bool det) {
-  const SetData sd{derived, tables, n_tab};
+                                         const double *derived, int n_tab, bool det) {
+  const SetData sd{derived, n_tab};
   const typename M::Ctx ctx = M::context(sd);
   Xoshiro rng{rs[0], rs[1], rs[2], rs[3]};
   double z[M::kState];
@@ -252,8 +252,7 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
   const bool live = i < v.n_total;
   const size_t ii = live ? i : v.n_total - 1;
   const size_t set = v.n_sets == 1 ? 0 : ii / v.n_particles;
-  const SetData sd{v.derived + set * kMaxDerived,
-                   v.tables + set * (size_t)kMaxTables * v.n_tab, v.n_tab};
+  const SetData sd{v.derived + set * kMaxDerived, v.n_tab};
   const typename M::Ctx ctx = M::context(sd);
   const bool det = v.deterministic != 0;
 
@@ -288,7 +287,8 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
       int yi[M::kLeanState];
       typename M::Lean lc;
       uint32_t done = 0;
-      lc.off = (uint32_t)set * (uint32_t)(kMaxTables * v.n_tab);
+      lc.set = (uint32_t)set;
+      const LeanTabs tabs{v.tab_inf, v.tab_walk, (uint32_t)v.n_tab, (uint32_t)v.n_wrows};
       if (!det && M::lean_load(sd, y, yi, lc)) {
         // the usual case: integer compartments, setup from the memo tables, no calls
         const uint32_t s_inv_addr = (uint32_t)__cvta_generic_to_shared(s_inv);
@@ -304,8 +304,7 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
             phase = phase + 1 == freq ? 0 : phase + 1;
           }
           for (uint32_t k = 0; k < nk; ++k) {
-            ok = M::template lean_update<SCR>((resets & 1u) != 0, yi, rng, lc, v.tables,
-                                              (uint32_t)v.n_tab, s_inv_addr);
+            ok = M::template lean_update<SCR>((resets & 1u) != 0, yi, rng, lc, tabs, s_inv_addr);
             if (!ok) break;
             resets >>= 1;
             ++done;
@@ -315,7 +314,7 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
       }
       if (done < n_steps) {  // whatever the lean path did not take
         uint64_t rs[4] = {rng.s0, rng.s1, rng.s2, rng.s3};
-        run_general<M, SCR>(y, rs, t0 + done, n_steps - done, sd.derived, sd.tables, sd.n_tab, det);
+        run_general<M, SCR>(y, rs, t0 + done, n_steps - done, sd.derived, sd.n_tab, det);
         rng.s0 = rs[0]; rng.s1 = rs[1]; rng.s2 = rs[2]; rng.s3 = rs[3];
       }
     }
@@ -699,9 +698,12 @@ __global__ void k_prepare_sets(View v) {
 #pragma unroll
     for (int k = 0; k < kMaxDerived; ++k) v.derived[set * kMaxDerived + k] = d[k];
   }
-  if (e < M::kTables * v.n_tab) {
-    const int t = e / v.n_tab, n = e - t * v.n_tab;
-    v.tables[(set * kMaxTables + t) * (size_t)v.n_tab + n] = M::table(t, n, d);
+  // one thread per entry or row: n_tab infection entries, then kConst x n_wrows walk rows
+  if (e < v.n_tab) {
+    v.tab_inf[set * (size_t)v.n_tab + e] = M::inf_entry(e, d);
+  } else if (e - v.n_tab < M::kConst * v.n_wrows) {
+    const int w = e - v.n_tab, c = w / v.n_wrows, n = w - c * v.n_wrows;
+    M::walk_row(c, n, d, v.tab_walk + ((set * M::kConst + c) * (size_t)v.n_wrows + n) * kWalkK);
   }
 }
 

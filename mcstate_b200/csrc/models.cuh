@@ -9,8 +9,10 @@
 // A model is a struct with kState / kPar / kData, and
 //   derive()   per parameter set, once per update_state(pars): constants that
 //              depend on the parameters only (kMaxDerived doubles in HBM);
-//   table()    per parameter set: memo tables indexed by a compartment count
-//              (pure functions of a small integer and the parameters);
+//   walk_row(), inf_entry()  per parameter set: what the memo tables are
+//              built from -- a walk table per draw whose probability the
+//              parameters fix (samplers.cuh), and one entry per infectious count
+//              {q, q/(1-q)} for the state-dependent draw;
 //   context()  per thread, per launch: pointers to the above;
 //   initial(), update(), compare()  the general form, state as doubles;
 //   lean_load(), lean_update(), lean_store()  the same arithmetic for the usual
@@ -28,25 +30,25 @@ namespace mcb {
 constexpr int kMaxState = 8;
 constexpr int kMaxPar = 8;
 constexpr int kMaxDerived = 16;
-constexpr int kMaxTables = 3;
+constexpr int kMaxConst = 2;     // draws with a parameter-only probability, per model
 
 // where a thread finds its parameter set's prepared data
 struct SetData {
   const double *derived;   // [kMaxDerived]
-  const double2 *tables;   // [kMaxTables][n_tab]
   int n_tab;
 };
 
+// The memo tables as the lean path sees them: warp-uniform values that stay in the
+// kernel's parameter bank (no registers spent on them between uses).
+//   inf  [n_sets][n_tab]                     entries of the infection table
+//   walk [n_sets][n_const][n_wrows][kWalkK]  walk tables (samplers.cuh)
+struct LeanTabs {
+  const double2 *inf;
+  const double *walk;
+  uint32_t n_tab, n_wrows;
+};
+
 // ---- memo-table entries ----------------------------------------------------
-// A draw with a probability fixed by the parameter set (recovery, waning):
-// entry n = {(1-q)^n, r (n+1)}, or {-1, .} when count n is not a plain
-// inversion draw with this probability.
-__device__ __forceinline__ double2 const_binomial_entry(double p, double q, double qq, double r,
-                                                        int n) {
-  const double g = r * (double)(n + 1);
-  const bool plain = p > 0.0 && p <= 0.5 && !((double)n * q >= 10.0) && g > 1e-280 && g < 1e280;
-  return make_double2(plain ? pow_int(qq, n) : -1.0, g);
-}
 // Infection: entry I = {q, q/(1-q)} with q = p_SI(I) dt, {0, 0} when the
 // probability is zero (no draw), {-1, .} when it is not in (0, 1/2] or r is
 // near the ends of the exponent range.
@@ -88,13 +90,22 @@ __device__ __forceinline__ int draw_infection_lean(Xoshiro &rng, int S, double2 
   return k;
 }
 
+// Binomial(n, p) for the set's constant draw `c`: row n of its walk table, or -1
+// (generator untouched) when the table has no such row.
+template <int SCR>
+__device__ __forceinline__ int draw_const_lean(Xoshiro &rng, int n, uint32_t set_const,
+                                               const LeanTabs &t) {
+  if ((uint32_t)n >= t.n_wrows) return -1;
+  return draw_binomial_table<SCR>(rng, t.walk + ((size_t)(set_const * t.n_wrows + (uint32_t)n) * kWalkK));
+}
+
 struct SirModel {
   static constexpr int kState = 5;
   static constexpr int kPar = 7;  // beta gamma I0 exp_noise S0 R0 freq
   static constexpr int kData = 1; // incidence
-  static constexpr int kTables = 2;
+  static constexpr int kConst = 1;  // recovery
   enum { D_BETA, D_DT, D_EXP_NOISE, D_FREQ, D_NTOT, D_P_IR, D_Q_IR, D_QQ_IR, D_R_IR, D_FLIP_IR };
-  enum { T_IR, T_SI };
+  enum { C_IR };
 
   __device__ __forceinline__ static void derive(const double *__restrict__ p, double *d) {
     const double dt = 1.0 / p[6];
@@ -112,25 +123,24 @@ struct SirModel {
     d[D_R_IR] = q / qq;
     d[D_FLIP_IR] = p_ir > 0.5 ? 1.0 : 0.0;
   }
-  // entry n of table t
-  __device__ __forceinline__ static double2 table(int t, int n, const double *d) {
-    if (t == T_IR) return const_binomial_entry(d[D_P_IR], d[D_Q_IR], d[D_QQ_IR], d[D_R_IR], n);
-    return infection_entry(d[D_BETA], d[D_NTOT], d[D_DT], n);
+  // row n of the walk table of constant draw c; row I of the infection table
+  __device__ __forceinline__ static void walk_row(int, int n, const double *d, double *row) {
+    fill_walk_row(d[D_P_IR], d[D_Q_IR], d[D_QQ_IR], d[D_R_IR], n, row);
+  }
+  __device__ __forceinline__ static double2 inf_entry(int I, const double *d) {
+    return infection_entry(d[D_BETA], d[D_NTOT], d[D_DT], I);
   }
 
   struct Ctx {
     const double *derived;
     BinomialConst ir;
     double beta, dt, n_tot;
-    const double2 *tab_ir, *tab_si;
-    int n_tab;
     uint32_t freq;
   };
   __device__ __forceinline__ static Ctx context(const SetData &sd) {
     const double *d = sd.derived;
     Ctx c;
     c.derived = d;
-    c.n_tab = sd.n_tab;
     c.beta = __ldg(d + D_BETA);
     c.dt = __ldg(d + D_DT);
     c.n_tot = __ldg(d + D_NTOT);
@@ -140,9 +150,6 @@ struct SirModel {
     c.ir.qq = __ldg(d + D_QQ_IR);
     c.ir.r = __ldg(d + D_R_IR);
     c.ir.flip = __ldg(d + D_FLIP_IR) != 0.0;
-    c.ir.n_tab = sd.n_tab;
-    c.tab_ir = sd.tables + (size_t)T_IR * sd.n_tab;
-    c.tab_si = sd.tables + (size_t)T_SI * sd.n_tab;
     return c;
   }
   __device__ __forceinline__ static void initial(const double *__restrict__ p, double *y) {
@@ -172,18 +179,16 @@ struct SirModel {
   }
 
   // ---- the lean path ------------------------------------------------------
-  // Register diet: the hot loop keeps r = q/(1-q) of the recovery draw, one
-  // pointer to the set's tables and four counts (R is implied by the closed
-  // population); it makes no calls.  A step that meets anything unusual is
-  // abandoned with state and generator as they were at its start.
+  // Register diet: the hot loop keeps the set's index and four counts (R is
+  // implied by the closed population); it makes no calls.  A step that meets
+  // anything unusual is abandoned with state and generator as they were at its
+  // start.
   struct Lean {
-    double r_ir;
-    uint32_t off;  // entry offset of the set's tables: set * kMaxTables * n_tab
+    uint32_t set;
   };
   static constexpr int kLeanState = 4;  // S, I, cumulative, interval incidence
   __device__ __forceinline__ static bool lean_load(const SetData &sd, const double *y, int *yi,
                                                    Lean &c) {
-    c.r_ir = __ldg(sd.derived + D_R_IR);
     int all[kState];
     if (!to_counts<kState>(y, all)) return false;
     yi[0] = all[0]; yi[1] = all[1]; yi[2] = all[3]; yi[3] = all[4];
@@ -203,15 +208,15 @@ struct SirModel {
   // false: nothing changed, the general code must run this step.
   template <int SCR>
   __device__ __forceinline__ static bool lean_update(bool reset, int *y, Xoshiro &rng,
-                                                     const Lean &c, const double2 *__restrict__ tables,
-                                                     uint32_t n_tab, uint32_t s_inv) {
+                                                     const Lean &c, const LeanTabs &t,
+                                                     uint32_t s_inv) {
     const int S = y[0], I = y[1];
     int n_IR = 0;
     if (I != 0) {
-      n_IR = draw_binomial_const_lean<SCR>(rng, I, c.r_ir, __ldg(tables + (c.off + T_IR * n_tab + (uint32_t)I)), s_inv);
+      n_IR = draw_const_lean<SCR>(rng, I, c.set * kConst + C_IR, t);
       if (n_IR < 0) return false;
     }
-    const int n_SI = draw_infection_lean<SCR>(rng, S, __ldg(tables + (c.off + T_SI * n_tab + (uint32_t)I)), s_inv);
+    const int n_SI = draw_infection_lean<SCR>(rng, S, __ldg(t.inf + (c.set * t.n_tab + (uint32_t)I)), s_inv);
     if (n_SI < 0) {
       if (I != 0) xo_rewind(rng);  // the recovery draw's uniform
       return false;
@@ -228,10 +233,10 @@ struct SirsModel {
   static constexpr int kState = 4;
   static constexpr int kPar = 8;  // alpha beta gamma I0 exp_noise S0 R0 freq
   static constexpr int kData = 1;
-  static constexpr int kTables = 3;
+  static constexpr int kConst = 2;  // recovery, waning
   enum { D_BETA, D_DT, D_EXP_NOISE, D_FREQ, D_NTOT, D_P_IR, D_Q_IR, D_QQ_IR, D_R_IR, D_FLIP_IR,
          D_P_RS, D_Q_RS, D_QQ_RS, D_R_RS, D_FLIP_RS };
-  enum { T_IR, T_SI, T_RS };
+  enum { C_IR, C_RS };
 
   __device__ __forceinline__ static void derive(const double *__restrict__ p, double *d) {
     const double dt = 1.0 / p[7];
@@ -249,38 +254,32 @@ struct SirsModel {
     d[D_P_RS] = p_rs; d[D_Q_RS] = q2; d[D_QQ_RS] = 1.0 - q2; d[D_R_RS] = q2 / (1.0 - q2);
     d[D_FLIP_RS] = p_rs > 0.5 ? 1.0 : 0.0;
   }
-  __device__ __forceinline__ static double2 table(int t, int n, const double *d) {
-    if (t == T_IR) return const_binomial_entry(d[D_P_IR], d[D_Q_IR], d[D_QQ_IR], d[D_R_IR], n);
-    if (t == T_RS) return const_binomial_entry(d[D_P_RS], d[D_Q_RS], d[D_QQ_RS], d[D_R_RS], n);
-    return infection_entry(d[D_BETA], d[D_NTOT], d[D_DT], n);
+  __device__ __forceinline__ static void walk_row(int c, int n, const double *d, double *row) {
+    if (c == C_IR) fill_walk_row(d[D_P_IR], d[D_Q_IR], d[D_QQ_IR], d[D_R_IR], n, row);
+    else fill_walk_row(d[D_P_RS], d[D_Q_RS], d[D_QQ_RS], d[D_R_RS], n, row);
+  }
+  __device__ __forceinline__ static double2 inf_entry(int I, const double *d) {
+    return infection_entry(d[D_BETA], d[D_NTOT], d[D_DT], I);
   }
 
   struct Ctx {
     const double *derived;
     BinomialConst ir, rs;
     double beta, dt, n_tot;
-    const double2 *tab_ir, *tab_si, *tab_rs;
-    int n_tab;
     uint32_t freq;
   };
   __device__ __forceinline__ static Ctx context(const SetData &sd) {
     const double *d = sd.derived;
     Ctx c;
     c.derived = d;
-    c.n_tab = sd.n_tab;
     c.beta = __ldg(d + D_BETA);
     c.dt = __ldg(d + D_DT);
     c.n_tot = __ldg(d + D_NTOT);
     c.freq = (uint32_t)__ldg(d + D_FREQ);
     c.ir.p = __ldg(d + D_P_IR); c.ir.q = __ldg(d + D_Q_IR); c.ir.qq = __ldg(d + D_QQ_IR);
     c.ir.r = __ldg(d + D_R_IR); c.ir.flip = __ldg(d + D_FLIP_IR) != 0.0;
-    c.ir.n_tab = sd.n_tab;
     c.rs.p = __ldg(d + D_P_RS); c.rs.q = __ldg(d + D_Q_RS); c.rs.qq = __ldg(d + D_QQ_RS);
     c.rs.r = __ldg(d + D_R_RS); c.rs.flip = __ldg(d + D_FLIP_RS) != 0.0;
-    c.rs.n_tab = sd.n_tab;
-    c.tab_ir = sd.tables + (size_t)T_IR * sd.n_tab;
-    c.tab_si = sd.tables + (size_t)T_SI * sd.n_tab;
-    c.tab_rs = sd.tables + (size_t)T_RS * sd.n_tab;
     return c;
   }
   __device__ __forceinline__ static void initial(const double *__restrict__ p, double *y) {
@@ -310,14 +309,11 @@ struct SirsModel {
   }
 
   struct Lean {
-    double r_ir, r_rs;
-    uint32_t off;
+    uint32_t set;
   };
   static constexpr int kLeanState = 4;
   __device__ __forceinline__ static bool lean_load(const SetData &sd, const double *y, int *yi,
                                                    Lean &c) {
-    c.r_ir = __ldg(sd.derived + D_R_IR);
-    c.r_rs = __ldg(sd.derived + D_R_RS);
     if (!to_counts<kState>(y, yi)) return false;
     const double n_tot = __ldg(sd.derived + D_NTOT);
     return y[0] + y[1] + y[2] == n_tot && n_tot < (double)sd.n_tab;
@@ -328,16 +324,17 @@ struct SirsModel {
   }
   template <int SCR>
   __device__ __forceinline__ static bool lean_update(bool reset, int *y, Xoshiro &rng,
-                                                     const Lean &c, const double2 *__restrict__ tables,
-                                                     uint32_t n_tab, uint32_t s_inv) {
+                                                     const Lean &c, const LeanTabs &t,
+                                                     uint32_t s_inv) {
     const int S = y[0], I = y[1], R = y[2];
-    const int n_SI = draw_infection_lean<SCR>(rng, S, __ldg(tables + (c.off + T_SI * n_tab + (uint32_t)I)), s_inv);
+    const double2 e_si = __ldg(t.inf + (c.set * t.n_tab + (uint32_t)I));
+    const int n_SI = draw_infection_lean<SCR>(rng, S, e_si, s_inv);
     if (n_SI < 0) return false;
     // did the infection draw take a uniform?  (it returns 0 without one for S = 0 or p = 0)
-    const bool si_drew = S != 0 && I != 0 && __ldg(tables + (c.off + T_SI * n_tab + (uint32_t)I)).x != 0.0;
+    const bool si_drew = S != 0 && e_si.x != 0.0;
     int n_IR = 0;
     if (I != 0) {
-      n_IR = draw_binomial_const_lean<SCR>(rng, I, c.r_ir, __ldg(tables + (c.off + T_IR * n_tab + (uint32_t)I)), s_inv);
+      n_IR = draw_const_lean<SCR>(rng, I, c.set * kConst + C_IR, t);
       if (n_IR < 0) {
         if (si_drew) xo_rewind(rng);
         return false;
@@ -345,7 +342,7 @@ struct SirsModel {
     }
     int n_RS = 0;
     if (R != 0) {
-      n_RS = draw_binomial_const_lean<SCR>(rng, R, c.r_rs, __ldg(tables + (c.off + T_RS * n_tab + (uint32_t)R)), s_inv);
+      n_RS = draw_const_lean<SCR>(rng, R, c.set * kConst + C_RS, t);
       if (n_RS < 0) {
         if (I != 0) xo_rewind(rng);
         if (si_drew) xo_rewind(rng);

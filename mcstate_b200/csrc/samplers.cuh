@@ -146,54 +146,142 @@ __device__ __forceinline__ void xo_rewind(Xoshiro &r) {
 // with the general code, which handles those cases by the book.
 // s_inv: the {k, RN(1/k)} table in shared memory; g = r (n + 1) must be away from
 // overflow/underflow (the caller's table entry guarantees it).
-// The loop is unrolled by two so f and its successor swap roles without moves.
 __device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
   double2 e;
   asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(e.x), "=d"(e.y) : "r"(addr));
   return e;
 }
+__device__ __forceinline__ double2 ldg_f64x2(const double *p) {
+  double2 e;
+  asm("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(e.x), "=d"(e.y) : "l"(p));
+  return e;
+}
+// one 32-byte load (LDG.256): four consecutive table entries
+__device__ __forceinline__ double4 ldg_f64x4(const double *p) {
+  double4 e;
+  asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
+      : "=d"(e.x), "=d"(e.y), "=d"(e.z), "=d"(e.w) : "l"(p));
+  return e;
+}
 
 // s_inv_addr: shared-window address of the {k, RN(1/k)} table.
-// One predicate drives the loop: keep walking while u >= f, f changed, and the
-// table has another entry; the two rare reasons are told apart after the loop
+// One predicate drives each step: keep walking while u >= f, f changed, and the
+// table has another entry; the two rare reasons are told apart after the walk
 // (the order of the reference's tests is kept: a stalled f abandons the attempt
 // whatever u is).
+// Every lane of a warp is at the same k in the same step, so the first four
+// steps are written out with their divisor known at compile time: g/1, g/2 and
+// g/4 are exact scalings (g is away from underflow), g/3 takes its reciprocal as
+// an immediate.  The loop from k = 5 is unrolled by two so f and its successor
+// swap roles without moves.
+#define MCB_WALK_STEP(K, FACTOR)                                    \
+  u -= f;                                                           \
+  fn = f * ((FACTOR) - r);                                          \
+  if (!((u >= fn) & (fn != f) & ((K) < kmax))) { k = (K); goto walk_out; } \
+  f = fn;
 template <int SCR>
 __device__ __forceinline__ int walk_lean(Xoshiro &rng, int n, double r, double f0, double g,
                                          uint32_t s_inv_addr) {
-  uint32_t a = s_inv_addr;
-  const uint32_t a_end = s_inv_addr + 16u * (uint32_t)min(n, kInvSmall - 1);
+  const int kmax = min(n, kInvSmall - 1);
   double u = xo_real<SCR>(rng);
-  double f = f0;
-  if (!(u >= f)) return 0;   // n >= 1: the table has an entry to move to
-  bool bad;
-  for (;;) {
-    // The factors c_k = g/k - r do not depend on f or u: the next two are computed
-    // side by side (two independent dependency chains), then applied in order.
-    // The second may go unused; the table has one spare entry for its load.
-    const double2 e1 = lds_f64x2(a + 16);
-    const double2 e2 = lds_f64x2(a + 32);
-    double q1 = g * e1.y, q2 = g * e2.y;
-    double r1 = fma(-q1, e1.x, g), r2 = fma(-q2, e2.x, g);
-    q1 = fma(r1, e1.y, q1); q2 = fma(r2, e2.y, q2);
-    r1 = fma(-q1, e1.x, g); r2 = fma(-q2, e2.x, g);
-    const double c1 = fma(r1, e1.y, q1) - r, c2 = fma(r2, e2.y, q2) - r;
-    u -= f;
-    const double f1 = f * c1;
-    if (!((u >= f1) & (f1 != f) & (a + 16 < a_end))) {
-      bad = (f1 == f) | (u >= f1);  // stalled, or out of table with u >= f still
+  double f = f0, fn;
+  int k;
+  if (!(u >= f)) return 0;   // n >= 1: there is a k = 1 to move to
+  MCB_WALK_STEP(1, g)
+  MCB_WALK_STEP(2, g * 0.5)
+  MCB_WALK_STEP(3, div_small_int(g, 3.0, 1.0 / 3.0))
+  MCB_WALK_STEP(4, g * 0.25)
+  {
+    uint32_t a = s_inv_addr + 16u * 4u;
+    const uint32_t a_end = s_inv_addr + 16u * (uint32_t)kmax;
+    for (;;) {
+      // The factors c_k = g/k - r do not depend on f or u: the next two are computed
+      // side by side (two independent dependency chains), then applied in order.
+      // The second may go unused; the table has one spare entry for its load.
+      const double2 e1 = lds_f64x2(a + 16);
+      const double2 e2 = lds_f64x2(a + 32);
+      double q1 = g * e1.y, q2 = g * e2.y;
+      double r1 = fma(-q1, e1.x, g), r2 = fma(-q2, e2.x, g);
+      q1 = fma(r1, e1.y, q1); q2 = fma(r2, e2.y, q2);
+      r1 = fma(-q1, e1.x, g); r2 = fma(-q2, e2.x, g);
+      const double c1 = fma(r1, e1.y, q1) - r, c2 = fma(r2, e2.y, q2) - r;
+      u -= f;
+      fn = f * c1;
       a += 16;
-      break;
+      if (!((u >= fn) & (fn != f) & (a < a_end))) break;
+      u -= fn;
+      f = fn;
+      fn = f * c2;
+      a += 16;
+      if (!((u >= fn) & (fn != f) & (a < a_end))) break;
+      f = fn;
     }
-    u -= f1;
-    a += 32;
-    f = f1 * c2;
-    if (!((u >= f) & (f != f1) & (a < a_end))) {
-      bad = (f == f1) | (u >= f);
-      break;
-    }
+    k = (int)((a - s_inv_addr) >> 4);
   }
-  return bad ? -1 : (int)((a - s_inv_addr) >> 4);
+walk_out:
+  // stalled, or out of table with u >= f still
+  return ((fn == f) | (u >= fn)) ? -1 : k;
+}
+#undef MCB_WALK_STEP
+
+// ---------------------------------------------------------------------------
+// Walk tables: a draw whose probability is fixed by the parameter set
+// (recovery, waning) has a CDF walk that depends on the count n alone, so the
+// whole sequence f_0 .. f_{kWalkK-1} of every count is prepared once per
+// parameter set (k_prepare_sets) by the very operations of inversion_walk --
+// same bits -- and a draw is then one uniform, 32-byte loads and a
+// subtract-and-compare chain: no division, no product.
+//   row n: f_k >= 0 while the walk may stand at k; -1 from the first k the walk
+//   would abandon the attempt at (f stalled, k > n) to the end of the row; the
+//   whole row -1 when count n is not a plain inversion draw (n q >= 10 -> BTRS,
+//   p outside (0, 1/2], g near the ends of the exponent range).
+// ---------------------------------------------------------------------------
+constexpr int kWalkK = 32;
+
+__device__ __forceinline__ void fill_walk_row(double p, double q, double qq, double r, int n,
+                                              double *__restrict__ row) {
+  const double g = r * (double)(n + 1);
+  const bool plain = p > 0.0 && p <= 0.5 && !((double)n * q >= 10.0) && g > 1e-280 && g < 1e280;
+  double f = plain ? pow_int(qq, n) : -1.0;
+  bool dead = !plain;
+  row[0] = f;
+  for (int k = 1; k < kWalkK; ++k) {
+    if (!dead) {
+      const double fn = f * (g / (double)k - r);
+      if (fn == f || k > n) dead = true; else f = fn;
+    }
+    row[k] = dead ? -1.0 : f;
+  }
+}
+
+// Binomial(n, p) from row n of a walk table.  Returns the draw, or -1 with the
+// generator exactly as it was on entry (not a plain draw, an abandoned attempt, or
+// a walk past the row): the caller hands the rest of the interval to the general
+// code.  A -1 entry keeps the chain going (u >= -1) to the end of the row.
+template <int SCR>
+__device__ __forceinline__ int draw_binomial_table(Xoshiro &rng, const double *__restrict__ row) {
+  double4 F = ldg_f64x4(row);
+  if (F.x < 0.0) return -1;
+  double u = xo_real<SCR>(rng);
+  int k = 0;
+  for (;;) {
+    const bool c0 = u >= F.x;
+    u -= F.x;
+    const bool c1 = c0 & (u >= F.y);
+    u -= F.y;
+    const bool c2 = c1 & (u >= F.z);
+    u -= F.z;
+    const bool c3 = c2 & (u >= F.w);
+    u -= F.w;
+    k += (int)c0 + (int)c1 + (int)c2 + (int)c3;
+    if (!c3) break;
+    if (k == kWalkK) {
+      xo_rewind(rng);
+      return -1;
+    }
+    F = ldg_f64x4(row + k);
+  }
+  return k;
 }
 
 __device__ __forceinline__ double stirling_tail(double k) {
@@ -255,7 +343,6 @@ __device__ __forceinline__ double draw_binomial(Xoshiro &rng, bool deterministic
 struct BinomialConst {
   double p, q, qq, r;   // q = min(p, 1-p), qq = 1-q, r = q/qq
   bool flip;            // p > 0.5
-  int n_tab;            // entries in the set's memo table (the lean path)
 };
 
 template <int SCR>
@@ -272,21 +359,6 @@ __device__ __forceinline__ double draw_binomial_const(Xoshiro &rng, bool determi
     draw = inversion_walk<SCR>(rng, ni, c.r, pow_int(c.qq, ni));
   }
   return c.flip ? n - draw : draw;
-}
-
-// Lean draw of Binomial(n, p) for a probability fixed by the parameter set.
-// e = entry n of the set's table: {f0, g} with f0 = (1-q)^n, g = r (n + 1), or
-// f0 < 0 when this n is not a plain inversion draw (n q >= 10 -> BTRS; p outside
-// (0, 1/2]; g near the ends of the exponent range).  Returns the draw, or -1 with
-// the generator exactly as it was on entry: the caller then hands the rest of the
-// interval to the general code.
-template <int SCR>
-__device__ __forceinline__ int draw_binomial_const_lean(Xoshiro &rng, int n, double r, double2 e,
-                                                        uint32_t s_inv) {
-  if (e.x < 0.0) return -1;
-  const int k = walk_lean<SCR>(rng, n, r, e.x, e.y, s_inv);
-  if (k < 0) xo_rewind(rng);
-  return k;
 }
 
 // x log(lambda) - lambda - lgamma(x + 1); lgamma(x + 1) depends on the datum
