@@ -135,6 +135,7 @@ struct GraphEntry {
 
 struct mcb_model {
   int model_id = 0, scrambler = 0, device = 0, n_const = 0;
+  bool chain = false;   // K1/K2 launched with programmatic dependent launch
   const ModelDesc *desc = nullptr;
   mcb::View v{};
   uint64_t time = 0;
@@ -210,17 +211,38 @@ int ensure_stage(mcb_model *m, size_t bytes) {
 
 unsigned blocks_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
+// Launch with (chained = true) programmatic dependent launch: the kernel may be
+// scheduled while its predecessor in the stream drains -- its blocks do their
+// prologue and then wait (griddepcontrol.wait) until the predecessor has completed
+// and its writes are visible.  Inside a captured graph this becomes a programmatic
+// edge.  K1 and K2 of the filter loop are chained this way; both kernels wait
+// before they touch anything another kernel wrote.
+template <class... P, class... A>
+void launch_chained(mcb_model *m, bool chained, void (*kernel)(P...), unsigned grid, int threads,
+                    A... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.stream = m->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = chained ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+  ++m->launches;
+}
+
 template <class M, int SCR>
 void launch_run_compare(mcb_model *m, const double *y_in, double *y_out, uint64_t t0,
                         uint32_t n_steps, int prev_row, int row, double *hist, int *kappa_out) {
   const unsigned grid = blocks_for(m->v.n_total, mcb::kRunThreads);
   if (hist)
-    mcb::k_run_compare<M, SCR, true><<<grid, mcb::kRunThreads, 0, m->stream>>>(
-        m->v, y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out);
+    launch_chained(m, m->chain, mcb::k_run_compare<M, SCR, true>, grid, mcb::kRunThreads, m->v,
+                   y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out);
   else
-    mcb::k_run_compare<M, SCR, false><<<grid, mcb::kRunThreads, 0, m->stream>>>(
-        m->v, y_in, y_out, t0, n_steps, prev_row, row, nullptr, nullptr);
-  ++m->launches;
+    launch_chained(m, m->chain, mcb::k_run_compare<M, SCR, false>, grid, mcb::kRunThreads, m->v,
+                   y_in, y_out, t0, n_steps, prev_row, row, (double *)nullptr, (int *)nullptr);
 }
 
 // K1: [resample prev_row on load] -> n_steps updates -> compare against `row`
@@ -238,9 +260,8 @@ void run_compare(mcb_model *m, const double *y_in, double *y_out, uint64_t t0, u
 // K2: weights -> fixed point -> tile scan; the last block finalizes the interval
 void weights_scan(mcb_model *m, int row) {
   const unsigned grid = (unsigned)(m->v.n_sets * m->v.tiles_per_set);
-  if (row < 0) mcb::k_weights_scan<true><<<grid, mcb::kTileThreads, 0, m->stream>>>(m->v, row);
-  else mcb::k_weights_scan<false><<<grid, mcb::kTileThreads, 0, m->stream>>>(m->v, row);
-  ++m->launches;
+  if (row < 0) launch_chained(m, m->chain, mcb::k_weights_scan<true>, grid, mcb::kTileThreads, m->v, row);
+  else launch_chained(m, m->chain, mcb::k_weights_scan<false>, grid, mcb::kTileThreads, m->v, row);
 }
 
 void resample_gather(mcb_model *m, int row, const double *src, double *dst, int *kappa_out) {
@@ -344,6 +365,10 @@ uint64_t enqueue_filter_rows(mcb_model *m, int first, int last, bool hist,
   size_t snap_i = 0;
   int prev_weighted = -1;          // row whose resampling is still owed, or -1
   const double *in = v.y;
+  // the loop's K1 and K2 are chained by programmatic dependent launch (not when
+  // events sit between them for per-kernel timing); MCB_PDL=0 turns it off
+  static const bool pdl = !(getenv("MCB_PDL") && atoi(getenv("MCB_PDL")) == 0);
+  m->chain = pdl && !m->timing;
   for (int row = first; row < last; ++row) {
     const uint64_t t_end = m->data_time[row];
     const uint32_t n_steps = (uint32_t)(t_end - t);
@@ -375,6 +400,7 @@ uint64_t enqueue_filter_rows(mcb_model *m, int first, int last, bool hist,
     in = out;
     t = t_end;
   }
+  m->chain = false;
   mark(m, (int)m->n_data, 0);
   int *order_last = hist ? m->d_hist_order + (size_t)(last - first) * v.n_total : nullptr;
   finish_state(m, last, prev_weighted >= 0 ? 1 : 0, prev_weighted >= 0 ? order_last : nullptr);

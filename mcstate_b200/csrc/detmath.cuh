@@ -16,6 +16,21 @@ namespace mcb {
 __device__ __forceinline__ double bits_to_double(uint64_t u) { return __longlong_as_double((long long)u); }
 __device__ __forceinline__ uint64_t double_to_bits(double x) { return (uint64_t)__double_as_longlong(x); }
 
+// The coefficients live in constant memory: a 64-bit immediate costs two uniform
+// moves per use, a constant-bank operand none.
+__constant__ double c_exp_poly[12] = {
+    1.6059043836821613e-10, 2.08767569878681e-09,   2.505210838544172e-08,
+    2.755731922398589e-07,  2.7557319223985893e-06, 2.48015873015873e-05,
+    1.984126984126984e-04,  1.388888888888889e-03,  8.333333333333333e-03,
+    4.1666666666666664e-02, 1.6666666666666666e-01, 0.5};
+__constant__ double c_exp_red[3] = {1.4426950408889634074, 6.93147180559945286e-01,
+                                    2.31904681384629956e-17};
+__constant__ double c_log_poly[7] = {
+    1.531383769920937332e-01, 2.222219843214978396e-01, 3.999999999940941908e-01,
+    1.479819860511658591e-01, 1.818357216161805012e-01, 2.857142874366239149e-01,
+    6.666666666666735130e-01};
+__constant__ double c_log_ln2[2] = {1.90821492927058770002e-10, 6.93147180369123816490e-01};
+
 // exp(x): k = rint(x / ln 2); Cody-Waite reduction r = x - k ln2 with ln2 split
 // in two doubles (the fma keeps k*ln2_hi exact); degree-13 Taylor polynomial on
 // |r| <= ln2/2 (truncation < 5e-18); scaling by 2^k in two steps so a
@@ -24,21 +39,12 @@ __device__ __forceinline__ double det_exp(double x) {
   if (x != x) return x;
   if (x > 709.782712893384) return __longlong_as_double(0x7ff0000000000000LL);
   if (x < -745.1332191019412) return 0.0;
-  const double kd = rint(x * 1.4426950408889634074);
-  double r = fma(-kd, 6.93147180559945286e-01, x);
-  r = fma(-kd, 2.31904681384629956e-17, r);
-  double p = 1.6059043836821613e-10;
-  p = fma(p, r, 2.08767569878681e-09);
-  p = fma(p, r, 2.505210838544172e-08);
-  p = fma(p, r, 2.755731922398589e-07);
-  p = fma(p, r, 2.7557319223985893e-06);
-  p = fma(p, r, 2.48015873015873e-05);
-  p = fma(p, r, 1.984126984126984e-04);
-  p = fma(p, r, 1.388888888888889e-03);
-  p = fma(p, r, 8.333333333333333e-03);
-  p = fma(p, r, 4.1666666666666664e-02);
-  p = fma(p, r, 1.6666666666666666e-01);
-  p = fma(p, r, 0.5);
+  const double kd = rint(x * c_exp_red[0]);
+  double r = fma(-kd, c_exp_red[1], x);
+  r = fma(-kd, c_exp_red[2], r);
+  double p = c_exp_poly[0];
+#pragma unroll
+  for (int j = 1; j < 12; ++j) p = fma(p, r, c_exp_poly[j]);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
   const int k = (int)kd;
@@ -77,16 +83,12 @@ __device__ __forceinline__ double det_log(double x) {
   const double s = f / (2.0 + f);
   const double z = s * s;
   const double w = z * z;
-  const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01),
-                            3.999999999940941908e-01);
-  const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01,
-                                          1.818357216161805012e-01),
-                                   2.857142874366239149e-01),
-                            6.666666666666735130e-01);
+  const double t1 = w * fma(w, fma(w, c_log_poly[0], c_log_poly[1]), c_log_poly[2]);
+  const double t2 = z * fma(w, fma(w, fma(w, c_log_poly[3], c_log_poly[4]), c_log_poly[5]),
+                            c_log_poly[6]);
   const double R = t2 + t1;
   const double dk = (double)k;
-  return s * (hfsq + R) + dk * 1.90821492927058770002e-10 - hfsq + f +
-         dk * 6.93147180369123816490e-01;
+  return s * (hfsq + R) + dk * c_log_ln2[0] - hfsq + f + dk * c_log_ln2[1];
 }
 
 }  // namespace mcb

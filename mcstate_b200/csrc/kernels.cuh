@@ -77,6 +77,14 @@ struct View {
   const unsigned char *na_global;  // [n_data][n_sets_global] datum is NA, or nullptr
 };
 
+// ---- programmatic dependent launch (no-ops for a kernel launched the plain way) --
+__device__ __forceinline__ void grid_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;");
+}
+__device__ __forceinline__ void grid_dependency_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ---- order-preserving map double -> u64 so max is one integer atomic --------
 __device__ __forceinline__ unsigned long long key_of(double x) {
   const unsigned long long b = (unsigned long long)__double_as_longlong(x);
@@ -245,8 +253,12 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
   __shared__ unsigned long long s_key[kRunThreads / 32];
   __shared__ unsigned long long s_win[kRunThreads / 32][kWindow];
   __shared__ double2 s_inv[kInvSmall + 1];  // one spare entry (walk_lean looks two ahead)
-  if (v.flags[0]) return;
+  // programmatic dependent launch: let the next kernel be scheduled as this one
+  // drains, and do not read anything an earlier kernel wrote before the wait
+  grid_launch_dependents();
   if (threadIdx.x <= kInvSmall) s_inv[threadIdx.x] = c_inv_small[min((int)threadIdx.x, kInvSmall - 1)];
+  grid_dependency_wait();
+  if (v.flags[0]) return;
   __syncthreads();
   const size_t i = (size_t)blockIdx.x * kRunThreads + threadIdx.x;
   const bool live = i < v.n_total;
@@ -288,7 +300,8 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
       typename M::Lean lc;
       uint32_t done = 0;
       lc.set = (uint32_t)set;
-      const LeanTabs tabs{v.tab_inf, v.tab_walk, (uint32_t)v.n_tab, (uint32_t)v.n_wrows};
+      const LeanTabs tabs{v.tab_inf, v.tab_walk, (uint32_t)v.n_tab, (uint32_t)v.n_wrows,
+                          (32 - __clz(v.n_tab - 1) + 1) / 3};
       if (!det && M::lean_load(sd, y, yi, lc)) {
         // the usual case: integer compartments, setup from the memo tables, no calls
         const uint32_t s_inv_addr = (uint32_t)__cvta_generic_to_shared(s_inv);
@@ -505,6 +518,8 @@ template <bool GIVEN>
 __global__ void __launch_bounds__(kTileThreads, 4) k_weights_scan(View v, int row) {
   __shared__ unsigned long long s_warp[kTileThreads / 32];
   __shared__ bool s_last;
+  grid_launch_dependents();
+  grid_dependency_wait();
   if (v.flags[0]) return;
   const size_t set = blockIdx.x / v.tiles_per_set;
   const int tile = blockIdx.x % v.tiles_per_set;

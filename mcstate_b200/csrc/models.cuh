@@ -46,6 +46,7 @@ struct LeanTabs {
   const double2 *inf;
   const double *walk;
   uint32_t n_tab, n_wrows;
+  int pow_groups;   // groups of three bits beyond bit 0 in a count below n_tab
 };
 
 // ---- memo-table entries ----------------------------------------------------
@@ -81,11 +82,11 @@ __device__ __forceinline__ bool to_counts(const double *y, int *yi) {
 // a walk that met one of its rare exits.
 template <int SCR>
 __device__ __forceinline__ int draw_infection_lean(Xoshiro &rng, int S, double2 e,
-                                                   uint32_t s_inv) {
+                                                   int pow_groups, uint32_t s_inv) {
   if (S == 0 || e.x == 0.0) return 0;
   const double Sd1 = (double)(S + 1);
   if (e.x < 0.0 || (Sd1 - 1.0) * e.x >= 10.0) return -1;
-  const int k = walk_lean<SCR>(rng, S, e.y, pow_int_lean(1.0 - e.x, S), e.y * Sd1, s_inv);
+  const int k = walk_lean<SCR>(rng, S, e.y, pow_int_lean(1.0 - e.x, S, pow_groups), e.y * Sd1, s_inv);
   if (k < 0) xo_rewind(rng);
   return k;
 }
@@ -216,7 +217,7 @@ struct SirModel {
       n_IR = draw_const_lean<SCR>(rng, I, c.set * kConst + C_IR, t);
       if (n_IR < 0) return false;
     }
-    const int n_SI = draw_infection_lean<SCR>(rng, S, __ldg(t.inf + (c.set * t.n_tab + (uint32_t)I)), s_inv);
+    const int n_SI = draw_infection_lean<SCR>(rng, S, __ldg(t.inf + (c.set * t.n_tab + (uint32_t)I)), t.pow_groups, s_inv);
     if (n_SI < 0) {
       if (I != 0) xo_rewind(rng);  // the recovery draw's uniform
       return false;
@@ -328,7 +329,7 @@ struct SirsModel {
                                                      uint32_t s_inv) {
     const int S = y[0], I = y[1], R = y[2];
     const double2 e_si = __ldg(t.inf + (c.set * t.n_tab + (uint32_t)I));
-    const int n_SI = draw_infection_lean<SCR>(rng, S, e_si, s_inv);
+    const int n_SI = draw_infection_lean<SCR>(rng, S, e_si, t.pow_groups, s_inv);
     if (n_SI < 0) return false;
     // did the infection draw take a uniform?  (it returns 0 without one for S = 0 or p = 0)
     const bool si_drew = S != 0 && e_si.x != 0.0;

@@ -106,22 +106,28 @@ __device__ __forceinline__ double binomial_inversion(Xoshiro &rng, int n, double
 __device__ __forceinline__ long long as_ll(double x) { return __double_as_longlong(x); }
 
 // pow_int with the first multiplication peeled (1.0 * x == x) and the squaring
-// moved to the top of the loop: the same products in the same order.  The
-// conditional product is one predicated DMUL.
+// moved to the top of the loop: the same products in the same order (a product
+// by a square the count has no bit for is skipped, as pow_int never forms it).
+// The conditional product is one predicated DMUL.
 __device__ __forceinline__ void mul_if(double &acc, double x, int bit) {
   asm("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p mul.rn.f64 %0, %0, %1;\n\t}"
       : "+d"(acc) : "d"(x), "r"(bit));
 }
-__device__ __forceinline__ double pow_int_lean(double x, int n) {
+// `groups`: how many groups of three bits beyond bit 0 the largest count can have
+// (warp-uniform, from the table size): the loop runs on it, not on the lane's n,
+// so there is no per-lane loop control.  Squarings past a lane's top bit are
+// computed and never multiplied in.
+__device__ __forceinline__ double pow_int_lean(double x, int n, int groups) {
   double acc = (n & 1) ? x : 1.0;
-  n >>= 1;
-  while (n != 0) {
-    x *= x;
-    mul_if(acc, x, n & 1);
-    if ((n >> 1) == 0) break;
+#pragma unroll 1
+  for (int g = 0; g < groups; ++g) {
     x *= x;
     mul_if(acc, x, n & 2);
-    n >>= 2;
+    x *= x;
+    mul_if(acc, x, n & 4);
+    x *= x;
+    mul_if(acc, x, n & 8);
+    n >>= 3;
   }
   return acc;
 }
@@ -265,15 +271,25 @@ __device__ __forceinline__ int draw_binomial_table(Xoshiro &rng, const double *_
   double u = xo_real<SCR>(rng);
   int k = 0;
   for (;;) {
-    const bool c0 = u >= F.x;
-    u -= F.x;
-    const bool c1 = c0 & (u >= F.y);
-    u -= F.y;
-    const bool c2 = c1 & (u >= F.z);
-    u -= F.z;
-    const bool c3 = c2 & (u >= F.w);
-    u -= F.w;
-    k += (int)c0 + (int)c1 + (int)c2 + (int)c3;
+    // four steps of the chain: k counts the leading steps that go on (u >= f_k),
+    // each comparison and-ed with the one before inside the DSETP itself
+    int c3;
+    asm("{\n\t.reg .pred p0, p1, p2, p3;\n\t"
+        "setp.ge.f64 p0, %1, %3;\n\t"
+        "sub.rn.f64 %1, %1, %3;\n\t"
+        "setp.ge.and.f64 p1, %1, %4, p0;\n\t"
+        "sub.rn.f64 %1, %1, %4;\n\t"
+        "setp.ge.and.f64 p2, %1, %5, p1;\n\t"
+        "sub.rn.f64 %1, %1, %5;\n\t"
+        "setp.ge.and.f64 p3, %1, %6, p2;\n\t"
+        "sub.rn.f64 %1, %1, %6;\n\t"
+        "@p0 add.s32 %0, %0, 1;\n\t"
+        "@p1 add.s32 %0, %0, 1;\n\t"
+        "@p2 add.s32 %0, %0, 1;\n\t"
+        "@p3 add.s32 %0, %0, 1;\n\t"
+        "selp.s32 %2, 1, 0, p3;\n\t}"
+        : "+r"(k), "+d"(u), "=r"(c3)
+        : "d"(F.x), "d"(F.y), "d"(F.z), "d"(F.w));
     if (!c3) break;
     if (k == kWalkK) {
       xo_rewind(rng);
