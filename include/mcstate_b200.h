@@ -59,6 +59,10 @@ int mcb_model_lookup(const char *name, int *model_id, size_t *n_state, size_t *n
 const char *mcb_model_par_name(int model_id, size_t i);
 double mcb_model_par_default(int model_id, size_t i);
 const char *mcb_model_state_name(int model_id, size_t i);
+/* name of data field i (the column the compiled compare reads: "incidence" for
+ * sir/sirs -- tests/testthat/helper-mcstate.R:37 -- "observed" for volatility,
+ * helper-mcstate.R:107) */
+const char *mcb_model_data_name(int model_id, size_t i);
 
 /* ---- RNG state arithmetic on the host (pure seeding plumbing) ----------- */
 /* dust::dust_rng$new(seed): integer seed -> first stream */

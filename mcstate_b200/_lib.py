@@ -43,6 +43,7 @@ SIGNATURES = {
     "mcb_model_par_name": (C.c_char_p, [C.c_int, C.c_size_t]),
     "mcb_model_par_default": (C.c_double, [C.c_int, C.c_size_t]),
     "mcb_model_state_name": (C.c_char_p, [C.c_int, C.c_size_t]),
+    "mcb_model_data_name": (C.c_char_p, [C.c_int, C.c_size_t]),
     "mcb_rng_seed": (C.c_int, [C.c_uint64, u64p]),
     "mcb_rng_jump": (C.c_int, [u64p]),
     "mcb_rng_long_jump": (C.c_int, [u64p]),

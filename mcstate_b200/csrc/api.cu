@@ -49,6 +49,7 @@ struct ModelDesc {
   const char *par_names[mcb::kMaxPar];
   double par_defaults[mcb::kMaxPar];
   const char *state_names[mcb::kMaxState];
+  const char *data_names[2];
 };
 
 // defaults: scripts/generate_vignette_data.R:11-12, tests/testthat/helper-mcstate.R:11-15
@@ -56,12 +57,29 @@ const ModelDesc kModels[] = {
     {"sir", 5, 7, 1,
      {"beta", "gamma", "I0", "exp_noise", "S0", "R0", "freq"},
      {0.2, 0.1, 10.0, 1e6, 1000.0, 0.0, 4.0},
-     {"S", "I", "R", "cases_cumul", "cases_inc"}},
+     {"S", "I", "R", "cases_cumul", "cases_inc"},
+     {"incidence"}},
     {"sirs", 4, 8, 1,
      {"alpha", "beta", "gamma", "I0", "exp_noise", "S0", "R0", "freq"},
      {0.1, 0.2, 0.1, 10.0, 1e6, 1000.0, 0.0, 4.0},
-     {"S", "I", "R", "cases_inc"}},
+     {"S", "I", "R", "cases_inc"},
+     {"incidence"}},
+    // tests/testthat/helper-mcstate.R:99
+    {"volatility", 1, 5, 1,
+     {"alpha", "sigma", "gamma", "tau", "x0"},
+     {0.91, 1.0, 1.0, 1.0, 0.0},
+     {"x"},
+     {"observed"}},
 };
+// parameter slots of the closed population (S0, I0, R0) of a compartmental model, or
+// none; draws with a parameter-only probability (walk tables)
+struct ModelTables {
+  int pop[3];
+  int n_const;
+};
+const ModelTables kModelTables[] = {{{4, 2, 5}, mcb::SirModel::kConst},
+                                    {{5, 3, 6}, mcb::SirsModel::kConst},
+                                    {{-1, -1, -1}, 0}};
 constexpr int kNumModels = sizeof(kModels) / sizeof(kModels[0]);
 constexpr size_t kMaxWalkRows = 2048;  // counts covered by a walk table (samplers.cuh)
 
@@ -253,7 +271,9 @@ void run_compare(mcb_model *m, const double *y_in, double *y_out, uint64_t t0, u
     case 0: launch_run_compare<mcb::SirModel, 0>(m, y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out); break;
     case 1: launch_run_compare<mcb::SirModel, 1>(m, y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out); break;
     case 2: launch_run_compare<mcb::SirsModel, 0>(m, y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out); break;
-    default: launch_run_compare<mcb::SirsModel, 1>(m, y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out); break;
+    case 3: launch_run_compare<mcb::SirsModel, 1>(m, y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out); break;
+    case 4: launch_run_compare<mcb::VolatilityModel, 0>(m, y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out); break;
+    default: launch_run_compare<mcb::VolatilityModel, 1>(m, y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out); break;
   }
 }
 
@@ -268,8 +288,10 @@ void resample_gather(mcb_model *m, int row, const double *src, double *dst, int 
   const unsigned grid = blocks_for(m->v.n_total, mcb::kGatherThreads);
   if (m->v.n_state == 5)
     mcb::k_resample_gather<5><<<grid, mcb::kGatherThreads, 0, m->stream>>>(m->v, row, src, dst, kappa_out);
-  else
+  else if (m->v.n_state == 4)
     mcb::k_resample_gather<4><<<grid, mcb::kGatherThreads, 0, m->stream>>>(m->v, row, src, dst, kappa_out);
+  else
+    mcb::k_resample_gather<1><<<grid, mcb::kGatherThreads, 0, m->stream>>>(m->v, row, src, dst, kappa_out);
   ++m->launches;
 }
 
@@ -277,24 +299,28 @@ void finish_state(mcb_model *m, int last, int last_weighted, int *kappa_out) {
   const unsigned grid = blocks_for(m->v.n_total, mcb::kGatherThreads);
   if (m->v.n_state == 5)
     mcb::k_finish_state<5><<<grid, mcb::kGatherThreads, 0, m->stream>>>(m->v, last, last_weighted, kappa_out);
-  else
+  else if (m->v.n_state == 4)
     mcb::k_finish_state<4><<<grid, mcb::kGatherThreads, 0, m->stream>>>(m->v, last, last_weighted, kappa_out);
+  else
+    mcb::k_finish_state<1><<<grid, mcb::kGatherThreads, 0, m->stream>>>(m->v, last, last_weighted, kappa_out);
   ++m->launches;
 }
 
 void prepare_sets(mcb_model *m) {
-  const int n_const = m->model_id == 0 ? mcb::SirModel::kConst : mcb::SirsModel::kConst;
-  const dim3 grid(blocks_for((size_t)m->v.n_tab + (size_t)n_const * m->v.n_wrows, 128),
-                  (unsigned)m->v.n_sets);
+  const int n_const = kModelTables[m->model_id].n_const;
+  const size_t rows = n_const ? (size_t)m->v.n_tab + (size_t)n_const * m->v.n_wrows : 1;
+  const dim3 grid(blocks_for(rows, 128), (unsigned)m->v.n_sets);
   if (m->model_id == 0) mcb::k_prepare_sets<mcb::SirModel><<<grid, 128, 0, m->stream>>>(m->v);
-  else mcb::k_prepare_sets<mcb::SirsModel><<<grid, 128, 0, m->stream>>>(m->v);
+  else if (m->model_id == 1) mcb::k_prepare_sets<mcb::SirsModel><<<grid, 128, 0, m->stream>>>(m->v);
+  else mcb::k_prepare_sets<mcb::VolatilityModel><<<grid, 128, 0, m->stream>>>(m->v);
   ++m->launches;
 }
 
 void set_initial(mcb_model *m) {
   const unsigned grid = blocks_for(m->v.n_total, 256);
   if (m->model_id == 0) mcb::k_set_initial<mcb::SirModel><<<grid, 256, 0, m->stream>>>(m->v);
-  else mcb::k_set_initial<mcb::SirsModel><<<grid, 256, 0, m->stream>>>(m->v);
+  else if (m->model_id == 1) mcb::k_set_initial<mcb::SirsModel><<<grid, 256, 0, m->stream>>>(m->v);
+  else mcb::k_set_initial<mcb::VolatilityModel><<<grid, 256, 0, m->stream>>>(m->v);
   ++m->launches;
 }
 
@@ -585,6 +611,10 @@ double mcb_model_par_default(int model_id, size_t i) {
   if (model_id < 0 || model_id >= kNumModels || i >= (size_t)kModels[model_id].n_par) return NAN;
   return kModels[model_id].par_defaults[i];
 }
+const char *mcb_model_data_name(int model_id, size_t i) {
+  if (model_id < 0 || model_id >= kNumModels || i >= (size_t)kModels[model_id].n_data) return nullptr;
+  return kModels[model_id].data_names[i];
+}
 const char *mcb_model_state_name(int model_id, size_t i) {
   if (model_id < 0 || model_id >= kNumModels || i >= (size_t)kModels[model_id].n_state) return nullptr;
   return kModels[model_id].state_names[i];
@@ -705,12 +735,13 @@ int mcb_alloc_ex(int model_id, const double *pars, size_t n_particles, size_t n_
     const int np = m->desc->n_par;
     for (size_t p = 0; p < n_sets; ++p) {
       const double *pp = pars + p * np;
-      const double pop = model_id == 0 ? pp[4] + pp[2] + pp[5] : pp[5] + pp[3] + pp[6];
+      const int *ix = kModelTables[model_id].pop;
+      const double pop = ix[0] < 0 ? 0.0 : pp[ix[0]] + pp[ix[1]] + pp[ix[2]];
       if (pop > max_pop) max_pop = pop;
     }
     size_t n_tab = max_pop < 65535.0 ? (size_t)max_pop + 1 : 65536;
     n_tab = round_up(n_tab < 256 ? 256 : n_tab, 256);
-    const size_t n_const = model_id == 0 ? mcb::SirModel::kConst : mcb::SirsModel::kConst;
+    const size_t n_const = (size_t)kModelTables[model_id].n_const;
     const size_t row_bytes = (2 + n_const * mcb::kWalkK) * sizeof(double);
     const size_t budget = ((size_t)1 << 30) / (n_sets * row_bytes);
     if (n_tab > budget) n_tab = budget / 256 * 256;
@@ -721,7 +752,7 @@ int mcb_alloc_ex(int model_id, const double *pars, size_t n_particles, size_t n_
   }
   ALLOC(v.derived, n_sets * mcb::kMaxDerived * sizeof(double));
   ALLOC(v.tab_inf, n_sets * (size_t)v.n_tab * sizeof(double2));
-  ALLOC(v.tab_walk, n_sets * (size_t)m->n_const * v.n_wrows * mcb::kWalkK * sizeof(double));
+  ALLOC(v.tab_walk, n_sets * (size_t)(m->n_const ? m->n_const : 1) * v.n_wrows * mcb::kWalkK * sizeof(double));
   ALLOC(v.logw, v.ld * sizeof(double));
   ALLOC(v.cw, v.ld * sizeof(unsigned long long));
   ALLOC(v.tile_incl, n_sets * v.tiles_per_set * sizeof(unsigned long long));

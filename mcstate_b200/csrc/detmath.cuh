@@ -91,4 +91,39 @@ __device__ __forceinline__ double det_log(double x) {
   return s * (hfsq + R) + dk * c_log_ln2[0] - hfsq + f + dk * c_log_ln2[1];
 }
 
+// cos(2 pi u) for u in [0, 1).  Exact reduction: x = 4u = q + r (quadrant q, r in
+// [0, 1)), r <- 1 - r above one half, so only a = (pi/2) r in [0, pi/4] is
+// rounded; then the fdlibm kernel polynomials for sin and cos with explicit fma.
+// cos(pi/2 (q + r)) = {cos, -sin, -cos, sin}(pi/2 r) for q = 0..3.
+__constant__ double c_sin_poly[6] = {1.58969099521155010221e-10, -2.50507602534068634195e-08,
+                                     2.75573137070700676789e-06, -1.98412698298579493134e-04,
+                                     8.33333333332248946124e-03, -1.66666666666666324348e-01};
+__constant__ double c_cos_poly[6] = {-1.13596475577881948265e-11, 2.08757232129817482790e-09,
+                                     -2.75573143513906633035e-07, 2.48015872894767294178e-05,
+                                     -1.38888888888741095749e-03, 4.16666666666666019037e-02};
+__device__ __forceinline__ double det_cos2pi(double u) {
+  const double x = 4.0 * u;
+  const double qd = floor(x);
+  double r = x - qd;
+  const int q = (int)qd;
+  const bool swap = r > 0.5;
+  if (swap) r = 1.0 - r;
+  const double a = r * 1.57079632679489661923;
+  const double z = a * a;
+  const bool use_sin = ((q & 1) != 0) != swap;
+  double val;
+  if (use_sin) {
+    double t = fma(z, c_sin_poly[0], c_sin_poly[1]);
+#pragma unroll
+    for (int j = 2; j < 6; ++j) t = fma(z, t, c_sin_poly[j]);
+    val = fma(z * a, t, a);
+  } else {
+    double t = fma(z, c_cos_poly[0], c_cos_poly[1]);
+#pragma unroll
+    for (int j = 2; j < 6; ++j) t = fma(z, t, c_cos_poly[j]);
+    val = 1.0 - (0.5 * z - z * (z * t));
+  }
+  return (q == 1 || q == 2) ? -val : val;
+}
+
 }  // namespace mcb

@@ -296,36 +296,41 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
     rng.s3 = __ldcs(v.rng + 3 * v.ld_rng + i);
 
     if (n_steps > 0) {
-      int yi[M::kLeanState];
-      typename M::Lean lc;
       uint32_t done = 0;
-      lc.set = (uint32_t)set;
-      const LeanTabs tabs{v.tab_inf, v.tab_walk, (uint32_t)v.n_tab, (uint32_t)v.n_wrows,
-                          (32 - __clz(v.n_tab - 1) + 1) / 3};
-      if (!det && M::lean_load(sd, y, yi, lc)) {
-        // the usual case: integer compartments, setup from the memo tables, no calls
-        const uint32_t s_inv_addr = (uint32_t)__cvta_generic_to_shared(s_inv);
-        const uint32_t freq = (uint32_t)__ldg(sd.derived + M::D_FREQ);
-        uint32_t phase = t0 <= 0xffffffffULL ? (uint32_t)t0 % freq : (uint32_t)(t0 % freq);
-        bool ok = true;
-        while (ok && done < n_steps) {
-          // bit k: step done + k starts a new incidence interval
-          const uint32_t nk = min(n_steps - done, 32u);
-          uint32_t resets = 0;
-          for (uint32_t k = 0; k < nk; ++k) {
-            resets |= (phase == 0 ? 1u : 0u) << k;
-            phase = phase + 1 == freq ? 0 : phase + 1;
+      if constexpr (M::kHasLean) {
+        int yi[M::kLeanState];
+        typename M::Lean lc;
+        lc.set = (uint32_t)set;
+        const LeanTabs tabs{v.tab_inf, v.tab_walk, (uint32_t)v.n_tab, (uint32_t)v.n_wrows,
+                            (32 - __clz(v.n_tab - 1) + 1) / 3};
+        if (!det && M::lean_load(sd, y, yi, lc)) {
+          // the usual case: integer compartments, setup from the memo tables, no calls
+          const uint32_t s_inv_addr = (uint32_t)__cvta_generic_to_shared(s_inv);
+          const uint32_t freq = (uint32_t)__ldg(sd.derived + M::D_FREQ);
+          uint32_t phase = t0 <= 0xffffffffULL ? (uint32_t)t0 % freq : (uint32_t)(t0 % freq);
+          bool ok = true;
+          while (ok && done < n_steps) {
+            // bit k: step done + k starts a new incidence interval
+            const uint32_t nk = min(n_steps - done, 32u);
+            uint32_t resets = 0;
+            for (uint32_t k = 0; k < nk; ++k) {
+              resets |= (phase == 0 ? 1u : 0u) << k;
+              phase = phase + 1 == freq ? 0 : phase + 1;
+            }
+            for (uint32_t k = 0; k < nk; ++k) {
+              ok = M::template lean_update<SCR>((resets & 1u) != 0, yi, rng, lc, tabs, s_inv_addr);
+              if (!ok) break;
+              resets >>= 1;
+              ++done;
+            }
           }
-          for (uint32_t k = 0; k < nk; ++k) {
-            ok = M::template lean_update<SCR>((resets & 1u) != 0, yi, rng, lc, tabs, s_inv_addr);
-            if (!ok) break;
-            resets >>= 1;
-            ++done;
-          }
+          M::lean_store(sd, yi, y);
         }
-        M::lean_store(sd, yi, y);
       }
-      if (done < n_steps) {  // whatever the lean path did not take
+      if constexpr (!M::kHasLean) {
+        // a model without integer compartments has one form only: inline
+        for (uint32_t k = 0; k < n_steps; ++k) M::template update<SCR>(t0 + k, y, rng, ctx, det);
+      } else if (done < n_steps) {  // whatever the lean path did not take
         uint64_t rs[4] = {rng.s0, rng.s1, rng.s2, rng.s3};
         run_general<M, SCR>(y, rs, t0 + done, n_steps - done, sd.derived, sd.n_tab, det);
         rng.s0 = rs[0]; rng.s1 = rs[1]; rng.s2 = rs[2]; rng.s3 = rs[3];
@@ -714,11 +719,13 @@ __global__ void k_prepare_sets(View v) {
     for (int k = 0; k < kMaxDerived; ++k) v.derived[set * kMaxDerived + k] = d[k];
   }
   // one thread per entry or row: n_tab infection entries, then kConst x n_wrows walk rows
-  if (e < v.n_tab) {
-    v.tab_inf[set * (size_t)v.n_tab + e] = M::inf_entry(e, d);
-  } else if (e - v.n_tab < M::kConst * v.n_wrows) {
-    const int w = e - v.n_tab, c = w / v.n_wrows, n = w - c * v.n_wrows;
-    M::walk_row(c, n, d, v.tab_walk + ((set * M::kConst + c) * (size_t)v.n_wrows + n) * kWalkK);
+  if constexpr (M::kHasLean) {
+    if (e < v.n_tab) {
+      v.tab_inf[set * (size_t)v.n_tab + e] = M::inf_entry(e, d);
+    } else if (e - v.n_tab < M::kConst * v.n_wrows) {
+      const int w = e - v.n_tab, c = w / v.n_wrows, n = w - c * v.n_wrows;
+      M::walk_row(c, n, d, v.tab_walk + ((set * M::kConst + c) * (size_t)v.n_wrows + n) * kWalkK);
+    }
   }
 }
 

@@ -101,6 +101,7 @@ __device__ __forceinline__ int draw_const_lean(Xoshiro &rng, int n, uint32_t set
 }
 
 struct SirModel {
+  static constexpr bool kHasLean = true;
   static constexpr int kState = 5;
   static constexpr int kPar = 7;  // beta gamma I0 exp_noise S0 R0 freq
   static constexpr int kData = 1; // incidence
@@ -231,6 +232,7 @@ struct SirModel {
 };
 
 struct SirsModel {
+  static constexpr bool kHasLean = true;
   static constexpr int kState = 4;
   static constexpr int kPar = 8;  // alpha beta gamma I0 exp_noise S0 R0 freq
   static constexpr int kData = 1;
@@ -355,6 +357,50 @@ struct SirsModel {
     y[2] = R + n_IR - n_RS;
     y[3] = reset ? n_SI : y[3] + n_SI;
     return true;
+  }
+};
+
+// dust::dust_example("volatility") (tests/testthat/helper-mcstate.R:98-146): one
+// real-valued state, x' = alpha x + sigma N(0, 1), observed ~ N(gamma x, tau).
+// Linear and Gaussian, so the Kalman filter gives the exact likelihood the
+// particle filter estimates (helper-mcstate.R:116-142, test-if2.R:35-64).  No
+// integer compartments: there is no lean path and no memo table.
+struct VolatilityModel {
+  static constexpr bool kHasLean = false;
+  static constexpr int kState = 1;
+  static constexpr int kPar = 5;  // alpha sigma gamma tau x0
+  static constexpr int kData = 1; // observed
+  static constexpr int kConst = 0;
+  enum { D_ALPHA, D_SIGMA, D_GAMMA, D_TAU, D_LOG_TAU };
+
+  __device__ __forceinline__ static void derive(const double *__restrict__ p, double *d) {
+    d[D_ALPHA] = p[0];
+    d[D_SIGMA] = p[1];
+    d[D_GAMMA] = p[2];
+    d[D_TAU] = p[3];
+    d[D_LOG_TAU] = det_log(p[3]);
+  }
+  struct Ctx {
+    double alpha, sigma, gamma, tau, log_tau;
+  };
+  __device__ __forceinline__ static Ctx context(const SetData &sd) {
+    const double *d = sd.derived;
+    return Ctx{__ldg(d + D_ALPHA), __ldg(d + D_SIGMA), __ldg(d + D_GAMMA), __ldg(d + D_TAU),
+               __ldg(d + D_LOG_TAU)};
+  }
+  __device__ __forceinline__ static void initial(const double *__restrict__ p, double *y) {
+    y[0] = __ldg(p + 4);
+  }
+  template <int SCR>
+  __device__ __forceinline__ static void update(uint64_t, double *y, Xoshiro &rng, const Ctx &c,
+                                                bool det) {
+    const double z = det ? 0.0 : draw_normal<SCR>(rng, 0.0, 1.0);
+    y[0] = c.alpha * y[0] + c.sigma * z;
+  }
+  template <int SCR>
+  __device__ __forceinline__ static double compare(const double *y, double observed, double,
+                                                   Xoshiro &, const Ctx &c, bool) {
+    return density_normal_log(observed, c.gamma * y[0], c.tau, c.log_tau);
   }
 };
 

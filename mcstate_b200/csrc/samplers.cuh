@@ -17,6 +17,26 @@ __device__ __forceinline__ double draw_exponential(Xoshiro &r, double rate) {
   return -det_log(xo_real<SCR>(r)) / rate;
 }
 
+// Box-Muller, first variate only; a uniform at or below machine epsilon is drawn
+// again (both of the pair) so log never sees it.  sqrt is IEEE (correctly rounded).
+template <int SCR>
+__device__ __forceinline__ double draw_normal(Xoshiro &r, double mean, double sd) {
+  double u1, u2;
+  do {
+    u1 = xo_real<SCR>(r);
+    u2 = xo_real<SCR>(r);
+  } while (u1 <= 2.220446049250313e-16);
+  const double z = __dsqrt_rn(-2.0 * det_log(u1)) * det_cos2pi(u2);
+  return z * sd + mean;
+}
+
+// dnorm(x, mu, sd, log = TRUE); log_sd = det_log(sd), prepared per parameter set
+__device__ __forceinline__ double density_normal_log(double x, double mu, double sd,
+                                                     double log_sd) {
+  const double dx = x - mu;
+  return -(dx * dx) / (2.0 * sd * sd) - 0.918938533204672741780329736406 - log_sd;
+}
+
 // x^n by squaring, multiplying in the low bits first (not pow())
 __device__ __forceinline__ double pow_int(double x, int n) {
   double acc = 1.0;

@@ -488,7 +488,7 @@ class dust_generator:
         self.par_names = [L.mcb_model_par_name(mid.value, i).decode() for i in range(npar.value)]
         self.par_defaults = [L.mcb_model_par_default(mid.value, i) for i in range(npar.value)]
         self.state_names = [L.mcb_model_state_name(mid.value, i).decode() for i in range(ns.value)]
-        self.data_fields = ["incidence"]
+        self.data_fields = [L.mcb_model_data_name(mid.value, i).decode() for i in range(nd.value)]
         self.public_methods = self  # R: model$public_methods$has_compare()
 
     # -- static capability queries

@@ -200,9 +200,60 @@ double orc_log(double x) {
          dk * 6.93147180369123816490e-01;
 }
 
+/* cos(2 pi u) for u in [0, 1).  The reduction is exact: x = 4u = q + r with q the
+ * quadrant and r in [0, 1), r <- 1 - r above one half, so only a = (pi/2) r in
+ * [0, pi/4] is rounded; then the fdlibm kernel polynomials for sin and cos, written
+ * with explicit fma.  cos(pi/2 (q + r)) = {cos, -sin, -cos, sin}(pi/2 r) for q = 0..3. */
+double orc_cos2pi(double u) {
+  const double x = 4.0 * u;
+  const double qd = floor(x);
+  double r = x - qd;
+  const int q = (int)qd;
+  const int swap = r > 0.5;
+  if (swap) r = 1.0 - r;
+  const double a = r * 1.57079632679489661923;
+  const double z = a * a;
+  const int use_sin = (q & 1) ^ swap;
+  double val;
+  if (use_sin) {
+    double t = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    t = fma(z, t, 2.75573137070700676789e-06);
+    t = fma(z, t, -1.98412698298579493134e-04);
+    t = fma(z, t, 8.33333333332248946124e-03);
+    t = fma(z, t, -1.66666666666666324348e-01);
+    val = fma(z * a, t, a);
+  } else {
+    double t = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    t = fma(z, t, -2.75573143513906633035e-07);
+    t = fma(z, t, 2.48015872894767294178e-05);
+    t = fma(z, t, -1.38888888888741095749e-03);
+    t = fma(z, t, 4.16666666666666019037e-02);
+    val = 1.0 - (0.5 * z - z * (z * t));
+  }
+  return (q == 1 || q == 2) ? -val : val;
+}
+
 /* ------------------------------------------------------------------ */
 /* Samplers and densities [dust, unverified]           */
 /* ------------------------------------------------------------------ */
+/* Box-Muller, first variate only; a uniform at or below machine epsilon is drawn
+ * again (both of the pair) so log() never sees it [dust random/normal, unverified] */
+double orc_normal(uint64_t s[4], int scrambler, double mean, double sd) {
+  double u1, u2;
+  do {
+    u1 = orc_random_real(s, scrambler);
+    u2 = orc_random_real(s, scrambler);
+  } while (u1 <= 2.220446049250313e-16);
+  const double z = sqrt(-2.0 * orc_log(u1)) * orc_cos2pi(u2);
+  return z * sd + mean;
+}
+
+/* dnorm(x, mu, sd, log = TRUE) = -(x - mu)^2 / (2 sd^2) - log(sqrt(2 pi)) - log(sd) */
+double orc_density_normal_log(double x, double mu, double sd) {
+  const double dx = x - mu;
+  return -(dx * dx) / (2.0 * sd * sd) - 0.918938533204672741780329736406 - orc_log(sd);
+}
+
 double orc_exponential(uint64_t s[4], int scrambler, double rate) {
   return -orc_log(orc_random_real(s, scrambler)) / rate;
 }
@@ -471,29 +522,41 @@ void orc_history_single(const double *value, const int *order, size_t ny,
 /* parameter vectors:                                                  */
 /*   sir : beta gamma I0 exp_noise S0 R0 freq                          */
 /*   sirs: alpha beta gamma I0 exp_noise S0 R0 freq                    */
+/*   volatility: alpha sigma gamma tau x0                              */
+/*     (tests/testthat/helper-mcstate.R:98-146: x' = alpha x + sigma N(0,1),  */
+/*      observed ~ N(gamma x, tau); one real state, the Kalman filter is exact) */
 /* ------------------------------------------------------------------ */
 #define ORC_MAX_PAR 8
 #define ORC_MAX_STATE 8
 
-size_t orc_model_n_state(int model) { return model == ORC_MODEL_SIR ? 5 : 4; }
-size_t orc_model_n_par(int model) { return model == ORC_MODEL_SIR ? 7 : 8; }
+size_t orc_model_n_state(int model) {
+  return model == ORC_MODEL_SIR ? 5 : model == ORC_MODEL_SIRS ? 4 : 1;
+}
+size_t orc_model_n_par(int model) {
+  return model == ORC_MODEL_SIR ? 7 : model == ORC_MODEL_SIRS ? 8 : 5;
+}
 size_t orc_model_n_data(int model) { (void)model; return 1; }
 
 void orc_model_default_pars(int model, double *p) {
   if (model == ORC_MODEL_SIR) {
     /* scripts/generate_vignette_data.R:11-12, tests/testthat/helper-mcstate.R:11-15 */
     p[0] = 0.2; p[1] = 0.1; p[2] = 10.0; p[3] = 1e6; p[4] = 1000.0; p[5] = 0.0; p[6] = 4.0;
-  } else {
+  } else if (model == ORC_MODEL_SIRS) {
     p[0] = 0.1; p[1] = 0.2; p[2] = 0.1; p[3] = 10.0; p[4] = 1e6; p[5] = 1000.0;
     p[6] = 0.0; p[7] = 4.0;
+  } else {
+    /* tests/testthat/helper-mcstate.R:99 */
+    p[0] = 0.91; p[1] = 1.0; p[2] = 1.0; p[3] = 1.0; p[4] = 0.0;
   }
 }
 
 static void model_initial(int model, const double *p, double *y) {
   if (model == ORC_MODEL_SIR) {
     y[0] = p[4]; y[1] = p[2]; y[2] = p[5]; y[3] = 0.0; y[4] = 0.0;
-  } else {
+  } else if (model == ORC_MODEL_SIRS) {
     y[0] = p[5]; y[1] = p[3]; y[2] = p[6]; y[3] = 0.0;
+  } else {
+    y[0] = p[4];
   }
 }
 
@@ -535,11 +598,19 @@ static void sirs_update(uint64_t time, const double *y, uint64_t s[4], int scr, 
   yn[3] = (time % (uint64_t)freq == 0) ? n_SI : y[3] + n_SI;
 }
 
+/* x' = alpha x + sigma N(0, 1); deterministic mode puts the mean in place of the draw */
+static void volatility_update(const double *y, uint64_t s[4], int scr, int det, const double *p,
+                              double *yn) {
+  const double z = det ? 0.0 : orc_normal(s, scr, 0.0, 1.0);
+  yn[0] = p[0] * y[0] + p[1] * z;
+}
+
 void orc_model_update(int model, uint64_t time, const double *y, uint64_t s[4],
                       int scrambler, int deterministic, const double *pars,
                       double *y_next) {
   if (model == ORC_MODEL_SIR) sir_update(time, y, s, scrambler, deterministic, pars, y_next);
-  else sirs_update(time, y, s, scrambler, deterministic, pars, y_next);
+  else if (model == ORC_MODEL_SIRS) sirs_update(time, y, s, scrambler, deterministic, pars, y_next);
+  else volatility_update(y, s, scrambler, deterministic, pars, y_next);
 }
 
 /* tests/testthat/helper-mcstate.R:7-22 (R twin): Poisson density of the
@@ -547,6 +618,7 @@ void orc_model_update(int model, uint64_t time, const double *y, uint64_t s[4],
  * from the particle's own stream. datum = {incidence, lgamma(incidence+1)} */
 static double model_compare(int model, const double *y, const double *datum,
                             uint64_t s[4], int scr, int det, const double *p) {
+  if (model == ORC_MODEL_VOLATILITY) return orc_density_normal_log(datum[0], p[2] * y[0], p[3]);
   const double modelled = model == ORC_MODEL_SIR ? y[4] : y[3];
   const double rate = model == ORC_MODEL_SIR ? p[3] : p[4];
   const double noise = det ? 1.0 / rate : orc_exponential(s, scr, rate);

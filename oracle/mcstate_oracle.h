@@ -31,7 +31,7 @@ extern "C" {
 #endif
 
 enum { ORC_SCRAMBLER_PLUS = 0, ORC_SCRAMBLER_STARSTAR = 1 };
-enum { ORC_MODEL_SIR = 0, ORC_MODEL_SIRS = 1 };
+enum { ORC_MODEL_SIR = 0, ORC_MODEL_SIRS = 1, ORC_MODEL_VOLATILITY = 2 };
 /* how sum(w) and the cumulative sum are accumulated when resampling */
 enum {
   ORC_RESAMPLE_DUST_FP64 = 0, /* left-to-right fp64, as dust's resample_weight   */
@@ -58,6 +58,9 @@ double orc_log(double x);
 
 /* ---- samplers and densities ---- */
 double orc_exponential(uint64_t s[4], int scrambler, double rate);
+double orc_cos2pi(double u);
+double orc_normal(uint64_t s[4], int scrambler, double mean, double sd);
+double orc_density_normal_log(double x, double mu, double sd);
 double orc_binomial(uint64_t s[4], int scrambler, double n, double p);
 double orc_poisson(uint64_t s[4], int scrambler, double lambda);
 double orc_density_poisson_log(double x, double lgamma_x1, double lambda);

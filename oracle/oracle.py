@@ -21,7 +21,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libmcstate_oracle.so")
 
 PLUS, STARSTAR = 0, 1
-SIR, SIRS = 0, 1
+SIR, SIRS, VOLATILITY = 0, 1, 2
 DUST_FP64, EXACT = 0, 1
 
 _u64p = C.POINTER(C.c_uint64)
@@ -73,6 +73,9 @@ def lib():
         "orc_exp": (C.c_double, [C.c_double]),
         "orc_log": (C.c_double, [C.c_double]),
         "orc_exponential": (C.c_double, [_u64p, C.c_int, C.c_double]),
+        "orc_cos2pi": (C.c_double, [C.c_double]),
+        "orc_normal": (C.c_double, [_u64p, C.c_int, C.c_double, C.c_double]),
+        "orc_density_normal_log": (C.c_double, [C.c_double, C.c_double, C.c_double]),
         "orc_binomial": (C.c_double, [_u64p, C.c_int, C.c_double, C.c_double]),
         "orc_poisson": (C.c_double, [_u64p, C.c_int, C.c_double]),
         "orc_density_poisson_log": (C.c_double, [C.c_double, C.c_double, C.c_double]),

@@ -11,9 +11,12 @@ import numpy as np
 from oracle import oracle as O
 
 PAR_NAMES = {O.SIR: ["beta", "gamma", "I0", "exp_noise", "S0", "R0", "freq"],
-             O.SIRS: ["alpha", "beta", "gamma", "I0", "exp_noise", "S0", "R0", "freq"]}
+             O.SIRS: ["alpha", "beta", "gamma", "I0", "exp_noise", "S0", "R0", "freq"],
+             O.VOLATILITY: ["alpha", "sigma", "gamma", "tau", "x0"]}
 STATE_NAMES = {O.SIR: ["S", "I", "R", "cases_cumul", "cases_inc"],
-               O.SIRS: ["S", "I", "R", "cases_inc"]}
+               O.SIRS: ["S", "I", "R", "cases_inc"],
+               O.VOLATILITY: ["x"]}
+DATA_FIELD = {O.SIR: "incidence", O.SIRS: "incidence", O.VOLATILITY: "observed"}
 
 
 def _seed_words(seed):
@@ -118,8 +121,8 @@ class OracleDustModel:
     def set_data(self, data, shared=False):
         n_sets = 1 if shared or not self._multi else self._n_sets
         t = np.array([d[0] for d in data], dtype=np.uint64)
-        v = np.array([[np.nan if r["incidence"] is None else float(r["incidence"]) for r in d[1]]
-                      for d in data])
+        f = DATA_FIELD[self._gen.model_id]
+        v = np.array([[np.nan if r[f] is None else float(r[f]) for r in d[1]] for d in data])
         assert v.shape == (len(data), n_sets)
         self._o.set_data(t, v, shared=bool(shared))
         self._times = t
@@ -201,7 +204,7 @@ class OracleGenerator:
     name = "dust_generator"
 
     def __init__(self, model_name="sir", algorithm="xoshiro256plus"):
-        self.model_id = {"sir": O.SIR, "sirs": O.SIRS}[model_name]
+        self.model_id = {"sir": O.SIR, "sirs": O.SIRS, "volatility": O.VOLATILITY}[model_name]
         self.scrambler = {"xoshiro256plus": O.PLUS, "xoshiro256starstar": O.STARSTAR}[algorithm]
         self.par_names = PAR_NAMES[self.model_id]
         self.par_defaults = list(O.default_pars(self.model_id))
