@@ -193,6 +193,19 @@ int mcb_filter(mcb_model *m, uint64_t time_end, int save_trajectories,
                const uint64_t *snapshot_times, size_t n_snapshots,
                const double *min_log_likelihood, size_t n_min,
                double *log_likelihood, double *trajectories, double *snapshots);
+
+/* save_trajectories = MCB_TRAJECTORIES_ON_DEVICE: record the history (values and
+ * ancestor order) but leave it in device memory; `trajectories` is ignored.  Then
+ * mcb_filter_history traces the lineages of chosen final particles on the device
+ * and returns only those: out [n_rows+1][n][n_index] (same layout as
+ * `trajectories`, with n particles in place of n_total).  This is what pMCMC
+ * consumes of a run -- one sampled particle: R/pmcmc_state.R:32-51 calls
+ * filter$history(i), i.e. history_single(.., index_particle),
+ * R/particle_filter.R:616-646 -- without moving the [n_index, n_total, T+1]
+ * array (2.5 GB at 2^20 particles) across PCIe.  `particles`: 0-based indices
+ * into n_total (set-major).  Valid until the next filter call on the handle. */
+#define MCB_TRAJECTORIES_ON_DEVICE 2
+int mcb_filter_history(mcb_model *m, const size_t *particles, size_t n, double *out);
 /* the same, split so many handles / GPUs can be in flight at once: enqueue
  * returns as soon as the work is queued, collect waits and copies out */
 int mcb_filter_enqueue(mcb_model *m, uint64_t time_end);

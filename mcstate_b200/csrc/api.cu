@@ -185,6 +185,7 @@ struct mcb_model {
   double *d_hist_value = nullptr;
   int *d_hist_order = nullptr;
   double *d_traj = nullptr;
+  int hist_rows = -1, hist_first = 0;  // rows of the history held on the device, or -1
   double *d_snap = nullptr;
   size_t hist_rows_cap = 0, hist_index_cap = 0, snap_cap = 0;
 
@@ -458,7 +459,6 @@ int prepare_history(mcb_model *m, int rows) {
     const size_t T1 = (size_t)rows + 1;
     MCB_CUDA(cudaMalloc(&m->d_hist_value, T1 * v.n_index * v.ld * sizeof(double)));
     MCB_CUDA(cudaMalloc(&m->d_hist_order, T1 * v.n_total * sizeof(int)));
-    MCB_CUDA(cudaMalloc(&m->d_traj, T1 * v.n_total * v.n_index * sizeof(double)));
     m->hist_rows_cap = T1;
     m->hist_index_cap = v.n_index;
   }
@@ -535,12 +535,16 @@ int run_filter(mcb_model *m, uint64_t time_end, bool hist, const uint64_t *snaps
                            m->stream));
   MCB_CUDA(cudaMemcpyAsync(m->h_flags, m->d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost,
                            m->stream));
+  m->hist_rows = hist ? rows : -1;   // what mcb_filter_history may trace afterwards
+  m->hist_first = first;
   m->pending = true;
   m->pend_first = first;
   m->pend_last = last;
   if (!wait) return MCB_OK;
 
   if (hist && traj_out) {
+    if (!m->d_traj)
+      MCB_CUDA(cudaMalloc(&m->d_traj, m->hist_rows_cap * v.n_total * m->hist_index_cap * sizeof(double)));
     mcb::k_trace_history<<<blocks_for(v.n_total, 128), 128, 0, m->stream>>>(
         v, m->d_hist_value, m->d_hist_order, rows, first, m->d_traj);
     ++m->launches;
@@ -1221,11 +1225,40 @@ int mcb_filter(mcb_model *m, uint64_t time_end, int save_trajectories,
                const double *min_log_likelihood, size_t n_min, double *log_likelihood,
                double *trajectories, double *snapshots) {
   if (!m || !log_likelihood) return fail(MCB_ERR_ARG, "NULL argument");
-  if (save_trajectories && !trajectories) return fail(MCB_ERR_ARG, "trajectories is NULL");
+  if (save_trajectories == 1 && !trajectories) return fail(MCB_ERR_ARG, "trajectories is NULL");
+  if (save_trajectories == MCB_TRAJECTORIES_ON_DEVICE) trajectories = nullptr;
   if (n_snapshots && (!snapshot_times || !snapshots)) return fail(MCB_ERR_ARG, "snapshots is NULL");
   MCB_CUDA(cudaSetDevice(m->device));
   return run_filter(m, time_end, save_trajectories != 0, snapshot_times, n_snapshots,
                     min_log_likelihood, n_min, true, log_likelihood, trajectories, snapshots);
+}
+
+int mcb_filter_history(mcb_model *m, const size_t *particles, size_t n, double *out) {
+  if (!m || !particles || !out) return fail(MCB_ERR_ARG, "NULL argument");
+  if (m->hist_rows < 0)
+    return fail(MCB_ERR_STATE, "no history on the device: run filter with save_trajectories first");
+  if (n == 0) return MCB_OK;
+  MCB_CUDA(cudaSetDevice(m->device));
+  View &v = m->v;
+  std::vector<unsigned long long> idx(n);
+  for (size_t j = 0; j < n; ++j) {
+    if (particles[j] >= v.n_total) return fail(MCB_ERR_ARG, "particle index out of range");
+    idx[j] = particles[j];
+  }
+  const size_t T1 = (size_t)m->hist_rows + 1;
+  const size_t out_bytes = T1 * n * v.n_index * sizeof(double);
+  const size_t idx_bytes = round_up(n * sizeof(unsigned long long), 256);
+  MCB_TRY(ensure_stage(m, idx_bytes + out_bytes));
+  unsigned long long *d_idx = reinterpret_cast<unsigned long long *>(m->d_stage);
+  double *d_out = reinterpret_cast<double *>(reinterpret_cast<char *>(m->d_stage) + idx_bytes);
+  MCB_CUDA(cudaMemcpyAsync(d_idx, idx.data(), n * sizeof(unsigned long long),
+                           cudaMemcpyHostToDevice, m->stream));
+  mcb::k_trace_particles<<<blocks_for(n, 64), 64, 0, m->stream>>>(
+      v, m->d_hist_value, m->d_hist_order, m->hist_rows, m->hist_first, d_idx, n, d_out);
+  ++m->launches;
+  MCB_CUDA(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, m->stream));
+  MCB_CUDA(cudaStreamSynchronize(m->stream));
+  return MCB_OK;
 }
 
 int mcb_filter_enqueue(mcb_model *m, uint64_t time_end) {

@@ -808,6 +808,33 @@ __global__ void k_trace_history(View v, const double *__restrict__ value,
   }
 }
 
+// The same walk for a few chosen final particles (what pMCMC keeps of a run: one
+// sampled lineage, R/pmcmc_state.R:32-51): one thread per requested particle, so
+// the history stays in HBM and only n x n_index x T1 doubles leave the device.
+// out [T1][n][n_index].
+__global__ void k_trace_particles(View v, const double *__restrict__ value,
+                                  const int *__restrict__ order, int rows, int row_first,
+                                  const unsigned long long *__restrict__ particles, size_t n,
+                                  double *__restrict__ out) {
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int T1 = rows + 1;
+  const bool stopped = v.flags[0] != 0;
+  const int filled = stopped ? (v.flags[1] - row_first) + 2 : T1;
+  const double na = __longlong_as_double(0x7ff8000000000000LL);
+  size_t cur = (size_t)particles[j];
+  for (int t = T1 - 1; t >= 0; --t) {
+    double *o = out + ((size_t)t * n + j) * v.n_index;
+    if (t >= filled) {
+      for (int k = 0; k < v.n_index; ++k) o[k] = na;
+      continue;
+    }
+    if (!(stopped && t == filled - 1)) cur = (size_t)order[(size_t)t * v.n_total + cur];
+    for (int k = 0; k < v.n_index; ++k)
+      o[k] = value[((size_t)t * v.n_index + k) * v.ld + cur];
+  }
+}
+
 // stream i (i >= have) = J^(i - have + 1) applied to stream have-1, by the
 // precomputed powers J^(2^l) (rng.cuh).  The column loads are warp-uniform.
 __global__ void k_derive_streams(uint64_t *rng, size_t ld_rng, size_t have, size_t n_streams,

@@ -408,8 +408,12 @@ class dust_model:
         check(L.mcb_filter_rows(self._h, int(time_end), C.byref(n_rows)))
         ll = np.zeros(self._n_sets)
         traj = None
-        if save_trajectories:
+        on_device = isinstance(save_trajectories, str)
+        if on_device and save_trajectories != "device":
+            raise ValueError("save_trajectories must be a logical or 'device'")
+        if save_trajectories and not on_device:
             traj = np.zeros((n_rows.value + 1, self._n_total, self._n_index))
+        self._hist_rows = n_rows.value if save_trajectories else None
         snap_t, snaps = None, None
         if time_snapshot is not None and len(time_snapshot) > 0:
             snap_t = np.ascontiguousarray(time_snapshot, dtype=np.uint64)
@@ -417,7 +421,7 @@ class dust_model:
         mll = None
         if min_log_likelihood is not None:
             mll = np.ascontiguousarray(np.atleast_1d(min_log_likelihood), dtype=np.float64)
-        check(L.mcb_filter(self._h, int(time_end), int(bool(save_trajectories)),
+        check(L.mcb_filter(self._h, int(time_end), 2 if on_device else int(bool(save_trajectories)),
                            ptr(snap_t, u64p), 0 if snap_t is None else snap_t.size,
                            ptr(mll, f64p), 0 if mll is None else mll.size,
                            ptr(ll, f64p), ptr(traj, f64p), ptr(snaps, f64p)))
@@ -432,6 +436,36 @@ class dust_model:
             else:
                 snaps = snaps.transpose(2, 1, 0)
         return {"log_likelihood": ll, "trajectories": traj, "snapshots": snaps}
+
+    def filter_history(self, index_particle):
+        """Trajectories of chosen final particles of the last
+        ``filter(..., save_trajectories="device")`` (or True) call, traced on the device:
+        ``[n_index, n, T+1]``; with several parameter sets ``index_particle`` is
+        ``[n, n_pars]`` (1-based within each set) and the result ``[n_index, n, n_pars, T+1]``.
+        The 1-based indices are R's (R/particle_filter.R:616-646 history_single /
+        :653-714 history_multiple with an index)."""
+        if getattr(self, "_hist_rows", None) is None:
+            raise _lib.McbError(_lib.ERR_STATE, "filter was not run with save_trajectories")
+        ip = np.asarray(index_particle, dtype=np.int64)
+        if self._pars_multi:
+            if ip.ndim < 2:
+                ip = np.tile(np.atleast_1d(ip)[:, None], (1, self._n_sets))
+            if ip.shape[1] != self._n_sets:
+                raise ValueError("'index_particle' should have %d columns" % self._n_sets)
+            if ip.min() < 1 or ip.max() > self._n_particles:
+                raise IndexError("index_particle out of range")
+            glob = (ip - 1) + np.arange(self._n_sets)[None, :] * self._n_particles
+        else:
+            ip = np.atleast_1d(ip)
+            if ip.min() < 1 or ip.max() > self._n_particles:
+                raise IndexError("index_particle out of range")
+            glob = ip - 1
+        flat = np.ascontiguousarray(glob.ravel(), dtype=np.uintp)
+        out = np.zeros((self._hist_rows + 1, flat.size, self._n_index))
+        check(_lib.lib().mcb_filter_history(self._h, ptr(flat, szp), flat.size, ptr(out, f64p)))
+        if self._pars_multi:
+            return out.reshape(-1, glob.shape[0], self._n_sets, self._n_index).transpose(3, 1, 2, 0)
+        return out.transpose(2, 1, 0)
 
     # ---- asynchronous variant used to keep several GPUs / handles busy
     def filter_enqueue(self, time_end=None):

@@ -110,6 +110,22 @@ def check_time_step(curr, time_index, times, name):
                          % (name, time_index, times[time_index - 1, 1]))
 
 
+class _DeviceHistory:
+    """Trajectories of a compiled-filter run that stayed in device memory: lineages
+    are traced there on request (model.filter_history), so asking for one sampled
+    particle -- all that pMCMC keeps, R/pmcmc_state.R:32-51 -- moves
+    n_index x (T+1) doubles instead of the whole [n_index, N, T+1] array.  Valid
+    until the model's next filter call, like the reference's last_history."""
+
+    def __init__(self, model, n_particles, multi):
+        self._model, self._np, self._multi = model, int(n_particles), bool(multi)
+
+    def get(self, index_particle=None):
+        if index_particle is None:
+            index_particle = np.arange(1, self._np + 1)
+        return self._model.filter_history(index_particle)
+
+
 def history_single(history_value, history_order, index_particle=None):
     """R/particle_filter.R:616-646 (1-based indices)."""
     hv = np.asarray(history_value)
@@ -312,14 +328,18 @@ class particle_filter_state:
         snap = self._save_restart_time if self._save_restart_time.size else None
         # the one native call for all the intervals; min_log_likelihood is NOT forwarded,
         # as in the reference (:151)
-        res = self.model.filter(time, save_history, snap)
+        on_device = save_history and hasattr(self.model, "filter_history")
+        res = self.model.filter(time, "device" if on_device else save_history, snap)
         self.log_likelihood_step = np.nan
         ll = res["log_likelihood"]
         self.log_likelihood = self.log_likelihood + (ll if self._has_multiple_parameters else float(ll[0]))
         self.current_time_index = time_index
         if save_history:
-            self.history = {"value": res["trajectories"], "order": None,
-                            "index": self.history["index"]}
+            value = res["trajectories"]
+            if on_device:
+                value = _DeviceHistory(self.model, self._n_particles,
+                                       self._has_multiple_parameters)
+            self.history = {"value": value, "order": None, "index": self.history["index"]}
         self.restart_state = res["snapshots"]
         return self.log_likelihood
 
@@ -489,6 +509,8 @@ class particle_filter:
         if self._last_history is None:
             raise RuntimeError("Can't get history as model was run with save_history = FALSE")
         value, order = self._last_history["value"], self._last_history["order"]
+        if isinstance(value, _DeviceHistory):
+            return value.get(index_particle)
         if value.ndim == 4:
             return history_multiple(value, order, index_particle)
         return history_single(value, order, index_particle)

@@ -237,6 +237,69 @@ def test_filter_trajectories_and_snapshots(dust, orc, sir_data):
     assert np.array_equal(got["snapshots"][:, :, 2], m.state())
 
 
+def test_filter_history_of_chosen_particles_traced_on_device(dust, orc, sir_data):
+    """the history stays in HBM and single lineages are traced there
+    (history_single with an index, R/particle_filter.R:616-646; what pMCMC keeps,
+    R/pmcmc_state.R:32-51).  Same values as the full traced array."""
+    n = 1000
+    t, x = _data(sir_data, 40)
+    g = dust.dust_example("sir")
+    full = g.new({}, 0, n, seed=8)
+    lazy = g.new({}, 0, n, seed=8)
+    for m in (full, lazy):
+        _set_data(m, t, x)
+        m.set_index([1, 2, 5])
+    want = full.filter(save_trajectories=True)
+    got = lazy.filter(save_trajectories="device")
+    assert got["trajectories"] is None
+    assert np.array_equal(got["log_likelihood"], want["log_likelihood"])
+    pick = np.array([1, 500, 1000, 37, 37])
+    h = lazy.filter_history(pick)
+    assert h.shape == (3, 5, 41)
+    assert np.array_equal(h, want["trajectories"][:, pick - 1, :])
+    assert np.array_equal(lazy.filter_history(np.arange(1, n + 1)), want["trajectories"])
+    with pytest.raises(IndexError):
+        lazy.filter_history([n + 1])
+    # a run without history invalidates it
+    lazy.update_state(pars={}, time=0)
+    lazy.filter()
+    with pytest.raises(Exception, match="save_trajectories"):
+        lazy.filter_history([1])
+
+    # several parameter sets: indices are per set
+    sets = [{"beta": 0.2}, {"beta": 0.3}, {"beta": 0.25}]
+    full = g.new(sets, 0, 200, seed=3, pars_multi=True)
+    lazy = g.new(sets, 0, 200, seed=3, pars_multi=True)
+    for m in (full, lazy):
+        m.set_data(dust.dust_data({"time_end": t, "incidence": x}), True)
+        m.set_index([2, 5])
+    want = full.filter(save_trajectories=True)["trajectories"]     # [2, 200, 3, 41]
+    lazy.filter(save_trajectories="device")
+    ip = np.array([[1, 200, 7], [50, 50, 50]])
+    h = lazy.filter_history(ip)
+    assert h.shape == (2, 2, 3, 41)
+    for j in range(3):
+        assert np.array_equal(h[:, :, j, :], want[:, ip[:, j] - 1, j, :])
+
+
+def test_filter_history_after_early_stop(dust, sir_data):
+    n = 256
+    t, x = _data(sir_data, 30)
+    x = x.copy()
+    x[:6] = 0.0          # no infections, no noise: the first positive datum is impossible
+    pars = {"exp_noise": float("inf"), "I0": 0}
+    g = dust.dust_example("sir")
+    a, b = g.new(pars, 0, n, seed=2), g.new(pars, 0, n, seed=2)
+    for m in (a, b):
+        _set_data(m, t, x)
+    want = a.filter(save_trajectories=True)
+    b.filter(save_trajectories="device")
+    assert want["log_likelihood"][0] == -np.inf
+    got = b.filter_history([3, 200])
+    assert np.array_equal(got, want["trajectories"][:, [2, 199], :], equal_nan=True)
+    assert np.isnan(got[:, :, -1]).all()
+
+
 def test_filter_incremental_equals_one_shot(dust, orc, sir_data):
     # tests/testthat/test-particle-filter.R:604-658
     n = 500
