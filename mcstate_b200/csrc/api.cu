@@ -933,12 +933,44 @@ int mcb_run(mcb_model *m, uint64_t time_end, double *out) {
   return MCB_OK;
 }
 
+// model$simulate(times) (R/predict.R:79): every launch of the run kernel also writes
+// the selected rows of its end state into a slice buffer in HBM; slices are packed
+// to R's layout and copied out once per chunk (256 MB of slices), not once per time.
 int mcb_simulate(mcb_model *m, const uint64_t *times, size_t n_times, double *out) {
   if (!m || !times || !out) return fail(MCB_ERR_ARG, "NULL argument");
+  MCB_CUDA(cudaSetDevice(m->device));
+  View &v = m->v;
   for (size_t k = 0; k < n_times; ++k) {
     if (k > 0 && times[k] <= times[k - 1]) return fail(MCB_ERR_ARG, "'times' must be increasing");
-    MCB_TRY(mcb_run(m, times[k], out + k * m->v.n_total * (size_t)m->v.n_index));
+    if (times[k] < m->time) return fail(MCB_ERR_ARG, "'time_end' must be at least the current time");
   }
+  if (n_times == 0) return MCB_OK;
+  const size_t slice = (size_t)v.n_index * v.ld;                 // doubles per saved slice
+  const size_t packed = (size_t)v.n_index * v.n_total;           // doubles per packed slice
+  size_t chunk = ((size_t)256 << 20) / (slice * sizeof(double));
+  if (chunk < 1) chunk = 1;
+  if (chunk > n_times) chunk = n_times;
+  const size_t slice_bytes = round_up(chunk * slice * sizeof(double), 256);
+  MCB_TRY(ensure_stage(m, slice_bytes + chunk * packed * sizeof(double)));
+  double *d_slices = m->d_stage;
+  double *d_packed = reinterpret_cast<double *>(reinterpret_cast<char *>(m->d_stage) + slice_bytes);
+  for (size_t c0 = 0; c0 < n_times; c0 += chunk) {
+    const size_t nc = n_times - c0 < chunk ? n_times - c0 : chunk;
+    for (size_t k = 0; k < nc; ++k) {
+      const uint64_t t_end = times[c0 + k];
+      // n_steps = 0 (t_end == current time) still records the slice
+      run_compare(m, v.y, v.y, m->time, (uint32_t)(t_end - m->time), -1, -1, d_slices + k * slice,
+                  nullptr);
+      m->time = t_end;
+    }
+    const dim3 grid(blocks_for(v.n_total, 256), (unsigned)nc);
+    mcb::k_pack_slices<<<grid, 256, 0, m->stream>>>(d_slices, v.ld, v.n_total, v.n_index, nc, d_packed);
+    ++m->launches;
+    MCB_CUDA(cudaMemcpyAsync(out + c0 * packed, d_packed, nc * packed * sizeof(double),
+                             cudaMemcpyDeviceToHost, m->stream));
+    MCB_CUDA(cudaStreamSynchronize(m->stream));
+  }
+  reset_cursor(m);
   return MCB_OK;
 }
 

@@ -751,6 +751,17 @@ __global__ void k_pack_rows(const double *__restrict__ y, size_t ld, size_t n_to
   }
 }
 
+// model$simulate: n_slices saved slices [slice][n_rows][ld] -> R layout
+// [n_rows fastest][particle][slice] in one pass
+__global__ void k_pack_slices(const double *__restrict__ value, size_t ld, size_t n_total,
+                              int n_rows, size_t n_slices, double *__restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t s = blockIdx.y;
+  if (i >= n_total || s >= n_slices) return;
+  for (int k = 0; k < n_rows; ++k)
+    out[(s * n_total + i) * n_rows + k] = value[(s * n_rows + k) * ld + i];
+}
+
 // R layout (n_state fastest) -> SoA; recycle = 1: one state vector for everyone
 __global__ void k_unpack_state(const double *__restrict__ in, int recycle, int n_state,
                                size_t ld, size_t n_total, double *__restrict__ y) {

@@ -276,7 +276,20 @@ class pmcmc_state:
             "trajectories": np.stack(self._h_traj, axis=1) if self._h_traj else None,
             "restart": np.stack(self._h_restart, axis=1) if self._h_restart else None,
             "n_filter_runs": self.n_filter_runs,
+            "predict": None,
         }
+        if c.save_state or c.save_trajectories:
+            # R/pmcmc_state.R:336-353: what pmcmc_predict needs to carry the samples forward
+            data = self._filter.inputs()["data"]
+            time = int(data.times[-1, 1])
+            last_history = getattr(self._filter, "_last_history", None)
+            out["predict"] = {"is_continuous": False, "transform": self._pars.model,
+                              "index": None if last_history is None else last_history["index"],
+                              "time": time, "rate": data.rate, "model_time": time / data.rate,
+                              "filter": self._filter.inputs()}
+            if c.save_trajectories:
+                # the model steps of the saved trajectories (R/pmcmc_state.R:386-396)
+                out["trajectories_time"] = np.concatenate([data.times[:1, 0], data.times[:, 1]])
         return out
 
 
@@ -298,7 +311,59 @@ def pmcmc_combine(samples):
         parts = [s[key] for s in samples]
         out[key] = None if any(p is None for p in parts) else np.concatenate(parts, axis=1)
     out["n_filter_runs"] = int(sum(s["n_filter_runs"] for s in samples))
+    # the last chain's, as R/pmcmc_tools.R:148-152
+    out["predict"] = samples[-1].get("predict")
+    if "trajectories_time" in samples[-1]:
+        out["trajectories_time"] = samples[-1]["trajectories_time"]
     return out
+
+
+def pmcmc_predict(object, times, prepend_trajectories=False, n_threads=None, seed=None):
+    """``pmcmc_predict`` (R/predict.R:36-89): run the model forward from every retained
+    sample's final state with that sample's parameters -- one multi-parameter model
+    object, one particle per sample (``model$new(pars, times[1], NULL, pars_multi =
+    TRUE)``, ``update_state(state = state)``, ``simulate(times)``).  On the engine this
+    is one launch of the run kernel per requested time over all samples, the saved
+    rows collected in HBM and copied out once.
+
+    Returns ``dict(time, rate, state [n_index, n_samples, n_times], predicted)``
+    (``mcstate_trajectories_discrete``, R/trajectories.R:1-8)."""
+    pred = object.get("predict")
+    if pred is None:
+        raise ValueError("mcmc was run with return_state = FALSE, can't predict")
+    times = [int(t) for t in times]
+    if len(times) < 2:
+        raise ValueError("At least two times required for predict")
+    if times[0] != pred["time"]:
+        raise ValueError("Expected times[1] to be %d" % pred["time"])
+    if prepend_trajectories and object.get("trajectories") is None:
+        raise ValueError("mcmc was run with return_trajectories = FALSE, can't prepend trajectories")
+    state = object.get("state")
+    if state is None:
+        raise ValueError("mcmc was run with return_state = FALSE, can't predict")
+    inputs = pred["filter"]
+    pars = [pred["transform"](theta) for theta in np.asarray(object["pars"])]
+    nt = inputs["n_threads"] if n_threads is None else n_threads
+    mod = inputs["model"].new(pars, times[0], None, n_threads=nt, seed=seed, pars_multi=True)
+    # state is [n_state, n_samples]; the model's layout is [n_state, 1 particle, n_pars]
+    mod.update_state(state=np.asarray(state)[:, None, :])
+    if pred["index"] is not None:
+        mod.set_index(pred["index"])
+    y = np.asarray(mod.simulate(times))           # [n_index, 1, n_samples, n_times]
+    y = y.reshape(y.shape[0], -1, y.shape[-1])
+    res = {"time": np.array(times), "rate": pred["rate"], "state": y,
+           "predicted": np.ones(len(times), dtype=bool)}
+    if prepend_trajectories:
+        a_time = np.asarray(object["trajectories_time"])
+        a_state = np.asarray(object["trajectories"])
+        if a_time[-1] != res["time"][0] or a_state.shape[:2] != y.shape[:2]:
+            raise ValueError("trajectories and predictions do not line up")
+        # bind_mcstate_trajectories_discrete (R/trajectories.R:28-45)
+        res = {"time": np.concatenate([a_time, res["time"][1:]]), "rate": pred["rate"],
+               "state": np.concatenate([a_state, y[:, :, 1:]], axis=2),
+               "predicted": np.concatenate([np.zeros(a_time.size, dtype=bool),
+                                            res["predicted"][1:]])}
+    return res
 
 
 def _check_initial(initial, pars, n_chains):
@@ -372,10 +437,21 @@ def pmcmc_sharded(pars, filter, initial=None, control=None, group=None, device=N
                        getattr(filter.model, "algorithm", "xoshiro256plus"))
     mine = {k: _run_one(k, pars, initial, filter, control, seeds, device)
             for k in range(control.n_chains) if chain_owner(k, world) == rank}
+    # `predict` holds callables and the model generator: send only what differs by chain
+    # (the filter's live seed), every rank rebuilds the rest from its own pars / filter
+    for smp in mine.values():
+        if smp.get("predict") is not None:
+            smp["predict"] = {"seed": smp["predict"]["filter"]["seed"],
+                              **{k: smp["predict"][k] for k in
+                                 ("is_continuous", "index", "time", "rate", "model_time")}}
     gathered = [None] * world
     dist.all_gather_object(gathered, mine, group=group)
     merged = {}
     for part in gathered:
         merged.update(part)
     samples = [merged[k] for k in range(control.n_chains)]
+    for smp in samples:
+        if smp.get("predict") is not None:
+            seed = smp["predict"].pop("seed")
+            smp["predict"].update(transform=pars.model, filter=dict(filter.inputs(), seed=seed))
     return samples[0] if control.n_chains == 1 else pmcmc_combine(samples)

@@ -32,7 +32,7 @@ class OracleDustModel:
         self._gen = gen
         self._multi = bool(pars_multi)
         self._pars = [dict(p) for p in pars] if pars_multi else dict(pars or {})
-        self._np = int(n_particles)
+        self._np = 1 if n_particles is None else int(n_particles)  # R/if2.R:122
         self._n_pars = len(pars) if pars_multi else 0
         self._n_sets = max(1, self._n_pars)
         self._n_state = len(STATE_NAMES[gen.model_id])
@@ -72,6 +72,10 @@ class OracleDustModel:
     def run(self, time_end):
         self._o.run(int(time_end))
         return self._shape_out(self._o.state(self._index))
+
+    def simulate(self, time_end):
+        out = [self.run(t) for t in np.atleast_1d(time_end)]
+        return np.stack(out, axis=-1)
 
     def state(self, index=None):
         if index is None:

@@ -17,7 +17,8 @@ import pytest
 from mcstate_b200.particle_filter import particle_filter
 from mcstate_b200.particle_filter_data import particle_filter_data
 from mcstate_b200.pmcmc import (chain_owner, make_seeds, pmcmc, pmcmc_control, pmcmc_parameter,
-                                pmcmc_parameters, reflect_proposal, rmvnorm_generator)
+                                pmcmc_parameters, pmcmc_predict, reflect_proposal,
+                                rmvnorm_generator)
 from oracle_generator import OracleGenerator
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -202,6 +203,8 @@ _WORKER = textwrap.dedent("""
     control = pmcmc_control(10, n_chains=n_chains, n_workers=world, save_trajectories=True)
     res = pmcmc(example_pars(), example_filter(kind, sir), control=control)
     if rank == 0:
+        assert res["predict"]["filter"]["model"] is not None
+        res["predict"] = {{k: res["predict"][k] for k in ("time", "rate", "index")}}
         with open(sys.argv[3], "wb") as fh:
             pickle.dump(res, fh)
     dist.barrier()
@@ -246,3 +249,57 @@ def test_sharded_chains_equal_serial_b200(tmp_path, sir_data):
     sharded = _run_sharded(tmp_path, "gpu", 3, 2, "gloo")
     for key in ("pars", "probabilities", "chain", "iteration", "state", "trajectories"):
         assert np.array_equal(serial[key], sharded[key]), key
+
+
+# ---------------------------------------------------------------- pmcmc_predict (8f N3)
+@pytest.mark.parametrize("kind", BACKENDS)
+def test_predict_from_a_mcmc_run(kind, sir_data):
+    """tests/testthat/test-predict.R:3-29, 43-56, 59-101."""
+    p = example_filter(kind, sir_data, n_particles=100)
+    control = pmcmc_control(30, save_state=True, save_trajectories=True)
+    results = pmcmc(example_pars(), p, control=control)
+    last = int(sir_data["day"][-1]) * 4
+    assert results["predict"]["time"] == last and results["predict"]["rate"] == 4
+    steps = [last + 4 * k for k in range(26)]
+    y = pmcmc_predict(results, steps, seed=1)
+    assert list(y["time"]) == steps and y["rate"] == 4 and y["predicted"].all()
+    assert y["state"].shape == (3, 30, 26)
+    assert np.array_equal(y["state"][:, :, 0], results["state"][:3, :])   # starts where the run ended
+    assert np.all(np.diff(y["state"][0], axis=1) <= 0)                     # S falls
+    assert np.all(np.diff(y["state"][2], axis=1) >= 0)                     # R rises
+    # same seed, same prediction (test-predict.R:32-40)
+    assert np.array_equal(pmcmc_predict(results, steps, seed=1)["state"], y["state"])
+    # prepend the filter's trajectories (test-predict.R:43-56)
+    y1 = pmcmc_predict(results, steps, prepend_trajectories=True, seed=1)
+    assert list(y1["time"]) == list(range(0, last + 4 * 25 + 1, 4))
+    assert list(y1["predicted"]) == [False] * 101 + [True] * 25
+    assert np.array_equal(y1["state"][:, :, 100:], y["state"])
+    assert np.array_equal(y1["state"][:, :, :101], results["trajectories"])
+    with pytest.raises(ValueError, match="At least two times required"):
+        pmcmc_predict(results, [last])
+    with pytest.raises(ValueError, match="Expected times\\[1\\] to be %d" % last):
+        pmcmc_predict(results, [last + 4, last + 8])
+    no_traj = pmcmc(example_pars(), p, control=pmcmc_control(5, save_state=True,
+                                                             save_trajectories=False))
+    with pytest.raises(ValueError, match="can't prepend trajectories"):
+        pmcmc_predict(no_traj, steps, prepend_trajectories=True)
+    no_state = pmcmc(example_pars(), p, control=pmcmc_control(5, save_state=False))
+    with pytest.raises(ValueError, match="return_state = FALSE, can't predict"):
+        pmcmc_predict(no_state, steps)
+
+
+@pytest.mark.gpu
+def test_predict_engine_equals_oracle(sir_data):
+    """The same retained samples carried forward by the engine and by the CPU oracle:
+    identical on identical seeds."""
+    res = {}
+    for kind in ("oracle", "gpu"):
+        p = example_filter(kind, sir_data, n_particles=64, seed=3)
+        np.random.seed(0)
+        r = pmcmc(example_pars(), p, control=pmcmc_control(12, save_state=True,
+                                                           use_parallel_seed=True))
+        last = r["predict"]["time"]
+        res[kind] = (r, pmcmc_predict(r, [last + 2 * k for k in range(15)], seed=7))
+    assert np.array_equal(res["oracle"][0]["pars"], res["gpu"][0]["pars"])
+    assert np.array_equal(res["oracle"][0]["state"], res["gpu"][0]["state"])
+    assert np.array_equal(res["oracle"][1]["state"], res["gpu"][1]["state"])
