@@ -764,7 +764,7 @@ int mcb_alloc_ex(int model_id, const double *pars, size_t n_particles, size_t n_
   ALLOC(m->d_ll, n_sets * sizeof(double));
   ALLOC(m->d_min_ll, n_sets * sizeof(double));
   ALLOC(m->d_flags, 2 * sizeof(int));
-  ALLOC(m->d_ticket, sizeof(unsigned int));
+  ALLOC(m->d_ticket, (n_sets + 2) * sizeof(unsigned int));
   ALLOC(m->d_index, mcb::kMaxState * sizeof(int));
   ALLOC(m->d_kappa, v.ld * sizeof(int));
   ALLOC(m->d_u, n_sets * sizeof(double));
@@ -785,7 +785,7 @@ int mcb_alloc_ex(int model_id, const double *pars, size_t n_particles, size_t n_
     return cleanup(fail(MCB_ERR_CUDA, "pinned memory / stream creation failed"));
   m->stream = m->own_stream;
   cudaMemsetAsync(m->d_flags, 0, 2 * sizeof(int), m->stream);
-  cudaMemsetAsync(m->d_ticket, 0, sizeof(unsigned int), m->stream);
+  cudaMemsetAsync(m->d_ticket, 0, (n_sets + 2) * sizeof(unsigned int), m->stream);
   cudaMemsetAsync(v.y, 0, (size_t)v.n_state * v.ld * sizeof(double), m->stream);
   cudaMemsetAsync(v.y_tmp, 0, (size_t)v.n_state * v.ld * sizeof(double), m->stream);
   m->index_host.resize(v.n_state);

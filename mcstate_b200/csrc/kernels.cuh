@@ -63,7 +63,7 @@ struct View {
   double *ll;         // [n_sets] accumulated log-likelihood of this filter call
   const double *min_ll; // [n_min]
   int *flags;         // [0] stopped, [1] stop row
-  unsigned int *ticket; // K2 block counter (the last block finalizes)
+  unsigned int *ticket; // [n_sets + 2] K2 counters: tiles done per set, sets done, any set dead
   const int *index;   // [n_index] rows returned by run()/saved in trajectories
   size_t n_particles, n_sets, n_total, ld, ld_rng;
   int n_state, n_index, n_min, data_sets, tiles_per_set, shift, deterministic, n_tab, n_wrows;
@@ -419,21 +419,25 @@ __device__ __forceinline__ bool finish_set(const View &v, int row, size_t set,
   return false;
 }
 
-// Run by the LAST block of K2 to finish: inclusive prefix over every set's tile
-// sums, finish_set, then the early-exit rule of R/particle_filter_state.R:463-474.
-__device__ __forceinline__ void finalize_sets(const View &v, int row) {
+// The weights stage finishes per parameter set: the block that completes a set's
+// last tile (ticket counter of the set) turns the set's tile sums into an
+// inclusive prefix and runs finish_set, so many small sets (nested populations,
+// SMC^2) finish in parallel, each on the SM that happened to end it.  The last
+// set to finish (a second counter) applies the early-exit rule of
+// R/particle_filter_state.R:463-474 over all the sets.
+//   ticket [n_sets] per-set counters, [n_sets] the counter of finished sets,
+//          [n_sets + 1] "some set is dead" of this interval
+__device__ __forceinline__ void finalize_set(const View &v, int row, size_t set) {
   __shared__ unsigned long long s_tot[kTileThreads / 32];
   __shared__ unsigned long long s_carry;
-  __shared__ int s_dead;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = v.tiles_per_set;
-  if (tid == 0) s_dead = 0;
-  __syncthreads();
-  if (T <= 32) {
-    // many small sets (nested populations, SMC^2): one warp per set
-    for (size_t set = warp; set < v.n_sets; set += kTileThreads / 32) {
-      if (row >= 0 && datum_is_na(v, row, set)) continue;
-      unsigned long long *ts = v.tile_incl + set * T;
+  unsigned long long *ts = v.tile_incl + set * T;
+  bool dead = false;
+  const bool weighed = row < 0 || !datum_is_na(v, row, set);
+  if (weighed && T <= 32) {
+    // a small set: one warp
+    if (warp == 0) {
       unsigned long long incl = lane < T ? __ldcg(ts + lane) : 0ULL;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
@@ -442,80 +446,86 @@ __device__ __forceinline__ void finalize_sets(const View &v, int row) {
       }
       if (lane < T) ts[lane] = incl;
       const unsigned long long tot = shfl_u64(incl, 31);
-      if (lane == 0 && finish_set(v, row, set, tot)) atomicExch(&s_dead, 1);
+      if (lane == 0) dead = finish_set(v, row, set, tot);
     }
-  } else {
-    // few big sets: the whole block scans one set's tiles; each thread owns
-    // `per` consecutive tiles so a set of up to 256 * 8 tiles is one pass
+  } else if (weighed) {
+    // a big set: the whole block scans its tiles; each thread owns `per`
+    // consecutive tiles so a set of up to 256 * 8 tiles is one pass
     constexpr int kPer = 8;
-    for (size_t set = 0; set < v.n_sets; ++set) {
-      if (row >= 0 && datum_is_na(v, row, set)) continue;
-      unsigned long long *ts = v.tile_incl + set * T;
-      if (tid == 0) s_carry = 0;
-      __syncthreads();
-      for (int base = 0; base < T; base += kTileThreads * kPer) {
-        const int span = min(T - base, kTileThreads * kPer);
-        const int per = (span + kTileThreads - 1) / kTileThreads;
-        const int lo = base + tid * per, hi = min(base + span, lo + per);
-        unsigned long long x[kPer];
-        unsigned long long local = 0;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < T; base += kTileThreads * kPer) {
+      const int span = min(T - base, kTileThreads * kPer);
+      const int per = (span + kTileThreads - 1) / kTileThreads;
+      const int lo = base + tid * per, hi = min(base + span, lo + per);
+      unsigned long long x[kPer];
+      unsigned long long local = 0;
 #pragma unroll
-        for (int j = 0; j < kPer; ++j) {
-          x[j] = (j < per && lo + j < hi) ? __ldcg(ts + lo + j) : 0ULL;
-          local += x[j];
-          x[j] = local;
-        }
-        unsigned long long incl = local;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const unsigned long long o = shfl_up_u64(incl, d);
-          if (lane >= d) incl += o;
-        }
-        if (lane == 31) s_tot[warp] = incl;
-        __syncthreads();
-        unsigned long long offset = s_carry + incl - local;
-#pragma unroll
-        for (int w = 0; w < kTileThreads / 32; ++w)
-          if (w < warp) offset += s_tot[w];
-#pragma unroll
-        for (int j = 0; j < kPer; ++j)
-          if (j < per && lo + j < hi) ts[lo + j] = x[j] + offset;
-        __syncthreads();
-        if (tid == kTileThreads - 1) s_carry = offset + local;
-        __syncthreads();
+      for (int j = 0; j < kPer; ++j) {
+        x[j] = (j < per && lo + j < hi) ? __ldcg(ts + lo + j) : 0ULL;
+        local += x[j];
+        x[j] = local;
       }
-      if (tid == 0 && finish_set(v, row, set, s_carry)) s_dead = 1;
+      unsigned long long incl = local;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long o = shfl_up_u64(incl, d);
+        if (lane >= d) incl += o;
+      }
+      if (lane == 31) s_tot[warp] = incl;
       __syncthreads();
+      unsigned long long offset = s_carry + incl - local;
+#pragma unroll
+      for (int w = 0; w < kTileThreads / 32; ++w)
+        if (w < warp) offset += s_tot[w];
+#pragma unroll
+      for (int j = 0; j < kPer; ++j)
+        if (j < per && lo + j < hi) ts[lo + j] = x[j] + offset;
+      __syncthreads();
+      if (tid == kTileThreads - 1) s_carry = offset + local;
+      __syncthreads();
+    }
+    if (tid == 0) dead = finish_set(v, row, set, s_carry);
+  }
+  if (tid != 0) return;
+  bool any_dead = dead;
+  if (v.n_sets > 1) {
+    unsigned int *done = v.ticket + v.n_sets;
+    if (dead) atomicExch(done + 1, 1u);
+    __threadfence();
+    if (atomicAdd(done, 1u) != (unsigned)v.n_sets - 1) return;
+    // every set of this interval is finished: reset the counters, apply the stop rule
+    __threadfence();
+    any_dead = atomicExch(done + 1, 0u) != 0;
+    *done = 0;
+  }
+  if (row < 0) return;
+  bool stop = any_dead;
+  if (!stop && v.n_min > 0) {
+    const volatile double *ll = v.ll;
+    if (v.n_sets == 1) {
+      stop = ll[0] < v.min_ll[0];
+    } else if (v.n_min == 1) {
+      double tot = 0.0;
+      for (size_t p = 0; p < v.n_sets; ++p) tot += ll[p];
+      stop = tot < v.min_ll[0];
+    } else {
+      stop = true;
+      for (size_t p = 0; p < v.n_sets; ++p) stop = stop && (ll[p] < v.min_ll[p]);
     }
   }
-  __syncthreads();
-  if (tid == 0 && row >= 0) {
-    bool stop = s_dead != 0;
-    if (!stop && v.n_min > 0) {
-      if (v.n_sets == 1) {
-        stop = v.ll[0] < v.min_ll[0];
-      } else if (v.n_min == 1) {
-        double tot = 0.0;
-        for (size_t p = 0; p < v.n_sets; ++p) tot += v.ll[p];
-        stop = tot < v.min_ll[0];
-      } else {
-        stop = true;
-        for (size_t p = 0; p < v.n_sets; ++p) stop = stop && (v.ll[p] < v.min_ll[p]);
-      }
-    }
-    if (stop) {
-      for (size_t p = 0; p < v.n_sets; ++p) v.ll[p] = __longlong_as_double(0xfff0000000000000LL);
-      v.flags[1] = row;
-      __threadfence();
-      v.flags[0] = 1;
-    }
+  if (stop) {
+    for (size_t p = 0; p < v.n_sets; ++p) v.ll[p] = __longlong_as_double(0xfff0000000000000LL);
+    v.flags[1] = row;
+    __threadfence();
+    v.flags[0] = 1;
   }
 }
 
 // ---------------------------------------------------------------------------
 // K2: one block per tile of kTile particles (tiles never straddle a set):
 // w = exp(logw - max) -> fixed point, inclusive scan inside the tile, tile sum.
-// The last block to finish (ticket counter) then runs finalize_sets, so the
+// The block that takes its set's last ticket then runs finalize_set, so the
 // whole weights stage is one launch.
 // GIVEN = true: `logw` already holds weights in [0,1] (model$resample(weights)).
 // ---------------------------------------------------------------------------
@@ -589,17 +599,17 @@ __global__ void __launch_bounds__(kTileThreads, 4) k_weights_scan(View v, int ro
     }
     if (threadIdx.x == 0) v.tile_incl[blockIdx.x] = total;
   }
-  // ---- the last block to get here finishes the stage.  Only the tile sum
-  // (written by thread 0) is read by that block; cw is for the next launch.
+  // ---- the block that takes the set's last ticket finishes the set.  Only the
+  // tile sum (written by thread 0) is read by that block; cw is for the next launch.
   if (threadIdx.x == 0) {
     __threadfence();
-    s_last = atomicAdd(v.ticket, 1u) == gridDim.x - 1;
+    s_last = atomicAdd(v.ticket + set, 1u) == (unsigned)v.tiles_per_set - 1;
   }
   __syncthreads();
   if (!s_last) return;
-  if (threadIdx.x == 0) *v.ticket = 0;
+  if (threadIdx.x == 0) v.ticket[set] = 0;
   __threadfence();
-  finalize_sets(v, row);
+  finalize_set(v, row, set);
 }
 
 // ---------------------------------------------------------------------------
