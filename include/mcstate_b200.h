@@ -206,6 +206,14 @@ int mcb_filter(mcb_model *m, uint64_t time_end, int save_trajectories,
  * into n_total (set-major).  Valid until the next filter call on the handle. */
 #define MCB_TRAJECTORIES_ON_DEVICE 2
 int mcb_filter_history(mcb_model *m, const size_t *particles, size_t n, double *out);
+
+/* A filter of one parameter set whose particles are all resident at once (up to
+ * about 150 000 on a B200), run without trajectories or snapshots, executes as ONE
+ * cooperative kernel per mcb_filter call instead of two launches per data interval
+ * (csrc/persistent.cuh); results are bit-identical either way.  enable = 0 keeps
+ * this handle on the two-launch path (A/B measurements, tests); the environment
+ * variable MCB_PERSISTENT=0 does the same for every handle. */
+int mcb_set_persistent(mcb_model *m, int enable);
 /* the same, split so many handles / GPUs can be in flight at once: enqueue
  * returns as soon as the work is queued, collect waits and copies out */
 int mcb_filter_enqueue(mcb_model *m, uint64_t time_end);

@@ -78,6 +78,7 @@ SIGNATURES = {
     "mcb_filter": (C.c_int, [handle_p, C.c_uint64, C.c_int, u64p, C.c_size_t, f64p, C.c_size_t,
                              f64p, f64p, f64p]),
     "mcb_filter_history": (C.c_int, [handle_p, szp, C.c_size_t, f64p]),
+    "mcb_set_persistent": (C.c_int, [handle_p, C.c_int]),
     "mcb_filter_enqueue": (C.c_int, [handle_p, C.c_uint64]),
     "mcb_filter_collect": (C.c_int, [handle_p, f64p]),
     "mcb_launch_count": (C.c_int, [handle_p, u64p]),

@@ -19,6 +19,7 @@
 
 #include "../../include/mcstate_b200.h"
 #include "kernels.cuh"
+#include "persistent.cuh"
 
 namespace {
 
@@ -154,6 +155,10 @@ struct GraphEntry {
 struct mcb_model {
   int model_id = 0, scrambler = 0, device = 0, n_const = 0;
   bool chain = false;   // K1/K2 launched with programmatic dependent launch
+  // the single-launch filter (persistent.cuh): blocks that can be co-resident, or 0
+  int persist_blocks = 0;
+  uint64_t *d_data_time = nullptr;
+  unsigned long long *d_blk_sum = nullptr;
   const ModelDesc *desc = nullptr;
   mcb::View v{};
   uint64_t time = 0;
@@ -465,6 +470,74 @@ int prepare_history(mcb_model *m, int rows) {
   return MCB_OK;
 }
 
+// ---- the single-launch filter (persistent.cuh) -----------------------------------
+template <class M, int SCR>
+const void *persistent_kernel() {
+  return reinterpret_cast<const void *>(&mcb::k_filter_persistent<M, SCR>);
+}
+const void *persistent_kernel_for(const mcb_model *m) {
+  switch (m->model_id * 2 + m->scrambler) {
+    case 0: return persistent_kernel<mcb::SirModel, 0>();
+    case 1: return persistent_kernel<mcb::SirModel, 1>();
+    case 2: return persistent_kernel<mcb::SirsModel, 0>();
+    case 3: return persistent_kernel<mcb::SirsModel, 1>();
+    case 4: return persistent_kernel<mcb::VolatilityModel, 0>();
+    default: return persistent_kernel<mcb::VolatilityModel, 1>();
+  }
+}
+
+// how many blocks of the persistent kernel fit the device at once (0: not usable)
+int persistent_capacity(const mcb_model *m) {
+  static const bool on = !(getenv("MCB_PERSISTENT") && atoi(getenv("MCB_PERSISTENT")) == 0);
+  if (!on) return 0;
+  int coop = 0, sms = 0, per_sm = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, m->device);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+  if (!coop) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persistent_kernel_for(m),
+                                                    mcb::kPersistThreads, 0) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  const int cap = per_sm * sms;
+  return cap < mcb::kPersistMaxBlocks ? cap : mcb::kPersistMaxBlocks;
+}
+
+// One parameter set, no trajectories or snapshots, every particle resident at once:
+// the whole call is one cooperative launch between the uniforms and the stream update.
+bool use_persistent(const mcb_model *m, bool hist, size_t n_snap) {
+  const View &v = m->v;
+  return m->persist_blocks > 0 && !hist && n_snap == 0 && !m->timing && v.n_sets == 1 &&
+         v.n_fs == 1 && blocks_for(v.n_total, mcb::kPersistThreads) <= (unsigned)m->persist_blocks;
+}
+
+int launch_persistent(mcb_model *m, int first, int last) {
+  View &v = m->v;
+  cudaMemsetAsync(m->d_flags, 0, 2 * sizeof(int), m->stream);
+  cudaMemsetAsync(m->d_ll, 0, sizeof(double), m->stream);
+  cudaMemsetAsync(m->d_wmax + (size_t)first, 0, (size_t)(last - first) * sizeof(unsigned long long),
+                  m->stream);
+  draw_uniforms(m, first, last);
+  int weighed = 0;
+  for (int row = first; row < last; ++row) weighed += m->row_all_na[row] ? 0 : 1;
+  mcb::PersistArgs a;
+  a.data_time = m->d_data_time;
+  a.blk_sum = m->d_blk_sum;
+  a.first = first;
+  a.last = last;
+  a.t_start = m->time;
+  a.first_out_tmp = (weighed & 1) ? 1 : 0;   // so that the last weighed row writes y_tmp
+  void *args[] = {&v, &a};
+  const unsigned grid = blocks_for(v.n_total, mcb::kPersistThreads);
+  MCB_CUDA(cudaLaunchCooperativeKernel(persistent_kernel_for(m), dim3(grid),
+                                       dim3(mcb::kPersistThreads), args, 0, m->stream));
+  ++m->launches;
+  mcb::k_filter_finish<<<blocks_for((size_t)v.n_fs, 128), 128, 0, m->stream>>>(v, first, last,
+                                                                                m->d_fs_after);
+  ++m->launches;
+  return MCB_OK;
+}
+
 int run_filter(mcb_model *m, uint64_t time_end, bool hist, const uint64_t *snapshot_times,
                size_t n_snap, const double *min_ll, size_t n_min, bool wait,
                double *ll_out, double *traj_out, double *snap_out) {
@@ -505,7 +578,9 @@ int run_filter(mcb_model *m, uint64_t time_end, bool hist, const uint64_t *snaps
     MCB_CUDA(cudaMemcpyAsync(m->d_min_ll, min_ll, n_min * sizeof(double), cudaMemcpyHostToDevice,
                              m->stream));
 
-  if (rows > 0) {
+  if (rows > 0 && use_persistent(m, hist, n_snap)) {
+    MCB_TRY(launch_persistent(m, first, last));
+  } else if (rows > 0) {
     const GraphKey key{first, last, (hist ? 1 : 0) | (m->timing ? 2 : 0), (int)n_snap, (int)n_min,
                        snap_hash};
     auto it = m->graphs.find(key);
@@ -765,6 +840,7 @@ int mcb_alloc_ex(int model_id, const double *pars, size_t n_particles, size_t n_
   ALLOC(m->d_min_ll, n_sets * sizeof(double));
   ALLOC(m->d_flags, 2 * sizeof(int));
   ALLOC(m->d_ticket, (n_sets + 2) * sizeof(unsigned int));
+  ALLOC(m->d_blk_sum, mcb::kPersistMaxBlocks * sizeof(unsigned long long));
   ALLOC(m->d_index, mcb::kMaxState * sizeof(int));
   ALLOC(m->d_kappa, v.ld * sizeof(int));
   ALLOC(m->d_u, n_sets * sizeof(double));
@@ -832,6 +908,7 @@ int mcb_alloc_ex(int model_id, const double *pars, size_t n_particles, size_t n_
   cudaError_t err = cudaStreamSynchronize(m->stream);
   if (err != cudaSuccess)
     return cleanup(fail(MCB_ERR_CUDA, std::string("alloc: ") + cudaGetErrorString(err)));
+  m->persist_blocks = persistent_capacity(m);
   *out = m;
   return MCB_OK;
 }
@@ -844,7 +921,7 @@ int mcb_free(mcb_model *m) {
   void *ptrs[] = {m->v.y, m->v.y_tmp, m->v.rng, m->v.derived, m->v.tab_inf, m->v.tab_walk, m->d_pars, m->v.logw, m->v.cw, m->v.tile_incl,
                   m->v.setinfo, m->d_ll, m->d_min_ll, m->d_flags, m->d_ticket, m->d_index, m->d_kappa, m->d_u,
                   m->d_wmax, m->d_fs_after, m->d_na_global, m->d_data, m->d_stage, m->d_hist_value,
-                  m->d_hist_order, m->d_traj, m->d_snap};
+                  m->d_hist_order, m->d_traj, m->d_snap, m->d_data_time, m->d_blk_sum};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   for (cudaEvent_t e : m->events) cudaEventDestroy(e);
@@ -1176,10 +1253,13 @@ int mcb_set_data(mcb_model *m, size_t n_data, const uint64_t *time_end, const do
       packed[(r * sets + s) * 2 + 1] = std::isnan(x) ? NAN : std::lgamma(x + 1.0);
       if (!std::isnan(x)) m->row_all_na[r] = 0;
     }
-  void *old[] = {m->d_data, m->d_u, m->d_fs_after, m->d_wmax};
+  void *old[] = {m->d_data, m->d_u, m->d_fs_after, m->d_wmax, m->d_data_time};
   for (void *p : old)
     if (p) cudaFree(p);
   m->d_data = nullptr; m->d_u = nullptr; m->d_fs_after = nullptr; m->d_wmax = nullptr;
+  m->d_data_time = nullptr;
+  MCB_CUDA(cudaMalloc(&m->d_data_time, n_data * sizeof(uint64_t)));
+  MCB_CUDA(cudaMemcpy(m->d_data_time, time_end, n_data * sizeof(uint64_t), cudaMemcpyHostToDevice));
   MCB_CUDA(cudaMalloc(&m->d_data, packed.size() * sizeof(double)));
   MCB_CUDA(cudaMalloc(&m->d_u, n_data * v.n_sets * sizeof(double)));
   MCB_CUDA(cudaMalloc(&m->d_fs_after, n_data * (size_t)v.n_fs * 4 * sizeof(uint64_t)));
@@ -1290,6 +1370,13 @@ int mcb_filter_history(mcb_model *m, const size_t *particles, size_t n, double *
   ++m->launches;
   MCB_CUDA(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, m->stream));
   MCB_CUDA(cudaStreamSynchronize(m->stream));
+  return MCB_OK;
+}
+
+int mcb_set_persistent(mcb_model *m, int enable) {
+  if (!m) return fail(MCB_ERR_ARG, "model is NULL");
+  MCB_CUDA(cudaSetDevice(m->device));
+  m->persist_blocks = enable ? persistent_capacity(m) : 0;
   return MCB_OK;
 }
 

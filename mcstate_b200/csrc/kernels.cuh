@@ -242,6 +242,57 @@ __device__ __noinline__ void run_general(double *y, uint64_t *rs, uint64_t t0, u
   rs[0] = rng.s0; rs[1] = rng.s1; rs[2] = rng.s2; rs[3] = rng.s3;
 }
 
+// `n_steps` model updates of one particle, state and generator in registers: the
+// lean path where the model has one and the state allows it, the general code for
+// whatever is left (run_general, out of line), or -- for a model without integer
+// compartments -- its one form, inline.  s_inv: the block's {k, 1/k} table.
+template <class M, int SCR>
+__device__ __forceinline__ void run_model_steps(const View &v, const SetData &sd,
+                                                const typename M::Ctx &ctx, size_t set, double *y,
+                                                Xoshiro &rng, uint64_t t0, uint32_t n_steps,
+                                                bool det, const double2 *s_inv) {
+  if (n_steps == 0) return;
+  uint32_t done = 0;
+  if constexpr (M::kHasLean) {
+    int yi[M::kLeanState];
+    typename M::Lean lc;
+    lc.set = (uint32_t)set;
+    const LeanTabs tabs{v.tab_inf, v.tab_walk, (uint32_t)v.n_tab, (uint32_t)v.n_wrows,
+                        (32 - __clz(v.n_tab - 1) + 1) / 3};
+    if (!det && M::lean_load(sd, y, yi, lc)) {
+      // the usual case: integer compartments, setup from the memo tables, no calls
+      const uint32_t s_inv_addr = (uint32_t)__cvta_generic_to_shared(s_inv);
+      const uint32_t freq = (uint32_t)__ldg(sd.derived + M::D_FREQ);
+      uint32_t phase = t0 <= 0xffffffffULL ? (uint32_t)t0 % freq : (uint32_t)(t0 % freq);
+      bool ok = true;
+      while (ok && done < n_steps) {
+        // bit k: step done + k starts a new incidence interval
+        const uint32_t nk = min(n_steps - done, 32u);
+        uint32_t resets = 0;
+        for (uint32_t k = 0; k < nk; ++k) {
+          resets |= (phase == 0 ? 1u : 0u) << k;
+          phase = phase + 1 == freq ? 0 : phase + 1;
+        }
+        for (uint32_t k = 0; k < nk; ++k) {
+          ok = M::template lean_update<SCR>((resets & 1u) != 0, yi, rng, lc, tabs, s_inv_addr);
+          if (!ok) break;
+          resets >>= 1;
+          ++done;
+        }
+      }
+      M::lean_store(sd, yi, y);
+    }
+  }
+  if constexpr (!M::kHasLean) {
+    // a model without integer compartments has one form only: inline
+    for (uint32_t k = 0; k < n_steps; ++k) M::template update<SCR>(t0 + k, y, rng, ctx, det);
+  } else if (done < n_steps) {  // whatever the lean path did not take
+    uint64_t rs[4] = {rng.s0, rng.s1, rng.s2, rng.s3};
+    run_general<M, SCR>(y, rs, t0 + done, n_steps - done, sd.derived, sd.n_tab, det);
+    rng.s0 = rs[0]; rng.s1 = rs[1]; rng.s2 = rs[2]; rng.s3 = rs[3];
+  }
+}
+
 #ifndef MCB_K1_MINBLOCKS
 #define MCB_K1_MINBLOCKS 12
 #endif
@@ -295,47 +346,7 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
     rng.s2 = __ldcs(v.rng + 2 * v.ld_rng + i);
     rng.s3 = __ldcs(v.rng + 3 * v.ld_rng + i);
 
-    if (n_steps > 0) {
-      uint32_t done = 0;
-      if constexpr (M::kHasLean) {
-        int yi[M::kLeanState];
-        typename M::Lean lc;
-        lc.set = (uint32_t)set;
-        const LeanTabs tabs{v.tab_inf, v.tab_walk, (uint32_t)v.n_tab, (uint32_t)v.n_wrows,
-                            (32 - __clz(v.n_tab - 1) + 1) / 3};
-        if (!det && M::lean_load(sd, y, yi, lc)) {
-          // the usual case: integer compartments, setup from the memo tables, no calls
-          const uint32_t s_inv_addr = (uint32_t)__cvta_generic_to_shared(s_inv);
-          const uint32_t freq = (uint32_t)__ldg(sd.derived + M::D_FREQ);
-          uint32_t phase = t0 <= 0xffffffffULL ? (uint32_t)t0 % freq : (uint32_t)(t0 % freq);
-          bool ok = true;
-          while (ok && done < n_steps) {
-            // bit k: step done + k starts a new incidence interval
-            const uint32_t nk = min(n_steps - done, 32u);
-            uint32_t resets = 0;
-            for (uint32_t k = 0; k < nk; ++k) {
-              resets |= (phase == 0 ? 1u : 0u) << k;
-              phase = phase + 1 == freq ? 0 : phase + 1;
-            }
-            for (uint32_t k = 0; k < nk; ++k) {
-              ok = M::template lean_update<SCR>((resets & 1u) != 0, yi, rng, lc, tabs, s_inv_addr);
-              if (!ok) break;
-              resets >>= 1;
-              ++done;
-            }
-          }
-          M::lean_store(sd, yi, y);
-        }
-      }
-      if constexpr (!M::kHasLean) {
-        // a model without integer compartments has one form only: inline
-        for (uint32_t k = 0; k < n_steps; ++k) M::template update<SCR>(t0 + k, y, rng, ctx, det);
-      } else if (done < n_steps) {  // whatever the lean path did not take
-        uint64_t rs[4] = {rng.s0, rng.s1, rng.s2, rng.s3};
-        run_general<M, SCR>(y, rs, t0 + done, n_steps - done, sd.derived, sd.n_tab, det);
-        rng.s0 = rs[0]; rng.s1 = rs[1]; rng.s2 = rs[2]; rng.s3 = rs[3];
-      }
-    }
+    run_model_steps<M, SCR>(v, sd, ctx, set, y, rng, t0, n_steps, det, s_inv);
 
     if (n_steps > 0 || y_in != y_out) {
 #pragma unroll

@@ -467,6 +467,11 @@ class dust_model:
             return out.reshape(-1, glob.shape[0], self._n_sets, self._n_index).transpose(3, 1, 2, 0)
         return out.transpose(2, 1, 0)
 
+    def set_persistent(self, enable=True):
+        """Small single-set filters run as one cooperative kernel per call
+        (csrc/persistent.cuh); ``False`` keeps this model on the two-launch path."""
+        check(_lib.lib().mcb_set_persistent(self._h, int(bool(enable))))
+
     # ---- asynchronous variant used to keep several GPUs / handles busy
     def filter_enqueue(self, time_end=None):
         if time_end is None:

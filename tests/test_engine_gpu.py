@@ -521,3 +521,94 @@ def test_sirs_filter_bit_exact(dust, orc, sir_data, alg, scr):
     assert np.array_equal(m.filter()["log_likelihood"], o.filter()["log_likelihood"])
     assert np.array_equal(m.state(), o.state())
     assert np.array_equal(_rng_words(m), o.rng_state())
+
+
+# ---- the single-launch filter (csrc/persistent.cuh) == the two-launch path ---------
+def _pair(dust, name, pars, n, seed, **kw):
+    g = dust.dust_example(name)
+    a, b = g.new(pars, 0, n, seed=seed, **kw), g.new(pars, 0, n, seed=seed, **kw)
+    b.set_persistent(False)
+    return a, b
+
+
+def _same(a, b):
+    assert np.array_equal(a.state(), b.state())
+    assert np.array_equal(_rng_words(a), _rng_words(b))
+    assert a.time() == b.time()
+
+
+@pytest.mark.parametrize("n", [1, 100, 128, 129, 4097, 1 << 16, 150000])
+def test_persistent_filter_equals_two_launch(dust, orc, sir_data, n):
+    t, x = _data(sir_data)
+    a, b = _pair(dust, "sir", {}, n, 3)
+    for m in (a, b):
+        _set_data(m, t, x)
+    la, lb = a.filter()["log_likelihood"], b.filter()["log_likelihood"]
+    assert np.array_equal(la, lb)
+    _same(a, b)
+    # uses one launch for the rows (plus uniforms and the stream update)
+    assert a.launch_count() < b.launch_count() - 150
+    if n <= 4097:
+        o = orc.OracleModel(n_particles=n, seed=3, n_threads=8)
+        o.set_data(t, x)
+        assert np.array_equal(la, o.filter()["log_likelihood"])
+        assert np.array_equal(a.state(), o.state())
+        assert np.array_equal(_rng_words(a), o.rng_state())
+    # a second evaluation on the same handles (the generator carries over)
+    for m in (a, b):
+        m.update_state(pars={"beta": 0.25}, time=0)
+    assert np.array_equal(a.filter()["log_likelihood"], b.filter()["log_likelihood"])
+    _same(a, b)
+
+
+def test_persistent_filter_special_rows(dust, sir_data):
+    n = 3000
+    t, x = _data(sir_data, 40)
+    # missing data rows (no weights, no resampling there), incremental calls, early exit
+    xm = x.copy()
+    xm[[0, 5, 6, 17, 39]] = np.nan
+    a, b = _pair(dust, "sir", {}, n, 5)
+    for m in (a, b):
+        _set_data(m, t, xm)
+    for t_end in (t[9], t[10], t[39]):
+        assert np.array_equal(a.filter(t_end)["log_likelihood"], b.filter(t_end)["log_likelihood"])
+        _same(a, b)
+    # min_log_likelihood: stops at the same row with the same state and streams
+    a, b = _pair(dust, "sir", {}, n, 6)
+    for m in (a, b):
+        _set_data(m, t, x)
+    ra, rb = a.filter(min_log_likelihood=-60.0), b.filter(min_log_likelihood=-60.0)
+    assert ra["log_likelihood"][0] == -np.inf and rb["log_likelihood"][0] == -np.inf
+    _same(a, b)
+    assert a.time() < t[-1]
+    # impossible data: every weight is zero
+    x0 = x.copy()
+    x0[:6] = 0.0
+    a, b = _pair(dust, "sir", {"exp_noise": float("inf"), "I0": 0}, 500, 1)
+    for m in (a, b):
+        _set_data(m, t, x0)
+    assert a.filter()["log_likelihood"][0] == -np.inf == b.filter()["log_likelihood"][0]
+    _same(a, b)
+    # deterministic mode, the second scrambler, the other models
+    a, b = _pair(dust, "sir", {}, 777, 2, deterministic=True)
+    for m in (a, b):
+        _set_data(m, t, x)
+    assert np.array_equal(a.filter()["log_likelihood"], b.filter()["log_likelihood"])
+    _same(a, b)
+    g = dust.dust_example("sirs", "xoshiro256starstar")
+    a, b = g.new({"alpha": 0.05}, 0, 2000, seed=4), g.new({"alpha": 0.05}, 0, 2000, seed=4)
+    b.set_persistent(False)
+    for m in (a, b):
+        _set_data(m, t, x)
+    assert np.array_equal(a.filter()["log_likelihood"], b.filter()["log_likelihood"])
+    _same(a, b)
+    g = dust.dust_example("volatility")
+    a, b = g.new({}, 0, 5000, seed=4), g.new({}, 0, 5000, seed=4)
+    b.set_persistent(False)
+    rs = np.random.RandomState(2)
+    for m in (a, b):
+        m.set_data(dust.dust_data({"time_end": np.arange(1, 51, dtype=np.uint64),
+                                   "observed": rs.normal(size=50)}), False)
+        rs = np.random.RandomState(2)
+    assert np.array_equal(a.filter()["log_likelihood"], b.filter()["log_likelihood"])
+    _same(a, b)
