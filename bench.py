@@ -280,6 +280,26 @@ def run_engine(args):
     barrier()
     e2e_s = time.perf_counter() - t0
 
+    # ---- not the headline: BASELINE config C3's filter (one pMCMC chain of 2^16 particles
+    # per GPU) on the single-launch path (csrc/persistent.cuh) and on the two-launch path
+    small = None
+    if rank == 0:
+        small = {"n_particles": 1 << 16, "unit": "ms per filter evaluation (100 intervals)"}
+        for name, on in (("single_launch", True), ("two_launch", False)):
+            ms = gen.new(pars, 0, 1 << 16, seed=1, gpu_config=local)
+            ms.set_persistent(on)
+            ms.set_data(dust.dust_data({"time_end": t, "incidence": x}), False)
+            for _ in range(3):
+                ms.update_state(pars=pars, time=0)
+                ms.filter()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(20):
+                ms.update_state(pars=pars, time=0)
+                ms.filter()
+            torch.cuda.synchronize()
+            small[name] = (time.perf_counter() - t0) / 20 * 1e3
+
     tmax = torch.tensor([ms_total, e2e_s * 1e3], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -316,11 +336,11 @@ def run_engine(args):
         cores = os.cpu_count() or 1
         cpu = None
         if world == 1 or True:
-            n_cpu = 1 << 16
+            n_cpu = 1 << 19
             v, secs, _ = cpu_baseline(n_cpu, cores, reps=2)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": "oracle filter at %d particles x 100 intervals (1/16 of one GPU's "
-                             "work), best of 2 after warm-up, %.2f s" % (n_cpu, secs)}
+                   "sample": "oracle filter at %d particles x 100 intervals (1/2 of one GPU's "
+                             "work), best of 2 after a warm-up run, %.2f s each" % (n_cpu, secs)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
@@ -334,6 +354,7 @@ def run_engine(args):
                     "api": "particle_filter(data, model, 2^20, compare=None).run(pars)"},
             "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks.summary(),
+            "small_filter_c3": small,
         }
         print(json.dumps(line))
     if world > 1:

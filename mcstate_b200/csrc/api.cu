@@ -503,15 +503,15 @@ int persistent_capacity(const mcb_model *m) {
   return cap < mcb::kPersistMaxBlocks ? cap : mcb::kPersistMaxBlocks;
 }
 
-// One parameter set, no trajectories or snapshots, every particle resident at once:
-// the whole call is one cooperative launch between the uniforms and the stream update.
-bool use_persistent(const mcb_model *m, bool hist, size_t n_snap) {
+// One parameter set, no snapshots, every particle resident at once: the whole call is
+// one cooperative launch between the uniforms and the stream update.
+bool use_persistent(const mcb_model *m, size_t n_snap) {
   const View &v = m->v;
-  return m->persist_blocks > 0 && !hist && n_snap == 0 && !m->timing && v.n_sets == 1 &&
+  return m->persist_blocks > 0 && n_snap == 0 && !m->timing && v.n_sets == 1 &&
          v.n_fs == 1 && blocks_for(v.n_total, mcb::kPersistThreads) <= (unsigned)m->persist_blocks;
 }
 
-int launch_persistent(mcb_model *m, int first, int last) {
+int launch_persistent(mcb_model *m, int first, int last, bool hist) {
   View &v = m->v;
   cudaMemsetAsync(m->d_flags, 0, 2 * sizeof(int), m->stream);
   cudaMemsetAsync(m->d_ll, 0, sizeof(double), m->stream);
@@ -527,6 +527,8 @@ int launch_persistent(mcb_model *m, int first, int last) {
   a.last = last;
   a.t_start = m->time;
   a.first_out_tmp = (weighed & 1) ? 1 : 0;   // so that the last weighed row writes y_tmp
+  a.hist_value = hist ? m->d_hist_value : nullptr;
+  a.hist_order = hist ? m->d_hist_order : nullptr;
   void *args[] = {&v, &a};
   const unsigned grid = blocks_for(v.n_total, mcb::kPersistThreads);
   MCB_CUDA(cudaLaunchCooperativeKernel(persistent_kernel_for(m), dim3(grid),
@@ -578,8 +580,8 @@ int run_filter(mcb_model *m, uint64_t time_end, bool hist, const uint64_t *snaps
     MCB_CUDA(cudaMemcpyAsync(m->d_min_ll, min_ll, n_min * sizeof(double), cudaMemcpyHostToDevice,
                              m->stream));
 
-  if (rows > 0 && use_persistent(m, hist, n_snap)) {
-    MCB_TRY(launch_persistent(m, first, last));
+  if (rows > 0 && use_persistent(m, n_snap)) {
+    MCB_TRY(launch_persistent(m, first, last, hist));
   } else if (rows > 0) {
     const GraphKey key{first, last, (hist ? 1 : 0) | (m->timing ? 2 : 0), (int)n_snap, (int)n_min,
                        snap_hash};

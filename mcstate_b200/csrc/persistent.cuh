@@ -25,8 +25,8 @@
 // change a cumulative sum -- and the results are bit-identical to the two-launch
 // path and to the oracle (tests/test_engine_gpu.py).
 //
-// Used for one parameter set, no trajectories, no snapshots; everything else takes
-// the general path.  Reference semantics: R/particle_filter_state.R:63-117 (loop),
+// Used for one parameter set without snapshots; everything else takes the general
+// path.  Reference semantics: R/particle_filter_state.R:63-117 (loop),
 // R/particle_filter.R:570-587 (log-mean-exp), :515-523 / SURVEY.md R2b
 // (resampling), R/particle_filter_state.R:463-474 (early exit).
 #pragma once
@@ -48,6 +48,10 @@ struct PersistArgs {
   int first, last;               // rows [first, last)
   uint64_t t_start;              // model step the state is at
   int first_out_tmp;             // the first weighed row writes y_tmp (else y)
+  // trajectories (or nullptr): values [rows + 1][n_index][ld] of the post-update states,
+  // order [rows + 1][n_total] = the particle each slot continued (kernels.cuh K1, HIST)
+  double *hist_value;
+  int *hist_order;
 };
 
 // first index in [lo, hi] (hi = last valid) with arr[idx] >= key, arr in shared memory
@@ -94,6 +98,23 @@ k_filter_persistent(View v, PersistArgs a) {
     rng.s1 = v.rng[1 * v.ld_rng + i];
     rng.s2 = v.rng[2 * v.ld_rng + i];
     rng.s3 = v.rng[3 * v.ld_rng + i];
+  }
+
+  const bool hist = a.hist_value != nullptr;
+  auto save_slice = [&](int slice, size_t src) {   // slice 0 = the state before the first row
+    if (!live) return;
+    for (int k = 0; k < v.n_index; ++k) {
+      const int s = v.index[k];
+      double val = y[0];
+#pragma unroll
+      for (int q = 1; q < M::kState; ++q) val = (s == q) ? y[q] : val;
+      a.hist_value[((size_t)slice * v.n_index + k) * v.ld + i] = val;
+    }
+    (void)src;
+  };
+  if (hist) {
+    save_slice(0, i);
+    if (live) a.hist_order[i] = (int)i;
   }
 
   double ll = 0.0;            // the same value in every thread
@@ -152,18 +173,23 @@ k_filter_persistent(View v, PersistArgs a) {
     const bool weigh = !datum_is_na(v, row, 0);
 
     // ---- gather (resampling of the previous weighed row), update, compare
+    const int rel = row - a.first;
     if (owe_resample) {
       const size_t src = resample_source_p(live ? i : N - 1);
       if (live) {
 #pragma unroll
         for (int s = 0; s < M::kState; ++s) y[s] = __ldcg(buf_prev + (size_t)s * v.ld + src);
+        if (hist) a.hist_order[(size_t)rel * N + i] = (int)src;
       }
       owe_resample = false;
+    } else if (hist && rel > 0 && live) {
+      a.hist_order[(size_t)rel * N + i] = (int)i;
     }
     double lw = neg_inf;
     if (live) {
       run_model_steps<M, SCR>(v, sd, ctx, 0, y, rng, t, n_steps, det, s_inv);
       touched = touched || n_steps > 0;
+      if (hist) save_slice(rel + 1, i);
       if (weigh) {
         const double *d = v.data + (size_t)row * v.data_sets * 2;
         lw = M::template compare<SCR>(y, __ldg(d), __ldg(d + 1), rng, ctx, det);
@@ -283,7 +309,10 @@ k_filter_persistent(View v, PersistArgs a) {
     if (live) {
 #pragma unroll
       for (int s = 0; s < M::kState; ++s) y[s] = __ldcg(buf_prev + (size_t)s * v.ld + src);
+      if (hist) a.hist_order[(size_t)(a.last - a.first) * N + i] = (int)src;
     }
+  } else if (!stopped && hist && live) {
+    a.hist_order[(size_t)(a.last - a.first) * N + i] = (int)i;
   }
   if (live) {
 #pragma unroll

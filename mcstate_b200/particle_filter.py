@@ -110,6 +110,22 @@ def check_time_step(curr, time_index, times, name):
                          % (name, time_index, times[time_index - 1, 1]))
 
 
+class _PendingHistory(dict):
+    """``history`` of a filter state that has not stepped yet, on the compiled path:
+    ``value`` / ``order`` are allocated on first access."""
+
+    def __init__(self, allocate, index):
+        super().__init__(index=index)
+        self._allocate = allocate
+
+    def __getitem__(self, key):
+        if key in ("value", "order") and not dict.__contains__(self, key):
+            value, order = self._allocate()
+            dict.__setitem__(self, "value", value)
+            dict.__setitem__(self, "order", order)
+        return dict.__getitem__(self, key)
+
+
 class _DeviceHistory:
     """Trajectories of a compiled-filter run that stayed in device memory: lineages
     are traced there on request (model.filter_history), so asking for one sampled
@@ -267,13 +283,25 @@ class particle_filter_state:
         self.history = None
         if save_history:
             length = times.shape[0] + 1
-            state = model.state(None if index_data is None else index_data["state"])
-            value = np.full(state.shape + (length,), np.nan)
-            value[..., 0] = state
-            order = np.empty(tuple(shape) + (length,), dtype=np.int64)
-            order[...] = np.arange(1, n_particles + 1).reshape((n_particles,) + (1,) * len(shape))
-            self.history = {"value": value, "order": order,
-                            "index": None if index_data is None else index_data["state"]}
+            index_state = None if index_data is None else index_data["state"]
+
+            def allocate():
+                # R/particle_filter_state.R:270-285
+                state = model.state(index_state)
+                value = np.full(state.shape + (length,), np.nan)
+                value[..., 0] = state
+                order = np.empty(tuple(shape) + (length,), dtype=np.int64)
+                order[...] = np.arange(1, n_particles + 1).reshape((n_particles,) + (1,) * len(shape))
+                return value, order
+
+            if compare is None:
+                # the compiled filter returns its own history and never writes these
+                # arrays ([n_index, N, T+1]: 160 MB at 2^16 particles, per run): build
+                # them only if somebody looks
+                self.history = _PendingHistory(allocate, index_state)
+            else:
+                value, order = allocate()
+                self.history = {"value": value, "order": order, "index": index_state}
 
         self._save_restart_time = check_save_restart(save_restart, data)
         self.restart_state = None

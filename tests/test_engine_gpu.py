@@ -561,6 +561,30 @@ def test_persistent_filter_equals_two_launch(dust, orc, sir_data, n):
     _same(a, b)
 
 
+def test_persistent_filter_trajectories(dust, sir_data):
+    n = 5000
+    t, x = _data(sir_data, 50)
+    xm = x.copy()
+    xm[[3, 4, 20]] = np.nan
+    for data_x, kw in ((x, {}), (xm, {}), (x, {"min_log_likelihood": -70.0})):
+        a, b = _pair(dust, "sir", {}, n, 9)
+        for m in (a, b):
+            _set_data(m, t, data_x)
+            m.set_index([1, 3, 5])
+        ra = a.filter(save_trajectories=True, **kw)
+        rb = b.filter(save_trajectories=True, **kw)
+        assert np.array_equal(ra["log_likelihood"], rb["log_likelihood"])
+        assert np.array_equal(ra["trajectories"], rb["trajectories"], equal_nan=True)
+        _same(a, b)
+    # the lazily traced lineages too
+    a, b = _pair(dust, "sir", {}, n, 10)
+    for m in (a, b):
+        _set_data(m, t, x)
+        m.filter(save_trajectories="device")
+    pick = [1, 77, n]
+    assert np.array_equal(a.filter_history(pick), b.filter_history(pick))
+
+
 def test_persistent_filter_special_rows(dust, sir_data):
     n = 3000
     t, x = _data(sir_data, 40)
