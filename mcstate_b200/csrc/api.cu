@@ -77,10 +77,11 @@ const ModelDesc kModels[] = {
 struct ModelTables {
   int pop[3];
   int n_const;
+  int freq;      // parameter slot of the steps-per-incidence-interval count, or -1
 };
-const ModelTables kModelTables[] = {{{4, 2, 5}, mcb::SirModel::kConst},
-                                    {{5, 3, 6}, mcb::SirsModel::kConst},
-                                    {{-1, -1, -1}, 0}};
+const ModelTables kModelTables[] = {{{4, 2, 5}, mcb::SirModel::kConst, 6},
+                                    {{5, 3, 6}, mcb::SirsModel::kConst, 7},
+                                    {{-1, -1, -1}, 0, -1}};
 constexpr int kNumModels = sizeof(kModels) / sizeof(kModels[0]);
 constexpr size_t kMaxWalkRows = 2048;  // counts covered by a walk table (samplers.cuh)
 
@@ -116,6 +117,10 @@ int device_constants(int device) {
   inv[0] = make_double2(0.0, 0.0);
   for (int k = 1; k < mcb::kInvSmall; ++k) inv[k] = make_double2((double)k, 1.0 / (double)k);
   MCB_CUDA(cudaMemcpyToSymbol(mcb::c_inv_small, inv, sizeof inv));
+  double2 inv_g[mcb::kInvSmall + 1];
+  for (int k = 0; k < mcb::kInvSmall; ++k) inv_g[k] = inv[k];
+  inv_g[mcb::kInvSmall] = inv[mcb::kInvSmall - 1];
+  MCB_CUDA(cudaMemcpyToSymbol(mcb::g_inv_small, inv_g, sizeof inv_g));
   done[device] = true;
   return MCB_OK;
 }
@@ -235,6 +240,25 @@ int ensure_stage(mcb_model *m, size_t bytes) {
 
 unsigned blocks_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
+// Bit k of the result: step t0 + k starts a new incidence interval (step % freq == 0).
+// Known on the host when every parameter set has the same freq and the launch covers at
+// most 32 steps (the usual case); else the kernel works it out per thread.
+uint32_t reset_mask(const mcb_model *m, uint64_t t0, uint32_t n_steps, int *valid) {
+  *valid = 0;
+  const int slot = kModelTables[m->model_id].freq;
+  if (slot < 0 || n_steps > 32 || m->pars_host.empty()) return 0;
+  const double f0 = m->pars_host[slot];
+  for (size_t p = 1; p < m->v.n_sets; ++p)
+    if (m->pars_host[p * mcb::kMaxPar + slot] != f0) return 0;
+  if (!(f0 >= 1.0) || f0 > 4294967295.0 || f0 != std::floor(f0)) return 0;
+  const uint64_t freq = (uint64_t)f0;
+  uint32_t mask = 0;
+  for (uint32_t k = 0; k < n_steps; ++k)
+    if ((t0 + k) % freq == 0) mask |= 1u << k;
+  *valid = 1;
+  return mask;
+}
+
 // Launch with (chained = true) programmatic dependent launch: the kernel may be
 // scheduled while its predecessor in the stream drains -- its blocks do their
 // prologue and then wait (griddepcontrol.wait) until the predecessor has completed
@@ -261,6 +285,7 @@ template <class M, int SCR>
 void launch_run_compare(mcb_model *m, const double *y_in, double *y_out, uint64_t t0,
                         uint32_t n_steps, int prev_row, int row, double *hist, int *kappa_out) {
   const unsigned grid = blocks_for(m->v.n_total, mcb::kRunThreads);
+  m->v.reset_mask = reset_mask(m, t0, n_steps, &m->v.reset_mask_valid);
   if (hist)
     launch_chained(m, m->chain, mcb::k_run_compare<M, SCR, true>, grid, mcb::kRunThreads, m->v,
                    y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out);
@@ -529,6 +554,7 @@ int launch_persistent(mcb_model *m, int first, int last, bool hist) {
   a.first_out_tmp = (weighed & 1) ? 1 : 0;   // so that the last weighed row writes y_tmp
   a.hist_value = hist ? m->d_hist_value : nullptr;
   a.hist_order = hist ? m->d_hist_order : nullptr;
+  v.reset_mask_valid = 0;   // one launch covers rows with different start steps
   void *args[] = {&v, &a};
   const unsigned grid = blocks_for(v.n_total, mcb::kPersistThreads);
   MCB_CUDA(cudaLaunchCooperativeKernel(persistent_kernel_for(m), dim3(grid),

@@ -74,6 +74,10 @@ struct View {
   // so the shared stream advances identically everywhere.  n_fs == n_sets: one stream
   // per set (independent filters batched in one handle).  Streams n_total .. n_total+n_fs-1.
   int n_fs, n_sets_global, set_offset;
+  // bit k: step t0 + k of this launch starts a new incidence interval; valid when the
+  // host could tell (same freq in every set, at most 32 steps)
+  uint32_t reset_mask;
+  int reset_mask_valid;
   const unsigned char *na_global;  // [n_data][n_sets_global] datum is NA, or nullptr
 };
 
@@ -262,16 +266,22 @@ __device__ __forceinline__ void run_model_steps(const View &v, const SetData &sd
     if (!det && M::lean_load(sd, y, yi, lc)) {
       // the usual case: integer compartments, setup from the memo tables, no calls
       const uint32_t s_inv_addr = (uint32_t)__cvta_generic_to_shared(s_inv);
-      const uint32_t freq = (uint32_t)__ldg(sd.derived + M::D_FREQ);
-      uint32_t phase = t0 <= 0xffffffffULL ? (uint32_t)t0 % freq : (uint32_t)(t0 % freq);
       bool ok = true;
+      uint32_t freq = 1, phase = 0;
+      if (!v.reset_mask_valid) {
+        freq = (uint32_t)__ldg(sd.derived + M::D_FREQ);
+        phase = t0 <= 0xffffffffULL ? (uint32_t)t0 % freq : (uint32_t)(t0 % freq);
+      }
       while (ok && done < n_steps) {
         // bit k: step done + k starts a new incidence interval
         const uint32_t nk = min(n_steps - done, 32u);
-        uint32_t resets = 0;
-        for (uint32_t k = 0; k < nk; ++k) {
-          resets |= (phase == 0 ? 1u : 0u) << k;
-          phase = phase + 1 == freq ? 0 : phase + 1;
+        uint32_t resets = v.reset_mask;
+        if (!v.reset_mask_valid) {
+          resets = 0;
+          for (uint32_t k = 0; k < nk; ++k) {
+            resets |= (phase == 0 ? 1u : 0u) << k;
+            phase = phase + 1 == freq ? 0 : phase + 1;
+          }
         }
         for (uint32_t k = 0; k < nk; ++k) {
           ok = M::template lean_update<SCR>((resets & 1u) != 0, yi, rng, lc, tabs, s_inv_addr);
@@ -307,7 +317,7 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
   // programmatic dependent launch: let the next kernel be scheduled as this one
   // drains, and do not read anything an earlier kernel wrote before the wait
   grid_launch_dependents();
-  if (threadIdx.x <= kInvSmall) s_inv[threadIdx.x] = c_inv_small[min((int)threadIdx.x, kInvSmall - 1)];
+  if (threadIdx.x <= kInvSmall) s_inv[threadIdx.x] = __ldg(g_inv_small + threadIdx.x);
   grid_dependency_wait();
   if (v.flags[0]) return;
   __syncthreads();

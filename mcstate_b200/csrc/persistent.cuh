@@ -80,7 +80,7 @@ k_filter_persistent(View v, PersistArgs a) {
   const size_t i = (size_t)blockIdx.x * kPersistThreads + tid;
   const size_t N = v.n_total;
   const bool live = i < N;
-  if (tid <= kInvSmall) s_inv[tid] = c_inv_small[min(tid, kInvSmall - 1)];
+  if (tid <= kInvSmall) s_inv[tid] = __ldg(g_inv_small + tid);
   __syncthreads();
 
   const SetData sd{v.derived, v.n_tab};

@@ -52,6 +52,10 @@ __device__ __forceinline__ double pow_int(double x, int n) {
 // with IEEE division: the walk reads its divisor and reciprocal with one uniform load
 constexpr int kInvSmall = 64;
 __constant__ double2 c_inv_small[kInvSmall];
+// the same table in global memory: a block stages it in shared memory with one
+// coalesced load per thread (per-thread indexing of the constant bank serialises);
+// one spare entry (the lean walk looks two entries ahead)
+__device__ double2 g_inv_small[kInvSmall + 1];
 __constant__ double c_stirling_tail[10] = {
     0.0810614667953272,  0.0413406959554092,  0.0276779256849983, 0.02079067210376509,
     0.0166446911898211,  0.0138761288230707,  0.0118967099458917, 0.0104112652619720,
