@@ -420,23 +420,25 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
 // (scale_log_weights, R/particle_filter.R:570-587) and the resampling
 // thresholds.  One thread.  Returns true if the set is dead (all -Inf).
 // ---------------------------------------------------------------------------
+// u, mx, ll_old: the set's resampling uniform, max log-weight and likelihood so far,
+// loaded by the caller at the start of the kernel (they do not change during it) so
+// that no dependent global load sits on the tail of the weights stage.
 __device__ __forceinline__ bool finish_set(const View &v, int row, size_t set,
-                                           unsigned long long tot) {
+                                           unsigned long long tot, double u, double mx,
+                                           double ll_old) {
   const double n = (double)v.n_particles;
   const double tot_d = (double)tot;
-  const double u = v.u_draws[(size_t)(row < 0 ? 0 : row) * v.n_sets + set];
   SetInfo si;
   si.uu0 = tot_d * u / n;
   si.du = tot_d / n;
   v.setinfo[set] = si;
   if (row < 0) return false;
-  const double mx = key_to_double(v.wmax[(size_t)row * v.n_sets + set]);
   if (!(mx > __longlong_as_double(0xfff0000000000000LL)) || tot == 0) {
     v.ll[set] = __longlong_as_double(0xfff0000000000000LL);
     return true;
   }
   const double mean = (tot_d * bits_to_double((uint64_t)(1023 - v.shift) << 52)) / n;
-  v.ll[set] += det_log(mean) + mx;
+  v.ll[set] = ll_old + (det_log(mean) + mx);
   return false;
 }
 
@@ -448,7 +450,8 @@ __device__ __forceinline__ bool finish_set(const View &v, int row, size_t set,
 // R/particle_filter_state.R:463-474 over all the sets.
 //   ticket [n_sets] per-set counters, [n_sets] the counter of finished sets,
 //          [n_sets + 1] "some set is dead" of this interval
-__device__ __forceinline__ void finalize_set(const View &v, int row, size_t set) {
+__device__ __forceinline__ void finalize_set(const View &v, int row, size_t set, double pre_u,
+                                             double pre_mx, double pre_ll) {
   __shared__ unsigned long long s_tot[kTileThreads / 32];
   __shared__ unsigned long long s_carry;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -467,7 +470,7 @@ __device__ __forceinline__ void finalize_set(const View &v, int row, size_t set)
       }
       if (lane < T) ts[lane] = incl;
       const unsigned long long tot = shfl_u64(incl, 31);
-      if (lane == 0) dead = finish_set(v, row, set, tot);
+      if (lane == 0) dead = finish_set(v, row, set, tot, pre_u, pre_mx, pre_ll);
     }
   } else if (weighed) {
     // a big set: the whole block scans its tiles; each thread owns `per`
@@ -506,7 +509,7 @@ __device__ __forceinline__ void finalize_set(const View &v, int row, size_t set)
       if (tid == kTileThreads - 1) s_carry = offset + local;
       __syncthreads();
     }
-    if (tid == 0) dead = finish_set(v, row, set, s_carry);
+    if (tid == 0) dead = finish_set(v, row, set, s_carry, pre_u, pre_mx, pre_ll);
   }
   if (tid != 0) return;
   bool any_dead = dead;
@@ -559,8 +562,13 @@ __global__ void __launch_bounds__(kTileThreads, 4) k_weights_scan(View v, int ro
   if (v.flags[0]) return;
   const size_t set = blockIdx.x / v.tiles_per_set;
   const int tile = blockIdx.x % v.tiles_per_set;
+  // what the set's finishing thread will need, asked for now (finish_set)
+  double pre_u = 0.0, pre_ll = 0.0, mx = 0.0;
+  if (threadIdx.x == 0) {
+    pre_u = v.u_draws[(size_t)(row < 0 ? 0 : row) * v.n_sets + set];
+    pre_ll = v.ll[set];
+  }
   if (GIVEN || !datum_is_na(v, row, set)) {
-    double mx = 0.0;
     if (!GIVEN) mx = key_to_double(v.wmax[(size_t)row * v.n_sets + set]);
     const bool dead = !GIVEN && !(mx > __longlong_as_double(0xfff0000000000000LL));
     const double scale = bits_to_double((uint64_t)(1023 + v.shift) << 52);
@@ -630,7 +638,7 @@ __global__ void __launch_bounds__(kTileThreads, 4) k_weights_scan(View v, int ro
   if (!s_last) return;
   if (threadIdx.x == 0) v.ticket[set] = 0;
   __threadfence();
-  finalize_set(v, row, set);
+  finalize_set(v, row, set, pre_u, mx, pre_ll);
 }
 
 // ---------------------------------------------------------------------------
