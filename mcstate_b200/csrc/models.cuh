@@ -80,24 +80,35 @@ __device__ __forceinline__ bool to_counts(const double *y, int *yi) {
 // infection table.  Returns the draw, or -1 (generator untouched) when the
 // general code must take over: probability outside (0, 1/2], S q >= 10 (BTRS), or
 // a walk that met one of its rare exits.
+// f0 = (1-q)^S is asked for separately (infection_f0) so a model can compute it while
+// the loads of another draw are in flight: it consumes no uniform.
+__device__ __forceinline__ double infection_f0(int S, double2 e, int pow_groups) {
+  return pow_int_lean(1.0 - e.x, S, pow_groups);
+}
 template <int SCR>
-__device__ __forceinline__ int draw_infection_lean(Xoshiro &rng, int S, double2 e,
-                                                   int pow_groups, uint32_t s_inv) {
+__device__ __forceinline__ int draw_infection_lean(Xoshiro &rng, int S, double2 e, double f0,
+                                                   uint32_t s_inv) {
   if (S == 0 || e.x == 0.0) return 0;
   const double Sd1 = (double)(S + 1);
   if (e.x < 0.0 || (Sd1 - 1.0) * e.x >= 10.0) return -1;
-  const int k = walk_lean<SCR>(rng, S, e.y, pow_int_lean(1.0 - e.x, S, pow_groups), e.y * Sd1, s_inv);
+  const int k = walk_lean<SCR>(rng, S, e.y, f0, e.y * Sd1, s_inv);
   if (k < 0) xo_rewind(rng);
   return k;
 }
 
 // Binomial(n, p) for the set's constant draw `c`: row n of its walk table, or -1
 // (generator untouched) when the table has no such row.
+// row n of constant draw `set_const`'s walk table (n clamped into the table: the caller
+// checks n < n_wrows before it uses what was loaded)
+__device__ __forceinline__ const double *walk_row_ptr(int n, uint32_t set_const,
+                                                      const LeanTabs &t) {
+  return t.walk + (size_t)(set_const * t.n_wrows + min((uint32_t)n, t.n_wrows - 1)) * kWalkK;
+}
 template <int SCR>
-__device__ __forceinline__ int draw_const_lean(Xoshiro &rng, int n, uint32_t set_const,
+__device__ __forceinline__ int draw_const_lean(Xoshiro &rng, int n, const double *row, double4 F,
                                                const LeanTabs &t) {
   if ((uint32_t)n >= t.n_wrows) return -1;
-  return draw_binomial_table<SCR>(rng, t.walk + ((size_t)(set_const * t.n_wrows + (uint32_t)n) * kWalkK));
+  return draw_binomial_table<SCR>(rng, row, F);
 }
 
 struct SirModel {
@@ -213,12 +224,19 @@ struct SirModel {
                                                      const Lean &c, const LeanTabs &t,
                                                      uint32_t s_inv) {
     const int S = y[0], I = y[1];
+    // both draws' table entries depend on the state at the start of the step alone:
+    // ask for them together, and raise (1-q)^S -- which takes no uniform -- while the
+    // walk-table row is on its way
+    const double *row_ir = walk_row_ptr(I, c.set * kConst + C_IR, t);
+    const double2 e_si = __ldg(t.inf + (c.set * t.n_tab + (uint32_t)I));
+    const double4 F_ir = ldg_f64x4(row_ir);
+    const double f0 = infection_f0(S, e_si, t.pow_groups);
     int n_IR = 0;
     if (I != 0) {
-      n_IR = draw_const_lean<SCR>(rng, I, c.set * kConst + C_IR, t);
+      n_IR = draw_const_lean<SCR>(rng, I, row_ir, F_ir, t);
       if (n_IR < 0) return false;
     }
-    const int n_SI = draw_infection_lean<SCR>(rng, S, __ldg(t.inf + (c.set * t.n_tab + (uint32_t)I)), t.pow_groups, s_inv);
+    const int n_SI = draw_infection_lean<SCR>(rng, S, e_si, f0, s_inv);
     if (n_SI < 0) {
       if (I != 0) xo_rewind(rng);  // the recovery draw's uniform
       return false;
@@ -331,13 +349,14 @@ struct SirsModel {
                                                      uint32_t s_inv) {
     const int S = y[0], I = y[1], R = y[2];
     const double2 e_si = __ldg(t.inf + (c.set * t.n_tab + (uint32_t)I));
-    const int n_SI = draw_infection_lean<SCR>(rng, S, e_si, t.pow_groups, s_inv);
+    const int n_SI = draw_infection_lean<SCR>(rng, S, e_si, infection_f0(S, e_si, t.pow_groups), s_inv);
     if (n_SI < 0) return false;
     // did the infection draw take a uniform?  (it returns 0 without one for S = 0 or p = 0)
     const bool si_drew = S != 0 && e_si.x != 0.0;
     int n_IR = 0;
     if (I != 0) {
-      n_IR = draw_const_lean<SCR>(rng, I, c.set * kConst + C_IR, t);
+      const double *row = walk_row_ptr(I, c.set * kConst + C_IR, t);
+      n_IR = draw_const_lean<SCR>(rng, I, row, ldg_f64x4(row), t);
       if (n_IR < 0) {
         if (si_drew) xo_rewind(rng);
         return false;
@@ -345,7 +364,8 @@ struct SirsModel {
     }
     int n_RS = 0;
     if (R != 0) {
-      n_RS = draw_const_lean<SCR>(rng, R, c.set * kConst + C_RS, t);
+      const double *row = walk_row_ptr(R, c.set * kConst + C_RS, t);
+      n_RS = draw_const_lean<SCR>(rng, R, row, ldg_f64x4(row), t);
       if (n_RS < 0) {
         if (I != 0) xo_rewind(rng);
         if (si_drew) xo_rewind(rng);

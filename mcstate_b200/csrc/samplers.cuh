@@ -289,8 +289,8 @@ __device__ __forceinline__ void fill_walk_row(double p, double q, double qq, dou
 // a walk past the row): the caller hands the rest of the interval to the general
 // code.  A -1 entry keeps the chain going (u >= -1) to the end of the row.
 template <int SCR>
-__device__ __forceinline__ int draw_binomial_table(Xoshiro &rng, const double *__restrict__ row) {
-  double4 F = ldg_f64x4(row);
+__device__ __forceinline__ int draw_binomial_table(Xoshiro &rng, const double *__restrict__ row,
+                                                   double4 F) {   // F = the row's first four entries
   if (F.x < 0.0) return -1;
   double u = xo_real<SCR>(rng);
   int k = 0;
