@@ -199,11 +199,13 @@ __device__ __forceinline__ double4 ldg_f64x4(const double *p) {
 // table has another entry; the two rare reasons are told apart after the walk
 // (the order of the reference's tests is kept: a stalled f abandons the attempt
 // whatever u is).
-// Every lane of a warp is at the same k in the same step, so the first four
-// steps are written out with their divisor known at compile time: g/1, g/2 and
-// g/4 are exact scalings (g is away from underflow), g/3 takes its reciprocal as
-// an immediate.  The loop from k = 5 is unrolled by two so f and its successor
-// swap roles without moves.
+// Every lane of a warp is at the same k in the same step, so the first MCB_PEEL
+// steps are written out with their divisor known at compile time: g/1, g/2, g/4,
+// g/8 are exact scalings (g is away from underflow), the others take k and its
+// reciprocal as immediates (no table load, no address arithmetic).  A warp walks
+// as far as its slowest lane (about 8 steps at the benchmark's parameters), so
+// these steps are what nearly every warp executes.  The loop after them is
+// unrolled by two so f and its successor swap roles without moves.
 #define MCB_WALK_STEP(K, FACTOR)                                    \
   u -= f;                                                           \
   fn = f * ((FACTOR) - r);                                          \
@@ -221,8 +223,33 @@ __device__ __forceinline__ int walk_lean(Xoshiro &rng, int n, double r, double f
   MCB_WALK_STEP(2, g * 0.5)
   MCB_WALK_STEP(3, div_small_int(g, 3.0, 1.0 / 3.0))
   MCB_WALK_STEP(4, g * 0.25)
+#ifndef MCB_PEEL
+#define MCB_PEEL 12   // measured at 2^20: 4 -> 90.1 us, 8 -> 88.0, 12 -> 87.2, 16 -> 87.4
+#endif
+#if MCB_PEEL >= 6
+  MCB_WALK_STEP(5, div_small_int(g, 5.0, 1.0 / 5.0))
+  MCB_WALK_STEP(6, div_small_int(g, 6.0, 1.0 / 6.0))
+#endif
+#if MCB_PEEL >= 8
+  MCB_WALK_STEP(7, div_small_int(g, 7.0, 1.0 / 7.0))
+  MCB_WALK_STEP(8, g * 0.125)
+#endif
+#if MCB_PEEL >= 10
+  MCB_WALK_STEP(9, div_small_int(g, 9.0, 1.0 / 9.0))
+  MCB_WALK_STEP(10, div_small_int(g, 10.0, 1.0 / 10.0))
+#endif
+#if MCB_PEEL >= 12
+  MCB_WALK_STEP(11, div_small_int(g, 11.0, 1.0 / 11.0))
+  MCB_WALK_STEP(12, div_small_int(g, 12.0, 1.0 / 12.0))
+#endif
+#if MCB_PEEL >= 16
+  MCB_WALK_STEP(13, div_small_int(g, 13.0, 1.0 / 13.0))
+  MCB_WALK_STEP(14, div_small_int(g, 14.0, 1.0 / 14.0))
+  MCB_WALK_STEP(15, div_small_int(g, 15.0, 1.0 / 15.0))
+  MCB_WALK_STEP(16, g * 0.0625)
+#endif
   {
-    uint32_t a = s_inv_addr + 16u * 4u;
+    uint32_t a = s_inv_addr + 16u * (uint32_t)(MCB_PEEL < 6 ? 4 : MCB_PEEL);
     const uint32_t a_end = s_inv_addr + 16u * (uint32_t)kmax;
     for (;;) {
       // The factors c_k = g/k - r do not depend on f or u: the next two are computed
