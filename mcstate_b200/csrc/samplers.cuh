@@ -206,80 +206,93 @@ __device__ __forceinline__ double4 ldg_f64x4(const double *p) {
 // as far as its slowest lane (about 8 steps at the benchmark's parameters), so
 // these steps are what nearly every warp executes.  The loop after them is
 // unrolled by two so f and its successor swap roles without moves.
-#define MCB_WALK_STEP(K, FACTOR)                                    \
-  u -= f;                                                           \
-  fn = f * ((FACTOR) - r);                                          \
-  if (!((u >= fn) & (fn != f) & ((K) < kmax))) { k = (K); goto walk_out; } \
+#ifndef MCB_PEEL
+#define MCB_PEEL 12   // measured at 2^20: 4 -> 90.1 us, 8 -> 88.0, 12 -> 87.2, 16 -> 87.4
+#endif
+// RN(1/k) for the written-out steps, as constant-bank operands (a 64-bit immediate
+// would cost two uniform moves per use)
+__constant__ double c_recip[17] = {0.0,        1.0,        1.0 / 2.0,  1.0 / 3.0,  1.0 / 4.0,
+                                   1.0 / 5.0,  1.0 / 6.0,  1.0 / 7.0,  1.0 / 8.0,  1.0 / 9.0,
+                                   1.0 / 10.0, 1.0 / 11.0, 1.0 / 12.0, 1.0 / 13.0, 1.0 / 14.0,
+                                   1.0 / 15.0, 1.0 / 16.0};
+// One written-out step.  The two ways out need nothing but k (a stalled f abandons
+// the attempt whatever u is -- the order of the reference's tests), so no value has to
+// be kept in a fixed register for them and the steps chain without moves.  (Measured:
+// one compound exit to a common label 87.2 us, these two returns 86.3, per-step
+// landing pads 88.6.)
+#define MCB_WALK_STEP(K, FACTOR)                 \
+  u -= f;                                        \
+  fn = f * ((FACTOR) - r);                       \
+  if (fn == f) return -1;                        \
+  if (!(u >= fn)) return (K);                    \
   f = fn;
+#define MCB_WALK_DIV(K) div_small_int(g, (double)(K), c_recip[K])
 template <int SCR>
 __device__ __forceinline__ int walk_lean(Xoshiro &rng, int n, double r, double f0, double g,
                                          uint32_t s_inv_addr) {
   const int kmax = min(n, kInvSmall - 1);
   double u = xo_real<SCR>(rng);
   double f = f0, fn;
-  int k;
   if (!(u >= f)) return 0;   // n >= 1: there is a k = 1 to move to
-  MCB_WALK_STEP(1, g)
-  MCB_WALK_STEP(2, g * 0.5)
-  MCB_WALK_STEP(3, div_small_int(g, 3.0, 1.0 / 3.0))
-  MCB_WALK_STEP(4, g * 0.25)
-#ifndef MCB_PEEL
-#define MCB_PEEL 12   // measured at 2^20: 4 -> 90.1 us, 8 -> 88.0, 12 -> 87.2, 16 -> 87.4
-#endif
+  uint32_t a = s_inv_addr;
+  if (kmax > MCB_PEEL) {     // the usual case: every written-out step has a successor
+    MCB_WALK_STEP(1, g)
+    MCB_WALK_STEP(2, g * 0.5)
+    MCB_WALK_STEP(3, MCB_WALK_DIV(3))
+    MCB_WALK_STEP(4, g * 0.25)
 #if MCB_PEEL >= 6
-  MCB_WALK_STEP(5, div_small_int(g, 5.0, 1.0 / 5.0))
-  MCB_WALK_STEP(6, div_small_int(g, 6.0, 1.0 / 6.0))
+    MCB_WALK_STEP(5, MCB_WALK_DIV(5))
+    MCB_WALK_STEP(6, MCB_WALK_DIV(6))
 #endif
 #if MCB_PEEL >= 8
-  MCB_WALK_STEP(7, div_small_int(g, 7.0, 1.0 / 7.0))
-  MCB_WALK_STEP(8, g * 0.125)
+    MCB_WALK_STEP(7, MCB_WALK_DIV(7))
+    MCB_WALK_STEP(8, g * 0.125)
 #endif
 #if MCB_PEEL >= 10
-  MCB_WALK_STEP(9, div_small_int(g, 9.0, 1.0 / 9.0))
-  MCB_WALK_STEP(10, div_small_int(g, 10.0, 1.0 / 10.0))
+    MCB_WALK_STEP(9, MCB_WALK_DIV(9))
+    MCB_WALK_STEP(10, MCB_WALK_DIV(10))
 #endif
 #if MCB_PEEL >= 12
-  MCB_WALK_STEP(11, div_small_int(g, 11.0, 1.0 / 11.0))
-  MCB_WALK_STEP(12, div_small_int(g, 12.0, 1.0 / 12.0))
+    MCB_WALK_STEP(11, MCB_WALK_DIV(11))
+    MCB_WALK_STEP(12, MCB_WALK_DIV(12))
 #endif
 #if MCB_PEEL >= 16
-  MCB_WALK_STEP(13, div_small_int(g, 13.0, 1.0 / 13.0))
-  MCB_WALK_STEP(14, div_small_int(g, 14.0, 1.0 / 14.0))
-  MCB_WALK_STEP(15, div_small_int(g, 15.0, 1.0 / 15.0))
-  MCB_WALK_STEP(16, g * 0.0625)
+    MCB_WALK_STEP(13, MCB_WALK_DIV(13))
+    MCB_WALK_STEP(14, MCB_WALK_DIV(14))
+    MCB_WALK_STEP(15, MCB_WALK_DIV(15))
+    MCB_WALK_STEP(16, g * 0.0625)
 #endif
-  {
-    uint32_t a = s_inv_addr + 16u * (uint32_t)(MCB_PEEL < 6 ? 4 : MCB_PEEL);
-    const uint32_t a_end = s_inv_addr + 16u * (uint32_t)kmax;
-    for (;;) {
-      // The factors c_k = g/k - r do not depend on f or u: the next two are computed
-      // side by side (two independent dependency chains), then applied in order.
-      // The second may go unused; the table has one spare entry for its load.
-      const double2 e1 = lds_f64x2(a + 16);
-      const double2 e2 = lds_f64x2(a + 32);
-      double q1 = g * e1.y, q2 = g * e2.y;
-      double r1 = fma(-q1, e1.x, g), r2 = fma(-q2, e2.x, g);
-      q1 = fma(r1, e1.y, q1); q2 = fma(r2, e2.y, q2);
-      r1 = fma(-q1, e1.x, g); r2 = fma(-q2, e2.x, g);
-      const double c1 = fma(r1, e1.y, q1) - r, c2 = fma(r2, e2.y, q2) - r;
-      u -= f;
-      fn = f * c1;
-      a += 16;
-      if (!((u >= fn) & (fn != f) & (a < a_end))) break;
-      u -= fn;
-      f = fn;
-      fn = f * c2;
-      a += 16;
-      if (!((u >= fn) & (fn != f) & (a < a_end))) break;
-      f = fn;
-    }
-    k = (int)((a - s_inv_addr) >> 4);
+    a += 16u * (uint32_t)(MCB_PEEL < 6 ? 4 : MCB_PEEL);
   }
-walk_out:
+  // whatever is left (and counts too small for the written-out steps): the loop
+  const uint32_t a_end = s_inv_addr + 16u * (uint32_t)kmax;
+  for (;;) {
+    // The factors c_k = g/k - r do not depend on f or u: the next two are computed
+    // side by side (two independent dependency chains), then applied in order.
+    // The second may go unused; the table has one spare entry for its load.
+    const double2 e1 = lds_f64x2(a + 16);
+    const double2 e2 = lds_f64x2(a + 32);
+    double q1 = g * e1.y, q2 = g * e2.y;
+    double r1 = fma(-q1, e1.x, g), r2 = fma(-q2, e2.x, g);
+    q1 = fma(r1, e1.y, q1); q2 = fma(r2, e2.y, q2);
+    r1 = fma(-q1, e1.x, g); r2 = fma(-q2, e2.x, g);
+    const double c1 = fma(r1, e1.y, q1) - r, c2 = fma(r2, e2.y, q2) - r;
+    u -= f;
+    fn = f * c1;
+    a += 16;
+    if (!((u >= fn) & (fn != f) & (a < a_end))) break;
+    u -= fn;
+    f = fn;
+    fn = f * c2;
+    a += 16;
+    if (!((u >= fn) & (fn != f) & (a < a_end))) break;
+    f = fn;
+  }
   // stalled, or out of table with u >= f still
-  return ((fn == f) | (u >= fn)) ? -1 : k;
+  return ((fn == f) | (u >= fn)) ? -1 : (int)((a - s_inv_addr) >> 4);
 }
 #undef MCB_WALK_STEP
+#undef MCB_WALK_DIV
 
 // ---------------------------------------------------------------------------
 // Walk tables: a draw whose probability is fixed by the parameter set
