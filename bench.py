@@ -57,7 +57,13 @@ def ncu_traffic_bytes(kernel):
     import csv
     import glob
 
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_full_summary_r*.csv")))
+    import re
+
+    def version(path):   # ..._r01_v26.csv -> (1, 26): the latest capture, not the last name
+        return tuple(int(x) for x in re.findall(r"\d+", os.path.basename(path)))
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_full_summary_r*.csv")),
+                   key=version)
     if not files:
         return None, None
     try:
@@ -100,7 +106,7 @@ class ClockSampler:
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.02)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -244,12 +250,16 @@ def run_engine(args):
     launches0 = model.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    with ClockSampler(local) as clocks:
-        ev0.record(stream)
-        for _ in range(args.steps):
-            ll = step_resident()
-        ev1.record(stream)
-        barrier()
+    # clocks / throttle reasons are sampled from here to the end of the e2e loop: three
+    # back-to-back passes over the same workload (the headline pass alone lasts ~0.1 s,
+    # one nvidia-smi query)
+    clocks = ClockSampler(local)
+    clocks.__enter__()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        ll = step_resident()
+    ev1.record(stream)
+    barrier()
     ms_total = ev0.elapsed_time(ev1)
     launches = model.launch_count() - launches0
 
@@ -279,6 +289,7 @@ def run_engine(args):
         step_e2e()
     barrier()
     e2e_s = time.perf_counter() - t0
+    clocks.__exit__(None, None, None)
 
     # ---- not the headline: BASELINE config C3's filter (one pMCMC chain of 2^16 particles
     # per GPU) on the single-launch path (csrc/persistent.cuh) and on the two-launch path

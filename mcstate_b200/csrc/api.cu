@@ -537,7 +537,7 @@ int persistent_capacity(const mcb_model *m) {
     return 0;
   }
   const int cap = per_sm * sms;
-  return cap < mcb::kPersistMaxBlocks ? cap : mcb::kPersistMaxBlocks;
+  return cap < mcb::kPersistUseBlocks ? cap : mcb::kPersistUseBlocks;
 }
 
 // One parameter set, no snapshots, every particle resident at once: the whole call is

@@ -38,6 +38,10 @@ namespace mcb {
 
 constexpr int kPersistThreads = 128;
 constexpr int kPersistMaxBlocks = 1184;   // 8 per SM on 148 SMs: 151 552 particles
+// ...but past ~100 000 particles the SMs are full either way and the two-launch path's
+// leaner run kernel wins (measured: 75 000 -> 24.3 vs 28.9 us per interval, 131 072 ->
+// 31.6 vs 29.1): the single launch is used up to this many blocks
+constexpr int kPersistUseBlocks = 800;
 #ifndef MCB_PERSIST_MINBLOCKS
 #define MCB_PERSIST_MINBLOCKS 8
 #endif
