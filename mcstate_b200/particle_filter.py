@@ -228,6 +228,147 @@ def _pfs_compare_multiple(has_multiple_data, state, compare, data, pars):
             "weights": np.stack([w["weights"] for w in ws], axis=1)}
 
 
+# ---------------------------------------------------------------------------
+# multistage parameters (R/particle_filter_multistage.R): the model's parameters --
+# and, through transform_state, its state -- change at given times of the run
+# ---------------------------------------------------------------------------
+def transform_state_identity(x, *args):
+    return x
+
+
+class multistage_epoch:
+    """``multistage_epoch(start, pars = NULL, transform_state = NULL)``
+    (R/particle_filter_multistage.R:113-126).  ``start`` is in the data's time units."""
+
+    def __init__(self, start, pars=None, transform_state=None):
+        if transform_state is None:
+            transform_state = transform_state_identity
+        elif not callable(transform_state):
+            raise TypeError("'transform_state' must be a function")
+        self.start, self.pars, self.transform_state = start, pars, transform_state
+
+
+class multistage_parameters(list):
+    """``multistage_parameters(pars, epochs)`` (R/particle_filter_multistage.R:60-93): a
+    list of stages ``dict(pars, start, transform_state)``, the first being the base."""
+
+    def __init__(self, pars, epochs):
+        if not all(isinstance(e, multistage_epoch) for e in epochs):
+            raise TypeError("Expected all elements of 'epochs' to be 'multistage_epoch' objects")
+        sets_pars = [e.pars is None for e in epochs]
+        if any(sets_pars) and not all(sets_pars):
+            raise ValueError("If changing parameters, all epochs must contain 'pars'")
+        stages = [{"pars": pars, "start": None, "transform_state": None}]
+        stages += [{"pars": e.pars, "start": e.start, "transform_state": e.transform_state}
+                   for e in epochs]
+        super().__init__(stages)
+
+
+def filter_check_times(pars, data, save_restart):
+    """R/particle_filter_multistage.R:134-188: which stages overlap the data, the (1-based)
+    row index each one ends at, and which restart times fall into which stage."""
+    times = data.model_times
+    stages = [dict(st) for st in pars]
+    time_pars = np.array([st["start"] for st in stages[1:]], dtype=float)
+    start = np.concatenate([[-np.inf], time_pars])
+    end = np.concatenate([time_pars, [np.inf]])
+    drop = (end <= times[0, 0]) | (start > times[-1, 1])
+    index = [i + 1 for i in range(len(stages)) if not drop[i]]
+    stages = [st for st, d in zip(stages, drop) if not d]
+    time_pars = np.array([st["start"] for st in stages[1:]], dtype=float)
+    ends = list(times[:, 1])
+    time_index = [ends.index(t) + 1 if t in ends else None for t in time_pars] + [len(ends)]
+    bad = [str(index[i]) for i, t in enumerate(time_index) if t is None]
+    if bad:
+        raise ValueError("Could not map epoch to filter time: error for stage %s" % ", ".join(bad))
+    sr = [] if save_restart is None else list(np.atleast_1d(save_restart))
+    err = [t for t in sr if t in set(time_pars.tolist())]
+    if err:
+        raise ValueError("save_restart cannot include epoch change: error for %s"
+                         % ", ".join("%g" % e for e in err))
+    stage_of = np.searchsorted(np.concatenate([[0.0], time_pars]), sr, side="right")
+    for i, st in enumerate(stages):
+        st["time_index"] = time_index[i]
+        if save_restart is not None:
+            st["restart_index"] = [j for j in range(len(sr)) if stage_of[j] == i + 1]
+    return stages
+
+
+class _JoinedDeviceHistory:
+    """The stages' device-resident histories (one model object per stage), joined on
+    request (join_histories)."""
+
+    def __init__(self, parts, stages, names):
+        self._parts, self._stages, self._names = parts, stages, names
+
+    def get(self, index_particle=None):
+        hs = [{"value": p["value"].get(index_particle), "order": None, "index": p["index"]}
+              for p in self._parts]
+        return join_histories(hs, self._stages)["value"]
+
+
+def join_histories(history, stages):
+    """R/particle_filter_multistage.R:191-243.  A stage's arrays either span the whole
+    series (the R loop: only its own interval is filled) or hold just the rows of its own
+    filter call (the compiled filter: slice 0 is the state the call started from)."""
+    time_index = [st["time_index"] for st in stages]
+    if not isinstance(history[0]["index"], dict):
+        raise ValueError("Named index required")
+    nms = []
+    for h in history:
+        nms += [n for n in h["index"] if n not in nms]
+    if any(isinstance(h["value"], _DeviceHistory) for h in history):
+        return {"value": _JoinedDeviceHistory(history, stages, nms), "order": None,
+                "index": {n: None for n in nms}}
+    has_order = history[0]["order"] is not None
+    n_time = time_index[-1] + 1
+    first = history[0]["value"]
+    value = np.full((len(nms),) + first.shape[1:-1] + (n_time,), np.nan)
+    order = None
+    if has_order:
+        order = np.zeros(history[0]["order"].shape[:-1] + (n_time,), dtype=np.int64)
+    end = [t + 1 for t in time_index]                 # 1-based, inclusive
+    start = [1] + [e + 1 for e in end[:-1]]
+    for i, h in enumerate(history):
+        j = [nms.index(n) for n in h["index"]]
+        k = np.arange(start[i] - 1, end[i])           # 0-based slices of the joined array
+        v = np.asarray(h["value"])
+        if v.shape[-1] == n_time or has_order:        # full-length arrays: same slices
+            value[j, ..., k[0]:k[-1] + 1] = v[..., k[0]:k[-1] + 1]
+        else:                                         # this call's rows only
+            local = v if i == 0 else v[..., 1:]
+            value[j, ..., k[0]:k[-1] + 1] = local[..., :k.size]
+        if has_order:
+            order[..., k[0]:k[-1] + 1] = h["order"][..., k[0]:k[-1] + 1]
+    return {"value": value, "order": order, "index": {n: None for n in nms}}
+
+
+def join_restart_state(restart, stages):
+    """R/particle_filter_multistage.R:253-266."""
+    parts = []
+    for r, st in zip(restart, stages):
+        idx = st.get("restart_index", [])
+        if r is not None and len(idx):
+            parts.append(np.asarray(r)[..., idx])
+    if len({p.shape[0] for p in parts}) > 1:
+        raise ValueError("Restart state varies in size over the simulation:\n" + "\n".join(
+            "  - %d: %d rows" % (i + 1, p.shape[0]) for i, p in enumerate(parts)))
+    return np.concatenate(parts, axis=-1) if parts else None
+
+
+def particle_filter_update_state(transform, model_old, model_new):
+    """R/particle_filter_state.R:495-513."""
+    info_old, info_new = model_old.info(), model_new.info()
+    n_pars = model_old.n_pars()
+    if n_pars == 0:
+        state = transform(model_old.state(), info_old, info_new)
+    else:
+        old = model_old.state()
+        state = np.stack([transform(old[:, :, i], info_old[i], info_new[i])
+                          for i in range(n_pars)], axis=-1)
+    model_new.update_state(state=np.asarray(state, dtype=float), time=model_old.time())
+
+
 class particle_filter_state:
     """R/particle_filter_state.R: one run of the filter, steppable."""
 
@@ -323,6 +464,7 @@ class particle_filter_state:
         self._compare = compare
         self._constant_log_likelihood = constant_log_likelihood
         self._gpu = gpu_config is not None
+        self._gpu_config = gpu_config
         self._min_log_likelihood = min_log_likelihood
         self._save_restart = save_restart
 
@@ -353,7 +495,13 @@ class particle_filter_state:
         check_time_step(self.current_time_index, time_index, self._times, "Particle filter")
         time = int(self._times[time_index - 1, 1])
         save_history = self.history is not None
-        snap = self._save_restart_time if self._save_restart_time.size else None
+        # snapshots the model can take in THIS call: the restart times in (now, time]
+        # (a stage of a multistage run covers part of the series)
+        t_now = int(self._times[self.current_time_index - 1, 1]) if self.current_time_index else \
+            int(self._times[0, 0])
+        all_snap = self._save_restart_time
+        here = np.where((all_snap > t_now) & (all_snap <= time))[0]
+        snap = all_snap[here] if here.size else None
         # the one native call for all the intervals; min_log_likelihood is NOT forwarded,
         # as in the reference (:151)
         on_device = save_history and hasattr(self.model, "filter_history")
@@ -368,7 +516,16 @@ class particle_filter_state:
                 value = _DeviceHistory(self.model, self._n_particles,
                                        self._has_multiple_parameters)
             self.history = {"value": value, "order": None, "index": self.history["index"]}
-        self.restart_state = res["snapshots"]
+        if all_snap.size and res["snapshots"] is not None:
+            if here.size == all_snap.size:
+                self.restart_state = res["snapshots"]
+            else:
+                if self.restart_state is None:
+                    self.restart_state = np.full(res["snapshots"].shape[:-1] + (all_snap.size,),
+                                                 np.nan)
+                self.restart_state[..., here] = res["snapshots"]
+        elif not all_snap.size:
+            self.restart_state = None
         return self.log_likelihood
 
     # ---- R/particle_filter_state.R:35-136
@@ -417,6 +574,30 @@ class particle_filter_state:
         self.log_likelihood = log_likelihood
         self.current_time_index = time_index
         return log_likelihood_step if partial else log_likelihood
+
+    def fork_multistage(self, model, pars, transform_state):
+        """R/particle_filter_state.R:360-389: a new filter state for the next stage --
+        its own model object (created on the first run, reused afterwards) with the new
+        parameters, this one's RNG state, and this one's model state passed through
+        ``transform_state``; position in the data and likelihood carry over.  The
+        reference refuses this for its GPU back end (:361, the RNG state could not be
+        handed over); here it is a device copy."""
+        seed = self.model.rng_state()
+        save_history = self.history is not None
+        if model is not None:
+            model.set_rng_state(seed)
+        if pars is None:
+            pars = self.model.pars()
+        ret = particle_filter_state(
+            pars, self._generator, model, self._data, self._data_split, self._times,
+            self._n_particles, self._has_multiple_parameters, self._n_threads, None,
+            self._index, self._compare, None, self._gpu_config, seed,
+            self._min_log_likelihood, save_history, self._save_restart)
+        particle_filter_update_state(transform_state, self.model, ret.model)
+        ret.current_time_index = self.current_time_index
+        ret.log_likelihood = self.log_likelihood
+        ret.log_likelihood_step = self.log_likelihood_step
+        return ret
 
     def fork_smc2(self, pars):
         """R/particle_filter_state.R:402-424: re-run from the start with new parameters
@@ -498,6 +679,8 @@ class particle_filter:
         pars = {} if pars is None else pars
         if not isinstance(save_history, (bool, np.bool_)):
             raise TypeError("'save_history' must be a logical")
+        if isinstance(pars, multistage_parameters):
+            return self._run_multistage(pars, save_history, save_restart, min_log_likelihood)
         if self.has_multiple_parameters:
             if isinstance(pars, dict):
                 raise ValueError("Expected an unnamed list of parameters for 'pars'")
@@ -509,6 +692,37 @@ class particle_filter:
         self._last_model = [obj.model]
         self._last_state = obj.model.state
         self._last_restart_state = obj.restart_state
+        return obj.log_likelihood
+
+    def _run_multistage(self, pars, save_history, save_restart, min_log_likelihood):
+        """filter_run_multistage (R/particle_filter.R:852-898)."""
+        if self.has_multiple_parameters:
+            raise NotImplementedError("multistage parameters with a nested filter")
+        stages = filter_check_times(pars, self._data, save_restart)
+        models = list(self._last_model) if self._last_model else []
+        if len(models) != len(stages):
+            models = [models[0] if models else None] + [None] * (len(stages) - 1)
+        history, restart = [], []
+        obj = None
+        for i, st in enumerate(stages):
+            if i == 0:
+                self._last_model = None if models[0] is None else [models[0]]
+                obj = self.run_begin(st["pars"], save_history, save_restart, min_log_likelihood)
+            else:
+                obj = obj.fork_multistage(models[i], st["pars"], st["transform_state"])
+            obj.step(st["time_index"])
+            models[i] = obj.model
+            history.append(obj.history)
+            restart.append(obj.restart_state)
+        # the final RNG state goes into the first model, completing the cycle: the next
+        # run starts from the first model (:877-879)
+        if len(models) > 1:
+            models[0].set_rng_state(models[-1].rng_state())
+        self._last_model = models
+        self._last_state = models[-1].state
+        self._last_history = join_histories(history, stages) if save_history else None
+        self._last_restart_state = (join_restart_state(restart, stages)
+                                    if save_restart is not None else None)
         return obj.log_likelihood
 
     def run_begin(self, pars=None, save_history=False, save_restart=None,
@@ -537,7 +751,7 @@ class particle_filter:
         if self._last_history is None:
             raise RuntimeError("Can't get history as model was run with save_history = FALSE")
         value, order = self._last_history["value"], self._last_history["order"]
-        if isinstance(value, _DeviceHistory):
+        if isinstance(value, (_DeviceHistory, _JoinedDeviceHistory)):
             return value.get(index_particle)
         if value.ndim == 4:
             return history_multiple(value, order, index_particle)
