@@ -465,6 +465,66 @@ def test_full_size_filter_2_20(dust, orc, sir_data):
     assert again[0] != got[0] and abs(again[0] - got[0]) < 0.5
 
 
+def test_thousand_replicate_filters_agree_in_distribution(dust, orc, sir_data):
+    """BASELINE's criterion for runs whose random draws differ: mean and variance of the
+    log-likelihood over 1000 replicate filters.  The engine runs its 1000 replicates as
+    one batched handle with a seed per set; the oracle runs 1000 separate filters on
+    other seeds, so nothing is shared but the algorithm."""
+    from mcstate_b200.dust import dust_rng_distributed_state
+
+    n, reps = 256, 1000
+    t, x = _data(sir_data)
+    data = dust.dust_data({"time_end": t, "incidence": x})
+    seeds = dust_rng_distributed_state(101, 1, reps)
+    m = dust.dust_example("sir").new([{}] * reps, 0, n, seed=b"".join(seeds), pars_multi=True,
+                                     seed_per_set=True, gpu_config=0)
+    m.set_data(data, True)
+    got = m.filter()["log_likelihood"]
+    assert got.shape == (reps,) and np.isfinite(got).all()
+    want = np.empty(reps)
+    for k in range(reps):
+        o = orc.OracleModel(n_particles=n, seed=5000 + k, n_threads=8)
+        o.set_data(t, x)
+        want[k] = o.filter()["log_likelihood"][0]
+    se = np.sqrt(got.var(ddof=1) / reps + want.var(ddof=1) / reps)
+    assert abs(got.mean() - want.mean()) < 4 * se, (got.mean(), want.mean(), se)
+    ratio = got.var(ddof=1) / want.var(ddof=1)
+    assert 0.75 < ratio < 1.33, ratio           # sd of a variance ratio at 1000 reps ~ 0.07
+    # and both sit below the large-N value by about half their variance (log of an
+    # unbiased likelihood estimate)
+    big = dust.dust_example("sir").new({}, 0, 1 << 18, seed=3)
+    big.set_data(data, False)
+    ll_big = big.filter()["log_likelihood"][0]
+    assert abs(got.mean() + 0.5 * got.var(ddof=1) - ll_big) < 0.15
+
+
+def test_large_filter_2_24_properties(dust, sir_data):
+    """Sixteen times config C2 in one handle (2^24 particles, 8192 weight tiles, 1.9 GB of
+    state and streams): too long for the CPU oracle, so size-independent properties --
+    determinism, conservation, and agreement of the likelihood estimate with the 2^20 run
+    (its standard error shrinks with 1/sqrt(N))."""
+    n = 1 << 24
+    t, x = _data(sir_data, 40)
+    g = dust.dust_example("sir")
+    m = g.new({}, 0, n, seed=1)
+    _set_data(m, t, x)
+    ll = m.filter()["log_likelihood"][0]
+    st = m.state()
+    assert st.shape == (5, n) and np.all(st >= 0)
+    assert np.array_equal(st[0] + st[1] + st[2], np.full(n, 1010.0))
+    small = g.new({}, 0, 1 << 20, seed=2)
+    _set_data(small, t, x)
+    assert abs(ll - small.filter()["log_likelihood"][0]) < 0.02
+    # the first 2^20 streams are those of a 2^20 model: same first step for those slots
+    a, b = g.new({}, 0, n, seed=1), g.new({}, 0, 1 << 20, seed=1)
+    assert np.array_equal(a.run(4)[:, :1 << 20], b.run(4))
+    del a, b
+    m.update_state(pars={}, time=0)
+    m2 = g.new({}, 0, n, seed=1)
+    _set_data(m2, t, x)
+    assert m2.filter()["log_likelihood"][0] == ll
+
+
 # ---- the lean (integer-state, table-driven) path of K1 against the general one -------------
 # Every case is bit-exact against the oracle, which only knows the general algorithm.
 @pytest.mark.parametrize("pars,label", [
