@@ -126,6 +126,10 @@ int mcb_run(mcb_model *m, uint64_t time_end, double *out);
 int mcb_simulate(mcb_model *m, const uint64_t *times, size_t n_times, double *out);
 /* $state(index) (R/particle_filter_state.R:79,81,114,272); index NULL = all rows */
 int mcb_state(mcb_model *m, const size_t *index, size_t n_index, double *out);
+/* The full state of n chosen particles only: out [n][n_state] (R: model$state()[, i],
+ * what pmcmc keeps of an accepted step, R/pmcmc_state.R:40-43 -- one column of a
+ * [n_state, n_total] matrix that need not cross PCIe).  particles: 0-based, set-major. */
+int mcb_state_particles(mcb_model *m, const size_t *particles, size_t n, double *out);
 /*
  * $update_state(pars=, state=, time=, set_initial_state=)
  *   R/particle_filter_state.R:248,253,512; R/smc2.R:141

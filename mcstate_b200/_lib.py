@@ -64,6 +64,7 @@ SIGNATURES = {
     "mcb_run": (C.c_int, [handle_p, C.c_uint64, f64p]),
     "mcb_simulate": (C.c_int, [handle_p, u64p, C.c_size_t, f64p]),
     "mcb_state": (C.c_int, [handle_p, szp, C.c_size_t, f64p]),
+    "mcb_state_particles": (C.c_int, [handle_p, szp, C.c_size_t, f64p]),
     "mcb_update_state": (C.c_int, [handle_p, f64p, f64p, C.c_size_t, C.c_int, C.c_uint64, C.c_int]),
     "mcb_reorder": (C.c_int, [handle_p, i32p]),
     "mcb_rng_state": (C.c_int, [handle_p, C.c_int, u64p]),

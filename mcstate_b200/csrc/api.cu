@@ -1109,6 +1109,31 @@ int mcb_state(mcb_model *m, const size_t *index, size_t n_index, double *out) {
   return rc;
 }
 
+int mcb_state_particles(mcb_model *m, const size_t *particles, size_t n, double *out) {
+  if (!m || !particles || !out) return fail(MCB_ERR_ARG, "NULL argument");
+  if (n == 0) return MCB_OK;
+  MCB_CUDA(cudaSetDevice(m->device));
+  View &v = m->v;
+  std::vector<unsigned long long> idx(n);
+  for (size_t j = 0; j < n; ++j) {
+    if (particles[j] >= v.n_total) return fail(MCB_ERR_ARG, "particle index out of range");
+    idx[j] = particles[j];
+  }
+  const size_t idx_bytes = round_up(n * sizeof(unsigned long long), 256);
+  const size_t out_bytes = n * (size_t)v.n_state * sizeof(double);
+  MCB_TRY(ensure_stage(m, idx_bytes + out_bytes));
+  unsigned long long *d_idx = reinterpret_cast<unsigned long long *>(m->d_stage);
+  double *d_out = reinterpret_cast<double *>(reinterpret_cast<char *>(m->d_stage) + idx_bytes);
+  MCB_CUDA(cudaMemcpyAsync(d_idx, idx.data(), n * sizeof(unsigned long long),
+                           cudaMemcpyHostToDevice, m->stream));
+  mcb::k_state_particles<<<blocks_for(n, 64), 64, 0, m->stream>>>(v.y, v.ld, v.n_state, d_idx, n,
+                                                                    d_out);
+  ++m->launches;
+  MCB_CUDA(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, m->stream));
+  MCB_CUDA(cudaStreamSynchronize(m->stream));
+  return MCB_OK;
+}
+
 int mcb_update_state(mcb_model *m, const double *pars, const double *state, size_t state_len,
                      int has_time, uint64_t time, int set_initial_state) {
   if (!m) return fail(MCB_ERR_ARG, "model is NULL");

@@ -790,6 +790,17 @@ __global__ void k_pack_rows(const double *__restrict__ y, size_t ld, size_t n_to
   }
 }
 
+// the state of a few chosen particles (pMCMC keeps one: R/pmcmc_state.R:40-43):
+// out [n][n_state]
+__global__ void k_state_particles(const double *__restrict__ y, size_t ld, int n_state,
+                                  const unsigned long long *__restrict__ particles, size_t n,
+                                  double *__restrict__ out) {
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const size_t src = (size_t)particles[j];
+  for (int s = 0; s < n_state; ++s) out[j * n_state + s] = y[(size_t)s * ld + src];
+}
+
 // model$simulate: n_slices saved slices [slice][n_rows][ld] -> R layout
 // [n_rows fastest][particle][slice] in one pass
 __global__ void k_pack_slices(const double *__restrict__ value, size_t ld, size_t n_total,

@@ -270,6 +270,17 @@ class dust_model:
         check(_lib.lib().mcb_state(self._h, ptr(idx, szp), idx.size, ptr(out, f64p)))
         return self._shape_out(out, idx.size)
 
+    def state_particles(self, index_particle):
+        """``model$state()[, index_particle]`` without moving the other columns:
+        ``[n_state, n]`` (single parameter set; 1-based indices as in R)."""
+        ip = np.atleast_1d(np.asarray(index_particle, dtype=np.int64))
+        if ip.min() < 1 or ip.max() > self._n_total:
+            raise IndexError("index_particle out of range")
+        flat = np.ascontiguousarray(ip - 1, dtype=np.uintp)
+        out = np.zeros((flat.size, self._n_state))
+        check(_lib.lib().mcb_state_particles(self._h, ptr(flat, szp), flat.size, ptr(out, f64p)))
+        return out.T
+
     def update_state(self, pars=None, state=None, time=None, set_initial_state=None):
         """R/particle_filter_state.R:248,253,512; R/smc2.R:141; R/if2.R:160-161."""
         vec = None

@@ -744,6 +744,16 @@ class particle_filter:
             raise RuntimeError("Model has not yet been run")
         return self._last_state(index_state)
 
+    def state_particles(self, index_particle):
+        """``filter$state()[, index_particle]`` ([n_state, n]): only those columns leave the
+        device when the model object can select them (mcb_state_particles)."""
+        if self._last_model is None:
+            raise RuntimeError("Model has not yet been run")
+        model = self._last_model[-1]
+        if hasattr(model, "state_particles") and not self.has_multiple_parameters:
+            return model.state_particles(index_particle)
+        return np.asarray(self.state())[:, np.atleast_1d(index_particle) - 1]
+
     def history(self, index_particle=None):
         """R/particle_filter.R:377-397."""
         if self._last_model is None:

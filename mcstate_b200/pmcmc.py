@@ -211,7 +211,10 @@ class pmcmc_state:
         if c.save_trajectories:
             self._curr_traj = np.asarray(self._filter.history(i))[:, 0]
         if c.save_state:
-            self._curr_state = np.asarray(self._filter.state())[:, i - 1]
+            if hasattr(self._filter, "state_particles"):
+                self._curr_state = np.asarray(self._filter.state_particles(i))[:, 0]
+            else:
+                self._curr_state = np.asarray(self._filter.state())[:, i - 1]
         if c.save_restart is not None and len(c.save_restart) > 0:
             self._curr_restart = np.asarray(self._filter.restart_state(i, c.save_restart))[:, 0]
 

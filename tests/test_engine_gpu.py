@@ -120,6 +120,16 @@ def test_index_update_state_reorder_simulate(dust, orc):
         assert np.array_equal(sim[:, :, k], o.run(t))
 
 
+def test_state_of_chosen_particles(dust):
+    m = dust.dust_example("sir").new({"I0": 30}, 0, 5000, seed=2)
+    m.run(40)
+    full = m.state()
+    pick = [1, 5000, 77, 77]
+    assert np.array_equal(m.state_particles(pick), full[:, [0, 4999, 76, 76]])
+    with pytest.raises(IndexError):
+        m.state_particles([5001])
+
+
 def test_rng_state_roundtrip(dust, orc):
     g = dust.dust_example("sir")
     m = g.new({}, 0, 10, seed=1)
