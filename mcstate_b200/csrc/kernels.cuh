@@ -6,9 +6,12 @@
 //   K1 k_run_compare   [resample + gather of the previous interval, fused into the
 //                      load] -> `rate` model steps -> compare -> state', rng', logw, max
 //   K2 k_weights_scan  w = exp(logw - max) as fixed point, per-tile inclusive scan;
-//                      the last block adds the tile prefix, log-mean-exp -> ll,
-//                      resampling thresholds and the early-exit rule
+//                      the block that ends a parameter set adds its tile prefix,
+//                      log-mean-exp -> ll, resampling thresholds; the last set to
+//                      finish applies the early-exit rule
 // plus k_finish_state once per filter call (the last interval's resample).
+// Filters that fit the GPU in one wave run as ONE cooperative kernel per call instead
+// (persistent.cuh); the model steps (run_model_steps) are shared.
 //
 // Data layout (HBM): state is SoA [n_state][ld] fp64, RNG is SoA [4][ld_rng]
 // u64, both with ld a multiple of 32 so every row starts 256-byte aligned and a
