@@ -867,6 +867,9 @@ int mcb_alloc_ex(int model_id, const double *pars, size_t n_particles, size_t n_
     if (n_tab < 256) n_tab = 256;
     v.n_tab = (int)n_tab;
     v.n_wrows = (int)(n_tab < kMaxWalkRows ? n_tab : kMaxWalkRows);
+    int bits = 0;
+    while (((size_t)1 << bits) < n_tab) ++bits;
+    v.pow_groups = (bits + 1) / 3;
     m->n_const = (int)n_const;
   }
   ALLOC(v.derived, n_sets * mcb::kMaxDerived * sizeof(double));

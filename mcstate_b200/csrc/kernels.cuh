@@ -70,6 +70,7 @@ struct View {
   const int *index;   // [n_index] rows returned by run()/saved in trajectories
   size_t n_particles, n_sets, n_total, ld, ld_rng;
   int n_state, n_index, n_min, data_sets, tiles_per_set, shift, deterministic, n_tab, n_wrows;
+  int pow_groups;   // groups of three bits beyond bit 0 in a count below n_tab (pow_int_lean)
   // filter streams (resampling uniforms).  n_fs == 1: one stream shared by every set
   // (the dust pars_multi layout), drawn in set order; when the sets of one model are
   // sharded over several handles, each handle replays the whole order
@@ -104,8 +105,18 @@ __device__ __forceinline__ double key_to_double(unsigned long long k) {
   return __longlong_as_double((long long)b);
 }
 
-__device__ __forceinline__ bool datum_is_na(const View &v, int row, size_t set) {
+// is the datum of (row, set) missing?  The look-up itself:
+__device__ __forceinline__ bool datum_missing(const View &v, int row, size_t set) {
   const size_t ds = v.data_sets == 1 ? 0 : set;
+  const double x = __ldg(v.data + ((size_t)row * v.data_sets + ds) * 2);
+  return x != x;
+}
+// ...and as the per-interval kernels ask it: they are only launched for rows the host
+// weighs (row_all_na), so with one data stream for every set (data_sets == 1: a row is
+// missing for all sets or for none) there is nothing to look up.
+__device__ __forceinline__ bool datum_is_na(const View &v, int row, size_t set) {
+  if (v.data_sets == 1) return false;
+  const size_t ds = set;
   const double x = __ldg(v.data + ((size_t)row * v.data_sets + ds) * 2);
   return x != x;
 }
@@ -265,7 +276,7 @@ __device__ __forceinline__ void run_model_steps(const View &v, const SetData &sd
     typename M::Lean lc;
     lc.set = (uint32_t)set;
     const LeanTabs tabs{v.tab_inf, v.tab_walk, (uint32_t)v.n_tab, (uint32_t)v.n_wrows,
-                        (32 - __clz(v.n_tab - 1) + 1) / 3};
+                        v.pow_groups};
     if (!det && M::lean_load(sd, y, yi, lc)) {
       // the usual case: integer compartments, setup from the memo tables, no calls
       const uint32_t s_inv_addr = (uint32_t)__cvta_generic_to_shared(s_inv);
@@ -715,7 +726,7 @@ __global__ void k_draw_uniforms(View v, int row_first, int row_last, double *u_d
       bool na = false;
       if (row_first >= 0)
         na = (!per_set && v.na_global) ? v.na_global[(size_t)row * n_glob + pg] != 0
-                                       : (mine && datum_is_na(v, row, (size_t)p));
+                                       : (mine && datum_missing(v, row, (size_t)p));
       if (na) continue;
       const double u = xo_real<SCR>(r);
       if (mine) u_draws[slot + p] = u;

@@ -174,7 +174,7 @@ k_filter_persistent(View v, PersistArgs a) {
   for (int row = a.first; row < a.last; ++row) {
     const uint64_t t_end = __ldg(a.data_time + row);
     const uint32_t n_steps = (uint32_t)(t_end - t);
-    const bool weigh = !datum_is_na(v, row, 0);
+    const bool weigh = !datum_missing(v, row, 0);
 
     // ---- gather (resampling of the previous weighed row), update, compare
     const int rel = row - a.first;
