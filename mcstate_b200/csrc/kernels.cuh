@@ -105,6 +105,14 @@ __device__ __forceinline__ double key_to_double(unsigned long long k) {
   return __longlong_as_double((long long)b);
 }
 
+// which parameter set particle i belongs to: nothing to divide for one set, a 32-bit
+// division when the indices fit (a 64-bit one is a ~60-instruction routine)
+__device__ __forceinline__ size_t set_of(const View &v, size_t i) {
+  if (v.n_sets == 1) return 0;
+  if (v.n_total <= 0xffffffffULL) return (size_t)((uint32_t)i / (uint32_t)v.n_particles);
+  return i / v.n_particles;
+}
+
 // is the datum of (row, set) missing?  The look-up itself:
 __device__ __forceinline__ bool datum_missing(const View &v, int row, size_t set) {
   const size_t ds = v.data_sets == 1 ? 0 : set;
@@ -338,7 +346,7 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
   const size_t i = (size_t)blockIdx.x * kRunThreads + threadIdx.x;
   const bool live = i < v.n_total;
   const size_t ii = live ? i : v.n_total - 1;
-  const size_t set = v.n_sets == 1 ? 0 : ii / v.n_particles;
+  const size_t set = set_of(v, ii);
   const SetData sd{v.derived + set * kMaxDerived, v.n_tab};
   const typename M::Ctx ctx = M::context(sd);
   const bool det = v.deterministic != 0;
@@ -408,7 +416,8 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
   const size_t first = (size_t)blockIdx.x * kRunThreads;
   size_t last = first + kRunThreads - 1;
   if (last >= v.n_total) last = v.n_total - 1;
-  const bool one_set = v.n_sets == 1 || (first / v.n_particles == last / v.n_particles);
+  const size_t set_first = set_of(v, first);
+  const bool one_set = v.n_sets == 1 || set_first == set_of(v, last);
   unsigned long long *slot = v.wmax + (size_t)row * v.n_sets;
   if (one_set) {
     // warp max of a 64-bit key with two 32-bit REDUX: high words, then the low
@@ -422,7 +431,7 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
     if (threadIdx.x == 0) {
 #pragma unroll
       for (int w = 1; w < kRunThreads / 32; ++w) key = s_key[w] > key ? s_key[w] : key;
-      if (key) atomicMax(slot + first / v.n_particles, key);
+      if (key) atomicMax(slot + set_first, key);
     }
   } else if (weighted) {
     atomicMax(slot + set, key);
@@ -574,8 +583,8 @@ __global__ void __launch_bounds__(kTileThreads, 4) k_weights_scan(View v, int ro
   grid_launch_dependents();
   grid_dependency_wait();
   if (v.flags[0]) return;
-  const size_t set = blockIdx.x / v.tiles_per_set;
-  const int tile = blockIdx.x % v.tiles_per_set;
+  const size_t set = v.n_sets == 1 ? 0 : blockIdx.x / (unsigned)v.tiles_per_set;
+  const int tile = (int)(blockIdx.x - (unsigned)set * (unsigned)v.tiles_per_set);
   // what the set's finishing thread will need, asked for now (finish_set)
   double pre_u = 0.0, pre_ll = 0.0, mx = 0.0;
   if (threadIdx.x == 0) {
@@ -667,7 +676,7 @@ k_resample_gather(View v, int row, const double *__restrict__ src_buf,
   if (v.flags[0]) return;
   const size_t i = (size_t)blockIdx.x * kGatherThreads + threadIdx.x;
   if (i >= v.n_total) return;
-  const size_t set = v.n_sets == 1 ? 0 : i / v.n_particles;
+  const size_t set = set_of(v, i);
   size_t src = i;
   if (row < 0 || !datum_is_na(v, row, set)) src = resample_source(v, set, i - set * v.n_particles);
 #pragma unroll
@@ -692,7 +701,7 @@ k_finish_state(View v, int last, int last_weighted, int *__restrict__ kappa_out)
     }
     return;
   }
-  const size_t set = v.n_sets == 1 ? 0 : i / v.n_particles;
+  const size_t set = set_of(v, i);
   size_t src = i;
   if (last_weighted && !datum_is_na(v, last - 1, set))
     src = resample_source(v, set, i - set * v.n_particles);
@@ -786,7 +795,7 @@ template <class M>
 __global__ void k_set_initial(View v) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= v.n_total) return;
-  const size_t set = v.n_sets == 1 ? 0 : i / v.n_particles;
+  const size_t set = set_of(v, i);
   double y[M::kState];
   M::initial(v.pars + set * kMaxPar, y);
 #pragma unroll
@@ -839,7 +848,7 @@ __global__ void k_unpack_state(const double *__restrict__ in, int recycle, int n
 __global__ void k_gather_by_kappa(View v, const int *__restrict__ kappa) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= v.n_total) return;
-  const size_t set = v.n_sets == 1 ? 0 : i / v.n_particles;
+  const size_t set = set_of(v, i);
   const size_t src = set * v.n_particles + (size_t)(kappa[i] - 1);
   for (int s = 0; s < v.n_state; ++s) v.y_tmp[(size_t)s * v.ld + i] = v.y[(size_t)s * v.ld + src];
 }
