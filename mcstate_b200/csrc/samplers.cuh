@@ -238,11 +238,15 @@ __device__ __forceinline__ int walk_lean(Xoshiro &rng, int n, double r, double f
   if (kmax > MCB_PEEL) {     // the usual case: every written-out step has a successor
     MCB_WALK_STEP(1, g)
     MCB_WALK_STEP(2, g * 0.5)
-    MCB_WALK_STEP(3, MCB_WALK_DIV(3))
+    // g/6, g/12 and g/10 are g/3 and g/5 scaled by a power of two: the same bits as
+    // dividing (RN commutes with an exact scaling, g is away from underflow)
+    const double g3 = MCB_WALK_DIV(3);
+    MCB_WALK_STEP(3, g3)
     MCB_WALK_STEP(4, g * 0.25)
 #if MCB_PEEL >= 6
-    MCB_WALK_STEP(5, MCB_WALK_DIV(5))
-    MCB_WALK_STEP(6, MCB_WALK_DIV(6))
+    const double g5 = MCB_WALK_DIV(5);
+    MCB_WALK_STEP(5, g5)
+    MCB_WALK_STEP(6, g3 * 0.5)
 #endif
 #if MCB_PEEL >= 8
     MCB_WALK_STEP(7, MCB_WALK_DIV(7))
@@ -250,11 +254,11 @@ __device__ __forceinline__ int walk_lean(Xoshiro &rng, int n, double r, double f
 #endif
 #if MCB_PEEL >= 10
     MCB_WALK_STEP(9, MCB_WALK_DIV(9))
-    MCB_WALK_STEP(10, MCB_WALK_DIV(10))
+    MCB_WALK_STEP(10, g5 * 0.5)
 #endif
 #if MCB_PEEL >= 12
     MCB_WALK_STEP(11, MCB_WALK_DIV(11))
-    MCB_WALK_STEP(12, MCB_WALK_DIV(12))
+    MCB_WALK_STEP(12, g3 * 0.25)
 #endif
 #if MCB_PEEL >= 16
     MCB_WALK_STEP(13, MCB_WALK_DIV(13))
