@@ -559,6 +559,41 @@ def test_lean_path_special_cases(dust, orc, pars, label):
         assert np.array_equal(_rng_words(m), o.rng_state()), (label, t_end)
 
 
+def test_random_parameter_sweep(dust, orc, sir_data):
+    """Eighty random parameter sets (tiny to large populations, probabilities from ~0 to
+    beyond one half, 1-8 steps per day, both models, both scramblers, both execution
+    paths) through a short filter: every one bit-exact against the oracle.  Exercises the
+    borders of the lean path -- counts below the written-out walk steps, walk tables that
+    end, BTRS hand-overs mid-interval, flipped probabilities, stalled walks."""
+    rs = np.random.RandomState(20261020)
+    t_day, x = sir_data["day"][:25], sir_data["incidence"][:25]
+    for case in range(80):
+        model = "sir" if case % 4 else "sirs"
+        scr = int(rs.randint(2))
+        freq = float(rs.choice([1, 2, 3, 4, 8]))
+        s0 = float(rs.choice([3, 11, 12, 13, 40, 1000, 5000, 70000]))
+        pars = {"beta": float(rs.choice([0.0, 0.05, 0.2, 0.9, 3.0, 40.0])),
+                "gamma": float(rs.choice([0.0, 0.02, 0.1, 0.6931471805599453, 2.5])),
+                "S0": s0, "I0": float(rs.randint(0, max(2, int(min(s0, 200))))),
+                "freq": freq}
+        if model == "sirs":
+            pars["alpha"] = float(rs.choice([0.0, 0.01, 0.3, 5.0]))
+        n = int(rs.choice([1, 33, 200, 1000]))
+        seed = int(rs.randint(1, 1 << 30))
+        t = (t_day * freq).astype(np.uint64)
+        g = dust.dust_example(model, ["xoshiro256plus", "xoshiro256starstar"][scr])
+        m = g.new(pars, 0, n, seed=seed)
+        m.set_persistent(bool(case & 1))
+        o = orc.OracleModel(pars=g._pars_vector(pars, False), n_particles=n, seed=seed,
+                            model=0 if model == "sir" else 1, scrambler=scr, n_threads=4)
+        _set_data(m, t, x)
+        o.set_data(t, x)
+        got, want = m.filter()["log_likelihood"], o.filter()["log_likelihood"]
+        assert np.array_equal(got, want, equal_nan=True), (case, model, pars, n, got, want)
+        assert np.array_equal(m.state(), o.state()), (case, model, pars)
+        assert np.array_equal(_rng_words(m), o.rng_state()), (case, model, pars)
+
+
 def test_lean_path_leaves_non_integer_states_to_the_general_code(dust, orc):
     n = 500
     g = dust.dust_example("sir")
