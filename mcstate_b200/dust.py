@@ -79,6 +79,24 @@ class dust_rng:
         return self._s.tobytes()
 
 
+class dust_rng_pointer:
+    """``dust::dust_rng_pointer$new(seed, n_streams)$state()``
+    (tests/testthat/test-particle-filter.R:1316): the raw state of ``n_streams`` streams,
+    stream i = stream 0 jumped i times -- what a model with that seed holds."""
+
+    def __init__(self, seed, n_streams=1, algorithm="xoshiro256plus"):
+        first = dust_rng(seed, algorithm)
+        out, r = [], first
+        for i in range(int(n_streams)):
+            out.append(bytes(r.state()))
+            if i + 1 < int(n_streams):
+                r = dust_rng(out[-1], algorithm).jump()
+        self._state = b"".join(out)
+
+    def state(self):
+        return self._state
+
+
 def dust_rng_distributed_state(seed=None, n_streams=1, n_nodes=1, algorithm="xoshiro256plus"):
     """``dust::dust_rng_distributed_state`` (R/pmcmc_parallel.R:133, R/smc2.R:68):
     a list of raw states, node k long-jumped k times from the seed."""

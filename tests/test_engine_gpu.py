@@ -130,6 +130,14 @@ def test_state_of_chosen_particles(dust):
         m.state_particles([5001])
 
 
+def test_rng_pointer_matches_a_model_s_streams(dust, orc):
+    """dust_rng_pointer$new(seed, n)$state() (tests/testthat/test-particle-filter.R:1316)."""
+    raw = dust.dust_rng_pointer(9, 6).state()
+    assert np.array_equal(np.frombuffer(raw, dtype=np.uint64).reshape(-1, 4), orc.rng_streams(9, 6))
+    m = dust.dust_example("sir").new({}, 0, 5, seed=9)
+    assert m.rng_state() == raw
+
+
 def test_rng_state_roundtrip(dust, orc):
     g = dust.dust_example("sir")
     m = g.new({}, 0, 10, seed=1)
