@@ -325,11 +325,16 @@ def run_engine(args):
         per_launch_bytes = [BYTES_K1 * N_PARTICLES, BYTES_K2 * N_PARTICLES, 0,
                             BYTES_FINISH * N_PARTICLES]
         kernels = {}
+        busy_ms = float(sum(k_ms[k] for k in range(len(names)) if k_n[k]))
         for k, name in enumerate(names):
             if k_n[k]:
                 avg_ms = k_ms[k] / float(k_n[k])
+                # share_of_step: of the time the step's kernels run (what an ncu launch
+                # list can be compared with); share_of_wall: of the instrumented pass,
+                # which also holds the event records and launch gaps
                 kernels[name] = {"avg_us": 1e3 * avg_ms, "launches": int(k_n[k]),
-                                 "share_of_step": k_ms[k] / ms_instrumented,
+                                 "share_of_step": k_ms[k] / busy_ms,
+                                 "share_of_wall": k_ms[k] / ms_instrumented,
                                  "achieved_gbs": per_launch_bytes[k] / (avg_ms * 1e-3) / 1e9}
         dom = max(kernels, key=lambda n: kernels[n]["share_of_step"]) if kernels else None
         roofline = None
