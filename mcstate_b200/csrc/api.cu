@@ -71,6 +71,12 @@ const ModelDesc kModels[] = {
      {0.91, 1.0, 1.0, 1.0, 0.0},
      {"x"},
      {"observed"}},
+    // no compiled compare (n_data = 0): tests/testthat/test-particle-filter.R:579-586
+    {"walk", 1, 1, 0,
+     {"sd"},
+     {1.0},
+     {"x"},
+     {nullptr}},
 };
 // parameter slots of the closed population (S0, I0, R0) of a compartmental model, or
 // none; draws with a parameter-only probability (walk tables)
@@ -81,6 +87,7 @@ struct ModelTables {
 };
 const ModelTables kModelTables[] = {{{4, 2, 5}, mcb::SirModel::kConst, 6},
                                     {{5, 3, 6}, mcb::SirsModel::kConst, 7},
+                                    {{-1, -1, -1}, 0, -1},
                                     {{-1, -1, -1}, 0, -1}};
 constexpr int kNumModels = sizeof(kModels) / sizeof(kModels[0]);
 constexpr size_t kMaxWalkRows = 2048;  // counts covered by a walk table (samplers.cuh)
@@ -316,7 +323,9 @@ void run_compare(mcb_model *m, const double *y_in, double *y_out, uint64_t t0, u
     case 2: launch_run_compare<mcb::SirsModel, 0>(m, y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out); break;
     case 3: launch_run_compare<mcb::SirsModel, 1>(m, y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out); break;
     case 4: launch_run_compare<mcb::VolatilityModel, 0>(m, y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out); break;
-    default: launch_run_compare<mcb::VolatilityModel, 1>(m, y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out); break;
+    case 5: launch_run_compare<mcb::VolatilityModel, 1>(m, y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out); break;
+    case 6: launch_run_compare<mcb::WalkModel, 0>(m, y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out); break;
+    default: launch_run_compare<mcb::WalkModel, 1>(m, y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out); break;
   }
 }
 
@@ -355,7 +364,8 @@ void prepare_sets(mcb_model *m) {
   const dim3 grid(blocks_for(rows, 128), (unsigned)m->v.n_sets);
   if (m->model_id == 0) mcb::k_prepare_sets<mcb::SirModel><<<grid, 128, 0, m->stream>>>(m->v);
   else if (m->model_id == 1) mcb::k_prepare_sets<mcb::SirsModel><<<grid, 128, 0, m->stream>>>(m->v);
-  else mcb::k_prepare_sets<mcb::VolatilityModel><<<grid, 128, 0, m->stream>>>(m->v);
+  else if (m->model_id == 2) mcb::k_prepare_sets<mcb::VolatilityModel><<<grid, 128, 0, m->stream>>>(m->v);
+  else mcb::k_prepare_sets<mcb::WalkModel><<<grid, 128, 0, m->stream>>>(m->v);
   ++m->launches;
 }
 
@@ -363,7 +373,8 @@ void set_initial(mcb_model *m) {
   const unsigned grid = blocks_for(m->v.n_total, 256);
   if (m->model_id == 0) mcb::k_set_initial<mcb::SirModel><<<grid, 256, 0, m->stream>>>(m->v);
   else if (m->model_id == 1) mcb::k_set_initial<mcb::SirsModel><<<grid, 256, 0, m->stream>>>(m->v);
-  else mcb::k_set_initial<mcb::VolatilityModel><<<grid, 256, 0, m->stream>>>(m->v);
+  else if (m->model_id == 2) mcb::k_set_initial<mcb::VolatilityModel><<<grid, 256, 0, m->stream>>>(m->v);
+  else mcb::k_set_initial<mcb::WalkModel><<<grid, 256, 0, m->stream>>>(m->v);
   ++m->launches;
 }
 
@@ -519,7 +530,9 @@ const void *persistent_kernel_for(const mcb_model *m) {
     case 2: return persistent_kernel<mcb::SirsModel, 0>();
     case 3: return persistent_kernel<mcb::SirsModel, 1>();
     case 4: return persistent_kernel<mcb::VolatilityModel, 0>();
-    default: return persistent_kernel<mcb::VolatilityModel, 1>();
+    case 5: return persistent_kernel<mcb::VolatilityModel, 1>();
+    case 6: return persistent_kernel<mcb::WalkModel, 0>();
+    default: return persistent_kernel<mcb::WalkModel, 1>();
   }
 }
 
@@ -1304,6 +1317,8 @@ int mcb_set_data(mcb_model *m, size_t n_data, const uint64_t *time_end, const do
                  int shared) {
   if (!m || !time_end || !values) return fail(MCB_ERR_ARG, "NULL argument");
   if (n_data == 0) return fail(MCB_ERR_ARG, "data must have at least one row");
+  if (m->desc->n_data == 0)
+    return fail(MCB_ERR_STATE, "Your model does not have a built-in 'compare' function");
   MCB_CUDA(cudaSetDevice(m->device));
   View &v = m->v;
   for (size_t i = 1; i < n_data; ++i)

@@ -424,4 +424,39 @@ struct VolatilityModel {
   }
 };
 
+// dust::dust_example("walk"): a random walk, x' = x + N(0, sd), with NO compiled
+// compare -- the reference uses it to check that a filter without a compare function
+// refuses such a model (tests/testthat/test-particle-filter.R:579-586); with an R-level
+// compare it runs through the filter's R loop (model$run, $state, $reorder).
+struct WalkModel {
+  static constexpr bool kHasLean = false;
+  static constexpr int kState = 1;
+  static constexpr int kPar = 1;  // sd
+  static constexpr int kData = 0;
+  static constexpr int kConst = 0;
+  enum { D_SD };
+  __device__ __forceinline__ static void derive(const double *__restrict__ p, double *d) {
+    d[D_SD] = p[0];
+  }
+  struct Ctx {
+    double sd;
+  };
+  __device__ __forceinline__ static Ctx context(const SetData &sd) {
+    return Ctx{__ldg(sd.derived + D_SD)};
+  }
+  __device__ __forceinline__ static void initial(const double *__restrict__, double *y) {
+    y[0] = 0.0;
+  }
+  template <int SCR>
+  __device__ __forceinline__ static void update(uint64_t, double *y, Xoshiro &rng, const Ctx &c,
+                                                bool det) {
+    y[0] = y[0] + (det ? 0.0 : draw_normal<SCR>(rng, 0.0, c.sd));
+  }
+  template <int SCR>
+  __device__ __forceinline__ static double compare(const double *, double, double, Xoshiro &,
+                                                   const Ctx &, bool) {
+    return 0.0;   // never weighed: mcb_set_data refuses a model without a compare
+  }
+};
+
 }  // namespace mcb

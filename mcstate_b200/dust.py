@@ -561,7 +561,7 @@ class dust_generator:
 
     # -- static capability queries
     def has_compare(self):
-        return True
+        return len(self.data_fields) > 0      # "walk" has no compiled compare
 
     def has_gpu_support(self, fake_gpu=False):
         return True

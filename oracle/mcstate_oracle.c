@@ -530,10 +530,10 @@ void orc_history_single(const double *value, const int *order, size_t ny,
 #define ORC_MAX_STATE 8
 
 size_t orc_model_n_state(int model) {
-  return model == ORC_MODEL_SIR ? 5 : model == ORC_MODEL_SIRS ? 4 : 1;
+  return model == ORC_MODEL_SIR ? 5 : model == ORC_MODEL_SIRS ? 4 : 1;   /* volatility, walk: 1 */
 }
 size_t orc_model_n_par(int model) {
-  return model == ORC_MODEL_SIR ? 7 : model == ORC_MODEL_SIRS ? 8 : 5;
+  return model == ORC_MODEL_SIR ? 7 : model == ORC_MODEL_SIRS ? 8 : model == ORC_MODEL_VOLATILITY ? 5 : 1;
 }
 size_t orc_model_n_data(int model) { (void)model; return 1; }
 
@@ -544,9 +544,11 @@ void orc_model_default_pars(int model, double *p) {
   } else if (model == ORC_MODEL_SIRS) {
     p[0] = 0.1; p[1] = 0.2; p[2] = 0.1; p[3] = 10.0; p[4] = 1e6; p[5] = 1000.0;
     p[6] = 0.0; p[7] = 4.0;
-  } else {
+  } else if (model == ORC_MODEL_VOLATILITY) {
     /* tests/testthat/helper-mcstate.R:99 */
     p[0] = 0.91; p[1] = 1.0; p[2] = 1.0; p[3] = 1.0; p[4] = 0.0;
+  } else {
+    p[0] = 1.0;   /* walk: sd */
   }
 }
 
@@ -555,8 +557,10 @@ static void model_initial(int model, const double *p, double *y) {
     y[0] = p[4]; y[1] = p[2]; y[2] = p[5]; y[3] = 0.0; y[4] = 0.0;
   } else if (model == ORC_MODEL_SIRS) {
     y[0] = p[5]; y[1] = p[3]; y[2] = p[6]; y[3] = 0.0;
-  } else {
+  } else if (model == ORC_MODEL_VOLATILITY) {
     y[0] = p[4];
+  } else {
+    y[0] = 0.0;
   }
 }
 
@@ -610,7 +614,8 @@ void orc_model_update(int model, uint64_t time, const double *y, uint64_t s[4],
                       double *y_next) {
   if (model == ORC_MODEL_SIR) sir_update(time, y, s, scrambler, deterministic, pars, y_next);
   else if (model == ORC_MODEL_SIRS) sirs_update(time, y, s, scrambler, deterministic, pars, y_next);
-  else volatility_update(y, s, scrambler, deterministic, pars, y_next);
+  else if (model == ORC_MODEL_VOLATILITY) volatility_update(y, s, scrambler, deterministic, pars, y_next);
+  else y_next[0] = y[0] + (deterministic ? 0.0 : orc_normal(s, scrambler, 0.0, pars[0]));   /* walk */
 }
 
 /* tests/testthat/helper-mcstate.R:7-22 (R twin): Poisson density of the

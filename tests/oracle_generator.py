@@ -12,11 +12,13 @@ from oracle import oracle as O
 
 PAR_NAMES = {O.SIR: ["beta", "gamma", "I0", "exp_noise", "S0", "R0", "freq"],
              O.SIRS: ["alpha", "beta", "gamma", "I0", "exp_noise", "S0", "R0", "freq"],
-             O.VOLATILITY: ["alpha", "sigma", "gamma", "tau", "x0"]}
+             O.VOLATILITY: ["alpha", "sigma", "gamma", "tau", "x0"],
+             O.WALK: ["sd"]}
 STATE_NAMES = {O.SIR: ["S", "I", "R", "cases_cumul", "cases_inc"],
                O.SIRS: ["S", "I", "R", "cases_inc"],
-               O.VOLATILITY: ["x"]}
-DATA_FIELD = {O.SIR: "incidence", O.SIRS: "incidence", O.VOLATILITY: "observed"}
+               O.VOLATILITY: ["x"],
+               O.WALK: ["x"]}
+DATA_FIELD = {O.SIR: "incidence", O.SIRS: "incidence", O.VOLATILITY: "observed", O.WALK: None}
 
 
 def _seed_words(seed):
@@ -208,14 +210,15 @@ class OracleGenerator:
     name = "dust_generator"
 
     def __init__(self, model_name="sir", algorithm="xoshiro256plus"):
-        self.model_id = {"sir": O.SIR, "sirs": O.SIRS, "volatility": O.VOLATILITY}[model_name]
+        self.model_id = {"sir": O.SIR, "sirs": O.SIRS, "volatility": O.VOLATILITY,
+                         "walk": O.WALK}[model_name]
         self.scrambler = {"xoshiro256plus": O.PLUS, "xoshiro256starstar": O.STARSTAR}[algorithm]
         self.par_names = PAR_NAMES[self.model_id]
         self.par_defaults = list(O.default_pars(self.model_id))
         self.state_names = STATE_NAMES[self.model_id]
         self.public_methods = self
 
-    def has_compare(self): return True
+    def has_compare(self): return DATA_FIELD[self.model_id] is not None
     def has_gpu_support(self, fake_gpu=False): return False
     def time_type(self): return "discrete"
 

@@ -112,6 +112,49 @@ def test_constructor_validation(sir_data):
         p.history()
 
 
+@pytest.mark.parametrize("kind", BACKENDS)
+def test_model_without_a_compiled_compare(kind, sir_data):
+    """tests/testthat/test-particle-filter.R:579-586: the walk model has no built-in
+    compare, so a filter without a compare function refuses it; with one, it runs through
+    the R loop (model$run / $state / $reorder) like any other model."""
+    dat = example_sir(sir_data, n_days=30)
+    g = OracleGenerator("walk") if kind == "oracle" else _gpu_generator("walk")
+    assert not g.public_methods.has_compare()
+    with pytest.raises(ValueError, match="Your model does not have a built-in 'compare' function"):
+        particle_filter(dat["data"], g, 100, None)
+
+    def compare(state, observed, pars=None):
+        # the walk's position against the (scaled) incidence series: any smooth density will do
+        return -0.5 * (state[0, :] - observed["incidence"] / 10.0) ** 2
+
+    res = []
+    for _ in range(2):
+        np.random.seed(1)       # the R loop resamples with the host RNG (SURVEY.md Q2)
+        p = particle_filter(dat["data"], g, 200, compare, seed=3,
+                            gpu_config=0 if kind == "gpu" else None)
+        res.append((p.run({"sd": 0.5}, save_history=True), p.history(), p.state()))
+    assert np.isfinite(res[0][0]) and res[0][0] == res[1][0]
+    assert np.array_equal(res[0][1], res[1][1]) and res[0][1].shape == (1, 200, 31)
+    assert np.array_equal(res[0][2], res[1][2])
+
+
+@pytest.mark.gpu
+def test_walk_model_engine_equals_oracle(sir_data):
+    from mcstate_b200 import dust
+
+    m = dust.dust_example("walk", "xoshiro256starstar").new({"sd": 2.5}, 0, 3000, seed=4)
+    from oracle import oracle as O
+
+    o = O.OracleModel(pars=np.array([[2.5]]), n_particles=3000, seed=4, model=O.WALK,
+                      scrambler=O.STARSTAR)
+    for t_end in (1, 7, 40):
+        assert np.array_equal(m.run(t_end), o.run(t_end))
+    assert np.array_equal(np.frombuffer(m.rng_state(), dtype=np.uint64).reshape(-1, 4),
+                          o.rng_state())
+    with pytest.raises(Exception, match="does not have a built-in 'compare'"):
+        m.set_data(dust.dust_data({"time_end": [4, 8], "x": [0.0, 1.0]}), False)
+
+
 # ------------------------------------------------------------------ relations
 def test_same_seed_same_result_and_rng_continues(gen, sir_data):
     """tests/testthat/test-particle-filter.R:22-34."""
