@@ -379,6 +379,14 @@ void set_initial(mcb_model *m) {
 }
 
 void draw_uniforms(mcb_model *m, int row_first, int row_last) {
+  if (m->v.n_fs == 1) {   // one stream shared by every set: a warp, look-ups batched
+    if (m->scrambler == 0)
+      mcb::k_draw_uniforms_shared<0><<<1, 32, 0, m->stream>>>(m->v, row_first, row_last, m->d_u, m->d_fs_after);
+    else
+      mcb::k_draw_uniforms_shared<1><<<1, 32, 0, m->stream>>>(m->v, row_first, row_last, m->d_u, m->d_fs_after);
+    ++m->launches;
+    return;
+  }
   const unsigned grid = blocks_for((size_t)m->v.n_fs, 128);
   if (m->scrambler == 0)
     mcb::k_draw_uniforms<0><<<grid, 128, 0, m->stream>>>(m->v, row_first, row_last, m->d_u, m->d_fs_after);
