@@ -212,7 +212,7 @@ int mcb_filter(mcb_model *m, uint64_t time_end, int save_trajectories,
 int mcb_filter_history(mcb_model *m, const size_t *particles, size_t n, double *out);
 
 /* A filter of one parameter set whose particles are all resident at once (up to
- * about 100 000 on a B200), run without snapshots, executes as ONE
+ * about 150 000 on a B200), run without snapshots, executes as ONE
  * cooperative kernel per mcb_filter call instead of two launches per data interval
  * (csrc/persistent.cuh); results are bit-identical either way.  enable = 0 keeps
  * this handle on the two-launch path (A/B measurements, tests); the environment

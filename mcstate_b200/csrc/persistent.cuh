@@ -36,14 +36,22 @@
 
 namespace mcb {
 
-constexpr int kPersistThreads = 128;
-constexpr int kPersistMaxBlocks = 1184;   // 8 per SM on 148 SMs: 151 552 particles
-// ...but past ~100 000 particles the SMs are full either way and the two-launch path's
-// leaner run kernel wins (measured: 75 000 -> 24.3 vs 28.9 us per interval, 131 072 ->
-// 31.6 vs 29.1): the single launch is used up to this many blocks
-constexpr int kPersistUseBlocks = 800;
+// 256-thread blocks: half as many block sums to prefix in every block and wider tiles for
+// the search than 128 (measured per interval: 15.3 vs 16.6 us at 2^16 particles, 15.6 vs
+// 24.5 at 75 000, 22.8 vs 31.6 at 150 000; 13.0 vs 12.3 at 4096)
+#ifndef MCB_PERSIST_THREADS
+#define MCB_PERSIST_THREADS 256
+#endif
+constexpr int kPersistThreads = MCB_PERSIST_THREADS;
+constexpr int kPersistMaxBlocks = 1184 * 128 / kPersistThreads;   // 151 552 particles (8 x 128 threads per SM on 148 SMs)
+// the single launch is used up to this many blocks (all that can be co-resident: it beats
+// the two-launch path over the whole range, 22.8 vs 28.3 us per interval at 150 000)
+#ifndef MCB_PERSIST_USE_BLOCKS
+#define MCB_PERSIST_USE_BLOCKS (1184 * 128 / MCB_PERSIST_THREADS)
+#endif
+constexpr int kPersistUseBlocks = MCB_PERSIST_USE_BLOCKS;
 #ifndef MCB_PERSIST_MINBLOCKS
-#define MCB_PERSIST_MINBLOCKS 8
+#define MCB_PERSIST_MINBLOCKS (8 * 128 / MCB_PERSIST_THREADS)
 #endif
 
 struct PersistArgs {

@@ -5,7 +5,7 @@ from mcstate_b200 import dust
 d = np.loadtxt("tests/golden/sir_incidence.csv", delimiter=",", skiprows=1)
 t, x = d[:, 1].astype(np.uint64) * 4, d[:, 0]
 g = dust.dust_example("sir")
-for n in [1 << 12, 1 << 14, 1 << 16, 75000, 1 << 17]:
+for n in [1 << 12, 1 << 14, 1 << 15, 1 << 16, 75000, 100000, 1 << 17, 150000]:
     for persistent in (True, False):
         m = g.new({}, 0, n, seed=1)
         m.set_persistent(persistent)

@@ -650,7 +650,7 @@ def _same(a, b):
     assert a.time() == b.time()
 
 
-@pytest.mark.parametrize("n", [1, 100, 128, 129, 4097, 1 << 16, 100000])
+@pytest.mark.parametrize("n", [1, 100, 255, 256, 257, 4097, 1 << 16, 150000])
 def test_persistent_filter_equals_two_launch(dust, orc, sir_data, n):
     t, x = _data(sir_data)
     a, b = _pair(dust, "sir", {}, n, 3)
