@@ -768,6 +768,7 @@ __global__ void k_draw_uniforms_shared(View v, int row_first, int row_last, doub
   }
   const int n_glob = v.n_sets_global;
   const long long n_pairs = (long long)(row_last - row_first) * n_glob;
+  int row0 = row_first, pg0 = 0;     // lane 0's position: counted, not divided
   for (long long base = 0; base < n_pairs; base += 32) {
     const long long q = base + lane;
     bool na = false;
@@ -782,17 +783,19 @@ __global__ void k_draw_uniforms_shared(View v, int row_first, int row_last, doub
     if (lane == 0) {
       const int n_here = (int)min(32LL, n_pairs - base);
       for (int j = 0; j < n_here; ++j) {
-        const long long qq = base + j;
-        const int row = row_first + (int)(qq / n_glob), pg = (int)(qq % n_glob);
         if (!((mask >> j) & 1u)) {
           const double u = xo_real<SCR>(r);
-          const int p = pg - v.set_offset;
+          const int p = pg0 - v.set_offset;
           if (p >= 0 && p < (int)v.n_sets)
-            u_draws[(size_t)(row < 0 ? 0 : row) * v.n_sets + p] = u;
+            u_draws[(size_t)(row0 < 0 ? 0 : row0) * v.n_sets + p] = u;
         }
-        if (pg == n_glob - 1 && row >= 0) {
-          uint64_t *o = fs_after + (size_t)row * 4;
-          o[0] = r.s0; o[1] = r.s1; o[2] = r.s2; o[3] = r.s3;
+        if (++pg0 == n_glob) {
+          if (row0 >= 0) {
+            uint64_t *o = fs_after + (size_t)row0 * 4;
+            o[0] = r.s0; o[1] = r.s1; o[2] = r.s2; o[3] = r.s3;
+          }
+          pg0 = 0;
+          ++row0;
         }
       }
     }
