@@ -153,6 +153,7 @@ class smc2_engine:
         # but not the filters (Q1), so the two drift apart until a proposal is accepted
         self._model_theta = theta[self._lo:self._hi].copy()
         self._model = self._new_model(pars.model(self._model_theta))
+        self._child = None  # the proposal's model handle, allocated once and reused
         self._filter_facade = filter
 
         self.step_current = 0
@@ -173,6 +174,21 @@ class smc2_engine:
         if rng_state is not None:
             m.set_rng_state(rng_state)
         return m
+
+    def _fork(self, pars_model):
+        """The proposal's filter: a model at the start time with the proposed parameters and
+        the parent's generator state (fork_smc2, R/particle_filter_state.R:400-424).  One
+        handle serves every replenishment -- it is reset (F2) and takes the streams by a
+        device copy, instead of an allocation, a host round trip of the RNG state and a
+        free per proposal."""
+        if self._child is None:
+            self._child = self._new_model(pars_model)
+        else:
+            self._child.update_state(pars=pars_model, time=int(self._times[0, 0]),
+                                     set_initial_state=True)
+        self._child.copy_sets_from(self._model, np.ones(self._hi - self._lo, dtype=bool),
+                                   state=False, rng=True)
+        return self._child
 
     def _gather(self, local):
         if self._dist is None or self.world == 1:
@@ -227,7 +243,7 @@ class smc2_engine:
         # sets with an impossible proposal are not forked (:164-169); the batched child
         # still needs valid parameters in those slots, so they keep the current ones
         run_pars = np.where(finite[lo:hi, None], pars[lo:hi], self._model_theta)
-        child = self._new_model(self._pars.model(run_pars), self._model.rng_state())
+        child = self._fork(self._pars.model(run_pars))
         time_end = int(self._times[self.step_current - 1, 1])
         ll_child = child.filter(time_end)["log_likelihood"]
         self.n_filter_rows += (hi - lo) * self.step_current
