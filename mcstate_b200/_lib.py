@@ -102,6 +102,16 @@ def build(force: bool = False) -> str:
 _lib = None
 
 
+def load(path: str):
+    """dlopen one build of the engine and bind every entry point of the header."""
+    L = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    return L
+
+
 def lib():
     """Load the engine; raises if the shared library has not been built."""
     global _lib
@@ -110,13 +120,68 @@ def lib():
             raise RuntimeError(
                 "libmcstate_b200.so is missing: run `python -c 'import __graft_entry__ as g; "
                 "g.build()'` (mcstate_b200 has no CPU fallback)")
-        L = C.CDLL(LIB_PATH)
-        for name, (res, args) in SIGNATURES.items():
-            fn = getattr(L, name)
-            fn.restype = res
-            fn.argtypes = args
-        _lib = L
+        _lib = load(LIB_PATH)
     return _lib
+
+
+# ---- user-supplied models (dust::dust(<file>) in the reference) ----------------------
+USER_MODEL_DIR = os.path.join(_HERE, "_user_models")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+_USER_NVFLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+                 "-fmad=false", "-Xcompiler", "-fPIC,-Wall", "-ccbin", "/usr/bin/g++", "-shared"]
+_user_libs = {}
+
+
+def user_model_path(source: str) -> str:
+    """Where the engine built around ``source`` lives: the name carries a digest of the
+    model source, the engine sources and the flags, so a stale build is never loaded."""
+    import hashlib
+
+    src = os.path.join(_HERE, "csrc")
+    h = hashlib.sha256()
+    files = [source, os.path.join(os.path.dirname(_HERE), "include", "mcstate_b200.h")]
+    files += [os.path.join(src, f) for f in sorted(os.listdir(src)) if f.endswith((".cu", ".cuh"))]
+    for f in files:
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(_USER_NVFLAGS).encode())
+    stem = os.path.splitext(os.path.basename(source))[0]
+    return os.path.join(USER_MODEL_DIR, "libmcb_%s_%s.so" % (stem, h.hexdigest()[:12]))
+
+
+def build_user_model(source: str, quiet: bool = True, force: bool = False) -> str:
+    """Compile the engine around one user-supplied model header (sm_100a, in-tree; nvcc
+    cross-compiles without a GPU).  There is no other way to run such a model: without
+    nvcc, or if the source does not compile, this raises."""
+    source = os.path.abspath(source)
+    if not os.path.exists(source):
+        raise FileNotFoundError("model source '%s' does not exist" % source)
+    out = user_model_path(source)
+    if force or not os.path.exists(out):
+        if not os.path.exists(NVCC):
+            raise RuntimeError("nvcc (%s) is needed to compile '%s': mcstate_b200 has no "
+                               "interpreted or CPU path for user models" % (NVCC, source))
+        os.makedirs(USER_MODEL_DIR, exist_ok=True)
+        tmp = out + ".tmp%d" % os.getpid()
+        cmd = [NVCC] + _USER_NVFLAGS + ['-DMCB_USER_MODEL="%s"' % source, "-o", tmp,
+                                         os.path.join(_HERE, "csrc", "api.cu")]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            if os.path.exists(tmp):
+                os.remove(tmp)
+            raise RuntimeError("compiling '%s' failed:\n%s" % (source, r.stderr[-4000:]))
+        if not quiet and r.stderr:
+            print(r.stderr)
+        os.replace(tmp, out)
+    return out
+
+
+def user_lib(source: str, quiet: bool = True):
+    """The loaded engine for one user model (built on first use, one dlopen per build)."""
+    path = build_user_model(source, quiet)
+    if path not in _user_libs:
+        _user_libs[path] = load(path)
+    return _user_libs[path]
 
 
 def check(rc: int) -> None:

@@ -53,6 +53,39 @@ struct ModelDesc {
   const char *data_names[2];
 };
 
+// parameter slots of the closed population (S0, I0, R0) of a compartmental model, or
+// none; draws with a parameter-only probability (walk tables)
+struct ModelTables {
+  int pop[3];
+  int n_const;
+  int freq;      // parameter slot of the steps-per-incidence-interval count, or -1
+};
+
+// ---- which models this build of the library holds ---------------------------------
+// The stock library holds the four dust_example models the reference uses.  A build
+// with -DMCB_USER_MODEL="<header>" holds ONE model instead, the `mcb::UserModel` that
+// header defines by the contract at the top of models.cuh (what dust::dust(<file>) /
+// odin.dust::odin_dust do for the reference: a model source compiled into its own
+// shared object behind the same generator interface -- tests/testthat/
+// test-pmcmc-parallel.R:197, helper-mcstate.R:478-492 with compare_variable.cpp).  The
+// header also defines MCB_USER_MODEL_DESC, the ModelDesc initialiser (name, counts,
+// parameter names and defaults, state names, data field).
+#ifdef MCB_USER_MODEL
+}  // namespace
+#include MCB_USER_MODEL
+namespace {
+static_assert(!mcb::UserModel::kHasLean && mcb::UserModel::kConst == 0,
+              "a user model implements the general form (initial / update / compare)");
+static_assert(mcb::UserModel::kState >= 1 && mcb::UserModel::kState <= mcb::kMaxState &&
+              mcb::UserModel::kPar >= 1 && mcb::UserModel::kPar <= mcb::kMaxPar &&
+              mcb::UserModel::kData >= 0 && mcb::UserModel::kData <= 1,
+              "user model: 1..8 state variables, 1..8 parameters, at most one data field");
+#define MCB_MODELS(X) X(0, mcb::UserModel)
+const ModelDesc kModels[] = {MCB_USER_MODEL_DESC};
+const ModelTables kModelTables[] = {{{-1, -1, -1}, 0, -1}};   // no memo tables: general form only
+#else
+#define MCB_MODELS(X) \
+  X(0, mcb::SirModel) X(1, mcb::SirsModel) X(2, mcb::VolatilityModel) X(3, mcb::WalkModel)
 // defaults: scripts/generate_vignette_data.R:11-12, tests/testthat/helper-mcstate.R:11-15
 const ModelDesc kModels[] = {
     {"sir", 5, 7, 1,
@@ -78,17 +111,11 @@ const ModelDesc kModels[] = {
      {"x"},
      {nullptr}},
 };
-// parameter slots of the closed population (S0, I0, R0) of a compartmental model, or
-// none; draws with a parameter-only probability (walk tables)
-struct ModelTables {
-  int pop[3];
-  int n_const;
-  int freq;      // parameter slot of the steps-per-incidence-interval count, or -1
-};
 const ModelTables kModelTables[] = {{{4, 2, 5}, mcb::SirModel::kConst, 6},
                                     {{5, 3, 6}, mcb::SirsModel::kConst, 7},
                                     {{-1, -1, -1}, 0, -1},
                                     {{-1, -1, -1}, 0, -1}};
+#endif
 constexpr int kNumModels = sizeof(kModels) / sizeof(kModels[0]);
 constexpr size_t kMaxWalkRows = 2048;  // counts covered by a walk table (samplers.cuh)
 
@@ -318,14 +345,12 @@ void run_compare(mcb_model *m, const double *y_in, double *y_out, uint64_t t0, u
                  int prev_row, int row, double *hist, int *kappa_out) {
   const int key = m->model_id * 2 + m->scrambler;
   switch (key) {
-    case 0: launch_run_compare<mcb::SirModel, 0>(m, y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out); break;
-    case 1: launch_run_compare<mcb::SirModel, 1>(m, y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out); break;
-    case 2: launch_run_compare<mcb::SirsModel, 0>(m, y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out); break;
-    case 3: launch_run_compare<mcb::SirsModel, 1>(m, y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out); break;
-    case 4: launch_run_compare<mcb::VolatilityModel, 0>(m, y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out); break;
-    case 5: launch_run_compare<mcb::VolatilityModel, 1>(m, y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out); break;
-    case 6: launch_run_compare<mcb::WalkModel, 0>(m, y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out); break;
-    default: launch_run_compare<mcb::WalkModel, 1>(m, y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out); break;
+#define X(ID, M)                                                                                      \
+    case 2 * ID: launch_run_compare<M, 0>(m, y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out); break; \
+    case 2 * ID + 1: launch_run_compare<M, 1>(m, y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out); break;
+    MCB_MODELS(X)
+#undef X
+    default: break;
   }
 }
 
@@ -336,25 +361,29 @@ void weights_scan(mcb_model *m, int row) {
   else launch_chained(m, m->chain, mcb::k_weights_scan<false>, grid, mcb::kTileThreads, m->v, row);
 }
 
+// one instantiation per state count a model may have (models.cuh: kMaxState)
+#define MCB_STATE_COUNTS(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
+static_assert(mcb::kMaxState == 8, "MCB_STATE_COUNTS covers 1..kMaxState");
+
 void resample_gather(mcb_model *m, int row, const double *src, double *dst, int *kappa_out) {
   const unsigned grid = blocks_for(m->v.n_total, mcb::kGatherThreads);
-  if (m->v.n_state == 5)
-    mcb::k_resample_gather<5><<<grid, mcb::kGatherThreads, 0, m->stream>>>(m->v, row, src, dst, kappa_out);
-  else if (m->v.n_state == 4)
-    mcb::k_resample_gather<4><<<grid, mcb::kGatherThreads, 0, m->stream>>>(m->v, row, src, dst, kappa_out);
-  else
-    mcb::k_resample_gather<1><<<grid, mcb::kGatherThreads, 0, m->stream>>>(m->v, row, src, dst, kappa_out);
+  switch (m->v.n_state) {
+#define X(N) case N: mcb::k_resample_gather<N><<<grid, mcb::kGatherThreads, 0, m->stream>>>(m->v, row, src, dst, kappa_out); break;
+    MCB_STATE_COUNTS(X)
+#undef X
+    default: break;
+  }
   ++m->launches;
 }
 
 void finish_state(mcb_model *m, int last, int last_weighted, int *kappa_out) {
   const unsigned grid = blocks_for(m->v.n_total, mcb::kGatherThreads);
-  if (m->v.n_state == 5)
-    mcb::k_finish_state<5><<<grid, mcb::kGatherThreads, 0, m->stream>>>(m->v, last, last_weighted, kappa_out);
-  else if (m->v.n_state == 4)
-    mcb::k_finish_state<4><<<grid, mcb::kGatherThreads, 0, m->stream>>>(m->v, last, last_weighted, kappa_out);
-  else
-    mcb::k_finish_state<1><<<grid, mcb::kGatherThreads, 0, m->stream>>>(m->v, last, last_weighted, kappa_out);
+  switch (m->v.n_state) {
+#define X(N) case N: mcb::k_finish_state<N><<<grid, mcb::kGatherThreads, 0, m->stream>>>(m->v, last, last_weighted, kappa_out); break;
+    MCB_STATE_COUNTS(X)
+#undef X
+    default: break;
+  }
   ++m->launches;
 }
 
@@ -362,19 +391,23 @@ void prepare_sets(mcb_model *m) {
   const int n_const = kModelTables[m->model_id].n_const;
   const size_t rows = n_const ? (size_t)m->v.n_tab + (size_t)n_const * m->v.n_wrows : 1;
   const dim3 grid(blocks_for(rows, 128), (unsigned)m->v.n_sets);
-  if (m->model_id == 0) mcb::k_prepare_sets<mcb::SirModel><<<grid, 128, 0, m->stream>>>(m->v);
-  else if (m->model_id == 1) mcb::k_prepare_sets<mcb::SirsModel><<<grid, 128, 0, m->stream>>>(m->v);
-  else if (m->model_id == 2) mcb::k_prepare_sets<mcb::VolatilityModel><<<grid, 128, 0, m->stream>>>(m->v);
-  else mcb::k_prepare_sets<mcb::WalkModel><<<grid, 128, 0, m->stream>>>(m->v);
+  switch (m->model_id) {
+#define X(ID, M) case ID: mcb::k_prepare_sets<M><<<grid, 128, 0, m->stream>>>(m->v); break;
+    MCB_MODELS(X)
+#undef X
+    default: break;
+  }
   ++m->launches;
 }
 
 void set_initial(mcb_model *m) {
   const unsigned grid = blocks_for(m->v.n_total, 256);
-  if (m->model_id == 0) mcb::k_set_initial<mcb::SirModel><<<grid, 256, 0, m->stream>>>(m->v);
-  else if (m->model_id == 1) mcb::k_set_initial<mcb::SirsModel><<<grid, 256, 0, m->stream>>>(m->v);
-  else if (m->model_id == 2) mcb::k_set_initial<mcb::VolatilityModel><<<grid, 256, 0, m->stream>>>(m->v);
-  else mcb::k_set_initial<mcb::WalkModel><<<grid, 256, 0, m->stream>>>(m->v);
+  switch (m->model_id) {
+#define X(ID, M) case ID: mcb::k_set_initial<M><<<grid, 256, 0, m->stream>>>(m->v); break;
+    MCB_MODELS(X)
+#undef X
+    default: break;
+  }
   ++m->launches;
 }
 
@@ -533,14 +566,12 @@ const void *persistent_kernel() {
 }
 const void *persistent_kernel_for(const mcb_model *m) {
   switch (m->model_id * 2 + m->scrambler) {
-    case 0: return persistent_kernel<mcb::SirModel, 0>();
-    case 1: return persistent_kernel<mcb::SirModel, 1>();
-    case 2: return persistent_kernel<mcb::SirsModel, 0>();
-    case 3: return persistent_kernel<mcb::SirsModel, 1>();
-    case 4: return persistent_kernel<mcb::VolatilityModel, 0>();
-    case 5: return persistent_kernel<mcb::VolatilityModel, 1>();
-    case 6: return persistent_kernel<mcb::WalkModel, 0>();
-    default: return persistent_kernel<mcb::WalkModel, 1>();
+#define X(ID, M)                                          \
+    case 2 * ID: return persistent_kernel<M, 0>();        \
+    case 2 * ID + 1: return persistent_kernel<M, 1>();
+    MCB_MODELS(X)
+#undef X
+    default: return nullptr;
   }
 }
 

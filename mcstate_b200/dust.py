@@ -15,6 +15,7 @@ or ``(n_state, n_particles, n_pars)``; indices passed to ``set_index`` /
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -136,7 +137,8 @@ class dust_model:
 
     def __init__(self, generator, pars, time, n_particles, n_threads=1, seed=None,
                  pars_multi=False, deterministic=False, gpu_config=None, seed_per_set=False):
-        L = _lib.lib()
+        L = self._L = generator._L   # the library that holds this generator's model
+        self._ck = generator._check
         self._gen = generator
         self._n_threads = int(n_threads)
         self._pars_multi = bool(pars_multi)
@@ -161,7 +163,7 @@ class dust_model:
         # seed_per_set: one 32-byte seed per parameter set; each set then owns the streams a
         # separate model object seeded with it would (independent filters in one handle)
         self._n_fs = max(1, n_pars) if seed_per_set else 1
-        check(L.mcb_alloc_ex(generator.model_id, ptr(vec, f64p), int(n_particles), n_pars,
+        self._ck(L.mcb_alloc_ex(generator.model_id, ptr(vec, f64p), int(n_particles), n_pars,
                              int(time), ptr(words, u64p), words.size // 4,
                              _lib.SEED_PER_SET if seed_per_set else _lib.SEED_SHARED,
                              generator.scrambler, int(deterministic), device_id, C.byref(h)))
@@ -179,7 +181,7 @@ class dust_model:
         h = getattr(self, "_h", None)
         if h:
             try:
-                _lib.lib().mcb_free(h)
+                self._L.mcb_free(h)
             except Exception:
                 pass
             self._h = None
@@ -214,7 +216,7 @@ class dust_model:
 
     def time(self):
         t = C.c_uint64()
-        check(_lib.lib().mcb_time(self._h, C.byref(t)))
+        self._ck(self._L.mcb_time(self._h, C.byref(t)))
         return int(t.value)
 
     def pars(self):
@@ -242,7 +244,7 @@ class dust_model:
     def set_index(self, index):
         """R/particle_filter_state.R:261,263 (1-based; dict keeps row names)."""
         if index is None:
-            check(_lib.lib().mcb_set_index(self._h, None, 0))
+            self._ck(self._L.mcb_set_index(self._h, None, 0))
             self._n_index, self._index_names = self._n_state, None
             return
         if isinstance(index, dict):
@@ -254,20 +256,20 @@ class dust_model:
         if np.any(idx < 0) or np.any(idx >= self._n_state):
             raise ValueError("All elements of 'index' must lie in [1, %d]" % self._n_state)
         idx = idx.astype(np.uintp)
-        check(_lib.lib().mcb_set_index(self._h, ptr(idx, szp), idx.size))
+        self._ck(self._L.mcb_set_index(self._h, ptr(idx, szp), idx.size))
         self._n_index = int(idx.size)
 
     def run(self, time_end):
         """R/particle_filter_state.R:65."""
         out = np.zeros((self._n_total, self._n_index))
-        check(_lib.lib().mcb_run(self._h, int(time_end), ptr(out, f64p)))
+        self._ck(self._L.mcb_run(self._h, int(time_end), ptr(out, f64p)))
         return self._shape_out(out, self._n_index)
 
     def simulate(self, time_end):
         """R/predict.R:79: (n_index, n_particles[, n_pars], n_times)."""
         t = np.ascontiguousarray(np.atleast_1d(time_end), dtype=np.uint64)
         out = np.zeros((t.size, self._n_total, self._n_index))
-        check(_lib.lib().mcb_simulate(self._h, ptr(t, u64p), t.size, ptr(out, f64p)))
+        self._ck(self._L.mcb_simulate(self._h, ptr(t, u64p), t.size, ptr(out, f64p)))
         if self._pars_multi:
             return out.reshape(t.size, self._n_sets, self._n_particles, self._n_index).transpose(3, 2, 1, 0)
         return out.transpose(2, 1, 0)
@@ -276,7 +278,7 @@ class dust_model:
         """R/particle_filter_state.R:79,81,114,272."""
         if index is None:
             out = np.zeros((self._n_total, self._n_state))
-            check(_lib.lib().mcb_state(self._h, None, 0, ptr(out, f64p)))
+            self._ck(self._L.mcb_state(self._h, None, 0, ptr(out, f64p)))
             return self._shape_out(out, self._n_state)
         if isinstance(index, dict):
             index = list(index.values())
@@ -285,7 +287,7 @@ class dust_model:
             raise ValueError("All elements of 'index' must lie in [1, %d]" % self._n_state)
         idx = idx.astype(np.uintp)
         out = np.zeros((self._n_total, idx.size))
-        check(_lib.lib().mcb_state(self._h, ptr(idx, szp), idx.size, ptr(out, f64p)))
+        self._ck(self._L.mcb_state(self._h, ptr(idx, szp), idx.size, ptr(out, f64p)))
         return self._shape_out(out, idx.size)
 
     def state_particles(self, index_particle):
@@ -296,7 +298,7 @@ class dust_model:
             raise IndexError("index_particle out of range")
         flat = np.ascontiguousarray(ip - 1, dtype=np.uintp)
         out = np.zeros((flat.size, self._n_state))
-        check(_lib.lib().mcb_state_particles(self._h, ptr(flat, szp), flat.size, ptr(out, f64p)))
+        self._ck(self._L.mcb_state_particles(self._h, ptr(flat, szp), flat.size, ptr(out, f64p)))
         return out.T
 
     def update_state(self, pars=None, state=None, time=None, set_initial_state=None):
@@ -325,7 +327,7 @@ class dust_model:
             st_len = st.size
         if set_initial_state is None:
             set_initial_state = state is None
-        check(_lib.lib().mcb_update_state(self._h, ptr(vec, f64p), ptr(st, f64p), st_len,
+        self._ck(self._L.mcb_update_state(self._h, ptr(vec, f64p), ptr(st, f64p), st_len,
                                           int(time is not None), 0 if time is None else int(time),
                                           int(bool(set_initial_state))))
 
@@ -340,12 +342,12 @@ class dust_model:
         elif k.size != self._n_particles:
             raise ValueError("Expected a vector of length %d for 'index'" % self._n_particles)
         k = np.ascontiguousarray(k, dtype=np.int32).ravel()
-        check(_lib.lib().mcb_reorder(self._h, ptr(k, i32p)))
+        self._ck(self._L.mcb_reorder(self._h, ptr(k, i32p)))
 
     def rng_state(self, first_only=False, last_only=False):
         """R/particle_filter.R:813; R/particle_filter_state.R:363,406,420: raw bytes."""
         out = np.zeros((self._n_total + self._n_fs) * 4, dtype=np.uint64)
-        check(_lib.lib().mcb_rng_state(self._h, 0, ptr(out, u64p)))
+        self._ck(self._L.mcb_rng_state(self._h, 0, ptr(out, u64p)))
         if first_only:
             return out[:4].tobytes()
         if last_only:  # the filter stream(s)
@@ -358,7 +360,7 @@ class dust_model:
         if raw.size != (self._n_total + self._n_fs) * 4:
             raise ValueError("'rng_state' must be a raw vector of length %d (but was %d)"
                              % ((self._n_total + self._n_fs) * 32, raw.size * 8))
-        check(_lib.lib().mcb_set_rng_state(self._h, ptr(raw, u64p), raw.size))
+        self._ck(self._L.mcb_set_rng_state(self._h, ptr(raw, u64p), raw.size))
 
     def set_data(self, data, shared=False):
         """R/particle_filter_state.R:243-246: ``data`` = dust_data(...)."""
@@ -376,7 +378,7 @@ class dust_model:
                         raise KeyError("data is missing the field '%s'" % name)
                     x = row[name]
                     vals[i, j, f] = np.nan if x is None else float(x)
-        check(_lib.lib().mcb_set_data(self._h, times.size, ptr(times, u64p), ptr(vals, f64p),
+        self._ck(self._L.mcb_set_data(self._h, times.size, ptr(times, u64p), ptr(vals, f64p),
                                       int(bool(shared))))
         self._data_times = times
 
@@ -386,7 +388,7 @@ class dust_model:
         w = np.frombuffer(bytes(raw), dtype=np.uint64).copy()
         if w.size != 4:
             raise ValueError("the filter stream is 32 bytes")
-        check(_lib.lib().mcb_set_filter_stream(self._h, ptr(w, u64p)))
+        self._ck(self._L.mcb_set_filter_stream(self._h, ptr(w, u64p)))
 
     def set_stream_sharing(self, n_sets_global, set_offset, na_global):
         """This handle holds sets [set_offset, set_offset + n_pars) of ``n_sets_global``;
@@ -394,7 +396,7 @@ class dust_model:
         na = np.ascontiguousarray(na_global, dtype=np.uint8)
         if na.shape != (len(self._data_times), int(n_sets_global)):
             raise ValueError("'na_global' must be [n_data, n_sets_global]")
-        check(_lib.lib().mcb_set_stream_sharing(self._h, int(n_sets_global), int(set_offset),
+        self._ck(self._L.mcb_set_stream_sharing(self._h, int(n_sets_global), int(set_offset),
                                                 na.tobytes()))
 
     def copy_sets_from(self, other, take, state=True, rng=True):
@@ -403,13 +405,15 @@ class dust_model:
         t = np.ascontiguousarray(take, dtype=np.uint8)
         if t.size != self._n_sets:
             raise ValueError("'take' must have one flag per parameter set")
-        check(_lib.lib().mcb_copy_sets(self._h, other._h, t.tobytes(), int(state), int(rng)))
+        if other._L is not self._L:
+            raise ValueError("copy_sets_from needs two objects of the same model")
+        self._ck(self._L.mcb_copy_sets(self._h, other._h, t.tobytes(), int(state), int(rng)))
 
     def compare_data(self):
         """``$compare_data()``: log-weights for the datum at the current time, or None."""
         w = np.zeros(self._n_total)
         has = C.c_int(0)
-        check(_lib.lib().mcb_compare_data(self._h, ptr(w, f64p), C.byref(has)))
+        self._ck(self._L.mcb_compare_data(self._h, ptr(w, f64p), C.byref(has)))
         if not has.value:
             return None
         return w.reshape(self._n_sets, self._n_particles).T if self._pars_multi else w
@@ -419,7 +423,7 @@ class dust_model:
         w = np.asarray(weights, dtype=np.float64)
         w = np.ascontiguousarray(w.T if w.ndim == 2 else w).ravel()
         k = np.zeros(self._n_total, dtype=np.int32)
-        check(_lib.lib().mcb_resample(self._h, ptr(w, f64p), ptr(k, i32p)))
+        self._ck(self._L.mcb_resample(self._h, ptr(w, f64p), ptr(k, i32p)))
         return k.reshape(self._n_sets, self._n_particles).T if self._pars_multi else k
 
     def filter(self, time_end=None, save_trajectories=False, time_snapshot=None,
@@ -432,9 +436,9 @@ class dust_model:
             raise _lib.McbError(_lib.ERR_STATE, "Data has not been set for this object")
         if time_end is None:
             time_end = int(self._data_times[-1])
-        L = _lib.lib()
+        L = self._L
         n_rows = C.c_size_t()
-        check(L.mcb_filter_rows(self._h, int(time_end), C.byref(n_rows)))
+        self._ck(L.mcb_filter_rows(self._h, int(time_end), C.byref(n_rows)))
         ll = np.zeros(self._n_sets)
         traj = None
         on_device = isinstance(save_trajectories, str)
@@ -450,7 +454,7 @@ class dust_model:
         mll = None
         if min_log_likelihood is not None:
             mll = np.ascontiguousarray(np.atleast_1d(min_log_likelihood), dtype=np.float64)
-        check(L.mcb_filter(self._h, int(time_end), 2 if on_device else int(bool(save_trajectories)),
+        self._ck(L.mcb_filter(self._h, int(time_end), 2 if on_device else int(bool(save_trajectories)),
                            ptr(snap_t, u64p), 0 if snap_t is None else snap_t.size,
                            ptr(mll, f64p), 0 if mll is None else mll.size,
                            ptr(ll, f64p), ptr(traj, f64p), ptr(snaps, f64p)))
@@ -491,7 +495,7 @@ class dust_model:
             glob = ip - 1
         flat = np.ascontiguousarray(glob.ravel(), dtype=np.uintp)
         out = np.zeros((self._hist_rows + 1, flat.size, self._n_index))
-        check(_lib.lib().mcb_filter_history(self._h, ptr(flat, szp), flat.size, ptr(out, f64p)))
+        self._ck(self._L.mcb_filter_history(self._h, ptr(flat, szp), flat.size, ptr(out, f64p)))
         if self._pars_multi:
             return out.reshape(-1, glob.shape[0], self._n_sets, self._n_index).transpose(3, 1, 2, 0)
         return out.transpose(2, 1, 0)
@@ -499,38 +503,38 @@ class dust_model:
     def set_persistent(self, enable=True):
         """Small single-set filters run as one cooperative kernel per call
         (csrc/persistent.cuh); ``False`` keeps this model on the two-launch path."""
-        check(_lib.lib().mcb_set_persistent(self._h, int(bool(enable))))
+        self._ck(self._L.mcb_set_persistent(self._h, int(bool(enable))))
 
     # ---- asynchronous variant used to keep several GPUs / handles busy
     def filter_enqueue(self, time_end=None):
         if time_end is None:
             time_end = int(self._data_times[-1])
-        check(_lib.lib().mcb_filter_enqueue(self._h, int(time_end)))
+        self._ck(self._L.mcb_filter_enqueue(self._h, int(time_end)))
 
     def filter_collect(self):
         ll = np.zeros(self._n_sets)
-        check(_lib.lib().mcb_filter_collect(self._h, ptr(ll, f64p)))
+        self._ck(self._L.mcb_filter_collect(self._h, ptr(ll, f64p)))
         return ll
 
     def set_stream(self, cuda_stream):
-        check(_lib.lib().mcb_set_stream(self._h, C.c_void_p(cuda_stream)))
+        self._ck(self._L.mcb_set_stream(self._h, C.c_void_p(cuda_stream)))
 
     def synchronize(self):
-        check(_lib.lib().mcb_synchronize(self._h))
+        self._ck(self._L.mcb_synchronize(self._h))
 
     def set_kernel_timing(self, enable=True):
-        check(_lib.lib().mcb_set_kernel_timing(self._h, int(bool(enable))))
+        self._ck(self._L.mcb_set_kernel_timing(self._h, int(bool(enable))))
 
     def kernel_timing(self):
         """(ms[4], launches[4]) for run+compare, tile weights, finalize, resample+gather."""
         ms = np.zeros(4)
         n = np.zeros(4, dtype=np.uint64)
-        check(_lib.lib().mcb_kernel_timing(self._h, ptr(ms, f64p), ptr(n, u64p)))
+        self._ck(self._L.mcb_kernel_timing(self._h, ptr(ms, f64p), ptr(n, u64p)))
         return ms, n
 
     def launch_count(self):
         n = C.c_uint64()
-        check(_lib.lib().mcb_launch_count(self._h, C.byref(n)))
+        self._ck(self._L.mcb_launch_count(self._h, C.byref(n)))
         return int(n.value)
 
 
@@ -540,8 +544,11 @@ class dust_generator:
 
     name = "dust_generator"
 
-    def __init__(self, model_name, algorithm="xoshiro256plus"):
-        L = _lib.lib()
+    def __init__(self, model_name, algorithm="xoshiro256plus", library=None):
+        # `library`: a build of the engine that holds a user-supplied model (dust() below);
+        # the stock library holds the four dust_example models
+        L = self._L = _lib.lib() if library is None else library
+        check = self._check
         mid, ns, npar, nd = C.c_int(), C.c_size_t(), C.c_size_t(), C.c_size_t()
         check(L.mcb_model_lookup(model_name.encode(), C.byref(mid), C.byref(ns), C.byref(npar),
                                  C.byref(nd)))
@@ -558,6 +565,11 @@ class dust_generator:
         self.state_names = [L.mcb_model_state_name(mid.value, i).decode() for i in range(ns.value)]
         self.data_fields = [L.mcb_model_data_name(mid.value, i).decode() for i in range(nd.value)]
         self.public_methods = self  # R: model$public_methods$has_compare()
+
+    def _check(self, rc):
+        if rc != _lib.OK:
+            msg = self._L.mcb_last_error()
+            raise _lib.McbError(rc, msg.decode() if msg else "mcstate_b200 error %d" % rc)
 
     # -- static capability queries
     def has_compare(self):
@@ -576,7 +588,7 @@ class dust_generator:
         return self.algorithm
 
     def gpu_info(self):
-        L = _lib.lib()
+        L, check = self._L, self._check
         n = C.c_int(0)
         rc = L.mcb_device_count(C.byref(n))
         devices = []
@@ -612,6 +624,30 @@ class dust_generator:
         vals = {n: float(pars.get(n, d)) for n, d in zip(self.par_names, self.par_defaults)}
         return {"vars": list(self.state_names), "pars": vals,
                 "index": {n: i + 1 for i, n in enumerate(self.state_names)}}
+
+
+def dust(path, quiet=True, algorithm="xoshiro256plus"):
+    """``dust::dust(path)``: compile a user-supplied model and return its generator
+    (tests/testthat/test-pmcmc-parallel.R:197; with a compiled compare as in
+    tests/testthat/helper-mcstate.R:478-492 + compare_variable.cpp).
+
+    ``path`` is a CUDA header defining ``mcb::UserModel`` and ``MCB_USER_MODEL_DESC`` by
+    the contract of csrc/models.cuh (``mcstate_b200/examples/seir.cuh`` is one).  The
+    engine -- every kernel of the filter, templated on the model -- is compiled around
+    it for sm_100a into its own shared library with the same C ABI; the generator
+    returned behaves like the ``dust_example`` ones everywhere (particle_filter, pmcmc,
+    smc2, sharding).  No GPU is needed to build; none means no way to run."""
+    L = _lib.user_lib(path, quiet)
+    # a user build holds exactly one model: id 0
+    name = None
+    for cand in (os.path.splitext(os.path.basename(path))[0],):
+        mid = C.c_int()
+        if L.mcb_model_lookup(cand.encode(), C.byref(mid), None, None, None) == _lib.OK:
+            name = cand
+    if name is None:
+        raise ValueError("'%s': MCB_USER_MODEL_DESC must name the model after its file "
+                         "('%s')" % (path, os.path.splitext(os.path.basename(path))[0]))
+    return dust_generator(name, algorithm, library=L)
 
 
 def dust_example(name, algorithm="xoshiro256plus"):

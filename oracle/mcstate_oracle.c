@@ -525,15 +525,20 @@ void orc_history_single(const double *value, const int *order, size_t ny,
 /*   volatility: alpha sigma gamma tau x0                              */
 /*     (tests/testthat/helper-mcstate.R:98-146: x' = alpha x + sigma N(0,1),  */
 /*      observed ~ N(gamma x, tau); one real state, the Kalman filter is exact) */
+/*   seir: beta sigma gamma I0 exp_noise S0 E0 freq                    */
+/*     (not a dust example: the twin of mcstate_b200/examples/seir.cuh, the   */
+/*      user-supplied model the engine compiles the way dust::dust() would)   */
 /* ------------------------------------------------------------------ */
 #define ORC_MAX_PAR 8
 #define ORC_MAX_STATE 8
 
 size_t orc_model_n_state(int model) {
-  return model == ORC_MODEL_SIR ? 5 : model == ORC_MODEL_SIRS ? 4 : 1;   /* volatility, walk: 1 */
+  return model == ORC_MODEL_SIR ? 5 : model == ORC_MODEL_SIRS ? 4 : model == ORC_MODEL_SEIR ? 6
+       : 1;   /* volatility, walk: 1 */
 }
 size_t orc_model_n_par(int model) {
-  return model == ORC_MODEL_SIR ? 7 : model == ORC_MODEL_SIRS ? 8 : model == ORC_MODEL_VOLATILITY ? 5 : 1;
+  return model == ORC_MODEL_SIR ? 7 : model == ORC_MODEL_SIRS || model == ORC_MODEL_SEIR ? 8
+       : model == ORC_MODEL_VOLATILITY ? 5 : 1;
 }
 size_t orc_model_n_data(int model) { (void)model; return 1; }
 
@@ -547,6 +552,9 @@ void orc_model_default_pars(int model, double *p) {
   } else if (model == ORC_MODEL_VOLATILITY) {
     /* tests/testthat/helper-mcstate.R:99 */
     p[0] = 0.91; p[1] = 1.0; p[2] = 1.0; p[3] = 1.0; p[4] = 0.0;
+  } else if (model == ORC_MODEL_SEIR) {
+    p[0] = 0.3; p[1] = 0.25; p[2] = 0.1; p[3] = 10.0; p[4] = 1e6; p[5] = 1000.0; p[6] = 0.0;
+    p[7] = 4.0;
   } else {
     p[0] = 1.0;   /* walk: sd */
   }
@@ -559,6 +567,8 @@ static void model_initial(int model, const double *p, double *y) {
     y[0] = p[5]; y[1] = p[3]; y[2] = p[6]; y[3] = 0.0;
   } else if (model == ORC_MODEL_VOLATILITY) {
     y[0] = p[4];
+  } else if (model == ORC_MODEL_SEIR) {
+    y[0] = p[5]; y[1] = p[6]; y[2] = p[3]; y[3] = 0.0; y[4] = 0.0; y[5] = 0.0;
   } else {
     y[0] = 0.0;
   }
@@ -602,6 +612,27 @@ static void sirs_update(uint64_t time, const double *y, uint64_t s[4], int scr, 
   yn[3] = (time % (uint64_t)freq == 0) ? n_SI : y[3] + n_SI;
 }
 
+/* SIR with a latent compartment (vignettes/sir_models.Rmd:44-54 extended): draws in the
+ * order S->E, E->I, I->R; incidence counts E->I */
+static void seir_update(uint64_t time, const double *y, uint64_t s[4], int scr, int det,
+                        const double *p, double *yn) {
+  const double S = y[0], E = y[1], I = y[2], R = y[3];
+  const double beta = p[0], sigma = p[1], gamma = p[2], freq = p[7], dt = 1.0 / freq;
+  const double N = S + E + I + R;
+  const double p_SE = 1.0 - orc_exp(-beta * I / N);
+  const double p_EI = 1.0 - orc_exp(-sigma);
+  const double p_IR = 1.0 - orc_exp(-gamma);
+  const double n_SE = draw_binomial(s, scr, det, S, p_SE * dt);
+  const double n_EI = draw_binomial(s, scr, det, E, p_EI * dt);
+  const double n_IR = draw_binomial(s, scr, det, I, p_IR * dt);
+  yn[0] = S - n_SE;
+  yn[1] = E + n_SE - n_EI;
+  yn[2] = I + n_EI - n_IR;
+  yn[3] = R + n_IR;
+  yn[4] = y[4] + n_EI;
+  yn[5] = (time % (uint64_t)freq == 0) ? n_EI : y[5] + n_EI;
+}
+
 /* x' = alpha x + sigma N(0, 1); deterministic mode puts the mean in place of the draw */
 static void volatility_update(const double *y, uint64_t s[4], int scr, int det, const double *p,
                               double *yn) {
@@ -615,6 +646,7 @@ void orc_model_update(int model, uint64_t time, const double *y, uint64_t s[4],
   if (model == ORC_MODEL_SIR) sir_update(time, y, s, scrambler, deterministic, pars, y_next);
   else if (model == ORC_MODEL_SIRS) sirs_update(time, y, s, scrambler, deterministic, pars, y_next);
   else if (model == ORC_MODEL_VOLATILITY) volatility_update(y, s, scrambler, deterministic, pars, y_next);
+  else if (model == ORC_MODEL_SEIR) seir_update(time, y, s, scrambler, deterministic, pars, y_next);
   else y_next[0] = y[0] + (deterministic ? 0.0 : orc_normal(s, scrambler, 0.0, pars[0]));   /* walk */
 }
 
@@ -624,8 +656,8 @@ void orc_model_update(int model, uint64_t time, const double *y, uint64_t s[4],
 static double model_compare(int model, const double *y, const double *datum,
                             uint64_t s[4], int scr, int det, const double *p) {
   if (model == ORC_MODEL_VOLATILITY) return orc_density_normal_log(datum[0], p[2] * y[0], p[3]);
-  const double modelled = model == ORC_MODEL_SIR ? y[4] : y[3];
-  const double rate = model == ORC_MODEL_SIR ? p[3] : p[4];
+  const double modelled = model == ORC_MODEL_SIR ? y[4] : model == ORC_MODEL_SEIR ? y[5] : y[3];
+  const double rate = model == ORC_MODEL_SIR ? p[3] : p[4];   /* sirs, seir: slot 4 */
   const double noise = det ? 1.0 / rate : orc_exponential(s, scr, rate);
   return orc_density_poisson_log(datum[0], datum[1], modelled + noise);
 }

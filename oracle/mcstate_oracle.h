@@ -31,7 +31,8 @@ extern "C" {
 #endif
 
 enum { ORC_SCRAMBLER_PLUS = 0, ORC_SCRAMBLER_STARSTAR = 1 };
-enum { ORC_MODEL_SIR = 0, ORC_MODEL_SIRS = 1, ORC_MODEL_VOLATILITY = 2, ORC_MODEL_WALK = 3 };
+enum { ORC_MODEL_SIR = 0, ORC_MODEL_SIRS = 1, ORC_MODEL_VOLATILITY = 2, ORC_MODEL_WALK = 3,
+       ORC_MODEL_SEIR = 4 };   /* SEIR: the twin of the user-supplied example model */
 /* how sum(w) and the cumulative sum are accumulated when resampling */
 enum {
   ORC_RESAMPLE_DUST_FP64 = 0, /* left-to-right fp64, as dust's resample_weight   */

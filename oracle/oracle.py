@@ -21,7 +21,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libmcstate_oracle.so")
 
 PLUS, STARSTAR = 0, 1
-SIR, SIRS, VOLATILITY, WALK = 0, 1, 2, 3
+SIR, SIRS, VOLATILITY, WALK, SEIR = 0, 1, 2, 3, 4
 DUST_FP64, EXACT = 0, 1
 
 _u64p = C.POINTER(C.c_uint64)

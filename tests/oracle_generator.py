@@ -13,12 +13,15 @@ from oracle import oracle as O
 PAR_NAMES = {O.SIR: ["beta", "gamma", "I0", "exp_noise", "S0", "R0", "freq"],
              O.SIRS: ["alpha", "beta", "gamma", "I0", "exp_noise", "S0", "R0", "freq"],
              O.VOLATILITY: ["alpha", "sigma", "gamma", "tau", "x0"],
-             O.WALK: ["sd"]}
+             O.WALK: ["sd"],
+             O.SEIR: ["beta", "sigma", "gamma", "I0", "exp_noise", "S0", "E0", "freq"]}
 STATE_NAMES = {O.SIR: ["S", "I", "R", "cases_cumul", "cases_inc"],
                O.SIRS: ["S", "I", "R", "cases_inc"],
                O.VOLATILITY: ["x"],
-               O.WALK: ["x"]}
-DATA_FIELD = {O.SIR: "incidence", O.SIRS: "incidence", O.VOLATILITY: "observed", O.WALK: None}
+               O.WALK: ["x"],
+               O.SEIR: ["S", "E", "I", "R", "cases_cumul", "cases_inc"]}
+DATA_FIELD = {O.SIR: "incidence", O.SIRS: "incidence", O.VOLATILITY: "observed", O.WALK: None,
+              O.SEIR: "incidence"}
 
 
 def _seed_words(seed):
@@ -211,7 +214,7 @@ class OracleGenerator:
 
     def __init__(self, model_name="sir", algorithm="xoshiro256plus"):
         self.model_id = {"sir": O.SIR, "sirs": O.SIRS, "volatility": O.VOLATILITY,
-                         "walk": O.WALK}[model_name]
+                         "walk": O.WALK, "seir": O.SEIR}[model_name]
         self.scrambler = {"xoshiro256plus": O.PLUS, "xoshiro256starstar": O.STARSTAR}[algorithm]
         self.par_names = PAR_NAMES[self.model_id]
         self.par_defaults = list(O.default_pars(self.model_id))
