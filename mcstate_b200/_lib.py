@@ -173,6 +173,11 @@ def build_user_model(source: str, quiet: bool = True, force: bool = False) -> st
         if not quiet and r.stderr:
             print(r.stderr)
         os.replace(tmp, out)
+        # builds of the same model from older sources can never be loaded again
+        stem = os.path.basename(out).rsplit("_", 1)[0] + "_"
+        for f in os.listdir(USER_MODEL_DIR):
+            if f.startswith(stem) and f.endswith(".so") and f != os.path.basename(out):
+                os.remove(os.path.join(USER_MODEL_DIR, f))
     return out
 
 

@@ -1285,14 +1285,15 @@ int mcb_copy_sets(mcb_model *dst, mcb_model *src, const unsigned char *take, int
     return fail(MCB_ERR_STATE, "per-set RNG copies need per-set filter streams");
   MCB_CUDA(cudaSetDevice(dst->device));
   MCB_CUDA(cudaStreamSynchronize(src->stream));
-  unsigned char *d_take = nullptr;
-  MCB_CUDA(cudaMalloc(&d_take, a.n_sets));
-  cudaMemcpyAsync(d_take, take, a.n_sets, cudaMemcpyHostToDevice, dst->stream);
+  // the flags travel through the handle's staging buffer (no allocation per call: SMC^2
+  // copies sets at every replenishment)
+  MCB_TRY(ensure_stage(dst, a.n_sets));
+  unsigned char *d_take = reinterpret_cast<unsigned char *>(dst->d_stage);
+  MCB_CUDA(cudaMemcpyAsync(d_take, take, a.n_sets, cudaMemcpyHostToDevice, dst->stream));
   mcb::k_copy_sets<<<blocks_for(a.n_total, 256), 256, 0, dst->stream>>>(a, b, d_take, copy_state,
                                                                         copy_rng);
   ++dst->launches;
   cudaError_t err = cudaStreamSynchronize(dst->stream);
-  cudaFree(d_take);
   if (err != cudaSuccess) return fail(MCB_ERR_CUDA, std::string("copy_sets: ") + cudaGetErrorString(err));
   return MCB_OK;
 }

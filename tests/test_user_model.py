@@ -194,8 +194,9 @@ def test_user_model_through_particle_filter_and_pmcmc(seir, sir_data):
         pars = pmcmc_parameters([pmcmc_parameter("beta", 0.4, min=0.05, max=2.0),
                                  pmcmc_parameter("sigma", 0.3, min=0.05, max=2.0)],
                                 np.diag([0.002, 0.002]))
-        np.random.seed(3)
-        out = pmcmc(pars, f, control=pmcmc_control(15, save_state=True, progress=False))
+        # use_parallel_seed: the chain's filter and host RNG are seeded from the filter's seed
+        out = pmcmc(pars, f, control=pmcmc_control(15, save_state=True, progress=False,
+                                                   use_parallel_seed=True))
         res.append((ll, h, out["pars"], out["probabilities"], out["state"]))
     a, b = res
     assert a[0] == b[0]
