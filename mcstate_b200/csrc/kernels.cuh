@@ -328,8 +328,23 @@ __device__ __forceinline__ void run_model_steps(const View &v, const SetData &sd
 #ifndef MCB_K1_MINBLOCKS
 #define MCB_K1_MINBLOCKS 12
 #endif
+// A model without a lean path runs its update as written (doubles, the general samplers)
+// and spills at the 40 registers the lean SIR loop is tuned for (SEIR user model: 700 B of
+// spill stores per thread).  More registers and fewer resident blocks were measured
+// SLOWER all the same (2^20 particles, us per interval; profiles/ab_general_r01_v42.txt):
+//   min blocks      12 (40 regs)   8 (64)   6 (80)   4 (125, no spills)
+//   seir            210.5          210.9    225.5    272.0
+//   volatility      46.6           48.6     55.3
+// -- the spills hit L1 and occupancy hides the samplers' fp64 latency -- so the bound is
+// shared; the switch stays for a model that behaves differently.
+#ifndef MCB_K1_MINBLOCKS_GENERAL
+#define MCB_K1_MINBLOCKS_GENERAL MCB_K1_MINBLOCKS
+#endif
+template <class M>
+constexpr int k1_min_blocks() { return M::kHasLean ? MCB_K1_MINBLOCKS : MCB_K1_MINBLOCKS_GENERAL; }
+
 template <class M, int SCR, bool HIST>
-__global__ void __launch_bounds__(kRunThreads, MCB_K1_MINBLOCKS)
+__global__ void __launch_bounds__(kRunThreads, k1_min_blocks<M>())
 k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_out,
               uint64_t t0, uint32_t n_steps, int prev_row, int row,
               double *__restrict__ hist, int *__restrict__ kappa_out) {

@@ -11,8 +11,13 @@ from mcstate_b200 import dust
 n = 1 << 20
 d = np.loadtxt(os.path.join(ROOT, "tests", "golden", "sir_incidence.csv"), delimiter=",", skiprows=1)
 t, x = d[:, 1].astype(np.uint64) * 4, d[:, 0]
-for name, g in (("seir (user model)", dust.dust(os.path.join(ROOT, "mcstate_b200", "examples", "seir.cuh"))),
-                ("sir (stock)", dust.dust_example("sir"))):
+if len(sys.argv) > 1:   # a tuning build of the SEIR engine (A/B runs): python user_model_bench.py <lib.so>
+    from mcstate_b200 import _lib
+    models = ((os.path.basename(sys.argv[1]), dust.dust_generator("seir", library=_lib.load(sys.argv[1]))),)
+else:
+    models = (("seir (user model)", dust.dust(os.path.join(ROOT, "mcstate_b200", "examples", "seir.cuh"))),
+              ("sir (stock)", dust.dust_example("sir")))
+for name, g in models:
     m = g.new({}, 0, n, seed=1)
     m.set_data(dust.dust_data({"time_end": t, "incidence": x}), False)
     for _ in range(3):
