@@ -638,15 +638,11 @@ def dust(path, quiet=True, algorithm="xoshiro256plus"):
     returned behaves like the ``dust_example`` ones everywhere (particle_filter, pmcmc,
     smc2, sharding).  No GPU is needed to build; none means no way to run."""
     L = _lib.user_lib(path, quiet)
-    # a user build holds exactly one model: id 0
-    name = None
-    for cand in (os.path.splitext(os.path.basename(path))[0],):
-        mid = C.c_int()
-        if L.mcb_model_lookup(cand.encode(), C.byref(mid), None, None, None) == _lib.OK:
-            name = cand
-    if name is None:
+    # a user build holds exactly one model (id 0), named after its source file
+    name = os.path.splitext(os.path.basename(path))[0]
+    if L.mcb_model_lookup(name.encode(), None, None, None, None) != _lib.OK:
         raise ValueError("'%s': MCB_USER_MODEL_DESC must name the model after its file "
-                         "('%s')" % (path, os.path.splitext(os.path.basename(path))[0]))
+                         "('%s')" % (path, name))
     return dust_generator(name, algorithm, library=L)
 
 
