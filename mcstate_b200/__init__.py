@@ -6,8 +6,10 @@ interface for the hot path only: the dust model object (``dust``), the data
 helper (``particle_filter_data``) and the filter facade (``particle_filter``).
 """
 from . import _lib
-from .dust import (dust_data, dust_example, dust_generator, dust_model, dust_rng,
+from .dust import (dust, dust_data, dust_example, dust_generator, dust_model,
+                   dust_openmp_threads, dust_repair_environment, dust_rng,
                    dust_rng_distributed_state)
 
-__all__ = ["_lib", "dust_data", "dust_example", "dust_generator", "dust_model", "dust_rng",
+__all__ = ["_lib", "dust", "dust_data", "dust_example", "dust_generator", "dust_model",
+           "dust_openmp_threads", "dust_repair_environment", "dust_rng",
            "dust_rng_distributed_state"]

@@ -544,10 +544,11 @@ class dust_generator:
 
     name = "dust_generator"
 
-    def __init__(self, model_name, algorithm="xoshiro256plus", library=None):
-        # `library`: a build of the engine that holds a user-supplied model (dust() below);
-        # the stock library holds the four dust_example models
+    def __init__(self, model_name, algorithm="xoshiro256plus", library=None, source=None):
+        # `library`: a build of the engine that holds a user-supplied model (dust() below,
+        # `source` = the model's header); the stock library holds the four dust_example models
         L = self._L = _lib.lib() if library is None else library
+        self._source = source
         check = self._check
         mid, ns, npar, nd = C.c_int(), C.c_size_t(), C.c_size_t(), C.c_size_t()
         check(L.mcb_model_lookup(model_name.encode(), C.byref(mid), C.byref(ns), C.byref(npar),
@@ -565,6 +566,20 @@ class dust_generator:
         self.state_names = [L.mcb_model_state_name(mid.value, i).decode() for i in range(ns.value)]
         self.data_fields = [L.mcb_model_data_name(mid.value, i).decode() for i in range(nd.value)]
         self.public_methods = self  # R: model$public_methods$has_compare()
+
+    # A generator travels between processes (pmcmc_chains_prepare / _run, the samples'
+    # `predict` element) without its library handle; the receiving side binds it again
+    # -- dust::dust_repair_environment (R/pmcmc_chains.R:78).
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["_L"] = None
+        d["public_methods"] = None
+        return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        self.public_methods = self
+        dust_repair_environment(self)
 
     def _check(self, rc):
         if rc != _lib.OK:
@@ -643,7 +658,54 @@ def dust(path, quiet=True, algorithm="xoshiro256plus"):
     if L.mcb_model_lookup(name.encode(), None, None, None, None) != _lib.OK:
         raise ValueError("'%s': MCB_USER_MODEL_DESC must name the model after its file "
                          "('%s')" % (path, name))
-    return dust_generator(name, algorithm, library=L)
+    return dust_generator(name, algorithm, library=L, source=os.path.abspath(path))
+
+
+def dust_repair_environment(generator, quiet=True):
+    """``dust::dust_repair_environment(generator)`` (R/pmcmc_chains.R:78): make a generator
+    that was serialised in another process usable here -- bind the engine library again
+    (for a user-supplied model: its own build, compiled here if this machine has not got
+    it yet).  Harmless on a generator that is already bound, and on test doubles."""
+    if not isinstance(generator, dust_generator) or generator._L is not None:
+        return generator
+    src = generator._source
+    if src is not None and not os.path.exists(src):
+        # a model shipped inside the package, serialised from a checkout somewhere else
+        pkg = os.path.dirname(os.path.abspath(__file__))
+        tail = src.replace(os.sep, "/").rsplit("/mcstate_b200/", 1)
+        if len(tail) == 2 and os.path.exists(os.path.join(pkg, tail[1])):
+            src = generator._source = os.path.join(pkg, tail[1])
+    generator._L = _lib.lib() if src is None else _lib.user_lib(src, quiet)
+    mid = C.c_int()
+    generator._check(generator._L.mcb_model_lookup(generator.model_name.encode(), C.byref(mid),
+                                                   None, None, None))
+    generator.model_id = mid.value
+    return generator
+
+
+def dust_openmp_threads(n=None, action="error"):
+    """``dust::dust_openmp_threads(n, action)`` (R/particle_filter.R:505): a thread count
+    checked against what the host offers.  The engine's parallelism is the GPU's and
+    ignores ``n_threads``; the count still reaches host-side callers (pmcmc_predict)."""
+    limit = os.cpu_count() or 1
+    if n is None:
+        return limit
+    n = int(n)
+    if n < 1:
+        raise ValueError("'n' must be at least 1")
+    if n > limit:
+        if action == "fix":
+            return limit
+        msg = "Requested number of threads '%d' exceeds a limit of '%d'" % (n, limit)
+        if action == "error":
+            raise ValueError(msg)
+        if action in ("message", "warning"):
+            import warnings
+
+            warnings.warn(msg)
+            return limit
+        raise ValueError("'action' must be one of 'error', 'fix', 'message', 'warning'")
+    return n
 
 
 def dust_example(name, algorithm="xoshiro256plus"):

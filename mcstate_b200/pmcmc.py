@@ -21,6 +21,7 @@ calls ``set.seed`` (R/pmcmc.R:75-81).
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 
@@ -385,16 +386,23 @@ def _check_initial(initial, pars, n_chains):
     return initial
 
 
-def _run_one(k, pars, initial, filter, control, seeds, device):
-    """Chain k (0-based) on ``device``: a fresh filter on the chain's own streams and a
-    host RNG seeded as ``set.seed(seed$r)`` (R/pmcmc.R:75-81, R/pmcmc_chains.R:71-97)."""
-    if seeds is None:
-        return pmcmc_run_chain(pars, initial[k], filter, control, np.random.default_rng())
-    inputs = dict(filter.inputs())
+def _chain_from_inputs(inputs, seed, pars, initial_k, control, device=None, n_threads=None):
+    """One chain from a filter's inputs: a fresh filter on the chain's own streams and a
+    host RNG seeded as ``set.seed(seed$r)`` (R/pmcmc.R:75-81, R/pmcmc_chains.R:86-93)."""
+    inputs = dict(inputs)
     if device is not None and inputs.get("gpu_config") is not None:
         inputs["gpu_config"] = device
-    f = particle_filter_from_inputs(inputs, seeds[k]["dust"])
-    return pmcmc_run_chain(pars, initial[k], f, control, np.random.default_rng(seeds[k]["r"]))
+    f = particle_filter_from_inputs(inputs, seed["dust"])
+    if n_threads is not None:
+        f.set_n_threads(n_threads)
+    return pmcmc_run_chain(pars, initial_k, f, control, np.random.default_rng(seed["r"]))
+
+
+def _run_one(k, pars, initial, filter, control, seeds, device):
+    """Chain k (0-based) on ``device``."""
+    if seeds is None:
+        return pmcmc_run_chain(pars, initial[k], filter, control, np.random.default_rng())
+    return _chain_from_inputs(filter.inputs(), seeds[k], pars, initial[k], control, device)
 
 
 def pmcmc(pars, filter, initial=None, control=None):
@@ -458,3 +466,126 @@ def pmcmc_sharded(pars, filter, initial=None, control=None, group=None, device=N
             seed = smp["predict"].pop("seed")
             smp["predict"].update(transform=pars.model, filter=dict(filter.inputs(), seed=seed))
     return samples[0] if control.n_chains == 1 else pmcmc_combine(samples)
+
+
+# ---------------------------------------------------------------------------
+# chains run by hand, one process (and GPU) each, through files (R/pmcmc_chains.R)
+# ---------------------------------------------------------------------------
+def _serializer():
+    """R's saveRDS keeps closures (priors, index and compare functions); the counterpart
+    here is cloudpickle, with plain pickle (module-level functions only) as the fallback."""
+    try:
+        import cloudpickle
+
+        return cloudpickle
+    except ImportError:  # pragma: no cover
+        import pickle
+
+        return pickle
+
+
+def _save(obj, path):
+    tmp = path + ".tmp%d" % os.getpid()
+    with open(tmp, "wb") as fh:
+        _serializer().dump(obj, fh)
+    os.replace(tmp, path)
+
+
+def _load(path):
+    import pickle
+
+    with open(path, "rb") as fh:
+        return pickle.load(fh)
+
+
+def pmcmc_chains_path(path, chain_id=None):
+    """R/pmcmc_chains.R:130-136 (``.pkl`` where the reference writes ``.rds``)."""
+    if not isinstance(path, (str, os.PathLike)):
+        raise TypeError("'path' must be a scalar character")
+    path = os.fspath(path)
+    ids = [] if chain_id is None else np.atleast_1d(chain_id).tolist()
+    results = [os.path.join(path, "results_%d.pkl" % k) for k in ids]
+    return {"root": path, "inputs": os.path.join(path, "inputs.pkl"),
+            "control": os.path.join(path, "control.pkl"),
+            "results": results[0] if np.isscalar(chain_id) and chain_id is not None else results}
+
+
+def pmcmc_chains_prepare(path, pars, filter, control, initial=None):
+    """``pmcmc_chains_prepare`` (R/pmcmc_chains.R:34-61): write everything a chain needs
+    -- parameters, starting points, the filter's inputs, the control and each chain's
+    seeds -- under ``path``; any process that can read it (another GPU of the box, another
+    box) then runs chain k with ``pmcmc_chains_run(k, path)``.  Returns ``path``."""
+    p = pmcmc_chains_path(path)
+    if not isinstance(pars, pmcmc_parameters):
+        raise TypeError("'pars' must be a pmcmc_parameters")
+    if not hasattr(filter, "inputs"):
+        raise TypeError("'filter' must be a particle_filter")
+    if not isinstance(control, pmcmc_control):
+        raise TypeError("'control' must be a pmcmc_control")
+    if control.n_workers != 1:
+        raise ValueError("'n_workers' must be 1")
+    if not control.use_parallel_seed:
+        raise ValueError("'use_parallel_seed' must be TRUE")
+    initial = _check_initial(initial, pars, control.n_chains)
+    inputs = filter.inputs()
+    seed = make_seeds(control.n_chains, inputs["seed"],
+                      getattr(filter.model, "algorithm", "xoshiro256plus"))
+    os.makedirs(p["root"], exist_ok=True)
+    _save({"class": "pmcmc_inputs", "pars": pars, "initial": initial, "filter": inputs,
+           "control": control, "seed": seed}, p["inputs"])
+    _save(control, p["control"])
+    return p["root"]
+
+
+def pmcmc_chains_run(chain_id, path, n_threads=None, device=None):
+    """``pmcmc_chains_run`` (R/pmcmc_chains.R:71-98): run chain ``chain_id`` (1-based, as
+    in R) from the prepared inputs and write its samples; returns the results file.
+    ``device``: the GPU to run on when the filter was built with a ``gpu_config`` (the
+    prepared inputs name the device of the process that prepared them)."""
+    if isinstance(chain_id, bool) or int(chain_id) != chain_id or chain_id < 1:
+        raise ValueError("'chain_id' must be at least 1")
+    chain_id = int(chain_id)
+    p = pmcmc_chains_path(path, chain_id)
+    inputs = _load(p["inputs"])
+    if not (isinstance(inputs, dict) and inputs.get("class") == "pmcmc_inputs"):
+        raise TypeError("'inputs' must be a pmcmc_inputs")
+    from .dust import dust_repair_environment
+
+    dust_repair_environment(inputs["filter"]["model"])
+    control = inputs["control"]
+    if chain_id > control.n_chains:
+        raise ValueError("'chain_id' must be an integer in 1..%d" % control.n_chains)
+    k = chain_id - 1
+    samples = _chain_from_inputs(inputs["filter"], inputs["seed"][k], inputs["pars"],
+                                 inputs["initial"][k], control, device, n_threads)
+    _save(samples, p["results"])
+    return p["results"]
+
+
+def pmcmc_chains_collect(path):
+    """``pmcmc_chains_collect`` (R/pmcmc_chains.R:101-117): the combined samples, equal to
+    ``pmcmc()`` run with the same control in one process."""
+    control = _load(pmcmc_chains_path(path)["control"])
+    p = pmcmc_chains_path(path, list(range(1, control.n_chains + 1)))
+    missing = [k + 1 for k, f in enumerate(p["results"]) if not os.path.exists(f)]
+    if missing:
+        raise RuntimeError("Results missing for chains %s" % ", ".join(map(str, missing)))
+    samples = [_load(f) for f in p["results"]]
+    for smp in samples:   # the generator inside `predict` was serialised with the samples
+        if smp.get("predict") is not None:
+            from .dust import dust_repair_environment
+
+            dust_repair_environment(smp["predict"]["filter"]["model"])
+    return samples[0] if control.n_chains == 1 else pmcmc_combine(samples)
+
+
+def pmcmc_chains_cleanup(path):
+    """``pmcmc_chains_cleanup`` (R/pmcmc_chains.R:120-127): remove the files written, and
+    the directory if nothing else is in it."""
+    control = _load(pmcmc_chains_path(path)["control"])
+    p = pmcmc_chains_path(path, list(range(1, control.n_chains + 1)))
+    for f in [p["inputs"], p["control"]] + p["results"]:
+        if os.path.exists(f):
+            os.remove(f)
+    if os.path.isdir(p["root"]) and not os.listdir(p["root"]):
+        os.rmdir(p["root"])

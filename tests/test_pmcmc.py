@@ -303,3 +303,109 @@ def test_predict_engine_equals_oracle(sir_data):
     assert np.array_equal(res["oracle"][0]["pars"], res["gpu"][0]["pars"])
     assert np.array_equal(res["oracle"][0]["state"], res["gpu"][0]["state"])
     assert np.array_equal(res["oracle"][1]["state"], res["gpu"][1]["state"])
+
+
+# ---------------------------------------------------------------- chains run by hand
+from mcstate_b200.pmcmc import (pmcmc_chains_cleanup, pmcmc_chains_collect,  # noqa: E402
+                                pmcmc_chains_prepare, pmcmc_chains_run)
+
+
+def _same_samples(a, b):
+    assert a["pars_names"] == b["pars_names"]
+    for key in ("pars", "probabilities", "iteration", "chain", "state", "trajectories"):
+        if a.get(key) is None:
+            assert b.get(key) is None, key
+        else:
+            assert np.array_equal(a[key], b[key]), key
+    assert a["n_filter_runs"] == b["n_filter_runs"]
+
+
+@pytest.mark.parametrize("kind", BACKENDS)
+def test_split_chains_manually(kind, sir_data, tmp_path):
+    """tests/testthat/test-pmcmc-chains.R:1-28: prepare / run each chain / collect equals
+    pmcmc() with the same control; cleanup removes what was written."""
+    control = pmcmc_control(10, n_chains=4, use_parallel_seed=True, save_trajectories=True)
+    res1 = pmcmc(example_pars(), example_filter(kind, sir_data, 30), control=control)
+    path = str(tmp_path / "chains")
+    assert pmcmc_chains_prepare(path, example_pars(), example_filter(kind, sir_data, 30),
+                                control) == path
+    device = _device() if kind == "gpu" else None
+    results = [pmcmc_chains_run(k, path, device=device) for k in (3, 1, 4, 2)]  # any order
+    assert sorted(os.listdir(path)) == sorted(
+        ["control.pkl", "inputs.pkl"] + ["results_%d.pkl" % k for k in range(1, 5)])
+    assert results[1] == os.path.join(path, "results_1.pkl")
+    res2 = pmcmc_chains_collect(path)
+    _same_samples(res1, res2)
+    assert res2["predict"]["filter"]["model"].name == "dust_generator"
+    pmcmc_chains_cleanup(path)
+    assert not os.path.exists(path)
+
+
+def test_split_chains_in_other_processes(sir_data, tmp_path):
+    """What the files are for: each chain in its own interpreter, nothing shared but the
+    directory (the reference: one callr / cluster job per chain)."""
+    import subprocess
+    import sys
+
+    control = pmcmc_control(6, n_chains=2, use_parallel_seed=True)
+    res1 = pmcmc(example_pars(), example_filter("oracle", sir_data, 20), control=control)
+    path = str(tmp_path / "chains")
+    pmcmc_chains_prepare(path, example_pars(), example_filter("oracle", sir_data, 20), control)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for k in (1, 2):
+        code = ("import sys; sys.path[:0] = [%r, %r]; "
+                "from mcstate_b200.pmcmc import pmcmc_chains_run; "
+                "print(pmcmc_chains_run(%d, %r))" % (root, os.path.join(root, "tests"), k, path))
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
+                             timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        assert out.stdout.strip().endswith("results_%d.pkl" % k)
+    _same_samples(res1, pmcmc_chains_collect(path))
+
+
+def test_split_chains_errors(sir_data, tmp_path):
+    """tests/testthat/test-pmcmc-chains.R:62-124."""
+    f = example_filter("oracle", sir_data, 5)
+    with pytest.raises(ValueError, match="'n_workers' must be 1"):
+        pmcmc_chains_prepare(str(tmp_path / "a"), example_pars(), f,
+                             pmcmc_control(10, n_chains=4, n_workers=2, use_parallel_seed=True))
+    with pytest.raises(ValueError, match="'use_parallel_seed' must be TRUE"):
+        pmcmc_chains_prepare(str(tmp_path / "b"), example_pars(), f,
+                             pmcmc_control(10, n_chains=4, use_parallel_seed=False))
+    control = pmcmc_control(3, n_chains=4, use_parallel_seed=True)
+    path = pmcmc_chains_prepare(str(tmp_path / "c"), example_pars(), f, control)
+    with pytest.raises(RuntimeError, match="Results missing for chains 1, 2, 3, 4"):
+        pmcmc_chains_collect(path)
+    pmcmc_chains_run(2, path)
+    pmcmc_chains_run(3, path)
+    with pytest.raises(RuntimeError, match="Results missing for chains 1, 4"):
+        pmcmc_chains_collect(path)
+    with pytest.raises(ValueError, match="'chain_id' must be at least 1"):
+        pmcmc_chains_run(0, path)
+    with pytest.raises(ValueError, match=r"'chain_id' must be an integer in 1\.\.4"):
+        pmcmc_chains_run(5, path)
+
+
+def test_generator_survives_serialisation():
+    """dust::dust_repair_environment (R/pmcmc_chains.R:78): a generator read back in has
+    no library handle until it is repaired; stock and user-supplied models."""
+    import pickle
+
+    import cloudpickle
+
+    from mcstate_b200 import dust
+
+    for g in (dust.dust_example("sirs", "xoshiro256starstar"),
+              dust.dust(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                     "mcstate_b200", "examples", "seir.cuh"))):
+        h = pickle.loads(cloudpickle.dumps(g))
+        assert h._L is g._L and h.public_methods is h
+        assert (h.model_name, h.model_id, h.scrambler, h.par_names, h.state_names) == \
+            (g.model_name, g.model_id, g.scrambler, g.par_names, g.state_names)
+        h._L = None
+        assert dust.dust_repair_environment(h)._L is g._L
+    assert dust.dust_repair_environment("not a generator") == "not a generator"
+    assert dust.dust_openmp_threads(1) == 1
+    assert dust.dust_openmp_threads(10 ** 6, "fix") == dust.dust_openmp_threads()
+    with pytest.raises(ValueError, match="exceeds a limit"):
+        dust.dust_openmp_threads(10 ** 6)
