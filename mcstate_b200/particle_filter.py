@@ -825,6 +825,24 @@ class particle_filter:
         return prev
 
 
+def particle_filter_initial(state, rng=None):
+    """``particle_filter_initial(state)`` (R/particle_filter_initial.R:18-25): an
+    ``initial`` function for a filter restarted from saved state -- ``state`` is a matrix
+    ``[n_state, n_samples]`` (``pmcmc(...)["restart"][:, :, k]``); each call samples
+    ``n_particles`` of its columns with replacement (``sample.int``; here a
+    ``numpy.random.Generator``, a fresh one unless given)."""
+    state = np.asarray(state)
+    if state.ndim != 2:
+        raise TypeError("'state' must be a matrix")
+    state = state.copy()
+    gen = np.random.default_rng() if rng is None else rng
+
+    def initial(info, n_particles, pars):
+        return state[:, gen.integers(0, state.shape[1], int(n_particles))]
+
+    return initial
+
+
 def particle_filter_from_inputs(inputs, seed=None):
     """R/particle_filter.R:528-567."""
     return particle_filter(

@@ -322,6 +322,50 @@ def pmcmc_combine(samples):
     return out
 
 
+def pmcmc_filter(object, i):
+    """R/pmcmc_tools.R:64-90: keep the samples ``i`` (a boolean mask or 0-based indices)."""
+    i = np.asarray(i)
+    out = dict(object)
+    if out.get("chain") is not None:
+        out["chain"] = np.asarray(out["chain"])[i]
+    out["iteration"] = np.asarray(out["iteration"])[i]
+    out["pars"] = np.asarray(out["pars"])[i]
+    out["probabilities"] = np.asarray(out["probabilities"])[i]
+    for key in ("state", "trajectories", "restart"):     # samples along the second axis
+        if out.get(key) is not None:
+            out[key] = np.asarray(out[key])[:, i]
+    return out
+
+
+def pmcmc_thin(object, burnin=None, thin=None):
+    """``pmcmc_thin(object, burnin, thin)`` (R/pmcmc_tools.R:23-45): drop every sample
+    whose iteration is at most ``burnin``, then keep every ``thin``-th of the rest (per
+    chain: the iteration numbers decide, not the positions)."""
+    it = np.asarray(object["iteration"])
+    keep = np.ones(it.size, dtype=bool)
+    if burnin is not None:
+        if int(burnin) != burnin or burnin < 0:
+            raise ValueError("'burnin' must be a positive integer")
+        burnin_max = int(it.max())
+        if burnin >= burnin_max:
+            raise ValueError("'burnin' must be less than %d for your results" % burnin_max)
+        keep &= it > burnin
+    if thin is not None:
+        if int(thin) != thin or thin < 1:
+            raise ValueError("'thin' must be a positive integer")
+        offset = it[keep].min()
+        keep &= (it - offset) % int(thin) == 0
+    return pmcmc_filter(object, keep)
+
+
+def pmcmc_sample(object, n_sample, burnin=None, rng=None):
+    """``pmcmc_sample(object, n_sample, burnin)`` (R/pmcmc_tools.R:53-61): ``n_sample``
+    samples drawn with replacement from what is left after ``burnin``."""
+    object = pmcmc_thin(object, burnin)
+    gen = np.random.default_rng() if rng is None else rng
+    return pmcmc_filter(object, gen.integers(0, np.asarray(object["pars"]).shape[0], int(n_sample)))
+
+
 def pmcmc_predict(object, times, prepend_trajectories=False, n_threads=None, seed=None):
     """``pmcmc_predict`` (R/predict.R:36-89): run the model forward from every retained
     sample's final state with that sample's parameters -- one multi-parameter model

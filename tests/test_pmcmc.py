@@ -409,3 +409,99 @@ def test_generator_survives_serialisation():
     assert dust.dust_openmp_threads(10 ** 6, "fix") == dust.dust_openmp_threads()
     with pytest.raises(ValueError, match="exceeds a limit"):
         dust.dust_openmp_threads(10 ** 6)
+
+
+# ---------------------------------------------------------------- thin / sample / restart
+from mcstate_b200.particle_filter import particle_filter_initial  # noqa: E402
+from mcstate_b200.pmcmc import pmcmc_sample, pmcmc_thin  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def sir_pmcmc(sir_data):
+    """tests/testthat/helper-mcstate.R example_sir_pmcmc: 30 steps, state, trajectories and
+    restart state saved."""
+    control = pmcmc_control(30, save_state=True, save_trajectories=True, save_restart=[40],
+                            use_parallel_seed=True)
+    return pmcmc(example_pars(), example_filter("oracle", sir_data, 20), control=control)
+
+
+def test_pmcmc_thin(sir_pmcmc):
+    """tests/testthat/test-pmcmc-tools.R:3-68."""
+    res = sir_pmcmc
+    same = pmcmc_thin(res)
+    for k in ("pars", "probabilities", "state", "trajectories", "restart", "iteration"):
+        assert np.array_equal(same[k], res[k])
+    for args, i in (((9, None), np.arange(9, 30)), ((None, 4), np.arange(0, 30, 4)),
+                    ((9, 4), np.arange(9, 30, 4))):
+        out = pmcmc_thin(res, *args)
+        assert np.array_equal(out["pars"], res["pars"][i])
+        assert np.array_equal(out["probabilities"], res["probabilities"][i])
+        assert np.array_equal(out["state"], res["state"][:, i])
+        assert np.array_equal(out["trajectories"], res["trajectories"][:, i])
+        assert np.array_equal(out["restart"], res["restart"][:, i])
+        assert np.array_equal(out["iteration"], i + 1)
+    for b in (30, 100):
+        with pytest.raises(ValueError, match="'burnin' must be less than 30 for your results"):
+            pmcmc_thin(res, b)
+    bare = dict(res, state=None, trajectories=None)
+    out = pmcmc_thin(bare, 9, 4)
+    assert out["state"] is None and out["trajectories"] is None
+    assert np.array_equal(out["pars"], res["pars"][np.arange(9, 30, 4)])
+
+
+def test_pmcmc_thin_and_sample_combined_chains(sir_data):
+    """tests/testthat/test-pmcmc-tools.R:135-160, 276-299."""
+    control = pmcmc_control(30, n_chains=3, save_state=True, use_parallel_seed=True)
+    res = pmcmc(example_pars(), example_filter("oracle", sir_data, 10), control=control)
+    out = pmcmc_thin(res, 10)
+    assert np.array_equal(out["chain"], np.repeat([1, 2, 3], 20))
+    assert np.array_equal(out["iteration"], np.tile(np.arange(11, 31), 3))
+    out = pmcmc_thin(res, thin=4)
+    assert np.array_equal(out["iteration"], np.tile(np.arange(1, 31, 4), 3))
+    assert np.array_equal(out["state"], res["state"][:, np.isin(res["iteration"], np.arange(1, 31, 4))])
+    sub = pmcmc_sample(res, 50, burnin=9, rng=np.random.default_rng(1))
+    assert sub["pars"].shape == (50, 2) and sub["state"].shape == (5, 50)
+    assert np.all(sub["iteration"] >= 10) and set(sub["chain"]) == {1, 2, 3}
+    one = pmcmc_sample(pmcmc_thin(res, 25), 50, rng=np.random.default_rng(2))
+    assert len(set(zip(one["chain"], one["iteration"]))) < 50        # with replacement
+
+
+def test_particle_filter_initial():
+    """tests/testthat/test-pmcmc.R:598-606."""
+    m = np.arange(70).reshape(7, 10).T          # R: matrix(1:70 - 1, 10)
+    f = particle_filter_initial(m, np.random.default_rng(1))
+    res = f(None, 3, None)
+    assert res.shape == (10, 3)
+    assert np.array_equal(res % 10, np.tile(np.arange(10)[:, None], (1, 3)))
+    assert np.all(np.diff(res // 10, axis=0) == 0)
+    m[:] = -1                                    # the closure holds its own copy
+    assert f(None, 2, None).min() >= 0
+    with pytest.raises(TypeError, match="'state' must be a matrix"):
+        particle_filter_initial(np.zeros(3))
+
+
+@pytest.mark.parametrize("kind", BACKENDS)
+def test_restart_pmcmc_from_saved_state(kind, sir_data):
+    """tests/testthat/test-pmcmc.R:478-508: a second pmcmc on the later part of the data,
+    started from the restart state the first one saved."""
+    control1 = pmcmc_control(20, save_state=True, save_trajectories=True, save_restart=[40],
+                             use_parallel_seed=True)
+    res1 = pmcmc(example_pars(), example_filter(kind, sir_data, 50), control=control1)
+    assert res1["restart"].shape == (5, 20, 1)
+    s = res1["restart"][:, :, 0]
+    late = sir_data["day"] > 40
+    data2 = particle_filter_data({"day": sir_data["day"][late],
+                                  "incidence": sir_data["incidence"][late]}, "day", 4, 40)
+    gpu = _device() if kind == "gpu" else None
+    p2 = particle_filter(data2, _generator(kind), 50, None,
+                         index=lambda info: {"run": [5], "state": [1, 2, 3]}, seed=1,
+                         initial=particle_filter_initial(s, np.random.default_rng(4)),
+                         gpu_config=gpu)
+    control2 = pmcmc_control(20, save_state=True, save_trajectories=True, use_parallel_seed=True)
+    res2 = pmcmc(example_pars(), p2, control=control2)
+    assert res2["trajectories"].shape == (3, 20, 61)
+    assert np.array_equal(res2["trajectories_time"], np.arange(40, 101) * 4)
+    # every starting particle is one of the saved columns
+    start = res2["trajectories"][:, :, 0]
+    assert all(any(np.array_equal(start[:, j], s[:3, k]) for k in range(s.shape[1]))
+               for j in range(start.shape[1]))
