@@ -470,6 +470,19 @@ def pmcmc(pars, filter, initial=None, control=None):
     return samples[0] if control.n_chains == 1 else pmcmc_combine(samples)
 
 
+def pmcmc_parallel_threads(n_threads_total, n_workers, n_chains):
+    """R/pmcmc_parallel.R:199-209: threads per chain when ``n_workers`` run at a time --
+    an even split while every worker is busy, the spare threads shared by the last
+    ``n_chains % n_workers`` chains.  (The engine's parallelism is the GPU's; the counts
+    still size host-side work such as ``pmcmc_predict``.)"""
+    out = [n_threads_total / n_workers] * (n_chains // n_workers * n_workers)
+    spare = n_chains % n_workers
+    if spare:
+        each = n_threads_total // spare
+        out += [each] * (spare - 1) + [each + n_threads_total % spare]
+    return [int(x) if float(x).is_integer() else x for x in out]
+
+
 def chain_owner(chain, world):
     """Which rank runs chain ``chain`` (0-based): round robin, like the reference hands
     the next chain to the next free worker (R/pmcmc_parallel.R:71-102)."""

@@ -505,3 +505,16 @@ def test_restart_pmcmc_from_saved_state(kind, sir_data):
     start = res2["trajectories"][:, :, 0]
     assert all(any(np.array_equal(start[:, j], s[:3, k]) for k in range(s.shape[1]))
                for j in range(start.shape[1]))
+
+
+def test_thread_allocation():
+    """tests/testthat/test-pmcmc-parallel.R:180-190 (known answers)."""
+    from mcstate_b200.pmcmc import pmcmc_parallel_threads as f
+
+    assert f(1, 1, 1) == [1]
+    assert f(20, 2, 2) == [10, 10]
+    assert f(20, 2, 4) == [10] * 4
+    assert f(20, 2, 5) == [10] * 4 + [20]
+    assert f(6, 3, 7) == [2] * 6 + [6]
+    assert f(6, 3, 8) == [2] * 6 + [3, 3]
+    assert f(21, 3, 8) == [7] * 6 + [10, 11]

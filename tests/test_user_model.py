@@ -203,3 +203,43 @@ def test_user_model_through_particle_filter_and_pmcmc(seir, sir_data):
     assert np.array_equal(a[1], b[1])
     for k in (2, 3, 4):
         assert np.array_equal(a[k], b[k]), k
+
+
+@pytest.mark.gpu
+def test_user_model_chains_in_other_processes(seir, sir_data, tmp_path):
+    """tests/testthat/test-pmcmc-parallel.R:193-210 ("Can use workers on non-package
+    models": the worker must be able to load the compiled model): chains of a
+    user-supplied model prepared here and run in fresh interpreters, which bind the
+    model's own library again from the serialised generator."""
+    import subprocess
+    import sys
+
+    from mcstate_b200.particle_filter import particle_filter
+    from mcstate_b200.particle_filter_data import particle_filter_data
+    from mcstate_b200.pmcmc import (pmcmc, pmcmc_chains_collect, pmcmc_chains_prepare,
+                                    pmcmc_control, pmcmc_parameter, pmcmc_parameters)
+
+    data = particle_filter_data({"day": sir_data["day"], "incidence": sir_data["incidence"]},
+                                "day", 4, 0)
+
+    def make():
+        return particle_filter(data, seir, 500, None, seed=4, gpu_config=0,
+                               index=lambda info: {"run": [info["index"]["cases_inc"]],
+                                                   "state": [1, 2, 3, 4]})
+
+    pars = pmcmc_parameters([pmcmc_parameter("beta", 0.4, min=0.05, max=2.0),
+                             pmcmc_parameter("sigma", 0.3, min=0.05, max=2.0)],
+                            np.diag([0.002, 0.002]))
+    control = pmcmc_control(8, n_chains=2, save_state=True, use_parallel_seed=True)
+    want = pmcmc(pars, make(), control=control)
+    path = pmcmc_chains_prepare(str(tmp_path / "chains"), pars, make(), control)
+    for k in (1, 2):
+        code = ("import sys; sys.path.insert(0, %r); "
+                "from mcstate_b200.pmcmc import pmcmc_chains_run; "
+                "print(pmcmc_chains_run(%d, %r))" % (ROOT, k, path))
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
+                             timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+    got = pmcmc_chains_collect(path)
+    for key in ("pars", "probabilities", "state", "chain", "iteration"):
+        assert np.array_equal(got[key], want[key]), key
