@@ -97,6 +97,7 @@ class pmcmc_parameters:
         if proposal.shape != (len(names), len(names)):
             raise ValueError("Expected a square proposal matrix with %d rows" % len(names))
         self._names = names
+        self._vcv = proposal.copy()
         self._proposal = rmvnorm_generator(proposal)
         self._min = np.array([p.min for p in self._p])
         self._max = np.array([p.max for p in self._p])
@@ -120,6 +121,39 @@ class pmcmc_parameters:
     def model(self, theta):
         """theta -> what the filter's ``run`` takes (a dict of named values, transformed)."""
         return self._transform(dict(zip(self._names, (float(t) for t in theta))))
+
+    def mean(self):
+        return np.array([getattr(p, "mean", p.initial) for p in self._p])
+
+    def vcv(self):
+        return self._vcv.copy()
+
+    def summary(self):
+        """R/pmcmc_parameters.R:297-303: one record per parameter."""
+        return [{"name": p.name, "min": p.min, "max": p.max, "discrete": p.integer,
+                 "integer": p.integer} for p in self._p]
+
+    def fix(self, fixed):
+        """``pars$fix(c(name = value, ...))`` (R/pmcmc_parameters.R:355-377): a parameter set
+        over the remaining parameters; the fixed values re-enter in ``model()``, ahead of
+        the original transform."""
+        if not isinstance(fixed, dict):
+            raise ValueError("'fixed' must be named")
+        unknown = [n for n in fixed if n not in self._names]
+        if unknown:
+            raise ValueError("Fixed parameters not found in model: %s"
+                             % ", ".join("'%s'" % n for n in unknown))
+        if len(fixed) == len(self._names):
+            raise ValueError("Cannot fix all parameters")
+        vary = [i for i, n in enumerate(self._names) if n not in fixed]
+        names, base_transform = list(self._names), self._transform
+        values = {n: float(v) for n, v in fixed.items()}
+
+        def transform(d):
+            return base_transform({n: values[n] if n in values else d[n] for n in names})
+
+        return pmcmc_parameters([self._p[i] for i in vary], self._vcv[np.ix_(vary, vary)],
+                                transform)
 
 
 # ---------------------------------------------------------------------------

@@ -518,3 +518,47 @@ def test_thread_allocation():
     assert f(6, 3, 7) == [2] * 6 + [6]
     assert f(6, 3, 8) == [2] * 6 + [3, 3]
     assert f(21, 3, 8) == [7] * 6 + [10, 11]
+
+
+def test_fix_parameters():
+    """tests/testthat/test-pmcmc-parameters.R:256-308."""
+    rs = np.random.RandomState(1)
+    names = list("abcde")
+    vcv = np.cov(rs.uniform(size=(5, 5)), rowvar=False)
+    initial, rate = rs.uniform(size=5), rs.uniform(size=5)
+    plist = [pmcmc_parameter(n, i, prior=(lambda r: lambda p: math.log(r))(r))
+             for n, i, r in zip(names, initial, rate)]
+    p = pmcmc_parameters(plist, vcv)
+    assert np.array_equal(p.vcv(), vcv) and np.array_equal(p.mean(), initial)
+    assert [r["name"] for r in p.summary()] == names
+    p2 = p.fix({"b": 0.5, "d": 0.2})
+    assert p2.names() == ["a", "c", "e"]
+    assert np.array_equal(p2.initial(), initial[[0, 2, 4]])
+    assert np.allclose(p2.propose(p2.initial(), np.random.default_rng(1), 0.0), p2.initial())
+    gen = np.random.default_rng(2)
+    draws = np.array([p2.propose(initial[[0, 2, 4]], gen) for _ in range(20000)])
+    assert np.allclose(np.cov(draws, rowvar=False), vcv[np.ix_([0, 2, 4], [0, 2, 4])], atol=1e-2)
+    want = dict(zip(names, initial))
+    want.update(b=0.5, d=0.2)
+    assert p2.model(p2.initial()) == want
+    assert math.isclose(p2.prior(p2.initial()), sum(math.log(rate[i]) for i in (0, 2, 4)))
+    # a transform given to the original still runs, after the fixed values are put back
+    p3 = pmcmc_parameters(plist, vcv, transform=lambda d: dict(d, total=sum(d.values())))
+    got = p3.fix({"a": 1.0}).model(initial[1:])
+    assert math.isclose(got["total"], 1.0 + initial[1:].sum()) and got["a"] == 1.0
+    with pytest.raises(ValueError, match="'fixed' must be named"):
+        p.fix([1, 2])
+    with pytest.raises(ValueError, match="Fixed parameters not found in model: 'f'"):
+        p.fix({"a": 1, "b": 2, "f": 1})
+    with pytest.raises(ValueError, match="Cannot fix all parameters"):
+        p.fix(dict.fromkeys(names, 1.0))
+
+
+def test_pmcmc_with_fixed_parameter(sir_data):
+    """tests/testthat/test-pmcmc.R:573-596: gamma fixed, beta sampled."""
+    pars2 = example_pars().fix({"gamma": 0.1})
+    control = pmcmc_control(10, save_state=True, save_trajectories=True, use_parallel_seed=True)
+    res = pmcmc(pars2, example_filter("oracle", sir_data, 40), control=control)
+    assert res["pars"].shape == (10, 1) and res["pars_names"] == ["beta"]
+    assert res["state"].shape == (5, 10) and res["trajectories"].shape == (3, 10, 101)
+    assert res["predict"]["transform"](res["pars"][-1])["gamma"] == 0.1
