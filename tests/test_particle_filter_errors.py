@@ -1,0 +1,112 @@
+"""Extraction and error behaviour of the filter facade, ported from the blocks of
+tests/testthat/test-particle-filter.R that tests/test_particle_filter.py does not cover
+(file:line per test; messages are the reference's).  Oracle-backed generator on the CPU,
+the B200 engine under ``-m gpu``."""
+import numpy as np
+import pytest
+
+from mcstate_b200.particle_filter import particle_filter
+from test_particle_filter import BACKENDS, OracleGenerator, _gpu_generator, example_sir
+
+
+@pytest.fixture(params=BACKENDS)
+def gen(request):
+    return OracleGenerator("sir") if request.param == "oracle" else _gpu_generator("sir")
+
+
+def test_nothing_to_extract_before_a_run(gen, sir_data):
+    """tests/testthat/test-particle-filter.R:296-310."""
+    dat = example_sir(sir_data)
+    p = particle_filter(dat["data"], gen, 42, dat["compare"], index=dat["index"])
+    for call in (p.state, p.history, p.restart_state):
+        with pytest.raises(RuntimeError, match="Model has not yet been run"):
+            call()
+
+
+@pytest.mark.parametrize("compiled", [False, True])
+def test_filter_state_on_extraction(gen, sir_data, compiled):
+    """tests/testthat/test-particle-filter.R:313-325."""
+    dat = example_sir(sir_data)
+    p = particle_filter(dat["data"], gen, 42, None if compiled else dat["compare"],
+                        index=dat["index"], seed=1)
+    assert isinstance(p.run(), float)
+    state = p.state()
+    assert state.shape == (5, 42)
+    assert np.array_equal(p.state([1]), state[:1])
+    assert np.array_equal(p.state([2, 3]), state[1:3])
+
+
+@pytest.mark.parametrize("compiled", [False, True])
+def test_extract_one_restart_state(gen, sir_data, compiled):
+    """tests/testthat/test-particle-filter.R:452-477: the restart state at day 40 is the
+    final state of a filter run on the first 40 days; one particle of it can be asked for."""
+    n, end = 42, 40
+    dat = example_sir(sir_data)
+    np.random.seed(1)
+    p = particle_filter(dat["data"], gen, n, None if compiled else dat["compare"],
+                        index=dat["index"], seed=100)
+    p.run(save_restart=[end])
+    s, s1 = p.restart_state(), p.restart_state(1)
+    assert s.shape == (5, n, 1) and s1.shape == (5, 1, 1)
+    dat40 = example_sir(sir_data, n_days=end)
+    np.random.seed(1)
+    q = particle_filter(dat40["data"], gen, n, None if compiled else dat40["compare"],
+                        index=dat40["index"], seed=100)
+    q.run()
+    cmp = q.state()
+    assert np.array_equal(s[:, :, 0], cmp)
+    assert np.array_equal(s1[:, 0, 0], cmp[:, 0])
+
+
+def test_restart_state_needs_saving(gen, sir_data):
+    """tests/testthat/test-particle-filter.R:480-491."""
+    dat = example_sir(sir_data)
+    p = particle_filter(dat["data"], gen, 42, dat["compare"], index=dat["index"], seed=100)
+    p.run()
+    with pytest.raises(RuntimeError,
+                       match="Can't get history as model was run with save_restart = NULL"):
+        p.restart_state()
+
+
+def test_restart_dates_must_exist(gen, sir_data):
+    """tests/testthat/test-particle-filter.R:494-511."""
+    dat = example_sir(sir_data, n_days=20)
+    p = particle_filter(dat["data"], gen, 42, dat["compare"], index=dat["index"], seed=100)
+    for ask, bad in (([30], "30"), ([30, 50], "30, 50"), ([10, 30, 50], "30, 50")):
+        with pytest.raises(ValueError,
+                           match="'save_restart' contains times not in 'day': %s" % bad):
+            p.run(save_restart=ask)
+
+
+def test_no_partial_likelihood_with_compiled_compare(gen, sir_data):
+    """tests/testthat/test-particle-filter.R:589-601."""
+    dat = example_sir(sir_data)
+    p = particle_filter(dat["data"], gen, 100, None, index=dat["index"])
+    obj = p.run_begin()
+    with pytest.raises(ValueError, match="'partial' not supported with compiled compare"):
+        obj.step(10, True)
+
+
+def test_history_needs_saving_and_index_particle(gen, sir_data):
+    """tests/testthat/test-particle-filter.R:270-293 (tail), 536-554: history of chosen
+    particles equals the matching columns of the whole history."""
+    dat = example_sir(sir_data)
+    p = particle_filter(dat["data"], gen, 30, None, index=dat["index"], seed=3)
+    p.run()
+    with pytest.raises(RuntimeError,
+                       match="Can't get history as model was run with save_history = FALSE"):
+        p.history()
+    p.run(save_history=True)
+    h = p.history()
+    assert h.shape == (3, 30, 101)
+    assert np.array_equal(p.history([4, 9]), h[:, [3, 8], :])
+    assert np.array_equal(p.history(1), h[:, :1, :])
+
+
+def test_gpu_config_requires_gpu_support(sir_data):
+    """tests/testthat/test-particle-filter.R:1186-1194: a generator without GPU support
+    refuses ``gpu_config`` (the oracle-backed generator is such a model)."""
+    dat = example_sir(sir_data)
+    with pytest.raises(ValueError, match="'gpu_config' provided, but 'model' does not have GPU support"):
+        particle_filter(dat["data"], OracleGenerator("sir"), 10, None, index=dat["index"],
+                        gpu_config=0)
