@@ -394,10 +394,13 @@ class particle_filter_state:
             if has_multiple_parameters:
                 infos = model.info()
                 states = [initial(infos[i], n_particles, pars[i]) for i in range(len(pars))]
-                if not all(s is None for s in states):
-                    lens = {np.asarray(s).shape for s in states}
-                    if len(lens) != 1:
-                        raise ValueError("initial() produced unequal state lengths")
+                if not all(s is None for s in states):   # pfs_initial_multiple (:528-546)
+                    if any(isinstance(s, dict) for s in states):
+                        raise ValueError("Setting 'time' from initial no longer supported")
+                    lens = [np.asarray(s).shape for s in states]
+                    if len(set(lens)) != 1:
+                        raise ValueError("initial() produced unequal state lengths %s"
+                                         % ", ".join(str(int(np.prod(l))) for l in lens))
                     st = np.stack([np.asarray(s, dtype=float) for s in states], axis=-1)
                     if st.ndim == 2:  # vectors: recycle over particles
                         st = np.repeat(st[:, None, :], n_particles, axis=1)

@@ -110,3 +110,19 @@ def test_gpu_config_requires_gpu_support(sir_data):
     with pytest.raises(ValueError, match="'gpu_config' provided, but 'model' does not have GPU support"):
         particle_filter(dat["data"], OracleGenerator("sir"), 10, None, index=dat["index"],
                         gpu_config=0)
+
+
+def test_nested_initial_errors(gen, sir_data):
+    """tests/testthat/test-particle-filter.R:918-932, 1153-1167."""
+    from test_particle_filter import nested_data
+
+    data = nested_data(sir_data)[0]
+    pars = [{"beta": 0.2, "gamma": 0.1}, {"beta": 0.3, "gamma": 0.1}]
+    p = particle_filter(data, gen, 42, None, initial=lambda info, n, pars: {"time": 0})
+    with pytest.raises(ValueError, match="Setting 'time' from initial no longer supported"):
+        p.run(pars)
+    unequal = [dict(pars[0], extra=[]), dict(pars[1], extra=[10.0])]
+    p = particle_filter(data, gen, 42, None,
+                        initial=lambda info, n, pars: [1000.0] + list(pars["extra"]) + [0.0] * 3)
+    with pytest.raises(ValueError, match="unequal state"):
+        p.run(unequal)
