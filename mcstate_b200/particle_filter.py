@@ -770,6 +770,17 @@ class particle_filter:
             return history_multiple(value, order, index_particle)
         return history_single(value, order, index_particle)
 
+    def history_names(self):
+        """``rownames(filter$history())`` (tests/testthat/test-particle-filter.R:367-392):
+        the names of a named ``index$state``, else None -- numpy arrays carry no row
+        names, so they are asked for here."""
+        if self._last_model is None:
+            raise RuntimeError("Model has not yet been run")
+        if self._last_history is None:
+            raise RuntimeError("Can't get history as model was run with save_history = FALSE")
+        idx = self._last_history["index"]
+        return list(idx) if isinstance(idx, dict) else None
+
     def restart_state(self, index_particle=None, save_restart=None, restart_match=False):
         """R/particle_filter.R:444-468 (the compiled path has no order array, so
         ``restart_match`` falls back to plain subsetting exactly as there, :718)."""

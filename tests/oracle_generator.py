@@ -47,6 +47,7 @@ class OracleDustModel:
                                 seed=_seed_words(seed), model=gen.model_id,
                                 scrambler=gen.scrambler, deterministic=deterministic,
                                 n_threads=max(1, int(n_threads)))
+        self._n_threads = max(1, int(n_threads))
 
     def _shape_out(self, a):  # (rows, n_total) -> (rows, N[, P])
         if self._multi:
@@ -59,8 +60,12 @@ class OracleDustModel:
     def shape(self): return (self._np, self._n_pars) if self._multi else (self._np,)
     def time(self): return int(self._o.time())
     def pars(self): return self._pars
-    def n_threads(self): return 1
-    def set_n_threads(self, n): self._o.set_n_threads(int(n)); return 1
+    def n_threads(self): return self._n_threads
+
+    def set_n_threads(self, n):
+        prev, self._n_threads = self._n_threads, int(n)
+        self._o.set_n_threads(int(n))
+        return prev
     def uses_gpu(self, fake_gpu=False): return False
 
     def info(self):

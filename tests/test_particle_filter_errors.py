@@ -126,3 +126,131 @@ def test_nested_initial_errors(gen, sir_data):
                         initial=lambda info, n, pars: [1000.0] + list(pars["extra"]) + [0.0] * 3)
     with pytest.raises(ValueError, match="unequal state"):
         p.run(unequal)
+
+
+def test_names_on_history(gen, sir_data):
+    """tests/testthat/test-particle-filter.R:367-392: a named ``index$state`` names the
+    rows of the history; an unnamed one leaves them unnamed."""
+    dat = example_sir(sir_data)
+    named = particle_filter(dat["data"], gen, 42, dat["compare"], seed=100,
+                            index=lambda info: {"run": [4], "state": {"S": 1, "I": 2, "R": 3}})
+    named.run(save_history=True)
+    h = named.history()
+    assert h.shape == (3, 42, 101)
+    assert named.history_names() == ["S", "I", "R"]
+    plain = particle_filter(dat["data"], gen, 42, dat["compare"], seed=100,
+                            index=lambda info: {"run": [4], "state": [1, 2, 3]})
+    plain.run(save_history=True)
+    assert plain.history_names() is None
+
+
+def test_change_thread_count(gen, sir_data):
+    """tests/testthat/test-particle-filter.R:395-414."""
+    dat = example_sir(sir_data)
+    p = particle_filter(dat["data"], gen, 42, dat["compare"], index=dat["index"], seed=100,
+                        n_threads=1)
+    assert p.set_n_threads(2) == 1
+    p.run()
+    assert p._last_model[0].n_threads() == 2
+    assert p.set_n_threads(1) == 2
+    assert p._last_model[0].n_threads() == 1
+    p.run()
+    assert p._last_model[0].n_threads() == 1
+
+
+@pytest.mark.parametrize("compiled", [False, True])
+def test_stepping_errors(gen, sir_data, compiled):
+    """tests/testthat/test-particle-filter.R:661-711."""
+    dat = example_sir(sir_data)
+    p = particle_filter(dat["data"], gen, 42, None if compiled else dat["compare"],
+                        index=dat["index"], seed=1)
+    obj = p.run_begin()
+    obj.run()
+    for call in (obj.run, lambda: obj.step(100), lambda: obj.step(101)):
+        with pytest.raises(ValueError, match="Particle filter has reached the end of the data"):
+            call()
+    obj = p.run_begin()
+    obj.step(10)
+    for k, t in ((10, 40), (5, 20)):
+        with pytest.raises(ValueError, match=r"Particle filter has already run step index %d "
+                                             r"\(to model step %d\)" % (k, t)):
+            obj.step(k)
+    obj = p.run_begin()
+    with pytest.raises(ValueError,
+                       match=r"time_index 101 is beyond the length of the data \(max 100\)"):
+        obj.step(101)
+
+
+def _nested(sir_data, gen, compare="example", **kw):
+    from test_particle_filter import nested_data
+
+    data = nested_data(sir_data, n_days=100)[0]
+    dat = example_sir(sir_data)
+    cmp = dat["compare"] if compare == "example" else compare
+    return particle_filter(data, gen, 42, cmp, index=kw.pop("index", dat["index"]), **kw), dat
+
+
+NESTED_PARS = [{"beta": 0.2, "gamma": 0.1}, {"beta": 0.3, "gamma": 0.1}]
+
+
+def test_nested_impossible_likelihood(gen, sir_data):
+    """tests/testthat/test-particle-filter.R:1007-1034: the filter stops at the first
+    interval one population finds impossible; the history after it stays NA."""
+    dat = example_sir(sir_data)
+
+    def compare(state, observed, pars):
+        ret = dat["compare"](state, observed, pars)
+        if observed["incidence"] > 15:
+            ret[:] = -np.inf
+        return ret
+
+    p, _ = _nested(sir_data, gen, compare)
+    np.random.seed(1)
+    res = p.run(NESTED_PARS, save_history=True)
+    assert -np.inf in res
+    first = int(np.argmax(sir_data["incidence"] > 15))     # 0-based data row of population a
+    h = p.history()
+    assert h.shape == (3, 42, 2, 101)
+    assert not np.isnan(h[:, :, 0, :first + 2]).any()
+    assert np.isnan(h[:, :, 0, first + 2:]).all()
+
+
+def test_nested_null_compare_and_initial(gen, sir_data):
+    """tests/testthat/test-particle-filter.R:1036-1058."""
+    p, _ = _nested(sir_data, gen, lambda *a: None)
+    res = p.run(NESTED_PARS, save_history=True)
+    assert np.array_equal(res, [0.0, 0.0])
+    assert p.history().shape == (3, 42, 2, 101)
+    p, _ = _nested(sir_data, gen, initial=lambda *a: None, seed=100)
+    np.random.seed(1)
+    assert np.isfinite(p.run(NESTED_PARS)).all()
+
+
+def test_nested_index_must_agree(gen, sir_data):
+    """tests/testthat/test-particle-filter.R:1078-1093."""
+    p, _ = _nested(sir_data, gen, seed=100,
+                   index=lambda info: {"run": [int(round(info["pars"]["beta"] * 10))]})
+    with pytest.raises(ValueError, match="index must be identical across populations"):
+        p.run(NESTED_PARS, save_history=True)
+
+
+def test_nested_early_exit(gen, sir_data):
+    """tests/testthat/test-particle-filter.R:1251-1282: a scalar threshold applies to the
+    sum over populations, a vector one population by population (all must fall below)."""
+    def runs(min_ll=None):
+        np.random.seed(1)
+        p, _ = _nested(sir_data, gen, seed=1)
+        return np.array([p.run(NESTED_PARS, min_log_likelihood=min_ll) for _ in range(10)]).T
+
+    ll1 = runs()
+    tot = ll1.sum(axis=0)
+    ll2 = runs(float(tot.mean()))
+    assert np.isinf(ll2).any()
+    fin = np.isfinite(ll2).all(axis=0)
+    assert ll2[:, fin].sum(axis=0).min() >= tot.mean()
+    vec = ll1[:, int(np.argmin(np.abs(tot - tot.mean())))]
+    ll3 = runs(vec)
+    alive = (ll3 > -np.inf).any(axis=0)
+    assert not alive.all()
+    assert np.all(ll3[:, ~alive] == -np.inf)
+    assert np.all((ll3[:, alive] >= vec[:, None]).any(axis=0))
