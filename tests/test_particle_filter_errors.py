@@ -1,7 +1,7 @@
 """Extraction and error behaviour of the filter facade, ported from the blocks of
 tests/testthat/test-particle-filter.R that tests/test_particle_filter.py does not cover
-(file:line per test; messages are the reference's).  These are properties of the host
-mirror: they run on the oracle-backed generator."""
+(file:line per test; messages are the reference's).  Oracle-backed generator on the CPU,
+the B200 engine under ``-m gpu``."""
 import numpy as np
 import pytest
 
@@ -9,7 +9,7 @@ from mcstate_b200.particle_filter import particle_filter
 from test_particle_filter import BACKENDS, OracleGenerator, _gpu_generator, example_sir
 
 
-@pytest.fixture(params=BACKENDS[:1])   # oracle-backed generator (host logic)
+@pytest.fixture(params=BACKENDS)
 def gen(request):
     return OracleGenerator("sir") if request.param == "oracle" else _gpu_generator("sir")
 
