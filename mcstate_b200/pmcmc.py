@@ -448,20 +448,38 @@ def pmcmc_predict(object, times, prepend_trajectories=False, n_threads=None, see
     return res
 
 
-def _check_initial(initial, pars, n_chains):
-    # R/pmcmc.R: pmcmc_check_initial -- a vector is recycled over chains
+def pmcmc_check_initial(initial, pars, n_chains):
+    """``pmcmc_check_initial`` (R/pmcmc.R:112-154): None -> the parameters' own starting
+    point; a vector (or a dict, R's named vector) of ``n_pars`` values is used for every
+    chain; a matrix is ``[n_pars, n_chains]``, one COLUMN per chain as in R.  Returns the
+    per-chain starting points ``[n_chains, n_pars]`` (R: a list with one vector per chain)."""
+    nms = pars.names()
+    n_pars = len(nms)
     if initial is None:
         initial = pars.initial()
+    if isinstance(initial, dict):
+        if list(initial) != nms:
+            raise ValueError("Expected names of 'initial' to match parameters (%s)"
+                             % ", ".join("'%s'" % n for n in nms))
+        initial = [initial[n] for n in nms]
     initial = np.asarray(initial, dtype=float)
-    if initial.ndim == 1:
+    if initial.ndim == 2:
+        if initial.shape != (n_pars, n_chains):
+            raise ValueError("Expected 'initial' to be a matrix with dimensions %d x %d"
+                             % (n_pars, n_chains))
+        initial = initial.T.copy()
+    else:
+        if initial.shape != (n_pars,):
+            raise ValueError("Expected 'initial' to be a vector with length %d" % n_pars)
         initial = np.tile(initial[None, :], (n_chains, 1))
-    if initial.shape != (n_chains, len(pars.names())):
-        raise ValueError("Expected 'initial' to have %d columns and %d rows"
-                         % (len(pars.names()), n_chains))
-    for row in initial:
-        if not math.isfinite(pars.prior(row)):
-            raise ValueError("Starting point does not have finite prior probability")
+    bad = [k + 1 for k, row in enumerate(initial) if not math.isfinite(pars.prior(row))]
+    if bad:
+        raise ValueError("Starting point does not have finite prior probability (chain %s)"
+                         % ", ".join(map(str, bad)))
     return initial
+
+
+_check_initial = pmcmc_check_initial
 
 
 def _chain_from_inputs(inputs, seed, pars, initial_k, control, device=None, n_threads=None):

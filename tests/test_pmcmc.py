@@ -562,3 +562,103 @@ def test_pmcmc_with_fixed_parameter(sir_data):
     assert res["pars"].shape == (10, 1) and res["pars_names"] == ["beta"]
     assert res["state"].shape == (5, 10) and res["trajectories"].shape == (3, 10, 101)
     assert res["predict"]["transform"](res["pars"][-1])["gamma"] == 0.1
+
+
+# ---------------------------------------------------------------- the MH machinery on known targets
+class _ToyFilter:
+    """tests/testthat/helper-mcstate.R:222-249, 312-335: a "filter" whose run() is a known
+    log density -- the reference tests its MCMC machinery this way."""
+    n_particles = 10
+    has_multiple_parameters = False
+    has_multiple_data = False
+
+    def __init__(self, target):
+        self._target = target
+
+    def run(self, pars, *args):
+        return self._target(pars)
+
+    def state(self):
+        return np.ones((2, 10))
+
+
+def _unit_square_pars(proposal=None):
+    flat = lambda p: 0.0 if 0.0 <= p <= 1.0 else -math.inf  # noqa: E731  dunif(p, log = TRUE)
+    return pmcmc_parameters([pmcmc_parameter("a", 0.5, min=0, max=1, prior=flat),
+                             pmcmc_parameter("b", 0.5, min=0, max=1, prior=flat)],
+                            np.eye(2) * 0.1 if proposal is None else proposal)
+
+
+def test_mcmc_uniform_on_unit_square():
+    """tests/testthat/test-pmcmc.R:7-20: a flat target accepts every (reflected) proposal
+    and the chain's means sit at the centre."""
+    from mcstate_b200.pmcmc import pmcmc_run_chain
+
+    control = pmcmc_control(1000, save_state=False, save_trajectories=False)
+    res = pmcmc_run_chain(_unit_square_pars(), [0.5, 0.5], _ToyFilter(lambda p: 1.0), control,
+                          np.random.default_rng(1))
+    assert res["pars"].shape == (1000, 2)
+    assert np.all(np.any(np.diff(res["pars"], axis=0) != 0, axis=1))      # acceptance rate 1
+    assert np.all((res["pars"] >= 0) & (res["pars"] <= 1))
+    assert abs(res["pars"][:, 0].mean() - 0.5) < 0.05 and abs(res["pars"][:, 1].mean() - 0.5) < 0.05
+
+
+def test_mcmc_multivariate_gaussian():
+    """tests/testthat/test-pmcmc.R:23-37: a standard bivariate normal target is recovered
+    (Kolmogorov-Smirnov on thinned draws, uncorrelated components)."""
+    from scipy import stats
+
+    from mcstate_b200.pmcmc import pmcmc_run_chain
+
+    pars = pmcmc_parameters([pmcmc_parameter("a", 0, min=-100, max=100),
+                             pmcmc_parameter("b", 0, min=-100, max=100)], np.eye(2))
+    target = lambda p: float(-0.5 * (p["a"] ** 2 + p["b"] ** 2) - math.log(2 * math.pi))  # noqa: E731
+    control = pmcmc_control(4000, save_state=False, save_trajectories=False)
+    res = pmcmc_run_chain(pars, [0.0, 0.0], _ToyFilter(target), control, np.random.default_rng(1))
+    thin = res["pars"][::40]
+    assert stats.kstest(thin[:, 0], "norm").pvalue > 0.05
+    assert stats.kstest(thin[:, 1], "norm").pvalue > 0.05
+    assert abs(np.cov(res["pars"], rowvar=False)[0, 1]) < 0.1
+    assert np.allclose(res["probabilities"][:, 0] + res["probabilities"][:, 1],
+                       res["probabilities"][:, 2])
+
+
+def test_initial_conditions():
+    """tests/testthat/test-pmcmc.R:270-337."""
+    from mcstate_b200.pmcmc import pmcmc_check_initial
+
+    sir, uni = example_pars(), _unit_square_pars()
+    assert np.array_equal(pmcmc_check_initial(None, sir, 1), [[0.2, 0.1]])
+    assert np.array_equal(pmcmc_check_initial(None, sir, 5), np.tile([0.2, 0.1], (5, 1)))
+    for given in ([0.1, 0.2], {"a": 0.1, "b": 0.2}):
+        assert np.array_equal(pmcmc_check_initial(given, uni, 1), [[0.1, 0.2]])
+        assert np.array_equal(pmcmc_check_initial(given, uni, 5), np.tile([0.1, 0.2], (5, 1)))
+    with pytest.raises(ValueError, match="Expected 'initial' to be a vector with length 2"):
+        pmcmc_check_initial([0.1, 0.2, 0.4], uni, 1)
+    with pytest.raises(ValueError,
+                       match=r"Expected names of 'initial' to match parameters \('a', 'b'\)"):
+        pmcmc_check_initial({"x": 0.1, "y": 0.2}, uni, 1)
+    with pytest.raises(ValueError, match="Starting point does not have finite prior probability"):
+        pmcmc_check_initial([-0.1, 0.2], uni, 1)
+    # a matrix has one COLUMN per chain, as in R
+    assert np.array_equal(pmcmc_check_initial(np.array([[0.1], [0.2]]), uni, 1), [[0.1, 0.2]])
+    m = np.random.default_rng(1).uniform(size=(2, 5))
+    assert np.array_equal(pmcmc_check_initial(m, uni, 5), m.T)
+    for shape in ((3, 5), (2, 6)):
+        with pytest.raises(ValueError,
+                           match="Expected 'initial' to be a matrix with dimensions 2 x 5"):
+            pmcmc_check_initial(np.full(shape, 0.5), uni, 5)
+    m[[1, 0, 1], [1, 3, 4]] *= -1
+    with pytest.raises(ValueError, match=r"Starting point does not have finite prior "
+                                         r"probability \(chain 2, 4, 5\)"):
+        pmcmc_check_initial(m, uni, 5)
+
+
+def test_pmcmc_from_a_matrix_of_starting_points(sir_data):
+    """tests/testthat/test-pmcmc.R:340-362."""
+    initial = np.array([[0.2], [0.1]]) + np.random.default_rng(2).uniform(0, 0.001, (2, 3))
+    control = pmcmc_control(2, n_chains=3, use_parallel_seed=True)
+    res = pmcmc(example_pars(), example_filter("oracle", sir_data, 10), initial=initial,
+                control=control)
+    first = res["pars"][res["iteration"] == 1]
+    assert first.shape == (3, 2) and len({tuple(r) for r in first}) == 3
