@@ -36,6 +36,15 @@ class smc2_parameter:
 
     def __init__(self, name, sample, prior, min=-math.inf, max=math.inf, discrete=False,
                  integer=False):
+        if not callable(sample) or not callable(prior):
+            raise TypeError("'sample' and 'prior' must be functions")
+        if discrete:   # R/smc2_parameters.R: deprecated spelling of `integer`
+            import warnings
+
+            warnings.warn("'discrete' is deprecated.\nUse 'integer' instead.", DeprecationWarning,
+                          stacklevel=2)
+        if max <= min:
+            raise ValueError("'max' must be > 'min' (%g)" % min)
         self.name, self.sample, self.prior = name, sample, prior
         self.min, self.max = float(min), float(max)
         self.integer = bool(discrete or integer)
@@ -49,6 +58,8 @@ class smc2_parameters:
             raise ValueError("At least one parameter is required")
         self._p = list(parameters)
         self._names = [p.name for p in self._p]
+        if len(set(self._names)) != len(self._names):
+            raise ValueError("Duplicate parameter names")
         self._min = np.array([p.min for p in self._p])
         self._max = np.array([p.max for p in self._p])
         self._integer = np.array([p.integer for p in self._p])
@@ -56,6 +67,11 @@ class smc2_parameters:
 
     def names(self):
         return list(self._names)
+
+    def summary(self):
+        """R/smc2_parameters.R: one record per parameter."""
+        return [{"name": p.name, "min": p.min, "max": p.max, "discrete": p.integer,
+                 "integer": p.integer} for p in self._p]
 
     def sample(self, n, rng):
         return np.stack([np.asarray(p.sample(n, rng), dtype=float) for p in self._p], axis=1)

@@ -179,3 +179,40 @@ def test_sharded_smc2_equals_single_rank(tmp_path, kind):
     assert np.array_equal(want["pars"], got["pars"])
     assert np.array_equal(want["probabilities"], got["probabilities"])
     assert np.array_equal(want["statistics"]["ess"], got["statistics"]["ess"])
+
+
+def test_smc2_parameters():
+    """tests/testthat/test-smc2-parameters.R:6-112."""
+    import warnings
+
+    unif = lambda lo, hi: (lambda n, rng: rng.uniform(lo, hi, n))  # noqa: E731
+    dunif = lambda lo, hi: (lambda x: -math.log(hi - lo) if lo <= x <= hi else -math.inf)  # noqa: E731
+    p = smc2_parameter("a", unif(0, 10), dunif(0, 10), min=0, max=10, integer=True)
+    assert (p.name, p.min, p.max, p.integer) == ("a", 0.0, 10.0, True)
+    assert p.prior(1) == pytest.approx(math.log(0.1))
+    assert np.array_equal(p.sample(20, np.random.default_rng(1)),
+                          np.random.default_rng(1).uniform(0, 10, 20))
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        q = smc2_parameter("a", unif(0, 10), dunif(0, 10), min=0, max=10, discrete=True)
+    assert q.integer and "'discrete' is deprecated" in str(w[0].message)
+    with pytest.raises(ValueError, match=r"'max' must be > 'min' \(20\)"):
+        smc2_parameter("a", unif(0, 10), dunif(0, 10), min=20, max=10)
+    ps = smc2_parameters([smc2_parameter("beta", unif(0, 10), dunif(0, 10), min=0, max=10),
+                          smc2_parameter("gamma", unif(1, 2), dunif(1, 2), min=1, max=2)])
+    assert ps.names() == ["beta", "gamma"]
+    assert ps.summary() == [
+        {"name": "beta", "min": 0.0, "max": 10.0, "discrete": False, "integer": False},
+        {"name": "gamma", "min": 1.0, "max": 2.0, "discrete": False, "integer": False}]
+    theta = ps.sample(10, np.random.default_rng(2))
+    assert theta.shape == (10, 2) and np.all((theta[:, 1] >= 1) & (theta[:, 1] <= 2))
+    assert np.allclose(ps.prior(theta), math.log(0.1))
+    ps = smc2_parameters([smc2_parameter("beta", unif(0, 10), dunif(0, 10), min=0, max=10),
+                          smc2_parameter("gamma", lambda n, rng: rng.exponential(1.0, n),
+                                         lambda x: -x)])
+    theta = ps.sample(100, np.random.default_rng(3))
+    new = ps.propose(theta, np.eye(2) * 100, np.random.default_rng(4))
+    assert new.shape == (100, 2) and np.all((new[:, 0] > 0) & (new[:, 0] < 10))
+    assert ps.model(theta[:2])[1] == {"beta": theta[1, 0], "gamma": theta[1, 1]}
+    with pytest.raises(ValueError, match="Duplicate parameter names"):
+        smc2_parameters([p, p])
