@@ -32,7 +32,9 @@ class particle_filter_data:
             raise ValueError("The time column cannot be called '%s'" % time)
         if rate is None:
             raise ValueError("continuous-time data (rate = NULL) is not supported by this engine")
-        if int(rate) != rate or rate < 1:
+        if int(rate) != rate:
+            raise ValueError("'rate' must be an integer")
+        if rate < 1:
             raise ValueError("'rate' must be at least 1")
         rate = int(rate)
 
