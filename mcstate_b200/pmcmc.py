@@ -159,28 +159,81 @@ class pmcmc_parameters:
 # ---------------------------------------------------------------------------
 # control (R/pmcmc_control.R:187-290, the fields this path reads)
 # ---------------------------------------------------------------------------
+def pmcmc_filter_on_generation(n_steps, n_burnin=None, n_steps_retain=None):
+    """R/pmcmc_control.R:295-332: which steps a chain keeps -- every ``n_steps_every``-th
+    one, counted back from the LAST step, ``n_steps_retain`` of them; ``n_burnin`` is then
+    back-calculated (it can only grow)."""
+    n_burnin = 0 if n_burnin is None else n_burnin
+    if int(n_burnin) != n_burnin or n_burnin < 0:
+        raise ValueError("'n_burnin' must be a non-negative integer")
+    if n_burnin >= n_steps:
+        raise ValueError("'n_burnin' cannot be greater than or equal to 'n_steps'")
+    possible = int(n_steps - n_burnin)
+    n_steps_retain = possible if n_steps_retain is None else n_steps_retain
+    if int(n_steps_retain) != n_steps_retain or n_steps_retain < 1:
+        raise ValueError("'n_steps_retain' must be at least 1")
+    n_steps_retain = int(n_steps_retain)
+    if n_steps_retain > possible:
+        raise ValueError("'n_steps_retain' is too large, max possible is %d but given %d"
+                         % (possible, n_steps_retain))
+    every = possible // n_steps_retain
+    if every == 1 and (possible - n_steps_retain) / possible > 0.05:
+        raise ValueError("'n_steps_retain' is too large to skip any samples, and would result "
+                         "in just increasing 'n_burnin' by more than 5% of your post-burnin "
+                         "samples. Please adjust 'n_steps' 'n_burnin' or 'n_steps_retain' to "
+                         "make your intentions clearer")
+    return {"n_burnin": int(n_steps - every * (n_steps_retain - 1) - 1),
+            "n_steps_retain": n_steps_retain, "n_steps_every": every}
+
+
+def pmcmc_check_control(control):
+    """R/pmcmc_control.R:335-343."""
+    if control.n_steps != control.n_burnin + (control.n_steps_retain - 1) * control.n_steps_every + 1:
+        raise ValueError("Corrupt pmcmc_control (n_steps/n_steps_retain/n_burnin), "
+                         "perhaps you modified it after creation?")
+
+
 class pmcmc_control:
-    def __init__(self, n_steps, n_chains=1, n_burnin=0, n_steps_retain=None, save_state=True,
+    """``pmcmc_control(...)`` (R/pmcmc_control.R:187-290, the fields this path reads).
+    ``n_workers > 1`` shards the chains over the ranks of the process group (one GPU each);
+    ``n_threads_total`` is validated as the reference does when given, but not demanded
+    with workers: the filter's parallelism is the GPU's, not host threads."""
+
+    def __init__(self, n_steps, n_chains=1, n_burnin=None, n_steps_retain=None, save_state=True,
                  save_restart=None, save_trajectories=False, rerun_every=math.inf,
                  rerun_random=False, filter_early_exit=False, use_parallel_seed=False,
-                 n_workers=1, progress=False):
+                 n_workers=1, progress=False, n_threads_total=None, path=None):
         if n_steps < 1 or n_chains < 1 or n_workers < 1:
             raise ValueError("'n_steps', 'n_chains' and 'n_workers' must be at least 1")
-        if n_workers > n_chains:
-            raise ValueError("'n_chains' must be at least 'n_workers'")
-        if n_burnin >= n_steps:
-            raise ValueError("'n_burnin' cannot be greater than or equal to 'n_steps'")
-        self.n_steps, self.n_chains, self.n_burnin = int(n_steps), int(n_chains), int(n_burnin)
-        n_retain = self.n_steps - self.n_burnin
-        if n_steps_retain is None:
-            n_steps_retain = n_retain
-        if n_steps_retain > n_retain:
-            raise ValueError("'n_steps_retain' is too large, max possible is %d" % n_retain)
-        self.n_steps_retain = int(n_steps_retain)
-        self.n_steps_every = n_retain // self.n_steps_retain
-        # keep the last n_steps_retain * n_steps_every steps (R/pmcmc_control.R:292-311)
-        self.n_burnin = self.n_steps - self.n_steps_retain * self.n_steps_every
+        if n_threads_total is not None:
+            if int(n_threads_total) != n_threads_total or n_threads_total < 1:
+                raise ValueError("'n_threads_total' must be at least 1")
+            if n_threads_total < n_workers:
+                raise ValueError("'n_threads_total' (%d) is less than 'n_workers' (%d)"
+                                 % (n_threads_total, n_workers))
+            if n_threads_total % n_workers != 0:
+                raise ValueError("'n_threads_total' (%d) is not a multiple of 'n_workers' (%d)"
+                                 % (n_threads_total, n_workers))
+        if n_chains < n_workers:
+            raise ValueError("'n_chains' (%d) is less than 'n_workers' (%d)"
+                             % (n_chains, n_workers))
+        if path is not None and n_workers == 1:
+            import warnings
+
+            warnings.warn("'path' given when n_workers = 1 has no effect and is ignored")
+        self.n_steps, self.n_chains = int(n_steps), int(n_chains)
+        self.n_threads_total = None if n_threads_total is None else int(n_threads_total)
+        self.path = path
+        # keep n_steps_retain steps, every n_steps_every-th, ending at the last one
+        # (R/pmcmc_control.R:295-332)
+        gen = pmcmc_filter_on_generation(self.n_steps, n_burnin, n_steps_retain)
+        self.n_burnin, self.n_steps_retain = gen["n_burnin"], gen["n_steps_retain"]
+        self.n_steps_every = gen["n_steps_every"]
         self.save_state, self.save_trajectories = bool(save_state), bool(save_trajectories)
+        if save_restart is not None:
+            save_restart = [save_restart] if np.isscalar(save_restart) else list(save_restart)
+            if any(b <= a for a, b in zip(save_restart, save_restart[1:])):
+                raise ValueError("'save_restart' must be strictly increasing")
         self.save_restart = save_restart
         self.rerun_every, self.rerun_random = rerun_every, bool(rerun_random)
         self.filter_early_exit = bool(filter_early_exit)
@@ -290,6 +343,7 @@ class pmcmc_state:
     def run(self):
         # R/pmcmc_state.R:284-308
         c = self._control
+        pmcmc_check_control(c)
         rerun = _make_rerun(c.rerun_every, c.rerun_random, self._rng)
         for i in range(1, c.n_steps + 1):
             if rerun(i):

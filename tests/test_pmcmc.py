@@ -85,13 +85,65 @@ def test_rmvnorm_generator_moments_and_zero_rows():
 
 
 def test_control_validation_and_retention():
+    """tests/testthat/test-pmcmc-control.R:4-120."""
+    from mcstate_b200.pmcmc import pmcmc_check_control, pmcmc_filter_on_generation
+
+    with pytest.raises(ValueError, match=r"'n_chains' \(2\) is less than 'n_workers' \(5\)"):
+        pmcmc_control(100, n_chains=2, n_workers=5, n_threads_total=5)
+    with pytest.raises(ValueError, match=r"'n_threads_total' \(3\) is less than 'n_workers' \(5\)"):
+        pmcmc_control(100, n_chains=5, n_workers=5, n_threads_total=3)
+    with pytest.raises(ValueError,
+                       match=r"'n_threads_total' \(8\) is not a multiple of 'n_workers' \(5\)"):
+        pmcmc_control(100, n_chains=5, n_workers=5, n_threads_total=8)
+    assert pmcmc_control(100).save_restart is None
+    assert pmcmc_control(100, save_restart=1).save_restart == [1]
+    assert pmcmc_control(100, save_restart=[10, 20]).save_restart == [10, 20]
+    with pytest.raises(ValueError, match="'save_restart' must be strictly increasing"):
+        pmcmc_control(100, save_restart=[20, 10])
+    # filter on generation: the kept steps end at the last one
+    assert pmcmc_filter_on_generation(100, None, None) == \
+        {"n_burnin": 0, "n_steps_retain": 100, "n_steps_every": 1}
+    dat = pmcmc_filter_on_generation(100, 40, 20)
+    assert dat == {"n_burnin": 42, "n_steps_retain": 20, "n_steps_every": 3}
+    steps = [dat["n_burnin"] + 1 + k * dat["n_steps_every"] for k in range(dat["n_steps_retain"])]
+    assert steps == list(range(43, 101, 3))
+    for args in ((10, 100, 5), (100, 100, 5)):
+        with pytest.raises(ValueError,
+                           match="'n_burnin' cannot be greater than or equal to 'n_steps'"):
+            pmcmc_filter_on_generation(*args)
+    with pytest.raises(ValueError,
+                       match="'n_steps_retain' is too large, max possible is 90 but given 500"):
+        pmcmc_filter_on_generation(100, 10, 500)
+    with pytest.raises(ValueError, match="'n_steps_retain' is too large to skip any samples,"):
+        pmcmc_filter_on_generation(100, 10, 75)
     c = pmcmc_control(100, n_burnin=10, n_steps_retain=30)
-    assert (c.n_steps_every, c.n_burnin) == (3, 10)
-    with pytest.raises(ValueError):
-        pmcmc_control(10, n_chains=1, n_workers=2)
-    with pytest.raises(ValueError):
-        pmcmc_control(10, n_burnin=10)
+    assert (c.n_steps_every, c.n_burnin, c.n_steps_retain) == (3, 12, 30)
+    c = pmcmc_control(100, n_steps_retain=15, n_burnin=5)
+    pmcmc_check_control(c)
+    c.n_steps = 30
+    with pytest.raises(ValueError, match=r"Corrupt pmcmc_control \(n_steps/n_steps_retain/n_burnin\)"):
+        pmcmc_check_control(c)
+    with pytest.warns(UserWarning,
+                      match="'path' given when n_workers = 1 has no effect and is ignored"):
+        pmcmc_control(10, path="location")
     assert pmcmc_control(10, n_chains=2, n_workers=2).use_parallel_seed
+
+
+def test_retained_steps_end_at_the_last_one(sir_data):
+    """tests/testthat/test-pmcmc.R:609-645 ("Can filter pmcmc on creation"): a run that
+    retains 7 of 30 steps after a burn-in equals the full run at those iterations."""
+    full = pmcmc(example_pars(), example_filter("oracle", sir_data, 10),
+                 control=pmcmc_control(30, save_state=True, save_trajectories=True,
+                                       use_parallel_seed=True))
+    part = pmcmc(example_pars(), example_filter("oracle", sir_data, 10),
+                 control=pmcmc_control(30, save_state=True, save_trajectories=True,
+                                       use_parallel_seed=True, n_burnin=5, n_steps_retain=7))
+    assert list(part["iteration"]) == list(range(12, 31, 3)) and part["iteration"][-1] == 30
+    i = part["iteration"] - 1
+    assert np.array_equal(part["pars"], full["pars"][i])
+    assert np.array_equal(part["probabilities"], full["probabilities"][i])
+    assert np.array_equal(part["state"], full["state"][:, i])
+    assert np.array_equal(part["trajectories"], full["trajectories"][:, i])
 
 
 def test_make_seeds_deterministic_prefix_stable():
