@@ -78,6 +78,39 @@ def ncu_traffic_bytes(kernel):
         return None, None
 
 
+def ncu_issue_counters(kernel):
+    """Issue-slot and pipe utilisation of `kernel` (percent of peak, sustained, active
+    cycles) from the same committed `ncu --set full` summary as the traffic: the update
+    kernel is bound by instruction issue, not by HBM, so this is the roofline it is
+    read against (BASELINE north_star: "a fraction of the HBM or issue roofline").
+    None if the summary is absent or does not hold the kernel."""
+    import csv
+    import glob
+    import re
+
+    def version(path):
+        return tuple(int(x) for x in re.findall(r"\d+", os.path.basename(path)))
+
+    try:
+        files = sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_full_summary_r*.csv")),
+                       key=version)
+        rows = list(csv.reader(open(files[-1])))
+        hdr = rows[0]
+        keys = {"issue_active_pct": "smsp__issue_active.avg.pct_of_peak_sustained_active",
+                "fp64_pipe_pct": "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+                "alu_pipe_pct": "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+                "warp_instructions": "smsp__inst_executed.sum"}
+        mine = [r for r in rows[2:] if kernel in r[0]]
+        if not mine:
+            return None
+        out = {k: sum(float(r[hdr.index(col)]) for r in mine) / len(mine)
+               for k, col in keys.items()}
+        out["source"] = os.path.basename(files[-1])
+        return out
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -348,6 +381,7 @@ def run_engine(args):
                         "whole_interval_frac": (BYTES_INTERVAL * N_PARTICLES * 100 * args.steps /
                                                 (ms_total * 1e-3) / 1e9) / peak,
                         "instrumented_ms_per_step": ms_instrumented / args.steps,
+                        "issue": ncu_issue_counters(dom),
                         "kernels": kernels}
         cores = os.cpu_count() or 1
         cpu = None
