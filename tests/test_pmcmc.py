@@ -714,3 +714,19 @@ def test_pmcmc_from_a_matrix_of_starting_points(sir_data):
                 control=control)
     first = res["pars"][res["iteration"] == 1]
     assert first.shape == (3, 2) and len({tuple(r) for r in first}) == 3
+
+
+def test_rerun_schedule():
+    """tests/testthat/test-pmcmc-support.R:3-25."""
+    from mcstate_b200.pmcmc import _make_rerun
+
+    gen = np.random.default_rng(1)
+    fixed, rand = _make_rerun(3, False, gen), _make_rerun(3, True, gen)
+    i = range(11)
+    x = np.array([[fixed(k) for k in i] for _ in range(1000)])
+    y = np.array([[rand(k) for k in i] for _ in range(1000)])
+    assert np.array_equal(x, np.tile(np.resize([True, False, False], 11), (1000, 1)))
+    assert not np.array_equal(x, y) and 0.32 < y.mean() < 0.345
+    for random in (False, True):
+        never = _make_rerun(math.inf, random, gen)
+        assert not any(never(k) for k in i)
