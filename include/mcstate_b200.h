@@ -51,9 +51,14 @@ int mcb_device_info(int device_id, char *name, size_t name_len, int *cc_major,
                     int *cc_minor, int *n_sm, size_t *mem_bytes);
 
 /* ---- model registry (dust::dust_example; tests/testthat/helper-mcstate.R:3) */
-/* names: "sir", "sirs".  Parameter vectors are positional; names/defaults via the
- * two accessors so a host binding can map an R list and ignore extra keys
- * (R/particle_filter.R:283-284). */
+/* names: "sir", "sirs", "volatility", "walk" in the stock library.  Parameter vectors are
+ * positional; names/defaults via the accessors so a host binding can map an R list and
+ * ignore extra keys (R/particle_filter.R:283-284).
+ * A user-supplied model (dust::dust(file) / odin.dust: tests/testthat/
+ * test-pmcmc-parallel.R:197, helper-mcstate.R:478-492 + compare_variable.cpp) is a
+ * library of its own with THIS SAME ABI, built from the engine sources with
+ * -DMCB_USER_MODEL="<model header>"; it holds that one model as id 0, found by its name
+ * (mcstate_b200/examples/seir.cuh). */
 int mcb_model_lookup(const char *name, int *model_id, size_t *n_state, size_t *n_par,
                      size_t *n_data_fields);
 const char *mcb_model_par_name(int model_id, size_t i);
