@@ -382,6 +382,10 @@ class pmcmc_state:
             if c.save_trajectories:
                 # the model steps of the saved trajectories (R/pmcmc_state.R:386-396)
                 out["trajectories_time"] = np.concatenate([data.times[:1, 0], data.times[:, 1]])
+                # rownames(results$trajectories$state): the names of a named index$state
+                # (tests/testthat/test-pmcmc.R:239-267), None for an unnamed one
+                idx = out["predict"]["index"]
+                out["trajectories_names"] = list(idx) if isinstance(idx, dict) else None
         return out
 
 
@@ -407,6 +411,7 @@ def pmcmc_combine(samples):
     out["predict"] = samples[-1].get("predict")
     if "trajectories_time" in samples[-1]:
         out["trajectories_time"] = samples[-1]["trajectories_time"]
+        out["trajectories_names"] = samples[-1].get("trajectories_names")
     return out
 
 
@@ -487,8 +492,10 @@ def pmcmc_predict(object, times, prepend_trajectories=False, n_threads=None, see
         mod.set_index(pred["index"])
     y = np.asarray(mod.simulate(times))           # [n_index, 1, n_samples, n_times]
     y = y.reshape(y.shape[0], -1, y.shape[-1])
+    # rownames(y$state): names are copied from the index (tests/testthat/test-predict.R:129-141)
+    names = list(pred["index"]) if isinstance(pred["index"], dict) else None
     res = {"time": np.array(times), "rate": pred["rate"], "state": y,
-           "predicted": np.ones(len(times), dtype=bool)}
+           "predicted": np.ones(len(times), dtype=bool), "names": names}
     if prepend_trajectories:
         a_time = np.asarray(object["trajectories_time"])
         a_state = np.asarray(object["trajectories"])
@@ -498,7 +505,7 @@ def pmcmc_predict(object, times, prepend_trajectories=False, n_threads=None, see
         res = {"time": np.concatenate([a_time, res["time"][1:]]), "rate": pred["rate"],
                "state": np.concatenate([a_state, y[:, :, 1:]], axis=2),
                "predicted": np.concatenate([np.zeros(a_time.size, dtype=bool),
-                                            res["predicted"][1:]])}
+                                            res["predicted"][1:]]), "names": names}
     return res
 
 

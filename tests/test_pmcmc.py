@@ -730,3 +730,26 @@ def test_rerun_schedule():
     for random in (False, True):
         never = _make_rerun(math.inf, random, gen)
         assert not any(never(k) for k in i)
+
+
+def test_names_on_pmcmc_output_and_predictions(sir_data):
+    """tests/testthat/test-pmcmc.R:239-267, tests/testthat/test-predict.R:129-141: a named
+    ``index$state`` names the rows of the saved trajectories and of what is predicted from
+    them (numpy arrays carry no row names: they come beside the arrays)."""
+    data = particle_filter_data({"day": sir_data["day"], "incidence": sir_data["incidence"]},
+                                "day", 4, 0)
+    control = pmcmc_control(5, n_chains=2, save_state=True, save_trajectories=True,
+                            use_parallel_seed=True)
+    out = {}
+    for key, state in (("plain", [1, 2, 3]), ("named", {"a": 1, "b": 2, "c": 3})):
+        f = particle_filter(data, OracleGenerator("sir"), 10, None, seed=1,
+                            index=lambda info, state=state: {"run": [4], "state": state})
+        out[key] = pmcmc(example_pars(), f, control=control)
+    assert out["plain"]["trajectories_names"] is None
+    assert out["named"]["trajectories_names"] == ["a", "b", "c"]
+    assert np.array_equal(out["plain"]["trajectories"], out["named"]["trajectories"])
+    steps = [400, 404, 408]
+    assert pmcmc_predict(out["plain"], steps, seed=1)["names"] is None
+    for prepend in (False, True):
+        y = pmcmc_predict(out["named"], steps, prepend_trajectories=prepend, seed=1)
+        assert y["names"] == ["a", "b", "c"] and y["state"].shape[0] == 3
