@@ -676,19 +676,31 @@ class particle_filter:
         self._last_history = None
         self._last_state = None
         self._last_restart_state = None
+        self._last_stages = None
 
     def run(self, pars=None, save_history=False, save_restart=None, min_log_likelihood=None):
         """R/particle_filter.R:313-317 -> filter_run -> filter_run_simple (:819-849)."""
         pars = {} if pars is None else pars
         if not isinstance(save_history, (bool, np.bool_)):
             raise TypeError("'save_history' must be a logical")
-        if isinstance(pars, multistage_parameters):
-            return self._run_multistage(pars, save_history, save_restart, min_log_likelihood)
-        if self.has_multiple_parameters:
+        multistage = isinstance(pars, multistage_parameters)
+        if self.has_multiple_parameters and not multistage:
             if isinstance(pars, dict):
                 raise ValueError("Expected an unnamed list of parameters for 'pars'")
             if len(pars) != self.n_parameters:
                 raise ValueError("'pars' must have length %d" % self.n_parameters)
+        # the number of stages is fixed by the first run: one model object per stage is
+        # kept between runs (particle_filter_check_multistage_pars, R/particle_filter.R:971-986)
+        n_stages = len(pars) if multistage else 1
+        if self._last_stages is not None and self._last_stages != n_stages:
+            if self._last_stages == 1:
+                raise ValueError("Expected single-stage parameters (but given one with %d stages)"
+                                 % n_stages)
+            raise ValueError("Expected multistage_pars with %d stages (but given one with %d)"
+                             % (self._last_stages, n_stages))
+        self._last_stages = n_stages
+        if multistage:
+            return self._run_multistage(pars, save_history, save_restart, min_log_likelihood)
         obj = self.run_begin(pars, save_history, save_restart, min_log_likelihood)
         obj.run()
         self._last_history = obj.history
