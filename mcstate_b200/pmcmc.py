@@ -273,7 +273,12 @@ class pmcmc_state:
 
     def __init__(self, pars, initial, filter, control, rng):
         if getattr(filter, "has_multiple_parameters", False):
-            raise ValueError("nested filters need pmcmc_parameters_nested (out of scope here)")
+            if not getattr(filter, "has_multiple_data", False):    # R/pmcmc_state.R:220-223
+                raise ValueError("Can't use a filter with multiple parameter sets but not "
+                                 "multiple data")
+            # R/pmcmc_state.R:225-227: these are simple (non-nested) parameters
+            raise ValueError("'pars' and 'filter' disagree on nestedness (nested filters need "
+                             "pmcmc_parameters_nested: out of scope here)")
         self._filter, self._pars, self._control, self._rng = filter, pars, control, rng
         self.n_filter_runs = 0
         self._curr_pars = np.array(initial, dtype=float)
@@ -389,8 +394,14 @@ class pmcmc_state:
         return out
 
 
-def pmcmc_run_chain(pars, initial, filter, control, rng):
-    """R/pmcmc.R:93-102."""
+def pmcmc_run_chain(pars, initial, filter, control, rng, n_threads=None):
+    """R/pmcmc.R:93-102: the thread count given, else the control's share per worker, is
+    set on the filter before the chain starts."""
+    if hasattr(filter, "set_n_threads"):
+        if n_threads is not None:
+            filter.set_n_threads(n_threads)
+        elif getattr(control, "n_threads_total", None) is not None:
+            filter.set_n_threads(control.n_threads_total // control.n_workers)
     obj = pmcmc_state(pars, initial, filter, control, rng)
     obj.run()
     return obj.finish()
@@ -550,9 +561,8 @@ def _chain_from_inputs(inputs, seed, pars, initial_k, control, device=None, n_th
     if device is not None and inputs.get("gpu_config") is not None:
         inputs["gpu_config"] = device
     f = particle_filter_from_inputs(inputs, seed["dust"])
-    if n_threads is not None:
-        f.set_n_threads(n_threads)
-    return pmcmc_run_chain(pars, initial_k, f, control, np.random.default_rng(seed["r"]))
+    return pmcmc_run_chain(pars, initial_k, f, control, np.random.default_rng(seed["r"]),
+                           n_threads)
 
 
 def _run_one(k, pars, initial, filter, control, seeds, device):
@@ -571,6 +581,7 @@ def pmcmc(pars, filter, initial=None, control=None):
     chains r, r + world, ... on its own GPU (``pmcmc_sharded``)."""
     if control is None:
         raise TypeError("'control' must be a pmcmc_control")
+    pmcmc_check_control(control)
     if control.n_workers > 1:
         return pmcmc_sharded(pars, filter, initial, control)
     initial = _check_initial(initial, pars, control.n_chains)

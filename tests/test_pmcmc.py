@@ -753,3 +753,48 @@ def test_names_on_pmcmc_output_and_predictions(sir_data):
     for prepend in (False, True):
         y = pmcmc_predict(out["named"], steps, prepend_trajectories=prepend, seed=1)
         assert y["names"] == ["a", "b", "c"] and y["state"].shape[0] == 3
+
+
+def test_thread_count_and_filter_kind_checks(sir_data):
+    """tests/testthat/test-pmcmc.R:413-428 (thread count via the control), :693-704 (a
+    replicated, non-nested filter is refused)."""
+    f = example_filter("oracle", sir_data, 30)
+    res = pmcmc(example_pars(), f, control=pmcmc_control(5, n_threads_total=2))
+    assert res["predict"]["filter"]["n_threads"] == 2
+    f.set_n_threads(1)
+    res = pmcmc(example_pars(), f, control=pmcmc_control(5))
+    assert res["predict"]["filter"]["n_threads"] == 1
+    data = particle_filter_data({"day": sir_data["day"], "incidence": sir_data["incidence"]},
+                                "day", 4, 0)
+    rep = particle_filter(data, OracleGenerator("sir"), 42, None, seed=1, n_parameters=3)
+    with pytest.raises(ValueError, match="Can't use a filter with multiple parameter sets but "
+                                         "not multiple data"):
+        pmcmc(example_pars(), rep, control=pmcmc_control(2))
+
+
+def test_rerun_every_reruns_the_filter(sir_data):
+    """tests/testthat/test-pmcmc.R:365-410: with rerun_every = 2 no likelihood value
+    survives more than two steps, and run() is called n_steps + 1 + n_steps // 2 times."""
+    pars = pmcmc_parameters([pmcmc_parameter("beta", 0.2, min=0, max=1, prior=lambda p: -23.0),
+                             pmcmc_parameter("gamma", 0.1, min=0, max=1, prior=lambda p: -23.0)],
+                            np.eye(2) * 1e-4 * 50)
+
+    def longest_run(x):
+        best = cur = 1
+        for a, b in zip(x, x[1:]):
+            cur = cur + 1 if a == b else 1
+            best = max(best, cur)
+        return best
+
+    for every, check in ((2, lambda n: n <= 2), (math.inf, lambda n: n > 5)):
+        control = pmcmc_control(30, save_state=True, save_trajectories=True, rerun_every=every,
+                                use_parallel_seed=True)
+        res = pmcmc(pars, example_filter("oracle", sir_data, 100), control=control)
+        assert check(longest_run(list(res["probabilities"][:, 1]))), every
+    calls = []
+    toy = _ToyFilter(lambda p: calls.append(1) or 1.0)
+    from mcstate_b200.pmcmc import pmcmc_run_chain
+
+    pmcmc_run_chain(_unit_square_pars(), [0.5, 0.5], toy,
+                    pmcmc_control(10, rerun_every=2, save_state=False), np.random.default_rng(1))
+    assert len(calls) == 16
