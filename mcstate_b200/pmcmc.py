@@ -33,17 +33,32 @@ from .particle_filter import particle_filter_from_inputs
 # parameters (R/pmcmc_parameters.R)
 # ---------------------------------------------------------------------------
 class pmcmc_parameter:
-    """``pmcmc_parameter(name, initial, min, max, discrete, integer, prior)``."""
+    """``pmcmc_parameter(name, initial, min, max, discrete, integer, prior)``
+    (R/pmcmc_parameters.R:56-108)."""
 
     def __init__(self, name, initial, min=-math.inf, max=math.inf, discrete=False,
-                 integer=False, prior=None):
-        if not (min <= initial <= max):
-            raise ValueError("'initial' must be within [min, max] for '%s'" % name)
+                 integer=False, prior=None, mean=None):
+        if discrete:
+            import warnings
+
+            warnings.warn("'discrete' is deprecated.\nUse 'integer' instead.", DeprecationWarning,
+                          stacklevel=2)
+        if initial < min:
+            raise ValueError("'initial' must be >= 'min' (%g)" % min)
+        if initial > max:
+            raise ValueError("'initial' must be <= 'max' (%g)" % max)
         self.name, self.initial, self.min, self.max = name, float(initial), float(min), float(max)
+        self.mean = self.initial if mean is None else float(mean)
         self.integer = bool(discrete or integer)
         self.prior = prior if prior is not None else (lambda p: 0.0)
-        if not math.isfinite(self.prior(self.initial)):
-            raise ValueError("Prior for '%s' is not finite at its initial value" % name)
+        try:
+            value = self.prior(self.initial)
+        except Exception as e:
+            raise ValueError("Prior function for '%s' failed to evaluate initial value: %s"
+                             % (name, e)) from None
+        if not math.isfinite(value):
+            raise ValueError("Prior function for '%s' returned a non-finite value on initial "
+                             "value" % name)
 
 
 def reflect_proposal(x, x_min, x_max):
@@ -87,15 +102,30 @@ class pmcmc_parameters:
     """``pmcmc_parameters$new(parameters, proposal, transform)`` (R/pmcmc_parameters.R)."""
 
     def __init__(self, parameters, proposal, transform=None):
+        given_names = None
+        if isinstance(parameters, dict):          # R: a named list
+            given_names, parameters = list(parameters), list(parameters.values())
+        if not isinstance(parameters, (list, tuple)):
+            raise TypeError("'parameters' must be a list")
         if len(parameters) == 0:
             raise ValueError("At least one parameter is required")
+        if not all(isinstance(p, pmcmc_parameter) for p in parameters):
+            raise TypeError("Expected all elements of '...' to be 'pmcmc_parameter' objects")
         self._p = list(parameters)
         names = [p.name for p in self._p]
-        if len(set(names)) != len(names):
-            raise ValueError("Duplicate parameter names")
+        dup = [n for k, n in enumerate(names) if n in names[:k]]
+        if dup:
+            raise ValueError("Duplicate parameter names: %s"
+                             % ", ".join("'%s'" % n for n in dict.fromkeys(dup)))
+        if given_names is not None and given_names != names:
+            raise ValueError("'parameters' is named, but the names do not match parameters")
+        if hasattr(proposal, "index") and hasattr(proposal, "columns"):   # pandas.DataFrame
+            if list(proposal.index) != names or list(proposal.columns) != names:
+                raise ValueError("Expected dimension names of 'proposal' to match parameters")
         proposal = np.asarray(proposal, dtype=float)
         if proposal.shape != (len(names), len(names)):
-            raise ValueError("Expected a square proposal matrix with %d rows" % len(names))
+            raise ValueError("Expected a square proposal matrix with %d rows and columns"
+                             % len(names))
         self._names = names
         self._vcv = proposal.copy()
         self._proposal = rmvnorm_generator(proposal)
@@ -111,6 +141,9 @@ class pmcmc_parameters:
         return np.array([p.initial for p in self._p])
 
     def prior(self, theta):
+        """By position, not by name (a dict's values are taken in its own order)."""
+        if isinstance(theta, dict):
+            theta = list(theta.values())
         return float(sum(p.prior(t) for p, t in zip(self._p, theta)))
 
     def propose(self, theta, rng, scale=1.0):
@@ -123,7 +156,7 @@ class pmcmc_parameters:
         return self._transform(dict(zip(self._names, (float(t) for t in theta))))
 
     def mean(self):
-        return np.array([getattr(p, "mean", p.initial) for p in self._p])
+        return np.array([p.mean for p in self._p])
 
     def vcv(self):
         return self._vcv.copy()

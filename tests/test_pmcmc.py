@@ -798,3 +798,86 @@ def test_rerun_every_reruns_the_filter(sir_data):
     pmcmc_run_chain(_unit_square_pars(), [0.5, 0.5], toy,
                     pmcmc_control(10, rerun_every=2, save_state=False), np.random.default_rng(1))
     assert len(calls) == 16
+
+
+def test_pmcmc_parameter_objects():
+    """tests/testthat/test-pmcmc-parameters.R:3-52, 160-255, 310-330."""
+    import warnings
+
+    p = pmcmc_parameter("a", 1, 0, 10)
+    assert (p.name, p.initial, p.min, p.max, p.integer, p.prior(1)) == ("a", 1.0, 0.0, 10.0, False, 0.0)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert pmcmc_parameter("a", 1, 0, 10, discrete=True).integer
+    assert "'discrete' is deprecated" in str(w[0].message)
+    f = lambda p: math.log(1 / p)  # noqa: E731
+    assert pmcmc_parameter("a", 1, prior=f).prior is f
+    for kw in ({}, {"min": 0}, {"max": 0}):
+        pmcmc_parameter("a", 0, **kw)
+    with pytest.raises(ValueError, match=r"'initial' must be >= 'min' \(1\)"):
+        pmcmc_parameter("a", 0, min=1)
+    with pytest.raises(ValueError, match=r"'initial' must be <= 'max' \(-1\)"):
+        pmcmc_parameter("a", 0, max=-1)
+    pmcmc_parameter("a", 10, prior=math.log)
+    with pytest.raises(ValueError, match="Prior function for 'a' returned a non-finite value on "
+                                         "initial value"):
+        pmcmc_parameter("a", 0, prior=lambda p: -math.inf)
+
+    def boom(p):
+        raise RuntimeError("an error")
+
+    with pytest.raises(ValueError, match="Prior function for 'a' failed to evaluate initial "
+                                         "value: an error"):
+        pmcmc_parameter("a", 0, prior=boom)
+    with pytest.raises(TypeError, match="'parameters' must be a list"):
+        pmcmc_parameters(None, np.eye(2))
+    with pytest.raises(ValueError, match="At least one parameter is required"):
+        pmcmc_parameters([], np.eye(2))
+    with pytest.raises(TypeError, match="to be 'pmcmc_parameter' objects"):
+        pmcmc_parameters([1, 2], np.eye(2))
+    pars = [pmcmc_parameter("beta", 0.2), pmcmc_parameter("gamma", 0.1)]
+    for bad in (np.eye(1), np.eye(3), np.zeros((3, 2))):
+        with pytest.raises(ValueError,
+                           match="Expected a square proposal matrix with 2 rows and columns"):
+            pmcmc_parameters(pars, bad)
+    with pytest.raises(ValueError, match="Duplicate parameter names: 'a'"):
+        pmcmc_parameters([pmcmc_parameter("a", 0.2), pmcmc_parameter("a", 0.1)], np.ones((2, 2)))
+    six = [pmcmc_parameter(n, 0.1) for n in "aaabcc"]
+    with pytest.raises(ValueError, match="Duplicate parameter names: 'a', 'c'"):
+        pmcmc_parameters(six, np.ones((6, 6)))
+    ab = [pmcmc_parameter("a", 0.2), pmcmc_parameter("b", 0.1)]
+    pmcmc_parameters({"a": ab[0], "b": ab[1]}, np.ones((2, 2)))
+    with pytest.raises(ValueError,
+                       match="'parameters' is named, but the names do not match parameters"):
+        pmcmc_parameters({"b": ab[0], "a": ab[1]}, np.ones((2, 2)))
+
+
+def test_pmcmc_parameters_propose_transform_prior():
+    """tests/testthat/test-pmcmc-parameters.R:55-157."""
+    from mcstate_b200.pmcmc import rmvnorm_generator
+
+    kernel = np.eye(2) * 1e-4
+    p = example_pars().__class__(
+        [pmcmc_parameter("beta", 0.2, min=0, max=1, prior=lambda p: math.log(1e-10)),
+         pmcmc_parameter("gamma", 0.1, min=0, max=1, prior=lambda p: math.log(1e-10))], kernel)
+    p0 = p.initial()
+    assert np.array_equal(p0, [0.2, 0.1])
+    p1 = p.propose(p0, np.random.default_rng(1))
+    p2 = p.propose(p0, np.random.default_rng(1), 10)
+    assert np.array_equal(p1, rmvnorm_generator(kernel)(p0, np.random.default_rng(1)))
+    assert np.allclose(p2 - p0, (p1 - p0) * math.sqrt(10), rtol=1e-12, atol=0)
+    assert p.model(p0) == {"beta": 0.2, "gamma": 0.1}
+    assert p.model(p0 + 0.5) == pytest.approx({"beta": 0.7, "gamma": 0.6})
+    transform = lambda d: {"alpha": d["beta"] + d["gamma"], "gamma": [d["gamma"]] * 4,  # noqa: E731
+                           "beta": d["beta"]}
+    dexp = lambda x: -x  # noqa: E731
+    dnorm = lambda x: -0.5 * x * x - 0.5 * math.log(2 * math.pi)  # noqa: E731
+    q = pmcmc_parameters([pmcmc_parameter("beta", 0.2, prior=dexp),
+                          pmcmc_parameter("gamma", 0.1, prior=dnorm)], np.eye(2), transform)
+    got = q.model(q.initial())
+    assert got["alpha"] == pytest.approx(0.3) and got["gamma"] == [0.1] * 4 and got["beta"] == 0.2
+    assert q.prior(q.initial()) == pytest.approx(dexp(0.2) + dnorm(0.1))
+    assert q.prior([0.2, 0.1]) == pytest.approx(dexp(0.2) + dnorm(0.1))       # by position
+    assert q.prior({"beta": 1, "gamma": 0}) == pytest.approx(dexp(1) + dnorm(0))
+    assert [r["name"] for r in p.summary()] == ["beta", "gamma"]
+    assert all(r["min"] == 0 and r["max"] == 1 and not r["integer"] for r in p.summary())
