@@ -881,3 +881,30 @@ def test_pmcmc_parameters_propose_transform_prior():
     assert q.prior({"beta": 1, "gamma": 0}) == pytest.approx(dexp(1) + dnorm(0))
     assert [r["name"] for r in p.summary()] == ["beta", "gamma"]
     assert all(r["min"] == 0 and r["max"] == 1 and not r["integer"] for r in p.summary())
+
+
+def test_rmvnorm_generator_reference_cases():
+    """tests/testthat/test-utils.R:26-72."""
+    from mcstate_b200.pmcmc import rmvnorm_generator
+
+    for bad in (np.array([[1.0, 3.0], [2.0, 4.0]]), np.ones((2, 6))):
+        with pytest.raises(ValueError, match="vcv must be symmetric"):
+            rmvnorm_generator(bad)
+    with pytest.raises(ValueError, match="vcv must be positive definite"):
+        rmvnorm_generator(np.array([[1.0, 2.0], [2.0, 1.0]]))
+    n = 10
+    vcv = np.cov(np.random.default_rng(1).normal(size=(n, n)), rowvar=False)
+    i = [1, 4]
+    vcv[i, :] = 0
+    vcv[:, i] = 0
+    f = rmvnorm_generator(vcv)
+    gen = np.random.default_rng(2)
+    res = np.array([f(np.zeros(n), gen) for _ in range(100)])
+    assert np.all(res[:, i] == 0) and np.all(res[:, [0, 2, 3]] != 0)
+    vcv = np.array([[4.0, 2.0], [2.0, 3.0]])
+    theta = np.random.default_rng(3).uniform(size=2)
+    y1 = rmvnorm_generator(vcv)(theta, np.random.default_rng(1))
+    y2 = rmvnorm_generator(vcv)(theta, np.random.default_rng(1), 2)
+    y3 = rmvnorm_generator(vcv * 2)(theta, np.random.default_rng(1))
+    assert np.allclose((y1 - theta) * math.sqrt(2), y2 - theta, rtol=1e-12, atol=0)
+    assert np.allclose(y2, y3, rtol=1e-12, atol=1e-15)
