@@ -440,20 +440,52 @@ def pmcmc_run_chain(pars, initial, filter, control, rng, n_threads=None):
     return obj.finish()
 
 
-def pmcmc_combine(samples):
-    """R/pmcmc_tools.R:104-156: stack chains, remembering which sample came from which."""
+def pmcmc_combine(*args, samples=None):
+    """``pmcmc_combine(..., samples = list(...))`` (R/pmcmc_tools.R:104-190): stack chains,
+    remembering which sample came from which; the chains must agree in length, iterations,
+    parameters and in what they saved."""
+    if samples is None:
+        samples = list(args[0]) if len(args) == 1 and isinstance(args[0], (list, tuple)) \
+            else list(args)
+    elif isinstance(samples, dict):
+        samples = list(samples.values())        # names are ignored
+    elif not isinstance(samples, (list, tuple)):
+        raise TypeError("'samples' must be a list")
+    samples = list(samples)
+    if any(not (isinstance(x, dict) and "pars" in x and "iteration" in x) for x in samples):
+        raise TypeError("Elements of '...' must be all be 'mcstate_pmcmc' objects")
+    if len(samples) < 2:
+        raise ValueError("At least 2 samples objects must be provided")
+    if any(x.get("chain") is not None for x in samples):
+        raise ValueError("Chains have already been combined")
+    if len({np.asarray(x["pars"]).shape[0] for x in samples}) != 1:
+        raise ValueError("All chains must have the same length")
+    if any(x["pars_names"] != samples[0]["pars_names"]
+           or np.asarray(x["pars"]).shape[1] != np.asarray(samples[0]["pars"]).shape[1]
+           for x in samples):
+        raise ValueError("All parameters must have the same dimension names")
+    if any(not np.array_equal(x["iteration"], samples[0]["iteration"]) for x in samples):
+        raise ValueError("All chains must have the same iterations")
+    for key in ("state", "trajectories", "restart"):
+        have = [x.get(key) is not None for x in samples]
+        if any(have) and not all(have):
+            raise ValueError("If '%s' is present for any samples, it must be present for all"
+                             % key)
+    if any(not np.array_equal(x.get("trajectories_time"), samples[0].get("trajectories_time"))
+           for x in samples):
+        raise ValueError("trajectories data is inconsistent")
     out = {"pars_names": samples[0]["pars_names"]}
     for key in ("pars", "probabilities", "iteration"):
         out[key] = np.concatenate([s[key] for s in samples], axis=0)
-    out["chain"] = np.concatenate([np.full(s["pars"].shape[0], k + 1)
+    out["chain"] = np.concatenate([np.full(np.asarray(s["pars"]).shape[0], k + 1)
                                    for k, s in enumerate(samples)])
     for key in ("state", "trajectories", "restart"):
-        parts = [s[key] for s in samples]
+        parts = [s.get(key) for s in samples]
         out[key] = None if any(p is None for p in parts) else np.concatenate(parts, axis=1)
-    out["n_filter_runs"] = int(sum(s["n_filter_runs"] for s in samples))
+    out["n_filter_runs"] = int(sum(s.get("n_filter_runs", 0) for s in samples))
     # the last chain's, as R/pmcmc_tools.R:148-152
     out["predict"] = samples[-1].get("predict")
-    if "trajectories_time" in samples[-1]:
+    if samples[-1].get("trajectories_time") is not None:
         out["trajectories_time"] = samples[-1]["trajectories_time"]
         out["trajectories_names"] = samples[-1].get("trajectories_names")
     return out
@@ -624,7 +656,7 @@ def pmcmc(pars, filter, initial=None, control=None):
                            getattr(filter.model, "algorithm", "xoshiro256plus"))
     samples = [_run_one(k, pars, initial, filter, control, seeds, None)
                for k in range(control.n_chains)]
-    return samples[0] if control.n_chains == 1 else pmcmc_combine(samples)
+    return samples[0] if control.n_chains == 1 else pmcmc_combine(samples=samples)
 
 
 def pmcmc_parallel_threads(n_threads_total, n_workers, n_chains):
@@ -679,7 +711,7 @@ def pmcmc_sharded(pars, filter, initial=None, control=None, group=None, device=N
         if smp.get("predict") is not None:
             seed = smp["predict"].pop("seed")
             smp["predict"].update(transform=pars.model, filter=dict(filter.inputs(), seed=seed))
-    return samples[0] if control.n_chains == 1 else pmcmc_combine(samples)
+    return samples[0] if control.n_chains == 1 else pmcmc_combine(samples=samples)
 
 
 # ---------------------------------------------------------------------------
@@ -790,7 +822,7 @@ def pmcmc_chains_collect(path):
             from .dust import dust_repair_environment
 
             dust_repair_environment(smp["predict"]["filter"]["model"])
-    return samples[0] if control.n_chains == 1 else pmcmc_combine(samples)
+    return samples[0] if control.n_chains == 1 else pmcmc_combine(samples=samples)
 
 
 def pmcmc_chains_cleanup(path):

@@ -908,3 +908,58 @@ def test_rmvnorm_generator_reference_cases():
     y3 = rmvnorm_generator(vcv * 2)(theta, np.random.default_rng(1))
     assert np.allclose((y1 - theta) * math.sqrt(2), y2 - theta, rtol=1e-12, atol=0)
     assert np.allclose(y2, y3, rtol=1e-12, atol=1e-15)
+
+
+def test_pmcmc_combine(sir_data):
+    """tests/testthat/test-pmcmc-tools.R:71-272."""
+    from mcstate_b200.pmcmc import pmcmc_combine
+
+    control = pmcmc_control(10, save_state=True, save_trajectories=True, save_restart=[40],
+                            use_parallel_seed=True)
+    results = [pmcmc(example_pars(), example_filter("oracle", sir_data, 10, seed=k), control=control)
+               for k in (1, 2, 3)]
+    res = pmcmc_combine(*results)
+    assert res["pars"].shape == (30, 2) and res["probabilities"].shape == (30, 3)
+    assert res["state"].shape == (5, 30) and res["trajectories"].shape == (3, 30, 101)
+    assert res["restart"].shape == (5, 30, 1)
+    assert list(res["chain"]) == [1] * 10 + [2] * 10 + [3] * 10
+    i = slice(10, 20)
+    assert np.array_equal(res["pars"][i], results[1]["pars"])
+    assert np.array_equal(res["state"][:, i], results[1]["state"])
+    assert np.array_equal(res["trajectories"][:, i], results[1]["trajectories"])
+    assert np.array_equal(res["restart"][:, i], results[1]["restart"])
+    for other in (pmcmc_combine(samples=results), pmcmc_combine(results),
+                  pmcmc_combine(samples={"a": results[0], "b": results[1], "c": results[2]})):
+        assert all(np.array_equal(res[k], other[k]) for k in ("pars", "chain", "state", "iteration"))
+    bare = [dict(r, state=None, trajectories=None, predict=None) for r in results]
+    comb = pmcmc_combine(samples=bare)
+    assert comb["state"] is None and comb["trajectories"] is None and comb["predict"] is None
+    assert np.array_equal(comb["pars"], res["pars"])
+    for bad, msg in (((), "At least 2 samples objects must be provided"),
+                     ((results[0],), "At least 2 samples objects must be provided")):
+        with pytest.raises(ValueError, match=msg):
+            pmcmc_combine(*bad)
+    with pytest.raises(TypeError, match="'samples' must be a list"):
+        pmcmc_combine(samples=3)
+    with pytest.raises(ValueError, match="Chains have already been combined"):
+        pmcmc_combine(results[0], pmcmc_combine(results[1], results[2]))
+    with pytest.raises(ValueError, match="All chains must have the same length"):
+        pmcmc_combine(results[0], pmcmc_thin(results[1], burnin=2))
+    wide = dict(results[0], pars=np.hstack([results[0]["pars"], np.ones((10, 1))]),
+                pars_names=["beta", "gamma", "zeta"])
+    with pytest.raises(ValueError, match="All parameters must have the same dimension names"):
+        pmcmc_combine(wide, results[1])
+    with pytest.raises(ValueError, match="All chains must have the same iterations"):
+        pmcmc_combine(dict(results[0], iteration=results[0]["iteration"] + 1), results[1])
+    for key in ("state", "trajectories", "restart"):
+        with pytest.raises(ValueError, match="If '%s' is present for any samples, it must be "
+                                             "present for all" % key):
+            pmcmc_combine(dict(results[0], **{key: None}), results[1])
+    with pytest.raises(ValueError, match="trajectories data is inconsistent"):
+        pmcmc_combine(dict(results[0], trajectories_time=results[0]["trajectories_time"] + 1),
+                      results[1])
+    for bad in ((results[0], None),):
+        with pytest.raises(TypeError, match="Elements of"):
+            pmcmc_combine(*bad)
+    with pytest.raises(TypeError, match="Elements of"):
+        pmcmc_combine(samples=[results[0], None])
