@@ -71,3 +71,36 @@ def test_constant_log_likelihood_leaves_history_alone(sir_data):
         out.append((p.run(PARS, save_history=True), p.history(), p.state()))
     assert np.allclose(out[1][0], out[0][0] + np.array([-2.0, -3.0]), rtol=0, atol=1e-12)
     assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
+
+
+def test_nested_initial_states(sir_data):
+    """tests/testthat/test-particle-filter.R:1096-1123 (a matrix per population becomes the
+    first slice of the history), :1170-1183 (a vector is recycled over the particles)."""
+    n = 100
+    dat = example_sir(sir_data)
+    day = sir_data["day"][:20]
+    data = particle_filter_data({"day": np.concatenate([day, day]),
+                                 "incidence": np.full(40, np.nan),       # no shuffling occurs
+                                 "population": np.repeat(["a", "b"], 20)},
+                                "day", 4, 0, population="population")
+
+    def initial(info, n_particles, pars):
+        y = np.zeros((5, n_particles))
+        i0 = np.random.default_rng(1).poisson(pars["I0"], n_particles)
+        y[0] = 1100 - i0
+        y[1] = i0
+        return y
+
+    pars = [{"I0": 10, "beta": 0.2, "gamma": 0.1}, {"I0": 20, "beta": 0.3, "gamma": 0.1}]
+    for compare in (dat["compare"], None):
+        p = particle_filter(data, OracleGenerator("sir"), n, compare, index=dat["index"],
+                            initial=initial, seed=1)
+        p.run(pars, save_history=True)
+        h = p.history()
+        assert np.array_equal(h[:, :, 0, 0], initial(None, n, pars[0])[:3])
+        assert np.array_equal(h[:, :, 1, 0], initial(None, n, pars[1])[:3])
+    p = particle_filter(_nested(sir_data), OracleGenerator("sir"), 42, None, index=dat["index"],
+                        initial=lambda info, n_particles, pars: [1000.0, 0, 0, 0, 0], seed=1)
+    ll = p.run(PARS)
+    assert ll.shape == (2,)
+    assert np.all(p.state()[0] == 1000.0) and np.all(p.state()[1:4] == 0)   # nobody infected
