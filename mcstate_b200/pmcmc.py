@@ -399,6 +399,9 @@ class pmcmc_state:
         out = {
             "pars": np.array(self._h_pars)[keep],
             "probabilities": np.array(self._h_prob)[keep],
+            # every step, kept or not (the reference's results$pars_full: R/pmcmc_utils.R:100-121)
+            "pars_full": np.array(self._h_pars),
+            "probabilities_full": np.array(self._h_prob),
             "pars_names": self._pars.names(),
             "iteration": np.array(keep) + 1,
             "chain": None,
@@ -479,6 +482,9 @@ def pmcmc_combine(*args, samples=None):
         out[key] = np.concatenate([s[key] for s in samples], axis=0)
     out["chain"] = np.concatenate([np.full(np.asarray(s["pars"]).shape[0], k + 1)
                                    for k, s in enumerate(samples)])
+    for key in ("pars_full", "probabilities_full"):
+        parts = [s.get(key) for s in samples]
+        out[key] = None if any(p is None for p in parts) else np.concatenate(parts, axis=0)
     for key in ("state", "trajectories", "restart"):
         parts = [s.get(key) for s in samples]
         out[key] = None if any(p is None for p in parts) else np.concatenate(parts, axis=1)
@@ -503,6 +509,8 @@ def pmcmc_filter(object, i):
     for key in ("state", "trajectories", "restart"):     # samples along the second axis
         if out.get(key) is not None:
             out[key] = np.asarray(out[key])[:, i]
+    # the full chain does not survive a filter (R/pmcmc_tools.R:85-86)
+    out["pars_full"] = out["probabilities_full"] = None
     return out
 
 

@@ -963,3 +963,32 @@ def test_pmcmc_combine(sir_data):
             pmcmc_combine(*bad)
     with pytest.raises(TypeError, match="Elements of"):
         pmcmc_combine(samples=[results[0], None])
+
+
+def test_filter_on_creation_after_combining(sir_data):
+    """tests/testthat/test-pmcmc.R:648-690: the retained samples of a 2-chain run equal the
+    full run filtered at those iterations; the full parameter chain stays available until
+    the samples are filtered."""
+    from mcstate_b200.pmcmc import pmcmc_filter
+
+    def run(**kw):
+        control = pmcmc_control(30, n_chains=2, save_state=True, save_trajectories=True,
+                                use_parallel_seed=True, **kw)
+        return pmcmc(example_pars(), example_filter("oracle", sir_data, 10), control=control), control
+
+    r1, c1 = run()
+    r2, c2 = run(n_burnin=3, n_steps_retain=7)
+    assert r2["pars"].shape == (14, 2)
+    assert np.array_equal(r1["pars_full"], r1["pars"])
+    assert np.array_equal(r1["probabilities_full"], r1["probabilities"])
+    assert np.array_equal(r2["pars_full"], r1["pars"])
+    assert np.array_equal(r2["probabilities_full"], r1["probabilities"])
+    assert list(r1["iteration"]) == list(range(1, 31)) * 2
+    i = np.array([c2.n_burnin + 1 + k * c2.n_steps_every for k in range(c2.n_steps_retain)])
+    assert list(r2["iteration"]) == list(i) * 2
+    cmp = pmcmc_filter(r1, np.concatenate([i, i + c1.n_steps]) - 1)
+    for key in ("pars", "probabilities", "state", "trajectories", "chain", "iteration"):
+        assert np.array_equal(r2[key], cmp[key]), key
+    assert cmp["pars_full"] is None
+    r3 = pmcmc_thin(r2)
+    assert np.array_equal(r3["pars"], r2["pars"]) and r3["pars_full"] is None
