@@ -137,7 +137,7 @@ class dust_model:
 
     def __init__(self, generator, pars, time, n_particles, n_threads=1, seed=None,
                  pars_multi=False, deterministic=False, gpu_config=None, seed_per_set=False):
-        L = self._L = generator._L   # the library that holds this generator's model
+        L = self._L = generator._library()   # the library that holds this generator's model
         self._ck = generator._check
         self._gen = generator
         self._n_threads = int(n_threads)
@@ -579,11 +579,21 @@ class dust_generator:
     def __setstate__(self, d):
         self.__dict__.update(d)
         self.public_methods = self
-        dust_repair_environment(self)
+        try:
+            dust_repair_environment(self)
+        except Exception:
+            # no engine here (e.g. results collected on a machine without the library):
+            # the description survives, the library is bound when something needs it
+            self._L = None
+
+    def _library(self):
+        if self._L is None:
+            dust_repair_environment(self)
+        return self._L
 
     def _check(self, rc):
         if rc != _lib.OK:
-            msg = self._L.mcb_last_error()
+            msg = self._library().mcb_last_error()
             raise _lib.McbError(rc, msg.decode() if msg else "mcstate_b200 error %d" % rc)
 
     # -- static capability queries
@@ -603,7 +613,7 @@ class dust_generator:
         return self.algorithm
 
     def gpu_info(self):
-        L, check = self._L, self._check
+        L, check = self._library(), self._check
         n = C.c_int(0)
         rc = L.mcb_device_count(C.byref(n))
         devices = []

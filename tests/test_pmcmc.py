@@ -992,3 +992,27 @@ def test_filter_on_creation_after_combining(sir_data):
     assert cmp["pars_full"] is None
     r3 = pmcmc_thin(r2)
     assert np.array_equal(r3["pars"], r2["pars"]) and r3["pars_full"] is None
+
+
+def test_generator_unpickles_without_the_engine(monkeypatch):
+    """Results that carry a generator (``predict``) can be read where the engine library is
+    not available; the library is bound when something first needs it."""
+    import pickle
+
+    import cloudpickle
+
+    from mcstate_b200 import _lib, dust
+
+    g = dust.dust_example("sir")
+    blob = cloudpickle.dumps(g)
+
+    def missing():
+        raise RuntimeError("libmcstate_b200.so is missing")
+
+    monkeypatch.setattr(_lib, "lib", missing)
+    h = pickle.loads(blob)
+    assert h._L is None and h.par_names == g.par_names and h.has_compare()
+    with pytest.raises(RuntimeError, match="is missing"):
+        h.gpu_info()
+    monkeypatch.undo()
+    assert isinstance(h.gpu_info(), dict) and h._L is g._L
