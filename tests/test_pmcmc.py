@@ -1016,3 +1016,26 @@ def test_generator_unpickles_without_the_engine(monkeypatch):
         h.gpu_info()
     monkeypatch.undo()
     assert isinstance(h.gpu_info(), dict) and h._L is g._L
+
+
+def test_pmcmc_result_layout(sir_data):
+    """tests/testthat/test-pmcmc.R:88-166: what a chain returns (R's nested list
+    ``trajectories$state/time/rate`` is flat here: ``trajectories``, ``trajectories_time``,
+    ``predict["rate"]``)."""
+    f = example_filter("oracle", sir_data, 100)
+    res = pmcmc(example_pars(), f, control=pmcmc_control(30, save_state=True, save_trajectories=True,
+                                                        use_parallel_seed=True))
+    assert res["chain"] is None and list(res["iteration"]) == list(range(1, 31))
+    assert res["pars"].shape == (30, 2) and res["pars_names"] == ["beta", "gamma"]
+    assert res["probabilities"].shape == (30, 3)       # log prior, likelihood, posterior
+    assert np.any(np.diff(res["pars"], axis=0) != 0)   # it mixed
+    assert res["state"].shape == (5, 30) and res["trajectories"].shape == (3, 30, 101)
+    assert np.array_equal(res["trajectories"][:, :, -1], res["state"][:3])
+    assert np.array_equal(res["trajectories_time"], np.arange(0, 401, 4))
+    pred = res["predict"]
+    assert set(pred) == {"is_continuous", "transform", "index", "rate", "model_time", "time",
+                         "filter"}
+    assert pred["index"] == [1, 2, 3] and pred["rate"] == 4
+    assert pred["time"] == 400 and pred["model_time"] == 100 and not pred["is_continuous"]
+    assert pred["transform"]([0.2, 0.1]) == {"beta": 0.2, "gamma": 0.1}
+    assert pred["filter"]["n_particles"] == 100 and len(pred["filter"]["seed"]) == 32
