@@ -37,11 +37,12 @@ UNIT = "particle-steps/s"
 # unfused pipeline (K1 152 + K2 8 + K3 20 + K4 84).  The engine fuses K3+K4 into K1's load,
 # so the bytes its kernels must move are fewer; the per-kernel roofline uses THESE (the
 # conservative figure), the whole-interval fraction uses the survey's 264 B.
-#   k_run_compare : state in 40 (gathered) + rng in 32 + cumulative-weight probe 8
-#                   + state out 40 + rng out 32 + logw out 8                      = 160
+#   k_run_compare : ancestor index 4 + state in 40 (gathered) + rng in 32
+#                   + state out 40 + rng out 32 + logw out 8                      = 156
 #   k_weights_scan: logw in 8 + cumulative weight out 8                           = 16
-#   k_finish_state: (once per filter call) probe 8 + state in 40 + state out 40   = 88
-BYTES_K1, BYTES_K2, BYTES_FINISH = 160, 16, 88
+#   k_ancestors   : cumulative weight in 8 + ancestor index out 4                 = 12
+#   k_finish_state: (once per filter call) index 4 + state in 40 + state out 40   = 84
+BYTES_K1, BYTES_K2, BYTES_K3, BYTES_FINISH = 156, 16, 12, 84
 BYTES_INTERVAL = 264
 
 
@@ -354,9 +355,9 @@ def run_engine(args):
 
     if rank == 0:
         peak, peak_kind = measured_peak_gbs()
-        names = ["k_run_compare", "k_weights_scan", "unused", "k_finish_state"]
-        per_launch_bytes = [BYTES_K1 * N_PARTICLES, BYTES_K2 * N_PARTICLES, 0,
-                            BYTES_FINISH * N_PARTICLES]
+        names = ["k_run_compare", "k_weights_scan", "k_ancestors", "k_finish_state"]
+        per_launch_bytes = [BYTES_K1 * N_PARTICLES, BYTES_K2 * N_PARTICLES,
+                            BYTES_K3 * N_PARTICLES, BYTES_FINISH * N_PARTICLES]
         kernels = {}
         busy_ms = float(sum(k_ms[k] for k in range(len(names)) if k_n[k]))
         for k, name in enumerate(names):

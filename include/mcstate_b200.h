@@ -227,6 +227,12 @@ int mcb_set_persistent(mcb_model *m, int enable);
  * returns as soon as the work is queued, collect waits and copies out */
 int mcb_filter_enqueue(mcb_model *m, uint64_t time_end);
 int mcb_filter_collect(mcb_model *m, double *log_likelihood);
+/* Device address of the log-likelihood vector [n_pars] the enqueued filter writes
+ * (valid in stream order after mcb_filter_enqueue, until the next filter call): a
+ * sharded caller hands it straight to its all-gather on the handle's stream instead
+ * of a device -> host -> device round trip per data row (R/smc2.R:89-108 gathers one
+ * step likelihood per parameter particle per row). */
+int mcb_log_likelihood_device(mcb_model *m, double **device_ptr);
 /* number of kernels launched by this handle so far (bench.py: gpu_launches) */
 int mcb_launch_count(const mcb_model *m, uint64_t *n);
 /*

@@ -82,6 +82,7 @@ SIGNATURES = {
     "mcb_set_persistent": (C.c_int, [handle_p, C.c_int]),
     "mcb_filter_enqueue": (C.c_int, [handle_p, C.c_uint64]),
     "mcb_filter_collect": (C.c_int, [handle_p, f64p]),
+    "mcb_log_likelihood_device": (C.c_int, [handle_p, C.POINTER(C.c_void_p)]),
     "mcb_launch_count": (C.c_int, [handle_p, u64p]),
     "mcb_set_kernel_timing": (C.c_int, [handle_p, C.c_int]),
     "mcb_kernel_timing": (C.c_int, [handle_p, f64p, u64p]),

@@ -13,6 +13,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <set>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -121,18 +122,6 @@ constexpr size_t kMaxWalkRows = 2048;  // counts covered by a walk table (sample
 
 size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
 
-int ceil_log2(size_t n) {
-  int k = 0;
-  while (((size_t)1 << k) < n) ++k;
-  return k;
-}
-
-// fractional bits of a fixed-point weight: n of them must sum below 2^63
-int weight_shift(size_t n) {
-  int k = 62 - ceil_log2(n);
-  return k > 52 ? 52 : k;
-}
-
 // per-device table of jump-matrix powers, built once
 struct JumpCache {
   std::mutex mu;
@@ -151,10 +140,14 @@ int device_constants(int device) {
   inv[0] = make_double2(0.0, 0.0);
   for (int k = 1; k < mcb::kInvSmall; ++k) inv[k] = make_double2((double)k, 1.0 / (double)k);
   MCB_CUDA(cudaMemcpyToSymbol(mcb::c_inv_small, inv, sizeof inv));
-  double2 inv_g[mcb::kInvSmall + 1];
-  for (int k = 0; k < mcb::kInvSmall; ++k) inv_g[k] = inv[k];
-  inv_g[mcb::kInvSmall] = inv[mcb::kInvSmall - 1];
-  MCB_CUDA(cudaMemcpyToSymbol(mcb::g_inv_small, inv_g, sizeof inv_g));
+  // the fast walk's tables (samplers.cuh): 1/k and 2^(j/32); approximations are enough
+  double recip[mcb::kInvSmall];
+  recip[0] = 0.0;
+  for (int k = 1; k < mcb::kInvSmall; ++k) recip[k] = 1.0 / (double)k;
+  MCB_CUDA(cudaMemcpyToSymbol(mcb::c_recip, recip, sizeof recip));
+  double exp2_tab[mcb::kExp2Tab];
+  for (int j = 0; j < mcb::kExp2Tab; ++j) exp2_tab[j] = std::exp2((double)j / mcb::kExp2Tab);
+  MCB_CUDA(cudaMemcpyToSymbol(mcb::g_exp2_tab, exp2_tab, sizeof exp2_tab));
   done[device] = true;
   return MCB_OK;
 }
@@ -175,12 +168,16 @@ int jump_table_device(int device, uint64_t **out) {
   return MCB_OK;
 }
 
+// What a captured filter graph depends on besides the handle's buffers: the row range and
+// options, and -- baked into the kernel arguments at capture -- the model step the call
+// starts at and the incidence-reset schedule of every launch (from the parameters' freq).
 struct GraphKey {
   int row_first, row_last, hist, n_snap, n_min;
-  uint64_t snap_hash;
+  uint64_t snap_hash, time, sched_hash;
   bool operator<(const GraphKey &o) const {
-    return std::tie(row_first, row_last, hist, n_snap, n_min, snap_hash) <
-           std::tie(o.row_first, o.row_last, o.hist, o.n_snap, o.n_min, o.snap_hash);
+    return std::tie(row_first, row_last, hist, n_snap, n_min, snap_hash, time, sched_hash) <
+           std::tie(o.row_first, o.row_last, o.hist, o.n_snap, o.n_min, o.snap_hash, o.time,
+                    o.sched_hash);
   }
 };
 
@@ -239,7 +236,9 @@ struct mcb_model {
 
   cudaStream_t own_stream = nullptr, stream = nullptr;
   std::map<GraphKey, GraphEntry> graphs;
+  std::set<GraphKey> graph_seen;   // keys launched directly once (a graph from the second use)
   uint64_t launches = 0;
+  cudaError_t launch_error = cudaSuccess;   // first failed chained launch since the last check
 
   // optional per-kernel timing (bench.py roofline): 5 events per data row
   bool timing = false;
@@ -256,10 +255,19 @@ namespace {
 
 using mcb::View;
 
+// a chained launch (launch_chained) that failed since the last check
+int check_launches(mcb_model *m) {
+  if (m->launch_error == cudaSuccess) return MCB_OK;
+  const cudaError_t le = m->launch_error;
+  m->launch_error = cudaSuccess;
+  return fail(MCB_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(le));
+}
+
 void clear_graphs(mcb_model *m) {
   for (auto &g : m->graphs)
     if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
   m->graphs.clear();
+  m->graph_seen.clear();
 }
 
 int ensure_stage(mcb_model *m, size_t bytes) {
@@ -302,6 +310,7 @@ uint32_t reset_mask(const mcb_model *m, uint64_t t0, uint32_t n_steps, int *vali
 template <class... P, class... A>
 void launch_chained(mcb_model *m, bool chained, void (*kernel)(P...), unsigned grid, int threads,
                     A... args) {
+  if (m->launch_error != cudaSuccess) return;   // reported by the caller (check_launches)
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3((unsigned)threads);
@@ -311,64 +320,76 @@ void launch_chained(mcb_model *m, bool chained, void (*kernel)(P...), unsigned g
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = chained ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+  const cudaError_t err = cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+  if (err != cudaSuccess) m->launch_error = err;
   ++m->launches;
 }
 
 template <class M, int SCR>
 void launch_run_compare(mcb_model *m, const double *y_in, double *y_out, uint64_t t0,
-                        uint32_t n_steps, int prev_row, int row, double *hist, int *kappa_out) {
+                        uint32_t n_steps, const int *kappa, int row, double *hist) {
   const unsigned grid = blocks_for(m->v.n_total, mcb::kRunThreads);
-  // the run kernel needs ~4 KB of shared memory per block (12 blocks per SM): ask for a
+  // the run kernel needs ~1.5 KB of shared memory per block (12 blocks per SM): ask for a
   // small carve-out so the walk tables keep more of L1 (measured: 20 % beats the default
-  // by 1 %, 10 % costs occupancy, 50 % loses 4 %).  MCB_CARVEOUT overrides.
+  // by 1 %, 10 % costs occupancy, 50 % loses 4 %).  MCB_CARVEOUT overrides.  The
+  // attribute is per device: set once for every device this instantiation runs on.
   static const int carve = getenv("MCB_CARVEOUT") ? atoi(getenv("MCB_CARVEOUT")) : 20;
-  static bool carved = false;   // per instantiation
-  if (!carved) {
-    cudaFuncSetAttribute(mcb::k_run_compare<M, SCR, false>,
-                         cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-    cudaFuncSetAttribute(mcb::k_run_compare<M, SCR, true>,
-                         cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-    carved = true;
+  static std::mutex mu;
+  static std::map<int, bool> carved;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!carved[m->device]) {
+      cudaFuncSetAttribute(mcb::k_run_compare<M, SCR, false>,
+                           cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+      cudaFuncSetAttribute(mcb::k_run_compare<M, SCR, true>,
+                           cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+      carved[m->device] = true;
+    }
   }
   m->v.reset_mask = reset_mask(m, t0, n_steps, &m->v.reset_mask_valid);
   if (hist)
     launch_chained(m, m->chain, mcb::k_run_compare<M, SCR, true>, grid, mcb::kRunThreads, m->v,
-                   y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out);
+                   y_in, y_out, t0, n_steps, kappa, row, hist);
   else
     launch_chained(m, m->chain, mcb::k_run_compare<M, SCR, false>, grid, mcb::kRunThreads, m->v,
-                   y_in, y_out, t0, n_steps, prev_row, row, (double *)nullptr, (int *)nullptr);
+                   y_in, y_out, t0, n_steps, kappa, row, (double *)nullptr);
 }
 
-// K1: [resample prev_row on load] -> n_steps updates -> compare against `row`
+// K1: [gather by kappa on load] -> n_steps updates -> compare against `row`
 void run_compare(mcb_model *m, const double *y_in, double *y_out, uint64_t t0, uint32_t n_steps,
-                 int prev_row, int row, double *hist, int *kappa_out) {
+                 const int *kappa, int row, double *hist) {
   const int key = m->model_id * 2 + m->scrambler;
   switch (key) {
 #define X(ID, M)                                                                                      \
-    case 2 * ID: launch_run_compare<M, 0>(m, y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out); break; \
-    case 2 * ID + 1: launch_run_compare<M, 1>(m, y_in, y_out, t0, n_steps, prev_row, row, hist, kappa_out); break;
+    case 2 * ID: launch_run_compare<M, 0>(m, y_in, y_out, t0, n_steps, kappa, row, hist); break; \
+    case 2 * ID + 1: launch_run_compare<M, 1>(m, y_in, y_out, t0, n_steps, kappa, row, hist); break;
     MCB_MODELS(X)
 #undef X
     default: break;
   }
 }
 
-// K2: weights -> fixed point -> tile scan; the last block finalizes the interval
+// K2: weights -> fixed point -> tile scan; the last block of a set finalizes it
 void weights_scan(mcb_model *m, int row) {
   const unsigned grid = (unsigned)(m->v.n_sets * m->v.tiles_per_set);
   if (row < 0) launch_chained(m, m->chain, mcb::k_weights_scan<true>, grid, mcb::kTileThreads, m->v, row);
   else launch_chained(m, m->chain, mcb::k_weights_scan<false>, grid, mcb::kTileThreads, m->v, row);
 }
 
+// K3: the ancestor of every slot under the thresholds K2 left, into `kappa`
+void ancestors(mcb_model *m, int row, int *kappa) {
+  const unsigned grid = (unsigned)(m->v.n_sets * m->v.tiles_per_set);
+  launch_chained(m, m->chain, mcb::k_ancestors, grid, mcb::kTileThreads, m->v, row, kappa);
+}
+
 // one instantiation per state count a model may have (models.cuh: kMaxState)
 #define MCB_STATE_COUNTS(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
 static_assert(mcb::kMaxState == 8, "MCB_STATE_COUNTS covers 1..kMaxState");
 
-void resample_gather(mcb_model *m, int row, const double *src, double *dst, int *kappa_out) {
+void resample_gather(mcb_model *m, const int *kappa, const double *src, double *dst) {
   const unsigned grid = blocks_for(m->v.n_total, mcb::kGatherThreads);
   switch (m->v.n_state) {
-#define X(N) case N: mcb::k_resample_gather<N><<<grid, mcb::kGatherThreads, 0, m->stream>>>(m->v, row, src, dst, kappa_out); break;
+#define X(N) case N: mcb::k_resample_gather<N><<<grid, mcb::kGatherThreads, 0, m->stream>>>(m->v, kappa, src, dst); break;
     MCB_STATE_COUNTS(X)
 #undef X
     default: break;
@@ -376,10 +397,10 @@ void resample_gather(mcb_model *m, int row, const double *src, double *dst, int 
   ++m->launches;
 }
 
-void finish_state(mcb_model *m, int last, int last_weighted, int *kappa_out) {
+void finish_state(mcb_model *m, int last, const int *kappa) {
   const unsigned grid = blocks_for(m->v.n_total, mcb::kGatherThreads);
   switch (m->v.n_state) {
-#define X(N) case N: mcb::k_finish_state<N><<<grid, mcb::kGatherThreads, 0, m->stream>>>(m->v, last, last_weighted, kappa_out); break;
+#define X(N) case N: mcb::k_finish_state<N><<<grid, mcb::kGatherThreads, 0, m->stream>>>(m->v, last, kappa); break;
     MCB_STATE_COUNTS(X)
 #undef X
     default: break;
@@ -428,11 +449,12 @@ void draw_uniforms(mcb_model *m, int row_first, int row_last) {
   ++m->launches;
 }
 
-// boundary k of a data row: 0 before K1, 1 after K1, 2 after K2; row n_data holds the
-// two boundaries around k_finish_state
+// boundary k of a data row: 0 before K1, 1 after K1, 2 after K2, 3 after K3; row n_data
+// holds the two boundaries around k_finish_state
+constexpr size_t kMarks = 4;
 void mark(mcb_model *m, int row, int k) {
   if (!m->timing) return;
-  const size_t need = (size_t)(row + 1) * 3;
+  const size_t need = (size_t)(row + 1) * kMarks;
   while (m->events.size() < need) {
     cudaEvent_t e;
     cudaEventCreate(&e);
@@ -440,7 +462,7 @@ void mark(mcb_model *m, int row, int k) {
   }
   cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(m->stream, &st);
-  cudaEventRecordWithFlags(m->events[(size_t)row * 3 + k], m->stream,
+  cudaEventRecordWithFlags(m->events[(size_t)row * kMarks + k], m->stream,
                            st == cudaStreamCaptureStatusActive ? cudaEventRecordExternal
                                                                : cudaEventRecordDefault);
 }
@@ -479,14 +501,17 @@ uint64_t enqueue_filter_rows(mcb_model *m, int first, int last, bool hist,
   };
   if (hist) {
     // slice 0: the state before the first interval, identity order
-    run_compare(m, v.y, v.y, 0, 0, -1, -1, m->d_hist_value, nullptr);
+    run_compare(m, v.y, v.y, 0, 0, nullptr, -1, m->d_hist_value);
     iota(m->d_hist_order);
   }
   uint64_t t = m->time;
   size_t snap_i = 0;
-  int prev_weighted = -1;          // row whose resampling is still owed, or -1
+  // where K3 left the ancestors of the last weighed row (its resampling is applied by the
+  // next launch that loads the state), or nullptr.  With trajectories K3 writes straight
+  // into the order slice of the history; without, into the handle's scratch.
+  const int *kappa_prev = nullptr;
   const double *in = v.y;
-  // the loop's K1 and K2 are chained by programmatic dependent launch (not when
+  // the loop's K1, K2 and K3 are chained by programmatic dependent launch (not when
   // events sit between them for per-kernel timing); MCB_PDL=0 turns it off
   static const bool pdl = !(getenv("MCB_PDL") && atoi(getenv("MCB_PDL")) == 0);
   m->chain = pdl && !m->timing;
@@ -497,21 +522,27 @@ uint64_t enqueue_filter_rows(mcb_model *m, int first, int last, bool hist,
     // buffers alternate so that the last row always writes y_tmp
     double *out = ((last - 1 - row) & 1) == 0 ? v.y_tmp : v.y;
     double *hist_slice = hist ? m->d_hist_value + (size_t)(rel + 1) * v.n_index * v.ld : nullptr;
-    int *order_prev = hist ? m->d_hist_order + (size_t)rel * v.n_total : nullptr;
     const int weigh = m->row_all_na[row] ? -1 : row;
     mark(m, row, 0);
-    run_compare(m, in, out, t, n_steps, prev_weighted, weigh, hist_slice,
-                prev_weighted >= 0 ? order_prev : nullptr);
-    if (hist && rel > 0 && prev_weighted < 0) iota(order_prev);
+    run_compare(m, in, out, t, n_steps, kappa_prev, weigh, hist_slice);
+    if (hist && rel > 0 && !kappa_prev) iota(m->d_hist_order + (size_t)rel * v.n_total);
     mark(m, row, 1);
-    if (weigh >= 0) weights_scan(m, row);
-    mark(m, row, 2);
-    prev_weighted = weigh;
+    kappa_prev = nullptr;
+    if (weigh >= 0) {
+      weights_scan(m, row);
+      mark(m, row, 2);
+      int *dst = hist ? m->d_hist_order + (size_t)(rel + 1) * v.n_total : m->d_kappa;
+      ancestors(m, row, dst);
+      kappa_prev = dst;
+    } else {
+      mark(m, row, 2);
+    }
+    mark(m, row, 3);
     while (snap_i < snap_rows.size() && snap_rows[snap_i] < row) ++snap_i;
     if (snap_i < snap_rows.size() && snap_rows[snap_i] == row) {
       double *dst = m->d_snap + snap_i * (size_t)v.n_state * v.ld;
       if (weigh >= 0) {
-        resample_gather(m, row, out, dst, nullptr);
+        resample_gather(m, kappa_prev, out, dst);
       } else {
         mcb::k_copy_state_if_running<<<blocks_for(v.n_total, 256), 256, 0, m->stream>>>(v, out, dst);
         ++m->launches;
@@ -523,9 +554,8 @@ uint64_t enqueue_filter_rows(mcb_model *m, int first, int last, bool hist,
   }
   m->chain = false;
   mark(m, (int)m->n_data, 0);
-  int *order_last = hist ? m->d_hist_order + (size_t)(last - first) * v.n_total : nullptr;
-  finish_state(m, last, prev_weighted >= 0 ? 1 : 0, prev_weighted >= 0 ? order_last : nullptr);
-  if (hist && prev_weighted < 0) iota(order_last);
+  finish_state(m, last, kappa_prev);
+  if (hist && !kappa_prev) iota(m->d_hist_order + (size_t)(last - first) * v.n_total);
   mark(m, (int)m->n_data, 1);
   mcb::k_filter_finish<<<blocks_for((size_t)v.n_fs, 128), 128, 0, m->stream>>>(v, first, last,
                                                                                 m->d_fs_after);
@@ -673,15 +703,39 @@ int run_filter(mcb_model *m, uint64_t time_end, bool hist, const uint64_t *snaps
   if (rows > 0 && use_persistent(m, n_snap)) {
     MCB_TRY(launch_persistent(m, first, last, hist));
   } else if (rows > 0) {
+    // the reset schedule of every launch, as enqueue_filter_rows will bake it in
+    uint64_t sched_hash = 1469598103934665603ULL;
+    {
+      uint64_t t = m->time;
+      for (int r = first; r < last; ++r) {
+        int valid = 0;
+        const uint32_t mask = reset_mask(m, t, (uint32_t)(m->data_time[r] - t), &valid);
+        sched_hash = (sched_hash ^ (((uint64_t)mask << 1) | (uint64_t)valid)) * 1099511628211ULL;
+        t = m->data_time[r];
+      }
+    }
     const GraphKey key{first, last, (hist ? 1 : 0) | (m->timing ? 2 : 0), (int)n_snap, (int)n_min,
-                       snap_hash};
+                       snap_hash, m->time, sched_hash};
     auto it = m->graphs.find(key);
-    if (it == m->graphs.end()) {
+    // A graph pays for itself from the second use on: the first call with a key launches
+    // the kernels directly (SMC^2's proposals run a row range once -- capturing and
+    // instantiating a graph of hundreds of nodes for it costs more than it saves).
+    if (it == m->graphs.end() && !m->graph_seen.count(key) && !m->timing) {
+      m->graph_seen.insert(key);
+      enqueue_filter_rows(m, first, last, hist, snap_rows);
+      MCB_TRY(check_launches(m));
+    } else if (it == m->graphs.end()) {
       cudaGraph_t graph = nullptr;
       MCB_CUDA(cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal));
       const uint64_t n_k = enqueue_filter_rows(m, first, last, hist, snap_rows);
       m->launches -= n_k;  // counted per replay below
       cudaError_t err = cudaStreamEndCapture(m->stream, &graph);
+      if (m->launch_error != cudaSuccess) {
+        const cudaError_t le = m->launch_error;
+        m->launch_error = cudaSuccess;
+        if (graph) cudaGraphDestroy(graph);
+        return fail(MCB_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(le));
+      }
       if (err != cudaSuccess)
         return fail(MCB_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(err));
       GraphEntry e;
@@ -692,8 +746,10 @@ int run_filter(mcb_model *m, uint64_t time_end, bool hist, const uint64_t *snaps
       e.n_kernels = n_k;
       it = m->graphs.emplace(key, e).first;
     }
-    MCB_CUDA(cudaGraphLaunch(it->second.exec, m->stream));
-    m->launches += it->second.n_kernels;
+    if (it != m->graphs.end()) {
+      MCB_CUDA(cudaGraphLaunch(it->second.exec, m->stream));
+      m->launches += it->second.n_kernels;
+    }
   } else {
     MCB_CUDA(cudaMemsetAsync(m->d_flags, 0, 2 * sizeof(int), m->stream));
     MCB_CUDA(cudaMemsetAsync(m->d_ll, 0, v.n_sets * sizeof(double), m->stream));
@@ -884,8 +940,8 @@ int mcb_alloc_ex(int model_id, const double *pars, size_t n_particles, size_t n_
   v.n_min = 0;
   v.data_sets = 1;
   v.tiles_per_set = (int)((n_particles + mcb::kTile - 1) / mcb::kTile);
-  v.shift = weight_shift(n_particles);
   v.deterministic = deterministic;
+  v.independent = (seed_mode == MCB_SEED_PER_SET && n_sets > 1) ? 1 : 0;
 
   auto cleanup = [&](int rc) { mcb_free(m); return rc; };
 #define ALLOC(ptr, bytes)                                                         \
@@ -913,23 +969,21 @@ int mcb_alloc_ex(int model_id, const double *pars, size_t n_particles, size_t n_
     size_t n_tab = max_pop < 65535.0 ? (size_t)max_pop + 1 : 65536;
     n_tab = round_up(n_tab < 256 ? 256 : n_tab, 256);
     const size_t n_const = (size_t)kModelTables[model_id].n_const;
-    const size_t row_bytes = (2 + n_const * mcb::kWalkK) * sizeof(double);
+    const size_t row_bytes = (4 + n_const * mcb::kWalkK) * sizeof(double);
     const size_t budget = ((size_t)1 << 30) / (n_sets * row_bytes);
     if (n_tab > budget) n_tab = budget / 256 * 256;
     if (n_tab < 256) n_tab = 256;
     v.n_tab = (int)n_tab;
     v.n_wrows = (int)(n_tab < kMaxWalkRows ? n_tab : kMaxWalkRows);
-    int bits = 0;
-    while (((size_t)1 << bits) < n_tab) ++bits;
-    v.pow_groups = (bits + 1) / 3;
     m->n_const = (int)n_const;
   }
   ALLOC(v.derived, n_sets * mcb::kMaxDerived * sizeof(double));
-  ALLOC(v.tab_inf, n_sets * (size_t)v.n_tab * sizeof(double2));
+  ALLOC(v.tab_inf, n_sets * (size_t)v.n_tab * sizeof(double4));
   ALLOC(v.tab_walk, n_sets * (size_t)(m->n_const ? m->n_const : 1) * v.n_wrows * mcb::kWalkK * sizeof(double));
   ALLOC(v.logw, v.ld * sizeof(double));
   ALLOC(v.cw, v.ld * sizeof(unsigned long long));
-  ALLOC(v.tile_incl, n_sets * v.tiles_per_set * sizeof(unsigned long long));
+  ALLOC(v.tile_sum, n_sets * v.tiles_per_set * sizeof(unsigned long long));
+  ALLOC(v.tile_pre, n_sets * v.tiles_per_set * sizeof(mcb::u128));
   ALLOC(v.setinfo, n_sets * sizeof(mcb::SetInfo));
   ALLOC(m->d_ll, n_sets * sizeof(double));
   ALLOC(m->d_min_ll, n_sets * sizeof(double));
@@ -1013,7 +1067,7 @@ int mcb_free(mcb_model *m) {
   cudaSetDevice(m->device);
   if (m->stream) cudaStreamSynchronize(m->stream);
   clear_graphs(m);
-  void *ptrs[] = {m->v.y, m->v.y_tmp, m->v.rng, m->v.derived, m->v.tab_inf, m->v.tab_walk, m->d_pars, m->v.logw, m->v.cw, m->v.tile_incl,
+  void *ptrs[] = {m->v.y, m->v.y_tmp, m->v.rng, m->v.derived, m->v.tab_inf, m->v.tab_walk, m->d_pars, m->v.logw, m->v.cw, m->v.tile_sum, m->v.tile_pre,
                   m->v.setinfo, m->d_ll, m->d_min_ll, m->d_flags, m->d_ticket, m->d_index, m->d_kappa, m->d_u,
                   m->d_wmax, m->d_fs_after, m->d_na_global, m->d_data, m->d_stage, m->d_hist_value,
                   m->d_hist_order, m->d_traj, m->d_snap, m->d_data_time, m->d_blk_sum};
@@ -1096,9 +1150,10 @@ int mcb_run(mcb_model *m, uint64_t time_end, double *out) {
   MCB_CUDA(cudaSetDevice(m->device));
   if (time_end < m->time) return fail(MCB_ERR_ARG, "'time_end' must be at least the current time");
   if (time_end > m->time) {
-    run_compare(m, m->v.y, m->v.y, m->time, (uint32_t)(time_end - m->time), -1, -1, nullptr, nullptr);
+    run_compare(m, m->v.y, m->v.y, m->time, (uint32_t)(time_end - m->time), nullptr, -1, nullptr);
     m->time = time_end;
     reset_cursor(m);
+    MCB_TRY(check_launches(m));
   }
   if (out) return pack_to_host(m, m->v.y, m->d_index, m->v.n_index, out);
   MCB_CUDA(cudaGetLastError());
@@ -1131,10 +1186,11 @@ int mcb_simulate(mcb_model *m, const uint64_t *times, size_t n_times, double *ou
     for (size_t k = 0; k < nc; ++k) {
       const uint64_t t_end = times[c0 + k];
       // n_steps = 0 (t_end == current time) still records the slice
-      run_compare(m, v.y, v.y, m->time, (uint32_t)(t_end - m->time), -1, -1, d_slices + k * slice,
-                  nullptr);
+      run_compare(m, v.y, v.y, m->time, (uint32_t)(t_end - m->time), nullptr, -1,
+                  d_slices + k * slice);
       m->time = t_end;
     }
+    MCB_TRY(check_launches(m));
     const dim3 grid(blocks_for(v.n_total, 256), (unsigned)nc);
     mcb::k_pack_slices<<<grid, 256, 0, m->stream>>>(d_slices, v.ld, v.n_total, v.n_index, nc, d_packed);
     ++m->launches;
@@ -1415,7 +1471,8 @@ int mcb_compare_data(mcb_model *m, double *logw, int *has_data) {
   if (row < 0 || m->row_all_na[row]) return MCB_OK;
   MCB_CUDA(cudaMemsetAsync(v.logw, 0, v.n_total * sizeof(double), m->stream));
   MCB_CUDA(cudaMemsetAsync(m->d_flags, 0, 2 * sizeof(int), m->stream));
-  run_compare(m, v.y, v.y, m->time, 0, -1, row, nullptr, nullptr);
+  run_compare(m, v.y, v.y, m->time, 0, nullptr, row, nullptr);
+  MCB_TRY(check_launches(m));
   MCB_CUDA(cudaMemcpyAsync(logw, v.logw, v.n_total * sizeof(double), cudaMemcpyDeviceToHost,
                            m->stream));
   MCB_CUDA(cudaStreamSynchronize(m->stream));
@@ -1435,9 +1492,11 @@ int mcb_resample(mcb_model *m, const double *weights, int *kappa) {
                            m->stream));
   draw_uniforms(m, -1, 0);
   weights_scan(m, -1);
+  ancestors(m, -1, m->d_kappa);
+  MCB_TRY(check_launches(m));
   MCB_CUDA(cudaMemcpyAsync(v.y_tmp, v.y, (size_t)v.n_state * v.ld * sizeof(double),
                            cudaMemcpyDeviceToDevice, m->stream));
-  resample_gather(m, -1, v.y_tmp, v.y, m->d_kappa);
+  resample_gather(m, m->d_kappa, v.y_tmp, v.y);
   std::vector<int> k0(v.n_total);
   MCB_CUDA(cudaMemcpyAsync(k0.data(), m->d_kappa, v.n_total * sizeof(int), cudaMemcpyDeviceToHost,
                            m->stream));
@@ -1528,10 +1587,13 @@ int mcb_filter_collect(mcb_model *m, double *log_likelihood) {
       }
     };
     for (int row = m->pend_first; row < m->pend_last; ++row) {
-      add(0, (size_t)row * 3, (size_t)row * 3 + 1);
-      if (!m->row_all_na[row]) add(1, (size_t)row * 3 + 1, (size_t)row * 3 + 2);
+      add(0, (size_t)row * kMarks, (size_t)row * kMarks + 1);
+      if (!m->row_all_na[row]) {
+        add(1, (size_t)row * kMarks + 1, (size_t)row * kMarks + 2);
+        add(2, (size_t)row * kMarks + 2, (size_t)row * kMarks + 3);
+      }
     }
-    if (m->pend_last > m->pend_first) add(3, m->n_data * 3, m->n_data * 3 + 1);
+    if (m->pend_last > m->pend_first) add(3, m->n_data * kMarks, m->n_data * kMarks + 1);
   }
   if (last_row >= m->pend_first) {
     m->time = m->data_time[last_row];
@@ -1539,6 +1601,12 @@ int mcb_filter_collect(mcb_model *m, double *log_likelihood) {
   }
   if (log_likelihood)
     std::memcpy(log_likelihood, m->h_ll, m->v.n_sets * sizeof(double));
+  return MCB_OK;
+}
+
+int mcb_log_likelihood_device(mcb_model *m, double **device_ptr) {
+  if (!m || !device_ptr) return fail(MCB_ERR_ARG, "NULL argument");
+  *device_ptr = m->d_ll;
   return MCB_OK;
 }
 

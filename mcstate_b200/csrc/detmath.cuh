@@ -54,6 +54,27 @@ __device__ __forceinline__ double det_exp(double x) {
   return (p * s1) * s2;
 }
 
+// det_exp for x <= 0 (or -inf; a NaN gives 0): the same operations on the same values --
+// the same bits -- without the branches: the argument is clamped where the result is
+// zero anyway, and the underflow rule is a select.  For the weights, exp(logw - max).
+__device__ __forceinline__ double det_exp_nonpos(double x) {
+  const double xc = fmax(x, -746.0);
+  const double kd = rint(xc * c_exp_red[0]);
+  double r = fma(-kd, c_exp_red[1], xc);
+  r = fma(-kd, c_exp_red[2], r);
+  double p = c_exp_poly[0];
+#pragma unroll
+  for (int j = 1; j < 12; ++j) p = fma(p, r, c_exp_poly[j]);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const int k = (int)kd;
+  const int k1 = k >> 1, k2 = k - k1;
+  const double s1 = bits_to_double((uint64_t)(1023 + k1) << 52);
+  const double s2 = bits_to_double((uint64_t)(1023 + k2) << 52);
+  const double val = (p * s1) * s2;
+  return xc < -745.1332191019412 ? 0.0 : val;
+}
+
 // log(x): x = 2^k m with m in [sqrt(1/2), sqrt(2)); f = m - 1, s = f/(2+f);
 // log(1+f) = f - f^2/2 + s (f^2/2 + R(s^2)) with the classic 7-term minimax R;
 // ln2 is split so k*ln2_hi is exact.

@@ -2,14 +2,20 @@
 // (model$filter, R/particle_filter_state.R:151; per-interval order as
 // R/particle_filter_state.R:63-117).
 //
-// Two launches per data interval:
-//   K1 k_run_compare   [resample + gather of the previous interval, fused into the
-//                      load] -> `rate` model steps -> compare -> state', rng', logw, max
+// Three launches per data interval, chained by programmatic dependent launch:
+//   K1 k_run_compare   [gather of the previous interval's resampling fused into the
+//                      load: slot i starts from particle kappa[i]] -> `rate` model
+//                      steps -> compare -> state', rng', logw, max
 //   K2 k_weights_scan  w = exp(logw - max) as fixed point, per-tile inclusive scan;
-//                      the block that ends a parameter set adds its tile prefix,
-//                      log-mean-exp -> ll, resampling thresholds; the last set to
-//                      finish applies the early-exit rule
-// plus k_finish_state once per filter call (the last interval's resample).
+//                      the block that ends a parameter set turns the tile sums into a
+//                      prefix, log-mean-exp -> ll, resampling thresholds; the last set
+//                      to finish applies the early-exit rule
+//   K3 k_ancestors     systematic resampling as a merge: one block per 2048 output
+//                      slots stages the tile prefix and the two weight tiles its slots
+//                      fall into in shared memory and writes kappa (4 B per slot), so
+//                      K1 and every other state pass read their ancestor with one
+//                      coalesced load and do no search
+// plus k_finish_state once per filter call (the last interval's gather).
 // Filters that fit the GPU in one wave run as ONE cooperative kernel per call instead
 // (persistent.cuh); the model steps (run_model_steps) are shared.
 //
@@ -20,11 +26,12 @@
 // always writes `y_tmp` and k_finish_state lands the live state in `y`: the
 // launch sequence is fixed per row range and replays as a CUDA graph.
 //
-// Weights are summed as fixed-point integers (scale_log_weights:
-// R/particle_filter.R:570-587; resample_weight: SURVEY.md R2b).  Integer
-// addition is associative, so the tiled parallel scan gives the same
-// cumulative sums as a serial loop and the chosen ancestors do not depend on
-// tile size, SM count or scheduling.
+// Weights are summed as fixed-point integers, rint(w 2^52), in 128 bits
+// (scale_log_weights: R/particle_filter.R:570-587; resample_weight: SURVEY.md
+// R2b).  Integer addition is associative, so the tiled parallel scan gives the
+// same cumulative sums as a serial loop and the chosen ancestors do not depend
+// on tile size, SM count or scheduling; 52 fractional bits whatever the number
+// of particles keep every weight at least as precisely as a double sum would.
 #pragma once
 #include <cstdint>
 
@@ -44,8 +51,13 @@ constexpr int kTileItems = MCB_TILE_ITEMS;  // consecutive particles per thread 
 constexpr int kTile = kTileThreads * kTileItems;  // particles per weight tile
 constexpr int kGatherThreads = 256;
 
-struct SetInfo {   // per parameter set, rewritten every interval by K2b
-  double uu0, du;  // threshold_i = uu0 + i * du   (fixed-point units)
+typedef unsigned __int128 u128;
+constexpr int kShift = 52;   // fractional bits of a fixed-point weight
+
+struct SetInfo {   // per parameter set, rewritten every interval by K2's finishing block
+  double uu0, du;  // threshold_i = ceil(uu0 + i * du)   (fixed-point units)
+  int dead;        // every weight of the interval was zero: the set is not resampled
+  int pad;
 };
 
 struct View {
@@ -54,12 +66,13 @@ struct View {
   uint64_t *rng;      // [4][ld_rng]     stream n_total is the filter's
   const double *pars; // [n_sets][kMaxPar]
   double *derived;    // [n_sets][kMaxDerived]  parameter-only constants (Model::derive)
-  double2 *tab_inf;   // [n_sets][n_tab]                     infection entries (Model::inf_entry)
+  double4 *tab_inf;   // [n_sets][n_tab]                     infection entries (Model::inf_entry)
   double *tab_walk;   // [n_sets][n_const][n_wrows][kWalkK]  walk tables (Model::walk_row)
   const double *data; // [n_data][data_sets][2] = {value, lgamma(value+1)}
   double *logw;       // [n_total]
   unsigned long long *cw;        // [n_total] inclusive fixed-point cumsum inside a tile
-  unsigned long long *tile_incl; // [n_sets][tiles_per_set] tile sums, then inclusive prefix
+  unsigned long long *tile_sum;  // [n_sets][tiles_per_set] fixed-point weight of each tile
+  u128 *tile_pre;                // [n_sets][tiles_per_set] inclusive prefix of the tile sums
   unsigned long long *wmax;      // [n_data][n_sets] order-preserving key of max logw
   const double *u_draws;         // [n_data][n_sets] resampling uniforms (filter stream)
   SetInfo *setinfo;   // [n_sets]
@@ -69,8 +82,12 @@ struct View {
   unsigned int *ticket; // [n_sets + 2] K2 counters: tiles done per set, sets done, any set dead
   const int *index;   // [n_index] rows returned by run()/saved in trajectories
   size_t n_particles, n_sets, n_total, ld, ld_rng;
-  int n_state, n_index, n_min, data_sets, tiles_per_set, shift, deterministic, n_tab, n_wrows;
-  int pow_groups;   // groups of three bits beyond bit 0 in a count below n_tab (pow_int_lean)
+  int n_state, n_index, n_min, data_sets, tiles_per_set, deterministic, n_tab, n_wrows;
+  // independent != 0: the sets are separate filters batched in one handle (per-set
+  // seeds): a set whose weights all vanish gets -Inf and is not resampled, the others
+  // go on.  0: the sets of one multi-parameter filter -- any dead set ends the call
+  // (R/particle_filter_state.R:463-474).
+  int independent;
   // filter streams (resampling uniforms).  n_fs == 1: one stream shared by every set
   // (the dust pars_multi layout), drawn in set order; when the sets of one model are
   // sharded over several handles, each handle replays the whole order
@@ -139,116 +156,62 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long x,
   return __shfl_xor_sync(0xffffffffu, x, m);
 }
 
-// ---------------------------------------------------------------------------
-// Systematic resampling (dust resample_weight, SURVEY.md R2b; the R twin is
-// particle_resample, R/particle_filter.R:515-523): output slot `il` of `set`
-// takes the first particle whose inclusive cumulative weight reaches
-// ceil(uu0 + il du).  Compared exactly, as integers: binary search over the
-// set's tile prefix (8 KB, L1 resident), then inside the tile.  Thresholds grow
-// with il, so neighbouring threads probe neighbouring addresses and the
-// chosen sources are monotone (near-coalesced gather).
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ size_t resample_source(const View &v, size_t set, size_t il) {
-  const SetInfo si = v.setinfo[set];
-  const unsigned long long thr =
-      (unsigned long long)__double2ll_ru(si.uu0 + (double)il * si.du);
-  const unsigned long long *ts = v.tile_incl + set * v.tiles_per_set;
-  int lo = 0, hi = v.tiles_per_set - 1;  // first tile whose inclusive prefix reaches thr
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (__ldg(ts + mid) >= thr) hi = mid; else lo = mid + 1;
-  }
-  const unsigned long long before = lo ? __ldg(ts + lo - 1) : 0ULL;
-  const unsigned long long rem = thr > before ? thr - before : 0ULL;
-  const size_t tile_base = (size_t)lo * kTile;
-  const size_t in_tile = min((size_t)kTile, v.n_particles - tile_base);
-  const unsigned long long *cw = v.cw + set * v.n_particles + tile_base;
-  int a = 0, b = (int)in_tile - 1;
-  while (a < b) {
-    const int mid = (a + b) >> 1;
-    if (__ldg(cw + mid) >= rem) b = mid; else a = mid + 1;
-  }
-  return set * v.n_particles + tile_base + a;
+__device__ __forceinline__ u128 shfl_up_u128(u128 x, int d) {
+  const unsigned long long lo = shfl_up_u64((unsigned long long)x, d);
+  const unsigned long long hi = shfl_up_u64((unsigned long long)(x >> 64), d);
+  return ((u128)hi << 64) | lo;
+}
+
+// the double nearest to x (ties to even): the top 64 bits with a sticky last bit are
+// converted (one correctly rounded conversion), then scaled exactly (oracle twin:
+// u128_to_double)
+__device__ __forceinline__ double u128_to_double(u128 x) {
+  const unsigned long long hi = (unsigned long long)(x >> 64), lo = (unsigned long long)x;
+  if (hi == 0) return __ull2double_rn(lo);
+  const int s = 64 - __clzll((long long)hi);   // bits of hi in use: sums stay below 2^83
+  unsigned long long v = (hi << (64 - s)) | (lo >> s);
+  if ((lo << (64 - s)) != 0) v |= 1ULL;
+  return __ull2double_rn(v) * bits_to_double((uint64_t)(1023 + s) << 52);
+}
+
+// ceil(d) as an integer, d >= 0 and finite (doubles from 2^52 up are integers)
+__device__ __forceinline__ u128 ceil_to_u128(double d) {
+  if (d < 9223372036854775808.0) return (u128)__double2ull_ru(d);
+  const uint64_t b = double_to_bits(d);
+  const int e = (int)(b >> 52) - 1075;
+  const uint64_t m = (b & 0xfffffffffffffULL) | 0x10000000000000ULL;
+  return (u128)m << e;
 }
 
 // ---------------------------------------------------------------------------
-// The same search done by a whole warp for 32 consecutive output slots of one
-// set (the usual case in K1).  Thresholds grow with the slot, so the warp first
-// finds lane 0's position with 32-way probes (2 rounds over the tile prefix, 3
-// inside a 2048-particle tile, every probe round one coalesced or strided load
-// instead of a chain of 20 dependent ones), then each lane finishes inside a
-// 64-entry window staged in shared memory.  Lanes whose threshold lies beyond
-// the window, and warps whose slots span two tiles, fall back to the per-thread
-// search: the result is identical by construction.
+// Systematic resampling (dust resample_weight, SURVEY.md R2b; the R twin is
+// particle_resample, R/particle_filter.R:515-523): output slot `il` of a set
+// takes the first particle whose inclusive cumulative weight reaches
+// ceil(uu0 + il du), the last one if none does.  Compared exactly, as integers.
 // ---------------------------------------------------------------------------
-// first index in [0, n) with arr[idx] >= key, else n - 1; uniform across the warp
-__device__ __forceinline__ int warp_lower_bound(const unsigned long long *__restrict__ arr, int n,
-                                                unsigned long long key, int lane) {
-  int lo = 0, cnt = n;
-  while (cnt > 1) {
-    const int step = (cnt + 31) >> 5;
-    const int last = lo + cnt - 1;
-    const int idx = min(lo + (lane + 1) * step - 1, last);
-    const unsigned b = __ballot_sync(0xffffffffu, __ldg(arr + idx) >= key);
-    if (b == 0) return last;
-    const int j = __ffs(b) - 1;
-    lo += j * step;
-    cnt = min(lo + step - 1, last) - lo + 1;
+__device__ __forceinline__ u128 slot_threshold(const SetInfo &si, uint32_t il) {
+  return ceil_to_u128(si.uu0 + (double)il * si.du);
+}
+
+// first index in [lo, n) with pre[idx] >= thr, else n - 1
+__device__ __forceinline__ int tile_lower_bound(const u128 *pre, int lo, int n, u128 thr) {
+  int hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (pre[mid] >= thr) hi = mid; else lo = mid + 1;
   }
   return lo;
 }
 
-constexpr int kWindow = 64;
-__device__ __forceinline__ size_t resample_source_warp(const View &v, size_t set, size_t il,
-                                                       unsigned long long *s_win, int lane) {
-  const SetInfo si = v.setinfo[set];
-  const unsigned long long thr =
-      (unsigned long long)__double2ll_ru(si.uu0 + (double)il * si.du);
-  const unsigned long long thr0 = shfl_u64(thr, 0), thr31 = shfl_u64(thr, 31);
-  const unsigned long long *ts = v.tile_incl + set * v.tiles_per_set;
-  const int T = v.tiles_per_set;
-  const int t0 = warp_lower_bound(ts, T, thr0, lane);
-  if (t0 < T - 1 && thr31 > __ldg(ts + t0)) return resample_source(v, set, il);  // two tiles
-  const unsigned long long before = t0 ? __ldg(ts + t0 - 1) : 0ULL;
-  const unsigned long long rem = thr > before ? thr - before : 0ULL;
-  const size_t tile_base = (size_t)t0 * kTile;
-  const int in_tile = (int)min((size_t)kTile, v.n_particles - tile_base);
-  const unsigned long long *cw = v.cw + set * v.n_particles + tile_base;
-  const int a0 = warp_lower_bound(cw, in_tile, shfl_u64(rem, 0), lane);
-  // window cw[a0 .. a0 + 63] (clamped to the tile) -> shared memory
-  s_win[lane] = __ldg(cw + min(a0 + lane, in_tile - 1));
-  s_win[lane + 32] = __ldg(cw + min(a0 + 32 + lane, in_tile - 1));
-  __syncwarp();
-  int lo = 0, hi = kWindow - 1;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    const int mid = (lo + hi) >> 1;
-    if (s_win[mid] >= rem) hi = mid; else lo = mid + 1;
-  }
-  int a = min(a0 + lo, in_tile - 1);
-  if (lo == kWindow - 1 && s_win[kWindow - 1] < rem && a0 + kWindow < in_tile) {
-    // beyond the window: the plain search over what is left of the tile
-    int x = a0 + kWindow, y = in_tile - 1;
-    while (x < y) {
-      const int mid = (x + y) >> 1;
-      if (__ldg(cw + mid) >= rem) y = mid; else x = mid + 1;
-    }
-    a = x;
-  }
-  __syncwarp();
-  return set * v.n_particles + tile_base + a;
-}
-
 // ---------------------------------------------------------------------------
-// K1: one thread per particle: [resample of the previous interval, fused into
-// the load] -> `n_steps` model updates -> compare.  State (kState doubles) and
-// the generator (4 words) stay in registers throughout.
-//   prev_row >= 0: slot i starts from the particle systematic resampling picks
-//                  for it (reads y_in[src]; y_in != y_out), so the resampled
+// K1: one thread per particle: [gather of the previous interval's resampling,
+// fused into the load] -> `n_steps` model updates -> compare.  State (kState
+// doubles) and the generator (4 words) stay in registers throughout.
+//   kappa != nullptr: slot i starts from particle kappa[i], the ancestor K3 chose
+//                  for it (reads y_in[kappa[i]]; y_in != y_out), so the resampled
 //                  state is never written to HBM and read back;
-//   prev_row <  0: slot i continues its own particle (y_in may equal y_out);
+//   kappa == nullptr: slot i continues its own particle (y_in may equal y_out);
 //   row >= 0: weigh against data row `row`; row < 0: no compare (model$run).
-// kappa_out (trajectories only) records src, the order slice of prev_row.
 // ---------------------------------------------------------------------------
 // The general form of the model steps (state as doubles, every special case of
 // the draws), out of line so the run kernel's registers are sized for the lean
@@ -271,23 +234,22 @@ __device__ __noinline__ void run_general(double *y, uint64_t *rs, uint64_t t0, u
 // `n_steps` model updates of one particle, state and generator in registers: the
 // lean path where the model has one and the state allows it, the general code for
 // whatever is left (run_general, out of line), or -- for a model without integer
-// compartments -- its one form, inline.  s_inv: the block's {k, 1/k} table.
+// compartments -- its one form, inline.  s_exp2: the block's copy of g_exp2_tab.
 template <class M, int SCR>
 __device__ __forceinline__ void run_model_steps(const View &v, const SetData &sd,
                                                 const typename M::Ctx &ctx, size_t set, double *y,
                                                 Xoshiro &rng, uint64_t t0, uint32_t n_steps,
-                                                bool det, const double2 *s_inv) {
+                                                bool det, const double *s_exp2) {
   if (n_steps == 0) return;
   uint32_t done = 0;
   if constexpr (M::kHasLean) {
     int yi[M::kLeanState];
     typename M::Lean lc;
     lc.set = (uint32_t)set;
-    const LeanTabs tabs{v.tab_inf, v.tab_walk, (uint32_t)v.n_tab, (uint32_t)v.n_wrows,
-                        v.pow_groups};
+    const LeanTabs tabs{v.tab_inf, v.tab_walk, (uint32_t)v.n_tab, (uint32_t)v.n_wrows};
     if (!det && M::lean_load(sd, y, yi, lc)) {
       // the usual case: integer compartments, setup from the memo tables, no calls
-      const uint32_t s_inv_addr = (uint32_t)__cvta_generic_to_shared(s_inv);
+      const uint32_t s_exp2_addr = (uint32_t)__cvta_generic_to_shared(s_exp2);
       bool ok = true;
       uint32_t freq = 1, phase = 0;
       if (!v.reset_mask_valid) {
@@ -306,7 +268,7 @@ __device__ __forceinline__ void run_model_steps(const View &v, const SetData &sd
           }
         }
         for (uint32_t k = 0; k < nk; ++k) {
-          ok = M::template lean_update<SCR>((resets & 1u) != 0, yi, rng, lc, tabs, s_inv_addr);
+          ok = M::template lean_update<SCR>((resets & 1u) != 0, yi, rng, lc, tabs, s_exp2_addr);
           if (!ok) break;
           resets >>= 1;
           ++done;
@@ -346,15 +308,14 @@ constexpr int k1_min_blocks() { return M::kHasLean ? MCB_K1_MINBLOCKS : MCB_K1_M
 template <class M, int SCR, bool HIST>
 __global__ void __launch_bounds__(kRunThreads, k1_min_blocks<M>())
 k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_out,
-              uint64_t t0, uint32_t n_steps, int prev_row, int row,
-              double *__restrict__ hist, int *__restrict__ kappa_out) {
+              uint64_t t0, uint32_t n_steps, const int *__restrict__ kappa, int row,
+              double *__restrict__ hist) {
   __shared__ unsigned long long s_key[kRunThreads / 32];
-  __shared__ unsigned long long s_win[kRunThreads / 32][kWindow];
-  __shared__ double2 s_inv[kInvSmall + 1];  // one spare entry (walk_lean looks two ahead)
+  __shared__ double s_exp2[kExp2Tab];
   // programmatic dependent launch: let the next kernel be scheduled as this one
   // drains, and do not read anything an earlier kernel wrote before the wait
   grid_launch_dependents();
-  if (threadIdx.x <= kInvSmall) s_inv[threadIdx.x] = __ldg(g_inv_small + threadIdx.x);
+  if (threadIdx.x < kExp2Tab) s_exp2[threadIdx.x] = __ldg(g_exp2_tab + threadIdx.x);
   grid_dependency_wait();
   if (v.flags[0]) return;
   __syncthreads();
@@ -370,20 +331,9 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
   Xoshiro rng;
   unsigned long long key = 0;
   bool weighted = false;
-  // which particle this slot continues: systematic resampling of prev_row
-  size_t src = i;
-  {
-    const bool want = live && prev_row >= 0 && !datum_is_na(v, prev_row, set);
-    const int lane = threadIdx.x & 31;
-    const unsigned set0 = __shfl_sync(0xffffffffu, (unsigned)set, 0);  // every lane takes part
-    const bool together = want && set0 == (unsigned)set;
-    if (__all_sync(0xffffffffu, together))
-      src = resample_source_warp(v, set, i - set * v.n_particles, s_win[threadIdx.x >> 5], lane);
-    else if (want)
-      src = resample_source(v, set, i - set * v.n_particles);
-  }
+  // which particle this slot continues: the ancestor systematic resampling chose
+  const size_t src = (live && kappa) ? (size_t)__ldcs(kappa + i) : i;
   if (live) {
-    if (HIST && kappa_out) kappa_out[i] = (int)src;
 #pragma unroll
     // state and generator stream through once per launch: keep them out of L1's
     // way (evict-first), the memo tables and the search arrays live there
@@ -393,7 +343,7 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
     rng.s2 = __ldcs(v.rng + 2 * v.ld_rng + i);
     rng.s3 = __ldcs(v.rng + 3 * v.ld_rng + i);
 
-    run_model_steps<M, SCR>(v, sd, ctx, set, y, rng, t0, n_steps, det, s_inv);
+    run_model_steps<M, SCR>(v, sd, ctx, set, y, rng, t0, n_steps, det, s_exp2);
 
     if (n_steps > 0 || y_in != y_out) {
 #pragma unroll
@@ -461,21 +411,24 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
 // u, mx, ll_old: the set's resampling uniform, max log-weight and likelihood so far,
 // loaded by the caller at the start of the kernel (they do not change during it) so
 // that no dependent global load sits on the tail of the weights stage.
-__device__ __forceinline__ bool finish_set(const View &v, int row, size_t set,
-                                           unsigned long long tot, double u, double mx,
-                                           double ll_old) {
+__device__ __forceinline__ bool finish_set(const View &v, int row, size_t set, u128 tot, double u,
+                                           double mx, double ll_old) {
+  const double neg_inf = __longlong_as_double(0xfff0000000000000LL);
   const double n = (double)v.n_particles;
-  const double tot_d = (double)tot;
+  const double tot_d = u128_to_double(tot);
+  const bool dead = row >= 0 && (!(mx > neg_inf) || tot == 0);
   SetInfo si;
   si.uu0 = tot_d * u / n;
   si.du = tot_d / n;
+  si.dead = dead ? 1 : 0;
+  si.pad = 0;
   v.setinfo[set] = si;
   if (row < 0) return false;
-  if (!(mx > __longlong_as_double(0xfff0000000000000LL)) || tot == 0) {
-    v.ll[set] = __longlong_as_double(0xfff0000000000000LL);
+  if (dead) {
+    v.ll[set] = neg_inf;
     return true;
   }
-  const double mean = (tot_d * bits_to_double((uint64_t)(1023 - v.shift) << 52)) / n;
+  const double mean = (tot_d * 0x1p-52) / n;
   v.ll[set] = ll_old + (det_log(mean) + mx);
   return false;
 }
@@ -490,64 +443,59 @@ __device__ __forceinline__ bool finish_set(const View &v, int row, size_t set,
 //          [n_sets + 1] "some set is dead" of this interval
 __device__ __forceinline__ void finalize_set(const View &v, int row, size_t set, double pre_u,
                                              double pre_mx, double pre_ll) {
-  __shared__ unsigned long long s_tot[kTileThreads / 32];
-  __shared__ unsigned long long s_carry;
+  __shared__ u128 s_tot[kTileThreads / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = v.tiles_per_set;
-  unsigned long long *ts = v.tile_incl + set * T;
+  const unsigned long long *sums = v.tile_sum + set * T;
+  u128 *pre = v.tile_pre + set * T;
   bool dead = false;
   const bool weighed = row < 0 || !datum_is_na(v, row, set);
   if (weighed && T <= 32) {
     // a small set: one warp
     if (warp == 0) {
-      unsigned long long incl = lane < T ? __ldcg(ts + lane) : 0ULL;
+      u128 incl = lane < T ? (u128)__ldcg(sums + lane) : (u128)0;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
-        const unsigned long long o = shfl_up_u64(incl, d);
+        const u128 o = shfl_up_u128(incl, d);
         if (lane >= d) incl += o;
       }
-      if (lane < T) ts[lane] = incl;
-      const unsigned long long tot = shfl_u64(incl, 31);
-      if (lane == 0) dead = finish_set(v, row, set, tot, pre_u, pre_mx, pre_ll);
+      if (lane < T) pre[lane] = incl;
+      const unsigned long long tot_lo = shfl_u64((unsigned long long)incl, T - 1);
+      const unsigned long long tot_hi = shfl_u64((unsigned long long)(incl >> 64), T - 1);
+      // lane 0 is thread 0: the one that holds the set's uniform and likelihood so far
+      if (lane == 0)
+        dead = finish_set(v, row, set, ((u128)tot_hi << 64) | tot_lo, pre_u, pre_mx, pre_ll);
     }
   } else if (weighed) {
-    // a big set: the whole block scans its tiles; each thread owns `per`
-    // consecutive tiles so a set of up to 256 * 8 tiles is one pass
-    constexpr int kPer = 8;
-    if (tid == 0) s_carry = 0;
-    __syncthreads();
+    // a big set: the whole block scans its tiles, two consecutive tiles per thread: 512
+    // tiles (1 Mi particles) per pass, one barrier each
+    constexpr int kPer = 2;
+    u128 carry = 0;   // the same value in every thread
     for (int base = 0; base < T; base += kTileThreads * kPer) {
-      const int span = min(T - base, kTileThreads * kPer);
-      const int per = (span + kTileThreads - 1) / kTileThreads;
-      const int lo = base + tid * per, hi = min(base + span, lo + per);
-      unsigned long long x[kPer];
-      unsigned long long local = 0;
-#pragma unroll
-      for (int j = 0; j < kPer; ++j) {
-        x[j] = (j < per && lo + j < hi) ? __ldcg(ts + lo + j) : 0ULL;
-        local += x[j];
-        x[j] = local;
-      }
-      unsigned long long incl = local;
+      if (base) __syncthreads();   // s_tot is written again
+      const int i0 = base + tid * kPer;
+      const unsigned long long x0 = i0 < T ? __ldcg(sums + i0) : 0ULL;
+      const unsigned long long x1 = i0 + 1 < T ? __ldcg(sums + i0 + 1) : 0ULL;
+      const u128 local = (u128)x0 + x1;
+      u128 incl = local;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
-        const unsigned long long o = shfl_up_u64(incl, d);
+        const u128 o = shfl_up_u128(incl, d);
         if (lane >= d) incl += o;
       }
       if (lane == 31) s_tot[warp] = incl;
       __syncthreads();
-      unsigned long long offset = s_carry + incl - local;
+      u128 offset = carry + incl - local, total = 0;
 #pragma unroll
-      for (int w = 0; w < kTileThreads / 32; ++w)
+      for (int w = 0; w < kTileThreads / 32; ++w) {
         if (w < warp) offset += s_tot[w];
-#pragma unroll
-      for (int j = 0; j < kPer; ++j)
-        if (j < per && lo + j < hi) ts[lo + j] = x[j] + offset;
-      __syncthreads();
-      if (tid == kTileThreads - 1) s_carry = offset + local;
-      __syncthreads();
+        total += s_tot[w];
+      }
+      if (i0 < T) pre[i0] = offset + x0;
+      if (i0 + 1 < T) pre[i0 + 1] = offset + local;
+      carry += total;
     }
-    if (tid == 0) dead = finish_set(v, row, set, s_carry, pre_u, pre_mx, pre_ll);
+    if (tid == 0) dead = finish_set(v, row, set, carry, pre_u, pre_mx, pre_ll);
   }
   if (tid != 0) return;
   bool any_dead = dead;
@@ -562,7 +510,8 @@ __device__ __forceinline__ void finalize_set(const View &v, int row, size_t set,
     *done = 0;
   }
   if (row < 0) return;
-  bool stop = any_dead;
+  // independent filters batched in one handle: a dead set has its -Inf and the others go on
+  bool stop = any_dead && !v.independent;
   if (!stop && v.n_min > 0) {
     const volatile double *ll = v.ll;
     if (v.n_sets == 1) {
@@ -584,11 +533,21 @@ __device__ __forceinline__ void finalize_set(const View &v, int row, size_t set,
   }
 }
 
+// rint(w 2^52) for w in [0, 1] without the (quarter-rate) conversion: adding 2^52 lands
+// in [2^52, 2^53], where doubles are the integers, so the addition itself rounds to
+// nearest-even; the integer is then the distance of the bit patterns
+__device__ __forceinline__ unsigned long long weight_to_fixed(double w) {
+  const double t = fma(w, 0x1p52, 0x1p52);
+  return (unsigned long long)(__double_as_longlong(t) - 0x4330000000000000LL);
+}
+
 // ---------------------------------------------------------------------------
 // K2: one block per tile of kTile particles (tiles never straddle a set):
 // w = exp(logw - max) -> fixed point, inclusive scan inside the tile, tile sum.
 // The block that takes its set's last ticket then runs finalize_set, so the
-// whole weights stage is one launch.
+// whole weights stage is one launch.  The tile sum is published (and the ticket
+// taken) before the block stores its cumulative weights: only the sum is read
+// by the finishing block, the cumulative weights are for the next launch.
 // GIVEN = true: `logw` already holds weights in [0,1] (model$resample(weights)).
 // ---------------------------------------------------------------------------
 template <bool GIVEN>
@@ -606,19 +565,21 @@ __global__ void __launch_bounds__(kTileThreads, 4) k_weights_scan(View v, int ro
     pre_u = v.u_draws[(size_t)(row < 0 ? 0 : row) * v.n_sets + set];
     pre_ll = v.ll[set];
   }
-  if (GIVEN || !datum_is_na(v, row, set)) {
+  const bool have = GIVEN || !datum_is_na(v, row, set);   // block-uniform
+  const size_t in_set = (size_t)tile * kTile + (size_t)threadIdx.x * kTileItems;
+  const size_t base = set * v.n_particles + in_set;
+  const bool full = in_set + kTileItems <= v.n_particles && (base & 1) == 0;
+  unsigned long long q[kTileItems];
+  unsigned long long offset = 0, total = 0;
+  if (have) {
     if (!GIVEN) mx = key_to_double(v.wmax[(size_t)row * v.n_sets + set]);
     const bool dead = !GIVEN && !(mx > __longlong_as_double(0xfff0000000000000LL));
-    const double scale = bits_to_double((uint64_t)(1023 + v.shift) << 52);
-    const size_t in_set = (size_t)tile * kTile + (size_t)threadIdx.x * kTileItems;
-    const size_t base = set * v.n_particles + in_set;
-    const bool full = in_set + kTileItems <= v.n_particles && (base & 1) == 0;
     double lw[kTileItems];
     if (full) {  // 16-byte vector loads: the 8 values of a thread are contiguous
       const double2 *src = reinterpret_cast<const double2 *>(v.logw + base);
 #pragma unroll
       for (int j = 0; j < kTileItems / 2; ++j) {
-        const double2 t = src[j];
+        const double2 t = __ldcs(src + j);
         lw[2 * j] = t.x;
         lw[2 * j + 1] = t.y;
       }
@@ -627,15 +588,12 @@ __global__ void __launch_bounds__(kTileThreads, 4) k_weights_scan(View v, int ro
       for (int j = 0; j < kTileItems; ++j)
         lw[j] = in_set + j < v.n_particles ? v.logw[base + j] : __longlong_as_double(0xfff0000000000000LL);
     }
-    unsigned long long q[kTileItems];
     unsigned long long run = 0;
 #pragma unroll
     for (int j = 0; j < kTileItems; ++j) {
       unsigned long long x = 0;
-      if (in_set + j < v.n_particles && !dead) {
-        const double w = GIVEN ? lw[j] : det_exp(lw[j] - mx);
-        x = (unsigned long long)__double2ll_rn(w * scale);
-      }
+      if (in_set + j < v.n_particles && !dead)
+        x = weight_to_fixed(GIVEN ? lw[j] : det_exp_nonpos(lw[j] - mx));
       run += x;
       q[j] = run;
     }
@@ -647,13 +605,21 @@ __global__ void __launch_bounds__(kTileThreads, 4) k_weights_scan(View v, int ro
     }
     if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
     __syncthreads();
-    unsigned long long offset = incl - run;
-    unsigned long long total = 0;
+    offset = incl - run;
 #pragma unroll
     for (int w = 0; w < kTileThreads / 32; ++w) {
       if (w < (int)(threadIdx.x >> 5)) offset += s_warp[w];
       total += s_warp[w];
     }
+  }
+  // ---- publish the tile sum and take the set's ticket; the block that takes the last
+  // one finishes the set
+  if (threadIdx.x == 0) {
+    if (have) v.tile_sum[blockIdx.x] = total;
+    __threadfence();
+    s_last = atomicAdd(v.ticket + set, 1u) == (unsigned)v.tiles_per_set - 1;
+  }
+  if (have) {
     if (full) {
       ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(v.cw + base);
 #pragma unroll
@@ -664,13 +630,6 @@ __global__ void __launch_bounds__(kTileThreads, 4) k_weights_scan(View v, int ro
       for (int j = 0; j < kTileItems; ++j)
         if (in_set + j < v.n_particles) v.cw[base + j] = q[j] + offset;
     }
-    if (threadIdx.x == 0) v.tile_incl[blockIdx.x] = total;
-  }
-  // ---- the block that takes the set's last ticket finishes the set.  Only the
-  // tile sum (written by thread 0) is read by that block; cw is for the next launch.
-  if (threadIdx.x == 0) {
-    __threadfence();
-    s_last = atomicAdd(v.ticket + set, 1u) == (unsigned)v.tiles_per_set - 1;
   }
   __syncthreads();
   if (!s_last) return;
@@ -680,32 +639,168 @@ __global__ void __launch_bounds__(kTileThreads, 4) k_weights_scan(View v, int ro
 }
 
 // ---------------------------------------------------------------------------
-// Stand-alone resample + gather (src -> dst), used where the resampled state
-// must exist in memory: snapshots and model$resample.
-// row < 0: every set is resampled; else sets whose datum is NA copy through.
+// K3: the ancestors.  Systematic resampling is a merge of two sorted sequences --
+// the thresholds ceil(uu0 + i du) of the output slots and the cumulative weights
+// of the particles -- so one block takes 2048 consecutive output slots of a set,
+// stages the set's tile prefix and a window of two weight tiles in shared memory
+// (one coalesced round trip to L2 each), and every thread walks its 8 consecutive
+// slots through the window: a halving search when it enters a tile, a short
+// bounded search from the previous ancestor after that.  Work follows the OUTPUT,
+// so the cost does not depend on how the weights are spread (uniform, degenerate,
+// one particle holding all).  When slots of the block fall beyond the window, the
+// window moves to the first tile still needed and the threads carry on where they
+// stopped: as many rounds as the block's slots have tile pairs to visit (one or
+// two unless the weights are very uneven).  A set without a datum in this row, or
+// whose weights all vanished, keeps its particles (identity).
+//   kappa [n_total]: global index of the particle each slot continues
+// ---------------------------------------------------------------------------
+constexpr int kAncWinTiles = 2;
+constexpr int kAncMaxSmemTiles = 512;
+constexpr int kAncNear = 64;   // how far past the previous ancestor the short search looks
+static_assert(kTile == 2048, "the searches of k_ancestors run 11 halving steps");
+
+// first index in [0, n) with cw[idx] >= rem, else n - 1; n <= 2048.  Eleven halving
+// steps whatever the data (no divergence)
+__device__ __forceinline__ int tile_search(const unsigned long long *cw, int n,
+                                           unsigned long long rem) {
+  int pos = 0;
+#pragma unroll
+  for (int half = kTile / 2; half >= 1; half >>= 1) {
+    const int probe = pos + half - 1;
+    if (probe < n && cw[probe] < rem) pos = probe + 1;
+  }
+  return min(pos, n - 1);
+}
+// the same for a key at or beyond the one that found `pos`: nothing to do when the
+// previous ancestor still reaches it, six halving steps when the answer lies within
+// kAncNear particles, the full search otherwise
+__device__ __forceinline__ int tile_search_from(const unsigned long long *cw, int pos, int n,
+                                                unsigned long long rem) {
+  if (cw[pos] >= rem || pos >= n - 1) return pos;
+  const int hi = min(pos + kAncNear, n - 1);
+  if (cw[hi] < rem) return hi == n - 1 ? hi : tile_search(cw, n, rem);
+  int lo = pos + 1;
+#pragma unroll
+  for (int half = kAncNear / 2; half >= 1; half >>= 1) {
+    const int probe = lo + half - 1;
+    if (probe < hi && cw[probe] < rem) lo = probe + 1;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(kTileThreads, 4)
+k_ancestors(View v, int row, int *__restrict__ kappa) {
+  __shared__ u128 s_pre[kAncMaxSmemTiles];
+  __shared__ unsigned long long s_cw[kAncWinTiles * kTile];
+  __shared__ int s_tile;   // the first tile of the window / the first tile still needed
+  grid_launch_dependents();
+  grid_dependency_wait();
+  if (v.flags[0]) return;
+  const int T = v.tiles_per_set;
+  const size_t set = v.n_sets == 1 ? 0 : blockIdx.x / (unsigned)T;
+  const int tile = (int)(blockIdx.x - (unsigned)set * (unsigned)T);
+  const size_t gbase = set * v.n_particles;
+  const uint32_t il0 = (uint32_t)tile * kTile + threadIdx.x * kTileItems;  // first slot of the thread
+  const uint32_t n_p = (uint32_t)v.n_particles;
+  const int n_mine = il0 >= n_p ? 0 : (int)min((uint32_t)kTileItems, n_p - il0);
+  int *out = kappa + gbase + il0;
+  const SetInfo si = v.setinfo[set];
+  if ((row >= 0 && datum_is_na(v, row, set)) || si.dead) {   // block-uniform: identity
+    for (int k = 0; k < n_mine; ++k) out[k] = (int)(gbase + il0 + k);
+    return;
+  }
+  const u128 *pre_g = v.tile_pre + set * T;
+  const bool pre_staged = T <= kAncMaxSmemTiles;
+  const u128 *pre = pre_staged ? s_pre : pre_g;
+  // ---- the tile the block's first slot falls into: with the prefix staged, every
+  // thread looks at its own entries and the one at the lower bound reports it
+  const u128 thr_first = slot_threshold(si, (uint32_t)tile * kTile);
+  if (pre_staged) {
+    if (threadIdx.x == 0) s_tile = T - 1;   // no prefix reaches the threshold: the last tile
+    for (int t = threadIdx.x; t < T; t += kTileThreads) s_pre[t] = pre_g[t];
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += kTileThreads)
+      if (s_pre[t] >= thr_first && (t == 0 || s_pre[t - 1] < thr_first)) s_tile = t;
+  } else if (threadIdx.x == 0) {
+    s_tile = tile_lower_bound(pre_g, 0, T, thr_first);
+  }
+  __syncthreads();
+  int t_w = s_tile;   // first tile of the window (block-uniform)
+  const unsigned long long *cw_set = v.cw + gbase;
+  // the thread's slots, in order: tile and position only move forward
+  int k = 0, t = -1, pos = 0, tlen = 0;
+  u128 before = 0, tile_end = 0;
+  for (;;) {
+    __syncthreads();   // everyone has read s_tile and is done with the previous window
+    if (threadIdx.x == 0) s_tile = 0x7fffffff;
+    {  // ---- stage tiles t_w and t_w + 1 of the set's in-tile cumulative weights
+      const size_t w_base = (size_t)t_w * kTile;
+      const int w_len = (int)min((size_t)(kAncWinTiles * kTile), v.n_particles - w_base);
+      if (((gbase + w_base) & 1) == 0) {
+        const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(cw_set + w_base);
+        ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(s_cw);
+        for (int j = threadIdx.x; 2 * j + 1 < w_len; j += kTileThreads) dst[j] = __ldcg(src + j);
+        if ((w_len & 1) && threadIdx.x == 0) s_cw[w_len - 1] = __ldcg(cw_set + w_base + w_len - 1);
+      } else {
+        for (int j = threadIdx.x; j < w_len; j += kTileThreads) s_cw[j] = __ldcg(cw_set + w_base + j);
+      }
+    }
+    __syncthreads();
+    while (k < n_mine) {
+      const u128 thr = slot_threshold(si, il0 + k);
+      bool fresh = false;   // a tile this thread has not searched yet
+      if (t < 0 || (thr > tile_end && t < T - 1)) {
+        const int t_from = t < 0 ? t_w : t + 1;   // (t < 0 only in the first round: t_w = t_a)
+        t = (t_from < T - 1 && thr > pre[t_from]) ? tile_lower_bound(pre, t_from + 1, T, thr)
+                                                  : t_from;
+        before = t ? pre[t - 1] : (u128)0;
+        tile_end = pre[t];
+        tlen = (int)min((size_t)kTile, v.n_particles - (size_t)t * kTile);
+        fresh = true;
+        pos = 0;
+      }
+      if (t >= t_w + kAncWinTiles) {   // beyond the window: ask for it, wait for the next round
+        atomicMin(&s_tile, t);   // (pos == 0: the tile is searched afresh next round)
+        break;
+      }
+      const u128 d = thr > before ? thr - before : (u128)0;
+      const unsigned long long rem = (unsigned long long)(d >> 64) ? ~0ULL : (unsigned long long)d;
+      const unsigned long long *a = s_cw + (t - t_w) * kTile;
+      pos = (fresh || pos == 0) ? tile_search(a, tlen, rem) : tile_search_from(a, pos, tlen, rem);
+      out[k] = (int)(gbase + (size_t)t * kTile + pos);
+      ++k;
+    }
+    __syncthreads();
+    const int t_next = s_tile;
+    if (t_next == 0x7fffffff) break;   // every slot of the block has its ancestor
+    t_w = t_next;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Stand-alone gather (src -> dst) by the ancestors K3 wrote, used where the
+// resampled state must exist in memory: snapshots and model$resample.
 // ---------------------------------------------------------------------------
 template <int NS>
 __global__ void __launch_bounds__(kGatherThreads)
-k_resample_gather(View v, int row, const double *__restrict__ src_buf,
-                  double *__restrict__ dst_buf, int *__restrict__ kappa_out) {
+k_resample_gather(View v, const int *__restrict__ kappa, const double *__restrict__ src_buf,
+                  double *__restrict__ dst_buf) {
   if (v.flags[0]) return;
   const size_t i = (size_t)blockIdx.x * kGatherThreads + threadIdx.x;
   if (i >= v.n_total) return;
-  const size_t set = set_of(v, i);
-  size_t src = i;
-  if (row < 0 || !datum_is_na(v, row, set)) src = resample_source(v, set, i - set * v.n_particles);
+  const size_t src = (size_t)__ldcs(kappa + i);
 #pragma unroll
-  for (int s = 0; s < NS; ++s) dst_buf[(size_t)s * v.ld + i] = src_buf[(size_t)s * v.ld + src];
-  if (kappa_out) kappa_out[i] = (int)src;
+  for (int s = 0; s < NS; ++s)
+    __stcs(dst_buf + (size_t)s * v.ld + i, __ldcs(src_buf + (size_t)s * v.ld + src));
 }
 
 // End of a filter call over rows [first, last): bring the live state back into
-// v.y.  The last row always wrote v.y_tmp.  Running: resample row last-1 (if it
-// was weighed) on the way.  Stopped at row rs: the post-update state of rs, as
-// it is (R breaks before resampling), from whichever buffer rs wrote.
+// v.y.  The last row always wrote v.y_tmp.  Running: the resampling of row last-1
+// (kappa != nullptr: it was weighed) on the way.  Stopped at row rs: the post-update
+// state of rs, as it is (R breaks before resampling), from whichever buffer rs wrote.
 template <int NS>
 __global__ void __launch_bounds__(kGatherThreads)
-k_finish_state(View v, int last, int last_weighted, int *__restrict__ kappa_out) {
+k_finish_state(View v, int last, const int *__restrict__ kappa) {
   const size_t i = (size_t)blockIdx.x * kGatherThreads + threadIdx.x;
   if (i >= v.n_total) return;
   if (v.flags[0]) {
@@ -716,14 +811,12 @@ k_finish_state(View v, int last, int last_weighted, int *__restrict__ kappa_out)
     }
     return;
   }
-  const size_t set = set_of(v, i);
-  size_t src = i;
-  if (last_weighted && !datum_is_na(v, last - 1, set))
-    src = resample_source(v, set, i - set * v.n_particles);
+  const size_t src = kappa ? (size_t)__ldcs(kappa + i) : i;
 #pragma unroll
-  for (int s = 0; s < NS; ++s) v.y[(size_t)s * v.ld + i] = v.y_tmp[(size_t)s * v.ld + src];
-  if (kappa_out) kappa_out[i] = (int)src;
+  for (int s = 0; s < NS; ++s)
+    __stcs(v.y + (size_t)s * v.ld + i, __ldcs(v.y_tmp + (size_t)s * v.ld + src));
 }
+
 
 // ---- small kernels off the hot path ---------------------------------------
 

@@ -43,22 +43,22 @@ struct SetData {
 //   inf  [n_sets][n_tab]                     entries of the infection table
 //   walk [n_sets][n_const][n_wrows][kWalkK]  walk tables (samplers.cuh)
 struct LeanTabs {
-  const double2 *inf;
+  const double4 *inf;
   const double *walk;
   uint32_t n_tab, n_wrows;
-  int pow_groups;   // groups of three bits beyond bit 0 in a count below n_tab
 };
 
 // ---- memo-table entries ----------------------------------------------------
-// Infection: entry I = {q, q/(1-q)} with q = p_SI(I) dt, {0, 0} when the
-// probability is zero (no draw), {-1, .} when it is not in (0, 1/2] or r is
-// near the ends of the exponent range.
-__device__ __forceinline__ double2 infection_entry(double beta, double n_tot, double dt, int I) {
+// Infection: entry I = {q, q/(1-q), log(1-q), 0} with q = p_SI(I) dt; q = 0 when the
+// probability is zero (no draw), q = -1 when it is not in (0, 1/2] or r is near the
+// ends of the exponent range.  q and r are the values the exact walk uses; the
+// logarithm feeds the fast walk's first term (samplers.cuh).
+__device__ __forceinline__ double4 infection_entry(double beta, double n_tot, double dt, int I) {
   const double p = (1.0 - det_exp(-beta * (double)I / n_tot)) * dt;
-  if (p == 0.0) return make_double2(0.0, 0.0);
+  if (p == 0.0) return make_double4(0.0, 0.0, 0.0, 0.0);
   const double r = p / (1.0 - p);
   const bool plain = p > 0.0 && p <= 0.5 && r > 1e-270 && r < 1e270;
-  return make_double2(plain ? p : -1.0, r);
+  return make_double4(plain ? p : -1.0, r, plain ? det_log(1.0 - p) : 0.0, 0.0);
 }
 
 // y (doubles) -> int32 compartments; false unless every value is an integer in
@@ -79,19 +79,13 @@ __device__ __forceinline__ bool to_counts(const double *y, int *yi) {
 // Binomial(S, q) for a state-dependent probability: e = entry I of the set's
 // infection table.  Returns the draw, or -1 (generator untouched) when the
 // general code must take over: probability outside (0, 1/2], S q >= 10 (BTRS), or
-// a walk that met one of its rare exits.
-// f0 = (1-q)^S is asked for separately (infection_f0) so a model can compute it while
-// the loads of another draw are in flight: it consumes no uniform.
-__device__ __forceinline__ double infection_f0(int S, double2 e, int pow_groups) {
-  return pow_int_lean(1.0 - e.x, S, pow_groups);
-}
+// a walk the certificate of walk_fast does not cover.
 template <int SCR>
-__device__ __forceinline__ int draw_infection_lean(Xoshiro &rng, int S, double2 e, double f0,
-                                                   uint32_t s_inv) {
+__device__ __forceinline__ int draw_infection_lean(Xoshiro &rng, int S, double4 e,
+                                                   uint32_t s_exp2) {
   if (S == 0 || e.x == 0.0) return 0;
-  const double Sd1 = (double)(S + 1);
-  if (e.x < 0.0 || (Sd1 - 1.0) * e.x >= 10.0) return -1;
-  const int k = walk_lean<SCR>(rng, S, e.y, f0, e.y * Sd1, s_inv);
+  if (e.x < 0.0 || (double)S * e.x >= 10.0) return -1;
+  const int k = walk_fast<SCR>(rng, S, e.x, e.y, e.z, s_exp2);
   if (k < 0) xo_rewind(rng);
   return k;
 }
@@ -140,7 +134,7 @@ struct SirModel {
   __device__ __forceinline__ static void walk_row(int, int n, const double *d, double *row) {
     fill_walk_row(d[D_P_IR], d[D_Q_IR], d[D_QQ_IR], d[D_R_IR], n, row);
   }
-  __device__ __forceinline__ static double2 inf_entry(int I, const double *d) {
+  __device__ __forceinline__ static double4 inf_entry(int I, const double *d) {
     return infection_entry(d[D_BETA], d[D_NTOT], d[D_DT], I);
   }
 
@@ -222,21 +216,20 @@ struct SirModel {
   template <int SCR>
   __device__ __forceinline__ static bool lean_update(bool reset, int *y, Xoshiro &rng,
                                                      const Lean &c, const LeanTabs &t,
-                                                     uint32_t s_inv) {
+                                                     uint32_t s_exp2) {
     const int S = y[0], I = y[1];
     // both draws' table entries depend on the state at the start of the step alone:
-    // ask for them together, and raise (1-q)^S -- which takes no uniform -- while the
-    // walk-table row is on its way
+    // ask for them together
     const double *row_ir = walk_row_ptr(I, c.set * kConst + C_IR, t);
-    const double2 e_si = __ldg(t.inf + (c.set * t.n_tab + (uint32_t)I));
+    const double4 e_si =
+        ldg_f64x4(reinterpret_cast<const double *>(t.inf + (c.set * t.n_tab + (uint32_t)I)));
     const double4 F_ir = ldg_f64x4(row_ir);
-    const double f0 = infection_f0(S, e_si, t.pow_groups);
     int n_IR = 0;
     if (I != 0) {
       n_IR = draw_const_lean<SCR>(rng, I, row_ir, F_ir, t);
       if (n_IR < 0) return false;
     }
-    const int n_SI = draw_infection_lean<SCR>(rng, S, e_si, f0, s_inv);
+    const int n_SI = draw_infection_lean<SCR>(rng, S, e_si, s_exp2);
     if (n_SI < 0) {
       if (I != 0) xo_rewind(rng);  // the recovery draw's uniform
       return false;
@@ -279,7 +272,7 @@ struct SirsModel {
     if (c == C_IR) fill_walk_row(d[D_P_IR], d[D_Q_IR], d[D_QQ_IR], d[D_R_IR], n, row);
     else fill_walk_row(d[D_P_RS], d[D_Q_RS], d[D_QQ_RS], d[D_R_RS], n, row);
   }
-  __device__ __forceinline__ static double2 inf_entry(int I, const double *d) {
+  __device__ __forceinline__ static double4 inf_entry(int I, const double *d) {
     return infection_entry(d[D_BETA], d[D_NTOT], d[D_DT], I);
   }
 
@@ -346,10 +339,11 @@ struct SirsModel {
   template <int SCR>
   __device__ __forceinline__ static bool lean_update(bool reset, int *y, Xoshiro &rng,
                                                      const Lean &c, const LeanTabs &t,
-                                                     uint32_t s_inv) {
+                                                     uint32_t s_exp2) {
     const int S = y[0], I = y[1], R = y[2];
-    const double2 e_si = __ldg(t.inf + (c.set * t.n_tab + (uint32_t)I));
-    const int n_SI = draw_infection_lean<SCR>(rng, S, e_si, infection_f0(S, e_si, t.pow_groups), s_inv);
+    const double4 e_si =
+        ldg_f64x4(reinterpret_cast<const double *>(t.inf + (c.set * t.n_tab + (uint32_t)I)));
+    const int n_SI = draw_infection_lean<SCR>(rng, S, e_si, s_exp2);
     if (n_SI < 0) return false;
     // did the infection draw take a uniform?  (it returns 0 without one for S = 0 or p = 0)
     const bool si_drew = S != 0 && e_si.x != 0.0;

@@ -67,8 +67,8 @@ struct PersistArgs {
 };
 
 // first index in [lo, hi] (hi = last valid) with arr[idx] >= key, arr in shared memory
-__device__ __forceinline__ int smem_lower_bound(const unsigned long long *arr, int lo, int hi,
-                                                unsigned long long key) {
+template <class K>
+__device__ __forceinline__ int smem_lower_bound(const K *arr, int lo, int hi, K key) {
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
     if (arr[mid] >= key) hi = mid; else lo = mid + 1;
@@ -81,10 +81,11 @@ __global__ void __launch_bounds__(kPersistThreads, MCB_PERSIST_MINBLOCKS)
 k_filter_persistent(View v, PersistArgs a) {
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
-  __shared__ double2 s_inv[kInvSmall + 1];
-  __shared__ unsigned long long s_pre[kPersistMaxBlocks];   // inclusive prefix of block sums
+  __shared__ double s_exp2[kExp2Tab];
+  __shared__ u128 s_pre[kPersistMaxBlocks];   // inclusive prefix of block sums (128-bit: kernels.cuh)
   __shared__ unsigned long long s_win[kPersistThreads / 32][2 * kPersistThreads];
   __shared__ unsigned long long s_warp[kPersistThreads / 32];
+  __shared__ u128 s_warp2[kPersistThreads / 32];
   __shared__ unsigned long long s_key[kPersistThreads / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -92,7 +93,7 @@ k_filter_persistent(View v, PersistArgs a) {
   const size_t i = (size_t)blockIdx.x * kPersistThreads + tid;
   const size_t N = v.n_total;
   const bool live = i < N;
-  if (tid <= kInvSmall) s_inv[tid] = __ldg(g_inv_small + tid);
+  if (tid < kExp2Tab) s_exp2[tid] = __ldg(g_exp2_tab + tid);
   __syncthreads();
 
   const SetData sd{v.derived, v.n_tab};
@@ -145,11 +146,12 @@ k_filter_persistent(View v, PersistArgs a) {
   // staged in shared memory by the warp when its 32 slots fall into at most two
   // neighbouring blocks (thresholds grow with the slot), else searched in place.
   auto resample_source_p = [&](size_t slot) -> size_t {
-    const unsigned long long thr = (unsigned long long)__double2ll_ru(uu0 + (double)slot * du);
+    const u128 thr = ceil_to_u128(uu0 + (double)(uint32_t)slot * du);
     const int nb = n_blocks;
-    const int b = smem_lower_bound(s_pre, 0, nb - 1, thr);
-    const unsigned long long before = b ? s_pre[b - 1] : 0ULL;
-    const unsigned long long rem = thr > before ? thr - before : 0ULL;
+    const int b = smem_lower_bound<u128>(s_pre, 0, nb - 1, thr);
+    const u128 before = b ? s_pre[b - 1] : (u128)0;
+    const u128 dd = thr > before ? thr - before : (u128)0;
+    const unsigned long long rem = (unsigned long long)(dd >> 64) ? ~0ULL : (unsigned long long)dd;
     const int b0 = __shfl_sync(0xffffffffu, b, 0);
     const int b31 = __shfl_sync(0xffffffffu, b, 31);
     const size_t base = (size_t)b * kPersistThreads;
@@ -165,7 +167,7 @@ k_filter_persistent(View v, PersistArgs a) {
       }
       __syncwarp();
       const int off = (b - b0) * kPersistThreads;
-      pos = smem_lower_bound(win + off, 0, in_blk - 1, rem);
+      pos = smem_lower_bound<unsigned long long>(win + off, 0, in_blk - 1, rem);
       __syncwarp();
     } else {
       const unsigned long long *cw = v.cw + base;
@@ -199,7 +201,7 @@ k_filter_persistent(View v, PersistArgs a) {
     }
     double lw = neg_inf;
     if (live) {
-      run_model_steps<M, SCR>(v, sd, ctx, 0, y, rng, t, n_steps, det, s_inv);
+      run_model_steps<M, SCR>(v, sd, ctx, 0, y, rng, t, n_steps, det, s_exp2);
       touched = touched || n_steps > 0;
       if (hist) save_slice(rel + 1, i);
       if (weigh) {
@@ -240,8 +242,7 @@ k_filter_persistent(View v, PersistArgs a) {
     const bool dead = !(mx > neg_inf);
     unsigned long long x = 0;
     if (live && !dead) {
-      const double scale = bits_to_double((uint64_t)(1023 + v.shift) << 52);
-      x = (unsigned long long)__double2ll_rn(det_exp(lw - mx) * scale);
+      x = weight_to_fixed(det_exp_nonpos(lw - mx));
     }
     unsigned long long incl = x;
 #pragma unroll
@@ -266,35 +267,36 @@ k_filter_persistent(View v, PersistArgs a) {
       constexpr int kPer = (kPersistMaxBlocks + kPersistThreads - 1) / kPersistThreads;  // 10
       const int per = (n_blocks + kPersistThreads - 1) / kPersistThreads;
       const int lo = tid * per;
+      // a block sum is at most 2^60 (256 weights of at most 2^52): a thread's kPer <= 10
+      // of them fit 64 bits, the sums across threads are 128-bit
+      static_assert(kPer <= 15, "a thread's block sums must fit 64 bits");
       unsigned long long xs[kPer];
       unsigned long long local = 0;
 #pragma unroll
       for (int j = 0; j < kPer; ++j) {
-        xs[j] = (j < per && lo + j < n_blocks) ? __ldcg(a.blk_sum + lo + j) : 0ULL;
-        local += xs[j];
+        if (j < per && lo + j < n_blocks) local += __ldcg(a.blk_sum + lo + j);
         xs[j] = local;
       }
-      unsigned long long inc2 = local;
+      u128 inc2 = local;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
-        const unsigned long long o = shfl_up_u64(inc2, d);
+        const u128 o = shfl_up_u128(inc2, d);
         if (lane >= d) inc2 += o;
       }
-      __syncthreads();   // s_warp is free again
-      if (lane == 31) s_warp[warp] = inc2;
+      if (lane == 31) s_warp2[warp] = inc2;
       __syncthreads();
-      unsigned long long offset = inc2 - local;
+      u128 offset = inc2 - local;
 #pragma unroll
       for (int w = 0; w < kPersistThreads / 32; ++w)
-        if (w < warp) offset += s_warp[w];
+        if (w < warp) offset += s_warp2[w];
 #pragma unroll
       for (int j = 0; j < kPer; ++j)
         if (j < per && lo + j < n_blocks) s_pre[lo + j] = xs[j] + offset;
       __syncthreads();
     }
     // ---- finish the interval (finish_set + the early-exit rule), in every thread alike
-    const unsigned long long tot = s_pre[n_blocks - 1];
-    const double tot_d = (double)tot;
+    const u128 tot = s_pre[n_blocks - 1];
+    const double tot_d = u128_to_double(tot);
     const double u = __ldg(v.u_draws + row);
     uu0 = tot_d * u / n_d;
     du = tot_d / n_d;
@@ -302,7 +304,7 @@ k_filter_persistent(View v, PersistArgs a) {
     if (dead || tot == 0) {
       stop = true;
     } else {
-      const double mean = (tot_d * bits_to_double((uint64_t)(1023 - v.shift) << 52)) / n_d;
+      const double mean = (tot_d * 0x1p-52) / n_d;
       ll += det_log(mean) + mx;
       stop = v.n_min > 0 && ll < __ldg(v.min_ll);
     }

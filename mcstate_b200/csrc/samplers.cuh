@@ -52,10 +52,6 @@ __device__ __forceinline__ double pow_int(double x, int n) {
 // with IEEE division: the walk reads its divisor and reciprocal with one uniform load
 constexpr int kInvSmall = 64;
 __constant__ double2 c_inv_small[kInvSmall];
-// the same table in global memory: a block stages it in shared memory with one
-// coalesced load per thread (per-thread indexing of the constant bank serialises);
-// one spare entry (the lean walk looks two entries ahead)
-__device__ double2 g_inv_small[kInvSmall + 1];
 __constant__ double c_stirling_tail[10] = {
     0.0810614667953272,  0.0413406959554092,  0.0276779256849983, 0.02079067210376509,
     0.0166446911898211,  0.0138761288230707,  0.0118967099458917, 0.0104112652619720,
@@ -120,41 +116,37 @@ __device__ __forceinline__ double binomial_inversion(Xoshiro &rng, int n, double
 }
 
 // ---------------------------------------------------------------------------
-// Lean twins used by the integer-state path of the run kernel (models.cuh).
-// Same operations in the same order as the functions above -- same bits -- with
-// the bookkeeping stripped: comparisons of non-negative doubles are done on
-// their bit patterns (integer pipe instead of the half-rate fp64 pipe), the
-// {k, 1/k} table is read from shared memory with one 16-byte load, and every
-// rare event (walk past the table, stalled f, k > n) leaves to a cold function.
+// The lean path of the run kernel (models.cuh): the SAME draws as the functions
+// above -- same bits -- computed another way.
+//
+// Certified fast walk.  The inversion walk above is a chain of dependent,
+// individually rounded operations (integer power, correctly rounded divisions,
+// u -= f): exact to reproduce, slow to run.  But its OUTCOME is just "the k
+// whose slice [F_{k-1}, F_k) of the CDF holds u".  So the lean path evaluates
+// the CDF approximately with cheap operations -- f_0 = exp(n log(1-q)) from a
+// table-driven exponential, f_k = f_{k-1} (g (1/k) - r) with one fma per factor
+// -- and accepts the k it finds only when u is further than kWalkEps from both
+// ends of the slice, a margin far above the worst-case difference between the
+// approximate and the exact chain (bound below).  Anything closer, or anything
+// the exact walk treats specially (a factor that may round to one -> a stalled
+// f; a walk beyond the table), is handed back to the exact code with the
+// generator rewound.  The result is therefore ALWAYS the exact walk's; only
+// the cost differs (a draw is handed back about once in 10^9).
+//
+// Error bound (n q < 10, q <= 1/2, k <= 63, n < 2^16; ulp = 2^-52):
+//   exact chain   u_k = u - F*_{k-1} + d,  |d| <= k 2^-54 (each u -= f rounds a
+//                 value below one), so it walks on at k iff u >= F*_k - d;
+//   f_0           n log(1-q) carries <= 14.5 * 2 ulp absolute, the exponential
+//                 <= 2^-47 relative, pow_int's own roundings <= 32 * 2^-53:
+//                 together <= 2^-45 relative;
+//   factors       g (1/k) - r against RN(RN(g/k) - r): <= 2 ulp of g/k, i.e.
+//                 <= 2 ulp (n+1)/(n+1-k) relative to the factor, <= 2^-45 for the
+//                 k <= min(n, 63) walked; 63 of them compound to <= 2^-39;
+//   sums          F_k <= 1 + 2^-30, adding <= 64 terms rounds <= 2^-47.
+// Total |F_k (approximate) - F*_k (exact)| < 2^-38; kWalkEps = 2^-32 leaves a
+// factor 64.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ long long as_ll(double x) { return __double_as_longlong(x); }
-
-// pow_int with the first multiplication peeled (1.0 * x == x) and the squaring
-// moved to the top of the loop: the same products in the same order (a product
-// by a square the count has no bit for is skipped, as pow_int never forms it).
-// The conditional product is one predicated DMUL.
-__device__ __forceinline__ void mul_if(double &acc, double x, int bit) {
-  asm("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p mul.rn.f64 %0, %0, %1;\n\t}"
-      : "+d"(acc) : "d"(x), "r"(bit));
-}
-// `groups`: how many groups of three bits beyond bit 0 the largest count can have
-// (warp-uniform, from the table size): the loop runs on it, not on the lane's n,
-// so there is no per-lane loop control.  Squarings past a lane's top bit are
-// computed and never multiplied in.
-__device__ __forceinline__ double pow_int_lean(double x, int n, int groups) {
-  double acc = (n & 1) ? x : 1.0;
-#pragma unroll 1
-  for (int g = 0; g < groups; ++g) {
-    x *= x;
-    mul_if(acc, x, n & 2);
-    x *= x;
-    mul_if(acc, x, n & 4);
-    x *= x;
-    mul_if(acc, x, n & 8);
-    n >>= 3;
-  }
-  return acc;
-}
 
 // One step back of the xoshiro256 state walk (the map is linear and invertible):
 // s1 = A ^ (s1 << 17) with A = s1' ^ s2' unrolls to four shifted terms.
@@ -170,17 +162,6 @@ __device__ __forceinline__ void xo_rewind(Xoshiro &r) {
   r.s3 = s3m ^ s1;
 }
 
-// The CDF walk for the lean path.  Returns k >= 0, or -1 when anything unusual
-// happened (the walk ran past min(n, table), or f stopped changing): the caller
-// then rewinds the generator by the one uniform drawn here and repeats the draw
-// with the general code, which handles those cases by the book.
-// s_inv: the {k, RN(1/k)} table in shared memory; g = r (n + 1) must be away from
-// overflow/underflow (the caller's table entry guarantees it).
-__device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
-  double2 e;
-  asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(e.x), "=d"(e.y) : "r"(addr));
-  return e;
-}
 __device__ __forceinline__ double2 ldg_f64x2(const double *p) {
   double2 e;
   asm("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(e.x), "=d"(e.y) : "l"(p));
@@ -193,110 +174,96 @@ __device__ __forceinline__ double4 ldg_f64x4(const double *p) {
       : "=d"(e.x), "=d"(e.y), "=d"(e.z), "=d"(e.w) : "l"(p));
   return e;
 }
-
-// s_inv_addr: shared-window address of the {k, RN(1/k)} table.
-// One predicate drives each step: keep walking while u >= f, f changed, and the
-// table has another entry; the two rare reasons are told apart after the walk
-// (the order of the reference's tests is kept: a stalled f abandons the attempt
-// whatever u is).
-// Every lane of a warp is at the same k in the same step, so the first MCB_PEEL
-// steps are written out with their divisor known at compile time: g/1, g/2, g/4,
-// g/8 are exact scalings (g is away from underflow), the others take k and its
-// reciprocal as immediates (no table load, no address arithmetic).  A warp walks
-// as far as its slowest lane (about 8 steps at the benchmark's parameters), so
-// these steps are what nearly every warp executes.  The loop after them is
-// unrolled by two so f and its successor swap roles without moves.
-#ifndef MCB_PEEL
-#define MCB_PEEL 12   // measured at 2^20: 4 -> 90.1 us, 8 -> 88.0, 12 -> 87.2, 16 -> 87.4
-#endif
-// RN(1/k) for the written-out steps, as constant-bank operands (a 64-bit immediate
-// would cost two uniform moves per use)
-__constant__ double c_recip[17] = {0.0,        1.0,        1.0 / 2.0,  1.0 / 3.0,  1.0 / 4.0,
-                                   1.0 / 5.0,  1.0 / 6.0,  1.0 / 7.0,  1.0 / 8.0,  1.0 / 9.0,
-                                   1.0 / 10.0, 1.0 / 11.0, 1.0 / 12.0, 1.0 / 13.0, 1.0 / 14.0,
-                                   1.0 / 15.0, 1.0 / 16.0};
-// One written-out step.  The two ways out need nothing but k (a stalled f abandons
-// the attempt whatever u is -- the order of the reference's tests), so no value has to
-// be kept in a fixed register for them and the steps chain without moves.  (Measured:
-// one compound exit to a common label 87.2 us, these two returns 86.3, per-step
-// landing pads 88.6.)
-#define MCB_WALK_STEP(K, FACTOR)                 \
-  u -= f;                                        \
-  fn = f * ((FACTOR) - r);                       \
-  if (fn == f) return -1;                        \
-  if (!(u >= fn)) return (K);                    \
-  f = fn;
-#define MCB_WALK_DIV(K) div_small_int(g, (double)(K), c_recip[K])
-template <int SCR>
-__device__ __forceinline__ int walk_lean(Xoshiro &rng, int n, double r, double f0, double g,
-                                         uint32_t s_inv_addr) {
-  const int kmax = min(n, kInvSmall - 1);
-  double u = xo_real<SCR>(rng);
-  double f = f0, fn;
-  if (!(u >= f)) return 0;   // n >= 1: there is a k = 1 to move to
-  uint32_t a = s_inv_addr;
-  if (kmax > MCB_PEEL) {     // the usual case: every written-out step has a successor
-    MCB_WALK_STEP(1, g)
-    MCB_WALK_STEP(2, g * 0.5)
-    // g/6, g/12 and g/10 are g/3 and g/5 scaled by a power of two: the same bits as
-    // dividing (RN commutes with an exact scaling, g is away from underflow)
-    const double g3 = MCB_WALK_DIV(3);
-    MCB_WALK_STEP(3, g3)
-    MCB_WALK_STEP(4, g * 0.25)
-#if MCB_PEEL >= 6
-    const double g5 = MCB_WALK_DIV(5);
-    MCB_WALK_STEP(5, g5)
-    MCB_WALK_STEP(6, g3 * 0.5)
-#endif
-#if MCB_PEEL >= 8
-    MCB_WALK_STEP(7, MCB_WALK_DIV(7))
-    MCB_WALK_STEP(8, g * 0.125)
-#endif
-#if MCB_PEEL >= 10
-    MCB_WALK_STEP(9, MCB_WALK_DIV(9))
-    MCB_WALK_STEP(10, g5 * 0.5)
-#endif
-#if MCB_PEEL >= 12
-    MCB_WALK_STEP(11, MCB_WALK_DIV(11))
-    MCB_WALK_STEP(12, g3 * 0.25)
-#endif
-#if MCB_PEEL >= 16
-    MCB_WALK_STEP(13, MCB_WALK_DIV(13))
-    MCB_WALK_STEP(14, MCB_WALK_DIV(14))
-    MCB_WALK_STEP(15, MCB_WALK_DIV(15))
-    MCB_WALK_STEP(16, g * 0.0625)
-#endif
-    a += 16u * (uint32_t)(MCB_PEEL < 6 ? 4 : MCB_PEEL);
-  }
-  // whatever is left (and counts too small for the written-out steps): the loop
-  const uint32_t a_end = s_inv_addr + 16u * (uint32_t)kmax;
-  for (;;) {
-    // The factors c_k = g/k - r do not depend on f or u: the next two are computed
-    // side by side (two independent dependency chains), then applied in order.
-    // The second may go unused; the table has one spare entry for its load.
-    const double2 e1 = lds_f64x2(a + 16);
-    const double2 e2 = lds_f64x2(a + 32);
-    double q1 = g * e1.y, q2 = g * e2.y;
-    double r1 = fma(-q1, e1.x, g), r2 = fma(-q2, e2.x, g);
-    q1 = fma(r1, e1.y, q1); q2 = fma(r2, e2.y, q2);
-    r1 = fma(-q1, e1.x, g); r2 = fma(-q2, e2.x, g);
-    const double c1 = fma(r1, e1.y, q1) - r, c2 = fma(r2, e2.y, q2) - r;
-    u -= f;
-    fn = f * c1;
-    a += 16;
-    if (!((u >= fn) & (fn != f) & (a < a_end))) break;
-    u -= fn;
-    f = fn;
-    fn = f * c2;
-    a += 16;
-    if (!((u >= fn) & (fn != f) & (a < a_end))) break;
-    f = fn;
-  }
-  // stalled, or out of table with u >= f still
-  return ((fn == f) | (u >= fn)) ? -1 : (int)((a - s_inv_addr) >> 4);
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double e;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(e) : "r"(addr));
+  return e;
 }
-#undef MCB_WALK_STEP
-#undef MCB_WALK_DIV
+
+// 2^(j/32), j = 0..31, filled by the host; a block stages it in shared memory
+constexpr int kExp2Tab = 32;
+__device__ double g_exp2_tab[kExp2Tab];
+// 1/k as constant-bank operands (entry 0 unused); approximate values are all the fast
+// walk needs
+__constant__ double c_recip[kInvSmall];
+__constant__ double c_fexp[7] = {
+    46.16624130844683,           // 32 / ln 2
+    0x1.62e42fefa0000p-6,        // ln 2 / 32, leading 37 bits (k * this is exact for |k| < 2^16)
+    0x1.cf79abc9e3b3ap-45,       // ln 2 / 32, the rest
+    1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
+
+// exp(x) for x in [-700, 0], relative error below 2^-47: k = rint(32 x / ln 2),
+// r = x - k ln2/32 (|r| <= 0.0109), exp(x) = 2^(k >> 5) 2^((k & 31)/32) (1 + r + ... + r^5/120).
+// Not reproducible to the last bit across implementations and not meant to be: it
+// only proposes what the certificate of the fast walk then accepts or rejects.
+__device__ __forceinline__ double fast_exp_neg(double x, uint32_t s_exp2_addr) {
+  const double magic = 6755399441055744.0;   // 1.5 * 2^52: adding it rounds to an integer
+  const double tm = fma(x, c_fexp[0], magic);
+  const int ki = __double2loint(tm);
+  const double kd = tm - magic;
+  double r = fma(-kd, c_fexp[1], x);
+  r = fma(-kd, c_fexp[2], r);
+  double p = fma(r, c_fexp[3], c_fexp[4]);
+  p = fma(p, r, c_fexp[5]);
+  p = fma(p, r, c_fexp[6]);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const double v = lds_f64(s_exp2_addr + 8u * (uint32_t)(ki & (kExp2Tab - 1))) * p;
+  return __hiloint2double(__double2hiint(v) + ((ki >> 5) << 20), __double2loint(v));
+}
+
+constexpr double kWalkEps = 0x1p-32;
+
+// Binomial(n, q) by the certified fast walk: n >= 1, q in (0, 1/2] with n q < 10,
+// r = q/(1-q), lq = log(1-q) (both from the set's table).  Draws ONE uniform.  Returns
+// the exact walk's k, or -1 when the exact code must decide (the caller rewinds the
+// generator by that one uniform).
+template <int SCR>
+__device__ __forceinline__ int walk_fast(Xoshiro &rng, int n, double q, double r, double lq,
+                                         uint32_t s_exp2_addr) {
+  const double nd = (double)n, nd1 = nd + 1.0;
+  // the factor g/k - r passes one at k = q (n + 1): if that is (nearly) an integer the
+  // exact chain may meet f_k == f_{k-1} there and abandon the attempt -- its call
+  const double mode = q * nd1;
+  const double mode_r = (mode + 6755399441055744.0) - 6755399441055744.0;
+  const double f0 = fast_exp_neg(nd * lq, s_exp2_addr);
+  const double g = r * nd1;
+  const double u = xo_real<SCR>(rng);
+  if (fabs(mode - mode_r) <= mode * 0x1p-30) return -1;
+  double F = f0, f = f0;   // F = F_k, the CDF up to and including k
+  int k;
+  if (n >= 8) {
+    // the usual case: the first eight steps written out, each one compare, one fma for
+    // the factor (1/k straight from the constant bank), one product, one sum
+#define MCB_FAST_STEP(K)                               \
+    if (!(u >= F)) { k = (K) - 1; goto done; }         \
+    f *= fma(g, c_recip[K], -r);                       \
+    F += f;
+    MCB_FAST_STEP(1) MCB_FAST_STEP(2) MCB_FAST_STEP(3) MCB_FAST_STEP(4)
+    MCB_FAST_STEP(5) MCB_FAST_STEP(6) MCB_FAST_STEP(7) MCB_FAST_STEP(8)
+#undef MCB_FAST_STEP
+    k = 8;
+    const int kmax = min(n, kInvSmall - 1);
+    while (u >= F) {
+      if (k >= kmax) return -1;
+      ++k;
+      f *= fma(g, c_recip[k], -r);
+      F += f;
+    }
+  } else {
+    k = 0;
+    while (u >= F) {
+      if (k >= n) return -1;
+      ++k;
+      f *= fma(g, c_recip[k], -r);
+      F += f;
+    }
+  }
+done:
+  // F_{k-1} is F - f to within a rounding, far inside the margin (k = 0: the slice starts
+  // at zero, and a u below the margin is simply handed back)
+  return ((F - u > kWalkEps) & (u - (F - f) >= kWalkEps)) ? k : -1;
+}
 
 // ---------------------------------------------------------------------------
 // Walk tables: a draw whose probability is fixed by the parameter set

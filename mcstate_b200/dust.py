@@ -168,6 +168,7 @@ class dust_model:
                              _lib.SEED_PER_SET if seed_per_set else _lib.SEED_SHARED,
                              generator.scrambler, int(deterministic), device_id, C.byref(h)))
         self._h = h
+        self._device = device_id
         self._n_state = generator.n_state
         self._n_particles = int(n_particles)
         self._n_pars = n_pars
@@ -515,6 +516,20 @@ class dust_model:
         ll = np.zeros(self._n_sets)
         self._ck(self._L.mcb_filter_collect(self._h, ptr(ll, f64p)))
         return ll
+
+    def log_likelihood_device(self):
+        """The log-likelihood vector [n_pars] an enqueued filter writes, as a torch tensor
+        over the handle's own device memory (no copy): what a sharded caller hands to its
+        all-gather, in stream order after ``filter_enqueue`` (mcb_log_likelihood_device)."""
+        import torch
+
+        p = C.c_void_p()
+        self._ck(self._L.mcb_log_likelihood_device(self._h, C.byref(p)))
+
+        class _View:   # the CUDA array interface: torch wraps the memory, nothing is copied
+            __cuda_array_interface__ = {"shape": (self._n_sets,), "typestr": "<f8",
+                                        "data": (int(p.value), False), "version": 3}
+        return torch.as_tensor(_View(), device=torch.device("cuda", self._device))
 
     def set_stream(self, cuda_stream):
         self._ck(self._L.mcb_set_stream(self._h, C.c_void_p(cuda_stream)))

@@ -57,6 +57,65 @@ def gather_log_likelihood(local, counts, group=None, device=None):
     return np.concatenate([o[:c].cpu().numpy() for o, c in zip(out, counts)])
 
 
+class likelihood_gather:
+    """The all-gather of per-rank log-likelihood vectors with everything allocated once: a
+    device staging vector, the gathered device matrix and a pinned host copy.  With NCCL the
+    local vector can be the handle's own device memory (``gather_device``), so a data row of
+    SMC^2 costs one stream synchronisation: filter -> all-gather -> device-to-host copy are
+    queued on one stream and waited for together (R/smc2.R:89-108 gathers one step
+    likelihood per parameter particle per row)."""
+
+    def __init__(self, counts, group=None):
+        import torch
+
+        self._dist = _dist()
+        self._group = group
+        self.counts = [int(c) for c in counts]
+        self.world = len(self.counts)
+        self.rank = self._dist.get_rank(group)
+        self.width = max(self.counts)
+        self.nccl = self._dist.get_backend(group) == "nccl"
+        dev = torch.device("cuda", torch.cuda.current_device()) if self.nccl else None
+        self._local = torch.full((self.width,), float("nan"), dtype=torch.float64, device=dev)
+        self._all = torch.empty((self.world * self.width,), dtype=torch.float64, device=dev)
+        self._host = torch.empty((self.world * self.width,), dtype=torch.float64,
+                                 pin_memory=self.nccl)
+        self._take = np.concatenate([np.arange(c) + r * self.width
+                                     for r, c in enumerate(self.counts)])
+
+    def _finish(self, wait):
+        import torch
+
+        self._dist.all_gather_into_tensor(self._all, self._local, group=self._group)
+        if self.nccl:
+            self._host.copy_(self._all, non_blocking=True)
+            if wait:
+                torch.cuda.current_stream().synchronize()
+        else:
+            self._host.copy_(self._all)
+
+    def gather_host(self, local):
+        """local: this rank's values on the host -> every rank's, concatenated."""
+        import torch
+
+        n = self.counts[self.rank]
+        self._local[:n].copy_(torch.as_tensor(np.asarray(local, dtype=np.float64)),
+                              non_blocking=self.nccl)
+        self._finish(True)
+        return self._host.numpy()[self._take].copy()
+
+    def gather_device(self, local_device, wait=None):
+        """local_device: this rank's values as a CUDA tensor written by work already queued
+        on the current stream.  ``wait``: a callable that waits for the stream (the handle's
+        ``filter_collect``), so the caller synchronises once for the row."""
+        n = self.counts[self.rank]
+        self._local[:n].copy_(local_device, non_blocking=True)
+        self._finish(wait is None)
+        if wait is not None:
+            wait()
+        return self._host.numpy()[self._take].copy()
+
+
 class nested_filter_sharded:
     """``particle_filter$new(data_nested, model, n_particles, compare = NULL)`` with the
     populations split over the ranks of a process group (BASELINE config C4).
@@ -100,6 +159,7 @@ class nested_filter_sharded:
         self._na_global = np.stack([np.isnan(vals[pop_col == p]) for p in pops], axis=1)
         self._filter_stream = self._global_filter_stream(seed, model)
         self._attached = False
+        self._gather = likelihood_gather(self._counts, group)
 
     # -- seeds: particle streams of block [lo, hi) start at stream lo * n_particles of the seed
     def _algorithm(self, model):
@@ -137,8 +197,7 @@ class nested_filter_sharded:
             ll = obj.log_likelihood
         else:
             ll = self._filter.run(local_pars, save_history, save_restart)
-        ll = gather_log_likelihood(np.atleast_1d(ll), self._counts, self._group,
-                                   self._tensor_device)
+        ll = self._gather.gather_host(np.atleast_1d(ll))
         # the reference's rule when any population is impossible: the whole vector
         # (R/particle_filter_state.R:463-474, `ll[] <- -Inf`)
         if np.any(ll == -np.inf):

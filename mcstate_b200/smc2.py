@@ -170,6 +170,8 @@ class smc2_engine:
         self._model_theta = theta[self._lo:self._hi].copy()
         self._model = self._new_model(pars.model(self._model_theta))
         self._child = None  # the proposal's model handle, allocated once and reused
+        self._gather_obj = None
+        self._on_torch_stream = False
         self._filter_facade = filter
 
         self.step_current = 0
@@ -206,23 +208,41 @@ class smc2_engine:
                                    state=False, rng=True)
         return self._child
 
+    def _gatherer(self):
+        if self._gather_obj is None:
+            from .sharding import likelihood_gather
+
+            self._gather_obj = likelihood_gather(self._counts, self._group)
+        return self._gather_obj
+
     def _gather(self, local):
         if self._dist is None or self.world == 1:
             return np.asarray(local, dtype=float)
-        from .sharding import gather_log_likelihood
+        return self._gatherer().gather_host(local)
 
-        device = None
-        if self._dist.get_backend(self._group) == "nccl":
-            import torch
+    def _step_likelihood(self, time_end):
+        """One data row on every local filter and the step likelihoods of ALL parameter
+        particles (R/smc2.R:91).  Sharded over GPUs the row is queued, gathered and copied
+        out on one stream and waited for once."""
+        m = self._model
+        if self._dist is None or self.world == 1 or not hasattr(m, "log_likelihood_device"):
+            return self._gather(m.filter(time_end)["log_likelihood"])
+        g = self._gatherer()
+        if not g.nccl:
+            return g.gather_host(m.filter(time_end)["log_likelihood"])
+        import torch
 
-            device = torch.device("cuda", torch.cuda.current_device())
-        return gather_log_likelihood(local, self._counts, self._group, device)
+        if not self._on_torch_stream:
+            m.set_stream(torch.cuda.current_stream().cuda_stream)
+            self._on_torch_stream = True
+        m.filter_enqueue(time_end)
+        return g.gather_device(m.log_likelihood_device(), wait=m.filter_collect)
 
     # ---- R/smc2.R:89-108 ------------------------------------------------------------
     def step(self):
         t = self.step_current + 1
         time_end = int(self._times[t - 1, 1])
-        step_ll = self._gather(self._model.filter(time_end)["log_likelihood"])
+        step_ll = self._step_likelihood(time_end)
         self.n_filter_rows += self._hi - self._lo
         self.log_likelihood = self.log_likelihood + step_ll
         self.log_posterior = self.log_posterior + step_ll

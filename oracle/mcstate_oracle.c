@@ -401,21 +401,41 @@ double orc_scale_log_weights_r(const double *logw, size_t n, double *weights_out
   return log(tot / (double)n) + mx;
 }
 
-static int ceil_log2(size_t n) {
-  int k = 0;
-  while (((size_t)1 << k) < n) ++k;
-  return k;
-}
-
-/* number of fractional bits kept when a weight in [0,1] becomes an integer:
- * n of them must sum below 2^63 */
+/* Fixed-point weights.  A weight in [0, 1] becomes the integer rint(w 2^52): every
+ * weight keeps at least the precision a double sum of weights in [0, 1] has, whatever
+ * the number of particles (a rounding error of at most 2^-53 per weight, against up to
+ * n 2^-53 per addition of a left-to-right fp64 sum).  Sums are 128-bit integers (n
+ * below 2^31 of them stay below 2^83), so they are exact and independent of the order
+ * of summation -- a tiled parallel scan and this serial loop give the same bits. */
+typedef unsigned __int128 u128;
+#define ORC_WEIGHT_SHIFT 52
 int orc_weight_shift(size_t n) {
-  int k = 62 - ceil_log2(n);
-  return k > 52 ? 52 : k;
+  (void)n;
+  return ORC_WEIGHT_SHIFT;
 }
 
-static inline uint64_t weight_to_fixed(double w, int shift) {
-  return (uint64_t)llrint(w * u2d((uint64_t)(1023 + shift) << 52));
+static inline uint64_t weight_to_fixed(double w) {
+  return (uint64_t)llrint(w * 0x1p52);
+}
+
+/* the double nearest to x (ties to even): the top 64 bits with a sticky last bit
+ * are converted (one correctly rounded conversion), then scaled exactly */
+static inline double u128_to_double(u128 x) {
+  const uint64_t hi = (uint64_t)(x >> 64), lo = (uint64_t)x;
+  if (hi == 0) return (double)lo;
+  const int s = 64 - __builtin_clzll(hi);       /* bits of hi in use: 1..63 here */
+  uint64_t v = (hi << (64 - s)) | (lo >> s);
+  if ((lo << (64 - s)) != 0) v |= 1ULL;
+  return (double)v * u2d((uint64_t)(1023 + s) << 52);
+}
+
+/* ceil(d) as an integer, d >= 0 and finite (doubles from 2^52 up are integers) */
+static inline u128 ceil_to_u128(double d) {
+  if (d < 0x1p63) return (u128)(uint64_t)ceil(d);
+  const uint64_t b = d2u(d);
+  const int e = (int)(b >> 52) - 1075;
+  const uint64_t m = (b & 0xfffffffffffffULL) | 0x10000000000000ULL;
+  return (u128)m << e;
 }
 
 /* Compiled-filter flavour: NaN -> -Inf, weights exponentiated in place with the
@@ -431,13 +451,12 @@ double orc_scale_log_weights(double *w, size_t n, int mode) {
     return -INFINITY;
   }
   if (mode == ORC_RESAMPLE_EXACT) {
-    const int shift = orc_weight_shift(n);
-    uint64_t tot = 0;
+    u128 tot = 0;
     for (size_t i = 0; i < n; ++i) {
       w[i] = orc_exp(w[i] - mx);
-      tot += weight_to_fixed(w[i], shift);
+      tot += weight_to_fixed(w[i]);
     }
-    const double mean = ((double)tot * u2d((uint64_t)(1023 - shift) << 52)) / (double)n;
+    const double mean = (u128_to_double(tot) * 0x1p-52) / (double)n;
     return orc_log(mean) + mx;
   }
   double tot = 0.0;
@@ -475,16 +494,15 @@ void orc_particle_resample_r(const double *weights, size_t n, double u0, int *ka
  * depend on summation order and a parallel scan reproduces it bit for bit. */
 void orc_resample_weight(const double *w, size_t n, double u, int mode, int *kappa) {
   if (mode == ORC_RESAMPLE_EXACT) {
-    const int shift = orc_weight_shift(n);
-    uint64_t tot = 0;
-    for (size_t i = 0; i < n; ++i) tot += weight_to_fixed(w[i], shift);
-    const double tot_d = (double)tot;
+    u128 tot = 0;
+    for (size_t i = 0; i < n; ++i) tot += weight_to_fixed(w[i]);
+    const double tot_d = u128_to_double(tot);
     const double uu0 = tot_d * u / (double)n, du = tot_d / (double)n;
-    uint64_t ww = 0;
+    u128 ww = 0;
     size_t j = 0;
     for (size_t i = 0; i < n; ++i) {
-      const uint64_t thr = (uint64_t)ceil(uu0 + (double)i * du);
-      while (ww < thr && j < n) { ww += weight_to_fixed(w[j], shift); ++j; }
+      const u128 thr = ceil_to_u128(uu0 + (double)i * du);
+      while (ww < thr && j < n) { ww += weight_to_fixed(w[j]); ++j; }
       kappa[i] = j == 0 ? 0 : (int)(j - 1);
     }
     return;

@@ -166,14 +166,65 @@ def test_compare_data_bit_exact(dust, orc, sir_data):
     assert np.array_equal(_rng_words(m), o.rng_state())  # one exponential draw each
 
 
-WEIGHT_KINDS = ["uniform", "onehot", "sparse", "heavy", "tiny", "real"]
+WEIGHT_KINDS = ["uniform", "onehot", "sparse", "heavy", "tiny", "real", "onehot_last", "band"]
+
+
+def _weights(kind, n, rng):
+    if kind == "uniform":
+        return np.ones(n)
+    if kind == "onehot":
+        w = np.zeros(n); w[(2 * n) // 3] = 1.0
+        return w
+    if kind == "onehot_last":       # every slot walks to the last tile
+        w = np.zeros(n); w[n - 1] = 1.0
+        return w
+    if kind == "sparse":
+        w = rng.uniform(size=n); w[rng.uniform(size=n) < 0.9] = 0.0; w[n - 1] = 1.0
+        return w
+    if kind == "heavy":
+        w = np.exp(rng.normal(0, 10, n))
+        return w / w.max()
+    if kind == "tiny":
+        w = np.full(n, 1e-300); w[0] = 1.0
+        return w
+    if kind == "band":              # near one-hot over a dense band of weights in [2^-46, 2^-40]
+        w = 2.0 ** rng.uniform(-46, -40, n); w[n // 2] = 1.0
+        return w
+    lw = -0.5 * rng.normal(0, 3, n) ** 2
+    return np.exp(lw - lw.max())
+
+
+@pytest.mark.parametrize("kind", ["uniform", "onehot_last", "heavy", "band", "real"])
+@pytest.mark.parametrize("n", [1 << 20, (1 << 21) + 5])
+def test_resample_indices_bit_exact_headline_sizes(dust, orc, kind, n):
+    """The ancestors kernel at config C2's size (512 weight tiles, prefix staged in shared
+    memory) and beyond it (1025 tiles: prefix searched in global memory)."""
+    rng = np.random.default_rng(n + 1)
+    w = _weights(kind, n, rng)
+    g = dust.dust_example("volatility")
+    m = g.new({}, 0, n, seed=11)
+    m.update_state(state=np.arange(n, dtype=float).reshape(1, n))
+    u_words = _rng_words(m)[-1].copy()
+    got = m.resample(w)
+    u = _first_uniform(u_words)
+    want = orc.resample_weight(w, u, orc.EXACT) + 1
+    assert np.array_equal(got, want)
+    assert np.array_equal(m.state()[0], (want - 1).astype(float))
+
+
+def _first_uniform(words):
+    """first uniform of a stream given as four words (xoshiro256+, the default scrambler)"""
+    s = [int(x) for x in words]
+    return float(((s[0] + s[3]) & 0xFFFFFFFFFFFFFFFF) >> 11) * 2.0 ** -53
 
 
 @pytest.mark.parametrize("kind", WEIGHT_KINDS)
 @pytest.mark.parametrize("n", [1, 7, 1024, 1025, 5000, (1 << 17) + 11])
 def test_resample_indices_bit_exact(dust, orc, kind, n):
     rng = np.random.default_rng(n)
-    if kind == "uniform":
+    if kind in ("onehot_last", "band"):
+        w = _weights(kind, n, rng)
+    elif kind == "uniform":
         w = np.ones(n)
     elif kind == "onehot":
         w = np.zeros(n); w[(2 * n) // 3] = 1.0
@@ -481,6 +532,61 @@ def test_full_size_filter_2_20(dust, orc, sir_data):
     m2.update_state(pars={}, time=0)
     again = m2.filter()["log_likelihood"]
     assert again[0] != got[0] and abs(again[0] - got[0]) < 0.5
+
+
+def test_filter_graph_follows_freq_and_time(dust, orc, sir_data):
+    """The captured filter graph bakes in the step the call starts at and the incidence-reset
+    schedule of every launch: a later call with another `freq`, or from another step, must
+    not replay it (two-launch path: more particles than one wave holds)."""
+    n = 160_000
+    m, o, t, x = _filter_pair(dust, orc, n, sir_data, n_rows=6, pars={"freq": 4.0})
+    m.set_persistent(False)
+    _set_data(m, t, x)
+    o.set_data(t, x)
+    g = dust.dust_example("sir")
+    assert np.array_equal(m.filter()["log_likelihood"], o.filter()["log_likelihood"])
+    # three passes: a row range is launched directly the first time, captured as a graph the
+    # second and replayed from the third on
+    for _ in range(3):
+        for pars, time in (({"freq": 4.0}, 0), ({"freq": 2.0}, 0), ({"freq": 2.0}, 3),
+                           ({"freq": 4.0}, 1), ({"freq": 3.0}, 0)):
+            m.update_state(pars=pars, time=time)
+            o.update_state(pars=g._pars_vector(pars, False), time=time)
+            assert np.array_equal(m.filter()["log_likelihood"],
+                                  o.filter()["log_likelihood"]), (pars, time)
+            assert np.array_equal(m.state(), o.state()), (pars, time)
+
+
+def test_independent_sets_a_dead_one_does_not_stop_the_others(dust, sir_data):
+    """Per-set seeds = independent filters batched in one handle (what smc2 holds,
+    R/smc2.R:72-78,89-108): a parameter set whose weights all vanish gets -Inf, the others
+    carry on exactly as the separate filters would.  Set 1 cannot explain a positive count
+    (beta = 0, no observation noise)."""
+    from mcstate_b200.dust import dust_rng_distributed_state
+    from oracle_generator import OracleGenerator
+
+    n = 512
+    t, x = _data(sir_data, 12)
+    data = dust.dust_data({"time_end": t, "incidence": x})
+    plist = [{"beta": 0.2}, {"beta": 0.0, "exp_noise": float("inf")}, {"beta": 0.3}]
+    seeds = b"".join(dust_rng_distributed_state(7, 1, len(plist)))
+    m = dust.dust_example("sir").new(plist, 0, n, seed=seeds, pars_multi=True, seed_per_set=True,
+                                     gpu_config=0)
+    o = OracleGenerator("sir").new(plist, 0, n, seed=seeds, pars_multi=True, seed_per_set=True)
+    m.set_data(data, True)
+    o.set_data(data, True)
+    got, want = m.filter()["log_likelihood"], o.filter()["log_likelihood"]
+    assert got[1] == -np.inf and want[1] == -np.inf
+    assert np.isfinite(got[[0, 2]]).all()
+    assert np.array_equal(got, want)
+    assert np.array_equal(m.state()[:, :, [0, 2]], o.state()[:, :, [0, 2]])
+    # one data row at a time (how smc2 drives the handle): the dead set's step is -Inf every
+    # time, the others' steps add up to the one-shot value
+    m.update_state(pars=plist, time=0)
+    total = np.zeros(3)
+    for row in range(len(t)):
+        total += m.filter(int(t[row]))["log_likelihood"]
+    assert total[1] == -np.inf and np.isfinite(total[[0, 2]]).all()
 
 
 def test_thousand_replicate_filters_agree_in_distribution(dust, orc, sir_data):
