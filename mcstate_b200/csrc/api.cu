@@ -327,7 +327,7 @@ void launch_chained(mcb_model *m, bool chained, void (*kernel)(P...), unsigned g
 
 template <class M, int SCR>
 void launch_run_compare(mcb_model *m, const double *y_in, double *y_out, uint64_t t0,
-                        uint32_t n_steps, const int *kappa, int row, double *hist) {
+                        uint32_t n_steps, const int *kappa, int row, double *hist, int *order) {
   const unsigned grid = blocks_for(m->v.n_total, mcb::kRunThreads);
   // the run kernel needs ~1.5 KB of shared memory per block (12 blocks per SM): ask for a
   // small carve-out so the walk tables keep more of L1 (measured: 20 % beats the default
@@ -339,47 +339,59 @@ void launch_run_compare(mcb_model *m, const double *y_in, double *y_out, uint64_
   {
     std::lock_guard<std::mutex> lock(mu);
     if (!carved[m->device]) {
-      cudaFuncSetAttribute(mcb::k_run_compare<M, SCR, false>,
+      cudaFuncSetAttribute(mcb::k_run_compare<M, SCR, false, false>,
                            cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-      cudaFuncSetAttribute(mcb::k_run_compare<M, SCR, true>,
+      cudaFuncSetAttribute(mcb::k_run_compare<M, SCR, true, false>,
+                           cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+      cudaFuncSetAttribute(mcb::k_run_compare<M, SCR, false, true>,
+                           cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+      cudaFuncSetAttribute(mcb::k_run_compare<M, SCR, true, true>,
                            cudaFuncAttributePreferredSharedMemoryCarveout, carve);
       carved[m->device] = true;
     }
   }
   m->v.reset_mask = reset_mask(m, t0, n_steps, &m->v.reset_mask_valid);
-  if (hist)
-    launch_chained(m, m->chain, mcb::k_run_compare<M, SCR, true>, grid, mcb::kRunThreads, m->v,
-                   y_in, y_out, t0, n_steps, kappa, row, hist);
+  const bool single = m->v.n_sets == 1;
+  if (hist && single)
+    launch_chained(m, m->chain, mcb::k_run_compare<M, SCR, true, true>, grid, mcb::kRunThreads,
+                   m->v, y_in, y_out, t0, n_steps, kappa, row, hist, order);
+  else if (hist)
+    launch_chained(m, m->chain, mcb::k_run_compare<M, SCR, true, false>, grid, mcb::kRunThreads,
+                   m->v, y_in, y_out, t0, n_steps, kappa, row, hist, order);
+  else if (single)
+    launch_chained(m, m->chain, mcb::k_run_compare<M, SCR, false, true>, grid, mcb::kRunThreads,
+                   m->v, y_in, y_out, t0, n_steps, kappa, row, (double *)nullptr, (int *)nullptr);
   else
-    launch_chained(m, m->chain, mcb::k_run_compare<M, SCR, false>, grid, mcb::kRunThreads, m->v,
-                   y_in, y_out, t0, n_steps, kappa, row, (double *)nullptr);
+    launch_chained(m, m->chain, mcb::k_run_compare<M, SCR, false, false>, grid, mcb::kRunThreads,
+                   m->v, y_in, y_out, t0, n_steps, kappa, row, (double *)nullptr, (int *)nullptr);
 }
 
 // K1: [gather by kappa on load] -> n_steps updates -> compare against `row`
 void run_compare(mcb_model *m, const double *y_in, double *y_out, uint64_t t0, uint32_t n_steps,
-                 const int *kappa, int row, double *hist) {
+                 const int *kappa, int row, double *hist, int *order = nullptr) {
   const int key = m->model_id * 2 + m->scrambler;
   switch (key) {
 #define X(ID, M)                                                                                      \
-    case 2 * ID: launch_run_compare<M, 0>(m, y_in, y_out, t0, n_steps, kappa, row, hist); break; \
-    case 2 * ID + 1: launch_run_compare<M, 1>(m, y_in, y_out, t0, n_steps, kappa, row, hist); break;
+    case 2 * ID: launch_run_compare<M, 0>(m, y_in, y_out, t0, n_steps, kappa, row, hist, order); break; \
+    case 2 * ID + 1: launch_run_compare<M, 1>(m, y_in, y_out, t0, n_steps, kappa, row, hist, order); break;
     MCB_MODELS(X)
 #undef X
     default: break;
   }
 }
 
-// K2: weights -> fixed point -> tile scan; the last block of a set finalizes it
+// K2: weights -> fixed point -> tile scan and tile sums; empties the ancestor slots
 void weights_scan(mcb_model *m, int row) {
   const unsigned grid = (unsigned)(m->v.n_sets * m->v.tiles_per_set);
   if (row < 0) launch_chained(m, m->chain, mcb::k_weights_scan<true>, grid, mcb::kTileThreads, m->v, row);
   else launch_chained(m, m->chain, mcb::k_weights_scan<false>, grid, mcb::kTileThreads, m->v, row);
 }
 
-// K3: the ancestor of every slot under the thresholds K2 left, into `kappa`
-void ancestors(mcb_model *m, int row, int *kappa) {
+// K3: per set the total weight -> ll, thresholds, early-exit rule; every particle with
+// offspring into the ancestor slots (v.heads), read back by mcb::ancestor_of
+void ancestors(mcb_model *m, int row) {
   const unsigned grid = (unsigned)(m->v.n_sets * m->v.tiles_per_set);
-  launch_chained(m, m->chain, mcb::k_ancestors, grid, mcb::kTileThreads, m->v, row, kappa);
+  launch_chained(m, m->chain, mcb::k_ancestors, grid, mcb::kTileThreads, m->v, row);
 }
 
 // one instantiation per state count a model may have (models.cuh: kMaxState)
@@ -397,10 +409,10 @@ void resample_gather(mcb_model *m, const int *kappa, const double *src, double *
   ++m->launches;
 }
 
-void finish_state(mcb_model *m, int last, const int *kappa) {
+void finish_state(mcb_model *m, int last, const int *kappa, int *order) {
   const unsigned grid = blocks_for(m->v.n_total, mcb::kGatherThreads);
   switch (m->v.n_state) {
-#define X(N) case N: mcb::k_finish_state<N><<<grid, mcb::kGatherThreads, 0, m->stream>>>(m->v, last, kappa); break;
+#define X(N) case N: mcb::k_finish_state<N><<<grid, mcb::kGatherThreads, 0, m->stream>>>(m->v, last, kappa, order); break;
     MCB_STATE_COUNTS(X)
 #undef X
     default: break;
@@ -506,9 +518,9 @@ uint64_t enqueue_filter_rows(mcb_model *m, int first, int last, bool hist,
   }
   uint64_t t = m->time;
   size_t snap_i = 0;
-  // where K3 left the ancestors of the last weighed row (its resampling is applied by the
-  // next launch that loads the state), or nullptr.  With trajectories K3 writes straight
-  // into the order slice of the history; without, into the handle's scratch.
+  // the ancestor slots K3 filled for the last weighed row (its resampling is applied by
+  // the next launch that loads the state), or nullptr.  With trajectories that launch
+  // also records the ancestors in the order slice of the history.
   const int *kappa_prev = nullptr;
   const double *in = v.y;
   // the loop's K1, K2 and K3 are chained by programmatic dependent launch (not when
@@ -524,16 +536,16 @@ uint64_t enqueue_filter_rows(mcb_model *m, int first, int last, bool hist,
     double *hist_slice = hist ? m->d_hist_value + (size_t)(rel + 1) * v.n_index * v.ld : nullptr;
     const int weigh = m->row_all_na[row] ? -1 : row;
     mark(m, row, 0);
-    run_compare(m, in, out, t, n_steps, kappa_prev, weigh, hist_slice);
+    run_compare(m, in, out, t, n_steps, kappa_prev, weigh, hist_slice,
+                hist && kappa_prev ? m->d_hist_order + (size_t)rel * v.n_total : nullptr);
     if (hist && rel > 0 && !kappa_prev) iota(m->d_hist_order + (size_t)rel * v.n_total);
     mark(m, row, 1);
     kappa_prev = nullptr;
     if (weigh >= 0) {
       weights_scan(m, row);
       mark(m, row, 2);
-      int *dst = hist ? m->d_hist_order + (size_t)(rel + 1) * v.n_total : m->d_kappa;
-      ancestors(m, row, dst);
-      kappa_prev = dst;
+      ancestors(m, row);
+      kappa_prev = v.heads;
     } else {
       mark(m, row, 2);
     }
@@ -554,7 +566,8 @@ uint64_t enqueue_filter_rows(mcb_model *m, int first, int last, bool hist,
   }
   m->chain = false;
   mark(m, (int)m->n_data, 0);
-  finish_state(m, last, kappa_prev);
+  finish_state(m, last, kappa_prev,
+               hist && kappa_prev ? m->d_hist_order + (size_t)(last - first) * v.n_total : nullptr);
   if (hist && !kappa_prev) iota(m->d_hist_order + (size_t)(last - first) * v.n_total);
   mark(m, (int)m->n_data, 1);
   mcb::k_filter_finish<<<blocks_for((size_t)v.n_fs, 128), 128, 0, m->stream>>>(v, first, last,
@@ -983,8 +996,6 @@ int mcb_alloc_ex(int model_id, const double *pars, size_t n_particles, size_t n_
   ALLOC(v.logw, v.ld * sizeof(double));
   ALLOC(v.cw, v.ld * sizeof(unsigned long long));
   ALLOC(v.tile_sum, n_sets * v.tiles_per_set * sizeof(unsigned long long));
-  ALLOC(v.tile_pre, n_sets * v.tiles_per_set * sizeof(mcb::u128));
-  ALLOC(v.setinfo, n_sets * sizeof(mcb::SetInfo));
   ALLOC(m->d_ll, n_sets * sizeof(double));
   ALLOC(m->d_min_ll, n_sets * sizeof(double));
   ALLOC(m->d_flags, 2 * sizeof(int));
@@ -1001,6 +1012,7 @@ int mcb_alloc_ex(int model_id, const double *pars, size_t n_particles, size_t n_
   v.min_ll = m->d_min_ll;
   v.flags = m->d_flags;
   v.ticket = m->d_ticket;
+  v.heads = m->d_kappa;
   v.index = m->d_index;
   v.u_draws = m->d_u;
   v.wmax = m->d_wmax;
@@ -1067,8 +1079,8 @@ int mcb_free(mcb_model *m) {
   cudaSetDevice(m->device);
   if (m->stream) cudaStreamSynchronize(m->stream);
   clear_graphs(m);
-  void *ptrs[] = {m->v.y, m->v.y_tmp, m->v.rng, m->v.derived, m->v.tab_inf, m->v.tab_walk, m->d_pars, m->v.logw, m->v.cw, m->v.tile_sum, m->v.tile_pre,
-                  m->v.setinfo, m->d_ll, m->d_min_ll, m->d_flags, m->d_ticket, m->d_index, m->d_kappa, m->d_u,
+  void *ptrs[] = {m->v.y, m->v.y_tmp, m->v.rng, m->v.derived, m->v.tab_inf, m->v.tab_walk, m->d_pars, m->v.logw, m->v.cw, m->v.tile_sum,
+                  m->d_ll, m->d_min_ll, m->d_flags, m->d_ticket, m->d_index, m->d_kappa, m->d_u,
                   m->d_wmax, m->d_fs_after, m->d_na_global, m->d_data, m->d_stage, m->d_hist_value,
                   m->d_hist_order, m->d_traj, m->d_snap, m->d_data_time, m->d_blk_sum};
   for (void *p : ptrs)
@@ -1492,11 +1504,14 @@ int mcb_resample(mcb_model *m, const double *weights, int *kappa) {
                            m->stream));
   draw_uniforms(m, -1, 0);
   weights_scan(m, -1);
-  ancestors(m, -1, m->d_kappa);
+  ancestors(m, -1);
   MCB_TRY(check_launches(m));
   MCB_CUDA(cudaMemcpyAsync(v.y_tmp, v.y, (size_t)v.n_state * v.ld * sizeof(double),
                            cudaMemcpyDeviceToDevice, m->stream));
   resample_gather(m, m->d_kappa, v.y_tmp, v.y);
+  mcb::k_fill_ancestors<<<blocks_for(v.n_total, mcb::kGatherThreads), mcb::kGatherThreads, 0,
+                          m->stream>>>(v, m->d_kappa);
+  ++m->launches;
   std::vector<int> k0(v.n_total);
   MCB_CUDA(cudaMemcpyAsync(k0.data(), m->d_kappa, v.n_total * sizeof(int), cudaMemcpyDeviceToHost,
                            m->stream));

@@ -112,6 +112,24 @@ __device__ __forceinline__ double det_log(double x) {
   return s * (hfsq + R) + dk * c_log_ln2[0] - hfsq + f + dk * c_log_ln2[1];
 }
 
+// log(k!) for an integer-valued k >= 0 (the Poisson sampler's acceptance test): a
+// table below 16, from there Stirling's series for lgamma(x), x = k + 1, with four
+// correction terms (truncation below 1e-14 at x = 17).  IEEE operations and det_log
+// only: the same bits as the oracle's orc_lfact, which no libm lgamma would give.
+__constant__ double c_log_fact[16] = {
+    0.0, 0.0, 0.693147180559945, 1.7917594692280554, 3.178053830347945, 4.787491742782047,
+    6.579251212010102, 8.525161361065415, 10.604602902745249, 12.801827480081467,
+    15.104412573075514, 17.502307845873887, 19.987214495661885, 22.55216385312342,
+    25.191221182738683, 27.89927138384089};
+__device__ __forceinline__ double det_lfact(double k) {
+  if (k < 16.0) return c_log_fact[(int)k];
+  const double x = k + 1.0;
+  const double xi = 1.0 / x, x2 = xi * xi;
+  const double ser =
+      (1.0 / 12.0 - x2 * (1.0 / 360.0 - x2 * (1.0 / 1260.0 - x2 * (1.0 / 1680.0)))) * xi;
+  return (x - 0.5) * det_log(x) - x + 0.91893853320467274178 + ser;
+}
+
 // cos(2 pi u) for u in [0, 1).  Exact reduction: x = 4u = q + r (quadrant q, r in
 // [0, 1)), r <- 1 - r above one half, so only a = (pi/2) r in [0, pi/4] is
 // rounded; then the fdlibm kernel polynomials for sin and cos with explicit fma.

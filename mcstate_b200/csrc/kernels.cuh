@@ -6,15 +6,15 @@
 //   K1 k_run_compare   [gather of the previous interval's resampling fused into the
 //                      load: slot i starts from particle kappa[i]] -> `rate` model
 //                      steps -> compare -> state', rng', logw, max
-//   K2 k_weights_scan  w = exp(logw - max) as fixed point, per-tile inclusive scan;
-//                      the block that ends a parameter set turns the tile sums into a
-//                      prefix, log-mean-exp -> ll, resampling thresholds; the last set
-//                      to finish applies the early-exit rule
-//   K3 k_ancestors     systematic resampling as a merge: one block per 2048 output
-//                      slots stages the tile prefix and the two weight tiles its slots
-//                      fall into in shared memory and writes kappa (4 B per slot), so
-//                      K1 and every other state pass read their ancestor with one
-//                      coalesced load and do no search
+//   K2 k_weights_scan  w = exp(logw - max) as fixed point, per-tile inclusive scan
+//                      and tile sum; no block waits for another
+//   K3 k_ancestors     every block adds up its set's tile sums (log-mean-exp -> ll and
+//                      the early-exit rule by the set's first block), turns the
+//                      cumulative weight of each particle into the range of output
+//                      slots it owns -- a division, not a search -- and writes the
+//                      particle's index at the head of the range, so K1 and every
+//                      other state pass read their ancestor with one coalesced load
+//                      and a running maximum over the warp
 // plus k_finish_state once per filter call (the last interval's gather).
 // Filters that fit the GPU in one wave run as ONE cooperative kernel per call instead
 // (persistent.cuh); the model steps (run_model_steps) are shared.
@@ -54,10 +54,8 @@ constexpr int kGatherThreads = 256;
 typedef unsigned __int128 u128;
 constexpr int kShift = 52;   // fractional bits of a fixed-point weight
 
-struct SetInfo {   // per parameter set, rewritten every interval by K2's finishing block
+struct SetInfo {   // the resampling thresholds of a parameter set in one interval
   double uu0, du;  // threshold_i = ceil(uu0 + i * du)   (fixed-point units)
-  int dead;        // every weight of the interval was zero: the set is not resampled
-  int pad;
 };
 
 struct View {
@@ -72,14 +70,13 @@ struct View {
   double *logw;       // [n_total]
   unsigned long long *cw;        // [n_total] inclusive fixed-point cumsum inside a tile
   unsigned long long *tile_sum;  // [n_sets][tiles_per_set] fixed-point weight of each tile
-  u128 *tile_pre;                // [n_sets][tiles_per_set] inclusive prefix of the tile sums
+  int *heads;                    // [ld] ancestor slots: emptied by K2, filled by K3 (ancestor_of)
   unsigned long long *wmax;      // [n_data][n_sets] order-preserving key of max logw
   const double *u_draws;         // [n_data][n_sets] resampling uniforms (filter stream)
-  SetInfo *setinfo;   // [n_sets]
   double *ll;         // [n_sets] accumulated log-likelihood of this filter call
   const double *min_ll; // [n_min]
   int *flags;         // [0] stopped, [1] stop row
-  unsigned int *ticket; // [n_sets + 2] K2 counters: tiles done per set, sets done, any set dead
+  unsigned int *ticket; // [n_sets + 2] K3 counters: [n_sets] sets done, [n_sets + 1] any set dead
   const int *index;   // [n_index] rows returned by run()/saved in trajectories
   size_t n_particles, n_sets, n_total, ld, ld_rng;
   int n_state, n_index, n_min, data_sets, tiles_per_set, deterministic, n_tab, n_wrows;
@@ -108,6 +105,41 @@ __device__ __forceinline__ void grid_launch_dependents() {
 }
 __device__ __forceinline__ void grid_dependency_wait() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// ---- loads of data that streams through once per launch (state, generator, ancestor
+// slots): they must not push the memo tables -- read at every model step -- or the
+// kernel's few spilled registers out of L1.  MCB_STREAM_LD: 0 evict-first (ld.cs),
+// 1 no L1 allocation.
+#ifndef MCB_STREAM_LD
+#define MCB_STREAM_LD 1
+#endif
+__device__ __forceinline__ double ld_stream(const double *p) {
+#if MCB_STREAM_LD == 1
+  double x;
+  asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(x) : "l"(p));
+  return x;
+#else
+  return __ldcs(p);
+#endif
+}
+__device__ __forceinline__ uint64_t ld_stream(const uint64_t *p) {
+#if MCB_STREAM_LD == 1
+  uint64_t x;
+  asm volatile("ld.global.L1::no_allocate.u64 %0, [%1];" : "=l"(x) : "l"(p));
+  return x;
+#else
+  return __ldcs(reinterpret_cast<const unsigned long long *>(p));
+#endif
+}
+__device__ __forceinline__ int ld_stream(const int *p) {
+#if MCB_STREAM_LD == 1
+  int x;
+  asm volatile("ld.global.L1::no_allocate.s32 %0, [%1];" : "=r"(x) : "l"(p));
+  return x;
+#else
+  return __ldcs(p);
+#endif
 }
 
 // ---- order-preserving map double -> u64 so max is one integer atomic --------
@@ -193,23 +225,28 @@ __device__ __forceinline__ u128 slot_threshold(const SetInfo &si, uint32_t il) {
   return ceil_to_u128(si.uu0 + (double)il * si.du);
 }
 
-// first index in [lo, n) with pre[idx] >= thr, else n - 1
-__device__ __forceinline__ int tile_lower_bound(const u128 *pre, int lo, int n, u128 thr) {
-  int hi = n - 1;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (pre[mid] >= thr) hi = mid; else lo = mid + 1;
+// The particle slot i continues, from the slots K3 filled: the running maximum over
+// the warp (a slot that is a multiple of 32 is never empty, ancestors grow with the
+// slot, an empty slot holds -1).  Every lane of the warp calls this; lanes beyond
+// the particles pass live = false.
+__device__ __forceinline__ size_t ancestor_of(const int *__restrict__ heads, size_t i, bool live) {
+  int h = live ? ld_stream(heads + i) : -1;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(0xffffffffu, h, d);
+    if ((int)(threadIdx.x & 31) >= d) h = max(h, o);
   }
-  return lo;
+  return (size_t)h;
 }
 
 // ---------------------------------------------------------------------------
 // K1: one thread per particle: [gather of the previous interval's resampling,
 // fused into the load] -> `n_steps` model updates -> compare.  State (kState
 // doubles) and the generator (4 words) stay in registers throughout.
-//   kappa != nullptr: slot i starts from particle kappa[i], the ancestor K3 chose
-//                  for it (reads y_in[kappa[i]]; y_in != y_out), so the resampled
-//                  state is never written to HBM and read back;
+//   kappa != nullptr: the ancestor slots K3 filled: slot i starts from the particle
+//                  ancestor_of gives it (reads y_in[that]; y_in != y_out), so the
+//                  resampled state is never written to HBM and read back; with
+//                  trajectories the ancestor is also recorded in `order_out`;
 //   kappa == nullptr: slot i continues its own particle (y_in may equal y_out);
 //   row >= 0: weigh against data row `row`; row < 0: no compare (model$run).
 // ---------------------------------------------------------------------------
@@ -250,30 +287,26 @@ __device__ __forceinline__ void run_model_steps(const View &v, const SetData &sd
     if (!det && M::lean_load(sd, y, yi, lc)) {
       // the usual case: integer compartments, setup from the memo tables, no calls
       const uint32_t s_exp2_addr = (uint32_t)__cvta_generic_to_shared(s_exp2);
-      bool ok = true;
-      uint32_t freq = 1, phase = 0;
-      if (!v.reset_mask_valid) {
-        freq = (uint32_t)__ldg(sd.derived + M::D_FREQ);
-        phase = t0 <= 0xffffffffULL ? (uint32_t)t0 % freq : (uint32_t)(t0 % freq);
-      }
-      while (ok && done < n_steps) {
-        // bit k: step done + k starts a new incidence interval
-        const uint32_t nk = min(n_steps - done, 32u);
-        uint32_t resets = v.reset_mask;
-        if (!v.reset_mask_valid) {
+      // one counter runs the loop (registers are what this kernel is short of); bit 0 of
+      // `resets`: the next step starts a new incidence interval.  The mask comes from the
+      // host when it could tell (at most 32 steps, one freq for every set), else it is
+      // worked out here, 32 steps at a time.
+      uint32_t left = n_steps, resets = v.reset_mask;
+      do {
+        if (!v.reset_mask_valid && ((n_steps - left) & 31u) == 0) {
+          const uint32_t freq = (uint32_t)__ldg(sd.derived + M::D_FREQ);
+          const uint64_t t = t0 + (n_steps - left);
+          uint32_t phase = t <= 0xffffffffULL ? (uint32_t)t % freq : (uint32_t)(t % freq);
           resets = 0;
-          for (uint32_t k = 0; k < nk; ++k) {
+          for (uint32_t k = 0; k < 32u; ++k) {
             resets |= (phase == 0 ? 1u : 0u) << k;
             phase = phase + 1 == freq ? 0 : phase + 1;
           }
         }
-        for (uint32_t k = 0; k < nk; ++k) {
-          ok = M::template lean_update<SCR>((resets & 1u) != 0, yi, rng, lc, tabs, s_exp2_addr);
-          if (!ok) break;
-          resets >>= 1;
-          ++done;
-        }
-      }
+        if (!M::template lean_update<SCR>((resets & 1u) != 0, yi, rng, lc, tabs, s_exp2_addr)) break;
+        resets >>= 1;
+      } while (--left);
+      done = n_steps - left;
       M::lean_store(sd, yi, y);
     }
   }
@@ -305,11 +338,13 @@ __device__ __forceinline__ void run_model_steps(const View &v, const SetData &sd
 template <class M>
 constexpr int k1_min_blocks() { return M::kHasLean ? MCB_K1_MINBLOCKS : MCB_K1_MINBLOCKS_GENERAL; }
 
-template <class M, int SCR, bool HIST>
+// HIST: trajectories are recorded.  SINGLE: one parameter set (n_sets == 1): everything
+// that depends on the set is a constant, not a register.
+template <class M, int SCR, bool HIST, bool SINGLE>
 __global__ void __launch_bounds__(kRunThreads, k1_min_blocks<M>())
 k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_out,
               uint64_t t0, uint32_t n_steps, const int *__restrict__ kappa, int row,
-              double *__restrict__ hist) {
+              double *__restrict__ hist, int *__restrict__ order_out) {
   __shared__ unsigned long long s_key[kRunThreads / 32];
   __shared__ double s_exp2[kExp2Tab];
   // programmatic dependent launch: let the next kernel be scheduled as this one
@@ -322,7 +357,7 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
   const size_t i = (size_t)blockIdx.x * kRunThreads + threadIdx.x;
   const bool live = i < v.n_total;
   const size_t ii = live ? i : v.n_total - 1;
-  const size_t set = set_of(v, ii);
+  const size_t set = SINGLE ? 0 : set_of(v, ii);
   const SetData sd{v.derived + set * kMaxDerived, v.n_tab};
   const typename M::Ctx ctx = M::context(sd);
   const bool det = v.deterministic != 0;
@@ -332,16 +367,17 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
   unsigned long long key = 0;
   bool weighted = false;
   // which particle this slot continues: the ancestor systematic resampling chose
-  const size_t src = (live && kappa) ? (size_t)__ldcs(kappa + i) : i;
+  const size_t src = kappa ? ancestor_of(kappa, i, live) : i;
   if (live) {
+    if (HIST && order_out) order_out[i] = (int)src;
 #pragma unroll
     // state and generator stream through once per launch: keep them out of L1's
-    // way (evict-first), the memo tables and the search arrays live there
-    for (int s = 0; s < M::kState; ++s) y[s] = __ldcs(y_in + (size_t)s * v.ld + src);
-    rng.s0 = __ldcs(v.rng + 0 * v.ld_rng + i);
-    rng.s1 = __ldcs(v.rng + 1 * v.ld_rng + i);
-    rng.s2 = __ldcs(v.rng + 2 * v.ld_rng + i);
-    rng.s3 = __ldcs(v.rng + 3 * v.ld_rng + i);
+    // way (evict-first), the memo tables live there
+    for (int s = 0; s < M::kState; ++s) y[s] = ld_stream(y_in + (size_t)s * v.ld + src);
+    rng.s0 = ld_stream(v.rng + 0 * v.ld_rng + i);
+    rng.s1 = ld_stream(v.rng + 1 * v.ld_rng + i);
+    rng.s2 = ld_stream(v.rng + 2 * v.ld_rng + i);
+    rng.s3 = ld_stream(v.rng + 3 * v.ld_rng + i);
 
     run_model_steps<M, SCR>(v, sd, ctx, set, y, rng, t0, n_steps, det, s_exp2);
 
@@ -381,8 +417,8 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
   const size_t first = (size_t)blockIdx.x * kRunThreads;
   size_t last = first + kRunThreads - 1;
   if (last >= v.n_total) last = v.n_total - 1;
-  const size_t set_first = set_of(v, first);
-  const bool one_set = v.n_sets == 1 || set_first == set_of(v, last);
+  const size_t set_first = SINGLE ? 0 : set_of(v, first);
+  const bool one_set = SINGLE || set_first == set_of(v, last);
   unsigned long long *slot = v.wmax + (size_t)row * v.n_sets;
   if (one_set) {
     // warp max of a 64-bit key with two 32-bit REDUX: high words, then the low
@@ -405,99 +441,27 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
 
 // ---------------------------------------------------------------------------
 // Per parameter set, once its total weight is known: log-mean-exp into ll
-// (scale_log_weights, R/particle_filter.R:570-587) and the resampling
-// thresholds.  One thread.  Returns true if the set is dead (all -Inf).
+// (scale_log_weights, R/particle_filter.R:570-587).  One thread.  Returns true if
+// the set is dead (all -Inf).
 // ---------------------------------------------------------------------------
-// u, mx, ll_old: the set's resampling uniform, max log-weight and likelihood so far,
-// loaded by the caller at the start of the kernel (they do not change during it) so
-// that no dependent global load sits on the tail of the weights stage.
-__device__ __forceinline__ bool finish_set(const View &v, int row, size_t set, u128 tot, double u,
-                                           double mx, double ll_old) {
+__device__ __forceinline__ bool finish_set(const View &v, int row, size_t set, u128 tot, double tot_d,
+                                           double mx) {
   const double neg_inf = __longlong_as_double(0xfff0000000000000LL);
-  const double n = (double)v.n_particles;
-  const double tot_d = u128_to_double(tot);
-  const bool dead = row >= 0 && (!(mx > neg_inf) || tot == 0);
-  SetInfo si;
-  si.uu0 = tot_d * u / n;
-  si.du = tot_d / n;
-  si.dead = dead ? 1 : 0;
-  si.pad = 0;
-  v.setinfo[set] = si;
   if (row < 0) return false;
-  if (dead) {
+  if (!(mx > neg_inf) || tot == 0) {
     v.ll[set] = neg_inf;
     return true;
   }
-  const double mean = (tot_d * 0x1p-52) / n;
-  v.ll[set] = ll_old + (det_log(mean) + mx);
+  const double mean = (tot_d * 0x1p-52) / (double)v.n_particles;
+  v.ll[set] = v.ll[set] + (det_log(mean) + mx);
   return false;
 }
 
-// The weights stage finishes per parameter set: the block that completes a set's
-// last tile (ticket counter of the set) turns the set's tile sums into an
-// inclusive prefix and runs finish_set, so many small sets (nested populations,
-// SMC^2) finish in parallel, each on the SM that happened to end it.  The last
-// set to finish (a second counter) applies the early-exit rule of
-// R/particle_filter_state.R:463-474 over all the sets.
-//   ticket [n_sets] per-set counters, [n_sets] the counter of finished sets,
-//          [n_sets + 1] "some set is dead" of this interval
-__device__ __forceinline__ void finalize_set(const View &v, int row, size_t set, double pre_u,
-                                             double pre_mx, double pre_ll) {
-  __shared__ u128 s_tot[kTileThreads / 32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int T = v.tiles_per_set;
-  const unsigned long long *sums = v.tile_sum + set * T;
-  u128 *pre = v.tile_pre + set * T;
-  bool dead = false;
-  const bool weighed = row < 0 || !datum_is_na(v, row, set);
-  if (weighed && T <= 32) {
-    // a small set: one warp
-    if (warp == 0) {
-      u128 incl = lane < T ? (u128)__ldcg(sums + lane) : (u128)0;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const u128 o = shfl_up_u128(incl, d);
-        if (lane >= d) incl += o;
-      }
-      if (lane < T) pre[lane] = incl;
-      const unsigned long long tot_lo = shfl_u64((unsigned long long)incl, T - 1);
-      const unsigned long long tot_hi = shfl_u64((unsigned long long)(incl >> 64), T - 1);
-      // lane 0 is thread 0: the one that holds the set's uniform and likelihood so far
-      if (lane == 0)
-        dead = finish_set(v, row, set, ((u128)tot_hi << 64) | tot_lo, pre_u, pre_mx, pre_ll);
-    }
-  } else if (weighed) {
-    // a big set: the whole block scans its tiles, two consecutive tiles per thread: 512
-    // tiles (1 Mi particles) per pass, one barrier each
-    constexpr int kPer = 2;
-    u128 carry = 0;   // the same value in every thread
-    for (int base = 0; base < T; base += kTileThreads * kPer) {
-      if (base) __syncthreads();   // s_tot is written again
-      const int i0 = base + tid * kPer;
-      const unsigned long long x0 = i0 < T ? __ldcg(sums + i0) : 0ULL;
-      const unsigned long long x1 = i0 + 1 < T ? __ldcg(sums + i0 + 1) : 0ULL;
-      const u128 local = (u128)x0 + x1;
-      u128 incl = local;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const u128 o = shfl_up_u128(incl, d);
-        if (lane >= d) incl += o;
-      }
-      if (lane == 31) s_tot[warp] = incl;
-      __syncthreads();
-      u128 offset = carry + incl - local, total = 0;
-#pragma unroll
-      for (int w = 0; w < kTileThreads / 32; ++w) {
-        if (w < warp) offset += s_tot[w];
-        total += s_tot[w];
-      }
-      if (i0 < T) pre[i0] = offset + x0;
-      if (i0 + 1 < T) pre[i0 + 1] = offset + local;
-      carry += total;
-    }
-    if (tid == 0) dead = finish_set(v, row, set, carry, pre_u, pre_mx, pre_ll);
-  }
-  if (tid != 0) return;
+// The early-exit rule of R/particle_filter_state.R:463-474 over all the sets, by the
+// thread that finished the last set of the interval (a counter) -- the only thread of
+// the launch that runs this.
+//   ticket [n_sets] the counter of finished sets, [n_sets + 1] "some set is dead"
+__device__ __forceinline__ void apply_stop_rule(const View &v, int row, bool dead) {
   bool any_dead = dead;
   if (v.n_sets > 1) {
     unsigned int *done = v.ticket + v.n_sets;
@@ -543,242 +507,299 @@ __device__ __forceinline__ unsigned long long weight_to_fixed(double w) {
 
 // ---------------------------------------------------------------------------
 // K2: one block per tile of kTile particles (tiles never straddle a set):
-// w = exp(logw - max) -> fixed point, inclusive scan inside the tile, tile sum.
-// The block that takes its set's last ticket then runs finalize_set, so the
-// whole weights stage is one launch.  The tile sum is published (and the ticket
-// taken) before the block stores its cumulative weights: only the sum is read
-// by the finishing block, the cumulative weights are for the next launch.
+// w = exp(logw - max) -> fixed point, inclusive scan inside the tile -> the
+// tile's cumulative weights and its sum.  Nothing here waits for another block:
+// the sums are put together by every block of K3 for itself.  The block also
+// empties the ancestor slots of its particles' positions for K3 to fill.
 // GIVEN = true: `logw` already holds weights in [0,1] (model$resample(weights)).
 // ---------------------------------------------------------------------------
 template <bool GIVEN>
 __global__ void __launch_bounds__(kTileThreads, 4) k_weights_scan(View v, int row) {
   __shared__ unsigned long long s_warp[kTileThreads / 32];
-  __shared__ bool s_last;
   grid_launch_dependents();
-  grid_dependency_wait();
-  if (v.flags[0]) return;
   const size_t set = v.n_sets == 1 ? 0 : blockIdx.x / (unsigned)v.tiles_per_set;
   const int tile = (int)(blockIdx.x - (unsigned)set * (unsigned)v.tiles_per_set);
-  // what the set's finishing thread will need, asked for now (finish_set)
-  double pre_u = 0.0, pre_ll = 0.0, mx = 0.0;
-  if (threadIdx.x == 0) {
-    pre_u = v.u_draws[(size_t)(row < 0 ? 0 : row) * v.n_sets + set];
-    pre_ll = v.ll[set];
-  }
-  const bool have = GIVEN || !datum_is_na(v, row, set);   // block-uniform
   const size_t in_set = (size_t)tile * kTile + (size_t)threadIdx.x * kTileItems;
   const size_t base = set * v.n_particles + in_set;
-  const bool full = in_set + kTileItems <= v.n_particles && (base & 1) == 0;
-  unsigned long long q[kTileItems];
-  unsigned long long offset = 0, total = 0;
-  if (have) {
-    if (!GIVEN) mx = key_to_double(v.wmax[(size_t)row * v.n_sets + set]);
-    const bool dead = !GIVEN && !(mx > __longlong_as_double(0xfff0000000000000LL));
-    double lw[kTileItems];
-    if (full) {  // 16-byte vector loads: the 8 values of a thread are contiguous
-      const double2 *src = reinterpret_cast<const double2 *>(v.logw + base);
-#pragma unroll
-      for (int j = 0; j < kTileItems / 2; ++j) {
-        const double2 t = __ldcs(src + j);
-        lw[2 * j] = t.x;
-        lw[2 * j + 1] = t.y;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < kTileItems; ++j)
-        lw[j] = in_set + j < v.n_particles ? v.logw[base + j] : __longlong_as_double(0xfff0000000000000LL);
-    }
-    unsigned long long run = 0;
-#pragma unroll
-    for (int j = 0; j < kTileItems; ++j) {
-      unsigned long long x = 0;
-      if (in_set + j < v.n_particles && !dead)
-        x = weight_to_fixed(GIVEN ? lw[j] : det_exp_nonpos(lw[j] - mx));
-      run += x;
-      q[j] = run;
-    }
-    unsigned long long incl = run;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const unsigned long long o = shfl_up_u64(incl, d);
-      if ((threadIdx.x & 31) >= d) incl += o;
-    }
-    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
-    __syncthreads();
-    offset = incl - run;
-#pragma unroll
-    for (int w = 0; w < kTileThreads / 32; ++w) {
-      if (w < (int)(threadIdx.x >> 5)) offset += s_warp[w];
-      total += s_warp[w];
-    }
-  }
-  // ---- publish the tile sum and take the set's ticket; the block that takes the last
-  // one finishes the set
-  if (threadIdx.x == 0) {
-    if (have) v.tile_sum[blockIdx.x] = total;
-    __threadfence();
-    s_last = atomicAdd(v.ticket + set, 1u) == (unsigned)v.tiles_per_set - 1;
-  }
-  if (have) {
-    if (full) {
-      ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(v.cw + base);
-#pragma unroll
-      for (int j = 0; j < kTileItems / 2; ++j)
-        dst[j] = make_ulonglong2(q[2 * j] + offset, q[2 * j + 1] + offset);
-    } else {
-#pragma unroll
-      for (int j = 0; j < kTileItems; ++j)
-        if (in_set + j < v.n_particles) v.cw[base + j] = q[j] + offset;
-    }
-  }
-  __syncthreads();
-  if (!s_last) return;
-  if (threadIdx.x == 0) v.ticket[set] = 0;
-  __threadfence();
-  finalize_set(v, row, set, pre_u, mx, pre_ll);
-}
-
-// ---------------------------------------------------------------------------
-// K3: the ancestors.  Systematic resampling is a merge of two sorted sequences --
-// the thresholds ceil(uu0 + i du) of the output slots and the cumulative weights
-// of the particles -- so one block takes 2048 consecutive output slots of a set,
-// stages the set's tile prefix and a window of two weight tiles in shared memory
-// (one coalesced round trip to L2 each), and every thread walks its 8 consecutive
-// slots through the window: a halving search when it enters a tile, a short
-// bounded search from the previous ancestor after that.  Work follows the OUTPUT,
-// so the cost does not depend on how the weights are spread (uniform, degenerate,
-// one particle holding all).  When slots of the block fall beyond the window, the
-// window moves to the first tile still needed and the threads carry on where they
-// stopped: as many rounds as the block's slots have tile pairs to visit (one or
-// two unless the weights are very uneven).  A set without a datum in this row, or
-// whose weights all vanished, keeps its particles (identity).
-//   kappa [n_total]: global index of the particle each slot continues
-// ---------------------------------------------------------------------------
-constexpr int kAncWinTiles = 2;
-constexpr int kAncMaxSmemTiles = 512;
-constexpr int kAncNear = 64;   // how far past the previous ancestor the short search looks
-static_assert(kTile == 2048, "the searches of k_ancestors run 11 halving steps");
-
-// first index in [0, n) with cw[idx] >= rem, else n - 1; n <= 2048.  Eleven halving
-// steps whatever the data (no divergence)
-__device__ __forceinline__ int tile_search(const unsigned long long *cw, int n,
-                                           unsigned long long rem) {
-  int pos = 0;
-#pragma unroll
-  for (int half = kTile / 2; half >= 1; half >>= 1) {
-    const int probe = pos + half - 1;
-    if (probe < n && cw[probe] < rem) pos = probe + 1;
-  }
-  return min(pos, n - 1);
-}
-// the same for a key at or beyond the one that found `pos`: nothing to do when the
-// previous ancestor still reaches it, six halving steps when the answer lies within
-// kAncNear particles, the full search otherwise
-__device__ __forceinline__ int tile_search_from(const unsigned long long *cw, int pos, int n,
-                                                unsigned long long rem) {
-  if (cw[pos] >= rem || pos >= n - 1) return pos;
-  const int hi = min(pos + kAncNear, n - 1);
-  if (cw[hi] < rem) return hi == n - 1 ? hi : tile_search(cw, n, rem);
-  int lo = pos + 1;
-#pragma unroll
-  for (int half = kAncNear / 2; half >= 1; half >>= 1) {
-    const int probe = lo + half - 1;
-    if (probe < hi && cw[probe] < rem) lo = probe + 1;
-  }
-  return lo;
-}
-
-__global__ void __launch_bounds__(kTileThreads, 4)
-k_ancestors(View v, int row, int *__restrict__ kappa) {
-  __shared__ u128 s_pre[kAncMaxSmemTiles];
-  __shared__ unsigned long long s_cw[kAncWinTiles * kTile];
-  __shared__ int s_tile;   // the first tile of the window / the first tile still needed
-  grid_launch_dependents();
+  const bool full = in_set + kTileItems <= v.n_particles && (base & 3) == 0;
   grid_dependency_wait();
-  if (v.flags[0]) return;
+  // everything the block reads is asked for at once (the stop flag, the set's maximum,
+  // the log-weights): one trip to memory, not three in a row
+  const int stopped = __ldcg(v.flags);
+  double mx = 0.0;
+  if (!GIVEN) mx = key_to_double(__ldcg(v.wmax + (size_t)row * v.n_sets + set));
+  const bool have = GIVEN || !datum_is_na(v, row, set);   // block-uniform
+  const bool dead = !GIVEN && !(mx > __longlong_as_double(0xfff0000000000000LL));
+  double lw[kTileItems];
+  if (full) {  // 16-byte vector loads: the 8 values of a thread are contiguous
+    const double2 *src = reinterpret_cast<const double2 *>(v.logw + base);
+#pragma unroll
+    for (int j = 0; j < kTileItems / 2; ++j) {
+      const double2 t = __ldcs(src + j);
+      lw[2 * j] = t.x;
+      lw[2 * j + 1] = t.y;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < kTileItems; ++j)
+      lw[j] = in_set + j < v.n_particles ? v.logw[base + j]
+                                         : __longlong_as_double(0xfff0000000000000LL);
+  }
+  // a stopped filter: nothing more is written.  A set without a datum in this row: K3
+  // leaves it as it is and reads nothing of this tile
+  if (stopped || !have) return;
+  if (full) {
+    int4 *h = reinterpret_cast<int4 *>(v.heads + base);
+#pragma unroll
+    for (int j = 0; j < kTileItems / 4; ++j) h[j] = make_int4(-1, -1, -1, -1);
+  } else {
+#pragma unroll
+    for (int j = 0; j < kTileItems; ++j)
+      if (in_set + j < v.n_particles) v.heads[base + j] = -1;
+  }
+  unsigned long long q[kTileItems];
+  unsigned long long run = 0;
+#pragma unroll
+  for (int j = 0; j < kTileItems; ++j) {
+    unsigned long long x = 0;
+    if (in_set + j < v.n_particles && !dead)
+      x = weight_to_fixed(GIVEN ? lw[j] : det_exp_nonpos(lw[j] - mx));
+    run += x;
+    q[j] = run;
+  }
+  unsigned long long incl = run;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long o = shfl_up_u64(incl, d);
+    if ((threadIdx.x & 31) >= d) incl += o;
+  }
+  if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  unsigned long long offset = incl - run, total = 0;
+#pragma unroll
+  for (int w = 0; w < kTileThreads / 32; ++w) {
+    if (w < (int)(threadIdx.x >> 5)) offset += s_warp[w];
+    total += s_warp[w];
+  }
+  if (threadIdx.x == 0) v.tile_sum[blockIdx.x] = total;
+  if (full) {
+    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(v.cw + base);
+#pragma unroll
+    for (int j = 0; j < kTileItems / 2; ++j)
+      dst[j] = make_ulonglong2(q[2 * j] + offset, q[2 * j + 1] + offset);
+  } else {
+#pragma unroll
+    for (int j = 0; j < kTileItems; ++j)
+      if (in_set + j < v.n_particles) v.cw[base + j] = q[j] + offset;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K3: the ancestors.  Output slot i of a set continues the first particle whose
+// cumulative weight reaches ceil(uu0 + i du); turned round, particle j owns the
+// slots [c(C_{j-1}), c(C_j)) where C_j is its inclusive cumulative weight and
+// c(C) = #{i : ceil(uu0 + i du) <= C} -- a count that (C - uu0)/du gives directly.
+// So nothing is searched: one block per weight tile puts the set's tile sums
+// together for itself (what lies before its tile, and the total: the thresholds,
+// and for the set's first tile the log-mean-exp -> ll and the early-exit rule),
+// every thread turns its 8 cumulative weights into counts, and a particle with
+// offspring writes its index at its FIRST slot and at every multiple of 32 its
+// slots cover.  Whoever loads by ancestor (ancestor_of) reads its slot and takes the
+// running maximum over its warp: one coalesced 4-byte load, no dependent probes, and
+// a cost that does not depend on how the weights are spread.
+//
+// The count is exact.  x = (C - uu0)/du is evaluated in double with an error below
+// n 2^-50 slots (C, the tile offset, their difference and the product each round
+// once: 2^-53 relative to the total apiece); a threshold ceil(fl(uu0 + fl(i du)))
+// lies within n 2^-52 slots of the line uu0 + i du.  So when x is further than
+// kCountEps = 2^-12 from an integer, floor(x) + 1 IS the count (n < 2^31); otherwise
+// (one particle in 2000) the thresholds next to the estimate are evaluated as the
+// definition has them and compared as integers.
+//   heads [n_total]: emptied by K2; global index of the particle at the slots above
+// ---------------------------------------------------------------------------
+constexpr double kCountEps = 0x1p-12;
+constexpr uint32_t kHeavySlots = 2048;   // a particle with this many slots: the block writes them
+constexpr int kHeavyCap = 32;
+
+struct CountCtx {
+  double d0, inv_du;   // x = (q + d0) inv_du
+  SetInfo si;
+  u128 offset;         // cumulative weight before the tile
+  uint32_t n;          // particles (= slots) of the set
+};
+
+__device__ __noinline__ uint32_t count_exact(const CountCtx &c, unsigned long long q, uint32_t k) {
+  const u128 C = c.offset + q;
+  while (k < c.n && slot_threshold(c.si, k) <= C) ++k;
+  while (k > 0 && slot_threshold(c.si, k - 1) > C) --k;
+  return k;
+}
+
+// #{slots of the set whose threshold is at or below offset + q}
+__device__ __forceinline__ uint32_t slots_reached(const CountCtx &c, unsigned long long q) {
+  const double x = (__ull2double_rn(q) + c.d0) * c.inv_du;
+  const double xc = fmin(fmax(x, -1.0), (double)c.n);
+  const double fl = floor(xc);
+  const uint32_t k = min((uint32_t)(__double2int_rd(xc) + 1), c.n);
+  const double fr = xc - fl;
+  if (fr < kCountEps || fr > 1.0 - kCountEps) return count_exact(c, q, k);
+  return k;
+}
+
+__global__ void __launch_bounds__(kTileThreads, 4) k_ancestors(View v, int row) {
+  __shared__ u128 s_red[2][kTileThreads / 32];
+  __shared__ uint32_t s_cnt[kTileThreads / 32];
+  __shared__ uint32_t s_heavy[kHeavyCap][3];
+  __shared__ int s_heavy_n;
+  grid_launch_dependents();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = v.tiles_per_set;
   const size_t set = v.n_sets == 1 ? 0 : blockIdx.x / (unsigned)T;
   const int tile = (int)(blockIdx.x - (unsigned)set * (unsigned)T);
   const size_t gbase = set * v.n_particles;
-  const uint32_t il0 = (uint32_t)tile * kTile + threadIdx.x * kTileItems;  // first slot of the thread
   const uint32_t n_p = (uint32_t)v.n_particles;
-  const int n_mine = il0 >= n_p ? 0 : (int)min((uint32_t)kTileItems, n_p - il0);
-  int *out = kappa + gbase + il0;
-  const SetInfo si = v.setinfo[set];
-  if ((row >= 0 && datum_is_na(v, row, set)) || si.dead) {   // block-uniform: identity
-    for (int k = 0; k < n_mine; ++k) out[k] = (int)(gbase + il0 + k);
+  const uint32_t in_set = (uint32_t)tile * kTile + tid * kTileItems;   // the thread's first particle
+  const int n_mine = in_set >= n_p ? 0 : (int)min((uint32_t)kTileItems, n_p - in_set);
+  if (tid == 0) s_heavy_n = 0;
+  const size_t base = gbase + in_set;
+  const bool vec = n_mine == kTileItems && (base & 1) == 0;
+  const unsigned long long *sums = v.tile_sum + set * T;
+  grid_dependency_wait();
+  // everything the block reads is asked for at once -- the stop flag, the first round of
+  // tile sums, the uniform, the maximum, the thread's cumulative weights -- so the block
+  // makes one trip to memory, not five in a row (stale values of a set without a datum
+  // are read and never used)
+  const int stopped = __ldcg(v.flags);
+  const unsigned long long sum0 = tid < T ? __ldcg(sums + tid) : 0ULL;
+  const double u = __ldcg(v.u_draws + (size_t)(row < 0 ? 0 : row) * v.n_sets + set);
+  const unsigned long long mx_key = row >= 0 ? __ldcg(v.wmax + (size_t)row * v.n_sets + set) : 0ULL;
+  unsigned long long q[kTileItems];
+  if (vec) {
+    const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(v.cw + base);
+#pragma unroll
+    for (int j = 0; j < kTileItems / 2; ++j) {
+      const ulonglong2 t = __ldcs(src + j);
+      q[2 * j] = t.x;
+      q[2 * j + 1] = t.y;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < kTileItems; ++j) q[j] = j < n_mine ? __ldcs(v.cw + base + j) : 0ULL;
+  }
+  if (stopped) return;
+  int *heads = v.heads;
+  const bool leader = tile == 0 && tid == 0;   // finishes the set
+  if (row >= 0 && datum_is_na(v, row, set)) {   // block-uniform: nothing weighed, identity
+    for (int k = 0; k < n_mine; ++k) heads[gbase + in_set + k] = (int)(gbase + in_set + k);
+    if (leader) apply_stop_rule(v, row, false);
     return;
   }
-  const u128 *pre_g = v.tile_pre + set * T;
-  const bool pre_staged = T <= kAncMaxSmemTiles;
-  const u128 *pre = pre_staged ? s_pre : pre_g;
-  // ---- the tile the block's first slot falls into: with the prefix staged, every
-  // thread looks at its own entries and the one at the lower bound reports it
-  const u128 thr_first = slot_threshold(si, (uint32_t)tile * kTile);
-  if (pre_staged) {
-    if (threadIdx.x == 0) s_tile = T - 1;   // no prefix reaches the threshold: the last tile
-    for (int t = threadIdx.x; t < T; t += kTileThreads) s_pre[t] = pre_g[t];
+  // ---- the set's tile sums: what lies before this tile, and the total
+  u128 before = 0, total = 0;
+  {
+    total = sum0;
+    if (tid < tile) before = sum0;
+    for (int t = tid + kTileThreads; t < T; t += kTileThreads) {
+      const unsigned long long x = __ldcg(sums + t);
+      total += x;
+      if (t < tile) before += x;
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      total += ((u128)shfl_xor_u64((unsigned long long)(total >> 64), d) << 64) |
+               shfl_xor_u64((unsigned long long)total, d);
+      before += ((u128)shfl_xor_u64((unsigned long long)(before >> 64), d) << 64) |
+                shfl_xor_u64((unsigned long long)before, d);
+    }
+    if (lane == 0) { s_red[0][warp] = total; s_red[1][warp] = before; }
     __syncthreads();
-    for (int t = threadIdx.x; t < T; t += kTileThreads)
-      if (s_pre[t] >= thr_first && (t == 0 || s_pre[t - 1] < thr_first)) s_tile = t;
-  } else if (threadIdx.x == 0) {
-    s_tile = tile_lower_bound(pre_g, 0, T, thr_first);
+    total = 0; before = 0;
+#pragma unroll
+    for (int w = 0; w < kTileThreads / 32; ++w) { total += s_red[0][w]; before += s_red[1][w]; }
+  }
+  const double tot_d = u128_to_double(total);
+  const double n_d = (double)v.n_particles;
+  CountCtx c;
+  c.si.uu0 = tot_d * u / n_d;
+  c.si.du = tot_d / n_d;
+  c.offset = before;
+  c.n = n_p;
+  bool dead = false;
+  if (row >= 0) {
+    const double mx = key_to_double(mx_key);
+    dead = !(mx > __longlong_as_double(0xfff0000000000000LL)) || total == 0;
+    if (leader) {
+      finish_set(v, row, set, total, tot_d, mx);
+      apply_stop_rule(v, row, dead);
+    }
+  } else if (leader) {
+    apply_stop_rule(v, row, false);
+  }
+  if (dead || total == 0) {   // every weight vanished: the set keeps its particles
+    for (int k = 0; k < n_mine; ++k) heads[gbase + in_set + k] = (int)(gbase + in_set + k);
+    return;
+  }
+  c.d0 = u128_to_double(before) - c.si.uu0;
+  c.inv_du = 1.0 / c.si.du;
+
+  // ---- counts of the thread's 8 particles
+  uint32_t cnt[kTileItems];
+  {
+#pragma unroll
+    for (int j = 0; j < kTileItems; ++j) {
+      cnt[j] = j < n_mine ? slots_reached(c, q[j]) : n_p;
+      if (in_set + j >= n_p - 1) cnt[j] = n_p;   // the last particle takes whatever is left
+    }
+  }
+  // the count before the thread's first particle: the previous thread's last, the
+  // count at the tile's offset for the first thread (nothing for the set's first)
+  uint32_t prev = __shfl_up_sync(0xffffffffu, cnt[kTileItems - 1], 1);
+  if (lane == 31) s_cnt[warp] = cnt[kTileItems - 1];
+  __syncthreads();
+  if (lane == 0) prev = warp ? s_cnt[warp - 1] : (tile ? slots_reached(c, 0ULL) : 0u);
+
+  // ---- a particle with offspring: its index at its first slot and at the multiples of 32
+  // its slots cover (global slot numbers)
+#pragma unroll
+  for (int j = 0; j < kTileItems; ++j) {
+    const uint32_t a = prev, b = cnt[j];
+    prev = b;
+    if (b > a) {
+      const uint32_t A = (uint32_t)gbase + a, B = (uint32_t)gbase + b;
+      const int g = (int)((uint32_t)gbase + in_set + j);
+      heads[A] = g;
+      uint32_t m = (A | 31u) + 1u;
+      bool mine = true;
+      if (b - a >= kHeavySlots) {
+        const int e = atomicAdd(&s_heavy_n, 1);
+        if (e < kHeavyCap) {
+          s_heavy[e][0] = m; s_heavy[e][1] = B; s_heavy[e][2] = (uint32_t)g;
+          mine = false;
+        }
+      }
+      if (mine)
+        for (; m < B; m += 32) heads[m] = g;
+    }
   }
   __syncthreads();
-  int t_w = s_tile;   // first tile of the window (block-uniform)
-  const unsigned long long *cw_set = v.cw + gbase;
-  // the thread's slots, in order: tile and position only move forward
-  int k = 0, t = -1, pos = 0, tlen = 0;
-  u128 before = 0, tile_end = 0;
-  for (;;) {
-    __syncthreads();   // everyone has read s_tile and is done with the previous window
-    if (threadIdx.x == 0) s_tile = 0x7fffffff;
-    {  // ---- stage tiles t_w and t_w + 1 of the set's in-tile cumulative weights
-      const size_t w_base = (size_t)t_w * kTile;
-      const int w_len = (int)min((size_t)(kAncWinTiles * kTile), v.n_particles - w_base);
-      if (((gbase + w_base) & 1) == 0) {
-        const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(cw_set + w_base);
-        ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(s_cw);
-        for (int j = threadIdx.x; 2 * j + 1 < w_len; j += kTileThreads) dst[j] = __ldcg(src + j);
-        if ((w_len & 1) && threadIdx.x == 0) s_cw[w_len - 1] = __ldcg(cw_set + w_base + w_len - 1);
-      } else {
-        for (int j = threadIdx.x; j < w_len; j += kTileThreads) s_cw[j] = __ldcg(cw_set + w_base + j);
-      }
-    }
-    __syncthreads();
-    while (k < n_mine) {
-      const u128 thr = slot_threshold(si, il0 + k);
-      bool fresh = false;   // a tile this thread has not searched yet
-      if (t < 0 || (thr > tile_end && t < T - 1)) {
-        const int t_from = t < 0 ? t_w : t + 1;   // (t < 0 only in the first round: t_w = t_a)
-        t = (t_from < T - 1 && thr > pre[t_from]) ? tile_lower_bound(pre, t_from + 1, T, thr)
-                                                  : t_from;
-        before = t ? pre[t - 1] : (u128)0;
-        tile_end = pre[t];
-        tlen = (int)min((size_t)kTile, v.n_particles - (size_t)t * kTile);
-        fresh = true;
-        pos = 0;
-      }
-      if (t >= t_w + kAncWinTiles) {   // beyond the window: ask for it, wait for the next round
-        atomicMin(&s_tile, t);   // (pos == 0: the tile is searched afresh next round)
-        break;
-      }
-      const u128 d = thr > before ? thr - before : (u128)0;
-      const unsigned long long rem = (unsigned long long)(d >> 64) ? ~0ULL : (unsigned long long)d;
-      const unsigned long long *a = s_cw + (t - t_w) * kTile;
-      pos = (fresh || pos == 0) ? tile_search(a, tlen, rem) : tile_search_from(a, pos, tlen, rem);
-      out[k] = (int)(gbase + (size_t)t * kTile + pos);
-      ++k;
-    }
-    __syncthreads();
-    const int t_next = s_tile;
-    if (t_next == 0x7fffffff) break;   // every slot of the block has its ancestor
-    t_w = t_next;
+  const int n_heavy = min(s_heavy_n, kHeavyCap);
+  for (int e = 0; e < n_heavy; ++e) {
+    const uint32_t B = s_heavy[e][1];
+    const int g = (int)s_heavy[e][2];
+    for (uint32_t m = s_heavy[e][0] + 32u * tid; m < B; m += 32u * kTileThreads) heads[m] = g;
   }
 }
 
+// the slots in place: heads -> the ancestor of every slot (model$resample returns it)
+__global__ void __launch_bounds__(kGatherThreads) k_fill_ancestors(View v, int *heads) {
+  const size_t i = (size_t)blockIdx.x * kGatherThreads + threadIdx.x;
+  const bool live = i < v.n_total;
+  const size_t src = ancestor_of(heads, i, live);
+  if (live) heads[i] = (int)src;
+}
+
 // ---------------------------------------------------------------------------
-// Stand-alone gather (src -> dst) by the ancestors K3 wrote, used where the
+// Stand-alone gather (src -> dst) by the ancestor slots K3 filled, used where the
 // resampled state must exist in memory: snapshots and model$resample.
 // ---------------------------------------------------------------------------
 template <int NS>
@@ -787,8 +808,9 @@ k_resample_gather(View v, const int *__restrict__ kappa, const double *__restric
                   double *__restrict__ dst_buf) {
   if (v.flags[0]) return;
   const size_t i = (size_t)blockIdx.x * kGatherThreads + threadIdx.x;
-  if (i >= v.n_total) return;
-  const size_t src = (size_t)__ldcs(kappa + i);
+  const bool live = i < v.n_total;
+  const size_t src = ancestor_of(kappa, i, live);
+  if (!live) return;
 #pragma unroll
   for (int s = 0; s < NS; ++s)
     __stcs(dst_buf + (size_t)s * v.ld + i, __ldcs(src_buf + (size_t)s * v.ld + src));
@@ -800,10 +822,11 @@ k_resample_gather(View v, const int *__restrict__ kappa, const double *__restric
 // state of rs, as it is (R breaks before resampling), from whichever buffer rs wrote.
 template <int NS>
 __global__ void __launch_bounds__(kGatherThreads)
-k_finish_state(View v, int last, const int *__restrict__ kappa) {
+k_finish_state(View v, int last, const int *__restrict__ kappa, int *__restrict__ order_out) {
   const size_t i = (size_t)blockIdx.x * kGatherThreads + threadIdx.x;
-  if (i >= v.n_total) return;
+  const bool live = i < v.n_total;
   if (v.flags[0]) {
+    if (!live) return;
     const int rs = v.flags[1];
     if (((last - 1 - rs) & 1) == 0) {
 #pragma unroll
@@ -811,7 +834,9 @@ k_finish_state(View v, int last, const int *__restrict__ kappa) {
     }
     return;
   }
-  const size_t src = kappa ? (size_t)__ldcs(kappa + i) : i;
+  const size_t src = kappa ? ancestor_of(kappa, i, live) : i;
+  if (!live) return;
+  if (order_out) order_out[i] = (int)src;
 #pragma unroll
   for (int s = 0; s < NS; ++s)
     __stcs(v.y + (size_t)s * v.ld + i, __ldcs(v.y_tmp + (size_t)s * v.ld + src));

@@ -25,10 +25,14 @@
 #pragma once
 #include "samplers.cuh"
 
+#ifndef MCB_WALK_PF
+#define MCB_WALK_PF 0
+#endif
+
 namespace mcb {
 
 constexpr int kMaxState = 8;
-constexpr int kMaxPar = 8;
+constexpr int kMaxPar = 12;
 constexpr int kMaxDerived = 16;
 constexpr int kMaxConst = 2;     // draws with a parameter-only probability, per model
 
@@ -186,30 +190,34 @@ struct SirModel {
   }
 
   // ---- the lean path ------------------------------------------------------
-  // Register diet: the hot loop keeps the set's index and four counts (R is
-  // implied by the closed population); it makes no calls.  A step that meets
-  // anything unusual is abandoned with state and generator as they were at its
-  // start.
+  // Register diet: the hot loop keeps the set's index and three counts; it makes no
+  // calls.  R is implied by the closed population, and both incidence counters by S,
+  // which only ever falls by the infections: cumulative = its value at the start +
+  // (S at the start - S now), interval incidence = M - S with M = S + incidence,
+  // reset to the S of the moment when a new interval starts.  A step that meets
+  // anything unusual is abandoned with state and generator as they were at its start.
   struct Lean {
     uint32_t set;
   };
-  static constexpr int kLeanState = 4;  // S, I, cumulative, interval incidence
+  static constexpr int kLeanState = 3;  // S, I, M = S + interval incidence
   __device__ __forceinline__ static bool lean_load(const SetData &sd, const double *y, int *yi,
                                                    Lean &c) {
     int all[kState];
     if (!to_counts<kState>(y, all)) return false;
-    yi[0] = all[0]; yi[1] = all[1]; yi[2] = all[3]; yi[3] = all[4];
+    yi[0] = all[0]; yi[1] = all[1]; yi[2] = all[0] + all[4];
     // the tables are built for N = n_tot and cover counts < n_tab
     const double n_tot = __ldg(sd.derived + D_NTOT);
     return y[0] + y[1] + y[2] == n_tot && n_tot < (double)sd.n_tab;
   }
+  // y still holds the state lean_load saw
   __device__ __forceinline__ static void lean_store(const SetData &sd, const int *yi, double *y) {
     const double n_tot = __ldg(sd.derived + D_NTOT);
-    y[0] = (double)yi[0];
+    const double s_now = (double)yi[0];
+    y[3] = y[3] + (y[0] - s_now);             // exact: integers below 2^31
+    y[4] = (double)(yi[2] - yi[0]);
+    y[0] = s_now;
     y[1] = (double)yi[1];
-    y[2] = n_tot - (double)(yi[0] + yi[1]);   // exact: integers below 2^31
-    y[3] = (double)yi[2];
-    y[4] = (double)yi[3];
+    y[2] = n_tot - (double)(yi[0] + yi[1]);
   }
   // One model step; `reset`: it starts a new incidence interval (time % freq == 0).
   // false: nothing changed, the general code must run this step.
@@ -224,6 +232,11 @@ struct SirModel {
     const double4 e_si =
         ldg_f64x4(reinterpret_cast<const double *>(t.inf + (c.set * t.n_tab + (uint32_t)I)));
     const double4 F_ir = ldg_f64x4(row_ir);
+#if MCB_WALK_PF
+    // the row's next four entries (the next 32-byte sector of the same line) are wanted by
+    // most warps a few instructions from now: ask for them without a register
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(row_ir + 4));
+#endif
     int n_IR = 0;
     if (I != 0) {
       n_IR = draw_const_lean<SCR>(rng, I, row_ir, F_ir, t);
@@ -236,8 +249,7 @@ struct SirModel {
     }
     y[0] = S - n_SI;
     y[1] = I + n_SI - n_IR;
-    y[2] = y[2] + n_SI;
-    y[3] = reset ? n_SI : y[3] + n_SI;
+    if (reset) y[2] = S;
     return true;
   }
 };

@@ -2,7 +2,8 @@
 //
 // Algorithms are those of the reference's native dependency dust [SURVEY.md
 // A.2]: binomial by CDF inversion (n q < 10) or Hoermann's BTRS transformed
-// rejection, Poisson by Knuth's product (lambda < 10) or PTRS.  The number of
+// rejection (draw_binomial), Poisson by Knuth's product (lambda < 10) or PTRS
+// (draw_poisson), normal by Box-Muller, exponential by inversion.  The number of
 // uniforms a draw consumes is data dependent, which is why every particle owns
 // a stream; the order of draws and of floating-point operations is part of the
 // contract (bit-exact against the oracle).
@@ -167,11 +168,20 @@ __device__ __forceinline__ double2 ldg_f64x2(const double *p) {
   asm("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(e.x), "=d"(e.y) : "l"(p));
   return e;
 }
-// one 32-byte load (LDG.256): four consecutive table entries
+// one 32-byte load (LDG.256): four consecutive table entries.  MCB_TAB_LD = 1 asks L1 to
+// keep the line (evict-last): the tables are read at every model step
+#ifndef MCB_TAB_LD
+#define MCB_TAB_LD 0
+#endif
 __device__ __forceinline__ double4 ldg_f64x4(const double *p) {
   double4 e;
+#if MCB_TAB_LD == 1
+  asm("ld.global.nc.L1::evict_last.v4.f64 {%0, %1, %2, %3}, [%4];"
+      : "=d"(e.x), "=d"(e.y), "=d"(e.z), "=d"(e.w) : "l"(p));
+#else
   asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
       : "=d"(e.x), "=d"(e.y), "=d"(e.z), "=d"(e.w) : "l"(p));
+#endif
   return e;
 }
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
@@ -410,6 +420,46 @@ __device__ __forceinline__ double draw_binomial_const(Xoshiro &rng, bool determi
     draw = inversion_walk<SCR>(rng, ni, c.r, pow_int(c.qq, ni));
   }
   return c.flip ? n - draw : draw;
+}
+
+// Poisson(lambda) [SURVEY.md A.2]: lambda == 0 -> 0 without a draw; below 10 Knuth's
+// product of uniforms against exp(-lambda); from 10 up Hoermann's PTRS transformed
+// rejection (two uniforms per attempt), log(k!) from det_lfact.  deterministic = true
+// gives the mean.  Oracle twin: orc_poisson.
+template <int SCR>
+__device__ __noinline__ double poisson_ptrs(Xoshiro &rng, double lambda) {
+  const double b = 0.931 + 2.53 * sqrt(lambda);
+  const double a = -0.059 + 0.02483 * b;
+  const double inv_alpha = 1.1239 + 1.1328 / (b - 3.4);
+  const double v_r = 0.9277 - 3.6224 / (b - 2.0);
+  const double log_lambda = det_log(lambda);
+  for (;;) {
+    const double u = xo_real<SCR>(rng) - 0.5;
+    const double v = xo_real<SCR>(rng);
+    const double us = 0.5 - fabs(u);
+    const double k = floor((2.0 * a / us + b) * u + lambda + 0.43);
+    if (us >= 0.07 && v <= v_r) return k;
+    if (k < 0.0 || (us < 0.013 && v > us)) continue;
+    if (det_log(v) + det_log(inv_alpha) - det_log(a / (us * us) + b) <=
+        -lambda + k * log_lambda - det_lfact(k))
+      return k;
+  }
+}
+
+template <int SCR>
+__device__ __forceinline__ double draw_poisson(Xoshiro &rng, bool deterministic, double lambda) {
+  if (deterministic) return lambda;
+  if (lambda == 0.0) return 0.0;
+  if (lambda < 10.0) {
+    const double lim = det_exp(-lambda);
+    double prod = 1.0, k = 0.0;
+    for (;;) {
+      prod *= xo_real<SCR>(rng);
+      if (prod <= lim) return k;
+      k += 1.0;
+    }
+  }
+  return poisson_ptrs<SCR>(rng, lambda);
 }
 
 // x log(lambda) - lambda - lgamma(x + 1); lgamma(x + 1) depends on the datum

@@ -340,6 +340,26 @@ double orc_binomial(uint64_t s[4], int scrambler, double n, double p) {
   return p > 0.5 ? n - draw : draw;
 }
 
+/* log(k!) for an integer-valued k >= 0, reproducible to the bit (engine twin:
+ * det_lfact, csrc/detmath.cuh): a table below 16, from there Stirling's series for
+ * lgamma(x), x = k + 1, with four correction terms (truncation below 1e-14 at
+ * x = 17) -- IEEE operations and orc_log only, no libm lgamma. */
+static const double k_log_fact[16] = {
+    0.0, 0.0, 0.693147180559945, 1.7917594692280554, 3.178053830347945, 4.787491742782047,
+    6.579251212010102, 8.525161361065415, 10.604602902745249, 12.801827480081467,
+    15.104412573075514, 17.502307845873887, 19.987214495661885, 22.55216385312342,
+    25.191221182738683, 27.89927138384089};
+double orc_lfact(double k) {
+  if (k < 16.0) return k_log_fact[(int)k];
+  const double x = k + 1.0;
+  const double xi = 1.0 / x, x2 = xi * xi;
+  const double ser =
+      (1.0 / 12.0 - x2 * (1.0 / 360.0 - x2 * (1.0 / 1260.0 - x2 * (1.0 / 1680.0)))) * xi;
+  return (x - 0.5) * orc_log(x) - x + 0.91893853320467274178 + ser;
+}
+
+/* lambda == 0 -> 0 (no draw); Knuth's product below 10; Hoermann's
+ * PTRS from 10 up, with log(k!) from orc_lfact */
 double orc_poisson(uint64_t s[4], int scrambler, double lambda) {
   if (lambda == 0.0) return 0.0;
   if (lambda < 10.0) { /* Knuth: multiply uniforms until below exp(-lambda) */
@@ -365,7 +385,7 @@ double orc_poisson(uint64_t s[4], int scrambler, double lambda) {
     if (us >= 0.07 && v <= v_r) return k;
     if (k < 0.0 || (us < 0.013 && v > us)) continue;
     if (orc_log(v) + orc_log(inv_alpha) - orc_log(a / (us * us) + b) <=
-        -lambda + k * log_lambda - lgamma(k + 1.0))
+        -lambda + k * log_lambda - orc_lfact(k))
       return k;
   }
 }
@@ -543,11 +563,11 @@ void orc_history_single(const double *value, const int *order, size_t ny,
 /*   volatility: alpha sigma gamma tau x0                              */
 /*     (tests/testthat/helper-mcstate.R:98-146: x' = alpha x + sigma N(0,1),  */
 /*      observed ~ N(gamma x, tau); one real state, the Kalman filter is exact) */
-/*   seir: beta sigma gamma I0 exp_noise S0 E0 freq                    */
+/*   seir: beta sigma gamma I0 exp_noise S0 E0 freq import             */
 /*     (not a dust example: the twin of mcstate_b200/examples/seir.cuh, the   */
 /*      user-supplied model the engine compiles the way dust::dust() would)   */
 /* ------------------------------------------------------------------ */
-#define ORC_MAX_PAR 8
+#define ORC_MAX_PAR 12
 #define ORC_MAX_STATE 8
 
 size_t orc_model_n_state(int model) {
@@ -555,7 +575,7 @@ size_t orc_model_n_state(int model) {
        : 1;   /* volatility, walk: 1 */
 }
 size_t orc_model_n_par(int model) {
-  return model == ORC_MODEL_SIR ? 7 : model == ORC_MODEL_SIRS || model == ORC_MODEL_SEIR ? 8
+  return model == ORC_MODEL_SIR ? 7 : model == ORC_MODEL_SIRS ? 8 : model == ORC_MODEL_SEIR ? 9
        : model == ORC_MODEL_VOLATILITY ? 5 : 1;
 }
 size_t orc_model_n_data(int model) { (void)model; return 1; }
@@ -572,7 +592,7 @@ void orc_model_default_pars(int model, double *p) {
     p[0] = 0.91; p[1] = 1.0; p[2] = 1.0; p[3] = 1.0; p[4] = 0.0;
   } else if (model == ORC_MODEL_SEIR) {
     p[0] = 0.3; p[1] = 0.25; p[2] = 0.1; p[3] = 10.0; p[4] = 1e6; p[5] = 1000.0; p[6] = 0.0;
-    p[7] = 4.0;
+    p[7] = 4.0; p[8] = 0.0;
   } else {
     p[0] = 1.0;   /* walk: sd */
   }
@@ -631,7 +651,8 @@ static void sirs_update(uint64_t time, const double *y, uint64_t s[4], int scr, 
 }
 
 /* SIR with a latent compartment (vignettes/sir_models.Rmd:44-54 extended): draws in the
- * order S->E, E->I, I->R; incidence counts E->I */
+ * order S->E, E->I, I->R, then Poisson(import dt) exposed arrivals from outside (no draw
+ * when import == 0); incidence counts E->I */
 static void seir_update(uint64_t time, const double *y, uint64_t s[4], int scr, int det,
                         const double *p, double *yn) {
   const double S = y[0], E = y[1], I = y[2], R = y[3];
@@ -643,8 +664,10 @@ static void seir_update(uint64_t time, const double *y, uint64_t s[4], int scr, 
   const double n_SE = draw_binomial(s, scr, det, S, p_SE * dt);
   const double n_EI = draw_binomial(s, scr, det, E, p_EI * dt);
   const double n_IR = draw_binomial(s, scr, det, I, p_IR * dt);
+  const double lambda = p[8] * dt;
+  const double n_imp = det ? lambda : orc_poisson(s, scr, lambda);
   yn[0] = S - n_SE;
-  yn[1] = E + n_SE - n_EI;
+  yn[1] = E + n_SE - n_EI + n_imp;
   yn[2] = I + n_EI - n_IR;
   yn[3] = R + n_IR;
   yn[4] = y[4] + n_EI;

@@ -64,6 +64,7 @@ double orc_normal(uint64_t s[4], int scrambler, double mean, double sd);
 double orc_density_normal_log(double x, double mu, double sd);
 double orc_binomial(uint64_t s[4], int scrambler, double n, double p);
 double orc_poisson(uint64_t s[4], int scrambler, double lambda);
+double orc_lfact(double k);   /* log(k!), reproducible (engine twin: det_lfact) */
 double orc_density_poisson_log(double x, double lgamma_x1, double lambda);
 
 /* ---- weights and resampling ---- */

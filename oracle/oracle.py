@@ -78,6 +78,7 @@ def lib():
         "orc_density_normal_log": (C.c_double, [C.c_double, C.c_double, C.c_double]),
         "orc_binomial": (C.c_double, [_u64p, C.c_int, C.c_double, C.c_double]),
         "orc_poisson": (C.c_double, [_u64p, C.c_int, C.c_double]),
+        "orc_lfact": (C.c_double, [C.c_double]),
         "orc_density_poisson_log": (C.c_double, [C.c_double, C.c_double, C.c_double]),
         "orc_scale_log_weights_r": (C.c_double, [_f64p, C.c_size_t, _f64p]),
         "orc_scale_log_weights": (C.c_double, [_f64p, C.c_size_t, C.c_int]),

@@ -31,3 +31,13 @@ def sir_data():
     d = np.loadtxt(os.path.join(ROOT, "tests", "golden", "sir_incidence.csv"), delimiter=",",
                    skiprows=1)
     return {"day": d[:, 1].astype(int), "incidence": d[:, 0]}
+
+
+def free_port():
+    """A TCP port nobody listens on right now (torchrun rendezvous of the 2-rank tests): asked
+    of the kernel, so two tests of one pytest process never meet on a port still in TIME_WAIT."""
+    import socket
+
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]

@@ -53,6 +53,12 @@ def vectors():
     v["exp"] = {repr(x): bits(L.orc_exp(x)) for x in xs}
     xs = [1e-300, 1e-6, 0.1, 0.5, 0.999999, 1.0, 1.5, 10.0, 1e6, 1e300]
     v["log"] = {repr(x): bits(L.orc_log(x)) for x in xs}
+    v["lfact"] = {repr(k): bits(L.orc_lfact(k)) for k in (0.0, 1.0, 15.0, 16.0, 17.0, 250.0, 1e6)}
+    v["poisson_ptrs_seed7"] = {}
+    for lam in (10.0, 37.5, 1e4, 1e6):
+        st = O.seed_state(7).copy()
+        p = st.ctypes.data_as(O._u64p)
+        v["poisson_ptrs_seed7"][repr(lam)] = [L.orc_poisson(p, O.PLUS, lam) for _ in range(6)]
     xs = [0.0, 1e-9, 0.1, 0.125, 0.2, 0.3, 0.49, 0.6, 0.77, 0.999]
     v["cos2pi"] = {repr(x): bits(L.orc_cos2pi(x)) for x in xs}
 

@@ -14,7 +14,7 @@ PAR_NAMES = {O.SIR: ["beta", "gamma", "I0", "exp_noise", "S0", "R0", "freq"],
              O.SIRS: ["alpha", "beta", "gamma", "I0", "exp_noise", "S0", "R0", "freq"],
              O.VOLATILITY: ["alpha", "sigma", "gamma", "tau", "x0"],
              O.WALK: ["sd"],
-             O.SEIR: ["beta", "sigma", "gamma", "I0", "exp_noise", "S0", "E0", "freq"]}
+             O.SEIR: ["beta", "sigma", "gamma", "I0", "exp_noise", "S0", "E0", "freq", "import"]}
 STATE_NAMES = {O.SIR: ["S", "I", "R", "cases_cumul", "cases_inc"],
                O.SIRS: ["S", "I", "R", "cases_inc"],
                O.VOLATILITY: ["x"],

@@ -157,6 +157,20 @@ def test_poisson_moments(orc, lam):
     assert abs(x.var() - lam) < 0.06 * lam + 0.05
 
 
+def test_lfact_is_log_factorial(orc):
+    """log(k!) without libm's lgamma (table below 16, Stirling's series from there): the
+    Poisson sampler's acceptance test must give the same bits on the CPU and on the GPU."""
+    L = orc.lib()
+    for k in list(range(0, 400)) + [1000, 12345, 10 ** 6, 10 ** 9]:
+        want = math.lgamma(k + 1.0)
+        assert abs(L.orc_lfact(float(k)) - want) <= 1e-15 * max(1.0, want), k
+    s = orc.seed_state(3)
+    p = s.ctypes.data_as(C.POINTER(C.c_uint64))
+    before = s.copy()
+    assert L.orc_poisson(p, 0, 0.0) == 0.0
+    assert np.array_equal(s, before)   # lambda == 0: no uniform consumed
+
+
 def test_exponential_and_density(orc):
     x = _draws(orc, orc.lib().orc_exponential, 40000, 4.0)
     assert abs(x.mean() - 0.25) < 0.01

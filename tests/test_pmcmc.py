@@ -13,6 +13,7 @@ import textwrap
 
 import numpy as np
 import pytest
+from conftest import free_port
 
 from mcstate_b200.particle_filter import particle_filter
 from mcstate_b200.particle_filter_data import particle_filter_data
@@ -273,7 +274,7 @@ def _run_sharded(tmp_path, kind, n_chains, world, backend):
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
            "--nproc-per-node=%d" % world, "--master-addr", "127.0.0.1", "--master-port",
-           str(29500 + os.getpid() % 2000), str(script), kind, str(n_chains), str(out)]
+           str(free_port()), str(script), kind, str(n_chains), str(out)]
     p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stderr[-3000:]
     with open(out, "rb") as fh:

@@ -11,6 +11,7 @@ import textwrap
 
 import numpy as np
 import pytest
+from conftest import free_port
 
 from mcstate_b200.particle_filter import particle_filter
 from mcstate_b200.particle_filter_data import particle_filter_data, subset_populations
@@ -105,7 +106,7 @@ def _sharded(tmp_path, kind, n_pop, n_particles, world=2):
     out = tmp_path / "res.pkl"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
            "--nproc-per-node=%d" % world, "--master-addr", "127.0.0.1", "--master-port",
-           str(31000 + os.getpid() % 2000), str(script), kind, str(n_pop), str(n_particles),
+           str(free_port()), str(script), kind, str(n_pop), str(n_particles),
            str(out)]
     p = subprocess.run(cmd, env=dict(os.environ, MASTER_ADDR="127.0.0.1"), capture_output=True,
                        text=True, timeout=600)

@@ -9,6 +9,7 @@ import textwrap
 
 import numpy as np
 import pytest
+from conftest import free_port
 
 from mcstate_b200.particle_filter import particle_filter
 from mcstate_b200.particle_filter_data import particle_filter_data
@@ -169,7 +170,7 @@ def test_sharded_smc2_equals_single_rank(tmp_path, kind):
     script.write_text(_WORKER.format(root=ROOT))
     out = tmp_path / "res.pkl"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-           "--master-addr", "127.0.0.1", "--master-port", str(33000 + os.getpid() % 2000),
+           "--master-addr", "127.0.0.1", "--master-port", str(free_port()),
            str(script), kind, str(out)]
     r = subprocess.run(cmd, env=dict(os.environ, MASTER_ADDR="127.0.0.1"), capture_output=True,
                        text=True, timeout=900)

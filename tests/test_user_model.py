@@ -36,7 +36,7 @@ def test_user_model_library_builds_and_exports_the_abi():
     L = _lib.load(path)
     mid, ns, npar, nd = C.c_int(-1), C.c_size_t(), C.c_size_t(), C.c_size_t()
     assert L.mcb_model_lookup(b"seir", C.byref(mid), C.byref(ns), C.byref(npar), C.byref(nd)) == 0
-    assert (mid.value, ns.value, npar.value, nd.value) == (0, 6, 8, 1)
+    assert (mid.value, ns.value, npar.value, nd.value) == (0, 6, 9, 1)
     assert [L.mcb_model_par_name(0, i).decode() for i in range(8)] == \
         ["beta", "sigma", "gamma", "I0", "exp_noise", "S0", "E0", "freq"]
     assert [L.mcb_model_state_name(0, i).decode() for i in range(6)] == \
@@ -54,7 +54,8 @@ def test_user_model_generator_describes_itself():
     assert g.name == "dust_generator" and g.model_name == "seir"
     assert g.has_compare() and g.time_type() == "discrete"
     assert g.state_names == ["S", "E", "I", "R", "cases_cumul", "cases_inc"]
-    assert g.par_defaults == [0.3, 0.25, 0.1, 10.0, 1e6, 1000.0, 0.0, 4.0]
+    assert g.par_defaults == [0.3, 0.25, 0.1, 10.0, 1e6, 1000.0, 0.0, 4.0, 0.0]
+    assert g.par_names[-1] == "import"   # Poisson arrivals (samplers.cuh: draw_poisson)
     assert g._info({"beta": 0.4})["pars"]["beta"] == 0.4
 
 
@@ -128,6 +129,43 @@ def test_user_model_run_bit_exact(orc, alg, scr):
         for t_end in (1, 4, 7, 200):
             assert np.array_equal(m.run(t_end), o.run(t_end)), (pars, t_end)
             assert np.array_equal(_words(m), o.rng_state())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("alg,scr", [("xoshiro256plus", 0), ("xoshiro256starstar", 1)])
+def test_poisson_draws_bit_exact(orc, alg, scr):
+    """The device Poisson sampler (samplers.cuh: draw_poisson -- Knuth's product below 10,
+    PTRS from 10 up, log(k!) from det_lfact) against orc_poisson over a sweep of lambda,
+    through the SEIR model's importation term: with an empty population every binomial
+    returns 0 without a draw, so after one step E holds Poisson(import) from each
+    particle's own stream (BASELINE north_star item 1)."""
+    from mcstate_b200 import dust
+
+    g = dust.dust(SEIR, algorithm=alg)
+    n = 20000
+    L = orc.lib()
+    for lam in (0.0, 1e-3, 0.5, 3.0, 9.999, 10.0, 10.5, 37.5, 1e3, 1e6):
+        pars = {"S0": 0.0, "I0": 0.0, "E0": 0.0, "freq": 1.0, "import": lam}
+        m = g.new(pars, 0, n, seed=13)
+        y = m.run(1)
+        streams = orc.rng_streams(13, n + 1)[:n].copy()
+        want = np.array([L.orc_poisson(streams[i].ctypes.data_as(orc._u64p), scr, lam)
+                         for i in range(n)])
+        assert np.array_equal(y[1], want), lam
+        assert np.array_equal(_words(m)[:n], streams), lam
+        if lam >= 0.5:
+            assert abs(want.mean() - lam) < 5 * np.sqrt(lam / n)
+    # the importation term inside a running epidemic, filter and all, against the twin
+    t, x = np.arange(1, 31, dtype=np.uint64) * 4, np.arange(30) % 7 + 1.0
+    for pars in ({"import": 2.0}, {"import": 60.0, "beta": 0.1}):
+        m = g.new(pars, 0, 3000, seed=2)
+        m.set_data(dust.dust_data({"time_end": t, "incidence": x}), False)
+        o = orc.OracleModel(pars=g._pars_vector(pars, False), n_particles=3000, seed=2,
+                            model=SEIR_ID, scrambler=scr, n_threads=8)
+        o.set_data(t, x)
+        assert np.array_equal(m.filter()["log_likelihood"], o.filter()["log_likelihood"])
+        assert np.array_equal(m.state(), o.state())
+        assert np.array_equal(_words(m), o.rng_state())
 
 
 @pytest.mark.gpu
