@@ -7,7 +7,10 @@ the model's initial state, then 100 data intervals of 4 model steps each with co
 log-mean-exp, systematic resampling and state gather -- on the SIR model at
 2^20 particles (config C2).  At N > 1 GPUs every rank runs its own filter (independent
 chains, the pmcmc_parallel layout: R/pmcmc_parallel.R:8-20), so scaling is weak and the
-path has no collective; ranks only meet at the timing barrier.
+headline has no collective; ranks only meet at the timing barrier.  The configurations
+that DO exchange data between GPUs -- C3 pmcmc chains, C4 nested populations, C5 smc2 --
+are timed after the headline in the same launch (bench_configs.py) and reported under
+"configs" in the same JSON line (MCB_BENCH_CONFIGS=0 skips them).
 
   python bench.py --gpus N --steps K --warmup W          (this engine)
   python bench.py --impl reference ...                   (CPU arm: the oracle port on
@@ -37,13 +40,15 @@ UNIT = "particle-steps/s"
 # unfused pipeline (K1 152 + K2 8 + K3 20 + K4 84).  The engine fuses K3+K4 into K1's load,
 # so the bytes its kernels must move are fewer; the per-kernel roofline uses THESE (the
 # conservative figure), the whole-interval fraction uses the survey's 264 B.
-#   k_run_compare : ancestor index 4 + state in 40 (gathered) + rng in 32
+#   k_run_compare : ancestor slot 4 + state in 40 (gathered) + rng in 32
 #                   + state out 40 + rng out 32 + logw out 8                      = 156
-#   k_weights_scan: logw in 8 + cumulative weight out 8                           = 16
-#   k_ancestors   : cumulative weight in 8 + ancestor index out 4                 = 12
-#   k_finish_state: (once per filter call) index 4 + state in 40 + state out 40   = 84
-BYTES_K1, BYTES_K2, BYTES_K3, BYTES_FINISH = 156, 16, 12, 84
-BYTES_INTERVAL = 264
+#   k_weights_scan: logw in 8 + cumulative weight out 8 + ancestor slot emptied 4 = 20
+#   k_ancestors   : cumulative weight in 8 + ancestor slot out 4 (one per
+#                   particle with offspring, at most)                             = 12
+#   k_finish_state: (once per filter call) slot 4 + state in 40 + state out 40    = 84
+BYTES_K1, BYTES_K2, BYTES_K3, BYTES_FINISH = 156, 20, 12, 84
+BYTES_ENGINE_INTERVAL = BYTES_K1 + BYTES_K2 + BYTES_K3      # what this engine moves: 188
+BYTES_INTERVAL = 264                                         # SURVEY.md 8(d), unfused
 
 
 def load_data():
@@ -186,7 +191,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_sample = 1 << 17
+    n_sample = N_PARTICLES   # the configuration the metric is quoted on, not a fraction
     t, _ = load_data()
     from oracle import oracle as O
 
@@ -203,8 +208,8 @@ def run_reference(args):
             times.append(time.perf_counter() - t0)
     total = sum(times)
     value = n_sample * int(t[-1]) * len(times) / total
-    sample = "filter at %d particles (1/%d of the workload's 2^20), all 100 intervals" % (
-        n_sample, N_PARTICLES // n_sample)
+    sample = ("one whole filter evaluation per step: %d particles x 100 intervals x 4 steps, "
+              "the workload itself" % n_sample)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
@@ -239,8 +244,18 @@ def run_engine(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: mcstate_b200 has no CPU fallback")
     torch.cuda.set_device(local)
+    run_configs = os.environ.get("MCB_BENCH_CONFIGS", "1") != "0"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    elif run_configs:
+        # one rank: the sharded callers of bench_configs.py still take a process group
+        import socket
+
+        with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=0,
+                                world_size=1, device_id=torch.device("cuda", local))
 
     from mcstate_b200 import dust
     from mcstate_b200.particle_filter import particle_filter
@@ -345,6 +360,14 @@ def run_engine(args):
             torch.cuda.synchronize()
             small[name] = (time.perf_counter() - t0) / 20 * 1e3
 
+    # ---- the configurations with a collective (C3, C4, C5), same launch, own clocks
+    configs = None
+    if run_configs:
+        import bench_configs
+
+        del pf, model
+        configs = bench_configs.run_configs(local, ClockSampler)
+
     tmax = torch.tensor([ms_total, e2e_s * 1e3], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -379,19 +402,26 @@ def run_engine(args):
                         "frac": a / peak, "traffic": traffic, "traffic_source": traffic_src,
                         "peak_source": peak_kind,
                         "algorithmic_bytes_per_launch": per_launch_bytes[names.index(dom)],
-                        "whole_interval_frac": (BYTES_INTERVAL * N_PARTICLES * 100 * args.steps /
-                                                (ms_total * 1e-3) / 1e9) / peak,
+                        # the whole pipeline on the bytes this engine moves per particle and
+                        # interval (188 B: the gather is fused into K1's load) -- and, for
+                        # comparison only, on SURVEY.md 8(d)'s 264 B of an unfused pipeline
+                        "whole_interval_frac": (BYTES_ENGINE_INTERVAL * N_PARTICLES * 100 *
+                                                args.steps / (ms_total * 1e-3) / 1e9) / peak,
+                        "whole_interval_frac_unfused_264B": (
+                            BYTES_INTERVAL * N_PARTICLES * 100 * args.steps /
+                            (ms_total * 1e-3) / 1e9) / peak,
                         "instrumented_ms_per_step": ms_instrumented / args.steps,
                         "issue": ncu_issue_counters(dom),
                         "kernels": kernels}
         cores = os.cpu_count() or 1
         cpu = None
-        if world == 1 or True:
-            n_cpu = 1 << 19
-            v, secs, _ = cpu_baseline(n_cpu, cores, reps=2)
+        if world == 1:
+            n_cpu = N_PARTICLES
+            v, secs, ll_cpu = cpu_baseline(n_cpu, cores, reps=2)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": "oracle filter at %d particles x 100 intervals (1/2 of one GPU's "
-                             "work), best of 2 after a warm-up run, %.2f s each" % (n_cpu, secs)}
+                   "sample": "oracle filter at %d particles x 100 intervals (one GPU's whole "
+                             "workload), best of 2 after a warm-up run, %.2f s each" % (n_cpu, secs),
+                   "log_likelihood_equals_gpu": bool(ll_cpu == float(ll[0]))}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
@@ -406,9 +436,10 @@ def run_engine(args):
             "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks.summary(),
             "small_filter_c3": small,
+            "configs": configs,
         }
         print(json.dumps(line))
-    if world > 1:
+    if dist.is_initialized():
         dist.destroy_process_group()
 
 

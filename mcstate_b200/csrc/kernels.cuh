@@ -253,19 +253,24 @@ __device__ __forceinline__ size_t ancestor_of(const int *__restrict__ heads, siz
 // The general form of the model steps (state as doubles, every special case of
 // the draws), out of line so the run kernel's registers are sized for the lean
 // path: deterministic mode, non-integer or out-of-table states.
+// State and generator travel BY VALUE: a pointer to the caller's state would pin it to
+// local memory for the whole kernel (every thread's frame in L1, next to the memo tables),
+// whereas a value is only spilled around this call, which hardly ever happens.
+template <class M>
+struct ParticleState {
+  double y[M::kState];
+  uint64_t s0, s1, s2, s3;
+};
 template <class M, int SCR>
-__device__ __noinline__ void run_general(double *y, uint64_t *rs, uint64_t t0, uint32_t n_steps,
-                                         const double *derived, int n_tab, bool det) {
+__device__ __noinline__ ParticleState<M> run_general(ParticleState<M> p, uint64_t t0,
+                                                     uint32_t n_steps, const double *derived,
+                                                     int n_tab, bool det) {
   const SetData sd{derived, n_tab};
   const typename M::Ctx ctx = M::context(sd);
-  Xoshiro rng{rs[0], rs[1], rs[2], rs[3]};
-  double z[M::kState];
-#pragma unroll
-  for (int s = 0; s < M::kState; ++s) z[s] = y[s];
-  for (uint32_t k = 0; k < n_steps; ++k) M::template update<SCR>(t0 + k, z, rng, ctx, det);
-#pragma unroll
-  for (int s = 0; s < M::kState; ++s) y[s] = z[s];
-  rs[0] = rng.s0; rs[1] = rng.s1; rs[2] = rng.s2; rs[3] = rng.s3;
+  Xoshiro rng{p.s0, p.s1, p.s2, p.s3};
+  for (uint32_t k = 0; k < n_steps; ++k) M::template update<SCR>(t0 + k, p.y, rng, ctx, det);
+  p.s0 = rng.s0; p.s1 = rng.s1; p.s2 = rng.s2; p.s3 = rng.s3;
+  return p;
 }
 
 // `n_steps` model updates of one particle, state and generator in registers: the
@@ -314,9 +319,14 @@ __device__ __forceinline__ void run_model_steps(const View &v, const SetData &sd
     // a model without integer compartments has one form only: inline
     for (uint32_t k = 0; k < n_steps; ++k) M::template update<SCR>(t0 + k, y, rng, ctx, det);
   } else if (done < n_steps) {  // whatever the lean path did not take
-    uint64_t rs[4] = {rng.s0, rng.s1, rng.s2, rng.s3};
-    run_general<M, SCR>(y, rs, t0 + done, n_steps - done, sd.derived, sd.n_tab, det);
-    rng.s0 = rs[0]; rng.s1 = rs[1]; rng.s2 = rs[2]; rng.s3 = rs[3];
+    ParticleState<M> p;
+#pragma unroll
+    for (int s = 0; s < M::kState; ++s) p.y[s] = y[s];
+    p.s0 = rng.s0; p.s1 = rng.s1; p.s2 = rng.s2; p.s3 = rng.s3;
+    p = run_general<M, SCR>(p, t0 + done, n_steps - done, sd.derived, sd.n_tab, det);
+#pragma unroll
+    for (int s = 0; s < M::kState; ++s) y[s] = p.y[s];
+    rng.s0 = p.s0; rng.s1 = p.s1; rng.s2 = p.s2; rng.s3 = p.s3;
   }
 }
 
@@ -345,15 +355,18 @@ __global__ void __launch_bounds__(kRunThreads, k1_min_blocks<M>())
 k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_out,
               uint64_t t0, uint32_t n_steps, const int *__restrict__ kappa, int row,
               double *__restrict__ hist, int *__restrict__ order_out) {
-  __shared__ unsigned long long s_key[kRunThreads / 32];
-  __shared__ double s_exp2[kExp2Tab];
+  // every warp keeps its own copy of the 2^(j/32) table: the warps of a block never
+  // wait for one another (no block barrier anywhere in this kernel)
+  static_assert(kExp2Tab == 32, "one table entry per lane");
+  __shared__ double s_exp2_all[kRunThreads / 32][kExp2Tab];
+  double *s_exp2 = s_exp2_all[threadIdx.x >> 5];
   // programmatic dependent launch: let the next kernel be scheduled as this one
   // drains, and do not read anything an earlier kernel wrote before the wait
   grid_launch_dependents();
-  if (threadIdx.x < kExp2Tab) s_exp2[threadIdx.x] = __ldg(g_exp2_tab + threadIdx.x);
+  s_exp2[threadIdx.x & 31] = __ldg(g_exp2_tab + (threadIdx.x & 31));
+  __syncwarp();
   grid_dependency_wait();
   if (v.flags[0]) return;
-  __syncthreads();
   const size_t i = (size_t)blockIdx.x * kRunThreads + threadIdx.x;
   const bool live = i < v.n_total;
   const size_t ii = live ? i : v.n_total - 1;
@@ -412,12 +425,14 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
   }
   if (row < 0) return;
 
-  // max of logw per parameter set: block reduce when the block sits inside
-  // one set (the common case), else one atomic per weighted thread
-  const size_t first = (size_t)blockIdx.x * kRunThreads;
-  size_t last = first + kRunThreads - 1;
+  // max of logw per parameter set: one reduction per warp when the warp sits inside one
+  // set (the common case), and an atomic only if it would raise the maximum as it stands
+  // (the maximum only grows: after the first blocks hardly any warp has to); else one
+  // atomic per weighted thread
+  const size_t first = i - (threadIdx.x & 31);
+  size_t last = first + 31;
   if (last >= v.n_total) last = v.n_total - 1;
-  const size_t set_first = SINGLE ? 0 : set_of(v, first);
+  const size_t set_first = SINGLE ? 0 : set_of(v, first < v.n_total ? first : v.n_total - 1);
   const bool one_set = SINGLE || set_first == set_of(v, last);
   unsigned long long *slot = v.wmax + (size_t)row * v.n_sets;
   if (one_set) {
@@ -427,13 +442,8 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
     const unsigned m_hi = __reduce_max_sync(0xffffffffu, hi);
     const unsigned m_lo = __reduce_max_sync(0xffffffffu, hi == m_hi ? (unsigned)key : 0u);
     key = ((unsigned long long)m_hi << 32) | m_lo;
-    if ((threadIdx.x & 31) == 0) s_key[threadIdx.x >> 5] = key;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-#pragma unroll
-      for (int w = 1; w < kRunThreads / 32; ++w) key = s_key[w] > key ? s_key[w] : key;
-      if (key) atomicMax(slot + set_first, key);
-    }
+    if ((threadIdx.x & 31) == 0 && key && key > __ldcg(slot + set_first))
+      atomicMax(slot + set_first, key);
   } else if (weighted) {
     atomicMax(slot + set, key);
   }

@@ -190,34 +190,32 @@ struct SirModel {
   }
 
   // ---- the lean path ------------------------------------------------------
-  // Register diet: the hot loop keeps the set's index and three counts; it makes no
-  // calls.  R is implied by the closed population, and both incidence counters by S,
-  // which only ever falls by the infections: cumulative = its value at the start +
-  // (S at the start - S now), interval incidence = M - S with M = S + incidence,
-  // reset to the S of the moment when a new interval starts.  A step that meets
-  // anything unusual is abandoned with state and generator as they were at its start.
+  // Register diet: the hot loop works on S, I and M; it makes no calls.  R is implied by
+  // the closed population, and both incidence counters by S, which only ever falls by
+  // the infections: cumulative + S never changes (C, set once), and the interval
+  // incidence is M - S with M = S + incidence, reset to the S of the moment when a new
+  // interval starts.  A step that meets anything unusual is abandoned with state and
+  // generator as they were at its start.
   struct Lean {
     uint32_t set;
   };
-  static constexpr int kLeanState = 3;  // S, I, M = S + interval incidence
+  static constexpr int kLeanState = 4;  // S, I, M = S + interval incidence, C = S + cumulative
   __device__ __forceinline__ static bool lean_load(const SetData &sd, const double *y, int *yi,
                                                    Lean &c) {
     int all[kState];
     if (!to_counts<kState>(y, all)) return false;
-    yi[0] = all[0]; yi[1] = all[1]; yi[2] = all[0] + all[4];
+    yi[0] = all[0]; yi[1] = all[1]; yi[2] = all[0] + all[4]; yi[3] = all[0] + all[3];
     // the tables are built for N = n_tot and cover counts < n_tab
     const double n_tot = __ldg(sd.derived + D_NTOT);
     return y[0] + y[1] + y[2] == n_tot && n_tot < (double)sd.n_tab;
   }
-  // y still holds the state lean_load saw
   __device__ __forceinline__ static void lean_store(const SetData &sd, const int *yi, double *y) {
     const double n_tot = __ldg(sd.derived + D_NTOT);
-    const double s_now = (double)yi[0];
-    y[3] = y[3] + (y[0] - s_now);             // exact: integers below 2^31
-    y[4] = (double)(yi[2] - yi[0]);
-    y[0] = s_now;
+    y[0] = (double)yi[0];
     y[1] = (double)yi[1];
-    y[2] = n_tot - (double)(yi[0] + yi[1]);
+    y[2] = n_tot - (double)(yi[0] + yi[1]);   // exact: integers below 2^31
+    y[3] = (double)(yi[3] - yi[0]);
+    y[4] = (double)(yi[2] - yi[0]);
   }
   // One model step; `reset`: it starts a new incidence interval (time % freq == 0).
   // false: nothing changed, the general code must run this step.

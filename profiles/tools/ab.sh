@@ -1,7 +1,7 @@
 #!/bin/bash
 # usage: profiles/tools/ab.sh v1 v2 ... ; short bench per variant library (build/var/lib_<v>.so): per-kernel us, ms/step
 for v in "$@"; do
-  MCSTATE_B200_LIB=$PWD/build/var/lib_$v.so python bench.py --steps 5 --warmup 3 2>/dev/null > /tmp/b_$v.json
+  MCB_BENCH_CONFIGS=0 MCSTATE_B200_LIB=$PWD/build/var/lib_$v.so python bench.py --steps 5 --warmup 3 2>/dev/null > /tmp/b_$v.json
   python - <<P
 import json
 d=json.load(open("/tmp/b_$v.json"))

@@ -482,6 +482,51 @@ def test_multi_parameter_filter(dust, orc, sir_data, n, n_pars):
     assert np.array_equal(m.state(), st)
 
 
+@pytest.mark.parametrize("n,n_pars", [(2049, 37), (4097, 5), (300, 64), (70001, 3)])
+def test_scheduling_stress_many_sets_odd_tiles_repeated(dust, orc, sir_data, n, n_pars):
+    """In place of compute-sanitizer's racecheck (closed on this pool):
+    the cross-block protocols of the per-interval kernels -- K3's per-set counter and
+    early-exit rule, the ancestor slots K2 empties and K3 fills from other blocks' tiles,
+    the warp-level atomic maximum of K1 -- are run with many small parameter sets and tile
+    counts that do not divide the set (a last tile of 1 particle, sets that straddle
+    warps), several times over, while a second handle keeps the GPU busy on another stream
+    so that blocks are scheduled differently each time.  Every repetition must give the
+    oracle's bits."""
+    from mcstate_b200 import dust as d
+    import torch
+
+    m0, o, t, x = _filter_pair(dust, orc, n, sir_data, n_rows=25, n_pars=n_pars, seed=9)
+    del m0
+    o.set_data(t, x, shared=True)
+    rng0 = orc.rng_streams(9, n * n_pars + 1).tobytes()
+    want = o.filter()["log_likelihood"]
+    want_state = o.state().reshape(5, n_pars, n).transpose(0, 2, 1)
+    want_rng = o.rng_state()
+    g = dust.dust_example("sir")
+    noise = g.new({}, 0, 1 << 18, seed=3)                     # the other stream's work
+    noise.set_persistent(False)
+    _set_data(noise, t, x)
+    plist = [{"beta": 0.2 + 0.02 * p} for p in range(n_pars)]
+    for rep in range(6):
+        m = g.new(plist, 0, n, seed=9, pars_multi=True)
+        m.set_data(d.dust_data({"time_end": t, "incidence": x}), True)
+        if rep % 2:
+            noise.update_state(pars={}, time=0)
+            noise.filter_enqueue()
+        got = m.filter()["log_likelihood"]
+        if rep % 2:
+            noise.filter_collect()
+        assert np.array_equal(got, want), rep
+        assert np.array_equal(m.state(), want_state), rep
+        assert np.array_equal(_rng_words(m), want_rng), rep
+        # the same handle again from the start (the second use of a row range replays a graph)
+        for _ in range(2):
+            m.update_state(pars=plist, time=0)
+            m.set_rng_state(rng0)
+            assert np.array_equal(m.filter()["log_likelihood"], want), rep
+    torch.cuda.synchronize()
+
+
 def test_nested_equals_independent_filters_on_split_streams(dust, orc, sir_data):
     # tests/testthat/test-particle-filter.R:1285-1353: streams 1..n -> population 1,
     # n+1..2n -> population 2; the filter stream is shared and drawn in set order
