@@ -7,10 +7,11 @@ helper (``particle_filter_data``) and the filter facade (``particle_filter``).  
 ``dust(path)`` function -- user-supplied models -- is reached as ``dust.dust``.)
 """
 from . import _lib
+from ._rng import set_seed
 from .dust import (dust_data, dust_example, dust_generator, dust_model,
                    dust_openmp_threads, dust_repair_environment, dust_rng,
                    dust_rng_distributed_state)
 
 __all__ = ["_lib", "dust_data", "dust_example", "dust_generator", "dust_model",
            "dust_openmp_threads", "dust_repair_environment", "dust_rng",
-           "dust_rng_distributed_state"]
+           "dust_rng_distributed_state", "set_seed"]

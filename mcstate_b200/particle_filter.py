@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import numpy as np
 
+from ._rng import host_rng
 from .particle_filter_data import particle_filter_data, particle_filter_data_split
 
 
@@ -861,7 +862,7 @@ def particle_filter_initial(state, rng=None):
     if state.ndim != 2:
         raise TypeError("'state' must be a matrix")
     state = state.copy()
-    gen = np.random.default_rng() if rng is None else rng
+    gen = host_rng() if rng is None else rng
 
     def initial(info, n_particles, pars):
         return state[:, gen.integers(0, state.shape[1], int(n_particles))]

@@ -25,6 +25,7 @@ import os
 
 import numpy as np
 
+from ._rng import host_rng
 from .dust import dust_rng, dust_rng_distributed_state
 from .particle_filter import particle_filter_from_inputs
 
@@ -539,7 +540,7 @@ def pmcmc_sample(object, n_sample, burnin=None, rng=None):
     """``pmcmc_sample(object, n_sample, burnin)`` (R/pmcmc_tools.R:53-61): ``n_sample``
     samples drawn with replacement from what is left after ``burnin``."""
     object = pmcmc_thin(object, burnin)
-    gen = np.random.default_rng() if rng is None else rng
+    gen = host_rng() if rng is None else rng
     return pmcmc_filter(object, gen.integers(0, np.asarray(object["pars"]).shape[0], int(n_sample)))
 
 
@@ -641,7 +642,7 @@ def _chain_from_inputs(inputs, seed, pars, initial_k, control, device=None, n_th
 def _run_one(k, pars, initial, filter, control, seeds, device):
     """Chain k (0-based) on ``device``."""
     if seeds is None:
-        return pmcmc_run_chain(pars, initial[k], filter, control, np.random.default_rng())
+        return pmcmc_run_chain(pars, initial[k], filter, control, host_rng())
     return _chain_from_inputs(filter.inputs(), seeds[k], pars, initial[k], control, device)
 
 

@@ -123,6 +123,16 @@ class nested_filter_sharded:
     ``run(pars)`` takes the FULL list of per-population parameters on every rank (as the
     reference's nested filter does, R/particle_filter.R:907-913) and returns the full
     vector of log-likelihoods on every rank.
+
+    Bit-identical to the unsharded filter for every run that ends normally.  When a
+    population becomes impossible (all weights -Inf) the RESULT is still the unsharded
+    one -- the whole vector -Inf, R/particle_filter_state.R:463-474 -- but only the rank
+    that holds the population stops at that row: the other ranks' particle streams run on
+    to the end, so the model objects are then in a different state from the unsharded
+    filter's (which stopped everywhere).  ``run`` starts every evaluation from
+    ``update_state(pars, time)`` and the filter's seed handling, like the reference's
+    ``particle_filter$run``; a caller that needs the streams to continue identically after
+    an impossible evaluation must recreate the filter.
     """
 
     def __init__(self, data, model, n_particles, seed=1, index=None, gpu_config=None,

@@ -23,6 +23,7 @@ import math
 
 import numpy as np
 
+from ._rng import host_rng
 from .dust import dust_rng_distributed_state
 from .particle_filter import particle_resample, scale_log_weights
 from .particle_filter_data import particle_filter_data_split
@@ -336,7 +337,7 @@ def smc2(pars, filter, control, group=None):
 
 def smc2_predict(result, n=None, rng=None):
     """``predict.smc2_result`` (R/smc2.R:236-240)."""
-    rng = np.random.default_rng() if rng is None else rng
+    rng = host_rng() if rng is None else rng
     w = result["probabilities"][:, 3]
     i = rng.choice(w.size, size=w.size if n is None else n, replace=True, p=w)
     return result["pars"][i]

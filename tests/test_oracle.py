@@ -220,6 +220,37 @@ def test_scale_log_weights_flavours_agree(orc):
         assert abs(a_d - a_e) < 1e-10 * abs(a_d)  # north_star tolerance (fp64, 1e-10 relative)
 
 
+@pytest.mark.parametrize("n", [1 << 20, 1 << 24])
+def test_scale_log_weights_flavours_agree_at_headline_sizes(orc, n):
+    """The engine's weight sums (fixed point, 52 fractional bits, 128-bit accumulators:
+    csrc/kernels.cuh) against dust's left-to-right fp64 sum at the sizes the bench runs
+    (2^20) and beyond (2^24), on the cases where a fixed-point sum could lose something: a
+    near-one-hot set with a dense band of weights in [2^-46, 2^-40] (each keeps 6+ bits)
+    and one in [2^-60, 2^-50] (most round to zero -- together they are 2^-30 of the total).
+    The log-mean-exp agrees within the north_star's 1e-10 relative everywhere; the chosen
+    ancestors differ in at most one slot in a million and never by more than a few
+    particles (PARITY_NOTES.md #14 quotes the measured figures)."""
+    rng = np.random.default_rng(0)
+    cases = {}
+    lw = rng.normal(-300, 40, n); lw[rng.uniform(size=n) < 0.05] = -np.inf; lw[0] = -250.0
+    cases["normal"] = lw
+    lw = np.log(2.0) * rng.uniform(-46, -40, n); lw[n // 2] = 0.0
+    cases["band_46_40"] = lw
+    lw = np.log(2.0) * rng.uniform(-60, -50, n); lw[n // 2] = 0.0
+    cases["band_60_50"] = lw
+    cases["uniform"] = np.zeros(n)
+    cases["mild"] = rng.normal(0, 3, n)
+    for name, lw in cases.items():
+        w_d, a_d = orc.scale_log_weights(lw, orc.DUST_FP64)
+        w_e, a_e = orc.scale_log_weights(lw, orc.EXACT)
+        assert np.array_equal(w_d, w_e), name
+        assert abs(a_d - a_e) <= 1e-10 * max(abs(a_d), 1.0), (name, a_d, a_e)
+        k_e = orc.resample_weight(w_e, 0.37, orc.EXACT)
+        k_d = orc.resample_weight(w_d, 0.37, orc.DUST_FP64)
+        assert np.mean(k_e != k_d) < 2e-6, name
+        assert np.abs(k_e - k_d).max() <= 16, name
+
+
 # ---------------------------------------------------------------- resampling
 def test_particle_resample_r_matches_numpy_restatement(orc):
     rng = np.random.default_rng(1)

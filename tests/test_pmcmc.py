@@ -1040,3 +1040,21 @@ def test_pmcmc_result_layout(sir_data):
     assert pred["time"] == 400 and pred["model_time"] == 100 and not pred["is_continuous"]
     assert pred["transform"]([0.2, 0.1]) == {"beta": 0.2, "gamma": 0.1}
     assert pred["filter"]["n_particles"] == 100 and len(pred["filter"]["seed"]) == 32
+
+
+def test_default_run_is_reproducible_with_set_seed(sir_data):
+    """The reference's default pmcmc draws proposals from R's global RNG, so set.seed()
+    makes a run reproducible (R/pmcmc.R:61-90); here mcstate_b200.set_seed() does."""
+    import mcstate_b200
+
+    def once():
+        mcstate_b200.set_seed(42)
+        f = example_filter("oracle", sir_data, n_particles=32, seed=1)
+        return pmcmc(example_pars(), f, control=pmcmc_control(15, save_state=False))["pars"]
+
+    a, b = once(), once()
+    assert np.array_equal(a, b)
+    mcstate_b200.set_seed(43)
+    f = example_filter("oracle", sir_data, n_particles=32, seed=1)
+    c = pmcmc(example_pars(), f, control=pmcmc_control(15, save_state=False))["pars"]
+    assert not np.array_equal(a, c)
