@@ -44,6 +44,9 @@ typedef struct mcb_model mcb_model;
 
 /* ---- library ---------------------------------------------------------- */
 int mcb_version(void);
+/* The message of the last failed call ON THIS THREAD (thread-local, so it takes no handle):
+ * R calls the shim from its single interpreter thread, and a threaded host reads the
+ * message on the thread whose call failed. */
 const char *mcb_last_error(void);
 /* replaces model$public_methods$has_gpu_support / gpu_info (R/particle_filter.R:212,241) */
 int mcb_device_count(int *n_devices);

@@ -619,14 +619,28 @@ __global__ void __launch_bounds__(kTileThreads, 4) k_weights_scan(View v, int ro
 // a cost that does not depend on how the weights are spread.
 //
 // The count is exact.  x = (C - uu0)/du is evaluated in double with an error below
-// n 2^-50 slots (C, the tile offset, their difference and the product each round
-// once: 2^-53 relative to the total apiece); a threshold ceil(fl(uu0 + fl(i du)))
+// n 2^-49 slots (C, the tile offset, their difference and the product each round
+// once, 2^-53 relative to the total apiece, and n / total stands in for 1 / du to
+// within two ulps); a threshold ceil(fl(uu0 + fl(i du)))
 // lies within n 2^-52 slots of the line uu0 + i du.  So when x is further than
 // kCountEps = 2^-12 from an integer, floor(x) + 1 IS the count (n < 2^31); otherwise
 // (one particle in 2000) the thresholds next to the estimate are evaluated as the
 // definition has them and compared as integers.
 //   heads [n_total]: emptied by K2; global index of the particle at the slots above
 // ---------------------------------------------------------------------------
+// The sum over a warp of values below 2^110 (a thread's share of the tile sums: each at
+// most 2^63, fewer than 2^20 tiles), in 22-bit limbs: a 32-lane integer reduction (REDUX)
+// of limbs cannot overflow 32 bits, and five of them replace twenty 64-bit shuffles.
+__device__ __forceinline__ u128 warp_sum_u128(u128 x) {
+  u128 sum = 0;
+#pragma unroll
+  for (int l = 0; l < 5; ++l) {
+    const unsigned limb = (unsigned)(x >> (22 * l)) & 0x3fffffu;
+    sum += (u128)__reduce_add_sync(0xffffffffu, limb) << (22 * l);
+  }
+  return sum;
+}
+
 constexpr double kCountEps = 0x1p-12;
 constexpr uint32_t kHeavySlots = 2048;   // a particle with this many slots: the block writes them
 constexpr int kHeavyCap = 32;
@@ -645,9 +659,16 @@ __device__ __noinline__ uint32_t count_exact(const CountCtx &c, unsigned long lo
   return k;
 }
 
+// RN(q) for a 64-bit q from its two halves: hi 2^32 is exact, the fma rounds hi 2^32 + lo
+// once -- the correctly rounded conversion in three native instructions (the 64-bit
+// conversion is a routine)
+__device__ __forceinline__ double u64_to_double(unsigned long long q) {
+  return fma((double)(uint32_t)(q >> 32), 4294967296.0, (double)(uint32_t)q);
+}
+
 // #{slots of the set whose threshold is at or below offset + q}
 __device__ __forceinline__ uint32_t slots_reached(const CountCtx &c, unsigned long long q) {
-  const double x = (__ull2double_rn(q) + c.d0) * c.inv_du;
+  const double x = (u64_to_double(q) + c.d0) * c.inv_du;
   const double xc = fmin(fmax(x, -1.0), (double)c.n);
   const double fl = floor(xc);
   const uint32_t k = min((uint32_t)(__double2int_rd(xc) + 1), c.n);
@@ -704,7 +725,8 @@ __global__ void __launch_bounds__(kTileThreads, 4) k_ancestors(View v, int row) 
     if (leader) apply_stop_rule(v, row, false);
     return;
   }
-  // ---- the set's tile sums: what lies before this tile, and the total
+  // ---- the set's tile sums: what lies before this tile, and the total.  Every thread
+  // adds up its share, the warps' sums meet in shared memory
   u128 before = 0, total = 0;
   {
     total = sum0;
@@ -714,13 +736,8 @@ __global__ void __launch_bounds__(kTileThreads, 4) k_ancestors(View v, int row) 
       total += x;
       if (t < tile) before += x;
     }
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) {
-      total += ((u128)shfl_xor_u64((unsigned long long)(total >> 64), d) << 64) |
-               shfl_xor_u64((unsigned long long)total, d);
-      before += ((u128)shfl_xor_u64((unsigned long long)(before >> 64), d) << 64) |
-                shfl_xor_u64((unsigned long long)before, d);
-    }
+    total = warp_sum_u128(total);
+    before = warp_sum_u128(before);
     if (lane == 0) { s_red[0][warp] = total; s_red[1][warp] = before; }
     __syncthreads();
     total = 0; before = 0;
@@ -730,8 +747,11 @@ __global__ void __launch_bounds__(kTileThreads, 4) k_ancestors(View v, int row) 
   const double tot_d = u128_to_double(total);
   const double n_d = (double)v.n_particles;
   CountCtx c;
+  // three independent divisions: the two the thresholds are defined by, and n / total for
+  // the estimate (1 / du to within an ulp or two, which its error bound allows for)
   c.si.uu0 = tot_d * u / n_d;
   c.si.du = tot_d / n_d;
+  c.inv_du = n_d / tot_d;
   c.offset = before;
   c.n = n_p;
   bool dead = false;
@@ -750,7 +770,6 @@ __global__ void __launch_bounds__(kTileThreads, 4) k_ancestors(View v, int row) 
     return;
   }
   c.d0 = u128_to_double(before) - c.si.uu0;
-  c.inv_du = 1.0 / c.si.du;
 
   // ---- counts of the thread's 8 particles
   uint32_t cnt[kTileItems];
@@ -768,28 +787,44 @@ __global__ void __launch_bounds__(kTileThreads, 4) k_ancestors(View v, int row) 
   __syncthreads();
   if (lane == 0) prev = warp ? s_cnt[warp - 1] : (tile ? slots_reached(c, 0ULL) : 0u);
 
-  // ---- a particle with offspring: its index at its first slot and at the multiples of 32
-  // its slots cover (global slot numbers)
+  // ---- a particle with offspring: its index at its first slot (global slot numbers) ...
+  const uint32_t g0 = (uint32_t)gbase + in_set;   // the thread's first particle
+  const uint32_t lo = (uint32_t)gbase + prev, hi = (uint32_t)gbase + cnt[kTileItems - 1];
+  uint32_t heavy = 0;   // bit j: particle j's slots are written by the whole block
+  {
+    uint32_t a = prev;
 #pragma unroll
-  for (int j = 0; j < kTileItems; ++j) {
-    const uint32_t a = prev, b = cnt[j];
-    prev = b;
-    if (b > a) {
-      const uint32_t A = (uint32_t)gbase + a, B = (uint32_t)gbase + b;
-      const int g = (int)((uint32_t)gbase + in_set + j);
-      heads[A] = g;
-      uint32_t m = (A | 31u) + 1u;
-      bool mine = true;
+    for (int j = 0; j < kTileItems; ++j) {
+      const uint32_t b = cnt[j];
+      if (b > a) heads[(uint32_t)gbase + a] = (int)(g0 + j);
       if (b - a >= kHeavySlots) {
         const int e = atomicAdd(&s_heavy_n, 1);
         if (e < kHeavyCap) {
-          s_heavy[e][0] = m; s_heavy[e][1] = B; s_heavy[e][2] = (uint32_t)g;
-          mine = false;
+          s_heavy[e][0] = (((uint32_t)gbase + a) | 31u) + 1u;
+          s_heavy[e][1] = (uint32_t)gbase + b;
+          s_heavy[e][2] = g0 + j;
+          heavy |= 1u << j;
         }
       }
-      if (mine)
-        for (; m < B; m += 32) heads[m] = g;
+      a = b;
     }
+  }
+  // ... and at every multiple of 32 its slots cover.  The thread's 8 particles own the
+  // slots [lo, hi) -- about 8 of them, so mostly one multiple of 32 or none: the
+  // multiples are walked once per thread, each given to the particle whose range holds it
+  for (uint32_t m = (lo | 31u) + 1u; m < hi; m += 32) {
+    const uint32_t rel = m - (uint32_t)gbase;
+    int j = 0;
+#pragma unroll
+    for (int k = 0; k < kTileItems - 1; ++k) j += cnt[k] <= rel ? 1 : 0;
+    if ((heavy >> j) & 1u) {   // the block writes that particle's: on to the end of its range
+      uint32_t end = cnt[0];
+#pragma unroll
+      for (int k = 1; k < kTileItems; ++k) end = k == j ? cnt[k] : end;
+      m = ((((uint32_t)gbase + end - 1u) | 31u) + 1u) - 32u;
+      continue;
+    }
+    heads[m] = (int)(g0 + j);
   }
   __syncthreads();
   const int n_heavy = min(s_heavy_n, kHeavyCap);

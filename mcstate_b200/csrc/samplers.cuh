@@ -193,6 +193,9 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
 // 2^(j/32), j = 0..31, filled by the host; a block stages it in shared memory
 constexpr int kExp2Tab = 32;
 __device__ double g_exp2_tab[kExp2Tab];
+#ifndef MCB_EXP2_GLOBAL
+#define MCB_EXP2_GLOBAL 1
+#endif
 // 1/k as constant-bank operands (entry 0 unused); approximate values are all the fast
 // walk needs
 __constant__ double c_recip[kInvSmall];
@@ -218,7 +221,15 @@ __device__ __forceinline__ double fast_exp_neg(double x, uint32_t s_exp2_addr) {
   p = fma(p, r, c_fexp[6]);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
+#if MCB_EXP2_GLOBAL
+  // the 256-byte table straight from global memory (two lines that never leave L1):
+  // one address computation instead of a per-warp shared-memory address kept or rebuilt
+  // at every step
+  (void)s_exp2_addr;
+  const double v = __ldg(g_exp2_tab + (ki & (kExp2Tab - 1))) * p;
+#else
   const double v = lds_f64(s_exp2_addr + 8u * (uint32_t)(ki & (kExp2Tab - 1))) * p;
+#endif
   return __hiloint2double(__double2hiint(v) + ((ki >> 5) << 20), __double2loint(v));
 }
 
@@ -314,11 +325,13 @@ __device__ __forceinline__ int draw_binomial_table(Xoshiro &rng, const double *_
                                                    double4 F) {   // F = the row's first four entries
   if (F.x < 0.0) return -1;
   double u = xo_real<SCR>(rng);
-  int k = 0;
-  for (;;) {
+  int k = 0, c3;
+  // one way out of the loop (the lanes of a warp leave it at different rounds: with a
+  // single exit they meet again once, and what follows runs once)
+  bool more;
+  do {
     // four steps of the chain: k counts the leading steps that go on (u >= f_k),
     // each comparison and-ed with the one before inside the DSETP itself
-    int c3;
     asm("{\n\t.reg .pred p0, p1, p2, p3;\n\t"
         "setp.ge.f64 p0, %1, %3;\n\t"
         "sub.rn.f64 %1, %1, %3;\n\t"
@@ -335,12 +348,12 @@ __device__ __forceinline__ int draw_binomial_table(Xoshiro &rng, const double *_
         "selp.s32 %2, 1, 0, p3;\n\t}"
         : "+r"(k), "+d"(u), "=r"(c3)
         : "d"(F.x), "d"(F.y), "d"(F.z), "d"(F.w));
-    if (!c3) break;
-    if (k == kWalkK) {
-      xo_rewind(rng);
-      return -1;
-    }
-    F = ldg_f64x4(row + k);
+    more = c3 != 0 && k < kWalkK;
+    if (more) F = ldg_f64x4(row + k);
+  } while (more);
+  if (c3) {   // walked past the row
+    xo_rewind(rng);
+    return -1;
   }
   return k;
 }
