@@ -276,7 +276,11 @@ def run_engine(args):
     pars = {"beta": 0.2, "gamma": 0.1}
     pf.run(pars)                       # creates the model object and uploads the data once
     model = pf._last_model[0]
-    stream = torch.cuda.current_stream()
+    # everything of the timed region -- the L2 flush, the engine's kernels, the events --
+    # is ordered on ONE stream torch knows about (not torch's default stream: its handle
+    # is 0, which the engine reads as "the handle's own stream")
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     model.set_stream(stream.cuda_stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 

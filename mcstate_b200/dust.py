@@ -532,7 +532,11 @@ class dust_model:
         return torch.as_tensor(_View(), device=torch.device("cuda", self._device))
 
     def set_stream(self, cuda_stream):
-        self._ck(self._L.mcb_set_stream(self._h, C.c_void_p(cuda_stream)))
+        """Launch on this ``cudaStream_t`` (an integer handle, e.g. ``torch.cuda.Stream().
+        cuda_stream``); ``None`` or 0 goes back to the stream the handle owns.  0 is also the
+        handle of CUDA's default stream -- which cannot be used here (no graph capture on
+        it): give the handle a stream of its own and order other work on that."""
+        self._ck(self._L.mcb_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
 
     def synchronize(self):
         self._ck(self._L.mcb_synchronize(self._h))

@@ -234,10 +234,17 @@ class smc2_engine:
         import torch
 
         if not self._on_torch_stream:
-            m.set_stream(torch.cuda.current_stream().cuda_stream)
+            # a stream of this engine's own that torch knows about: the handle launches on
+            # it, the copy into the gather buffer, the collective's hand-over and the copy
+            # out are ordered on it.  (Not torch's default stream: its handle is 0, which
+            # set_stream reads as "the handle's own stream", and graphs cannot be captured
+            # on it.)
+            self._stream = torch.cuda.Stream()
+            m.set_stream(self._stream.cuda_stream)
             self._on_torch_stream = True
-        m.filter_enqueue(time_end)
-        return g.gather_device(m.log_likelihood_device(), wait=m.filter_collect)
+        with torch.cuda.stream(self._stream):
+            m.filter_enqueue(time_end)
+            return g.gather_device(m.log_likelihood_device(), wait=m.filter_collect)
 
     # ---- R/smc2.R:89-108 ------------------------------------------------------------
     def step(self):

@@ -244,11 +244,16 @@ _WORKER = textwrap.dedent("""
     from test_pmcmc import example_filter, example_pars
     from mcstate_b200.pmcmc import pmcmc, pmcmc_control
     kind, n_chains = sys.argv[1], int(sys.argv[2])
-    backend = os.environ.get("MCB_TEST_BACKEND", {backend!r}) if kind == "gpu" else {backend!r}
+    backend = {backend!r}
+    if kind == "gpu":   # one GPU per rank and NCCL when the box has the GPUs, else as asked
+        import torch
+        backend = os.environ.get("MCB_TEST_BACKEND") or (
+            "nccl" if torch.cuda.device_count() >= int(os.environ["WORLD_SIZE"]) else {backend!r})
     if backend == "nccl":
         import torch
         torch.cuda.set_device(int(os.environ["LOCAL_RANK"]) % torch.cuda.device_count())
-    dist.init_process_group(backend)
+    import datetime
+    dist.init_process_group(backend, timeout=datetime.timedelta(seconds=120))
     rank, world = dist.get_rank(), dist.get_world_size()
     d = np.loadtxt(os.path.join({root!r}, "tests", "golden", "sir_incidence.csv"), delimiter=",",
                    skiprows=1)

@@ -70,13 +70,18 @@ _WORKER = textwrap.dedent("""
     from test_sharding import nested_data, pars_for, make_generator
     from mcstate_b200.sharding import nested_filter_sharded
     kind, n_pop, n_particles = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
-    backend = os.environ.get("MCB_TEST_BACKEND", "gloo") if kind == "gpu" else "gloo"
+    backend = "gloo"
+    if kind == "gpu":   # one GPU per rank and NCCL when the box has the GPUs, else gloo
+        import torch
+        backend = os.environ.get("MCB_TEST_BACKEND") or (
+            "nccl" if torch.cuda.device_count() >= int(os.environ["WORLD_SIZE"]) else "gloo")
     dev = None
     if kind == "gpu":
         import torch
         dev = int(os.environ["LOCAL_RANK"]) % torch.cuda.device_count()
         torch.cuda.set_device(dev)
-    dist.init_process_group(backend)
+    import datetime
+    dist.init_process_group(backend, timeout=datetime.timedelta(seconds=120))
     f = nested_filter_sharded(nested_data(n_pop), make_generator(kind), n_particles, seed=7,
                               gpu_config=dev)
     p = pars_for(n_pop)

@@ -145,11 +145,16 @@ _WORKER = textwrap.dedent("""
     from test_smc2 import example
     from mcstate_b200.smc2 import smc2, smc2_control
     kind = sys.argv[1]
-    backend = os.environ.get("MCB_TEST_BACKEND", "gloo") if kind == "gpu" else "gloo"
+    backend = "gloo"
+    if kind == "gpu":   # one GPU per rank and NCCL when the box has the GPUs, else gloo
+        import torch
+        backend = os.environ.get("MCB_TEST_BACKEND") or (
+            "nccl" if torch.cuda.device_count() >= int(os.environ["WORLD_SIZE"]) else "gloo")
     if backend == "nccl":
         import torch
         torch.cuda.set_device(int(os.environ["LOCAL_RANK"]) % torch.cuda.device_count())
-    dist.init_process_group(backend)
+    import datetime
+    dist.init_process_group(backend, timeout=datetime.timedelta(seconds=120))
     f, p = example(kind, n_days=30)
     res = smc2(p, f, smc2_control(7, seed=5))
     if dist.get_rank() == 0:
@@ -173,7 +178,7 @@ def test_sharded_smc2_equals_single_rank(tmp_path, kind):
            "--master-addr", "127.0.0.1", "--master-port", str(free_port()),
            str(script), kind, str(out)]
     r = subprocess.run(cmd, env=dict(os.environ, MASTER_ADDR="127.0.0.1"), capture_output=True,
-                       text=True, timeout=900)
+                       text=True, timeout=400)
     assert r.returncode == 0, r.stderr[-3000:]
     with open(out, "rb") as fh:
         got = pickle.load(fh)
