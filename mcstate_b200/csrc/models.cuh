@@ -115,7 +115,8 @@ struct SirModel {
   static constexpr int kPar = 7;  // beta gamma I0 exp_noise S0 R0 freq
   static constexpr int kData = 1; // incidence
   static constexpr int kConst = 1;  // recovery
-  enum { D_BETA, D_DT, D_EXP_NOISE, D_FREQ, D_NTOT, D_P_IR, D_Q_IR, D_QQ_IR, D_R_IR, D_FLIP_IR };
+  enum { D_BETA, D_DT, D_EXP_NOISE, D_FREQ, D_NTOT, D_P_IR, D_Q_IR, D_QQ_IR, D_R_IR, D_FLIP_IR,
+         D_INV_EXP_NOISE };
   enum { C_IR };
 
   __device__ __forceinline__ static void derive(const double *__restrict__ p, double *d) {
@@ -133,6 +134,7 @@ struct SirModel {
     d[D_QQ_IR] = qq;
     d[D_R_IR] = q / qq;
     d[D_FLIP_IR] = p_ir > 0.5 ? 1.0 : 0.0;
+    d[D_INV_EXP_NOISE] = reciprocal_for(p[3]);
   }
   // row n of the walk table of constant draw c; row I of the infection table
   __device__ __forceinline__ static void walk_row(int, int n, const double *d, double *row) {
@@ -185,7 +187,8 @@ struct SirModel {
                                                    double lgamma_obs1, Xoshiro &rng,
                                                    const Ctx &c, bool det) {
     const double rate = __ldg(c.derived + D_EXP_NOISE);
-    const double noise = det ? 1.0 / rate : draw_exponential<SCR>(rng, rate);
+    const double noise = det ? 1.0 / rate
+                             : draw_exponential_fixed<SCR>(rng, rate, __ldg(c.derived + D_INV_EXP_NOISE));
     return density_poisson_log(observed, lgamma_obs1, y[4] + noise);
   }
 

@@ -18,6 +18,34 @@ __device__ __forceinline__ double draw_exponential(Xoshiro &r, double rate) {
   return -det_log(xo_real<SCR>(r)) / rate;
 }
 
+// a / b for a divisor the parameter set fixes, correctly rounded WITHOUT the division
+// sequence -- the bits of `a / b`: y = RN(1/b) (prepared once per parameter set by
+// reciprocal_for), q0 = RN(a y), then two residual corrections q <- RN(q + RN(a - b q) y).
+// The residuals are exact up to a rounding that cannot matter, the first correction makes
+// q faithful, and Markstein's theorem gives RN(a/b) from the second -- for every b whose
+// significand is not all ones, with a, b and the quotient away from the ends of the
+// exponent range.  reciprocal_for returns 0 where that is not so, and the caller divides.
+__device__ __forceinline__ double reciprocal_for(double b) {
+  const uint64_t bits = double_to_bits(b);
+  const int e = (int)((bits >> 52) & 0x7ff);
+  const bool ok = !(bits >> 63) && e > 1023 - 200 && e < 1023 + 200 &&
+                  (bits & 0xfffffffffffffULL) != 0xfffffffffffffULL;
+  return ok ? 1.0 / b : 0.0;
+}
+__device__ __forceinline__ double div_by_fixed(double a, double b, double y) {
+  if (y == 0.0 || !(fabs(a) > 1e-200 && fabs(a) < 1e200)) return a / b;
+  double q = a * y;
+  double r = fma(-q, b, a);
+  q = fma(r, y, q);
+  r = fma(-q, b, a);
+  return fma(r, y, q);
+}
+// the exponential draw with the rate's reciprocal prepared: same bits as draw_exponential
+template <int SCR>
+__device__ __forceinline__ double draw_exponential_fixed(Xoshiro &r, double rate, double inv) {
+  return div_by_fixed(-det_log(xo_real<SCR>(r)), rate, inv);
+}
+
 // Box-Muller, first variate only; a uniform at or below machine epsilon is drawn
 // again (both of the pair) so log never sees it.  sqrt is IEEE (correctly rounded).
 template <int SCR>
