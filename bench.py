@@ -132,8 +132,12 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, active=True):
+        # `active = False` (every rank but 0): a no-op.  One sampler per box is enough, and
+        # nvidia-smi queries from eight processes at once contend for the driver with the
+        # very launches and synchronisations being timed.
         self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+        self.active = active
 
     def _run(self):
         while not self._stop.is_set():
@@ -145,16 +149,18 @@ class ClockSampler:
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.05)
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        if self.active:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
         return self
 
     def __exit__(self, *a):
         self._stop.set()
-        self._t.join(timeout=6)
+        if self._t is not None:
+            self._t.join(timeout=6)
 
     def summary(self):
         if not self.rows:
@@ -309,7 +315,7 @@ def run_engine(args):
     # clocks / throttle reasons are sampled from here to the end of the e2e loop: three
     # back-to-back passes over the same workload (the headline pass alone lasts ~0.1 s,
     # one nvidia-smi query)
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(local, active=rank == 0)
     clocks.__enter__()
     ev0.record(stream)
     for _ in range(args.steps):
@@ -373,7 +379,7 @@ def run_engine(args):
         import bench_configs
 
         del pf, model
-        configs = bench_configs.run_configs(local, ClockSampler)
+        configs = bench_configs.run_configs(local, lambda idx: ClockSampler(idx, active=rank == 0))
 
     tmax = torch.tensor([ms_total, e2e_s * 1e3], device="cuda", dtype=torch.float64)
     if world > 1:

@@ -75,15 +75,20 @@ struct ModelTables {
 }  // namespace
 #include MCB_USER_MODEL
 namespace {
-static_assert(!mcb::UserModel::kHasLean && mcb::UserModel::kConst == 0,
-              "a user model implements the general form (initial / update / compare)");
+static_assert(mcb::UserModel::kHasLean || mcb::UserModel::kConst == 0,
+              "memo tables (kConst > 0) are read by a lean path only");
+static_assert(mcb::UserModel::kConst <= mcb::kMaxConst, "at most kMaxConst fixed-probability draws");
 static_assert(mcb::UserModel::kState >= 1 && mcb::UserModel::kState <= mcb::kMaxState &&
               mcb::UserModel::kPar >= 1 && mcb::UserModel::kPar <= mcb::kMaxPar &&
               mcb::UserModel::kData >= 0 && mcb::UserModel::kData <= 1,
               "user model: 1..8 state variables, 1..8 parameters, at most one data field");
 #define MCB_MODELS(X) X(0, mcb::UserModel)
 const ModelDesc kModels[] = {MCB_USER_MODEL_DESC};
+#ifdef MCB_USER_MODEL_TABLES   // a model with a lean path says what its memo tables cover
+const ModelTables kModelTables[] = {MCB_USER_MODEL_TABLES};
+#else
 const ModelTables kModelTables[] = {{{-1, -1, -1}, 0, -1}};   // no memo tables: general form only
+#endif
 #else
 #define MCB_MODELS(X) \
   X(0, mcb::SirModel) X(1, mcb::SirsModel) X(2, mcb::VolatilityModel) X(3, mcb::WalkModel)

@@ -33,7 +33,7 @@ namespace mcb {
 
 constexpr int kMaxState = 8;
 constexpr int kMaxPar = 12;
-constexpr int kMaxDerived = 16;
+constexpr int kMaxDerived = 24;
 constexpr int kMaxConst = 2;     // draws with a parameter-only probability, per model
 
 // where a thread finds its parameter set's prepared data

@@ -1,7 +1,9 @@
 """A user-supplied model (mcstate_b200/examples/seir.cuh, compiled by dust.dust) at config
 C2's size: 2^20 particles x 100 data intervals x 4 steps.  The model has three binomial
-draws per step and no memo tables (general form only), so this is what a model costs
-before anyone tunes it; the stock SIR model is timed beside it through the same calls."""
+draws per step; the example header also carries the optional lean path (memo tables for its two
+fixed-probability draws, certified fast walk for the infection draw), so this is what a user model
+costs once it has one (the general form alone: profiles/user_model_r01_v41.txt, 21.1 ms);
+the stock SIR model is timed beside it through the same calls."""
 import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
