@@ -151,7 +151,7 @@ def run_configs(local, sampler_cls, c3_steps=1000, c4_evals=30):
     n5 = 1 << 14
     f5 = particle_filter(data, gen, n5, None, seed=1, gpu_config=local)
     unif = lambda k, rng: rng.uniform(0.05, 0.5, k)  # noqa: E731
-    dunif = lambda v: 0.0 if 0.05 <= v <= 0.5 else -math.inf  # noqa: E731
+    dunif = lambda v: np.where((v >= 0.05) & (v <= 0.5), 0.0, -math.inf)  # noqa: E731
     pars5 = smc2_parameters([smc2_parameter("beta", unif, dunif, min=0.05, max=0.5),
                              smc2_parameter("gamma", unif, dunif, min=0.05, max=0.5)])
     warm = smc2_engine(pars5, f5, smc2_control(128 * world, seed=3))

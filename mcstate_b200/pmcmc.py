@@ -96,7 +96,38 @@ def rmvnorm_generator(vcv):
         x[include] = rng.standard_normal(res.shape[0]) @ (res * math.sqrt(scale))
         return np.asarray(mean, dtype=float) + x
 
+    def draw_rows(means, rng, scale=1.0):
+        """One draw per row of ``means`` in one go: the normal deviates in the order of
+        ``len(means)`` successive ``draw`` calls (so the generator ends in the same state),
+        the linear map term by term."""
+        means = np.atleast_2d(np.asarray(means, dtype=float))
+        z = rng.standard_normal((means.shape[0], res.shape[0]))
+        r = res * math.sqrt(scale)
+        x = np.zeros(means.shape)
+        acc = np.zeros((means.shape[0], res.shape[0]))
+        for j in range(res.shape[0]):
+            acc += z[:, j:j + 1] * r[j]
+        x[:, include] = acc
+        return means + x
+
+    draw.rows = draw_rows
     return draw
+
+
+def reflect_proposal_rows(x, x_min, x_max):
+    """``reflect_proposal`` for a matrix of proposals, one per row (same formulas)."""
+    x = np.array(x, dtype=float)
+    lo_b = np.broadcast_to(np.asarray(x_min, dtype=float), x.shape)
+    hi_b = np.broadcast_to(np.asarray(x_max, dtype=float), x.shape)
+    out = (x < lo_b) | (x > hi_b)
+    if out.any():
+        fmin, fmax = np.isfinite(lo_b), np.isfinite(hi_b)
+        both, lo, hi = out & fmin & fmax, out & fmin & ~fmax, out & ~fmin & fmax
+        xr = hi_b[both] - lo_b[both]
+        x[both] = np.abs(np.mod(x[both] + xr - lo_b[both], 2 * xr) - xr) + lo_b[both]
+        x[lo] = 2 * lo_b[lo] - x[lo]
+        x[hi] = 2 * hi_b[hi] - x[hi]
+    return x
 
 
 class pmcmc_parameters:

@@ -27,7 +27,7 @@ from ._rng import host_rng
 from .dust import dust_rng_distributed_state
 from .particle_filter import particle_resample, scale_log_weights
 from .particle_filter_data import particle_filter_data_split
-from .pmcmc import reflect_proposal, rmvnorm_generator
+from .pmcmc import reflect_proposal_rows, rmvnorm_generator
 from .sharding import block_range
 
 
@@ -78,15 +78,29 @@ class smc2_parameters:
         return np.stack([np.asarray(p.sample(n, rng), dtype=float) for p in self._p], axis=1)
 
     def prior(self, theta):
+        """Sum of the parameters' log densities per row.  A ``prior`` that takes a whole
+        column at once (numpy in, numpy out) is called once per parameter; a scalar-only
+        one is called per value, as the reference does."""
         theta = np.atleast_2d(theta)
-        return np.array([sum(p.prior(x) for p, x in zip(self._p, row)) for row in theta])
+        total = np.zeros(theta.shape[0])
+        for j, p in enumerate(self._p):
+            col = None
+            try:
+                col = np.asarray(p.prior(theta[:, j]), dtype=float)
+            except Exception:
+                col = None
+            if col is None or col.shape != (theta.shape[0],):
+                col = np.array([p.prior(x) for x in theta[:, j]], dtype=float)
+            total = total + col
+        return total
 
     def propose(self, theta, vcv, rng):
-        # R/smc2_parameters.R: one multivariate-normal step per row, reflected at the bounds
-        draw = rmvnorm_generator(vcv)
-        out = np.stack([draw(row, rng) for row in theta])
+        # R/smc2_parameters.R: one multivariate-normal step per row, reflected at the bounds;
+        # all rows at once (with 1024 parameter particles a Python loop over the rows costs
+        # more than the GPU work of a replenishment)
+        out = rmvnorm_generator(vcv).rows(theta, rng)
         out[:, self._integer] = np.round(out[:, self._integer])
-        return np.stack([reflect_proposal(row, self._min, self._max) for row in out])
+        return reflect_proposal_rows(out, self._min, self._max)
 
     def model(self, theta):
         return [self._transform(dict(zip(self._names, (float(x) for x in row))))
@@ -176,6 +190,7 @@ class smc2_engine:
         self._filter_facade = filter
 
         self.step_current = 0
+        self.phase_seconds = {}
         self.acceptance_rate = np.full(self.n_steps, np.nan)
         self.ess = np.full(self.n_steps, np.nan)
         self.n_filter_rows = 0  # model rows x parameter sets run on this rank
@@ -247,10 +262,23 @@ class smc2_engine:
             return g.gather_device(m.log_likelihood_device(), wait=m.filter_collect)
 
     # ---- R/smc2.R:89-108 ------------------------------------------------------------
+    def _lap(self, key, t0):
+        """Wall time per phase (filter + gather, host arithmetic, the pieces of a
+        replenishment), kept for profiles/tools/c5_phases.py; a perf_counter call each."""
+        import time
+
+        now = time.perf_counter()
+        self.phase_seconds[key] = self.phase_seconds.get(key, 0.0) + (now - t0)
+        return now
+
     def step(self):
+        import time
+
+        t0 = time.perf_counter()
         t = self.step_current + 1
         time_end = int(self._times[t - 1, 1])
         step_ll = self._step_likelihood(time_end)
+        t0 = self._lap("row: filter + gather", t0)
         self.n_filter_rows += self._hi - self._lo
         self.log_likelihood = self.log_likelihood + step_ll
         self.log_posterior = self.log_posterior + step_ll
@@ -260,10 +288,15 @@ class smc2_engine:
             ess = self.weights.sum() ** 2 / np.sum(self.weights ** 2)
         self.step_current = t
         self.ess[t - 1] = ess
+        t0 = self._lap("row: host arithmetic", t0)
         if ess < self._control.degeneracy_threshold * self._control.n_parameter_sets:
             kernel = cov_wt(self.pars, self.weights) * self._control.covariance_scaling
             self.resample()
-            self.update(self.propose(kernel))
+            t0 = self._lap("replenish: kernel + resample", t0)
+            proposed = self.propose(kernel)
+            t0 = self._lap("replenish: propose (batched re-run + gather)", t0)
+            self.update(proposed)
+            self._lap("replenish: update", t0)
 
     def run(self):
         for _ in range(self.step_current, self.n_steps):
