@@ -333,6 +333,11 @@ __device__ __forceinline__ void run_model_steps(const View &v, const SetData &sd
 #ifndef MCB_K1_MINBLOCKS
 #define MCB_K1_MINBLOCKS 12
 #endif
+// the warp's maximum goes to the atomic only if it would raise the maximum as it stands (1),
+// or always, as a fire-and-forget reduction (0)
+#ifndef MCB_MAX_FILTER
+#define MCB_MAX_FILTER 1
+#endif
 // A model without a lean path runs its update as written (doubles, the general samplers)
 // and spills at the 40 registers the lean SIR loop is tuned for (SEIR user model: 700 B of
 // spill stores per thread).  More registers and fewer resident blocks were measured
@@ -442,8 +447,12 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
     const unsigned m_hi = __reduce_max_sync(0xffffffffu, hi);
     const unsigned m_lo = __reduce_max_sync(0xffffffffu, hi == m_hi ? (unsigned)key : 0u);
     key = ((unsigned long long)m_hi << 32) | m_lo;
+#if MCB_MAX_FILTER
     if ((threadIdx.x & 31) == 0 && key && key > __ldcg(slot + set_first))
       atomicMax(slot + set_first, key);
+#else
+    if ((threadIdx.x & 31) == 0 && key) atomicMax(slot + set_first, key);
+#endif
   } else if (weighted) {
     atomicMax(slot + set, key);
   }
