@@ -212,6 +212,57 @@ def test_resample_indices_bit_exact_headline_sizes(dust, orc, kind, n):
     assert np.array_equal(m.state()[0], (want - 1).astype(float))
 
 
+@pytest.mark.parametrize("kind", ["cluster40", "two_in_a_thread", "heavy_then_light", "steps"])
+def test_resample_heavy_particles_and_block_written_ranges(dust, orc, kind):
+    """The ancestors kernel's special paths (csrc/kernels.cuh: k_ancestors): a particle that
+    owns >= 2048 output slots is written by its whole block (a list of at most 32 per tile),
+    the others by their thread, which must skip the block-written ranges:
+      cluster40         40 equal heavy particles side by side in one tile (the list overflows:
+                        eight of them fall back to their threads)
+      two_in_a_thread   two heavy particles among the 8 of one thread, light ones between
+      heavy_then_light  one particle with half the slots, then thousands with one or none
+      steps             weights falling by 2^-3 per particle: ranges of every size"""
+    n = 1 << 18
+    rng = np.random.default_rng(17)
+    w = np.zeros(n)
+    if kind == "cluster40":
+        w[5000:5040] = 1.0
+    elif kind == "two_in_a_thread":
+        w[:] = 1e-7 * rng.uniform(size=n)
+        w[16001] = 1.0; w[16006] = 0.75; w[16003] = 2e-6
+    elif kind == "heavy_then_light":
+        w[:] = rng.uniform(size=n) / n
+        w[777] = 1.0
+    else:
+        w[1000:1040] = 2.0 ** (-3.0 * np.arange(40))
+    g = dust.dust_example("volatility")
+    m = g.new({}, 0, n, seed=3)
+    m.update_state(state=np.arange(n, dtype=float).reshape(1, n))
+    for _ in range(2):
+        u = _first_uniform(_rng_words(m)[-1].copy())
+        got = m.resample(w)
+        want = orc.resample_weight(w, u, orc.EXACT) + 1
+        assert np.array_equal(got, want), kind
+    # a multi-set model: sets that do not start on a multiple of 32, one of them one-hot
+    n, n_pars = 3001, 5
+    gs = dust.dust_example("sir")
+    ms = gs.new([{"beta": 0.2 + 0.01 * p} for p in range(n_pars)], 0, n, seed=4, pars_multi=True)
+    ws = rng.uniform(size=(n, n_pars)) ** 6
+    ws[:, 2] = 0.0; ws[1234, 2] = 1.0
+    ws /= ws.max(axis=0)
+    u_words = _rng_words(ms)[-1].copy()
+    got = ms.resample(ws)
+    st = [int(x) for x in u_words]
+    for p in range(n_pars):     # one uniform per set from the shared filter stream, in set order
+        r = (st[0] + st[3]) & 0xFFFFFFFFFFFFFFFF
+        u = float(r >> 11) * 2.0 ** -53
+        want = orc.resample_weight(np.ascontiguousarray(ws[:, p]), u, orc.EXACT) + 1
+        assert np.array_equal(got[:, p], want), p
+        t = (st[1] << 17) & 0xFFFFFFFFFFFFFFFF
+        st[2] ^= st[0]; st[3] ^= st[1]; st[1] ^= st[2]; st[0] ^= st[3]; st[2] ^= t
+        st[3] = ((st[3] << 45) | (st[3] >> 19)) & 0xFFFFFFFFFFFFFFFF
+
+
 def _first_uniform(words):
     """first uniform of a stream given as four words (xoshiro256+, the default scrambler)"""
     s = [int(x) for x in words]
