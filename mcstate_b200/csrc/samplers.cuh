@@ -201,6 +201,12 @@ __device__ __forceinline__ double2 ldg_f64x2(const double *p) {
 #ifndef MCB_TAB_LD
 #define MCB_TAB_LD 0
 #endif
+#ifndef MCB_WALK_EARLY_U
+#define MCB_WALK_EARLY_U 0
+#endif
+#ifndef MCB_WALK_AHEAD
+#define MCB_WALK_AHEAD 0
+#endif
 __device__ __forceinline__ double4 ldg_f64x4(const double *p) {
   double4 e;
 #if MCB_TAB_LD == 1
@@ -351,9 +357,24 @@ __device__ __forceinline__ void fill_walk_row(double p, double q, double qq, dou
 template <int SCR>
 __device__ __forceinline__ int draw_binomial_table(Xoshiro &rng, const double *__restrict__ row,
                                                    double4 F) {   // F = the row's first four entries
+#if MCB_WALK_EARLY_U
+  // the uniform is drawn before the row's first entries are looked at: the generator's
+  // ~20 instructions run while the load is in flight (rewound if the row is not a walk)
+  double u = xo_real<SCR>(rng);
+  if (F.x < 0.0) {
+    xo_rewind(rng);
+    return -1;
+  }
+#else
   if (F.x < 0.0) return -1;
   double u = xo_real<SCR>(rng);
+#endif
   int k = 0, c3;
+#if MCB_WALK_AHEAD
+  // the row's next four entries are asked for now, and arrive while the first four are
+  // walked (most warps go on to them)
+  double4 F_next = ldg_f64x4(row + 4);
+#endif
   // one way out of the loop (the lanes of a warp leave it at different rounds: with a
   // single exit they meet again once, and what follows runs once)
   bool more;
@@ -377,7 +398,13 @@ __device__ __forceinline__ int draw_binomial_table(Xoshiro &rng, const double *_
         : "+r"(k), "+d"(u), "=r"(c3)
         : "d"(F.x), "d"(F.y), "d"(F.z), "d"(F.w));
     more = c3 != 0 && k < kWalkK;
+#if MCB_WALK_AHEAD
+    if (more) {
+      if (k == 4) F = F_next; else F = ldg_f64x4(row + k);
+    }
+#else
     if (more) F = ldg_f64x4(row + k);
+#endif
   } while (more);
   if (c3) {   // walked past the row
     xo_rewind(rng);
