@@ -354,7 +354,7 @@ def run_engine(args):
     clocks.__exit__(None, None, None)
 
     # ---- not the headline: BASELINE config C3's filter (one pMCMC chain of 2^16 particles
-    # per GPU) on the single-launch path (csrc/persistent.cuh) and on the two-launch path
+    # per GPU) on the single-launch path (csrc/persistent.cuh) and on the per-interval path
     small = None
     if rank == 0:
         small = {"n_particles": 1 << 16, "unit": "ms per filter evaluation (100 intervals)"}

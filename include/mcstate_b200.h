@@ -221,9 +221,9 @@ int mcb_filter_history(mcb_model *m, const size_t *particles, size_t n, double *
 
 /* A filter of one parameter set whose particles are all resident at once (up to
  * about 150 000 on a B200), run without snapshots, executes as ONE
- * cooperative kernel per mcb_filter call instead of two launches per data interval
+ * cooperative kernel per mcb_filter call instead of three launches per data interval
  * (csrc/persistent.cuh); results are bit-identical either way.  enable = 0 keeps
- * this handle on the two-launch path (A/B measurements, tests); the environment
+ * this handle on the per-interval path (A/B measurements, tests); the environment
  * variable MCB_PERSISTENT=0 does the same for every handle. */
 int mcb_set_persistent(mcb_model *m, int enable);
 /* the same, split so many handles / GPUs can be in flight at once: enqueue
@@ -241,7 +241,7 @@ int mcb_launch_count(const mcb_model *m, uint64_t *n);
 /*
  * Per-kernel device timing for the roofline report.  When enabled, the filter's
  * CUDA graph carries event records around the four per-interval kernels
- * (0: run+compare, 1: tile weights, 2: finalize, 3: resample+gather);
+ * (0: run+compare, 1: weights scan, 2: ancestors, 3: the final gather of a call);
  * mcb_kernel_timing returns the accumulated milliseconds and launch counts
  * since the last reset and clears them.
  */

@@ -503,7 +503,7 @@ class dust_model:
 
     def set_persistent(self, enable=True):
         """Small single-set filters run as one cooperative kernel per call
-        (csrc/persistent.cuh); ``False`` keeps this model on the two-launch path."""
+        (csrc/persistent.cuh); ``False`` keeps this model on the per-interval path."""
         self._ck(self._L.mcb_set_persistent(self._h, int(bool(enable))))
 
     # ---- asynchronous variant used to keep several GPUs / handles busy
@@ -545,7 +545,7 @@ class dust_model:
         self._ck(self._L.mcb_set_kernel_timing(self._h, int(bool(enable))))
 
     def kernel_timing(self):
-        """(ms[4], launches[4]) for run+compare, tile weights, finalize, resample+gather."""
+        """(ms[4], launches[4]) for run+compare, weights scan, ancestors, the final gather."""
         ms = np.zeros(4)
         n = np.zeros(4, dtype=np.uint64)
         self._ck(self._L.mcb_kernel_timing(self._h, ptr(ms, f64p), ptr(n, u64p)))
