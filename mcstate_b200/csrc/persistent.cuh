@@ -2,13 +2,12 @@
 // a single wave (one particle per thread, every block resident): BASELINE config
 // C3 -- a pMCMC chain of 2^16 particles per GPU -- is this case.
 //
-// A filter of 2^16 particles is latency bound under the two-launch-per-interval
-// scheme of kernels.cuh: its kernels run for a few microseconds and the launch
-// boundaries, the one-block tail of the weights stage and the HBM round trip of the
-// generator state dominate.  Here a thread owns output slot i for all the data
-// rows: the generator never leaves its registers, the log-weight goes from the
-// compare straight into the scan, and the intervals are separated by two grid-wide
-// barriers instead of two kernel boundaries:
+// A filter of 2^16 particles is latency bound under the per-interval launches of
+// kernels.cuh: its kernels run for a few microseconds each and the three launch
+// boundaries per interval and the HBM round trip of the generator state dominate.
+// Here a thread owns output slot i for all the data rows: the generator never leaves
+// its registers, the log-weight goes from the compare straight into the scan, and
+// the intervals are separated by two grid-wide barriers instead of kernel boundaries:
 //
 //   per data row:  [gather: slot i takes the particle systematic resampling picks]
 //                  -> n_steps model updates -> compare -> state to HBM, block max
@@ -21,9 +20,10 @@
 //                  and identically in every block
 //
 // Arithmetic, draw order and the integer weight sums are those of kernels.cuh --
-// integer addition is associative, so the tiling (128 here, 2048 there) does not
-// change a cumulative sum -- and the results are bit-identical to the two-launch
-// path and to the oracle (tests/test_engine_gpu.py).
+// integer addition is associative, so the tiling (256 here, 2048 there) does not
+// change a cumulative sum -- and the ancestors (searched here, counted there) are the
+// same: the results are bit-identical to the per-interval path and to the oracle
+// (tests/test_engine_gpu.py).
 //
 // Used for one parameter set without snapshots; everything else takes the general
 // path.  Reference semantics: R/particle_filter_state.R:63-117 (loop),
