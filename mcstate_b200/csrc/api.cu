@@ -334,11 +334,11 @@ template <class M, int SCR>
 void launch_run_compare(mcb_model *m, const double *y_in, double *y_out, uint64_t t0,
                         uint32_t n_steps, const int *kappa, int row, double *hist, int *order) {
   const unsigned grid = blocks_for(m->v.n_total, mcb::kRunThreads);
-  // the run kernel needs ~1.5 KB of shared memory per block (12 blocks per SM): ask for a
-  // small carve-out so the walk tables keep more of L1 (measured: 20 % beats the default
-  // by 1 %, 10 % costs occupancy, 50 % loses 4 %).  MCB_CARVEOUT overrides.  The
-  // attribute is per device: set once for every device this instantiation runs on.
-  static const int carve = getenv("MCB_CARVEOUT") ? atoi(getenv("MCB_CARVEOUT")) : 20;
+  // the run kernel uses no shared memory: ask for all of the L1 / shared-memory array as
+  // cache, for the walk tables (0 and 20 % measure the same, profiles/ab_r02_v18.txt;
+  // MCB_CARVEOUT overrides).  The attribute is per device: set once for every device this
+  // instantiation runs on.
+  static const int carve = getenv("MCB_CARVEOUT") ? atoi(getenv("MCB_CARVEOUT")) : 0;
   static std::mutex mu;
   static std::map<int, bool> carved;
   {

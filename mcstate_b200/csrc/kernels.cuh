@@ -276,12 +276,12 @@ __device__ __noinline__ ParticleState<M> run_general(ParticleState<M> p, uint64_
 // `n_steps` model updates of one particle, state and generator in registers: the
 // lean path where the model has one and the state allows it, the general code for
 // whatever is left (run_general, out of line), or -- for a model without integer
-// compartments -- its one form, inline.  s_exp2: the block's copy of g_exp2_tab.
+// compartments -- its one form, inline.
 template <class M, int SCR>
 __device__ __forceinline__ void run_model_steps(const View &v, const SetData &sd,
                                                 const typename M::Ctx &ctx, size_t set, double *y,
                                                 Xoshiro &rng, uint64_t t0, uint32_t n_steps,
-                                                bool det, const double *s_exp2) {
+                                                bool det) {
   if (n_steps == 0) return;
   uint32_t done = 0;
   if constexpr (M::kHasLean) {
@@ -291,7 +291,6 @@ __device__ __forceinline__ void run_model_steps(const View &v, const SetData &sd
     const LeanTabs tabs{v.tab_inf, v.tab_walk, (uint32_t)v.n_tab, (uint32_t)v.n_wrows};
     if (!det && M::lean_load(sd, y, yi, lc)) {
       // the usual case: integer compartments, setup from the memo tables, no calls
-      const uint32_t s_exp2_addr = (uint32_t)__cvta_generic_to_shared(s_exp2);
       // one counter runs the loop (registers are what this kernel is short of); bit 0 of
       // `resets`: the next step starts a new incidence interval.  The mask comes from the
       // host when it could tell (at most 32 steps, one freq for every set), else it is
@@ -308,7 +307,7 @@ __device__ __forceinline__ void run_model_steps(const View &v, const SetData &sd
             phase = phase + 1 == freq ? 0 : phase + 1;
           }
         }
-        if (!M::template lean_update<SCR>((resets & 1u) != 0, yi, rng, lc, tabs, s_exp2_addr)) break;
+        if (!M::template lean_update<SCR>((resets & 1u) != 0, yi, rng, lc, tabs)) break;
         resets >>= 1;
       } while (--left);
       done = n_steps - left;
@@ -360,16 +359,11 @@ __global__ void __launch_bounds__(kRunThreads, k1_min_blocks<M>())
 k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_out,
               uint64_t t0, uint32_t n_steps, const int *__restrict__ kappa, int row,
               double *__restrict__ hist, int *__restrict__ order_out) {
-  // every warp keeps its own copy of the 2^(j/32) table: the warps of a block never
-  // wait for one another (no block barrier anywhere in this kernel)
-  static_assert(kExp2Tab == 32, "one table entry per lane");
-  __shared__ double s_exp2_all[kRunThreads / 32][kExp2Tab];
-  double *s_exp2 = s_exp2_all[threadIdx.x >> 5];
+  // (no shared memory and no block barrier anywhere in this kernel: the warps of a block
+  // never wait for one another)
   // programmatic dependent launch: let the next kernel be scheduled as this one
   // drains, and do not read anything an earlier kernel wrote before the wait
   grid_launch_dependents();
-  s_exp2[threadIdx.x & 31] = __ldg(g_exp2_tab + (threadIdx.x & 31));
-  __syncwarp();
   grid_dependency_wait();
   if (v.flags[0]) return;
   const size_t i = (size_t)blockIdx.x * kRunThreads + threadIdx.x;
@@ -397,7 +391,7 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
     rng.s2 = ld_stream(v.rng + 2 * v.ld_rng + i);
     rng.s3 = ld_stream(v.rng + 3 * v.ld_rng + i);
 
-    run_model_steps<M, SCR>(v, sd, ctx, set, y, rng, t0, n_steps, det, s_exp2);
+    run_model_steps<M, SCR>(v, sd, ctx, set, y, rng, t0, n_steps, det);
 
     if (n_steps > 0 || y_in != y_out) {
 #pragma unroll

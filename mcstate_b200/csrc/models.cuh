@@ -25,10 +25,6 @@
 #pragma once
 #include "samplers.cuh"
 
-#ifndef MCB_WALK_PF
-#define MCB_WALK_PF 0
-#endif
-
 namespace mcb {
 
 constexpr int kMaxState = 8;
@@ -85,11 +81,10 @@ __device__ __forceinline__ bool to_counts(const double *y, int *yi) {
 // general code must take over: probability outside (0, 1/2], S q >= 10 (BTRS), or
 // a walk the certificate of walk_fast does not cover.
 template <int SCR>
-__device__ __forceinline__ int draw_infection_lean(Xoshiro &rng, int S, double4 e,
-                                                   uint32_t s_exp2) {
+__device__ __forceinline__ int draw_infection_lean(Xoshiro &rng, int S, double4 e) {
   if (S == 0 || e.x == 0.0) return 0;
   if (e.x < 0.0 || (double)S * e.x >= 10.0) return -1;
-  const int k = walk_fast<SCR>(rng, S, e.x, e.y, e.z, s_exp2);
+  const int k = walk_fast<SCR>(rng, S, e.x, e.y, e.z);
   if (k < 0) xo_rewind(rng);
   return k;
 }
@@ -224,8 +219,7 @@ struct SirModel {
   // false: nothing changed, the general code must run this step.
   template <int SCR>
   __device__ __forceinline__ static bool lean_update(bool reset, int *y, Xoshiro &rng,
-                                                     const Lean &c, const LeanTabs &t,
-                                                     uint32_t s_exp2) {
+                                                     const Lean &c, const LeanTabs &t) {
     const int S = y[0], I = y[1];
     // both draws' table entries depend on the state at the start of the step alone:
     // ask for them together
@@ -233,17 +227,12 @@ struct SirModel {
     const double4 e_si =
         ldg_f64x4(reinterpret_cast<const double *>(t.inf + (c.set * t.n_tab + (uint32_t)I)));
     const double4 F_ir = ldg_f64x4(row_ir);
-#if MCB_WALK_PF
-    // the row's next four entries (the next 32-byte sector of the same line) are wanted by
-    // most warps a few instructions from now: ask for them without a register
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(row_ir + 4));
-#endif
     int n_IR = 0;
     if (I != 0) {
       n_IR = draw_const_lean<SCR>(rng, I, row_ir, F_ir, t);
       if (n_IR < 0) return false;
     }
-    const int n_SI = draw_infection_lean<SCR>(rng, S, e_si, s_exp2);
+    const int n_SI = draw_infection_lean<SCR>(rng, S, e_si);
     if (n_SI < 0) {
       if (I != 0) xo_rewind(rng);  // the recovery draw's uniform
       return false;
@@ -351,12 +340,11 @@ struct SirsModel {
   }
   template <int SCR>
   __device__ __forceinline__ static bool lean_update(bool reset, int *y, Xoshiro &rng,
-                                                     const Lean &c, const LeanTabs &t,
-                                                     uint32_t s_exp2) {
+                                                     const Lean &c, const LeanTabs &t) {
     const int S = y[0], I = y[1], R = y[2];
     const double4 e_si =
         ldg_f64x4(reinterpret_cast<const double *>(t.inf + (c.set * t.n_tab + (uint32_t)I)));
-    const int n_SI = draw_infection_lean<SCR>(rng, S, e_si, s_exp2);
+    const int n_SI = draw_infection_lean<SCR>(rng, S, e_si);
     if (n_SI < 0) return false;
     // did the infection draw take a uniform?  (it returns 0 without one for S = 0 or p = 0)
     const bool si_drew = S != 0 && e_si.x != 0.0;

@@ -81,7 +81,6 @@ __global__ void __launch_bounds__(kPersistThreads, MCB_PERSIST_MINBLOCKS)
 k_filter_persistent(View v, PersistArgs a) {
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
-  __shared__ double s_exp2[kExp2Tab];
   __shared__ u128 s_pre[kPersistMaxBlocks];   // inclusive prefix of block sums (128-bit: kernels.cuh)
   __shared__ unsigned long long s_win[kPersistThreads / 32][2 * kPersistThreads];
   __shared__ unsigned long long s_warp[kPersistThreads / 32];
@@ -93,8 +92,6 @@ k_filter_persistent(View v, PersistArgs a) {
   const size_t i = (size_t)blockIdx.x * kPersistThreads + tid;
   const size_t N = v.n_total;
   const bool live = i < N;
-  if (tid < kExp2Tab) s_exp2[tid] = __ldg(g_exp2_tab + tid);
-  __syncthreads();
 
   const SetData sd{v.derived, v.n_tab};
   const typename M::Ctx ctx = M::context(sd);
@@ -201,7 +198,7 @@ k_filter_persistent(View v, PersistArgs a) {
     }
     double lw = neg_inf;
     if (live) {
-      run_model_steps<M, SCR>(v, sd, ctx, 0, y, rng, t, n_steps, det, s_exp2);
+      run_model_steps<M, SCR>(v, sd, ctx, 0, y, rng, t, n_steps, det);
       touched = touched || n_steps > 0;
       if (hist) save_slice(rel + 1, i);
       if (weigh) {

@@ -196,40 +196,20 @@ __device__ __forceinline__ double2 ldg_f64x2(const double *p) {
   asm("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(e.x), "=d"(e.y) : "l"(p));
   return e;
 }
-// one 32-byte load (LDG.256): four consecutive table entries.  MCB_TAB_LD = 1 asks L1 to
-// keep the line (evict-last): the tables are read at every model step
-#ifndef MCB_TAB_LD
-#define MCB_TAB_LD 0
-#endif
-#ifndef MCB_WALK_EARLY_U
-#define MCB_WALK_EARLY_U 0
-#endif
-#ifndef MCB_WALK_AHEAD
-#define MCB_WALK_AHEAD 0
-#endif
+// one 32-byte load (LDG.256): four consecutive table entries (an evict-last hint on these
+// loads measured the same: profiles/ab_r02_v3.txt)
 __device__ __forceinline__ double4 ldg_f64x4(const double *p) {
   double4 e;
-#if MCB_TAB_LD == 1
-  asm("ld.global.nc.L1::evict_last.v4.f64 {%0, %1, %2, %3}, [%4];"
-      : "=d"(e.x), "=d"(e.y), "=d"(e.z), "=d"(e.w) : "l"(p));
-#else
   asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
       : "=d"(e.x), "=d"(e.y), "=d"(e.z), "=d"(e.w) : "l"(p));
-#endif
-  return e;
-}
-__device__ __forceinline__ double lds_f64(uint32_t addr) {
-  double e;
-  asm("ld.shared.f64 %0, [%1];" : "=d"(e) : "r"(addr));
   return e;
 }
 
-// 2^(j/32), j = 0..31, filled by the host; a block stages it in shared memory
+// 2^(j/32), j = 0..31, filled by the host.  Read straight from global memory: its two
+// lines never leave L1, and a shared-memory copy costs an address kept or rebuilt at
+// every step (measured 0.9 us per launch slower: profiles/ab_r02_v6.txt)
 constexpr int kExp2Tab = 32;
 __device__ double g_exp2_tab[kExp2Tab];
-#ifndef MCB_EXP2_GLOBAL
-#define MCB_EXP2_GLOBAL 1
-#endif
 // 1/k as constant-bank operands (entry 0 unused); approximate values are all the fast
 // walk needs
 __constant__ double c_recip[kInvSmall];
@@ -243,7 +223,7 @@ __constant__ double c_fexp[7] = {
 // r = x - k ln2/32 (|r| <= 0.0109), exp(x) = 2^(k >> 5) 2^((k & 31)/32) (1 + r + ... + r^5/120).
 // Not reproducible to the last bit across implementations and not meant to be: it
 // only proposes what the certificate of the fast walk then accepts or rejects.
-__device__ __forceinline__ double fast_exp_neg(double x, uint32_t s_exp2_addr) {
+__device__ __forceinline__ double fast_exp_neg(double x) {
   const double magic = 6755399441055744.0;   // 1.5 * 2^52: adding it rounds to an integer
   const double tm = fma(x, c_fexp[0], magic);
   const int ki = __double2loint(tm);
@@ -255,15 +235,7 @@ __device__ __forceinline__ double fast_exp_neg(double x, uint32_t s_exp2_addr) {
   p = fma(p, r, c_fexp[6]);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
-#if MCB_EXP2_GLOBAL
-  // the 256-byte table straight from global memory (two lines that never leave L1):
-  // one address computation instead of a per-warp shared-memory address kept or rebuilt
-  // at every step
-  (void)s_exp2_addr;
   const double v = __ldg(g_exp2_tab + (ki & (kExp2Tab - 1))) * p;
-#else
-  const double v = lds_f64(s_exp2_addr + 8u * (uint32_t)(ki & (kExp2Tab - 1))) * p;
-#endif
   return __hiloint2double(__double2hiint(v) + ((ki >> 5) << 20), __double2loint(v));
 }
 
@@ -274,14 +246,13 @@ constexpr double kWalkEps = 0x1p-32;
 // the exact walk's k, or -1 when the exact code must decide (the caller rewinds the
 // generator by that one uniform).
 template <int SCR>
-__device__ __forceinline__ int walk_fast(Xoshiro &rng, int n, double q, double r, double lq,
-                                         uint32_t s_exp2_addr) {
+__device__ __forceinline__ int walk_fast(Xoshiro &rng, int n, double q, double r, double lq) {
   const double nd = (double)n, nd1 = nd + 1.0;
   // the factor g/k - r passes one at k = q (n + 1): if that is (nearly) an integer the
   // exact chain may meet f_k == f_{k-1} there and abandon the attempt -- its call
   const double mode = q * nd1;
   const double mode_r = (mode + 6755399441055744.0) - 6755399441055744.0;
-  const double f0 = fast_exp_neg(nd * lq, s_exp2_addr);
+  const double f0 = fast_exp_neg(nd * lq);
   const double g = r * nd1;
   const double u = xo_real<SCR>(rng);
   if (fabs(mode - mode_r) <= mode * 0x1p-30) return -1;
@@ -357,24 +328,9 @@ __device__ __forceinline__ void fill_walk_row(double p, double q, double qq, dou
 template <int SCR>
 __device__ __forceinline__ int draw_binomial_table(Xoshiro &rng, const double *__restrict__ row,
                                                    double4 F) {   // F = the row's first four entries
-#if MCB_WALK_EARLY_U
-  // the uniform is drawn before the row's first entries are looked at: the generator's
-  // ~20 instructions run while the load is in flight (rewound if the row is not a walk)
-  double u = xo_real<SCR>(rng);
-  if (F.x < 0.0) {
-    xo_rewind(rng);
-    return -1;
-  }
-#else
   if (F.x < 0.0) return -1;
   double u = xo_real<SCR>(rng);
-#endif
   int k = 0, c3;
-#if MCB_WALK_AHEAD
-  // the row's next four entries are asked for now, and arrive while the first four are
-  // walked (most warps go on to them)
-  double4 F_next = ldg_f64x4(row + 4);
-#endif
   // one way out of the loop (the lanes of a warp leave it at different rounds: with a
   // single exit they meet again once, and what follows runs once)
   bool more;
@@ -398,13 +354,7 @@ __device__ __forceinline__ int draw_binomial_table(Xoshiro &rng, const double *_
         : "+r"(k), "+d"(u), "=r"(c3)
         : "d"(F.x), "d"(F.y), "d"(F.z), "d"(F.w));
     more = c3 != 0 && k < kWalkK;
-#if MCB_WALK_AHEAD
-    if (more) {
-      if (k == 4) F = F_next; else F = ldg_f64x4(row + k);
-    }
-#else
     if (more) F = ldg_f64x4(row + k);
-#endif
   } while (more);
   if (c3) {   // walked past the row
     xo_rewind(rng);

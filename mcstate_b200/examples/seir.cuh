@@ -145,15 +145,14 @@ struct UserModel {
   // (state and generator as they were), update() must run this step.
   template <int SCR>
   __device__ __forceinline__ static bool lean_update(bool reset, int *y, Xoshiro &rng,
-                                                     const Lean &c, const LeanTabs &t,
-                                                     uint32_t s_exp2) {
+                                                     const Lean &c, const LeanTabs &t) {
     const int S = y[0], E = y[1], I = y[2];
     const double4 e_se =
         ldg_f64x4(reinterpret_cast<const double *>(t.inf + (c.set * t.n_tab + (uint32_t)I)));
     const double *row_ei = walk_row_ptr(E, c.set * kConst + C_EI, t);
     const double *row_ir = walk_row_ptr(I, c.set * kConst + C_IR, t);
     const double4 F_ei = ldg_f64x4(row_ei), F_ir = ldg_f64x4(row_ir);
-    const int n_SE = draw_infection_lean<SCR>(rng, S, e_se, s_exp2);
+    const int n_SE = draw_infection_lean<SCR>(rng, S, e_se);
     if (n_SE < 0) return false;
     const bool se_drew = S != 0 && e_se.x != 0.0;   // (no uniform for S = 0 or p = 0)
     int n_EI = 0;
