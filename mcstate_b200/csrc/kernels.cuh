@@ -302,7 +302,8 @@ __device__ __forceinline__ void run_model_steps(const View &v, const SetData &sd
           const uint64_t t = t0 + (n_steps - left);
           uint32_t phase = t <= 0xffffffffULL ? (uint32_t)t % freq : (uint32_t)(t % freq);
           resets = 0;
-          for (uint32_t k = 0; k < 32u; ++k) {
+          const uint32_t nk = min(left, 32u);   // (only as many bits as steps are left)
+          for (uint32_t k = 0; k < nk; ++k) {
             resets |= (phase == 0 ? 1u : 0u) << k;
             phase = phase + 1 == freq ? 0 : phase + 1;
           }
