@@ -228,7 +228,7 @@ def run_reference(args):
         "note": "mcstate is pure R and its native dependency dust is absent from the image, so "
                 "the reference arm is the C/OpenMP oracle port of dust's filter loop",
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def config_dict(n_gpus):
@@ -251,9 +251,6 @@ def run_engine(args):
         raise SystemExit("bench.py needs a CUDA device: mcstate_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     run_configs = os.environ.get("MCB_BENCH_CONFIGS", "1") != "0"
-    # stdout carries the one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION) goes
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     elif run_configs:
@@ -450,9 +447,32 @@ def run_engine(args):
             "small_filter_c3": small,
             "configs": configs,
         }
-        print(json.dumps(line))
+        emit(line)
     if dist.is_initialized():
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def own_stdout():
+    """stdout carries ONE JSON line and nothing else: whatever a library prints there (NCCL's
+    version banner, for one) is sent to stderr for the whole run, and the line is written to
+    the real stdout at the end."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -462,6 +482,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     args = ap.parse_args()
+    own_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
