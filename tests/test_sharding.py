@@ -67,7 +67,7 @@ _WORKER = textwrap.dedent("""
     import numpy as np
     import torch.distributed as dist
     sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
-    from test_sharding import nested_data, pars_for, make_generator
+    from test_sharding import nested_data, pars_for, make_generator, impossible
     from mcstate_b200.sharding import nested_filter_sharded
     kind, n_pop, n_particles = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
     backend = "gloo"
@@ -86,6 +86,11 @@ _WORKER = textwrap.dedent("""
                               gpu_config=dev)
     p = pars_for(n_pop)
     out = [f.run(p), f.run(p), f.run(list(reversed(p)))]
+    if os.environ.get("MCB_TEST_IMPOSSIBLE"):
+        # the last population cannot have produced its data (no infections, no noise): the
+        # whole vector is -Inf on every rank, as from the unsharded filter
+        # (R/particle_filter_state.R:463-474), and the next evaluation is a normal one again
+        out = [f.run(impossible(p)), f.run(p)]
     if dist.get_rank() == 0:
         with open(sys.argv[4], "wb") as fh:
             pickle.dump(out, fh)
@@ -120,6 +125,12 @@ def _sharded(tmp_path, kind, n_pop, n_particles, world=2):
         return pickle.load(fh)
 
 
+def impossible(pars):
+    """the last population without infections or observation noise: modelled incidence is
+    exactly 0, every positive observation has log density -Inf"""
+    return list(pars[:-1]) + [dict(pars[-1], exp_noise=float("inf"), I0=0)]
+
+
 def _unsharded(kind, n_pop, n_particles):
     f = particle_filter(nested_data(n_pop), make_generator(kind), n_particles, None, seed=7,
                         gpu_config=0 if kind == "gpu" else None)
@@ -138,3 +149,17 @@ def test_sharded_nested_filter_equals_unsharded(tmp_path, kind):
     for w, g in zip(want, got):
         assert np.array_equal(np.asarray(w), np.asarray(g)), (w, g)
     assert not np.array_equal(want[0], want[1])  # the second run continued the streams
+
+
+def test_sharded_nested_filter_with_an_impossible_population(tmp_path, monkeypatch):
+    """ADVICE (round 1): when one population is impossible only its rank stops early; the
+    gathered RESULT must still be the unsharded filter's (all -Inf), on every rank, and the
+    filter must be usable afterwards."""
+    monkeypatch.setenv("MCB_TEST_IMPOSSIBLE", "1")
+    got = _sharded(tmp_path, "oracle", 3, 40)
+    f = particle_filter(nested_data(3), make_generator("oracle"), 40, None, seed=7)
+    p = pars_for(3)
+    want_bad = f.run(impossible(p))
+    assert np.all(np.asarray(want_bad) == -np.inf)
+    assert np.array_equal(np.asarray(got[0]), np.asarray(want_bad))
+    assert np.all(np.isfinite(got[1])) and len(got[1]) == 3
