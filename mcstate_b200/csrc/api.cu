@@ -395,7 +395,7 @@ void weights_scan(mcb_model *m, int row) {
 // K3: per set the total weight -> ll, thresholds, early-exit rule; every particle with
 // offspring into the ancestor slots (v.heads), read back by mcb::ancestor_of
 void ancestors(mcb_model *m, int row) {
-  const unsigned grid = (unsigned)(m->v.n_sets * m->v.tiles_per_set);
+  const unsigned grid = (unsigned)(m->v.n_sets * m->v.anc_blocks_per_set);
   launch_chained(m, m->chain, mcb::k_ancestors, grid, mcb::kTileThreads, m->v, row);
 }
 
@@ -958,6 +958,7 @@ int mcb_alloc_ex(int model_id, const double *pars, size_t n_particles, size_t n_
   v.n_min = 0;
   v.data_sets = 1;
   v.tiles_per_set = (int)((n_particles + mcb::kTile - 1) / mcb::kTile);
+  v.anc_blocks_per_set = (int)((n_particles + mcb::kAncTile - 1) / mcb::kAncTile);
   v.deterministic = deterministic;
   v.independent = (seed_mode == MCB_SEED_PER_SET && n_sets > 1) ? 1 : 0;
 

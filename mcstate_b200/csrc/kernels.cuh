@@ -44,11 +44,28 @@ namespace mcb {
 #endif
 constexpr int kRunThreads = MCB_RUN_THREADS;
 constexpr int kTileThreads = 256;
+// K2 (weights scan) works on tiles of kTile particles, 4 per thread: the tile is the unit of
+// the cumulative weights and of the tile sums.  K3 (ancestors) takes 8 particles per thread
+// -- a block covers kAncTiles = 2 weight tiles -- because its per-block prologue (the sum of
+// the set's tile sums) is worth spreading over more particles.  Measured, K2 / K3 us per
+// launch at 2^20 particles (profiles/ab_r02_v23.txt): 4 and 4: 11.0 / 15.7, 8 and 8:
+// 12.3 / 14.4, 16 and 16: 14.3 / 15.9.
 #ifndef MCB_TILE_ITEMS
-#define MCB_TILE_ITEMS 8
+#define MCB_TILE_ITEMS 4
+#endif
+#ifndef MCB_ANC_ITEMS
+#define MCB_ANC_ITEMS 8
 #endif
 constexpr int kTileItems = MCB_TILE_ITEMS;  // consecutive particles per thread in K2
-constexpr int kTile = kTileThreads * kTileItems;  // particles per weight tile
+constexpr int kAncItems = MCB_ANC_ITEMS;    // consecutive particles per thread in K3
+#ifndef MCB_TILE_MINBLOCKS
+#define MCB_TILE_MINBLOCKS 4
+#endif
+constexpr int kTile = kTileThreads * kTileItems;     // particles per weight tile
+constexpr int kAncTile = kTileThreads * kAncItems;   // particles per block of K3
+constexpr int kAncTiles = kAncTile / kTile;          // weight tiles per block of K3
+static_assert(kAncTile % kTile == 0 && kAncTiles >= 1 && kTileItems % 4 == 0 && kAncItems % 4 == 0,
+              "a block of K3 covers whole weight tiles");
 constexpr int kGatherThreads = 256;
 
 typedef unsigned __int128 u128;
@@ -79,7 +96,9 @@ struct View {
   unsigned int *ticket; // [n_sets + 2] K3 counters: [n_sets] sets done, [n_sets + 1] any set dead
   const int *index;   // [n_index] rows returned by run()/saved in trajectories
   size_t n_particles, n_sets, n_total, ld, ld_rng;
-  int n_state, n_index, n_min, data_sets, tiles_per_set, deterministic, n_tab, n_wrows;
+  // tiles_per_set: weight tiles (kTile particles) per set; anc_blocks_per_set: blocks of K3
+  int n_state, n_index, n_min, data_sets, tiles_per_set, anc_blocks_per_set, deterministic, n_tab,
+      n_wrows;
   // independent != 0: the sets are separate filters batched in one handle (per-set
   // seeds): a set whose weights all vanish gets -Inf and is not resampled, the others
   // go on.  0: the sets of one multi-parameter filter -- any dead set ends the call
@@ -520,7 +539,7 @@ __device__ __forceinline__ unsigned long long weight_to_fixed(double w) {
 }
 
 // ---------------------------------------------------------------------------
-// K2: one block per tile of kTile particles (tiles never straddle a set):
+// K2: one block per tile of kTile particles, kTileItems per thread (tiles never straddle a set):
 // w = exp(logw - max) -> fixed point, inclusive scan inside the tile -> the
 // tile's cumulative weights and its sum.  Nothing here waits for another block:
 // the sums are put together by every block of K3 for itself.  The block also
@@ -528,7 +547,7 @@ __device__ __forceinline__ unsigned long long weight_to_fixed(double w) {
 // GIVEN = true: `logw` already holds weights in [0,1] (model$resample(weights)).
 // ---------------------------------------------------------------------------
 template <bool GIVEN>
-__global__ void __launch_bounds__(kTileThreads, 4) k_weights_scan(View v, int row) {
+__global__ void __launch_bounds__(kTileThreads, MCB_TILE_MINBLOCKS) k_weights_scan(View v, int row) {
   __shared__ unsigned long long s_warp[kTileThreads / 32];
   grid_launch_dependents();
   const size_t set = v.n_sets == 1 ? 0 : blockIdx.x / (unsigned)v.tiles_per_set;
@@ -681,23 +700,26 @@ __device__ __forceinline__ uint32_t slots_reached(const CountCtx &c, unsigned lo
   return k;
 }
 
-__global__ void __launch_bounds__(kTileThreads, 4) k_ancestors(View v, int row) {
+__global__ void __launch_bounds__(kTileThreads, MCB_TILE_MINBLOCKS) k_ancestors(View v, int row) {
   __shared__ u128 s_red[2][kTileThreads / 32];
   __shared__ uint32_t s_cnt[kTileThreads / 32];
   __shared__ uint32_t s_heavy[kHeavyCap][3];
   __shared__ int s_heavy_n;
   grid_launch_dependents();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int T = v.tiles_per_set;
-  const size_t set = v.n_sets == 1 ? 0 : blockIdx.x / (unsigned)T;
-  const int tile = (int)(blockIdx.x - (unsigned)set * (unsigned)T);
+  const int T = v.tiles_per_set;          // weight tiles of a set (K2's)
+  const int NB = v.anc_blocks_per_set;    // blocks of this kernel per set
+  const size_t set = v.n_sets == 1 ? 0 : blockIdx.x / (unsigned)NB;
+  const int blk = (int)(blockIdx.x - (unsigned)set * (unsigned)NB);
+  const int tile = blk * kAncTiles;       // the block's first weight tile
   const size_t gbase = set * v.n_particles;
   const uint32_t n_p = (uint32_t)v.n_particles;
-  const uint32_t in_set = (uint32_t)tile * kTile + tid * kTileItems;   // the thread's first particle
-  const int n_mine = in_set >= n_p ? 0 : (int)min((uint32_t)kTileItems, n_p - in_set);
+  const uint32_t in_set = (uint32_t)blk * kAncTile + tid * kAncItems;   // the thread's first particle
+  const int n_mine = in_set >= n_p ? 0 : (int)min((uint32_t)kAncItems, n_p - in_set);
+  const int my_tile = tile + (tid * kAncItems) / kTile;   // the weight tile of the thread's particles
   if (tid == 0) s_heavy_n = 0;
   const size_t base = gbase + in_set;
-  const bool vec = n_mine == kTileItems && (base & 1) == 0;
+  const bool vec = n_mine == kAncItems && (base & 1) == 0;
   const unsigned long long *sums = v.tile_sum + set * T;
   grid_dependency_wait();
   // everything the block reads is asked for at once -- the stop flag, the first round of
@@ -708,22 +730,22 @@ __global__ void __launch_bounds__(kTileThreads, 4) k_ancestors(View v, int row) 
   const unsigned long long sum0 = tid < T ? __ldcg(sums + tid) : 0ULL;
   const double u = __ldcg(v.u_draws + (size_t)(row < 0 ? 0 : row) * v.n_sets + set);
   const unsigned long long mx_key = row >= 0 ? __ldcg(v.wmax + (size_t)row * v.n_sets + set) : 0ULL;
-  unsigned long long q[kTileItems];
+  unsigned long long q[kAncItems];
   if (vec) {
     const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(v.cw + base);
 #pragma unroll
-    for (int j = 0; j < kTileItems / 2; ++j) {
+    for (int j = 0; j < kAncItems / 2; ++j) {
       const ulonglong2 t = __ldcs(src + j);
       q[2 * j] = t.x;
       q[2 * j + 1] = t.y;
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < kTileItems; ++j) q[j] = j < n_mine ? __ldcs(v.cw + base + j) : 0ULL;
+    for (int j = 0; j < kAncItems; ++j) q[j] = j < n_mine ? __ldcs(v.cw + base + j) : 0ULL;
   }
   if (stopped) return;
   int *heads = v.heads;
-  const bool leader = tile == 0 && tid == 0;   // finishes the set
+  const bool leader = blk == 0 && tid == 0;   // finishes the set
   if (row >= 0 && datum_is_na(v, row, set)) {   // block-uniform: nothing weighed, identity
     for (int k = 0; k < n_mine; ++k) heads[gbase + in_set + k] = (int)(gbase + in_set + k);
     if (leader) apply_stop_rule(v, row, false);
@@ -773,32 +795,36 @@ __global__ void __launch_bounds__(kTileThreads, 4) k_ancestors(View v, int row) 
     for (int k = 0; k < n_mine; ++k) heads[gbase + in_set + k] = (int)(gbase + in_set + k);
     return;
   }
+  // the cumulative weights are per weight tile: a thread beyond the block's first tile adds
+  // the sums of the tiles in between (one, with two tiles per block)
+  for (int t = tile; t < my_tile && t < T; ++t) before += __ldcg(sums + t);
+  c.offset = before;
   c.d0 = u128_to_double(before) - c.si.uu0;
 
   // ---- counts of the thread's 8 particles
-  uint32_t cnt[kTileItems];
+  uint32_t cnt[kAncItems];
   {
 #pragma unroll
-    for (int j = 0; j < kTileItems; ++j) {
+    for (int j = 0; j < kAncItems; ++j) {
       cnt[j] = j < n_mine ? slots_reached(c, q[j]) : n_p;
       if (in_set + j >= n_p - 1) cnt[j] = n_p;   // the last particle takes whatever is left
     }
   }
   // the count before the thread's first particle: the previous thread's last, the
   // count at the tile's offset for the first thread (nothing for the set's first)
-  uint32_t prev = __shfl_up_sync(0xffffffffu, cnt[kTileItems - 1], 1);
-  if (lane == 31) s_cnt[warp] = cnt[kTileItems - 1];
+  uint32_t prev = __shfl_up_sync(0xffffffffu, cnt[kAncItems - 1], 1);
+  if (lane == 31) s_cnt[warp] = cnt[kAncItems - 1];
   __syncthreads();
   if (lane == 0) prev = warp ? s_cnt[warp - 1] : (tile ? slots_reached(c, 0ULL) : 0u);
 
   // ---- a particle with offspring: its index at its first slot (global slot numbers) ...
   const uint32_t g0 = (uint32_t)gbase + in_set;   // the thread's first particle
-  const uint32_t lo = (uint32_t)gbase + prev, hi = (uint32_t)gbase + cnt[kTileItems - 1];
+  const uint32_t lo = (uint32_t)gbase + prev, hi = (uint32_t)gbase + cnt[kAncItems - 1];
   uint32_t heavy = 0;   // bit j: particle j's slots are written by the whole block
   {
     uint32_t a = prev;
 #pragma unroll
-    for (int j = 0; j < kTileItems; ++j) {
+    for (int j = 0; j < kAncItems; ++j) {
       const uint32_t b = cnt[j];
       if (b > a) heads[(uint32_t)gbase + a] = (int)(g0 + j);
       if (b - a >= kHeavySlots) {
@@ -820,11 +846,11 @@ __global__ void __launch_bounds__(kTileThreads, 4) k_ancestors(View v, int row) 
     const uint32_t rel = m - (uint32_t)gbase;
     int j = 0;
 #pragma unroll
-    for (int k = 0; k < kTileItems - 1; ++k) j += cnt[k] <= rel ? 1 : 0;
+    for (int k = 0; k < kAncItems - 1; ++k) j += cnt[k] <= rel ? 1 : 0;
     if ((heavy >> j) & 1u) {   // the block writes that particle's: on to the end of its range
       uint32_t end = cnt[0];
 #pragma unroll
-      for (int k = 1; k < kTileItems; ++k) end = k == j ? cnt[k] : end;
+      for (int k = 1; k < kAncItems; ++k) end = k == j ? cnt[k] : end;
       m = ((((uint32_t)gbase + end - 1u) | 31u) + 1u) - 32u;
       continue;
     }
