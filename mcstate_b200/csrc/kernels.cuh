@@ -353,9 +353,10 @@ __device__ __forceinline__ void run_model_steps(const View &v, const SetData &sd
 #define MCB_K1_MINBLOCKS 12
 #endif
 // the warp's maximum goes to the atomic only if it would raise the maximum as it stands (1),
-// or always, as a fire-and-forget reduction (0)
+// or always, as a fire-and-forget reduction (0: a same-address atomic per warp, which a
+// short launch cannot absorb)
 #ifndef MCB_MAX_FILTER
-#define MCB_MAX_FILTER 0
+#define MCB_MAX_FILTER 1
 #endif
 // A model without a lean path runs its update as written (doubles, the general samplers)
 // and spills at the 40 registers the lean SIR loop is tuned for (SEIR user model: 700 B of
@@ -445,9 +446,11 @@ k_run_compare(View v, const double *__restrict__ y_in, double *__restrict__ y_ou
   if (row < 0) return;
 
   // max of logw per parameter set: one reduction per warp when the warp sits inside one
-  // set (the common case) and one fire-and-forget atomic per warp (reading the maximum as
-  // it stands first, to skip the atomic when it would not raise it, measured 0.3 us
-  // slower: profiles/ab_r02_v14.txt); else one atomic per weighted thread
+  // set (the common case), and an atomic only if it would raise the maximum as it stands
+  // (the maximum only grows: after the first blocks hardly any warp has to).  Without the
+  // look 32768 atomics on one address bound a short launch: the SIR kernel gains 0.3 us
+  // (profiles/ab_r02_v14.txt) but the volatility kernel goes from 24 to 34 us
+  // (profiles/weights_r02_v25.txt).  Else one atomic per weighted thread
   const size_t first = i - (threadIdx.x & 31);
   size_t last = first + 31;
   if (last >= v.n_total) last = v.n_total - 1;
