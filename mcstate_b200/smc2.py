@@ -184,7 +184,10 @@ class smc2_engine:
         # but not the filters (Q1), so the two drift apart until a proposal is accepted
         self._model_theta = theta[self._lo:self._hi].copy()
         self._model = self._new_model(pars.model(self._model_theta))
-        self._child = None  # the proposal's model handle, allocated once and reused
+        # the proposal's model handle, allocated once -- here, with the engine, not at the
+        # first replenishment (a few hundred MB of device memory: its allocation belongs to
+        # setting the engine up, not to a data row) -- and reused by every replenishment
+        self._child = self._new_model(pars.model(self._model_theta))
         self._gather_obj = None
         self._on_torch_stream = False
         self._filter_facade = filter
@@ -215,11 +218,8 @@ class smc2_engine:
         handle serves every replenishment -- it is reset (F2) and takes the streams by a
         device copy, instead of an allocation, a host round trip of the RNG state and a
         free per proposal."""
-        if self._child is None:
-            self._child = self._new_model(pars_model)
-        else:
-            self._child.update_state(pars=pars_model, time=int(self._times[0, 0]),
-                                     set_initial_state=True)
+        self._child.update_state(pars=pars_model, time=int(self._times[0, 0]),
+                                 set_initial_state=True)
         self._child.copy_sets_from(self._model, np.ones(self._hi - self._lo, dtype=bool),
                                    state=False, rng=True)
         return self._child
