@@ -64,8 +64,9 @@ constexpr int kAncItems = MCB_ANC_ITEMS;    // consecutive particles per thread 
 constexpr int kTile = kTileThreads * kTileItems;     // particles per weight tile
 constexpr int kAncTile = kTileThreads * kAncItems;   // particles per block of K3
 constexpr int kAncTiles = kAncTile / kTile;          // weight tiles per block of K3
-static_assert(kAncTile % kTile == 0 && kAncTiles >= 1 && kTileItems % 4 == 0 && kAncItems % 4 == 0,
-              "a block of K3 covers whole weight tiles");
+static_assert(kAncTile % kTile == 0 && kAncTiles >= 1 && kTileItems % 4 == 0 && kAncItems % 4 == 0 &&
+                  kTile % kAncItems == 0,
+              "a block of K3 covers whole weight tiles, a thread of K3 stays inside one");
 constexpr int kGatherThreads = 256;
 
 typedef unsigned __int128 u128;
@@ -567,7 +568,7 @@ __global__ void __launch_bounds__(kTileThreads, MCB_TILE_MINBLOCKS) k_weights_sc
   const bool have = GIVEN || !datum_is_na(v, row, set);   // block-uniform
   const bool dead = !GIVEN && !(mx > __longlong_as_double(0xfff0000000000000LL));
   double lw[kTileItems];
-  if (full) {  // 16-byte vector loads: the 8 values of a thread are contiguous
+  if (full) {  // 16-byte vector loads: a thread's values are contiguous
     const double2 *src = reinterpret_cast<const double2 *>(v.logw + base);
 #pragma unroll
     for (int j = 0; j < kTileItems / 2; ++j) {
@@ -635,10 +636,10 @@ __global__ void __launch_bounds__(kTileThreads, MCB_TILE_MINBLOCKS) k_weights_sc
 // cumulative weight reaches ceil(uu0 + i du); turned round, particle j owns the
 // slots [c(C_{j-1}), c(C_j)) where C_j is its inclusive cumulative weight and
 // c(C) = #{i : ceil(uu0 + i du) <= C} -- a count that (C - uu0)/du gives directly.
-// So nothing is searched: one block per weight tile puts the set's tile sums
-// together for itself (what lies before its tile, and the total: the thresholds,
-// and for the set's first tile the log-mean-exp -> ll and the early-exit rule),
-// every thread turns its 8 cumulative weights into counts, and a particle with
+// So nothing is searched: a block (two weight tiles, 8 particles per thread) puts the
+// set's tile sums together for itself (what lies before its tiles, and the total: the
+// thresholds, and for the set's first block the log-mean-exp -> ll and the early-exit
+// rule), every thread turns its 8 cumulative weights into counts, and a particle with
 // offspring writes its index at its FIRST slot and at every multiple of 32 its
 // slots cover.  Whoever loads by ancestor (ancestor_of) reads its slot and takes the
 // running maximum over its warp: one coalesced 4-byte load, no dependent probes, and
