@@ -251,6 +251,7 @@ def run_engine(args):
         raise SystemExit("bench.py needs a CUDA device: mcstate_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     run_configs = os.environ.get("MCB_BENCH_CONFIGS", "1") != "0"
+    configs_error = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     elif run_configs:
@@ -260,8 +261,12 @@ def run_engine(args):
         with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sk:
             sk.bind(("127.0.0.1", 0))
             port = sk.getsockname()[1]
-        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=0,
-                                world_size=1, device_id=torch.device("cuda", local))
+        try:
+            dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=0,
+                                    world_size=1, device_id=torch.device("cuda", local))
+        except Exception as exc:   # the headline does not need the group: say so and go on
+            configs_error = "process group: %r" % (exc,)
+            run_configs = False
 
     from mcstate_b200 import dust
     from mcstate_b200.particle_filter import particle_filter
@@ -370,18 +375,27 @@ def run_engine(args):
             torch.cuda.synchronize()
             small[name] = (time.perf_counter() - t0) / 20 * 1e3
 
+    tmax = torch.tensor([ms_total, e2e_s * 1e3], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(tmax[0]), float(tmax[1])
     # ---- the configurations with a collective (C3, C4, C5), same launch, own clocks
     configs = None
     if run_configs:
         import bench_configs
 
         del pf, model
-        configs = bench_configs.run_configs(local, lambda idx: ClockSampler(idx, active=rank == 0))
+        try:
+            configs = bench_configs.run_configs(local,
+                                                lambda idx: ClockSampler(idx, active=rank == 0))
+        except Exception as exc:   # the headline line is printed whatever happens here
+            import traceback
 
-    tmax = torch.tensor([ms_total, e2e_s * 1e3], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = float(tmax[0]), float(tmax[1])
+            traceback.print_exc()
+            configs_error = repr(exc)
+    if configs is None and configs_error is not None:
+        configs = {"error": configs_error}
+
     work = world * N_PARTICLES * n_steps_model * args.steps
     value = work / (ms_total * 1e-3)
     e2e_value = work / (e2e_ms * 1e-3)
