@@ -117,6 +117,30 @@ def ncu_issue_counters(kernel):
         return None
 
 
+def ncu_launch_list_us(kernel):
+    """Average duration (us) of `kernel` in the committed ncu launch list of the latest
+    capture (profiles/ncu_launches_r*.csv: `gpu__time_duration.sum` per launch, serialised,
+    cold caches) -- the kernel's own execution time, beside the CUDA-event figure, which for
+    a short kernel also holds the launch.  (None, None) if absent."""
+    import csv
+    import glob
+    import re
+
+    def version(path):
+        return tuple(int(x) for x in re.findall(r"\d+", os.path.basename(path)))
+
+    try:
+        files = sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_launches_r*.csv")), key=version)
+        rows = list(csv.reader(open(files[-1])))
+        hdr = next(r for r in rows if "Kernel Name" in r and "Metric Value" in r)
+        kn, mv = hdr.index("Kernel Name"), hdr.index("Metric Value")
+        vals = [float(r[mv].replace(",", "")) for r in rows[rows.index(hdr) + 1:]
+                if len(r) > mv and ("::" + kernel) in r[kn]]
+        return (sum(vals) / len(vals) / 1e3 if vals else None), os.path.basename(files[-1])
+    except Exception:
+        return None, None
+
+
 def measured_peak_gbs():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -413,7 +437,9 @@ def run_engine(args):
                 # share_of_step: of the time the step's kernels run (what an ncu launch
                 # list can be compared with); share_of_wall: of the instrumented pass,
                 # which also holds the event records and launch gaps
+                ncu_us, ncu_src = ncu_launch_list_us(name)
                 kernels[name] = {"avg_us": 1e3 * avg_ms, "launches": int(k_n[k]),
+                                 "ncu_launch_list_us": ncu_us, "ncu_launch_list": ncu_src,
                                  "share_of_step": k_ms[k] / busy_ms,
                                  "share_of_wall": k_ms[k] / ms_instrumented,
                                  "achieved_gbs": per_launch_bytes[k] / (avg_ms * 1e-3) / 1e9}

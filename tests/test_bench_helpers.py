@@ -20,6 +20,10 @@ def test_ncu_summary_helpers():
     assert issue["warp_instructions"] > 1e6
     assert bench.ncu_issue_counters("no_such_kernel") is None
     assert bench.ncu_traffic_bytes("no_such_kernel")[0] is None
+    us, lst = bench.ncu_launch_list_us("k_weights_scan")
+    assert lst.startswith("ncu_launches_r") and 1.0 < us < 100.0
+    assert 20.0 < bench.ncu_launch_list_us("k_run_compare")[0] < 200.0
+    assert bench.ncu_launch_list_us("no_such_kernel")[0] is None
     json.dumps({"issue": issue, "traffic": traffic})
     peak, kind = bench.measured_peak_gbs()
     assert peak > 1000 and kind in ("measured", "fallback")
